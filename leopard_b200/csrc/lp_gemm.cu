@@ -1,0 +1,333 @@
+// leopard_b200 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] · W[N,K]^T )          A, W bf16 row-major (K contiguous), fp32 accumulate in TMEM
+//
+// Replaces every dense contraction on Leopard's prefill path, which the reference delegates to cuBLAS /
+// TransformerEngine through torch:
+//   K1  patch-embed GEMM + bias + position embedding   (HF SiglipVisionEmbeddings; Megatron
+//       Pai-Megatron-Patch/megatron_patch/model/idefics2/idefics_vision_tower.py:118-150)
+//   K2/K4/K5 ViT qkv / out-proj / fc1(GELU-tanh) / fc2  (megatron_patch/model/llava/clip_encoder.py:51-72)
+//   K7  projector linear_1(GELU) / linear_2            (evaluations/models/llava_multiimg_siglip_anyres.py:179-192)
+//   K10/K13/K14/K15/K16 decoder qkv / o / gate‖up(SwiGLU) / down / lm_head
+//       (megatron_patch/model/llava/transformer.py:116-176,577-624)
+//
+// Structure (one CTA per SM, static round-robin tile scheduler):
+//   warp 0      TMA producer   : cp.async.bulk.tensor A/W k-blocks -> 128B-swizzled smem ring (STAGES deep)
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered
+//                                TMEM accumulator (2 x BN columns), tcgen05.commit frees smem / signals epilogue
+//   warps 2-5   epilogue       : tcgen05.ld accumulator rows -> bias / activation / residual -> 16-byte stores
+// Ragged M, N, K are handled by TMA zero fill on loads and predication on stores.
+#include "lp_common.cuh"
+#include "lp_host.h"
+#include "../../include/leopard_b200.h"
+
+namespace lp {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  void* C;
+  long long ldc;
+  int out_fp32;
+  const float* bias;
+  const bf16* residual;
+  long long ldr;
+  int res_row_mod;
+  int act;
+  int num_m_blk, num_n_blk, num_k_blk;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;  // +1024: manual 1 KiB alignment of the base
+};
+
+__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// applies bias/activation/residual to 32 accumulator columns of one row and stores them
+__device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& args, float* v, const float* bias_s, int row,
+                                                     int rrow, bool row_ok, int col0, int n_limit) {
+  if (args.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (args.act == LP_ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+  } else if (args.act == LP_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+  }
+  if (!row_ok) return;
+  if (args.residual) {
+    const bf16* rp = args.residual + (long long)rrow * args.ldr + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (col0 + g * 8 < n_limit) {
+        const uint4 u = *reinterpret_cast<const uint4*>(rp + g * 8);
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                     f3 = unpack_bf16x2(u.w);
+        float* w = v + g * 8;
+        w[0] += f0.x; w[1] += f0.y; w[2] += f1.x; w[3] += f1.y;
+        w[4] += f2.x; w[5] += f2.y; w[6] += f3.x; w[7] += f3.y;
+      }
+    }
+  }
+  if (args.out_fp32) {
+    float* cp = reinterpret_cast<float*>(args.C) + (long long)row * args.ldc + col0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (col0 + g * 4 < n_limit)
+        *reinterpret_cast<float4*>(cp + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+  } else {
+    bf16* cp = reinterpret_cast<bf16*>(args.C) + (long long)row * args.ldc + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (col0 + g * 8 < n_limit) {
+        const float* w = v + g * 8;
+        uint4 u;
+        u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
+        u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
+        *reinterpret_cast<uint4*>(cp + g * 8) = u;
+      }
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmArgs args) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_smem = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = args.num_m_blk * args.num_n_blk;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % args.num_m_blk, n_blk = tile / args.num_m_blk;
+        for (int kb = 0; kb < args.num_k_blk; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < args.num_k_blk; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(a_addr, 0, 1024);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + L::A_BYTES, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int lg = warp & 3;  // TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 64;
+    int as = 0;
+    uint32_t aphase = 0;
+    const bool swiglu = args.act == LP_ACT_SWIGLU;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % args.num_m_blk, n_blk = tile / args.num_m_blk;
+      const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+      float* bs = bias_smem + as * BN;
+      if (args.bias) {
+        for (int i = et; i < BN; i += 128) bs[i] = (n0 + i < args.N) ? args.bias[n0 + i] : 0.f;
+      }
+      epi_named_barrier();
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m0 + lg * 32 + lane;
+      const bool row_ok = row < args.M;
+      const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+      if (!swiglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= args.N) break;
+          uint32_t r[32];
+          LP_TMEM_LD_32(r, taddr0 + c * 32);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_store_chunk(args, v, bs + c * 32, row, rrow, row_ok, col0, args.N);
+        }
+      } else {
+        // columns are interleaved in 32-wide granules [gate | up | gate | up ...]; output has N/2 columns
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int col0 = n0 + c * 64;
+          if (col0 >= args.N) break;
+          uint32_t rg[32], ru[32];
+          LP_TMEM_LD_32(rg, taddr0 + c * 64);
+          LP_TMEM_LD_32(ru, taddr0 + c * 64 + 32);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+            if (args.bias) { g += bs[c * 64 + j]; u += bs[c * 64 + 32 + j]; }
+            v[j] = silu_f(g) * u;
+          }
+          GemmArgs a2 = args;
+          a2.bias = nullptr;
+          a2.act = LP_ACT_NONE;
+          epilogue_store_chunk(a2, v, nullptr, row, rrow, row_ok, col0 / 2, args.N / 2);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_bf16_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = args.num_m_blk * args.num_n_blk;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, args);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                            int N, int K, const float* bias, const void* residual, long long ldr, int res_row_mod,
+                            int act, int out_fp32, int block_n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(M > 0 && N > 0 && K > 0, "lp_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  LP_REQUIRE(N % 8 == 0, "lp_gemm_bf16: N=%d must be a multiple of 8", N);
+  LP_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "lp_gemm_bf16: lda/ldw must be multiples of 8 elements (TMA 16 B rule)");
+  LP_REQUIRE(ldc % (out_fp32 ? 4 : 8) == 0, "lp_gemm_bf16: ldc=%lld breaks 16 B store alignment", ldc);
+  LP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+             "lp_gemm_bf16: A/W/C must be 16-byte aligned");
+  LP_REQUIRE(residual == nullptr || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+             "lp_gemm_bf16: residual must be 16-byte aligned with ldr %% 8 == 0");
+  LP_REQUIRE(act >= LP_ACT_NONE && act <= LP_ACT_SWIGLU, "lp_gemm_bf16: bad act %d", act);
+  LP_REQUIRE(act != LP_ACT_SWIGLU || N % 64 == 0, "lp_gemm_bf16: SwiGLU needs N %% 64 == 0 (32-wide gate/up granules)");
+  if (block_n == 0) {
+    // wave-quantisation heuristic: pick the tile width with the smaller ceil(tiles / SMs) * tile cost
+    const int sms = sm_count();
+    const long long mb = (M + GEMM_BM - 1) / GEMM_BM;
+    const long long t256 = mb * ((N + 255) / 256), t128 = mb * ((N + 127) / 128);
+    const long long c256 = ((t256 + sms - 1) / sms) * 2, c128 = ((t128 + sms - 1) / sms) * 1;
+    block_n = (c128 < c256) ? 128 : 256;
+  }
+  LP_REQUIRE(block_n == 128 || block_n == 256, "lp_gemm_bf16: block_n must be 0, 128 or 256");
+
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32;
+  args.bias = bias;
+  args.residual = reinterpret_cast<const bf16*>(residual);
+  args.ldr = ldr; args.res_row_mod = res_row_mod;
+  args.act = act;
+  args.num_m_blk = (M + GEMM_BM - 1) / GEMM_BM;
+  args.num_n_blk = (N + block_n - 1) / block_n;
+  args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, (uint32_t)block_n);
+  if (rc) return rc;
+  if (block_n == 256) return launch_gemm<256, 4>(tmA, tmB, args, stream);
+  return launch_gemm<128, 6>(tmA, tmB, args, stream);
+}

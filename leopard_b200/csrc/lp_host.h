@@ -1,0 +1,39 @@
+// leopard_b200 — host-side helpers shared by the .cu translation units (not part of the public C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lp {
+
+// error plumbing: every entry point returns 0 or a negative lp_status and records a message
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define LP_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      lp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+      return -2; /* LP_ERR_CUDA */                                                            \
+    }                                                                                         \
+  } while (0)
+
+#define LP_REQUIRE(cond, ...)           \
+  do {                                  \
+    if (!(cond)) {                      \
+      lp::set_error(__VA_ARGS__);       \
+      return -1; /* LP_ERR_ARG */       \
+    }                                   \
+  } while (0)
+
+int sm_count();
+
+// 2-D / 3-D bf16 tensor maps with 128B swizzle (inner box = 64 elements = 128 B), zero OOB fill.
+// dims/strides are innermost-first; strides are in ELEMENTS for dims >= 1.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                      uint32_t box_inner, uint32_t box_outer);
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
+                      uint64_t ld2_elems, uint32_t b0, uint32_t b1, uint32_t b2);
+
+}  // namespace lp
