@@ -64,6 +64,47 @@ int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, i
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);
 
+/* out = LayerNorm(x) * gamma + beta, eps inside rsqrt; one row per CTA, fp32 statistics (two-pass).
+ *   SigLIP layer_norm1/2 and post_layernorm / ln_post (MP/model/idefics2/idefics_vision_tower.py:77-81,176).
+ * shuffle_side = 26 additionally applies Leopard's pixel_shuffle (EV/llava_multiimg_siglip_anyres.py:165-176 ==
+ *   MP/model/llava/vlm_model.py:456-466) through the store address: input row (b, h, w) of a side x side grid goes to
+ *   output row b*(side/2)^2 + (h/2)*(side/2) + (w/2), columns ((h%2)*2 + (w%2))*D .. +D, so `out` is [M/4, 4*D].
+ * x/out bf16, gamma/beta fp32 [D]; D % 8 == 0, D <= 4096. */
+int lp_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo, int M,
+                 int D, float eps, int shuffle_side, void* stream);
+
+/* out = x * rsqrt(mean(x^2) + eps) * gamma   (MLM/legacy/model/rms_norm.py:26-31; HF LlamaRMSNorm) */
+int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void* out, long long ldo, int M, int D, float eps,
+               void* stream);
+
+/* cos/sin[s, j] = cos/sin(pos[s] * inv_freq[j]), fp32 [S, half]
+ *   (MLM/core/models/common/embeddings/rotary_pos_embedding.py:125-157; inv_freq incl. llama3.1 rescale :48-83 is
+ *   computed by the host shim) */
+int lp_rope_table(const int* pos, const float* inv_freq, float* cos_out, float* sin_out, int S, int half, void* stream);
+
+/* in-place rotate-half RoPE on n_heads heads of width head_dim starting at column col0 of x[S, ld] (bf16):
+ *   t*cos + cat(-t2, t1)*sin  (rotary_pos_embedding.py:197-239) */
+int lp_rope_inplace(void* x, long long ld, int S, int col0, int n_heads, int head_dim, const float* cos_t,
+                    const float* sin_t, void* stream);
+
+/* Token embedding + image-feature merge for one sequence (B = 1).
+ *   Every id == image_id is an image slot that receives rows_per_slot consecutive rows of feats (slots consume feature
+ *   rows in order); every other id receives table[clamp(id, 0, vocab-1)].
+ *   rows_per_slot = 169, image_id = 128200: HF expand convention (_merge_input_ids_with_image_features as called at
+ *     EV/llava_multiimg_siglip_anyres.py:285-287; SURVEY.md App. A.1, B = 1 / no padding) -> S = L + 168 * slots.
+ *   rows_per_slot = 1, image_id = -200: Megatron scatter convention (MP/model/llava/vlm_model.py:516-533).
+ * plan: device int32 scratch [2*L + 2]; on completion plan[2*L] = number of slots, plan[2*L+1] = merged length S
+ *   (the host shim reads them back to raise the reference's count-mismatch error). */
+int lp_embed_merge(const long long* ids, int L, long long image_id, int rows_per_slot, const void* table, long long ldt,
+                   long long vocab, const void* feats, long long ldf, int n_feat_rows, void* out, long long ldo,
+                   int max_out_rows, int D, int* plan, void* stream);
+
+/* out[(n*G+py)*G+px, c*196 + ky*14 + kx] = pixels[n, c, py*14+ky, px*14+kx] (bf16), columns [C*196, ldo) zeroed:
+ *   A operand of the patch-embedding GEMM (conv1 k=14 s=14, MP/model/idefics2/idefics_vision_tower.py:57-64,118-122).
+ *   pixels: [N, C, H, W] fp32 (HF eval, EV/...anyres.py:403-405) or bf16 (Megatron). */
+int lp_im2col_patch14(const void* pixels, int pixels_fp32, void* out, long long ldo, int N, int C, int H, int W,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
