@@ -16,6 +16,7 @@
 #ifndef LEOPARD_B200_H
 #define LEOPARD_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -104,6 +105,100 @@ int lp_embed_merge(const long long* ids, int L, long long image_id, int rows_per
  *   pixels: [N, C, H, W] fp32 (HF eval, EV/...anyres.py:403-405) or bf16 (Megatron). */
 int lp_im2col_patch14(const void* pixels, int pixels_fp32, void* out, long long ldo, int N, int C, int H, int W,
                       void* stream);
+
+/* Standalone pixel_shuffle(x, scale_factor=2) (EV/llava_multiimg_siglip_anyres.py:165-176): x bf16 [M, D] with
+ * M = B*side*side rows -> out [M/4, 4*D].  (The fused path never materialises x: lp_layernorm's shuffle store.) */
+int lp_pixel_shuffle(const void* x, long long ldx, void* out, long long ldo, int M, int D, int side, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Model-level entry points (the layer loops).  Weight structs hold DEVICE pointers in the kernel-native layout that
+ * leopard_b200/native_weights.py produces from an HF- or Megatron-layout state dict:
+ *   bf16 matrices in nn.Linear layout [out, in]; biases / norm gains as fp32 vectors (bf16-rounded values).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct lp_vit_dims {
+  int layers, hidden, ffn, heads, head_dim, head_stride; /* 27, 1152, 4304, 16, 72, 80 */
+  int grid, tokens, patch_k, patch_k_pad;                /* 26, 676, 588, 592 */
+  float eps;                                             /* 1e-6 */
+} lp_vit_dims;
+
+typedef struct lp_vit_layer_weights {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void* qkv_w;  /* [3*heads*head_stride, hidden]: per head 72 real rows + 8 zero rows; q block, k block, v block */
+  const float* qkv_b; /* [3*heads*head_stride], zero in the pad rows */
+  const void* out_w;  /* [hidden, hidden] */
+  const float* out_b;
+  const void* fc1_w;  /* [ffn, hidden] */
+  const float* fc1_b;
+  const void* fc2_w;  /* [hidden, ffn] */
+  const float* fc2_b;
+} lp_vit_layer_weights;
+
+typedef struct lp_vit_weights {
+  const void* patch_w;  /* [hidden, patch_k_pad]: conv1 weight flattened (c, ky, kx), zero padded */
+  const float* patch_b; /* [hidden] */
+  const void* pos;      /* bf16 [tokens, hidden] learned position embedding */
+  const lp_vit_layer_weights* layers; /* HOST array of `layers` structs */
+  const float *post_g, *post_b;
+} lp_vit_weights;
+
+typedef struct lp_proj_weights {
+  const void* w1; /* [hidden_dec, 4*hidden_vit] */
+  const float* b1;
+  const void* w2; /* [hidden_dec, hidden_dec] */
+  const float* b2;
+  int act;        /* LP_ACT_GELU_ERF (HF eval) or LP_ACT_GELU_TANH (Megatron fused path) */
+} lp_proj_weights;
+
+typedef struct lp_dec_dims {
+  int layers, hidden, ffn, heads, kv_heads, head_dim; /* 32, 4096, 14336, 32, 8, 128 */
+  int vocab;                                          /* rows of lm_head (multiple of 8) */
+  float eps;                                          /* 1e-5 */
+} lp_dec_dims;
+
+typedef struct lp_dec_layer_weights {
+  const float* ln1_g;
+  const void* qkv_w;    /* [(heads + 2*kv_heads)*head_dim, hidden]: all q heads, then k heads, then v heads */
+  const void* o_w;      /* [hidden, hidden] */
+  const float* ln2_g;
+  const void* gateup_w; /* [2*ffn, hidden], 32-row granules interleaved gate/up (see lp_gemm_bf16, LP_ACT_SWIGLU) */
+  const void* down_w;   /* [hidden, ffn] */
+} lp_dec_layer_weights;
+
+typedef struct lp_dec_weights {
+  const lp_dec_layer_weights* layers; /* HOST array */
+  const float* final_g;
+  const void* lm_head;   /* [vocab, hidden] */
+  const float* inv_freq; /* device fp32 [head_dim/2] (llama3.1-rescaled where configured) */
+} lp_dec_weights;
+
+enum lp_logits_mode { LP_LOGITS_NONE = 0, LP_LOGITS_LAST = 1, LP_LOGITS_ALL = 2 };
+
+/* SigLIP tower over N crops: pixels [N,3,364,364] (fp32 or bf16) -> ln_post output.
+ *   shuffle = 0: out is last_hidden_state [N*676, 1152] (what `self.vision_tower(pixel_values).last_hidden_state`
+ *     returns, EV/llava_multiimg_siglip_anyres.py:268,273; MP/model/idefics2/idefics_vision_tower.py:104-178);
+ *   shuffle = 1: out is pixel_shuffle(last_hidden_state) [N*169, 4608] (EV/...anyres.py:165-176), written directly. */
+size_t lp_vit_workspace_bytes(const lp_vit_dims* dims, int N);
+int lp_vit_forward(const lp_vit_dims* dims, const lp_vit_weights* w, const void* pixels, int pixels_fp32, int N,
+                   void* out, long long ldo, int shuffle, void* workspace, size_t ws_bytes, void* stream);
+
+/* linear_2(act(linear_1(x))) on shuffled rows [rows, in_dim] -> [rows, hidden]
+ *   (myLlavaMultiModalProjector.forward EV/...anyres.py:187-192; Megatron MultimodalProjector
+ *    MLM/core/models/vision/multimodal_projector.py:50-57 via MP/model/llava/vlm_model.py:468-475) */
+size_t lp_project_workspace_bytes(int rows, int hidden);
+int lp_project(const lp_proj_weights* w, const void* shuffled, int rows, int in_dim, int hidden, void* out,
+               long long ldo, void* workspace, size_t ws_bytes, void* stream);
+
+/* Decoder prefill over n_seqs packed sequences (rows cu_seqlens_host[s] .. cu_seqlens_host[s+1]-1 of x).
+ *   x: bf16 [R, hidden] merged embeddings; used as the residual stream and overwritten with the last layer's output.
+ *   pos_ids: device int32 [R].  kv_cache: NULL or bf16 [layers][2][R][kv_heads*head_dim] (K after RoPE, then V).
+ *   logits: LP_LOGITS_LAST -> [n_seqs, vocab] (final norm + lm_head on each sequence's last row only);
+ *           LP_LOGITS_ALL  -> [R, vocab] (what the reference materialises, EV/...anyres.py:333); fp32 or bf16.
+ *   Replaces HF LlamaForCausalLM.forward (EV/...anyres.py:322-333) / Megatron ParallelTransformer.forward +
+ *   parallel_lm_logits (MP/model/llava/transformer.py:1747-1860, MP/model/llava/vlm_model.py:32-60). */
+size_t lp_decoder_workspace_bytes(const lp_dec_dims* dims, int total_rows, int n_seqs);
+int lp_decoder_prefill(const lp_dec_dims* dims, const lp_dec_weights* w, void* x, const int* pos_ids,
+                       const int* cu_seqlens_host, int n_seqs, void* kv_cache, void* logits, long long ld_logits,
+                       int logits_mode, int logits_fp32, void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

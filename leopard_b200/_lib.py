@@ -11,34 +11,76 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "lib" / "libleopard_b200.so"
 
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SWIGLU = 0, 1, 2, 3
-MERGE_HF_EXPAND, MERGE_MEGATRON_SCATTER = 0, 1
+LOGITS_NONE, LOGITS_LAST, LOGITS_ALL = 0, 1, 2
 
 
 class NativeError(RuntimeError):
     pass
 
 
-_lib = None
+_vp, _ll, _i, _f, _sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
 
-_vp, _ll, _i, _fp = C.c_void_p, C.c_longlong, C.c_int, C.c_void_p
 
-# name -> argtypes (restype is int unless listed in _RESTYPES)
+class VitDims(C.Structure):
+    _fields_ = [(n, _i) for n in ("layers", "hidden", "ffn", "heads", "head_dim", "head_stride", "grid", "tokens",
+                                  "patch_k", "patch_k_pad")] + [("eps", _f)]
+
+
+class VitLayerWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_w", "qkv_b", "out_w", "out_b", "fc1_w",
+                                   "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [("patch_w", _vp), ("patch_b", _vp), ("pos", _vp), ("layers", C.POINTER(VitLayerWeights)),
+                ("post_g", _vp), ("post_b", _vp)]
+
+
+class ProjWeights(C.Structure):
+    _fields_ = [("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("act", _i)]
+
+
+class DecDims(C.Structure):
+    _fields_ = [(n, _i) for n in ("layers", "hidden", "ffn", "heads", "kv_heads", "head_dim", "vocab")] + [("eps", _f)]
+
+
+class DecLayerWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in ("ln1_g", "qkv_w", "o_w", "ln2_g", "gateup_w", "down_w")]
+
+
+class DecWeights(C.Structure):
+    _fields_ = [("layers", C.POINTER(DecLayerWeights)), ("final_g", _vp), ("lm_head", _vp), ("inv_freq", _vp)]
+
+
+_P = C.POINTER
+
+# name -> (restype, argtypes); must list EVERY symbol include/leopard_b200.h declares (tests/test_abi.py checks)
 _SIGS = {
-    "lp_last_error": [],
-    "lp_abi_version": [],
-    "lp_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
+    "lp_last_error": (C.c_char_p, []),
+    "lp_abi_version": (_i, []),
+    "lp_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "lp_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _i, _vp]),
+    "lp_layernorm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
+    "lp_rmsnorm": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _vp]),
+    "lp_rope_table": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "lp_rope_inplace": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lp_embed_merge": (_i, [_vp, _i, _ll, _i, _vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp]),
+    "lp_im2col_patch14": (_i, [_vp, _i, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "lp_pixel_shuffle": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "lp_vit_workspace_bytes": (_sz, [_P(VitDims), _i]),
+    "lp_vit_forward": (_i, [_P(VitDims), _P(VitWeights), _vp, _i, _i, _vp, _ll, _i, _vp, _sz, _vp]),
+    "lp_project_workspace_bytes": (_sz, [_i, _i]),
+    "lp_project": (_i, [_P(ProjWeights), _vp, _i, _i, _i, _vp, _ll, _vp, _sz, _vp]),
+    "lp_decoder_workspace_bytes": (_sz, [_P(DecDims), _i, _i]),
+    "lp_decoder_prefill": (_i, [_P(DecDims), _P(DecWeights), _vp, _vp, _P(_i), _i, _vp, _vp, _ll, _i, _i, _vp, _sz,
+                                _vp]),
 }
-_RESTYPES = {"lp_last_error": C.c_char_p}
+
+_lib = None
 
 
 def declared_symbols():
     return sorted(_SIGS)
-
-
-def register(name, argtypes, restype=None):
-    _SIGS[name] = argtypes
-    if restype is not None:
-        _RESTYPES[name] = restype
 
 
 def lib():
@@ -53,10 +95,13 @@ def lib():
             L = C.CDLL(str(LIB_PATH))
         except OSError as e:  # pragma: no cover
             raise NativeError(f"cannot load {LIB_PATH}: {e}") from e
-        for name, argtypes in _SIGS.items():
-            fn = getattr(L, name)
+        for name, (restype, argtypes) in _SIGS.items():
+            try:
+                fn = getattr(L, name)
+            except AttributeError as e:
+                raise NativeError(f"{LIB_PATH} does not export {name}: rebuild the library") from e
             fn.argtypes = argtypes
-            fn.restype = _RESTYPES.get(name, C.c_int)
+            fn.restype = restype
         _lib = L
     return _lib
 
@@ -75,5 +120,3 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-register("lp_attention_fwd", [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.c_float, _vp, _ll, _i, _vp])

@@ -235,6 +235,19 @@ __global__ void im2col_patch14_kernel(const T* __restrict__ pix, bf16* __restric
   }
 }
 
+// ---- standalone pixel shuffle (the fused path is lp_layernorm's shuffle store) ----------------------------------
+// out[b, oh*half + ow, (dy*2+dx)*D + e] = x[b, (2oh+dy)*side + 2ow+dx, e]; one CTA per input row
+__global__ void __launch_bounds__(128)
+pixel_shuffle_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo, int side, int D) {
+  const int row = blockIdx.x;
+  const int per = side * side, half = side >> 1;
+  const int b = row / per, t = row % per, h = t / side, w = t % side;
+  const long long orow = (long long)b * (half * half) + (h >> 1) * half + (w >> 1);
+  const uint4* sp = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  uint4* dp = reinterpret_cast<uint4*>(out + orow * ldo + (((h & 1) << 1) | (w & 1)) * D);
+  for (int c = threadIdx.x; c < (D >> 3); c += blockDim.x) dp[c] = sp[c];
+}
+
 }  // namespace lp
 
 using namespace lp;
@@ -325,6 +338,17 @@ extern "C" int lp_im2col_patch14(const void* pixels, int pixels_fp32, void* out,
   else
     im2col_patch14_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(pixels),
                                                           reinterpret_cast<bf16*>(out), ldo, N, C, H, W);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lp_pixel_shuffle(const void* x, long long ldx, void* out, long long ldo, int M, int D, int side,
+                                void* stream) {
+  LP_REQUIRE(M > 0 && D % 8 == 0 && side > 0 && side % 2 == 0 && M % (side * side) == 0,
+             "lp_pixel_shuffle: bad M=%d D=%d side=%d", M, D, side);
+  LP_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && aligned16(x) && aligned16(out), "lp_pixel_shuffle: alignment");
+  pixel_shuffle_kernel<<<M, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, side, D);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,202 @@
+// leopard_b200 — model-level entry points: the layer loops of the prefill path, enqueued on one stream.
+//
+//   lp_vit_forward      SigLIP-SO400M/14-364 tower over N crops, ln_post fused with the pixel-shuffle store
+//                       (HF `self.vision_tower(pixel_values).last_hidden_state`, evaluations/models/
+//                        llava_multiimg_siglip_anyres.py:268,273; Megatron Idefics2ViTModel.forward,
+//                        Pai-Megatron-Patch/megatron_patch/model/idefics2/idefics_vision_tower.py:104-178)
+//   lp_project          the 2-layer MLP projector on the already-shuffled rows
+//                       (myLlavaMultiModalProjector.forward, EV/...anyres.py:187-192; vlm_model.py:468-475)
+//   lp_decoder_prefill  Llama-3.1-8B / Mistral-7B stack + final norm + lm_head over packed sequences
+//                       (HF `self.language_model(...)` EV/...anyres.py:322-333; Megatron ParallelTransformer.forward,
+//                        megatron_patch/model/llava/transformer.py:1747-1860 and parallel_lm_logits vlm_model.py:32-60)
+// No allocation, no host synchronisation: scratch comes from the caller's workspace.
+#include "lp_host.h"
+#include "../../include/leopard_b200.h"
+#include <cuda_bf16.h>
+
+using namespace lp;
+
+namespace {
+struct Carver {
+  uint8_t* p;
+  size_t used = 0, cap;
+  Carver(void* base, size_t bytes) : p(reinterpret_cast<uint8_t*>(base)), cap(bytes) {}
+  void* take(size_t bytes) {
+    size_t off = (used + 255) & ~size_t(255);
+    used = off + bytes;
+    return p ? p + off : nullptr;
+  }
+};
+inline size_t bf(size_t n) { return n * 2; }
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ ViT
+static size_t vit_ws(const lp_vit_dims* d, int N, Carver* c, void** A, void** x, void** h, void** qkv, void** att,
+                     void** mlp) {
+  const size_t rows = (size_t)N * d->tokens;
+  Carver tmp(nullptr, 0);
+  Carver& cv = c ? *c : tmp;
+  void* a = cv.take(bf(rows * d->patch_k_pad));
+  void* xx = cv.take(bf(rows * d->hidden));
+  void* hh = cv.take(bf(rows * d->hidden));
+  void* q = cv.take(bf(rows * 3 * d->heads * d->head_stride));
+  void* at = cv.take(bf(rows * d->hidden));
+  void* m = cv.take(bf(rows * d->ffn));
+  if (A) { *A = a; *x = xx; *h = hh; *qkv = q; *att = at; *mlp = m; }
+  return cv.used + 256;
+}
+
+extern "C" size_t lp_vit_workspace_bytes(const lp_vit_dims* d, int N) {
+  return vit_ws(d, N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int lp_vit_forward(const lp_vit_dims* d, const lp_vit_weights* w, const void* pixels, int pixels_fp32, int N,
+                              void* out, long long ldo, int shuffle, void* workspace, size_t ws_bytes, void* stream) {
+  LP_REQUIRE(d && w && pixels && out && N > 0, "lp_vit_forward: null argument or N=%d", N);
+  LP_REQUIRE(d->hidden == d->heads * d->head_dim && d->head_dim == 72 && d->head_stride == 80,
+             "lp_vit_forward: SigLIP-SO400M head geometry expected (16 x 72, stride 80)");
+  LP_REQUIRE(d->grid * d->grid == d->tokens && d->patch_k_pad % 8 == 0 && d->patch_k_pad >= d->patch_k,
+             "lp_vit_forward: bad patch geometry");
+  LP_REQUIRE(ws_bytes >= lp_vit_workspace_bytes(d, N), "lp_vit_forward: workspace too small (%zu < %zu)", ws_bytes,
+             lp_vit_workspace_bytes(d, N));
+  Carver cv(workspace, ws_bytes);
+  void *A, *x, *h, *qkv, *att, *mlp;
+  vit_ws(d, N, &cv, &A, &x, &h, &qkv, &att, &mlp);
+  const int rows = N * d->tokens;
+  const int img = d->grid * 14;
+  const int qkv_w = 3 * d->heads * d->head_stride;
+  int rc;
+#define LP_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
+  LP_TRY(lp_im2col_patch14(pixels, pixels_fp32, A, d->patch_k_pad, N, 3, img, img, stream));
+  // patch embedding GEMM + bias + learned position embedding (row % tokens)
+  LP_TRY(lp_gemm_bf16(A, d->patch_k_pad, w->patch_w, d->patch_k_pad, x, d->hidden, rows, d->hidden, d->patch_k_pad,
+                      w->patch_b, w->pos, d->hidden, d->tokens, LP_ACT_NONE, 0, 0, stream));
+  for (int l = 0; l < d->layers; ++l) {
+    const lp_vit_layer_weights* L = &w->layers[l];
+    LP_TRY(lp_layernorm(x, d->hidden, L->ln1_g, L->ln1_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
+    LP_TRY(lp_gemm_bf16(h, d->hidden, L->qkv_w, d->hidden, qkv, qkv_w, rows, qkv_w, d->hidden, L->qkv_b, nullptr, 0, 0,
+                        LP_ACT_NONE, 0, 0, stream));
+    LP_TRY(lp_attention_fwd(qkv, qkv_w, N, d->tokens, d->heads, d->heads, d->head_dim, d->head_stride, 0,
+                            d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0,
+                            1.0f / sqrtf((float)d->head_dim), att, d->hidden, 1, stream));
+    LP_TRY(lp_gemm_bf16(att, d->hidden, L->out_w, d->hidden, x, d->hidden, rows, d->hidden, d->hidden, L->out_b, x,
+                        d->hidden, 0, LP_ACT_NONE, 0, 0, stream));
+    LP_TRY(lp_layernorm(x, d->hidden, L->ln2_g, L->ln2_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
+    LP_TRY(lp_gemm_bf16(h, d->hidden, L->fc1_w, d->hidden, mlp, d->ffn, rows, d->ffn, d->hidden, L->fc1_b, nullptr, 0,
+                        0, LP_ACT_GELU_TANH, 0, 0, stream));
+    LP_TRY(lp_gemm_bf16(mlp, d->ffn, L->fc2_w, d->ffn, x, d->hidden, rows, d->hidden, d->ffn, L->fc2_b, x, d->hidden,
+                        0, LP_ACT_NONE, 0, 0, stream));
+  }
+  // ln_post; shuffle != 0 writes the pixel-shuffled [N*tokens/4, 4*hidden] layout directly
+  LP_TRY(lp_layernorm(x, d->hidden, w->post_g, w->post_b, out, ldo, rows, d->hidden, d->eps, shuffle ? d->grid : 0,
+                      stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ projector
+extern "C" size_t lp_project_workspace_bytes(int rows, int hidden) { return bf((size_t)rows * hidden) + 512; }
+
+extern "C" int lp_project(const lp_proj_weights* w, const void* shuffled, int rows, int in_dim, int hidden, void* out,
+                          long long ldo, void* workspace, size_t ws_bytes, void* stream) {
+  LP_REQUIRE(w && shuffled && out && rows > 0, "lp_project: null argument");
+  LP_REQUIRE(ws_bytes >= lp_project_workspace_bytes(rows, hidden), "lp_project: workspace too small");
+  Carver cv(workspace, ws_bytes);
+  void* mid = cv.take(bf((size_t)rows * hidden));
+  int rc;
+  LP_TRY(lp_gemm_bf16(shuffled, in_dim, w->w1, in_dim, mid, hidden, rows, hidden, in_dim, w->b1, nullptr, 0, 0, w->act,
+                      0, 0, stream));
+  LP_TRY(lp_gemm_bf16(mid, hidden, w->w2, hidden, out, ldo, rows, hidden, hidden, w->b2, nullptr, 0, 0, LP_ACT_NONE, 0,
+                      0, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+static size_t dec_ws(const lp_dec_dims* d, int R, int n_seq, Carver* c, void** h, void** qkv, void** att, void** act,
+                     float** cs, float** sn, void** last) {
+  Carver tmp(nullptr, 0);
+  Carver& cv = c ? *c : tmp;
+  const int qkv_w = (d->heads + 2 * d->kv_heads) * d->head_dim;
+  void* hh = cv.take(bf((size_t)R * d->hidden));
+  void* q = cv.take(bf((size_t)R * qkv_w));
+  void* at = cv.take(bf((size_t)R * d->hidden));
+  void* ac = cv.take(bf((size_t)R * d->ffn));
+  float* c1 = (float*)cv.take((size_t)R * (d->head_dim / 2) * 4);
+  float* s1 = (float*)cv.take((size_t)R * (d->head_dim / 2) * 4);
+  void* la = cv.take(bf((size_t)n_seq * d->hidden));
+  if (h) { *h = hh; *qkv = q; *att = at; *act = ac; *cs = c1; *sn = s1; *last = la; }
+  return cv.used + 256;
+}
+
+extern "C" size_t lp_decoder_workspace_bytes(const lp_dec_dims* d, int total_rows, int n_seqs) {
+  return dec_ws(d, total_rows, n_seqs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w, void* x, const int* pos_ids,
+                                  const int* cu_seqlens_host, int n_seqs, void* kv_cache, void* logits,
+                                  long long ld_logits, int logits_mode, int logits_fp32, void* workspace,
+                                  size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(d && w && x && pos_ids && cu_seqlens_host && n_seqs > 0, "lp_decoder_prefill: null argument");
+  LP_REQUIRE(d->head_dim == 128 && d->heads % d->kv_heads == 0, "lp_decoder_prefill: head_dim must be 128");
+  const int R = cu_seqlens_host[n_seqs];
+  LP_REQUIRE(R > 0 && cu_seqlens_host[0] == 0, "lp_decoder_prefill: bad cu_seqlens");
+  LP_REQUIRE(ws_bytes >= lp_decoder_workspace_bytes(d, R, n_seqs), "lp_decoder_prefill: workspace too small (%zu < %zu)",
+             ws_bytes, lp_decoder_workspace_bytes(d, R, n_seqs));
+  LP_REQUIRE(logits_mode == LP_LOGITS_NONE || logits != nullptr, "lp_decoder_prefill: logits buffer missing");
+  Carver cv(workspace, ws_bytes);
+  void *h, *qkv, *att, *act, *last;
+  float *cs, *sn;
+  dec_ws(d, R, n_seqs, &cv, &h, &qkv, &att, &act, &cs, &sn, &last);
+  const int H = d->hidden, hd = d->head_dim;
+  const int q_w = d->heads * hd, kv_w = d->kv_heads * hd, qkv_w = q_w + 2 * kv_w;
+  const float scale = 1.0f / sqrtf((float)hd);
+  bool uniform = true;
+  for (int s = 1; s < n_seqs; ++s)
+    uniform &= (cu_seqlens_host[s + 1] - cu_seqlens_host[s]) == (cu_seqlens_host[1] - cu_seqlens_host[0]);
+  int rc;
+  LP_TRY(lp_rope_table(pos_ids, w->inv_freq, cs, sn, R, hd / 2, stream));
+  for (int l = 0; l < d->layers; ++l) {
+    const lp_dec_layer_weights* L = &w->layers[l];
+    LP_TRY(lp_rmsnorm(x, H, L->ln1_g, h, H, R, H, d->eps, stream));
+    LP_TRY(lp_gemm_bf16(h, H, L->qkv_w, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE, 0, 0, stream));
+    // q heads and k heads are contiguous column-wise: one RoPE launch covers heads + kv_heads
+    LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
+    if (uniform) {
+      LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, R / n_seqs, d->heads, d->kv_heads, hd, hd, 0, q_w, q_w + kv_w, 1,
+                              scale, att, H, 1, stream));
+    } else {
+      for (int s = 0; s < n_seqs; ++s) {
+        const int r0 = cu_seqlens_host[s], T = cu_seqlens_host[s + 1] - r0;
+        LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->kv_heads, hd,
+                                hd, 0, q_w, q_w + kv_w, 1, scale, (__nv_bfloat16*)att + (size_t)r0 * H, H, 1, stream));
+      }
+    }
+    if (kv_cache) {  // [layers][2][R][kv_w]: K (post-RoPE) then V
+      __nv_bfloat16* kc = (__nv_bfloat16*)kv_cache + (size_t)l * 2 * R * kv_w;
+      LP_CHECK_CUDA(cudaMemcpy2DAsync(kc, bf(kv_w), (const __nv_bfloat16*)qkv + q_w, bf(qkv_w), bf(kv_w), R,
+                                      cudaMemcpyDeviceToDevice, stream));
+      LP_CHECK_CUDA(cudaMemcpy2DAsync(kc + (size_t)R * kv_w, bf(kv_w), (const __nv_bfloat16*)qkv + q_w + kv_w,
+                                      bf(qkv_w), bf(kv_w), R, cudaMemcpyDeviceToDevice, stream));
+    }
+    LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, R, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 0, stream));
+    LP_TRY(lp_rmsnorm(x, H, L->ln2_g, h, H, R, H, d->eps, stream));
+    LP_TRY(lp_gemm_bf16(h, H, L->gateup_w, H, act, d->ffn, R, 2 * d->ffn, H, nullptr, nullptr, 0, 0, LP_ACT_SWIGLU, 0,
+                        0, stream));
+    LP_TRY(lp_gemm_bf16(act, d->ffn, L->down_w, d->ffn, x, H, R, H, d->ffn, nullptr, x, H, 0, LP_ACT_NONE, 0, 0,
+                        stream));
+  }
+  if (logits_mode == LP_LOGITS_ALL) {
+    LP_TRY(lp_rmsnorm(x, H, w->final_g, h, H, R, H, d->eps, stream));
+    LP_TRY(lp_gemm_bf16(h, H, w->lm_head, H, logits, ld_logits, R, d->vocab, H, nullptr, nullptr, 0, 0, LP_ACT_NONE,
+                        logits_fp32, 0, stream));
+  } else if (logits_mode == LP_LOGITS_LAST) {
+    for (int s = 0; s < n_seqs; ++s) {
+      const int r = cu_seqlens_host[s + 1] - 1;
+      LP_TRY(lp_rmsnorm((const __nv_bfloat16*)x + (size_t)r * H, H, w->final_g, (__nv_bfloat16*)last + (size_t)s * H, H,
+                        1, H, d->eps, stream));
+    }
+    LP_TRY(lp_gemm_bf16(last, H, w->lm_head, H, logits, ld_logits, n_seqs, d->vocab, H, nullptr, nullptr, 0, 0,
+                        LP_ACT_NONE, logits_fp32, 0, stream));
+  }
+  return 0;
+}

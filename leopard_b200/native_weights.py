@@ -1,0 +1,287 @@
+"""Checkpoint -> kernel-native device layout (what the lp_*_weights structs of include/leopard_b200.h point at).
+
+Accepts the two layouts the reference produces:
+  * HF (transformers <= 4.4x LLaVA keys, separate q/k/v and gate/up)  — `load_hf`
+  * Megatron (`language_model/{embedding,vision_tower,mm_projector,encoder,output_layer}`, fused + interleaved)
+    — `megatron_to_hf` first restores HF tensors exactly as the reference converter does
+      (Pai-Megatron-Patch/toolkits/model_checkpoints_convertor/llava/hf2megatron_llava.py:1100-1460 and the layer code
+       megatron_patch/model/llava/transformer.py:713-738 for the GQA group interleave).
+Re-layout is pure data movement (cat / pad / permute on the device); no arithmetic on the path happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict
+
+import torch
+
+from . import _lib
+from .config import LeopardConfig
+
+V = "vision_tower.vision_model."
+P = "multi_modal_projector."
+LM = "language_model.model."
+
+HEAD_STRIDE = 80       # SigLIP head_dim 72 zero-padded to 5 x 16 (UMMA K granularity)
+PATCH_K_PAD = 592      # 588 -> next multiple of 8 elements (TMA needs 16-byte row strides)
+
+
+def rope_inv_freq(dec) -> torch.Tensor:
+    """Host-side RoPE inverse frequencies incl. the llama3.1 rescale
+    (megatron/core/models/common/embeddings/rotary_pos_embedding.py:48-83,112-123)."""
+    d = dec.head_dim
+    inv = 1.0 / (dec.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    rs = dec.rope_scaling
+    if rs is None:
+        return inv
+    wavelen = 2 * math.pi / inv
+    low_wl = rs.original_max_position / rs.low_freq_factor
+    high_wl = rs.original_max_position / rs.high_freq_factor
+    smooth = (rs.original_max_position / wavelen - rs.low_freq_factor) / (rs.high_freq_factor - rs.low_freq_factor)
+    mid = (1 - smooth) * inv / rs.factor + smooth * inv
+    out = torch.where(wavelen > low_wl, inv / rs.factor, torch.where(wavelen < high_wl, inv, mid))
+    return out.float()
+
+
+class NativeWeights:
+    """Device tensors in kernel layout + the ctypes structs handed to lp_vit_forward / lp_project / lp_decoder_prefill."""
+
+    def __init__(self, cfg: LeopardConfig, device):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self._keep = []          # every device tensor referenced by a struct
+        self.embed = None        # [vocab, hidden] bf16
+        self.vocab_padded = (cfg.dec.vocab + 7) // 8 * 8
+        v, d = cfg.vit, cfg.dec
+        self.vit_dims = _lib.VitDims(v.layers, v.hidden, v.ffn, v.heads, v.head_dim, HEAD_STRIDE, v.grid, v.tokens,
+                                     v.patch_k, PATCH_K_PAD, v.eps)
+        self.dec_dims = _lib.DecDims(d.layers, d.hidden, d.ffn, d.heads, d.kv_heads, d.head_dim, self.vocab_padded,
+                                     d.eps)
+        self.vit_layers = (_lib.VitLayerWeights * max(v.layers, 1))()
+        self.dec_layers = (_lib.DecLayerWeights * max(d.layers, 1))()
+        self.vit = _lib.VitWeights()
+        self.proj = _lib.ProjWeights()
+        self.dec = _lib.DecWeights()
+
+    # -- helpers
+    def _bf(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _f32(self, t: torch.Tensor) -> torch.Tensor:
+        # vectors are kept as fp32 holding the checkpoint's (bf16-rounded) values
+        t = t.to(device=self.device).to(torch.bfloat16).float().contiguous()
+        self._keep.append(t)
+        return t
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr())
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._keep)
+
+
+def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> NativeWeights:
+    """Build NativeWeights from HF-layout tensors; `get(name)` returns one tensor (any float dtype, any device)."""
+    nw = NativeWeights(cfg, device)
+    v, d = cfg.vit, cfg.dec
+    dev = nw.device
+
+    # ---- SigLIP tower
+    pw = get(V + "embeddings.patch_embedding.weight").to(dev).reshape(v.hidden, v.patch_k)
+    pw = torch.nn.functional.pad(pw, (0, PATCH_K_PAD - v.patch_k))
+    nw.vit.patch_w = nw._p(nw._bf(pw))
+    nw.vit.patch_b = nw._p(nw._f32(get(V + "embeddings.patch_embedding.bias")))
+    nw.vit.pos = nw._p(nw._bf(get(V + "embeddings.position_embedding.weight")))
+    pad_rows = HEAD_STRIDE - v.head_dim
+
+    def pad_heads(w):  # [heads*72, ...] -> [heads*80, ...] with zero rows after each head
+        w = w.to(dev)
+        shp = w.shape
+        w = w.reshape(v.heads, v.head_dim, -1)
+        w = torch.nn.functional.pad(w, (0, 0, 0, pad_rows))
+        return w.reshape(v.heads * HEAD_STRIDE, *shp[1:])
+
+    for i in range(v.layers):
+        b = f"{V}encoder.layers.{i}."
+        L = nw.vit_layers[i]
+        L.ln1_g = nw._p(nw._f32(get(b + "layer_norm1.weight")))
+        L.ln1_b = nw._p(nw._f32(get(b + "layer_norm1.bias")))
+        L.ln2_g = nw._p(nw._f32(get(b + "layer_norm2.weight")))
+        L.ln2_b = nw._p(nw._f32(get(b + "layer_norm2.bias")))
+        qkv_w = torch.cat([pad_heads(get(b + f"self_attn.{n}_proj.weight")) for n in "qkv"], 0)
+        qkv_b = torch.cat([pad_heads(get(b + f"self_attn.{n}_proj.bias")) for n in "qkv"], 0)
+        L.qkv_w = nw._p(nw._bf(qkv_w))
+        L.qkv_b = nw._p(nw._f32(qkv_b))
+        L.out_w = nw._p(nw._bf(get(b + "self_attn.out_proj.weight")))
+        L.out_b = nw._p(nw._f32(get(b + "self_attn.out_proj.bias")))
+        L.fc1_w = nw._p(nw._bf(get(b + "mlp.fc1.weight")))
+        L.fc1_b = nw._p(nw._f32(get(b + "mlp.fc1.bias")))
+        L.fc2_w = nw._p(nw._bf(get(b + "mlp.fc2.weight")))
+        L.fc2_b = nw._p(nw._f32(get(b + "mlp.fc2.bias")))
+    nw.vit.layers = C.cast(nw.vit_layers, C.POINTER(_lib.VitLayerWeights))
+    nw.vit.post_g = nw._p(nw._f32(get(V + "post_layernorm.weight")))
+    nw.vit.post_b = nw._p(nw._f32(get(V + "post_layernorm.bias")))
+
+    # ---- projector
+    nw.proj.w1 = nw._p(nw._bf(get(P + "linear_1.weight")))
+    nw.proj.b1 = nw._p(nw._f32(get(P + "linear_1.bias")))
+    nw.proj.w2 = nw._p(nw._bf(get(P + "linear_2.weight")))
+    nw.proj.b2 = nw._p(nw._f32(get(P + "linear_2.bias")))
+    nw.proj.act = _lib.ACT_GELU_ERF if cfg.projector_act == "gelu" else _lib.ACT_GELU_TANH
+
+    # ---- decoder
+    nw.embed = nw._bf(get(LM + "embed_tokens.weight"))
+    for i in range(d.layers):
+        b = f"{LM}layers.{i}."
+        L = nw.dec_layers[i]
+        L.ln1_g = nw._p(nw._f32(get(b + "input_layernorm.weight")))
+        L.ln2_g = nw._p(nw._f32(get(b + "post_attention_layernorm.weight")))
+        qkv = torch.cat([get(b + f"self_attn.{n}_proj.weight").to(dev) for n in "qkv"], 0)
+        L.qkv_w = nw._p(nw._bf(qkv))
+        del qkv
+        L.o_w = nw._p(nw._bf(get(b + "self_attn.o_proj.weight")))
+        g = get(b + "mlp.gate_proj.weight").to(dev).reshape(d.ffn // 32, 1, 32, d.hidden)
+        u = get(b + "mlp.up_proj.weight").to(dev).reshape(d.ffn // 32, 1, 32, d.hidden)
+        L.gateup_w = nw._p(nw._bf(torch.cat([g, u], 1).reshape(2 * d.ffn, d.hidden)))
+        del g, u
+        L.down_w = nw._p(nw._bf(get(b + "mlp.down_proj.weight")))
+    nw.dec.layers = C.cast(nw.dec_layers, C.POINTER(_lib.DecLayerWeights))
+    nw.dec.final_g = nw._p(nw._f32(get(LM + "norm.weight")))
+    head = get("language_model.lm_head.weight").to(dev)
+    if nw.vocab_padded != d.vocab:
+        head = torch.nn.functional.pad(head, (0, 0, 0, nw.vocab_padded - d.vocab))
+    nw.dec.lm_head = nw._p(nw._bf(head))
+    inv = rope_inv_freq(d).to(dev).contiguous()
+    nw._keep.append(inv)
+    nw.dec.inv_freq = nw._p(inv)
+    return nw
+
+
+def random_native(cfg: LeopardConfig, device="cuda", seed: int = 1234) -> NativeWeights:
+    """Benchmark-only initialisation: same distributions as weights.synth_tensor but drawn ON the device (fast);
+    values differ from the CPU-seeded checkpoint, so this is for throughput runs, never for parity."""
+    from .weights import tensor_specs
+    g = torch.Generator(device=device).manual_seed(seed)
+    specs = {n: (s, k) for n, s, k in tensor_specs(cfg)}
+
+    def get(name):
+        shape, kind = specs[name]
+        if kind in ("linear", "conv"):
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            return (torch.randn(shape, device=device, generator=g) * fan_in ** -0.5).to(torch.bfloat16)
+        if kind == "norm":
+            return (1.0 + torch.randn(shape, device=device, generator=g) * 0.02).to(torch.bfloat16)
+        scale = 0.05 if kind == "embed" else 0.02
+        return (torch.randn(shape, device=device, generator=g) * scale).to(torch.bfloat16)
+
+    return load_hf(cfg, get, device)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Megatron checkpoint layout -> HF layout
+# ----------------------------------------------------------------------------------------------------------------
+def megatron_to_hf(cfg: LeopardConfig, lm: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """`lm` = flattened `state['model']['language_model']` of a TP=1 Megatron checkpoint with keys such as
+    'encoder.layers.0.self_attention.query_key_value.weight'.  Returns HF-named tensors."""
+    v, d = cfg.vit, cfg.dec
+    out: Dict[str, torch.Tensor] = {}
+    out[LM + "embed_tokens.weight"] = lm["embedding.word_embeddings.weight"][: d.vocab]
+    out["language_model.lm_head.weight"] = lm["output_layer.weight"][: d.vocab]
+    fin = "encoder.final_norm.weight" if "encoder.final_norm.weight" in lm else "encoder.final_layernorm.weight"
+    out[LM + "norm.weight"] = lm[fin]
+    rep = d.heads // d.kv_heads
+    hd = d.head_dim
+    for i in range(d.layers):
+        s, t = f"encoder.layers.{i}.", f"{LM}layers.{i}."
+        out[t + "input_layernorm.weight"] = lm[s + "input_norm.weight"]
+        out[t + "post_attention_layernorm.weight"] = lm[s + "post_attention_norm.weight"]
+        # fused rows per kv group: [rep q heads | k | v] x kv_heads (megatron_patch/model/llava/transformer.py:713-738)
+        qkv = lm[s + "self_attention.query_key_value.weight"].reshape(d.kv_heads, (rep + 2) * hd, d.hidden)
+        out[t + "self_attn.q_proj.weight"] = qkv[:, : rep * hd].reshape(d.heads * hd, d.hidden)
+        out[t + "self_attn.k_proj.weight"] = qkv[:, rep * hd: (rep + 1) * hd].reshape(d.kv_heads * hd, d.hidden)
+        out[t + "self_attn.v_proj.weight"] = qkv[:, (rep + 1) * hd:].reshape(d.kv_heads * hd, d.hidden)
+        out[t + "self_attn.o_proj.weight"] = lm[s + "self_attention.dense.weight"]
+        h4 = lm[s + "mlp.dense_h_to_4h.weight"]  # [gate ; up] (hf2megatron_llava.py:1287-1295)
+        out[t + "mlp.gate_proj.weight"], out[t + "mlp.up_proj.weight"] = h4[: d.ffn], h4[d.ffn:]
+        out[t + "mlp.down_proj.weight"] = lm[s + "mlp.dense_4h_to_h.weight"]
+    out[P + "linear_1.weight"] = lm["mm_projector.encoder.linear_fc1.weight"]
+    out[P + "linear_1.bias"] = lm["mm_projector.encoder.linear_fc1.bias"]
+    out[P + "linear_2.weight"] = lm["mm_projector.encoder.linear_fc2.weight"]
+    out[P + "linear_2.bias"] = lm["mm_projector.encoder.linear_fc2.bias"]
+    out[V + "embeddings.patch_embedding.weight"] = lm["vision_tower.conv1.weight"]
+    out[V + "embeddings.patch_embedding.bias"] = lm["vision_tower.conv1.bias"]
+    out[V + "embeddings.position_embedding.weight"] = lm["vision_tower.position_embeddings.weight"]
+    out[V + "post_layernorm.weight"] = lm["vision_tower.ln_post.weight"]
+    out[V + "post_layernorm.bias"] = lm["vision_tower.ln_post.bias"]
+    for i in range(v.layers):
+        s, t = f"vision_tower.transformer.layers.{i}.", f"{V}encoder.layers.{i}."
+        # rows interleaved [head, (q,k,v), 72] (hf2megatron_llava.py:1355-1374)
+        w = lm[s + "self_attention.linear_qkv.weight"].reshape(v.heads, 3, v.head_dim, v.hidden)
+        bb = lm[s + "self_attention.linear_qkv.bias"].reshape(v.heads, 3, v.head_dim)
+        for j, n in enumerate("qkv"):
+            out[t + f"self_attn.{n}_proj.weight"] = w[:, j].reshape(v.hidden, v.hidden)
+            out[t + f"self_attn.{n}_proj.bias"] = bb[:, j].reshape(v.hidden)
+        out[t + "layer_norm1.weight"] = lm[s + "self_attention.linear_qkv.layer_norm_weight"]
+        out[t + "layer_norm1.bias"] = lm[s + "self_attention.linear_qkv.layer_norm_bias"]
+        out[t + "self_attn.out_proj.weight"] = lm[s + "self_attention.linear_proj.weight"]
+        out[t + "self_attn.out_proj.bias"] = lm[s + "self_attention.linear_proj.bias"]
+        out[t + "mlp.fc1.weight"] = lm[s + "mlp.linear_fc1.weight"]
+        out[t + "mlp.fc1.bias"] = lm[s + "mlp.linear_fc1.bias"]
+        out[t + "layer_norm2.weight"] = lm[s + "mlp.linear_fc1.layer_norm_weight"]
+        out[t + "layer_norm2.bias"] = lm[s + "mlp.linear_fc1.layer_norm_bias"]
+        out[t + "mlp.fc2.weight"] = lm[s + "mlp.linear_fc2.weight"]
+        out[t + "mlp.fc2.bias"] = lm[s + "mlp.linear_fc2.bias"]
+    return out
+
+
+def hf_to_megatron(cfg: LeopardConfig, get: Callable[[str], torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Inverse of megatron_to_hf (used by tests and by the Megatron shim's synthetic constructor)."""
+    v, d = cfg.vit, cfg.dec
+    lm: Dict[str, torch.Tensor] = {}
+    lm["embedding.word_embeddings.weight"] = get(LM + "embed_tokens.weight")
+    lm["output_layer.weight"] = get("language_model.lm_head.weight")
+    lm["encoder.final_norm.weight"] = get(LM + "norm.weight")
+    rep, hd = d.heads // d.kv_heads, d.head_dim
+    for i in range(d.layers):
+        s, t = f"encoder.layers.{i}.", f"{LM}layers.{i}."
+        lm[s + "input_norm.weight"] = get(t + "input_layernorm.weight")
+        lm[s + "post_attention_norm.weight"] = get(t + "post_attention_layernorm.weight")
+        q = get(t + "self_attn.q_proj.weight").reshape(d.kv_heads, rep * hd, d.hidden)
+        k = get(t + "self_attn.k_proj.weight").reshape(d.kv_heads, hd, d.hidden)
+        vv = get(t + "self_attn.v_proj.weight").reshape(d.kv_heads, hd, d.hidden)
+        lm[s + "self_attention.query_key_value.weight"] = torch.cat([q, k, vv], 1).reshape(-1, d.hidden)
+        lm[s + "self_attention.dense.weight"] = get(t + "self_attn.o_proj.weight")
+        lm[s + "mlp.dense_h_to_4h.weight"] = torch.cat([get(t + "mlp.gate_proj.weight"), get(t + "mlp.up_proj.weight")], 0)
+        lm[s + "mlp.dense_4h_to_h.weight"] = get(t + "mlp.down_proj.weight")
+    lm["mm_projector.encoder.linear_fc1.weight"] = get(P + "linear_1.weight")
+    lm["mm_projector.encoder.linear_fc1.bias"] = get(P + "linear_1.bias")
+    lm["mm_projector.encoder.linear_fc2.weight"] = get(P + "linear_2.weight")
+    lm["mm_projector.encoder.linear_fc2.bias"] = get(P + "linear_2.bias")
+    lm["vision_tower.conv1.weight"] = get(V + "embeddings.patch_embedding.weight")
+    lm["vision_tower.conv1.bias"] = get(V + "embeddings.patch_embedding.bias")
+    lm["vision_tower.position_embeddings.weight"] = get(V + "embeddings.position_embedding.weight")
+    lm["vision_tower.ln_post.weight"] = get(V + "post_layernorm.weight")
+    lm["vision_tower.ln_post.bias"] = get(V + "post_layernorm.bias")
+    for i in range(v.layers):
+        s, t = f"vision_tower.transformer.layers.{i}.", f"{V}encoder.layers.{i}."
+        ws = [get(t + f"self_attn.{n}_proj.weight").reshape(v.heads, 1, v.head_dim, v.hidden) for n in "qkv"]
+        bs = [get(t + f"self_attn.{n}_proj.bias").reshape(v.heads, 1, v.head_dim) for n in "qkv"]
+        lm[s + "self_attention.linear_qkv.weight"] = torch.cat(ws, 1).reshape(3 * v.hidden, v.hidden)
+        lm[s + "self_attention.linear_qkv.bias"] = torch.cat(bs, 1).reshape(3 * v.hidden)
+        lm[s + "self_attention.linear_qkv.layer_norm_weight"] = get(t + "layer_norm1.weight")
+        lm[s + "self_attention.linear_qkv.layer_norm_bias"] = get(t + "layer_norm1.bias")
+        lm[s + "self_attention.linear_proj.weight"] = get(t + "self_attn.out_proj.weight")
+        lm[s + "self_attention.linear_proj.bias"] = get(t + "self_attn.out_proj.bias")
+        lm[s + "mlp.linear_fc1.weight"] = get(t + "mlp.fc1.weight")
+        lm[s + "mlp.linear_fc1.bias"] = get(t + "mlp.fc1.bias")
+        lm[s + "mlp.linear_fc1.layer_norm_weight"] = get(t + "layer_norm2.weight")
+        lm[s + "mlp.linear_fc1.layer_norm_bias"] = get(t + "layer_norm2.bias")
+        lm[s + "mlp.linear_fc2.weight"] = get(t + "mlp.fc2.weight")
+        lm[s + "mlp.linear_fc2.bias"] = get(t + "mlp.fc2.bias")
+    return lm

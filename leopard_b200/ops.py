@@ -55,3 +55,92 @@ def attention(qkv, B, T, n_heads, n_kv_heads, head_dim, head_stride, q_off, k_of
                                      out.stride(0), variant, _lib.stream_ptr())
     _lib.check(rc, "lp_attention_fwd")
     return out
+
+
+def _chk_f32(t, name):
+    if t is not None and (t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous CUDA fp32 tensor")
+
+
+def layernorm(x, gamma, beta, eps, shuffle_side=0, out=None):
+    """LayerNorm over the last dim of x [M, D]; shuffle_side=26 stores the pixel-shuffled layout [M/4, 4D]."""
+    _chk_bf16(x, "x")
+    _chk_f32(gamma, "gamma")
+    _chk_f32(beta, "beta")
+    M, D = x.shape
+    if out is None:
+        shape = (M // 4, 4 * D) if shuffle_side else (M, D)
+        out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_layernorm(_lib.ptr(x), x.stride(0), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out),
+                                 out.stride(0), M, D, float(eps), shuffle_side, _lib.stream_ptr())
+    _lib.check(rc, "lp_layernorm")
+    return out
+
+
+def rmsnorm(x, gamma, eps, out=None):
+    _chk_bf16(x, "x")
+    _chk_f32(gamma, "gamma")
+    M, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.lib().lp_rmsnorm(_lib.ptr(x), x.stride(0), _lib.ptr(gamma), _lib.ptr(out), out.stride(0), M, D,
+                               float(eps), _lib.stream_ptr())
+    _lib.check(rc, "lp_rmsnorm")
+    return out
+
+
+def rope_table(pos, inv_freq):
+    """pos int32 [S], inv_freq fp32 [half] -> (cos, sin) fp32 [S, half]."""
+    S, half = pos.numel(), inv_freq.numel()
+    cs = torch.empty((S, half), device=pos.device, dtype=torch.float32)
+    sn = torch.empty_like(cs)
+    rc = _lib.lib().lp_rope_table(_lib.ptr(pos), _lib.ptr(inv_freq), _lib.ptr(cs), _lib.ptr(sn), S, half,
+                                  _lib.stream_ptr())
+    _lib.check(rc, "lp_rope_table")
+    return cs, sn
+
+
+def rope_inplace(x, col0, n_heads, head_dim, cs, sn):
+    _chk_bf16(x, "x")
+    rc = _lib.lib().lp_rope_inplace(_lib.ptr(x), x.stride(0), x.shape[0], col0, n_heads, head_dim, _lib.ptr(cs),
+                                    _lib.ptr(sn), _lib.stream_ptr())
+    _lib.check(rc, "lp_rope_inplace")
+    return x
+
+
+def im2col_patch14(pixels, ldo=592):
+    """pixels [N,C,H,W] fp32/bf16 -> bf16 [N*(H/14)*(W/14), ldo]."""
+    N, Cc, H, W = pixels.shape
+    pixels = pixels.contiguous()
+    out = torch.empty((N * (H // 14) * (W // 14), ldo), device=pixels.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_im2col_patch14(_lib.ptr(pixels), 1 if pixels.dtype == torch.float32 else 0, _lib.ptr(out), ldo,
+                                      N, Cc, H, W, _lib.stream_ptr())
+    _lib.check(rc, "lp_im2col_patch14")
+    return out
+
+
+def embed_merge(ids, table, feats, image_id, rows_per_slot):
+    """ids int64 [L]; table bf16 [V, D]; feats bf16 [rows, D] or None -> (out [S, D], n_slots, S) (lp_embed_merge)."""
+    L = ids.numel()
+    D = table.shape[1]
+    n_feat = 0 if feats is None else feats.shape[0]
+    cap = L + (n_feat // rows_per_slot) * (rows_per_slot - 1)
+    out = torch.zeros((cap, D), device=table.device, dtype=torch.bfloat16)
+    plan = torch.empty(2 * L + 2, device=table.device, dtype=torch.int32)
+    rc = _lib.lib().lp_embed_merge(_lib.ptr(ids), L, image_id, rows_per_slot, _lib.ptr(table), table.stride(0),
+                                   table.shape[0], _lib.ptr(feats), feats.stride(0) if feats is not None else 0,
+                                   n_feat, _lib.ptr(out), out.stride(0), cap, D, _lib.ptr(plan), _lib.stream_ptr())
+    _lib.check(rc, "lp_embed_merge")
+    n_slots, S = plan[2 * L:].tolist()
+    return out, n_slots, S
+
+
+def pixel_shuffle(x2d, side):
+    """x2d bf16 [B*side*side, D] -> [B*side*side/4, 4*D] (lp_pixel_shuffle)."""
+    _chk_bf16(x2d, "x")
+    M, D = x2d.shape
+    out = torch.empty((M // 4, 4 * D), device=x2d.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_pixel_shuffle(_lib.ptr(x2d), x2d.stride(0), _lib.ptr(out), out.stride(0), M, D, side,
+                                     _lib.stream_ptr())
+    _lib.check(rc, "lp_pixel_shuffle")
+    return out

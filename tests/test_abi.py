@@ -1,0 +1,81 @@
+"""not gpu: the C-ABI library builds, loads and exports exactly what include/leopard_b200.h declares; ctypes
+signatures cover every symbol; argument errors are reported as status codes (no compute without a GPU)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_symbols():
+    txt = (ROOT / "include" / "leopard_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported_and_bound(native_lib):
+    from leopard_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 17
+    assert syms == _lib.declared_symbols(), "ctypes table and header disagree"
+    for s in syms:
+        assert hasattr(native_lib, s), s
+    assert native_lib.lp_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from leopard_b200 import _lib
+    # sizes implied by the C declarations (LP64): ints are 4 bytes, pointers 8
+    assert C.sizeof(_lib.VitDims) == 11 * 4
+    assert C.sizeof(_lib.VitLayerWeights) == 12 * 8
+    assert C.sizeof(_lib.VitWeights) == 6 * 8
+    assert C.sizeof(_lib.ProjWeights) == 4 * 8 + 8
+    assert C.sizeof(_lib.DecDims) == 8 * 4
+    assert C.sizeof(_lib.DecLayerWeights) == 6 * 8
+    assert C.sizeof(_lib.DecWeights) == 4 * 8
+
+
+def test_argument_errors_are_status_codes(native_lib):
+    rc = native_lib.lp_gemm_bf16(None, 8, None, 8, None, 8, 0, 8, 8, None, None, 0, 0, 0, 0, 0, None)
+    assert rc == -1 and b"empty problem" in native_lib.lp_last_error()
+    rc = native_lib.lp_attention_fwd(None, 64, 1, 4, 1, 1, 64, 64, 0, 64, 128, 1, 0.125, None, 64, 0, None)
+    assert rc == -1 and b"head_dim" in native_lib.lp_last_error()
+    rc = native_lib.lp_layernorm(None, 8, None, None, None, 8, 4, 5000, 1e-6, 0, None)
+    assert rc == -1
+
+
+def test_workspace_queries_are_host_only(native_lib):
+    from leopard_b200 import _lib
+    from leopard_b200.config import leopard_llava
+    from leopard_b200.native_weights import HEAD_STRIDE, PATCH_K_PAD
+    v, d = leopard_llava().vit, leopard_llava().dec
+    vd = _lib.VitDims(v.layers, v.hidden, v.ffn, v.heads, v.head_dim, HEAD_STRIDE, v.grid, v.tokens, v.patch_k,
+                      PATCH_K_PAD, v.eps)
+    n28 = native_lib.lp_vit_workspace_bytes(C.byref(vd), 28)
+    assert 28 * 676 * (592 + 1152 * 3 + 3840 + 4304) * 2 <= n28 < 1.01 * 28 * 676 * (592 + 1152 * 3 + 3840 + 4304) * 2 + 4096
+    dd = _lib.DecDims(d.layers, d.hidden, d.ffn, d.heads, d.kv_heads, d.head_dim, d.vocab, d.eps)
+    n = native_lib.lp_decoder_workspace_bytes(C.byref(dd), 4796, 1)
+    assert n >= 4796 * (4096 * 2 + 6144 + 14336) * 2
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from leopard_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.NativeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_engine_refuses_cpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from leopard_b200 import _lib
+    from leopard_b200.config import leopard_llava, reduced
+    from leopard_b200.engine import PrefillEngine
+    from leopard_b200.native_weights import NativeWeights
+    cfg = reduced(leopard_llava(), 1, 1, 1024)
+    with pytest.raises(_lib.NativeError, match="no CPU fallback"):
+        PrefillEngine(cfg, NativeWeights(cfg, "cpu"))
