@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — Leopard-LLaVA multi-image prefill throughput on B200 (contract: see the task's bench section).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU implementation of the same path
+                                                            (oracle port, host cores, bounded sample; rank 0 only)
+
+Metric  : prefill tokens/sec = merged decoder rows (image rows + text rows) processed / time, whole job.
+Workload: BASELINE.json configs[2] — 4 images 896x1152 -> adaptive allocation -> 28 crops (4 x (6 tiles + global)),
+          64 text ids + 28 placeholders -> S = 4796 merged rows; ONE such request per GPU per step (the config's batch
+          of 8 spread over 8 GPUs = weak scaling: per-GPU work fixed as N grows).  Synthetic weights/pixels/ids.
+A step  : ViT over 28 crops -> pixel-shuffle + projector -> embed+merge -> 32-layer decoder -> last-token logits.
+value   : inputs already resident in HBM.   e2e: the same through the reference-facing plugin call
+          (myLlavaForConditionalGeneration.generate, max_new_tokens=1) with HOST tensors: pinned host -> device copy
+          of pixel_values/ids and device -> host read of the generated token inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+IMAGE_SIZES = [(896, 1152)] * 4   # (width, height) x 4 — SlideVQA-shape, BASELINE.json configs[2]
+N_TEXT = 64
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_workload(cfg):
+    import torch
+    from leopard_b200.preprocess import plan_crops
+    per_image = plan_crops(IMAGE_SIZES)          # [7, 7, 7, 7] from the reference allocator
+    n_crops = sum(per_image)
+    g = torch.Generator().manual_seed(1)
+    pix = torch.rand((n_crops, 3, cfg.vit.image_size, cfg.vit.image_size), generator=g) * 2 - 1   # U(-1, 1), fp32
+    g2 = torch.Generator().manual_seed(2)
+    text = torch.randint(0, 128000, (N_TEXT,), generator=g2, dtype=torch.long)
+    ids = torch.cat([text[:24], torch.full((n_crops,), cfg.image_token_index, dtype=torch.long), text[24:]])[None]
+    S = ids.shape[1] + n_crops * (cfg.tokens_per_crop - 1)
+    return pix, ids, n_crops, S, per_image
+
+
+def flops_model(n_crops, S, cfg):
+    """Algorithmic FLOPs of one step."""
+    T = cfg.vit.tokens
+    vit = n_crops * (27 * (30_449_664 * T + 4608 * T * T) + 1_354_752 * T)
+    proj = n_crops * 2 * 169 * (4608 * 4096 + 4096 * 4096)
+    dec_lin = S * 2 * 32 * 218_103_808
+    dec_att = 262_144 * S * S
+    head = 2 * 4096 * cfg.dec.vocab
+    return {"vit": vit, "proj": proj, "dec_linear": dec_lin, "dec_attn": dec_att, "lm_head_last": head,
+            "total": vit + proj + dec_lin + dec_att + head}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_sample(cfg, n_crops, S, threads=None):
+    """Time the oracle (restated reference forward, torch-cpu fp32) on a bounded sample of the SAME workload:
+    1 of 27 ViT layers over all crops, projector on all crops, 1 of 32 decoder layers at the full S, final norm +
+    last-row lm_head; extrapolate x27 / x32 (BASELINE.md §3 fallback).  Returns (tokens_per_s, seconds_measured, info)."""
+    import torch
+    from oracle import model as om
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+
+    class ShapeCK:
+        """random tensor per distinct shape (values do not affect dense CPU timing)"""
+        def __init__(self, cfg):
+            from leopard_b200.weights import tensor_specs
+            self.specs = {n: s for n, s, _ in tensor_specs(cfg)}
+            self.cache = {}
+
+        def f32(self, name):
+            s = self.specs[name]
+            if s not in self.cache:
+                self.cache[s] = torch.randn(s) * 0.02
+            return self.cache[s]
+
+    ck = ShapeCK(cfg)
+    t_all = time.perf_counter()
+    with torch.no_grad():
+        pix = torch.rand(n_crops, 3, cfg.vit.image_size, cfg.vit.image_size)
+        t0 = time.perf_counter(); x = om.vit_embed(ck, cfg, pix); t_embed = time.perf_counter() - t0
+        t0 = time.perf_counter(); x = om.vit_layer(ck, cfg, x, 0); t_vl = time.perf_counter() - t0
+        t0 = time.perf_counter(); f = om.projector(ck, cfg, x); t_proj = time.perf_counter() - t0
+        emb = torch.randn(S, cfg.dec.hidden) * 0.1
+        cos, sin = om.rope_cos_sin(cfg.dec, torch.arange(S))
+        t0 = time.perf_counter(); y = om.decoder_layer(ck, cfg, emb, 0, cos, sin); t_dl = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        h = om.rmsnorm(y[-1:], ck.f32("language_model.model.norm.weight"), cfg.dec.eps)
+        torch.nn.functional.linear(h, ck.f32("language_model.lm_head.weight"))
+        t_head = time.perf_counter() - t0
+    measured = time.perf_counter() - t_all
+    est = t_embed + cfg.vit.layers * t_vl + t_proj + cfg.dec.layers * t_dl + t_head
+    info = {"t_vit_layer_s": round(t_vl, 3), "t_decoder_layer_s": round(t_dl, 3), "t_projector_s": round(t_proj, 3),
+            "estimated_full_step_s": round(est, 2)}
+    return S / est, measured, info
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own (CPU) implementation of the path = the oracle port, on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from leopard_b200.config import leopard_llava
+    cfg = leopard_llava()
+    _, _, n_crops, S, _ = make_workload(cfg)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vals, secs, info = [], [], {}
+    steps = max(1, min(args.steps, 2))       # each step is ~20-40 s of CPU work; keep the whole run to minutes
+    for i in range(min(args.warmup, 1) + steps):
+        v, s, info = cpu_reference_sample(cfg, n_crops, S, cores)
+        if i >= min(args.warmup, 1):
+            vals.append(v); secs.append(s)
+    value = statistics.mean(vals)
+    sample = ("1 of 27 ViT layers on all 28 crops + projector + 1 of 32 decoder layers at S=4796 + last-row lm_head, "
+              "torch-cpu fp32 oracle port, extrapolated x27/x32 to a full step")
+    line = {
+        "impl": "reference", "metric": "prefill tokens/sec (Leopard-LLaVA 4-image prefill, whole job)", "value": value,
+        "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1000.0 * S / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3: LLaVA 4x(896x1152) -> 28 crops, S=4796, 1 request/step (CPU: rank 0 only)",
+                   "crops": n_crops, "S": S},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample, **info},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: leopard_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from leopard_b200 import _lib
+    from leopard_b200.config import leopard_llava
+    from leopard_b200.hf import myLlavaForConditionalGeneration
+    from leopard_b200.native_weights import random_native
+
+    cfg = leopard_llava()
+    L = _lib.lib()
+    model = myLlavaForConditionalGeneration.from_native(cfg, random_native(cfg, dev, seed=1234))
+    eng = model.engine
+    pix_h, ids_h, n_crops, S, per_image = make_workload(cfg)
+    pix_h, ids_h = pix_h.pin_memory(), ids_h.pin_memory()
+    pix_d, ids_d = pix_h.to(dev), ids_h.to(dev)
+
+    def step_resident():
+        logits, _, _ = eng.prefill([(ids_d[0], pix_d)], "last")
+        return logits
+
+    def step_e2e():
+        out = model.generate(ids_h, pixel_values=pix_h, attention_mask=None, max_new_tokens=1, use_cache=False)
+        return out.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = L.lp_launch_count()
+    total_ms = timed(step_resident, args.steps)
+    launches = L.lp_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.steps * S / (total_ms / 1000.0)
+
+    # ---- e2e through the plugin API with host buffers
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    e2e_value = world * args.steps * S / (e2e_ms / 1000.0)
+    h2d = pix_h.numel() * pix_h.element_size() + ids_h.numel() * ids_h.element_size()
+    d2h = (ids_h.shape[1] + 1) * 8
+
+    # ---- per-kernel event timing of one more step (rank 0): roofline of the dominant kernel
+    roofline, stages = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        cap = 4096
+        _lib.check(L.lp_profile_enable(cap), "lp_profile_enable")
+        step_resident()
+        recs = (_lib.ProfileRecord * cap)()
+        n = L.lp_profile_read(C.cast(recs, C.c_void_p), cap)
+        by_kind = {}
+        gemm_shapes = {}
+        for r in recs[:n]:
+            by_kind[r.kind] = by_kind.get(r.kind, 0.0) + r.ms
+            if r.kind == 1:
+                key = (r.a, r.b, r.c)
+                g = gemm_shapes.setdefault(key, [0.0, 0])
+                g[0] += r.ms; g[1] += 1
+        step_ms_prof = sum(by_kind.values())
+        # dominant kernel = the GEMM shape with the largest summed time (decoder gate/up: M=S, N=28672, K=4096)
+        (m, nn, k), (ms_sum, cnt) = max(gemm_shapes.items(), key=lambda kv: kv[1][0])
+        avg_ms = ms_sum / cnt
+        ach = 2.0 * m * nn * k / (avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel M={m} N={nn} K={k} (x{cnt}/step)", "achieved": ach,
+                    "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                    "peak_kind": "sustained cuBLAS bf16, " + peaks["source"], "avg_launch_ms": avg_ms,
+                    "share_of_step": ms_sum / step_ms_prof, "traffic": None}
+        fm = flops_model(n_crops, S, cfg)
+        names = {1: "gemm", 2: "attention", 3: "norm", 4: "rope", 5: "merge", 6: "im2col", 7: "shuffle"}
+        gemm_all = sum(v[0] for v in gemm_shapes.values())
+        gemm_flops = sum(2.0 * a * b * c * v[1] for (a, b, c), v in gemm_shapes.items())
+        stages = {
+            "kernel_ms": {names.get(kk, str(kk)): round(v, 3) for kk, v in sorted(by_kind.items())},
+            "sum_kernel_ms": round(step_ms_prof, 3),
+            "all_gemms_tflops": gemm_flops / (gemm_all * 1e-3) / 1e12,
+            "attention_tflops": (fm["dec_attn"] + n_crops * 27 * 4608 * 676 * 676) / (by_kind.get(2, 1e9) * 1e-3) / 1e12,
+            "step_tflops_algorithmic": fm["total"] / ((total_ms / args.steps) * 1e-3) / 1e12,
+            "frac_of_sustained_peak": fm["total"] / ((total_ms / args.steps) * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "flops": {kk: float(v) for kk, v in fm.items()},
+        }
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, secs, info = cpu_reference_sample(cfg, n_crops, S, os.cpu_count())
+        cpu = {"value": v, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "1/27 ViT layers (28 crops) + projector + 1/32 decoder layers (S=4796) + last-row lm_head, "
+                         "oracle torch-cpu fp32, extrapolated to a full step", "seconds_measured": round(secs, 1), **info}
+
+    if rank == 0:
+        line = {
+            "metric": "prefill tokens/sec (Leopard-LLaVA 4-image prefill, whole job)", "value": value, "unit": "tokens/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "cfg3: LLaVA 4x(896x1152) -> adaptive allocation -> 28 crops, 92 prompt ids -> S=4796 "
+                                   "merged rows, 1 request per GPU per step, last-token logits",
+                       "crops_per_image": per_image, "S": S, "model": "SigLIP-SO400M/14-364 + Llama-3.1-8B (synthetic)",
+                       "l2_policy": "inputs larger than L2: 17 GB of weights stream from HBM every step (L2 = 126 MB)",
+                       "parallelism": f"dp{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "leopard_b200.hf.myLlavaForConditionalGeneration.generate(host ids, pixel_values=host fp32, max_new_tokens=1)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", __file__, "--gpus", str(args.gpus), "--steps",
+               str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -190,15 +190,40 @@ int lp_project(const lp_proj_weights* w, const void* shuffled, int rows, int in_
 
 /* Decoder prefill over n_seqs packed sequences (rows cu_seqlens_host[s] .. cu_seqlens_host[s+1]-1 of x).
  *   x: bf16 [R, hidden] merged embeddings; used as the residual stream and overwritten with the last layer's output.
- *   pos_ids: device int32 [R].  kv_cache: NULL or bf16 [layers][2][R][kv_heads*head_dim] (K after RoPE, then V).
+ *   pos_ids: device int32 [R].  kv_cache: NULL or bf16 [layers][2][kv_capacity][kv_heads*head_dim] (K after RoPE, then V; rows
+ *     0..R-1 are written, kv_capacity >= R leaves room for decode steps).
  *   logits: LP_LOGITS_LAST -> [n_seqs, vocab] (final norm + lm_head on each sequence's last row only);
  *           LP_LOGITS_ALL  -> [R, vocab] (what the reference materialises, EV/...anyres.py:333); fp32 or bf16.
  *   Replaces HF LlamaForCausalLM.forward (EV/...anyres.py:322-333) / Megatron ParallelTransformer.forward +
  *   parallel_lm_logits (MP/model/llava/transformer.py:1747-1860, MP/model/llava/vlm_model.py:32-60). */
 size_t lp_decoder_workspace_bytes(const lp_dec_dims* dims, int total_rows, int n_seqs);
 int lp_decoder_prefill(const lp_dec_dims* dims, const lp_dec_weights* w, void* x, const int* pos_ids,
-                       const int* cu_seqlens_host, int n_seqs, void* kv_cache, void* logits, long long ld_logits,
-                       int logits_mode, int logits_fp32, void* workspace, size_t ws_bytes, void* stream);
+                       const int* cu_seqlens_host, int n_seqs, void* kv_cache, long long kv_capacity, void* logits,
+                       long long ld_logits, int logits_mode, int logits_fp32, void* workspace, size_t ws_bytes,
+                       void* stream);
+
+/* One greedy-decode step after a prefill (cached branch of myLlavaForConditionalGeneration.forward,
+ * EV/llava_multiimg_siglip_anyres.py:291-320; B = 1, no padding => position = number of cached rows, App. A.2).
+ *   token_id: DEVICE int64[1] (the previously sampled token); its embedding row is gathered from embed_table.
+ *   kv_cache: the prefill's cache, row `position` of every layer is written, rows 0..position are attended to.
+ *   logits: fp32 [vocab] of the new position. */
+size_t lp_decode_workspace_bytes(const lp_dec_dims* dims);
+int lp_decode_step(const lp_dec_dims* dims, const lp_dec_weights* w, const void* embed_table, long long ld_embed,
+                   const long long* token_id, int position, void* kv_cache, long long kv_capacity, void* logits,
+                   void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Measurement hooks (used by bench.py only).
+ * lp_launch_count: kernels this library has launched since load (the bench's "gpu_launches" claim).
+ * lp_profile_enable(capacity > 0): from now on every lp_gemm_bf16 / lp_attention_fwd / norm / rope / merge launch is
+ *   bracketed by a CUDA event pair on ITS stream, until `capacity` records are taken; capacity 0 disables.
+ * lp_profile_read: synchronises on the recorded events, returns up to `capacity` records and disables profiling.
+ *   kind: 1 gemm (a,b,c = M,N,K), 2 attention (a,b,c = B,T,heads*1000+head_dim), 3 norm (a,b = M,D), 4 rope, 5 merge,
+ *   6 im2col, 7 pixel-shuffle. */
+typedef struct lp_profile_record { int kind, a, b, c; float ms; } lp_profile_record;
+long long lp_launch_count(void);
+int lp_profile_enable(int capacity);
+int lp_profile_read(lp_profile_record* out, int capacity);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,10 @@ class DecWeights(C.Structure):
     _fields_ = [("layers", C.POINTER(DecLayerWeights)), ("final_g", _vp), ("lm_head", _vp), ("inv_freq", _vp)]
 
 
+class ProfileRecord(C.Structure):
+    _fields_ = [("kind", _i), ("a", _i), ("b", _i), ("c", _i), ("ms", _f)]
+
+
 _P = C.POINTER
 
 # name -> (restype, argtypes); must list EVERY symbol include/leopard_b200.h declares (tests/test_abi.py checks)
@@ -72,8 +76,13 @@ _SIGS = {
     "lp_project_workspace_bytes": (_sz, [_i, _i]),
     "lp_project": (_i, [_P(ProjWeights), _vp, _i, _i, _i, _vp, _ll, _vp, _sz, _vp]),
     "lp_decoder_workspace_bytes": (_sz, [_P(DecDims), _i, _i]),
-    "lp_decoder_prefill": (_i, [_P(DecDims), _P(DecWeights), _vp, _vp, _P(_i), _i, _vp, _vp, _ll, _i, _i, _vp, _sz,
-                                _vp]),
+    "lp_decoder_prefill": (_i, [_P(DecDims), _P(DecWeights), _vp, _vp, _P(_i), _i, _vp, _ll, _vp, _ll, _i, _i, _vp,
+                                _sz, _vp]),
+    "lp_decode_workspace_bytes": (_sz, [_P(DecDims)]),
+    "lp_decode_step": (_i, [_P(DecDims), _P(DecWeights), _vp, _ll, _vp, _i, _vp, _ll, _vp, _vp, _sz, _vp]),
+    "lp_launch_count": (_ll, []),
+    "lp_profile_enable": (_i, [_i]),
+    "lp_profile_read": (_i, [_vp, _i]),
 }
 
 _lib = None

@@ -379,6 +379,8 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
                              128, 1);
   if (rc) return rc;
   const bool ptm = (variant & 1) != 0;
+  ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
+  note_launch();
   if (head_dim == 72) {
     LP_REQUIRE(!causal, "lp_attention_fwd: head_dim 72 is the (non-causal) ViT configuration");
     return ptm ? launch_attn<80, false, true>(tm, a, stream) : launch_attn<80, false, false>(tm, a, stream);

@@ -110,12 +110,12 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
 }
 
 // cos/sin tables [S, half] from integer positions and fp32 inverse frequencies
-__global__ void rope_table_kernel(const int* __restrict__ pos, const float* __restrict__ inv_freq,
+__global__ void rope_table_kernel(const int* __restrict__ pos, int pos_base, const float* __restrict__ inv_freq,
                                   float* __restrict__ cs, float* __restrict__ sn, int S, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * half) return;
   const int s = i / half, j = i % half;
-  const float a = (float)pos[s] * inv_freq[j];
+  const float a = (float)(pos ? pos[s] : pos_base + s) * inv_freq[j];
   cs[i] = cosf(a);
   sn[i] = sinf(a);
 }
@@ -262,6 +262,8 @@ extern "C" int lp_layernorm(const void* x, long long ldx, const float* gamma, co
              "lp_layernorm: 16-byte alignment required");
   LP_REQUIRE(shuffle_side == 0 || (shuffle_side % 2 == 0 && M % (shuffle_side * shuffle_side) == 0),
              "lp_layernorm: pixel-shuffle store needs an even grid side and M %% side^2 == 0");
+  ProfScope prof(3, M, D, 0, reinterpret_cast<cudaStream_t>(stream));
+  note_launch();
   norm_kernel<false><<<M, NORM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), ldx, gamma, beta, reinterpret_cast<bf16*>(out), ldo, D, eps, shuffle_side);
   LP_CHECK_CUDA(cudaGetLastError());
@@ -273,6 +275,8 @@ extern "C" int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void
   LP_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= NORM_THREADS * NORM_MAXC * 8, "lp_rmsnorm: bad M=%d D=%d", M, D);
   LP_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && aligned16(x) && aligned16(out) && aligned16(gamma),
              "lp_rmsnorm: 16-byte alignment required");
+  ProfScope prof(3, M, D, 1, reinterpret_cast<cudaStream_t>(stream));
+  note_launch();
   norm_kernel<true><<<M, NORM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), ldx, gamma, nullptr, reinterpret_cast<bf16*>(out), ldo, D, eps, 0);
   LP_CHECK_CUDA(cudaGetLastError());
@@ -281,13 +285,25 @@ extern "C" int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void
 
 extern "C" int lp_rope_table(const int* pos, const float* inv_freq, float* cos_out, float* sin_out, int S, int half,
                              void* stream) {
-  LP_REQUIRE(S > 0 && half > 0, "lp_rope_table: bad S=%d half=%d", S, half);
+  LP_REQUIRE(S > 0 && half > 0 && pos != nullptr, "lp_rope_table: bad S=%d half=%d", S, half);
   const int total = S * half;
-  rope_table_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pos, inv_freq, cos_out,
+  ProfScope prof(4, S, half, 0, reinterpret_cast<cudaStream_t>(stream));
+  note_launch();
+  rope_table_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pos, 0, inv_freq, cos_out,
                                                                                            sin_out, S, half);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+namespace lp {
+// positions pos_base .. pos_base + S - 1 without a device-side position array (decode step)
+int rope_table_base(int pos_base, const float* inv_freq, float* cs, float* sn, int S, int half, cudaStream_t stream) {
+  note_launch();
+  rope_table_kernel<<<(S * half + 255) / 256, 256, 0, stream>>>(nullptr, pos_base, inv_freq, cs, sn, S, half);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace lp
 
 extern "C" int lp_rope_inplace(void* x, long long ld, int S, int col0, int n_heads, int head_dim, const float* cos_t,
                                const float* sin_t, void* stream) {
@@ -296,6 +312,8 @@ extern "C" int lp_rope_inplace(void* x, long long ld, int S, int col0, int n_hea
   LP_REQUIRE(ld % 8 == 0 && col0 % 8 == 0 && aligned16(x), "lp_rope_inplace: 16-byte alignment required");
   const int half = head_dim / 2;
   const long long total = (long long)S * n_heads * (half / 8);
+  ProfScope prof(4, S, n_heads, 1, reinterpret_cast<cudaStream_t>(stream));
+  note_launch();
   rope_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<bf16*>(x), ld, S, col0, n_heads, half, cos_t, sin_t);
   LP_CHECK_CUDA(cudaGetLastError());
@@ -316,6 +334,8 @@ extern "C" int lp_embed_merge(const long long* ids, int L, long long image_id, i
   int* dst = plan;
   int* src = plan + L;
   int* totals = plan + 2 * L;
+  ProfScope prof(5, L, D, rows_per_slot, stream);
+  note_launch(2);
   merge_plan_kernel<<<1, 1024, 0, stream>>>(ids, L, image_id, rows_per_slot, dst, src, totals);
   LP_CHECK_CUDA(cudaGetLastError());
   merge_copy_kernel<<<L, 128, 0, stream>>>(ids, dst, src, reinterpret_cast<const bf16*>(table), ldt, vocab,
@@ -332,6 +352,8 @@ extern "C" int lp_im2col_patch14(const void* pixels, int pixels_fp32, void* out,
   LP_REQUIRE(ldo >= C * 196 && ldo % 8 == 0 && aligned16(out), "lp_im2col_patch14: ldo=%lld too small/unaligned", ldo);
   const long long total = (long long)N * (H / 14) * (W / 14) * (C * 14 + 1);
   const unsigned grid = (unsigned)((total + 255) / 256);
+  ProfScope prof(6, N, H, W, stream);
+  note_launch();
   if (pixels_fp32)
     im2col_patch14_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(pixels),
                                                            reinterpret_cast<bf16*>(out), ldo, N, C, H, W);
@@ -347,6 +369,8 @@ extern "C" int lp_pixel_shuffle(const void* x, long long ldx, void* out, long lo
   LP_REQUIRE(M > 0 && D % 8 == 0 && side > 0 && side % 2 == 0 && M % (side * side) == 0,
              "lp_pixel_shuffle: bad M=%d D=%d side=%d", M, D, side);
   LP_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && aligned16(x) && aligned16(out), "lp_pixel_shuffle: alignment");
+  ProfScope prof(7, M, D, side, reinterpret_cast<cudaStream_t>(stream));
+  note_launch();
   pixel_shuffle_kernel<<<M, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, side, D);
   LP_CHECK_CUDA(cudaGetLastError());

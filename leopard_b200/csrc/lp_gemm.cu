@@ -328,6 +328,8 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, (uint32_t)block_n);
   if (rc) return rc;
+  ProfScope prof(1, M, N, K, stream);
+  note_launch();
   if (block_n == 256) return launch_gemm<256, 4>(tmA, tmB, args, stream);
   return launch_gemm<128, 6>(tmA, tmB, args, stream);
 }

@@ -28,6 +28,24 @@ int sm_count() {
   return n;
 }
 
+// ---- launch counter / profiler ------------------------------------------------------------------------------------
+static long long g_launches = 0;
+void note_launch(int n) { g_launches += n; }
+
+struct ProfRec { cudaEvent_t e0, e1; int kind, a, b, c; };
+static ProfRec* g_recs = nullptr;
+static int g_cap = 0, g_n = 0, g_enabled = 0;
+
+ProfScope::ProfScope(int kind, int a, int b, int c, cudaStream_t s) : idx(-1), stream(s) {
+  if (!g_enabled || g_n >= g_cap) return;
+  idx = g_n++;
+  g_recs[idx].kind = kind; g_recs[idx].a = a; g_recs[idx].b = b; g_recs[idx].c = c;
+  cudaEventRecord(g_recs[idx].e0, stream);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_recs[idx].e1, stream);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -84,3 +102,43 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
 
 extern "C" const char* lp_last_error(void) { return lp::get_error(); }
 extern "C" int lp_abi_version(void) { return LP_ABI_VERSION; }
+
+extern "C" long long lp_launch_count(void) { return lp::g_launches; }
+
+extern "C" int lp_profile_enable(int capacity) {
+  using namespace lp;
+  if (capacity > g_cap) {
+    ProfRec* n = new ProfRec[capacity];
+    for (int i = 0; i < g_cap; ++i) n[i] = g_recs[i];
+    for (int i = g_cap; i < capacity; ++i) {
+      if (cudaEventCreate(&n[i].e0) != cudaSuccess || cudaEventCreate(&n[i].e1) != cudaSuccess) {
+        set_error("lp_profile_enable: cudaEventCreate failed");
+        delete[] n;
+        return LP_ERR_CUDA;
+      }
+    }
+    delete[] g_recs;
+    g_recs = n;
+    g_cap = capacity;
+  }
+  g_n = 0;
+  g_enabled = capacity > 0;
+  return 0;
+}
+
+extern "C" int lp_profile_read(lp_profile_record* out, int capacity) {
+  using namespace lp;
+  g_enabled = 0;
+  int n = g_n < capacity ? g_n : capacity;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_recs[i].e1) != cudaSuccess || cudaEventElapsedTime(&ms, g_recs[i].e0, g_recs[i].e1) != cudaSuccess) {
+      set_error("lp_profile_read: event query failed");
+      return LP_ERR_CUDA;
+    }
+    out[i].kind = g_recs[i].kind; out[i].a = g_recs[i].a; out[i].b = g_recs[i].b; out[i].c = g_recs[i].c;
+    out[i].ms = ms;
+  }
+  g_n = 0;
+  return n;
+}

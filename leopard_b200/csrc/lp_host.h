@@ -29,6 +29,15 @@ const char* get_error();
 
 int sm_count();
 
+// launch accounting + optional per-launch CUDA-event timing (off by default; see lp_profile_* in the public header)
+void note_launch(int n = 1);
+struct ProfScope {
+  int idx;
+  cudaStream_t stream;
+  ProfScope(int kind, int a, int b, int c, cudaStream_t s);
+  ~ProfScope();
+};
+
 // 2-D / 3-D bf16 tensor maps with 128B swizzle (inner box = 64 elements = 128 B), zero OOB fill.
 // dims/strides are innermost-first; strides are in ELEMENTS for dims >= 1.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,

@@ -132,9 +132,9 @@ extern "C" size_t lp_decoder_workspace_bytes(const lp_dec_dims* d, int total_row
 }
 
 extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w, void* x, const int* pos_ids,
-                                  const int* cu_seqlens_host, int n_seqs, void* kv_cache, void* logits,
-                                  long long ld_logits, int logits_mode, int logits_fp32, void* workspace,
-                                  size_t ws_bytes, void* stream_) {
+                                  const int* cu_seqlens_host, int n_seqs, void* kv_cache, long long kv_capacity,
+                                  void* logits, long long ld_logits, int logits_mode, int logits_fp32,
+                                  void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LP_REQUIRE(d && w && x && pos_ids && cu_seqlens_host && n_seqs > 0, "lp_decoder_prefill: null argument");
   LP_REQUIRE(d->head_dim == 128 && d->heads % d->kv_heads == 0, "lp_decoder_prefill: head_dim must be 128");
@@ -143,6 +143,7 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
   LP_REQUIRE(ws_bytes >= lp_decoder_workspace_bytes(d, R, n_seqs), "lp_decoder_prefill: workspace too small (%zu < %zu)",
              ws_bytes, lp_decoder_workspace_bytes(d, R, n_seqs));
   LP_REQUIRE(logits_mode == LP_LOGITS_NONE || logits != nullptr, "lp_decoder_prefill: logits buffer missing");
+  LP_REQUIRE(kv_cache == nullptr || kv_capacity >= R, "lp_decoder_prefill: kv_capacity %lld < %d rows", kv_capacity, R);
   Carver cv(workspace, ws_bytes);
   void *h, *qkv, *att, *act, *last;
   float *cs, *sn;
@@ -172,10 +173,10 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
       }
     }
     if (kv_cache) {  // [layers][2][R][kv_w]: K (post-RoPE) then V
-      __nv_bfloat16* kc = (__nv_bfloat16*)kv_cache + (size_t)l * 2 * R * kv_w;
+      __nv_bfloat16* kc = (__nv_bfloat16*)kv_cache + (size_t)l * 2 * kv_capacity * kv_w;
       LP_CHECK_CUDA(cudaMemcpy2DAsync(kc, bf(kv_w), (const __nv_bfloat16*)qkv + q_w, bf(qkv_w), bf(kv_w), R,
                                       cudaMemcpyDeviceToDevice, stream));
-      LP_CHECK_CUDA(cudaMemcpy2DAsync(kc + (size_t)R * kv_w, bf(kv_w), (const __nv_bfloat16*)qkv + q_w + kv_w,
+      LP_CHECK_CUDA(cudaMemcpy2DAsync(kc + (size_t)kv_capacity * kv_w, bf(kv_w), (const __nv_bfloat16*)qkv + q_w + kv_w,
                                       bf(qkv_w), bf(kv_w), R, cudaMemcpyDeviceToDevice, stream));
     }
     LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, R, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 0, stream));

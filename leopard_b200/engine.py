@@ -95,7 +95,7 @@ class PrefillEngine:
         return out[:S], n_slots
 
     def decoder(self, x: torch.Tensor, pos_ids: torch.Tensor, cu_seqlens: Sequence[int], logits_mode: str = "last",
-                logits_dtype=torch.float32, want_kv: bool = False):
+                logits_dtype=torch.float32, want_kv: bool = False, kv_capacity: int = 0):
         """x [R, D] packed merged embeddings (overwritten) -> (logits, kv_cache or None).
         logits: 'last' -> [n_seqs, V]; 'all' -> [R, V]; 'none' -> None."""
         d = self.cfg.dec
@@ -111,12 +111,13 @@ class PrefillEngine:
             logits = torch.empty((R, vp), dtype=logits_dtype, device=self.device)
         kv = None
         if want_kv:
-            kv = torch.empty((d.layers, 2, R, d.kv_heads * d.head_dim), dtype=torch.bfloat16, device=self.device)
+            kv = torch.empty((d.layers, 2, max(R, kv_capacity), d.kv_heads * d.head_dim), dtype=torch.bfloat16,
+                             device=self.device)
         cu = (C.c_int * (n + 1))(*[int(c) for c in cu_seqlens])
         ws = self._workspace("dec", L.lp_decoder_workspace_bytes(C.byref(self.w.dec_dims), R, n))
         pos = pos_ids.to(self.device, torch.int32).contiguous()
         rc = L.lp_decoder_prefill(C.byref(self.w.dec_dims), C.byref(self.w.dec), _lib.ptr(x), _lib.ptr(pos), cu, n,
-                                  _lib.ptr(kv), _lib.ptr(logits), logits.stride(0) if logits is not None else 0, mode,
+                                  _lib.ptr(kv), kv.shape[2] if kv is not None else 0, _lib.ptr(logits), logits.stride(0) if logits is not None else 0, mode,
                                   1 if logits_dtype == torch.float32 else 0, _lib.ptr(ws), ws.numel(),
                                   _lib.stream_ptr())
         _lib.check(rc, "lp_decoder_prefill")
@@ -127,7 +128,7 @@ class PrefillEngine:
     # ------------------------------------------------------------------ whole path
     @torch.no_grad()
     def prefill(self, samples: List[Tuple[torch.Tensor, Optional[torch.Tensor]]], logits_mode: str = "last",
-                logits_dtype=torch.float32, want_kv: bool = False, convention: str = "hf"):
+                logits_dtype=torch.float32, want_kv: bool = False, convention: str = "hf", kv_capacity: int = 0):
         """samples: [(input_ids [L] or [1,L], pixel_values [N_i,3,364,364] or None), ...] — independent requests.
         All crops go through the tower as one batch, every request becomes one packed decoder sequence.
         convention 'hf': one placeholder id per crop, expanded to 169 rows; 'megatron': one -200 per feature row.
@@ -163,5 +164,5 @@ class PrefillEngine:
             self.merge(ids, f, image_id, per_slot, out=x[cu[k]:cu[k + 1]])
             f0 += n_rows
         pos = torch.cat([torch.arange(ln, dtype=torch.int32, device=self.device) for ln in lens])
-        logits, kv = self.decoder(x, pos, cu, logits_mode, logits_dtype, want_kv)
+        logits, kv = self.decoder(x, pos, cu, logits_mode, logits_dtype, want_kv, cu[-1] + kv_capacity)
         return logits, kv, cu

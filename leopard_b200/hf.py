@@ -1,0 +1,321 @@
+"""Drop-in for the HF-eval plugin surface of the reference (first row).
+
+Same names and call conventions as evaluations/models/llava_multiimg_siglip_anyres.py:
+    pixel_shuffle(x, scale_factor=2)                                   (:165-176)
+    myLlavaMultiModalProjector(config).forward(image_features)         (:179-192)
+    myLlavaForConditionalGeneration.from_pretrained(...).eval().to(dev)
+        .forward(input_ids, pixel_values, attention_mask, ...) -> LlavaCausalLMOutputWithPast-like   (:201-361)
+        .generate(input_ids, pixel_values=, attention_mask=, pad_token_id=, eos_token_id=, max_new_tokens=, use_cache=)
+                                                                        (call site :448-452)
+All arithmetic runs in the native library; tensors may arrive on the host (they are copied to the model's device, as
+`.to(llava.device)` does in the reference driver) but there is no CPU compute path: without CUDA every call raises.
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass
+from pathlib import Path
+from types import SimpleNamespace
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .config import DecoderConfig, LeopardConfig, RopeScaling, VitConfig, leopard_llava
+from .engine import PrefillEngine
+from .native_weights import NativeWeights, load_hf
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.NativeError(f"{what}: tensor is on {t.device}; leopard_b200 computes on CUDA only (no CPU fallback)")
+
+
+def pixel_shuffle(x: torch.Tensor, scale_factor: int = 2) -> torch.Tensor:
+    """[bsz, seq, dim] -> [bsz, seq/4, 4*dim]; 2x2 spatial neighbourhoods concatenated along channels
+    (evaluations/models/llava_multiimg_siglip_anyres.py:165-176).  Native kernel: lp_pixel_shuffle."""
+    if scale_factor != 2:
+        raise NotImplementedError("Leopard uses scale_factor=2 only")
+    _require_cuda(x, "pixel_shuffle")
+    bsz, seq, dim = x.shape
+    side = int(seq ** 0.5)
+    y = ops.pixel_shuffle(x.to(torch.bfloat16).reshape(bsz * seq, dim).contiguous(), side)
+    return y.view(bsz, seq // 4, dim * 4).to(x.dtype)
+
+
+class myLlavaMultiModalProjector(nn.Module):
+    """linear_2(act(linear_1(pixel_shuffle(x)))) with the reference's attribute names (…anyres.py:179-192).
+    `config` needs .vision_config.hidden_size, .text_config.hidden_size and .projector_hidden_act."""
+
+    def __init__(self, config):
+        super().__init__()
+        vh, th = config.vision_config.hidden_size, config.text_config.hidden_size
+        self.linear_1 = nn.Linear(vh * 4, th, bias=True)
+        self.act_name = getattr(config, "projector_hidden_act", "gelu")
+        self.act = nn.GELU() if self.act_name == "gelu" else nn.GELU(approximate="tanh")  # attribute parity only
+        self.linear_2 = nn.Linear(th, th, bias=True)
+        self._native = None
+
+    def _sync(self, device):
+        ver = tuple(p._version for p in self.parameters()) + (str(device),)
+        if self._native is None or self._native[0] != ver:
+            bf = lambda t: t.detach().to(device, torch.bfloat16).contiguous()  # noqa: E731
+            f32 = lambda t: t.detach().to(device).to(torch.bfloat16).float().contiguous()  # noqa: E731
+            self._native = (ver, bf(self.linear_1.weight), f32(self.linear_1.bias), bf(self.linear_2.weight),
+                            f32(self.linear_2.bias))
+        return self._native[1:]
+
+    def forward(self, image_features: torch.Tensor) -> torch.Tensor:
+        _require_cuda(image_features, "myLlavaMultiModalProjector")
+        w1, b1, w2, b2 = self._sync(image_features.device)
+        n, seq, dim = image_features.shape
+        x = ops.pixel_shuffle(image_features.to(torch.bfloat16).reshape(n * seq, dim).contiguous(), int(seq ** 0.5))
+        act = _lib.ACT_GELU_ERF if self.act_name == "gelu" else _lib.ACT_GELU_TANH
+        h = ops.gemm(x, w1, bias=b1, act=act)
+        y = ops.gemm(h, w2, bias=b2)
+        return y.view(n, seq // 4, -1).to(image_features.dtype)
+
+
+@dataclass
+class LlavaCausalLMOutputWithPast:
+    """Field-compatible with transformers' LlavaCausalLMOutputWithPast (…anyres.py:351-361)."""
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    past_key_values: Optional[tuple] = None
+    hidden_states: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+
+    def __getitem__(self, i):
+        return tuple(v for v in (self.loss, self.logits, self.past_key_values) if v is not None)[i]
+
+
+def _config_from_hf_json(d: dict) -> LeopardConfig:
+    t, v = d.get("text_config", {}), d.get("vision_config", {})
+    rs = t.get("rope_scaling")
+    dec = DecoderConfig(hidden=t.get("hidden_size", 4096), ffn=t.get("intermediate_size", 14336),
+                        heads=t.get("num_attention_heads", 32), kv_heads=t.get("num_key_value_heads", 8),
+                        layers=t.get("num_hidden_layers", 32), vocab=t.get("vocab_size", 128256),
+                        rope_theta=float(t.get("rope_theta", 500000.0)),
+                        rope_scaling=None if not rs else RopeScaling(
+                            factor=rs.get("factor", 8.0), low_freq_factor=rs.get("low_freq_factor", 1.0),
+                            high_freq_factor=rs.get("high_freq_factor", 4.0),
+                            original_max_position=rs.get("original_max_position_embeddings", 8192)),
+                        eps=t.get("rms_norm_eps", 1e-5))
+    vit = VitConfig(image_size=v.get("image_size", 364), patch_size=v.get("patch_size", 14),
+                    hidden=v.get("hidden_size", 1152), ffn=v.get("intermediate_size", 4304),
+                    heads=v.get("num_attention_heads", 16), layers=v.get("num_hidden_layers", 27),
+                    eps=v.get("layer_norm_eps", 1e-6))
+    return LeopardConfig(vit=vit, dec=dec, image_token_index=d.get("image_token_index", 128200),
+                         projector_act=d.get("projector_hidden_act", "gelu"))
+
+
+class _VisionTower:
+    """`model.vision_tower(pixel_values).last_hidden_state` (…anyres.py:268,273)."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def __call__(self, pixel_values, **_):
+        eng = self._o.engine
+        out = eng.vit(pixel_values.to(eng.device), shuffle=False)
+        n = pixel_values.shape[0]
+        return SimpleNamespace(last_hidden_state=out.view(n, eng.cfg.vit.tokens, -1).to(pixel_values.dtype))
+
+
+class _Projector:
+    """`model.multi_modal_projector(selected_image_feature)` (…anyres.py:283)."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def __call__(self, image_features):
+        eng = self._o.engine
+        n, seq, dim = image_features.shape
+        x = ops.pixel_shuffle(image_features.to(eng.device, torch.bfloat16).reshape(n * seq, dim).contiguous(),
+                              int(seq ** 0.5))
+        return eng.project(x).view(n, seq // 4, -1).to(image_features.dtype)
+
+
+class _LanguageModel:
+    """`model.language_model(inputs_embeds=..., position_ids=..., use_cache=...)` -> (logits, past) (…anyres.py:322-333)."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def __call__(self, inputs_embeds=None, position_ids=None, attention_mask=None, past_key_values=None,
+                 use_cache=None, **_):
+        if past_key_values is not None:
+            raise NotImplementedError("cached decode goes through myLlavaForConditionalGeneration.generate")
+        eng = self._o.engine
+        if inputs_embeds.shape[0] != 1:
+            raise NotImplementedError("the reference path is B = 1 (SURVEY.md App. A.1)")
+        x = inputs_embeds[0].to(eng.device, torch.bfloat16).contiguous().clone()
+        S = x.shape[0]
+        pos = torch.arange(S, device=eng.device) if position_ids is None else position_ids.reshape(-1)
+        logits, kv = eng.decoder(x, pos, [0, S], "all", torch.float32, want_kv=bool(use_cache))
+        out = SimpleNamespace(logits=logits[None], past_key_values=self._o._legacy_cache(kv, S) if kv is not None else None,
+                              hidden_states=None, attentions=None)
+        return out
+
+
+class myLlavaForConditionalGeneration:
+    """Native-backed stand-in for the reference class of the same name (…anyres.py:195-361)."""
+
+    def __init__(self, config: Union[LeopardConfig, dict, None] = None):
+        if config is None:
+            config = leopard_llava()
+        if isinstance(config, dict):
+            config = _config_from_hf_json(config)
+        self.config = config
+        self.engine: Optional[PrefillEngine] = None
+        self._native: Optional[NativeWeights] = None
+        self._pending = None  # HF-layout getter waiting for a CUDA device
+        self.device = torch.device("cpu")
+        self.dtype = torch.float32
+        self.training = False
+        self.vision_tower = _VisionTower(self)
+        self.multi_modal_projector = _Projector(self)
+        self.language_model = _LanguageModel(self)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_native(cls, cfg: LeopardConfig, native: NativeWeights):
+        m = cls(cfg)
+        m._native, m.device = native, native.device
+        m.engine = PrefillEngine(cfg, native)
+        return m
+
+    @classmethod
+    def from_state_dict(cls, cfg: LeopardConfig, getter, device=None):
+        """`getter(name)` returns HF-layout tensors (a dict's __getitem__, a SyntheticCheckpoint, ...)."""
+        m = cls(cfg)
+        m._pending = getter
+        if device is not None:
+            m.to(device)
+        return m
+
+    @classmethod
+    def from_pretrained(cls, path, torch_dtype=None, **_):
+        """Load an HF-layout checkpoint directory (config.json + *.safetensors / pytorch_model*.bin), the layout
+        written by the reference converter (hf2megatron_llava.py:1026-1052,1453).  Weights stay on the host until
+        `.to(device)`; `torch_dtype` is accepted for call compatibility (the native path computes in bf16)."""
+        path = Path(path)
+        cfg = _config_from_hf_json(json.loads((path / "config.json").read_text()))
+        tensors = {}
+        st = sorted(path.glob("*.safetensors"))
+        if st:
+            from safetensors.torch import load_file
+            for f in st:
+                tensors.update(load_file(str(f)))
+        else:
+            for f in sorted(path.glob("pytorch_model*.bin")):
+                tensors.update(torch.load(f, map_location="cpu", weights_only=True))
+        if not tensors:
+            raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {path}")
+        # transformers >= 4.5x nests the towers under `model.`; accept both spellings
+        def get(name):
+            for cand in (name, "model." + name, name.replace("language_model.model.", "model.language_model.")):
+                if cand in tensors:
+                    return tensors[cand]
+            raise KeyError(name)
+        m = cls.from_state_dict(cfg, get)
+        if torch_dtype is not None:
+            m.dtype = torch_dtype
+        return m
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.NativeError("myLlavaForConditionalGeneration.to(): only CUDA devices are supported (no CPU fallback)")
+        if self._native is None or self._native.device != device:
+            if self._pending is None:
+                raise _lib.NativeError("no weights to move: construct with from_pretrained/from_state_dict/from_native")
+            self._native = load_hf(self.config, self._pending, device)
+            self.engine = PrefillEngine(self.config, self._native)
+        self.device = device
+        return self
+
+    def cuda(self, index=0):
+        return self.to(f"cuda:{index}")
+
+    def get_input_embeddings(self):
+        eng = self._eng()
+
+        def embed(input_ids):
+            flat = input_ids.reshape(-1).to(eng.device)
+            out, _ = eng.merge(flat, None, image_id=-(2 ** 62), rows_per_slot=1)
+            return out.view(*input_ids.shape, -1)
+        return embed
+
+    def _eng(self) -> PrefillEngine:
+        if self.engine is None:
+            raise _lib.NativeError("model is not on a CUDA device yet: call .to('cuda:0') (no CPU fallback)")
+        return self.engine
+
+    def _legacy_cache(self, kv, S):
+        """[layers, 2, cap, kv_w] -> tuple-of-tuples [layer][k|v] shaped [1, kv_heads, S, head_dim] (views), the legacy
+        format the reference indexes directly (…anyres.py:294)."""
+        d = self.config.dec
+        return tuple((kv[l, 0, :S].view(S, d.kv_heads, d.head_dim).permute(1, 0, 2)[None],
+                      kv[l, 1, :S].view(S, d.kv_heads, d.head_dim).permute(1, 0, 2)[None]) for l in range(d.layers))
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, input_ids=None, pixel_values=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, vision_feature_layer=None, vision_feature_select_strategy=None, labels=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None):
+        eng = self._eng()
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention maps / hidden states are not materialised by the fused path")
+        if past_key_values is not None:
+            raise NotImplementedError("cached single-token steps are driven by .generate()")
+        if inputs_embeds is not None:
+            out = self.language_model(inputs_embeds=inputs_embeds, position_ids=position_ids, use_cache=use_cache)
+            logits, past = out.logits, out.past_key_values
+        else:
+            if input_ids.dim() != 2 or input_ids.shape[0] != 1:
+                raise NotImplementedError("the reference eval path is B = 1, no padding (SURVEY.md App. A.1)")
+            if attention_mask is not None and not bool(attention_mask.all()):
+                raise NotImplementedError("padded prompts are outside the reference's usage (…anyres.py:443-446)")
+            pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
+            ids = input_ids.to(eng.device, non_blocking=True)
+            logits, kv, cu = eng.prefill([(ids[0], pix)], "all", torch.float32, want_kv=bool(use_cache))
+            logits = logits[None]
+            past = self._legacy_cache(kv, cu[-1]) if kv is not None else None
+        loss = None
+        if labels is not None:
+            # shift-by-one CE over the merged sequence; not on the prefill hot path (eval never passes labels)
+            lab = labels.to(logits.device)
+            if lab.shape[1] != logits.shape[1]:
+                raise ValueError("labels must already be expanded to the merged length")
+            loss = torch.nn.functional.cross_entropy(logits[0, :-1].float(), lab[0, 1:], ignore_index=-100)
+        if return_dict is False:
+            return tuple(v for v in (loss, logits, past) if v is not None)
+        return LlavaCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past)
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------ generate (greedy, as the reference calls it)
+    @torch.no_grad()
+    def generate(self, input_ids, pixel_values=None, attention_mask=None, pad_token_id=None, eos_token_id=None,
+                 max_new_tokens: int = 128, use_cache: bool = True, **_):
+        """Greedy decoding; returns LongTensor [1, L_in + n_new] (prompt included, un-expanded — the caller slices
+        `[:, L_in:]`, …anyres.py:453-454).  Prefill emits only the last row's logits (lp_decoder_prefill LAST mode)."""
+        eng = self._eng()
+        if input_ids.dim() != 2 or input_ids.shape[0] != 1:
+            raise NotImplementedError("the reference eval path is B = 1")
+        eos = set()
+        if eos_token_id is not None:
+            eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else {int(eos_token_id)}
+        ids = input_ids.to(eng.device, non_blocking=True)
+        pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
+        from .decode import GreedyDecoder
+        dec = GreedyDecoder(eng)
+        new_tokens = dec.run(ids[0], pix, max_new_tokens, eos)
+        return torch.cat([ids, new_tokens[None]], dim=1)

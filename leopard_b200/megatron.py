@@ -1,0 +1,99 @@
+"""Drop-in for the Megatron plugin surface of the reference (second row) — forward / prefill only.
+
+    model_provider(pre_process=True, post_process=True) -> model         (Pai-Megatron-Patch/examples/llava/
+                                                                          pretrain_megatron_llava.py:37-50)
+    model(tokens, position_ids, attention_mask, images=images) -> logits [b, s, V]
+                                                                         (forward_step :157-158; GPTModel.forward
+                                                                          megatron_patch/model/llava/gpt_model.py:90-113)
+Conventions kept from the reference: image slots are ids == -200, one per feature ROW (169 per crop), crops ordered
+tiles + [global]; ids -100 (padding) read embedding row 0 (vlm_model.py:226); `images` with last dim <= 100 is the
+"no image" dummy (vlm_model.py:518; dummy = zeros(1, 10), pretrain_megatron_llava.py:188); a feature/slot count
+mismatch raises AssertionError with the reference's message (vlm_model.py:528-529).  The attention mask is ignored
+exactly like the flash-attention path of the reference (causal only).  Backward / optimizer (§8f-1) are not part of
+this round: `labels` returns the masked-CE inputs' logits path only via forward(); training raises NotImplementedError.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from .config import LeopardConfig, leopard_llava
+from .engine import PrefillEngine
+from .native_weights import NativeWeights, load_hf, megatron_to_hf
+
+IMAGE_TOKEN_INDEX = -200
+IGNORE_INDEX = -100
+
+_provider_state = {"cfg": None, "getter": None, "device": None}
+
+
+def configure_provider(cfg: Optional[LeopardConfig] = None, hf_getter: Optional[Callable] = None,
+                       megatron_state: Optional[dict] = None, device="cuda"):
+    """What Megatron's `args` + checkpoint loading supply in the reference: the configuration and the weights
+    `model_provider()` should build from.  `megatron_state` is `state['model']['language_model']` flattened to
+    'encoder.layers.0....' keys (TP = 1)."""
+    cfg = cfg or leopard_llava()
+    if megatron_state is not None:
+        hf = megatron_to_hf(cfg, megatron_state)
+        hf_getter = hf.__getitem__
+    _provider_state.update(cfg=cfg, getter=hf_getter, device=device)
+
+
+class GPTModel:
+    """Forward-only native stand-in for megatron_patch.model.llava.gpt_model.GPTModel."""
+
+    def __init__(self, cfg: LeopardConfig, native: NativeWeights, pre_process=True, post_process=True):
+        if not (pre_process and post_process):
+            raise NotImplementedError("pipeline parallel stages are out of scope (the reference runs PP = 1)")
+        self.cfg = cfg
+        self.engine = PrefillEngine(cfg, native)
+        self.input_tensor = None
+
+    def set_input_tensor(self, t):  # gpt_model.py:86-88
+        self.input_tensor = t
+
+    @torch.no_grad()
+    def forward(self, input_ids, position_ids=None, attention_mask=None, retriever_input_ids=None,
+                retriever_position_ids=None, retriever_attn_mask=None, labels=None, tokentype_ids=None,
+                inference_params=None, images=None):
+        if labels is not None:
+            raise NotImplementedError("loss / backward (SURVEY.md §8f-1) is not part of the prefill path yet")
+        eng = self.engine
+        b, s = input_ids.shape
+        has_img = images is not None and images.shape[-1] > 100  # vlm_model.py:518
+        feats = None
+        if has_img:
+            feats = eng.image_features(images.to(eng.device)).reshape(-1, self.cfg.dec.hidden)
+        n_slots = int((input_ids == IMAGE_TOKEN_INDEX).sum())
+        n_feat = 0 if feats is None else feats.shape[0]
+        if has_img:
+            assert n_feat == n_slots, \
+                f"The number of image features doesn't match the number of image tokens. {n_feat} != {n_slots}"
+        ids = input_ids.to(eng.device)
+        x = torch.empty((b * s, self.cfg.dec.hidden), dtype=torch.bfloat16, device=eng.device)
+        f0 = 0
+        for i in range(b):  # features are consumed in row-major [b, s] order (vlm_model.py:531-533)
+            k = int((ids[i] == IMAGE_TOKEN_INDEX).sum()) if has_img else 0
+            row_ids = ids[i] if has_img else ids[i].clamp(min=0)
+            eng.merge(row_ids, feats[f0:f0 + k] if k else None, IMAGE_TOKEN_INDEX, 1, out=x[i * s:(i + 1) * s])
+            f0 += k
+        if position_ids is None:
+            pos = torch.arange(s, device=eng.device, dtype=torch.int32).repeat(b)
+        else:
+            pos = position_ids.reshape(-1)
+        logits, _ = eng.decoder(x, pos, [i * s for i in range(b + 1)], "all", torch.bfloat16)
+        return logits.view(b, s, -1)
+
+    __call__ = forward
+
+
+def model_provider(pre_process=True, post_process=True):
+    """Same signature as examples/llava/pretrain_megatron_llava.py:37-50."""
+    st = _provider_state
+    if st["getter"] is None:
+        raise _lib.NativeError("model_provider(): call configure_provider(...) first (Megatron's args/checkpoint "
+                               "plumbing is outside the hot path)")
+    native = load_hf(st["cfg"], st["getter"], st["device"])
+    return GPTModel(st["cfg"], native, pre_process, post_process)
