@@ -47,7 +47,7 @@ int lp_abi_version(void);
  *   (res_row_mod = 676 adds the ViT position embedding, idefics_vision_tower.py:147-150).  residual may alias C.
  * act == LP_ACT_SWIGLU: W rows are interleaved in 32-row granules [gate_0..31, up_0..31, gate_32..63, ...] and the
  *   output has N' = N/2 columns; otherwise N' = N.
- * block_n: 128, 256, or 0 = choose.  Requires N % 8 == 0, lda/ldw % 8 == 0, 16-byte aligned bases. */
+ * block_n: 128, 160, 192, 224, 256, or 0 = choose (wave-quantisation heuristic).  Requires N % 8 == 0, lda/ldw % 8 == 0, 16-byte aligned bases. */
 int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
                  int K, const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
                  int block_n, void* stream);
@@ -60,7 +60,8 @@ int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, voi
  *   v likewise from v_off.  Supported (head_dim, head_stride): (128,128) and (72,80) — the latter expects the 8 pad
  *   columns of q and k to be exact zeros (the ViT qkv weight is stored zero-padded).
  * out: bf16 [B*T, ldo], head h at cols h*head_dim.  scale = head_dim^-0.5 in the reference.
- * variant bit 0: keep P in TMEM (tcgen05.mma A-from-TMEM) instead of shared memory. */
+ * variant bit 0: keep P in TMEM (tcgen05.mma A-from-TMEM) instead of shared memory (one-tile kernel);
+ * variant bit 1: two 128-row query tiles per CTA ping-ponged on the tensor pipe (P always in TMEM). */
 int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, int n_kv_heads, int head_dim,
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);

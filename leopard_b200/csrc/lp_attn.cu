@@ -28,15 +28,6 @@ constexpr int ATT_BN = 128;  // kv rows per tile
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_BOX_BYTES = 128 * 128;  // one TMA box: 128 rows x 64 bf16
 
-struct AttnArgs {
-  int T, B, n_heads, group;
-  int q_off, k_off, v_off, hs;
-  int dh_out;
-  bf16* O;
-  long long ldo;
-  float scale_log2;
-};
-
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -378,6 +369,11 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
   int rc = make_tmap_bf16_3d(&tm, qkv, (uint64_t)ld, (uint64_t)T, (uint64_t)B, (uint64_t)ld, (uint64_t)T * ld, 64,
                              128, 1);
   if (rc) return rc;
+  if (variant & 2) {  // two query tiles per CTA (lp_attn2.cu)
+    ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
+    note_launch();
+    return launch_attn2(tm, a, head_dim, causal, stream);
+  }
   const bool ptm = (variant & 1) != 0;
   ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
   note_launch();

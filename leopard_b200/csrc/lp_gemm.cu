@@ -15,7 +15,11 @@
 //   warp 0      TMA producer   : cp.async.bulk.tensor A/W k-blocks -> 128B-swizzled smem ring (STAGES deep)
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered
 //                                TMEM accumulator (2 x BN columns), tcgen05.commit frees smem / signals epilogue
-//   warps 2-5   epilogue       : tcgen05.ld accumulator rows -> bias / activation / residual -> 16-byte stores
+//   warps 2-9   epilogue       : two warpgroups split the tile's columns; tcgen05.ld accumulator rows -> bias /
+//                                activation / residual -> 16-byte stores
+// Tiles are rasterised in groups of `group_m` row-blocks so that whichever operand does not fit the 126 MB L2
+// is streamed from HBM once (host heuristic), and the tile width BN in {128,160,192,224,256} is chosen per problem
+// to minimise wave quantisation (ceil(tiles / SMs) * BN).
 // Ragged M, N, K are handled by TMA zero fill on loads and predication on stores.
 #include "lp_common.cuh"
 #include "lp_host.h"
@@ -25,7 +29,8 @@ namespace lp {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_THREADS = 256;
 
 struct GemmArgs {
   int M, N, K;
@@ -38,6 +43,7 @@ struct GemmArgs {
   int res_row_mod;
   int act;
   int num_m_blk, num_n_blk, num_k_blk;
+  int group_m;
 };
 
 template <int BN, int STAGES>
@@ -50,7 +56,17 @@ struct GemmSmem {
   static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;  // +1024: manual 1 KiB alignment of the base
 };
 
-__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// tile index -> (m_blk, n_blk): groups of `group_m` row-blocks, row-block fastest inside a group
+__device__ __forceinline__ void tile_coords(const GemmArgs& a, int tile, int& m_blk, int& n_blk) {
+  const int per_group = a.group_m * a.num_n_blk;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int m0 = g * a.group_m;
+  const int gsz = min(a.group_m, a.num_m_blk - m0);
+  n_blk = r / gsz;
+  m_blk = m0 + (r - n_blk * gsz);
+}
 
 // applies bias/activation/residual to 32 accumulator columns of one row and stores them
 __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& args, float* v, const float* bias_s, int row,
@@ -64,7 +80,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& args, float
   }
   if (args.act == LP_ACT_GELU_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
   } else if (args.act == LP_ACT_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
@@ -111,6 +127,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs args) {
   using L = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256u : 512u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -132,12 +149,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -153,7 +170,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % args.num_m_blk, n_blk = tile / args.num_m_blk;
+        int m_blk, n_blk;
+        tile_coords(args, tile, m_blk, n_blk);
         for (int kb = 0; kb < args.num_k_blk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -195,18 +213,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int lg = warp & 3;  // TMEM lane quarter this warp may read
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int lg = warp & 3;            // TMEM lane quarter this warp may read
+    const int wg = (warp - 2) >> 2;     // warpgroup 0 / 1: first / second part of the tile's columns
     const int et = threadIdx.x - 64;
     int as = 0;
     uint32_t aphase = 0;
     const bool swiglu = args.act == LP_ACT_SWIGLU;
+    constexpr int NC = BN / 32;         // 32-column chunks per tile
+    constexpr int NP = BN / 64;         // 64-column gate/up pairs per tile
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % args.num_m_blk, n_blk = tile / args.num_m_blk;
+      int m_blk, n_blk;
+      tile_coords(args, tile, m_blk, n_blk);
       const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
       float* bs = bias_smem + as * BN;
       if (args.bias) {
-        for (int i = et; i < BN; i += 128) bs[i] = (n0 + i < args.N) ? args.bias[n0 + i] : 0.f;
+        for (int i = et; i < BN; i += GEMM_EPI_THREADS) bs[i] = (n0 + i < args.N) ? args.bias[n0 + i] : 0.f;
       }
       epi_named_barrier();
       mbar_wait(&tfull_bar[as], aphase);
@@ -216,8 +238,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
       if (!swiglu) {
+        const int c_begin = wg == 0 ? 0 : (NC + 1) / 2, c_end = wg == 0 ? (NC + 1) / 2 : NC;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= args.N) break;
           uint32_t r[32];
@@ -230,8 +253,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
         // columns are interleaved in 32-wide granules [gate | up | gate | up ...]; output has N/2 columns
+        const int c_begin = wg == 0 ? 0 : (NP + 1) / 2, c_end = wg == 0 ? (NP + 1) / 2 : NP;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int col0 = n0 + c * 64;
           if (col0 >= args.N) break;
           uint32_t rg[32], ru[32];
@@ -263,7 +287,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -302,15 +326,24 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
              "lp_gemm_bf16: residual must be 16-byte aligned with ldr %% 8 == 0");
   LP_REQUIRE(act >= LP_ACT_NONE && act <= LP_ACT_SWIGLU, "lp_gemm_bf16: bad act %d", act);
   LP_REQUIRE(act != LP_ACT_SWIGLU || N % 64 == 0, "lp_gemm_bf16: SwiGLU needs N %% 64 == 0 (32-wide gate/up granules)");
+  const int sms = sm_count();
+  const long long mb = (M + GEMM_BM - 1) / GEMM_BM;
   if (block_n == 0) {
-    // wave-quantisation heuristic: pick the tile width with the smaller ceil(tiles / SMs) * tile cost
-    const int sms = sm_count();
-    const long long mb = (M + GEMM_BM - 1) / GEMM_BM;
-    const long long t256 = mb * ((N + 255) / 256), t128 = mb * ((N + 127) / 128);
-    const long long c256 = ((t256 + sms - 1) / sms) * 2, c128 = ((t128 + sms - 1) / sms) * 1;
-    block_n = (c128 < c256) ? 128 : 256;
+    // wave-quantisation heuristic: minimise ceil(tiles / SMs) * (BN + per-tile overhead); the narrow tiles are
+    // shared-memory-bandwidth bound on one CTA (A 4 KiB + B BN*32 B per K=16 step), hence their penalty
+    const int cand[5] = {256, 224, 192, 160, 128};
+    const double pen[5] = {1.0, 1.0, 1.02, 1.08, 1.25};
+    double best = 1e30;
+    for (int i = 0; i < 5; ++i) {
+      if (act == LP_ACT_SWIGLU && cand[i] % 64 != 0) continue;
+      const long long tiles = mb * ((N + cand[i] - 1) / cand[i]);
+      const double cost = (double)((tiles + sms - 1) / sms) * (cand[i] + 12) * pen[i];
+      if (cost < best) { best = cost; block_n = cand[i]; }
+    }
   }
-  LP_REQUIRE(block_n == 128 || block_n == 256, "lp_gemm_bf16: block_n must be 0, 128 or 256");
+  LP_REQUIRE(block_n == 128 || block_n == 160 || block_n == 192 || block_n == 224 || block_n == 256,
+             "lp_gemm_bf16: block_n must be 0, 128, 160, 192, 224 or 256");
+  LP_REQUIRE(act != LP_ACT_SWIGLU || block_n % 64 == 0, "lp_gemm_bf16: SwiGLU needs block_n %% 64 == 0");
 
   GemmArgs args;
   args.M = M; args.N = N; args.K = K;
@@ -322,6 +355,15 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   args.num_m_blk = (M + GEMM_BM - 1) / GEMM_BM;
   args.num_n_blk = (N + block_n - 1) / block_n;
   args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+  {
+    // L2-aware rasterisation: keep the operand that fits L2 resident, stream the other from HBM once
+    const double l2_budget = 56e6;
+    const double a_bytes = 2.0 * M * K, w_bytes = 2.0 * N * K;
+    if (a_bytes <= l2_budget) args.group_m = args.num_m_blk;                 // A resident, W tiles read once
+    else if (w_bytes <= l2_budget) args.group_m = max(1, sms / args.num_n_blk);  // W resident, A read once
+    else args.group_m = 16;
+    if (args.group_m > args.num_m_blk) args.group_m = args.num_m_blk;
+  }
 
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
@@ -330,6 +372,11 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   if (rc) return rc;
   ProfScope prof(1, M, N, K, stream);
   note_launch();
-  if (block_n == 256) return launch_gemm<256, 4>(tmA, tmB, args, stream);
-  return launch_gemm<128, 6>(tmA, tmB, args, stream);
+  switch (block_n) {
+    case 256: return launch_gemm<256, 4>(tmA, tmB, args, stream);
+    case 224: return launch_gemm<224, 5>(tmA, tmB, args, stream);
+    case 192: return launch_gemm<192, 5>(tmA, tmB, args, stream);
+    case 160: return launch_gemm<160, 6>(tmA, tmB, args, stream);
+    default: return launch_gemm<128, 6>(tmA, tmB, args, stream);
+  }
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace lp {
@@ -37,6 +38,17 @@ struct ProfScope {
   ProfScope(int kind, int a, int b, int c, cudaStream_t s);
   ~ProfScope();
 };
+
+// attention launch arguments (shared by lp_attn.cu and lp_attn2.cu)
+struct AttnArgs {
+  int T, B, n_heads, group;
+  int q_off, k_off, v_off, hs;
+  int dh_out;
+  __nv_bfloat16* O;
+  long long ldo;
+  float scale_log2;
+};
+int launch_attn2(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, cudaStream_t stream);
 
 // 2-D / 3-D bf16 tensor maps with 128B swizzle (inner box = 64 elements = 128 B), zero OOB fill.
 // dims/strides are innermost-first; strides are in ELEMENTS for dims >= 1.

@@ -1,0 +1,143 @@
+"""not gpu: host-side logic — weight-layout conversions, native re-layout (pure data movement), DP sharding over a
+world_size-2 gloo group, bench workload bookkeeping."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from leopard_b200 import dp
+from leopard_b200.config import leopard_llava, reduced
+from leopard_b200.native_weights import HEAD_STRIDE, PATCH_K_PAD, hf_to_megatron, load_hf, megatron_to_hf
+from leopard_b200.weights import SyntheticCheckpoint, tensor_specs
+
+
+def tiny_cfg():
+    return reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=512)
+
+
+def test_megatron_hf_roundtrip_and_group_interleave():
+    cfg = tiny_cfg()
+    ck = SyntheticCheckpoint(cfg)
+    meg = hf_to_megatron(cfg, lambda n: ck[n])
+    back = megatron_to_hf(cfg, meg)
+    for name, _, _ in tensor_specs(cfg):
+        assert torch.equal(back[name], ck[name]), name
+    # fused QKV rows are grouped per kv head: [4 q heads | k | v] (transformer.py:713-738)
+    qkv = meg["encoder.layers.0.self_attention.query_key_value.weight"]
+    assert qkv.shape == ((32 + 16) * 128, 4096)
+    q = ck["language_model.model.layers.0.self_attn.q_proj.weight"]
+    k = ck["language_model.model.layers.0.self_attn.k_proj.weight"]
+    g = 3
+    assert torch.equal(qkv[g * 768: g * 768 + 512], q[g * 512:(g + 1) * 512])
+    assert torch.equal(qkv[g * 768 + 512: g * 768 + 640], k[g * 128:(g + 1) * 128])
+    h4 = meg["encoder.layers.0.mlp.dense_h_to_4h.weight"]
+    assert torch.equal(h4[:14336], ck["language_model.model.layers.0.mlp.gate_proj.weight"])
+    # ViT qkv interleave [head, (q,k,v), 72]
+    vq = meg["vision_tower.transformer.layers.0.self_attention.linear_qkv.weight"].view(16, 3, 72, 1152)
+    assert torch.equal(vq[5, 1], ck["vision_tower.vision_model.encoder.layers.0.self_attn.k_proj.weight"][5 * 72:6 * 72])
+
+
+def test_native_layout_is_pure_relayout():
+    cfg = tiny_cfg()
+    ck = SyntheticCheckpoint(cfg)
+    nw = load_hf(cfg, lambda n: ck[n], "cpu")
+    tensors = {t.data_ptr(): t for t in nw._keep}
+    L = nw.vit_layers[0]
+    qkv = tensors[L.qkv_w]
+    assert qkv.shape == (3 * 16 * HEAD_STRIDE, 1152)
+    k = ck["vision_tower.vision_model.encoder.layers.0.self_attn.k_proj.weight"]
+    blk = qkv[16 * HEAD_STRIDE:2 * 16 * HEAD_STRIDE].view(16, HEAD_STRIDE, 1152)
+    assert torch.equal(blk[:, :72].reshape(1152, 1152), k) and bool((blk[:, 72:] == 0).all())
+    qb = tensors[L.qkv_b].view(3, 16, HEAD_STRIDE)
+    assert bool((qb[:, :, 72:] == 0).all())
+    pw = tensors[nw.vit.patch_w]
+    assert pw.shape == (1152, PATCH_K_PAD) and bool((pw[:, 588:] == 0).all())
+    D = nw.dec_layers[0]
+    gu = tensors[D.gateup_w].view(14336 // 32, 2, 32, 4096)
+    assert torch.equal(gu[:, 0].reshape(14336, 4096), ck["language_model.model.layers.0.mlp.gate_proj.weight"])
+    assert torch.equal(gu[:, 1].reshape(14336, 4096), ck["language_model.model.layers.0.mlp.up_proj.weight"])
+    qkvd = tensors[D.qkv_w]
+    assert qkvd.shape == (6144, 4096)
+    assert torch.equal(qkvd[4096:5120], ck["language_model.model.layers.0.self_attn.k_proj.weight"])
+    assert nw.vocab_padded == 512
+
+
+def test_vocab_padding_for_mistral():
+    from dataclasses import replace
+    from leopard_b200.config import leopard_idefics2_decoder
+    cfg = tiny_cfg()
+    cfg = replace(cfg, dec=replace(leopard_idefics2_decoder(), layers=1, vocab=1003), image_token_index=1001)
+    ck = SyntheticCheckpoint(cfg)
+    nw = load_hf(cfg, lambda n: ck[n], "cpu")
+    assert nw.vocab_padded == 1008
+
+
+def test_assignment_is_balanced_and_deterministic():
+    costs = [dp.request_cost(n, 64 + 169 * n) for n in [50, 1, 1, 28, 17, 3, 3, 40, 9, 9, 2, 30]]
+    bins = dp.assign(costs, 4)
+    assert sorted(i for b in bins for i in b) == list(range(12))
+    loads = [sum(costs[i] for i in b) for b in bins]
+    assert max(loads) / (sum(loads) / 4) < 1.15
+    naive = [sum(costs[i] for i in b) for b in dp.contiguous(12, 4)]
+    assert max(loads) < max(naive)
+    assert dp.assign(costs, 4) == bins
+    assert dp.contiguous(10, 4) == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9]]
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        reqs = None
+        n_req = 5
+        if rank == 0:
+            reqs = []
+            for k, n in enumerate([3, 0, 1, 2, 1]):
+                ids = torch.randint(0, 1000, (10 + k,), generator=g)
+                pix = None if n == 0 else torch.randn(n, 3, 4, 4, generator=g)
+                reqs.append((ids, pix))
+        local, mine = dp.scatter_requests(reqs, "cpu", src=0)
+        # stand-in for the per-request result: [sum(ids), n_crops, pixel checksum]
+        res = torch.tensor([[float(i.sum()), 0.0 if p is None else float(p.shape[0]),
+                             0.0 if p is None else float(p.sum())] for i, p in local]).reshape(len(local), 3)
+        allres = dp.gather_results(res, mine, n_req)
+        q.put((rank, mine, allres))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_scatter_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got.sort(key=lambda t: t[0])
+    (r0, m0, a0), (r1, m1, a1) = got
+    assert sorted(m0 + m1) == [0, 1, 2, 3, 4] and m0 and m1
+    assert torch.equal(a0, a1)
+    g = torch.Generator().manual_seed(0)
+    for k, n in enumerate([3, 0, 1, 2, 1]):
+        ids = torch.randint(0, 1000, (10 + k,), generator=g)
+        pix = None if n == 0 else torch.randn(n, 3, 4, 4, generator=g)
+        assert float(a0[k, 0]) == float(ids.sum()) and float(a0[k, 1]) == float(n)
+        if pix is not None:
+            assert abs(float(a0[k, 2]) - float(pix.sum())) < 1e-4
+
+
+def test_bench_workload_bookkeeping():
+    import bench
+    cfg = leopard_llava()
+    pix, ids, n_crops, S, per_image = bench.make_workload(cfg)
+    assert per_image == [7, 7, 7, 7] and n_crops == 28 and S == 4796 and ids.shape == (1, 92)
+    assert pix.shape == (28, 3, 364, 364) and float(pix.min()) >= -1 and float(pix.max()) <= 1
+    fm = bench.flops_model(n_crops, S, cfg)
+    assert abs(fm["total"] / 1e12 - 90.5) < 0.3  # 90.5 TFLOP per cfg3 request

@@ -39,6 +39,30 @@ CASES = {
     "vitbig_fc1": (18928, 4304, 1152, True, 1, False, 0, False, 256),
     "vitbig_fc2": (18928, 1152, 4304, True, 0, True, 0, False, 0),
     "lm_head": (64, 128256, 4096, False, 0, False, 0, True, 0),
+    # --- bench shapes (cfg3): ViT M = 28*676, decoder M = 4796; block_n sweeps
+    "v_patch": (18928, 1152, 592, True, 0, True, 676, False, 0),
+    "v_qkv": (18928, 3840, 1152, True, 0, False, 0, False, 0),
+    "v_out": (18928, 1152, 1152, True, 0, True, 0, False, 0),
+    "v_out_256": (18928, 1152, 1152, True, 0, True, 0, False, 256),
+    "v_fc1": (18928, 4304, 1152, True, 1, False, 0, False, 0),
+    "v_fc2": (18928, 1152, 4304, True, 0, True, 0, False, 0),
+    "v_fc2_256": (18928, 1152, 4304, True, 0, True, 0, False, 256),
+    "p_1": (4732, 4096, 4608, True, 2, False, 0, False, 0),
+    "d_qkv": (4796, 6144, 4096, False, 0, False, 0, False, 0),
+    "d_qkv_192": (4796, 6144, 4096, False, 0, False, 0, False, 192),
+    "d_o": (4796, 4096, 4096, False, 0, True, 0, False, 0),
+    "d_o_256": (4796, 4096, 4096, False, 0, True, 0, False, 256),
+    "d_o_160": (4796, 4096, 4096, False, 0, True, 0, False, 160),
+    "d_gateup": (4796, 28672, 4096, False, 3, False, 0, False, 0),
+    "d_gateup_192": (4796, 28672, 4096, False, 3, False, 0, False, 192),
+    "d_down": (4796, 4096, 14336, False, 0, True, 0, False, 0),
+    "d_down_256": (4796, 4096, 14336, False, 0, True, 0, False, 256),
+    "d_down_160": (4796, 4096, 14336, False, 0, True, 0, False, 160),
+    "r224": (300, 520, 1160, True, 0, True, 0, False, 224),
+    "r192": (300, 520, 1160, True, 1, True, 0, False, 192),
+    "r160": (300, 520, 1160, True, 2, True, 0, False, 160),
+    "sw192": (300, 1152, 1160, True, 3, False, 0, False, 192),
+    "sw128": (300, 1152, 1160, True, 3, True, 0, False, 128),
 }
 
 
