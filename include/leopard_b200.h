@@ -66,6 +66,15 @@ int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, i
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);
 
+/* Cross-attention with separate query and key/value buffers, non-causal (Idefics2 perceiver resampler: 64 latent
+ * queries attend to concat(context, latents); MP/model/idefics2/perceiver_transformer.py:582-706, flash-varlen call
+ * :347-420; HF Idefics2PerceiverAttention).  q: bf16 [B*Tq, ldq], head h at cols h*head_dim; kv: bf16 [B*Tk, ldkv],
+ * k of kv-head g at cols k_off + g*head_dim, v at v_off + g*head_dim.  head_dim 96 or 128, Tq <= 128 per tile row
+ * block (any Tq works; rows are tiled by 128).  out: bf16 [B*Tq, ldo]. */
+int lp_attention_cross(const void* q, long long ldq, const void* kv, long long ldkv, int B, int Tq, int Tk, int n_heads,
+                       int n_kv_heads, int head_dim, int k_off, int v_off, float scale, void* out, long long ldo,
+                       void* stream);
+
 /* out = LayerNorm(x) * gamma + beta, eps inside rsqrt; one row per CTA, fp32 statistics (two-pass).
  *   SigLIP layer_norm1/2 and post_layernorm / ln_post (MP/model/idefics2/idefics_vision_tower.py:77-81,176).
  * shuffle_side = 26 additionally applies Leopard's pixel_shuffle (EV/llava_multiimg_siglip_anyres.py:165-176 ==
@@ -181,6 +190,14 @@ enum lp_logits_mode { LP_LOGITS_NONE = 0, LP_LOGITS_LAST = 1, LP_LOGITS_ALL = 2 
 size_t lp_vit_workspace_bytes(const lp_vit_dims* dims, int N);
 int lp_vit_forward(const lp_vit_dims* dims, const lp_vit_weights* w, const void* pixels, int pixels_fp32, int N,
                    void* out, long long ldo, int shuffle, void* workspace, size_t ws_bytes, void* stream);
+
+/* Encoder layers + ln_post on an ALREADY EMBEDDED residual stream x [R, hidden] (overwritten) that packs n_seqs images
+ * of different lengths (rows cu_seqlens_host[s] .. cu_seqlens_host[s+1]-1): the NaViT / Idefics2 tower
+ * (MP/model/idefics2/idefics_vision_tower.py:152-178).  Padded patches are removed by the caller instead of masked —
+ * the result on valid patches is identical to the reference's key-padding mask.  out: bf16 [R, hidden]. */
+size_t lp_vit_layers_workspace_bytes(const lp_vit_dims* dims, int total_rows);
+int lp_vit_layers(const lp_vit_dims* dims, const lp_vit_weights* w, void* x, const int* cu_seqlens_host, int n_seqs,
+                  void* out, long long ldo, void* workspace, size_t ws_bytes, void* stream);
 
 /* linear_2(act(linear_1(x))) on shuffled rows [rows, in_dim] -> [rows, hidden]
  *   (myLlavaMultiModalProjector.forward EV/...anyres.py:187-192; Megatron MultimodalProjector

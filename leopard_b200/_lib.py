@@ -64,6 +64,7 @@ _SIGS = {
     "lp_abi_version": (_i, []),
     "lp_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "lp_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _i, _vp]),
+    "lp_attention_cross": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
     "lp_layernorm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
     "lp_rmsnorm": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _vp]),
     "lp_rope_table": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
@@ -73,6 +74,8 @@ _SIGS = {
     "lp_pixel_shuffle": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "lp_vit_workspace_bytes": (_sz, [_P(VitDims), _i]),
     "lp_vit_forward": (_i, [_P(VitDims), _P(VitWeights), _vp, _i, _i, _vp, _ll, _i, _vp, _sz, _vp]),
+    "lp_vit_layers_workspace_bytes": (_sz, [_P(VitDims), _i]),
+    "lp_vit_layers": (_i, [_P(VitDims), _P(VitWeights), _vp, _P(_i), _i, _vp, _ll, _vp, _sz, _vp]),
     "lp_project_workspace_bytes": (_sz, [_i, _i]),
     "lp_project": (_i, [_P(ProjWeights), _vp, _i, _i, _i, _vp, _ll, _vp, _sz, _vp]),
     "lp_decoder_workspace_bytes": (_sz, [_P(DecDims), _i, _i]),

@@ -82,6 +82,42 @@ class LeopardConfig:
         return self.vit.hidden * self.shuffle * self.shuffle  # 4608
 
 
+@dataclass(frozen=True)
+class PerceiverConfig:
+    """Idefics2 perceiver resampler (Pai-Megatron-Patch/megatron_patch/model/idefics2/perceiver_transformer.py:1243-1723;
+    HF Idefics2PerceiverConfig): 64 latents, 3 layers, 16 q / 4 kv heads x 96, gated MLP 4096 -> 16384 -> 4096."""
+    latents: int = 64
+    depth: int = 3
+    heads: int = 16
+    kv_heads: int = 4
+    head_dim: int = 96
+    hidden: int = 4096
+    ffn: int = 16384
+    eps: float = 1e-6
+
+
+@dataclass(frozen=True)
+class Idefics2Config:
+    """Leopard-Idefics2 = NaViT SigLIP tower (<= 980 px, 70 x 70 position table) + modality projection (gated MLP
+    1152 -> 14336 -> 4096) + perceiver + Mistral-7B (EX/idefics2/train_multiimg_idefics2.sh:93-98,234,239)."""
+    vit: VitConfig = field(default_factory=lambda: VitConfig(image_size=980))
+    perceiver: PerceiverConfig = field(default_factory=PerceiverConfig)
+    dec: DecoderConfig = field(default_factory=lambda: DecoderConfig(vocab=32003, rope_theta=10000.0, rope_scaling=None))
+    modality_ffn: int = 14336
+    image_token_id: int = 32001
+
+
+def leopard_idefics2() -> Idefics2Config:
+    return Idefics2Config()
+
+
+def reduced_idefics2(cfg: Idefics2Config, vit_layers: int, perceiver_depth: int, dec_layers: int,
+                     vocab: Optional[int] = None) -> Idefics2Config:
+    dec = replace(cfg.dec, layers=dec_layers, vocab=vocab or cfg.dec.vocab)
+    return replace(cfg, vit=replace(cfg.vit, layers=vit_layers), perceiver=replace(cfg.perceiver, depth=perceiver_depth),
+                   dec=dec, image_token_id=min(cfg.image_token_id, dec.vocab - 2))
+
+
 def leopard_llava() -> LeopardConfig:
     return LeopardConfig()
 

@@ -37,7 +37,8 @@ __device__ __forceinline__ void softmax_named_barrier() { asm volatile("bar.sync
 
 template <int DH, bool CAUSAL, bool P_TMEM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQKV,
+                const AttnArgs args) {
   constexpr int NB = (DH + 63) / 64;   // 64-column TMA boxes per head
   constexpr int KS_QK = DH / 16;       // K=16 steps of S = Q K^T
   constexpr int KS_PV = ATT_BN / 16;   // K=16 steps of O += P V
@@ -69,11 +70,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) 
   const int batch = blockIdx.z;
   const int kv_head = head / args.group;
   const int q0 = q_tile * ATT_BM;
-  const int T = args.T;
+  const int T = args.Tk;   // key/value length (masks, tile count)
+  const int Tq = args.T;   // query length (output rows)
   int n_kv = (T + ATT_BN - 1) / ATT_BN;
   if (CAUSAL) n_kv = min(n_kv, q_tile + 1);
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -102,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) 
       mbar_arrive_expect_tx(q_full, HEAD_BYTES);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
-        tma_load_3d(smem + Q_OFF + b * ATT_BOX_BYTES, &tmQKV, q_full, args.q_off + head * args.hs + b * 64, q0, batch);
+        tma_load_3d(smem + Q_OFF + b * ATT_BOX_BYTES, &tmQ, q_full, args.q_off + head * args.hs + b * 64, q0, batch);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
@@ -294,8 +297,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) 
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
-    const bool row_ok = q_idx < T;
-    bf16* op = args.O + ((long long)batch * T + q_idx) * args.ldo + (long long)head * args.dh_out;
+    const bool row_ok = q_idx < Tq;
+    bf16* op = args.O + ((long long)batch * Tq + q_idx) * args.ldo + (long long)head * args.dh_out;
 #pragma unroll 1
     for (int c = 0; c < DH / 16; ++c) {
       uint32_t o[16];
@@ -326,7 +329,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) 
 }
 
 template <int DH, bool CAUSAL, bool P_TMEM>
-static int launch_attn(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream) {
+static int launch_attn(const CUtensorMap& tmq, const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream) {
   constexpr int NB = (DH + 63) / 64;
   constexpr int SMEM = 5 * NB * ATT_BOX_BYTES + (P_TMEM ? 0 : 2 * ATT_BOX_BYTES) + 256 + 1024;
   auto kern = attn_fwd_kernel<DH, CAUSAL, P_TMEM>;
@@ -336,7 +339,7 @@ static int launch_attn(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t st
     configured = true;
   }
   dim3 grid((a.T + ATT_BM - 1) / ATT_BM, a.n_heads, a.B);
-  kern<<<grid, ATT_THREADS, SMEM, stream>>>(tm, a);
+  kern<<<grid, ATT_THREADS, SMEM, stream>>>(tmq, tm, a);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -359,7 +362,7 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
   LP_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "lp_attention_fwd: qkv/out must be 16-byte aligned");
   AttnArgs a;
-  a.T = T; a.B = B; a.n_heads = n_heads; a.group = n_heads / n_kv_heads;
+  a.T = T; a.Tk = T; a.B = B; a.n_heads = n_heads; a.group = n_heads / n_kv_heads;
   a.q_off = q_off; a.k_off = k_off; a.v_off = v_off; a.hs = head_stride;
   a.dh_out = head_dim;
   a.O = reinterpret_cast<bf16*>(out);
@@ -379,8 +382,42 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
   note_launch();
   if (head_dim == 72) {
     LP_REQUIRE(!causal, "lp_attention_fwd: head_dim 72 is the (non-causal) ViT configuration");
-    return ptm ? launch_attn<80, false, true>(tm, a, stream) : launch_attn<80, false, false>(tm, a, stream);
+    return ptm ? launch_attn<80, false, true>(tm, tm, a, stream) : launch_attn<80, false, false>(tm, tm, a, stream);
   }
-  if (causal) return ptm ? launch_attn<128, true, true>(tm, a, stream) : launch_attn<128, true, false>(tm, a, stream);
-  return ptm ? launch_attn<128, false, true>(tm, a, stream) : launch_attn<128, false, false>(tm, a, stream);
+  if (causal)
+    return ptm ? launch_attn<128, true, true>(tm, tm, a, stream) : launch_attn<128, true, false>(tm, tm, a, stream);
+  return ptm ? launch_attn<128, false, true>(tm, tm, a, stream) : launch_attn<128, false, false>(tm, tm, a, stream);
+}
+
+// Cross-attention with separate query / key-value buffers (Idefics2 perceiver: 64 latent queries over
+// concat(context, latents); megatron_patch/model/idefics2/perceiver_transformer.py:582-706): non-causal, one q tile.
+extern "C" int lp_attention_cross(const void* q, long long ldq, const void* kv, long long ldkv, int B, int Tq, int Tk,
+                                  int n_heads, int n_kv_heads, int head_dim, int k_off, int v_off, float scale,
+                                  void* out, long long ldo, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(B > 0 && Tq > 0 && Tk > 0 && n_heads > 0 && n_kv_heads > 0 && n_heads % n_kv_heads == 0,
+             "lp_attention_cross: bad sizes B=%d Tq=%d Tk=%d heads=%d/%d", B, Tq, Tk, n_heads, n_kv_heads);
+  LP_REQUIRE(head_dim == 96 || head_dim == 128, "lp_attention_cross: head_dim must be 96 or 128 (got %d)", head_dim);
+  LP_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+             "lp_attention_cross: strides/offsets must be multiples of 8 elements");
+  LP_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "lp_attention_cross: q/kv/out must be 16-byte aligned");
+  AttnArgs a;
+  a.T = Tq; a.Tk = Tk; a.B = B; a.n_heads = n_heads; a.group = n_heads / n_kv_heads;
+  a.q_off = 0; a.k_off = k_off; a.v_off = v_off; a.hs = head_dim;
+  a.dh_out = head_dim;
+  a.O = reinterpret_cast<bf16*>(out);
+  a.ldo = ldo;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  CUtensorMap tq, tkv;
+  int rc = make_tmap_bf16_3d(&tq, q, (uint64_t)ldq, (uint64_t)Tq, (uint64_t)B, (uint64_t)ldq, (uint64_t)Tq * ldq, 64, 128, 1);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tkv, kv, (uint64_t)ldkv, (uint64_t)Tk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Tk * ldkv, 64, 128,
+                         1);
+  if (rc) return rc;
+  ProfScope prof(2, B, Tk, n_heads * 1000 + head_dim, stream);
+  note_launch();
+  if (head_dim == 96) return launch_attn<96, false, true>(tq, tkv, a, stream);
+  return launch_attn<128, false, true>(tq, tkv, a, stream);
 }

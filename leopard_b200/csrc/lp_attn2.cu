@@ -67,7 +67,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   const int qp = (int)gridDim.x - 1 - (int)blockIdx.x;  // heavy (late) causal pairs first
   const int head = blockIdx.y, batch = blockIdx.z;
   const int kv_head = head / args.group;
-  const int T = args.T;
+  const int T = args.T;  // self-attention only: Tk == T
   const int q0A = qp * 256, q0B = q0A + 128;
   const int n_total = (T + 127) / 128;
   const bool actB = q0B < T;

@@ -53,7 +53,9 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;  // +1024: manual 1 KiB alignment of the base
+  static constexpr int STAGE_OUT_OFF = (BIAS_OFF + 2 * BN * 4 + 1023) & ~1023;  // 8 warps x 2 KiB output staging
+  static constexpr int TOTAL = STAGE_OUT_OFF + 8 * 2048 + 1024;  // +1024: manual 1 KiB alignment of the base
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
 __device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -122,10 +124,90 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& args, float
   }
 }
 
+// ---- staged epilogue (bf16 outputs) ------------------------------------------------------------------------------
+// Each epilogue warp owns a 32-row x 32-column bf16 staging tile (2 KiB, 64-byte rows, TMA SWIZZLE_64B layout:
+// 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)).  Residual rows are fetched with coalesced 16-byte loads
+// (4 lanes per row), handed to the owning thread through the tile, the finished rows go back into the tile and leave
+// with one TMA store per chunk (the tensor map clips rows >= M / columns >= N', so no store predication is needed).
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
+  return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+struct ResidualRegs { uint4 v[4]; };
+
+// coalesced fetch of the residual chunk [32 rows x 32 cols] for rows row_base .. row_base+31, columns col0 .. col0+31
+__device__ __forceinline__ void residual_fetch(const GemmArgs& args, ResidualRegs& rr, int row_base, int col0, int n_limit,
+                                               int lane) {
+  const int seg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row_base + i * 8 + (lane >> 2);
+    rr.v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < args.M && col0 + seg * 8 < n_limit) {
+      const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
+      rr.v[i] = *reinterpret_cast<const uint4*>(args.residual + (long long)rrow * args.ldr + col0 + seg * 8);
+    }
+  }
+}
+
+__device__ __forceinline__ void staged_store_chunk(const GemmArgs& args, const CUtensorMap* tmC, uint8_t* stage,
+                                                   float* v, const ResidualRegs* rr, int row_base, int col0, int lane) {
+  // previous TMA store of this warp must have finished reading the staging tile
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  if (rr != nullptr) {
+    const int seg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(stage + stage_off(i * 8 + (lane >> 2), seg)) = rr->v[i];
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 u = *reinterpret_cast<const uint4*>(stage + stage_off(lane, g));
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      float* w = v + g * 8;
+      w[0] += f0.x; w[1] += f0.y; w[2] += f1.x; w[3] += f1.y;
+      w[4] += f2.x; w[5] += f2.y; w[6] += f3.x; w[7] += f3.y;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float* w = v + g * 8;
+    uint4 u;
+    u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
+    u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
+    *reinterpret_cast<uint4*>(stage + stage_off(lane, g)) = u;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stage, col0, row_base);
+    tma_store_commit();
+  }
+}
+
+__device__ __forceinline__ void apply_bias_act(const GemmArgs& args, float* v, const float* bias_s) {
+  if (args.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (args.act == LP_ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+  } else if (args.act == LP_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmArgs args) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256u : 512u;
   extern __shared__ uint8_t smem_raw[];
@@ -143,6 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (!args.out_fp32) tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -237,8 +320,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < args.M;
       const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+      uint8_t* stage = smem + L::STAGE_OUT_OFF + (warp - 2) * 2048;
+      const int row_base = m0 + lg * 32;
+      const bool has_res = args.residual != nullptr;
       if (!swiglu) {
         const int c_begin = wg == 0 ? 0 : (NC + 1) / 2, c_end = wg == 0 ? (NC + 1) / 2 : NC;
+        ResidualRegs rr;
+        if (has_res && !args.out_fp32 && n0 + c_begin * 32 < args.N)
+          residual_fetch(args, rr, row_base, n0 + c_begin * 32, args.N, lane);
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           const int col0 = n0 + c * 32;
@@ -249,11 +338,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_store_chunk(args, v, bs + c * 32, row, rrow, row_ok, col0, args.N);
+          if (args.out_fp32) {
+            epilogue_store_chunk(args, v, bs + c * 32, row, rrow, row_ok, col0, args.N);
+          } else {
+            apply_bias_act(args, v, bs + c * 32);
+            ResidualRegs cur = rr;
+            if (has_res && c + 1 < c_end && col0 + 32 < args.N)  // prefetch the next chunk's residual
+              residual_fetch(args, rr, row_base, col0 + 32, args.N, lane);
+            staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0, lane);
+          }
         }
       } else {
         // columns are interleaved in 32-wide granules [gate | up | gate | up ...]; output has N/2 columns
         const int c_begin = wg == 0 ? 0 : (NP + 1) / 2, c_end = wg == 0 ? (NP + 1) / 2 : NP;
+        ResidualRegs rr;
+        if (has_res && n0 + c_begin * 64 < args.N)
+          residual_fetch(args, rr, row_base, (n0 + c_begin * 64) / 2, args.N / 2, lane);
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           const int col0 = n0 + c * 64;
@@ -269,10 +369,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (args.bias) { g += bs[c * 64 + j]; u += bs[c * 64 + 32 + j]; }
             v[j] = silu_f(g) * u;
           }
-          GemmArgs a2 = args;
-          a2.bias = nullptr;
-          a2.act = LP_ACT_NONE;
-          epilogue_store_chunk(a2, v, nullptr, row, rrow, row_ok, col0 / 2, args.N / 2);
+          ResidualRegs cur = rr;
+          if (has_res && c + 1 < c_end && col0 + 64 < args.N)
+            residual_fetch(args, rr, row_base, (col0 + 64) / 2, args.N / 2, lane);
+          staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0 / 2, lane);
         }
       }
       tc_fence_before();
@@ -281,6 +381,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp have landed before the CTA may exit
   }
 
   tc_fence_before();
@@ -292,7 +393,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& args,
+                       cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   auto kern = gemm_bf16_kernel<BN, STAGES>;
   static bool configured = false;
@@ -302,7 +404,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = args.num_m_blk * args.num_n_blk;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, args);
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, args);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -365,18 +467,25 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     if (args.group_m > args.num_m_blk) args.group_m = args.num_m_blk;
   }
 
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
+  CUtensorMap tmA, tmB, tmC;
+  int rc = 0;
+  if (!out_fp32) {  // output tile map: 32 x 32 bf16 boxes with 64-byte swizzle (see staged_store_chunk)
+    rc = make_tmap_2d(&tmC, C, 2, (uint64_t)(act == LP_ACT_SWIGLU ? N / 2 : N), (uint64_t)M, (uint64_t)ldc, 32, 32, 64);
+    if (rc) return rc;
+  } else {
+    tmC = CUtensorMap{};
+  }
+  rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, (uint32_t)block_n);
   if (rc) return rc;
   ProfScope prof(1, M, N, K, stream);
   note_launch();
   switch (block_n) {
-    case 256: return launch_gemm<256, 4>(tmA, tmB, args, stream);
-    case 224: return launch_gemm<224, 5>(tmA, tmB, args, stream);
-    case 192: return launch_gemm<192, 5>(tmA, tmB, args, stream);
-    case 160: return launch_gemm<160, 6>(tmA, tmB, args, stream);
-    default: return launch_gemm<128, 6>(tmA, tmB, args, stream);
+    case 256: return launch_gemm<256, 4>(tmA, tmB, tmC, args, stream);
+    case 224: return launch_gemm<224, 4>(tmA, tmB, tmC, args, stream);
+    case 192: return launch_gemm<192, 5>(tmA, tmB, tmC, args, stream);
+    case 160: return launch_gemm<160, 5>(tmA, tmB, tmC, args, stream);
+    default: return launch_gemm<128, 6>(tmA, tmB, tmC, args, stream);
   }
 }

@@ -63,7 +63,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -71,7 +71,7 @@ static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u stride %llu)", (int)r, rank,
@@ -88,6 +88,22 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   cuuint64_t strides[1] = {ld_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   return encode(map, base, 2, dims, strides, box);
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  if (elem_bytes != 2) {
+    set_error("make_tmap_2d: only 2-byte elements are supported");
+    return LP_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * (cuuint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return encode(map, base, 2, dims, strides, box, swz);
 }
 
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,

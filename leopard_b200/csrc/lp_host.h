@@ -41,7 +41,8 @@ struct ProfScope {
 
 // attention launch arguments (shared by lp_attn.cu and lp_attn2.cu)
 struct AttnArgs {
-  int T, B, n_heads, group;
+  int T, B, n_heads, group;   // T = query rows per sequence
+  int Tk;                     // key/value rows per sequence (== T for self-attention)
   int q_off, k_off, v_off, hs;
   int dh_out;
   __nv_bfloat16* O;
@@ -54,6 +55,9 @@ int launch_attn2(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int cau
 // dims/strides are innermost-first; strides are in ELEMENTS for dims >= 1.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer);
+// generic 2-D map: elem_bytes 2 (bf16); swizzle_bytes in {0, 32, 64, 128}; inner box bytes must equal the swizzle span
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
                       uint64_t ld2_elems, uint32_t b0, uint32_t b1, uint32_t b2);
 

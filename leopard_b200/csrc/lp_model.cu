@@ -46,6 +46,44 @@ static size_t vit_ws(const lp_vit_dims* d, int N, Carver* c, void** A, void** x,
   return cv.used + 256;
 }
 
+static int vit_layers_impl(const lp_vit_dims* d, const lp_vit_weights* w, void* x, void* h, void* qkv, void* att,
+                           void* mlp, int rows, const int* cu, int n_seqs, int uniform_T, void* out, long long ldo,
+                           int shuffle_side, void* stream) {
+  const int qkv_w = 3 * d->heads * d->head_stride;
+  const float scale = 1.0f / sqrtf((float)d->head_dim);
+  int rc;
+#define LP_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
+  for (int l = 0; l < d->layers; ++l) {
+    const lp_vit_layer_weights* L = &w->layers[l];
+    LP_TRY(lp_layernorm(x, d->hidden, L->ln1_g, L->ln1_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
+    LP_TRY(lp_gemm_bf16(h, d->hidden, L->qkv_w, d->hidden, qkv, qkv_w, rows, qkv_w, d->hidden, L->qkv_b, nullptr, 0, 0,
+                        LP_ACT_NONE, 0, 0, stream));
+    if (cu == nullptr) {
+      LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, uniform_T, d->heads, d->heads, d->head_dim, d->head_stride, 0,
+                              d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0, scale, att, d->hidden, 2,
+                              stream));
+    } else {
+      for (int s = 0; s < n_seqs; ++s) {  // one launch per image (lengths differ)
+        const int r0 = cu[s], T = cu[s + 1] - r0;
+        LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->heads,
+                                d->head_dim, d->head_stride, 0, d->heads * d->head_stride,
+                                2 * d->heads * d->head_stride, 0, scale, (__nv_bfloat16*)att + (size_t)r0 * d->hidden,
+                                d->hidden, 2, stream));
+      }
+    }
+    LP_TRY(lp_gemm_bf16(att, d->hidden, L->out_w, d->hidden, x, d->hidden, rows, d->hidden, d->hidden, L->out_b, x,
+                        d->hidden, 0, LP_ACT_NONE, 0, 0, stream));
+    LP_TRY(lp_layernorm(x, d->hidden, L->ln2_g, L->ln2_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
+    LP_TRY(lp_gemm_bf16(h, d->hidden, L->fc1_w, d->hidden, mlp, d->ffn, rows, d->ffn, d->hidden, L->fc1_b, nullptr, 0,
+                        0, LP_ACT_GELU_TANH, 0, 0, stream));
+    LP_TRY(lp_gemm_bf16(mlp, d->ffn, L->fc2_w, d->ffn, x, d->hidden, rows, d->hidden, d->ffn, L->fc2_b, x, d->hidden,
+                        0, LP_ACT_NONE, 0, 0, stream));
+  }
+  // ln_post; shuffle_side != 0 writes the pixel-shuffled [rows/4, 4*hidden] layout directly
+  LP_TRY(lp_layernorm(x, d->hidden, w->post_g, w->post_b, out, ldo, rows, d->hidden, d->eps, shuffle_side, stream));
+  return 0;
+}
+
 extern "C" size_t lp_vit_workspace_bytes(const lp_vit_dims* d, int N) {
   return vit_ws(d, N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
@@ -64,33 +102,35 @@ extern "C" int lp_vit_forward(const lp_vit_dims* d, const lp_vit_weights* w, con
   vit_ws(d, N, &cv, &A, &x, &h, &qkv, &att, &mlp);
   const int rows = N * d->tokens;
   const int img = d->grid * 14;
-  const int qkv_w = 3 * d->heads * d->head_stride;
   int rc;
-#define LP_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
   LP_TRY(lp_im2col_patch14(pixels, pixels_fp32, A, d->patch_k_pad, N, 3, img, img, stream));
   // patch embedding GEMM + bias + learned position embedding (row % tokens)
   LP_TRY(lp_gemm_bf16(A, d->patch_k_pad, w->patch_w, d->patch_k_pad, x, d->hidden, rows, d->hidden, d->patch_k_pad,
                       w->patch_b, w->pos, d->hidden, d->tokens, LP_ACT_NONE, 0, 0, stream));
-  for (int l = 0; l < d->layers; ++l) {
-    const lp_vit_layer_weights* L = &w->layers[l];
-    LP_TRY(lp_layernorm(x, d->hidden, L->ln1_g, L->ln1_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
-    LP_TRY(lp_gemm_bf16(h, d->hidden, L->qkv_w, d->hidden, qkv, qkv_w, rows, qkv_w, d->hidden, L->qkv_b, nullptr, 0, 0,
-                        LP_ACT_NONE, 0, 0, stream));
-    LP_TRY(lp_attention_fwd(qkv, qkv_w, N, d->tokens, d->heads, d->heads, d->head_dim, d->head_stride, 0,
-                            d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0,
-                            1.0f / sqrtf((float)d->head_dim), att, d->hidden, 1, stream));
-    LP_TRY(lp_gemm_bf16(att, d->hidden, L->out_w, d->hidden, x, d->hidden, rows, d->hidden, d->hidden, L->out_b, x,
-                        d->hidden, 0, LP_ACT_NONE, 0, 0, stream));
-    LP_TRY(lp_layernorm(x, d->hidden, L->ln2_g, L->ln2_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
-    LP_TRY(lp_gemm_bf16(h, d->hidden, L->fc1_w, d->hidden, mlp, d->ffn, rows, d->ffn, d->hidden, L->fc1_b, nullptr, 0,
-                        0, LP_ACT_GELU_TANH, 0, 0, stream));
-    LP_TRY(lp_gemm_bf16(mlp, d->ffn, L->fc2_w, d->ffn, x, d->hidden, rows, d->hidden, d->ffn, L->fc2_b, x, d->hidden,
-                        0, LP_ACT_NONE, 0, 0, stream));
-  }
-  // ln_post; shuffle != 0 writes the pixel-shuffled [N*tokens/4, 4*hidden] layout directly
-  LP_TRY(lp_layernorm(x, d->hidden, w->post_g, w->post_b, out, ldo, rows, d->hidden, d->eps, shuffle ? d->grid : 0,
-                      stream));
-  return 0;
+  return vit_layers_impl(d, w, x, h, qkv, att, mlp, rows, nullptr, N, d->tokens, out, ldo, shuffle ? d->grid : 0,
+                         stream);
+}
+
+// Encoder layers + ln_post on an already embedded residual stream x [R, hidden] holding n_seqs images of possibly
+// different lengths (NaViT, Idefics2: MP/model/idefics2/idefics_vision_tower.py:152-178 with padded patches REMOVED,
+// which is what the reference's key-padding mask / flash-varlen unpad achieve).
+extern "C" size_t lp_vit_layers_workspace_bytes(const lp_vit_dims* d, int total_rows) {
+  const size_t r = (size_t)total_rows;
+  return bf(r * d->hidden) * 2 + bf(r * 3 * d->heads * d->head_stride) + bf(r * d->ffn) + 5 * 256 + 256;
+}
+
+extern "C" int lp_vit_layers(const lp_vit_dims* d, const lp_vit_weights* w, void* x, const int* cu_seqlens_host,
+                             int n_seqs, void* out, long long ldo, void* workspace, size_t ws_bytes, void* stream) {
+  LP_REQUIRE(d && w && x && out && cu_seqlens_host && n_seqs > 0, "lp_vit_layers: null argument");
+  const int R = cu_seqlens_host[n_seqs];
+  LP_REQUIRE(R > 0 && cu_seqlens_host[0] == 0, "lp_vit_layers: bad cu_seqlens");
+  LP_REQUIRE(ws_bytes >= lp_vit_layers_workspace_bytes(d, R), "lp_vit_layers: workspace too small");
+  Carver cv(workspace, ws_bytes);
+  void* h = cv.take(bf((size_t)R * d->hidden));
+  void* qkv = cv.take(bf((size_t)R * 3 * d->heads * d->head_stride));
+  void* att = cv.take(bf((size_t)R * d->hidden));
+  void* mlp = cv.take(bf((size_t)R * d->ffn));
+  return vit_layers_impl(d, w, x, h, qkv, att, mlp, R, cu_seqlens_host, n_seqs, 0, out, ldo, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ projector
@@ -164,12 +204,12 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
     LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
     if (uniform) {
       LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, R / n_seqs, d->heads, d->kv_heads, hd, hd, 0, q_w, q_w + kv_w, 1,
-                              scale, att, H, 1, stream));
+                              scale, att, H, 2, stream));
     } else {
       for (int s = 0; s < n_seqs; ++s) {
         const int r0 = cu_seqlens_host[s], T = cu_seqlens_host[s + 1] - r0;
         LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->kv_heads, hd,
-                                hd, 0, q_w, q_w + kv_w, 1, scale, (__nv_bfloat16*)att + (size_t)r0 * H, H, 1, stream));
+                                hd, 0, q_w, q_w + kv_w, 1, scale, (__nv_bfloat16*)att + (size_t)r0 * H, H, 2, stream));
       }
     }
     if (kv_cache) {  // [layers][2][R][kv_w]: K (post-RoPE) then V

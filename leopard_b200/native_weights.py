@@ -84,7 +84,8 @@ class NativeWeights:
         return sum(t.numel() * t.element_size() for t in self._keep)
 
 
-def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda") -> NativeWeights:
+def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda",
+            with_projector: bool = True) -> NativeWeights:
     """Build NativeWeights from HF-layout tensors; `get(name)` returns one tensor (any float dtype, any device)."""
     nw = NativeWeights(cfg, device)
     v, d = cfg.vit, cfg.dec
@@ -126,12 +127,13 @@ def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda
     nw.vit.post_g = nw._p(nw._f32(get(V + "post_layernorm.weight")))
     nw.vit.post_b = nw._p(nw._f32(get(V + "post_layernorm.bias")))
 
-    # ---- projector
-    nw.proj.w1 = nw._p(nw._bf(get(P + "linear_1.weight")))
-    nw.proj.b1 = nw._p(nw._f32(get(P + "linear_1.bias")))
-    nw.proj.w2 = nw._p(nw._bf(get(P + "linear_2.weight")))
-    nw.proj.b2 = nw._p(nw._f32(get(P + "linear_2.bias")))
-    nw.proj.act = _lib.ACT_GELU_ERF if cfg.projector_act == "gelu" else _lib.ACT_GELU_TANH
+    # ---- projector (Leopard-LLaVA only; Idefics2 has its own connector, see idefics2.py)
+    if with_projector:
+        nw.proj.w1 = nw._p(nw._bf(get(P + "linear_1.weight")))
+        nw.proj.b1 = nw._p(nw._f32(get(P + "linear_1.bias")))
+        nw.proj.w2 = nw._p(nw._bf(get(P + "linear_2.weight")))
+        nw.proj.b2 = nw._p(nw._f32(get(P + "linear_2.bias")))
+        nw.proj.act = _lib.ACT_GELU_ERF if cfg.projector_act == "gelu" else _lib.ACT_GELU_TANH
 
     # ---- decoder
     nw.embed = nw._bf(get(LM + "embed_tokens.weight"))

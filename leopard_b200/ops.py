@@ -144,3 +144,18 @@ def pixel_shuffle(x2d, side):
                                      _lib.stream_ptr())
     _lib.check(rc, "lp_pixel_shuffle")
     return out
+
+
+def attention_cross(q, kv, B, Tq, Tk, n_heads, n_kv_heads, head_dim, k_off, v_off, scale=None, out=None):
+    """Cross-attention: q [B*Tq, heads*head_dim], kv [B*Tk, ...] with K at k_off, V at v_off (lp_attention_cross)."""
+    _chk_bf16(q, "q")
+    _chk_bf16(kv, "kv")
+    if scale is None:
+        scale = head_dim ** -0.5
+    if out is None:
+        out = torch.empty((B * Tq, n_heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_attention_cross(_lib.ptr(q), q.stride(0), _lib.ptr(kv), kv.stride(0), B, Tq, Tk, n_heads,
+                                       n_kv_heads, head_dim, k_off, v_off, float(scale), _lib.ptr(out), out.stride(0),
+                                       _lib.stream_ptr())
+    _lib.check(rc, "lp_attention_cross")
+    return out

@@ -64,6 +64,64 @@ def tensor_specs(cfg: LeopardConfig) -> Iterator[Tuple[str, Tuple[int, ...], str
     yield "language_model.lm_head.weight", (d.vocab, d.hidden), "linear"
 
 
+def idefics2_tensor_specs(cfg) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """HF Idefics2 key layout (`model.vision_model.*`, `model.connector.*`, `model.text_model.*`, `lm_head.weight`)."""
+    v, pc, d = cfg.vit, cfg.perceiver, cfg.dec
+    VM, CN, TM = "model.vision_model.", "model.connector.", "model.text_model."
+    yield VM + "embeddings.patch_embedding.weight", (v.hidden, 3, v.patch_size, v.patch_size), "conv"
+    yield VM + "embeddings.patch_embedding.bias", (v.hidden,), "bias"
+    yield VM + "embeddings.position_embedding.weight", (v.tokens, v.hidden), "pos"
+    for i in range(v.layers):
+        b = f"{VM}encoder.layers.{i}."
+        yield b + "layer_norm1.weight", (v.hidden,), "norm"
+        yield b + "layer_norm1.bias", (v.hidden,), "bias"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield b + f"self_attn.{n}.weight", (v.hidden, v.hidden), "linear"
+            yield b + f"self_attn.{n}.bias", (v.hidden,), "bias"
+        yield b + "layer_norm2.weight", (v.hidden,), "norm"
+        yield b + "layer_norm2.bias", (v.hidden,), "bias"
+        yield b + "mlp.fc1.weight", (v.ffn, v.hidden), "linear"
+        yield b + "mlp.fc1.bias", (v.ffn,), "bias"
+        yield b + "mlp.fc2.weight", (v.hidden, v.ffn), "linear"
+        yield b + "mlp.fc2.bias", (v.hidden,), "bias"
+    yield VM + "post_layernorm.weight", (v.hidden,), "norm"
+    yield VM + "post_layernorm.bias", (v.hidden,), "bias"
+    mp = CN + "modality_projection."
+    yield mp + "gate_proj.weight", (cfg.modality_ffn, v.hidden), "linear"
+    yield mp + "up_proj.weight", (cfg.modality_ffn, v.hidden), "linear"
+    yield mp + "down_proj.weight", (d.hidden, cfg.modality_ffn), "linear"
+    pr = CN + "perceiver_resampler."
+    yield pr + "latents", (pc.latents, pc.hidden), "latents"
+    for i in range(pc.depth):
+        b = f"{pr}layers.{i}."
+        yield b + "input_latents_norm.weight", (pc.hidden,), "norm"
+        yield b + "input_context_norm.weight", (pc.hidden,), "norm"
+        yield b + "self_attn.q_proj.weight", (pc.heads * pc.head_dim, pc.hidden), "linear"
+        yield b + "self_attn.k_proj.weight", (pc.kv_heads * pc.head_dim, pc.hidden), "linear"
+        yield b + "self_attn.v_proj.weight", (pc.kv_heads * pc.head_dim, pc.hidden), "linear"
+        yield b + "self_attn.o_proj.weight", (pc.hidden, pc.heads * pc.head_dim), "linear"
+        yield b + "post_attention_layernorm.weight", (pc.hidden,), "norm"
+        yield b + "mlp.gate_proj.weight", (pc.ffn, pc.hidden), "linear"
+        yield b + "mlp.up_proj.weight", (pc.ffn, pc.hidden), "linear"
+        yield b + "mlp.down_proj.weight", (pc.hidden, pc.ffn), "linear"
+    yield pr + "norm.weight", (pc.hidden,), "norm"
+    yield TM + "embed_tokens.weight", (d.vocab, d.hidden), "embed"
+    kv = d.kv_heads * d.head_dim
+    for i in range(d.layers):
+        b = f"{TM}layers.{i}."
+        yield b + "input_layernorm.weight", (d.hidden,), "norm"
+        yield b + "self_attn.q_proj.weight", (d.hidden, d.hidden), "linear"
+        yield b + "self_attn.k_proj.weight", (kv, d.hidden), "linear"
+        yield b + "self_attn.v_proj.weight", (kv, d.hidden), "linear"
+        yield b + "self_attn.o_proj.weight", (d.hidden, d.hidden), "linear"
+        yield b + "post_attention_layernorm.weight", (d.hidden,), "norm"
+        yield b + "mlp.gate_proj.weight", (d.ffn, d.hidden), "linear"
+        yield b + "mlp.up_proj.weight", (d.ffn, d.hidden), "linear"
+        yield b + "mlp.down_proj.weight", (d.hidden, d.ffn), "linear"
+    yield TM + "norm.weight", (d.hidden,), "norm"
+    yield "lm_head.weight", (d.vocab, d.hidden), "linear"
+
+
 def _seed_for(name: str, seed: int) -> int:
     return int.from_bytes(hashlib.sha256(f"{seed}:{name}".encode()).digest()[:7], "little")
 
@@ -84,6 +142,8 @@ def synth_tensor(name: str, shape, kind: str, seed: int = 1234) -> torch.Tensor:
         t = torch.randn(shape, generator=g) * 0.05
     elif kind == "pos":
         t = torch.randn(shape, generator=g) * 0.02
+    elif kind == "latents":
+        t = 1.0 + torch.randn(shape, generator=g) * 0.1   # the reference initialises latents to ones
     else:
         raise ValueError(kind)
     return t.to(torch.bfloat16)
@@ -92,10 +152,11 @@ def synth_tensor(name: str, shape, kind: str, seed: int = 1234) -> torch.Tensor:
 class SyntheticCheckpoint:
     """Lazy HF-layout state dict: `ckpt[name]` materialises one bf16 tensor; nothing is cached."""
 
-    def __init__(self, cfg: LeopardConfig, seed: int = 1234):
+    def __init__(self, cfg, seed: int = 1234):
         self.cfg = cfg
         self.seed = seed
-        self._specs: Dict[str, Tuple[Tuple[int, ...], str]] = {n: (s, k) for n, s, k in tensor_specs(cfg)}
+        specs = idefics2_tensor_specs(cfg) if hasattr(cfg, "perceiver") else tensor_specs(cfg)
+        self._specs: Dict[str, Tuple[Tuple[int, ...], str]] = {n: (s, k) for n, s, k in specs}
 
     def keys(self):
         return self._specs.keys()

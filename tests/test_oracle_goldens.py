@@ -143,3 +143,28 @@ def test_merge_conventions_agree():
         om.merge_hf_expand(ck, cfg, ids, feats[:1])
     with pytest.raises(AssertionError, match="doesn't match"):
         om.merge_megatron_scatter(ck, cfg, meg, feats[:1])
+
+
+def test_oracle_idefics2_matches_transformers():
+    """NaViT tower with padding masks + dropped all-zero image, modality projection, perceiver, merger, Mistral."""
+    import sys
+    sys.path.insert(0, str(G))
+    import gen_idefics2_goldens as gg
+    from leopard_b200.config import leopard_idefics2, reduced_idefics2
+    from oracle import idefics2 as oi
+    z = np.load(G / "idefics2_goldens.npz")
+    vl, pd, dl, vocab = [int(v) for v in z["meta"]]
+    cfg = reduced_idefics2(leopard_idefics2(), vl, pd, dl, vocab)
+    ck = SyntheticCheckpoint(cfg, seed=1234)
+    ids, pv, pm, n_img = gg.make_inputs(cfg)
+    st = {}
+    logits = oi.prefill_logits(ck, cfg, ids, pv, pm, stages=st)
+    feats = st["image_features"].reshape(-1, cfg.dec.hidden)
+    assert feats.shape[0] == n_img * cfg.perceiver.latents
+    assert np.abs(feats[:, ::7].numpy() - z["image_features"]).max() < 2e-4 * np.abs(z["image_features"]).max()
+    assert np.abs(logits[0][:, ::2].numpy() - z["logits"]).max() < 2e-4 * np.abs(z["logits"]).max()
+    # position ids: full image -> bucketised rows/cols of the 70 x 70 table
+    mask = oi.patch_mask_from_pixels(pm[0, :2], 14)
+    pos = oi.navit_position_ids(mask, 70)
+    assert pos[0, 0] == 0 and pos[0, 1] == 70 // 13 * 0 + int(torch.bucketize(torch.tensor(1 / 13), torch.arange(1 / 70, 1.0, 1 / 70), right=True))
+    assert int(mask[1].sum()) == 70 and bool((pos[1][~mask[1].reshape(-1)] == 0).all())

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/gemm3.log
+: > $L
+timeout 300 python tools/gpu_check_gemm.py --case tile1 --case ragged --case r224 --case r192 --case r160 --case sw192 --case sw128 --case ragged128 --case vit_patch --case fp32out >> $L 2>&1
+echo "small rc=$?" >> $L
+timeout 900 python tools/gpu_check_gemm.py --time >> $L 2>&1
+echo "all rc=$?" >> $L
+timeout 1200 python -m pytest tests -m gpu -x -q -k "not full_depth" >> $L 2>&1
+echo "tests rc=$?" >> $L
+timeout 600 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/bench4.json 2>> $L
+tail -5 $L
