@@ -110,6 +110,14 @@ def make_workload(cfg):
     return pix, ids, n_crops, S, per_image
 
 
+def workload_config(per_image, S, world, parallelism):
+    return {"workload": "cfg3: LLaVA 4x(896x1152) -> adaptive allocation -> 28 crops, 92 prompt ids -> S=4796 merged "
+                        "rows, 1 request per GPU per step, last-token logits",
+            "crops_per_image": per_image, "S": S, "model": "SigLIP-SO400M/14-364 + Llama-3.1-8B (synthetic)",
+            "l2_policy": "inputs larger than L2: 17 GB of weights stream from HBM every step (L2 = 126 MB)",
+            "parallelism": parallelism}
+
+
 def flops_model(n_crops, S, cfg):
     """Algorithmic FLOPs of one step."""
     T = cfg.vit.tokens
@@ -175,7 +183,7 @@ def run_reference(args):
     import torch
     from leopard_b200.config import leopard_llava
     cfg = leopard_llava()
-    _, _, n_crops, S, _ = make_workload(cfg)
+    _, _, n_crops, S, per_image_ref = make_workload(cfg)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     vals, secs, info = [], [], {}
@@ -192,8 +200,7 @@ def run_reference(args):
         "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": 1000.0 * S / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg3: LLaVA 4x(896x1152) -> 28 crops, S=4796, 1 request/step (CPU: rank 0 only)",
-                   "crops": n_crops, "S": S},
+        "config": workload_config(per_image_ref, S, 1, "CPU oracle port on rank 0's host cores"),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample, **info},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,6 +230,8 @@ def run_ours(args):
 
     cfg = leopard_llava()
     L = _lib.lib()
+    if args.gemm_pair is not None:
+        L.lp_gemm_set_pair_mode(int(args.gemm_pair))
     model = myLlavaForConditionalGeneration.from_native(cfg, random_native(cfg, dev, seed=1234))
     eng = model.engine
     pix_h, ids_h, n_crops, S, per_image = make_workload(cfg)
@@ -335,11 +344,7 @@ def run_ours(args):
             "metric": "prefill tokens/sec (Leopard-LLaVA 4-image prefill, whole job)", "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "cfg3: LLaVA 4x(896x1152) -> adaptive allocation -> 28 crops, 92 prompt ids -> S=4796 "
-                                   "merged rows, 1 request per GPU per step, last-token logits",
-                       "crops_per_image": per_image, "S": S, "model": "SigLIP-SO400M/14-364 + Llama-3.1-8B (synthetic)",
-                       "l2_policy": "inputs larger than L2: 17 GB of weights stream from HBM every step (L2 = 126 MB)",
-                       "parallelism": f"dp{world}, no data-path collective"},
+            "config": workload_config(per_image, S, world, f"dp{world}, no data-path collective"),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "leopard_b200.hf.myLlavaForConditionalGeneration.generate(host ids, pixel_values=host fp32, max_new_tokens=1)"},
@@ -360,6 +365,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="1 warm-up, timed loop only (for runs under ncu)")
+    ap.add_argument("--gemm-pair", type=int, default=None, help="override the GEMM CTA-pair mode (0/1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

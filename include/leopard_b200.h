@@ -52,6 +52,11 @@ int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, voi
                  int K, const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
                  int block_n, void* stream);
 
+/* GEMM scheduling mode: 0 = one CTA per 128-row tile; 1 = CTA pairs (thread-block cluster of 2, tcgen05
+ * cta_group::2, 256-row tiles) for problems with at least one tile per SM pair.  Returns the previous mode.
+ * Results are identical up to fp32 summation order (same K order: bit-identical in practice). */
+int lp_gemm_set_pair_mode(int enable);
+
 /* O[b,t,h,:] = softmax(scale * Q K^T (+causal)) V          (tcgen05 flash attention, fp32 softmax, bf16 in/out)
  *   replaces flash_attn_varlen_func (MP/model/llava/transformer.py:476-515,869-877; the 4x KV repeat_interleave at
  *   :829-836 is not materialised) and the ViT's TEDotProductAttention / HF SiglipAttention

@@ -63,6 +63,7 @@ _SIGS = {
     "lp_last_error": (C.c_char_p, []),
     "lp_abi_version": (_i, []),
     "lp_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "lp_gemm_set_pair_mode": (_i, [_i]),
     "lp_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _i, _vp]),
     "lp_attention_cross": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
     "lp_layernorm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),

@@ -16,33 +16,26 @@
 
 namespace lp {
 
-constexpr int NORM_THREADS = 128;
-constexpr int NORM_MAXC = 4;  // 16-byte chunks per thread -> D <= 128 * 4 * 8 = 4096
+constexpr int NORM_THREADS = 128;   // 4 warps = 4 rows per CTA
+constexpr int NORM_MAX_D = 4096;
 
-__device__ __forceinline__ float block_sum_128(float v, float* red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5;
-  __syncthreads();  // protect `red` from the previous use
-  if ((threadIdx.x & 31) == 0) red[w] = v;
-  __syncthreads();
-  return red[0] + red[1] + red[2] + red[3];
-}
-
-// one CTA per row; RMS = false: LayerNorm (two-pass in registers), RMS = true: RMSNorm
-template <bool RMS>
+// One WARP per row (no shared memory, shuffle reductions only), the row lives in registers between the statistics
+// pass and the normalise/store pass: 2 x rows x D x 2 bytes of HBM traffic, 16-byte accesses.
+// RMS = false: LayerNorm (two-pass mean / variance in fp32), RMS = true: RMSNorm.  CH = 16-byte chunks per lane.
+template <bool RMS, int CH>
 __global__ void __launch_bounds__(NORM_THREADS)
 norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
-            bf16* __restrict__ out, long long ldo, int D, float eps, int shuffle_side) {
-  __shared__ float red[4];
-  const int row = blockIdx.x;
+            bf16* __restrict__ out, long long ldo, int M, int D, float eps, int shuffle_side) {
+  const int row = blockIdx.x * (NORM_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;
   const bf16* xr = x + (long long)row * ldx;
-  float v[NORM_MAXC][8];
+  float v[CH][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXC; ++i) {
-    const int c = threadIdx.x + i * NORM_THREADS;
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
     if (c < nchunk) {
       const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
       const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -52,7 +45,8 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
       for (int j = 0; j < 8; ++j) s += RMS ? v[i][j] * v[i][j] : v[i][j];
     }
   }
-  s = block_sum_128(s, red);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float mean = 0.f, rstd;
   if (RMS) {
     rstd = rsqrtf(s / (float)D + eps);
@@ -60,8 +54,8 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
     mean = s / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXC; ++i) {
-      const int c = threadIdx.x + i * NORM_THREADS;
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane + i * 32;
       if (c < nchunk) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -70,7 +64,8 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
         }
       }
     }
-    q = block_sum_128(q, red);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     rstd = rsqrtf(q / (float)D + eps);
   }
   // destination row / column offset (pixel-shuffle store: 2x2 neighbourhoods are concatenated along channels)
@@ -86,8 +81,8 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
   }
   bf16* orp = out + orow * ldo + ocol;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXC; ++i) {
-    const int c = threadIdx.x + i * NORM_THREADS;
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
     if (c < nchunk) {
       const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8);
       const float4 g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
@@ -107,6 +102,16 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
       *reinterpret_cast<uint4*>(orp + c * 8) = u;
     }
   }
+}
+
+template <bool RMS>
+static void launch_norm(const bf16* x, long long ldx, const float* g, const float* b, bf16* out, long long ldo, int M,
+                        int D, float eps, int shuffle_side, cudaStream_t stream) {
+  const int grid = (M + NORM_THREADS / 32 - 1) / (NORM_THREADS / 32);
+  if (D <= 32 * 8 * 5)
+    norm_kernel<RMS, 5><<<grid, NORM_THREADS, 0, stream>>>(x, ldx, g, b, out, ldo, M, D, eps, shuffle_side);
+  else
+    norm_kernel<RMS, 16><<<grid, NORM_THREADS, 0, stream>>>(x, ldx, g, b, out, ldo, M, D, eps, shuffle_side);
 }
 
 // cos/sin tables [S, half] from integer positions and fp32 inverse frequencies
@@ -256,7 +261,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" int lp_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, void* out,
                             long long ldo, int M, int D, float eps, int shuffle_side, void* stream) {
-  LP_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= NORM_THREADS * NORM_MAXC * 8, "lp_layernorm: bad M=%d D=%d", M, D);
+  LP_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= NORM_MAX_D, "lp_layernorm: bad M=%d D=%d", M, D);
   LP_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && aligned16(x) && aligned16(out) && aligned16(gamma) &&
                  (beta == nullptr || aligned16(beta)),
              "lp_layernorm: 16-byte alignment required");
@@ -264,21 +269,21 @@ extern "C" int lp_layernorm(const void* x, long long ldx, const float* gamma, co
              "lp_layernorm: pixel-shuffle store needs an even grid side and M %% side^2 == 0");
   ProfScope prof(3, M, D, 0, reinterpret_cast<cudaStream_t>(stream));
   note_launch();
-  norm_kernel<false><<<M, NORM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(x), ldx, gamma, beta, reinterpret_cast<bf16*>(out), ldo, D, eps, shuffle_side);
+  launch_norm<false>(reinterpret_cast<const bf16*>(x), ldx, gamma, beta, reinterpret_cast<bf16*>(out), ldo, M, D, eps,
+                     shuffle_side, reinterpret_cast<cudaStream_t>(stream));
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void* out, long long ldo, int M, int D,
                           float eps, void* stream) {
-  LP_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= NORM_THREADS * NORM_MAXC * 8, "lp_rmsnorm: bad M=%d D=%d", M, D);
+  LP_REQUIRE(M > 0 && D > 0 && D % 8 == 0 && D <= NORM_MAX_D, "lp_rmsnorm: bad M=%d D=%d", M, D);
   LP_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && aligned16(x) && aligned16(out) && aligned16(gamma),
              "lp_rmsnorm: 16-byte alignment required");
   ProfScope prof(3, M, D, 1, reinterpret_cast<cudaStream_t>(stream));
   note_launch();
-  norm_kernel<true><<<M, NORM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(x), ldx, gamma, nullptr, reinterpret_cast<bf16*>(out), ldo, D, eps, 0);
+  launch_norm<true>(reinterpret_cast<const bf16*>(x), ldx, gamma, nullptr, reinterpret_cast<bf16*>(out), ldo, M, D, eps, 0,
+                    reinterpret_cast<cudaStream_t>(stream));
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

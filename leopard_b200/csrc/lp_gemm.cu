@@ -44,12 +44,14 @@ struct GemmArgs {
   int act;
   int num_m_blk, num_n_blk, num_k_blk;
   int group_m;
+  int prefetch_a;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool CTA2 = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;  // CTA pair: each CTA stages half of the W tile
+  static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = BAR_OFF + 256;
@@ -204,11 +206,20 @@ __device__ __forceinline__ void apply_bias_act(const GemmArgs& args, float* v, c
   }
 }
 
-template <int BN, int STAGES>
+// CTA2 = true: CTA pair (cluster of 2, tcgen05 cta_group::2).  The pair owns a 256 x BN tile: CTA r stages rows
+// [m0 + 128 r, +128) of A and rows [n0 + r BN/2, + BN/2) of W, the leader's MMA thread issues M = 256 MMAs that read
+// both CTAs' shared memory and write each CTA's 128 accumulator rows into its own TMEM.  Halving the W bytes staged
+// per SM relieves the per-SM L2->SMEM bandwidth (the 1-CTA kernel runs at ~75 % of it) and deepens the ring.
+template <int BN, int STAGES, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CTA2>;
+  constexpr int BMT = CTA2 ? 2 * GEMM_BM : GEMM_BM;  // rows per work unit
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256u : 512u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -232,16 +243,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -252,29 +263,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
         int m_blk, n_blk;
         tile_coords(args, tile, m_blk, n_blk);
+        const int a_row = m_blk * BMT + (int)cta_rank * GEMM_BM;
+        const int b_row = n_blk * BN + (int)cta_rank * L::B_ROWS;
         for (int kb = 0; kb < args.num_k_blk; ++kb) {
+          // (an explicit cp.async.bulk.prefetch.tensor.L2 of the k-block 8 ahead was measured: every CTA of a
+          //  row-block group re-requests the same W tile, and the doubled TMA/L2 request rate cost 10-30 %: removed)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (CTA2) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (it alone arrives, expecting 2 stages)
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(sa, &tmA, bar, kb * GEMM_BK, a_row);
+            tma_load_2d_pair(sb, &tmB, bar, kb * GEMM_BK, b_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, a_row);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BMT, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -285,12 +308,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = umma_desc_sw128(a_addr, 0, 1024);
           const uint64_t bdesc = umma_desc_sw128(a_addr + L::A_BYTES, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          for (int k = 0; k < GEMM_BK / 16; ++k) {  // +32 B per K=16 step inside the 128 B swizzle row
+            if (CTA2) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+          if (CTA2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTA2) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -305,10 +332,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool swiglu = args.act == LP_ACT_SWIGLU;
     constexpr int NC = BN / 32;         // 32-column chunks per tile
     constexpr int NP = BN / 64;         // 64-column gate/up pairs per tile
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += n_units) {
       int m_blk, n_blk;
       tile_coords(args, tile, m_blk, n_blk);
-      const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+      const int m0 = m_blk * BMT + (int)cta_rank * GEMM_BM, n0 = n_blk * BN;
       float* bs = bias_smem + as * BN;
       if (args.bias) {
         for (int i = et; i < BN; i += GEMM_EPI_THREADS) bs[i] = (n0 + i < args.N) ? args.bias[n0 + i] : 0.f;
@@ -377,7 +404,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CTA2 && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+        else mbar_arrive(&tempty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -385,29 +415,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();  // role branches above leave warps 0/1 diverged; barrier.cluster.*.aligned needs converged warps
+  if (CTA2) cluster_sync_all(); else __syncthreads();  // the leader's MMAs read the peer's smem: leave together
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTA2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool CTA2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& args,
                        cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CTA2>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, CTA2>;
   static bool configured = false;
   if (!configured) {
     LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   const int tiles = args.num_m_blk * args.num_n_blk;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, args);
+  if (!CTA2) {
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, args);
+  } else {
+    const int pairs = sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, args));
+  }
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+static int g_gemm_pair_mode = 0;  // 0 = one CTA per tile, 1 = CTA pairs where the problem is large enough
 
 }  // namespace lp
 
@@ -429,7 +480,11 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   LP_REQUIRE(act >= LP_ACT_NONE && act <= LP_ACT_SWIGLU, "lp_gemm_bf16: bad act %d", act);
   LP_REQUIRE(act != LP_ACT_SWIGLU || N % 64 == 0, "lp_gemm_bf16: SwiGLU needs N %% 64 == 0 (32-wide gate/up granules)");
   const int sms = sm_count();
-  const long long mb = (M + GEMM_BM - 1) / GEMM_BM;
+  // CTA pairs (256-row tiles) when asked for and the problem has at least one tile per pair
+  bool pair = g_gemm_pair_mode != 0 && M > GEMM_BM;
+  const int units = pair ? sms / 2 : sms;
+  const int bm_unit = pair ? 2 * GEMM_BM : GEMM_BM;
+  const long long mb = (M + bm_unit - 1) / bm_unit;
   if (block_n == 0) {
     // wave-quantisation heuristic: minimise ceil(tiles / SMs) * (BN + per-tile overhead); the narrow tiles are
     // shared-memory-bandwidth bound on one CTA (A 4 KiB + B BN*32 B per K=16 step), hence their penalty
@@ -438,8 +493,9 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     double best = 1e30;
     for (int i = 0; i < 5; ++i) {
       if (act == LP_ACT_SWIGLU && cand[i] % 64 != 0) continue;
+      if (pair && cand[i] == 160) continue;  // pair kernels are instantiated for 128 / 192 / 224 / 256
       const long long tiles = mb * ((N + cand[i] - 1) / cand[i]);
-      const double cost = (double)((tiles + sms - 1) / sms) * (cand[i] + 12) * pen[i];
+      const double cost = (double)((tiles + units - 1) / units) * (cand[i] + 12) * (pair ? 1.0 : pen[i]);
       if (cost < best) { best = cost; block_n = cand[i]; }
     }
   }
@@ -454,7 +510,8 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   args.residual = reinterpret_cast<const bf16*>(residual);
   args.ldr = ldr; args.res_row_mod = res_row_mod;
   args.act = act;
-  args.num_m_blk = (M + GEMM_BM - 1) / GEMM_BM;
+  if (pair && (block_n == 160 || mb * ((N + block_n - 1) / block_n) < units)) pair = false;
+  args.num_m_blk = pair ? (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) : (M + GEMM_BM - 1) / GEMM_BM;
   args.num_n_blk = (N + block_n - 1) / block_n;
   args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
   {
@@ -465,6 +522,7 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     else if (w_bytes <= l2_budget) args.group_m = max(1, sms / args.num_n_blk);  // W resident, A read once
     else args.group_m = 16;
     if (args.group_m > args.num_m_blk) args.group_m = args.num_m_blk;
+    args.prefetch_a = a_bytes > l2_budget ? 1 : 0;  // activations that cannot stay L2-resident are prefetched too
   }
 
   CUtensorMap tmA, tmB, tmC;
@@ -477,15 +535,30 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   }
   rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, (uint32_t)block_n);
+  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK,
+                         (uint32_t)(pair ? block_n / 2 : block_n));
   if (rc) return rc;
   ProfScope prof(1, M, N, K, stream);
   note_launch();
-  switch (block_n) {
-    case 256: return launch_gemm<256, 4>(tmA, tmB, tmC, args, stream);
-    case 224: return launch_gemm<224, 4>(tmA, tmB, tmC, args, stream);
-    case 192: return launch_gemm<192, 5>(tmA, tmB, tmC, args, stream);
-    case 160: return launch_gemm<160, 5>(tmA, tmB, tmC, args, stream);
-    default: return launch_gemm<128, 6>(tmA, tmB, tmC, args, stream);
+  if (pair) {
+    switch (block_n) {
+      case 256: return launch_gemm<256, 6, true>(tmA, tmB, tmC, args, stream);
+      case 224: return launch_gemm<224, 6, true>(tmA, tmB, tmC, args, stream);
+      case 192: return launch_gemm<192, 7, true>(tmA, tmB, tmC, args, stream);
+      default: return launch_gemm<128, 8, true>(tmA, tmB, tmC, args, stream);
+    }
   }
+  switch (block_n) {
+    case 256: return launch_gemm<256, 4, false>(tmA, tmB, tmC, args, stream);
+    case 224: return launch_gemm<224, 4, false>(tmA, tmB, tmC, args, stream);
+    case 192: return launch_gemm<192, 5, false>(tmA, tmB, tmC, args, stream);
+    case 160: return launch_gemm<160, 5, false>(tmA, tmB, tmC, args, stream);
+    default: return launch_gemm<128, 6, false>(tmA, tmB, tmC, args, stream);
+  }
+}
+
+extern "C" int lp_gemm_set_pair_mode(int enable) {
+  const int old = g_gemm_pair_mode;
+  g_gemm_pair_mode = enable ? 1 : 0;
+  return old;
 }

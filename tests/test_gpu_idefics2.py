@@ -48,7 +48,7 @@ def test_host_position_ids_match_oracle():
     for b, (nh, nw) in enumerate(rects):
         assert torch.equal(navit_position_ids(nh, nw, 70), ref[b][mask[b].reshape(-1)])
     bad = pm.clone()
-    bad[1, :14, 150:164] = True
+    bad[1, :14, 154:168] = True
     with pytest.raises(ValueError, match="rectangle"):
         patch_rectangles(bad)
 

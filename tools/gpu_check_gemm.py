@@ -150,7 +150,11 @@ def main():
     ap.add_argument("--case", action="append")
     ap.add_argument("--list", action="store_true")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--pair", action="store_true", help="CTA-pair (cta_group::2) GEMM mode")
     args = ap.parse_args()
+    if args.pair:
+        from leopard_b200 import _lib
+        _lib.lib().lp_gemm_set_pair_mode(1)
     if args.list:
         print("\n".join(CASES))
         return 0
