@@ -58,6 +58,10 @@ CASES = {
     "d_down": (4796, 4096, 14336, False, 0, True, 0, False, 0),
     "d_down_256": (4796, 4096, 14336, False, 0, True, 0, False, 256),
     "d_down_160": (4796, 4096, 14336, False, 0, True, 0, False, 160),
+    "v_out_b": (18928, 1152, 1152, True, 0, False, 0, False, 0),
+    "v_out_n": (18928, 1152, 1152, False, 0, False, 0, False, 0),
+    "v_out_n256": (18928, 1152, 1152, False, 0, False, 0, False, 256),
+    "v_k2304_n": (18928, 1152, 2304, False, 0, False, 0, False, 0),
     "r224": (300, 520, 1160, True, 0, True, 0, False, 224),
     "r192": (300, 520, 1160, True, 1, True, 0, False, 192),
     "r160": (300, 520, 1160, True, 2, True, 0, False, 160),
@@ -151,10 +155,14 @@ def main():
     ap.add_argument("--list", action="store_true")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--pair", action="store_true", help="CTA-pair (cta_group::2) GEMM mode")
+    ap.add_argument("--single", action="store_true", help="one CTA per tile")
     args = ap.parse_args()
     if args.pair:
         from leopard_b200 import _lib
         _lib.lib().lp_gemm_set_pair_mode(1)
+    if args.single:
+        from leopard_b200 import _lib
+        _lib.lib().lp_gemm_set_pair_mode(0)
     if args.list:
         print("\n".join(CASES))
         return 0
