@@ -43,6 +43,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    cands = sorted((ROOT / "profiles").glob("*_gemm_gateup_traffic.json"))
+    if not cands:
+        return None
+    d = json.loads(cands[-1].read_text())
+    return {"dram_bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"],
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes"]["total"], "source": cands[-1].name}
+
+
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -313,7 +323,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel M={m} N={nn} K={k} (x{cnt}/step)", "achieved": ach,
                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
                     "peak_kind": "sustained cuBLAS bf16, " + peaks["source"], "avg_launch_ms": avg_ms,
-                    "share_of_step": ms_sum / step_ms_prof, "traffic": None}
+                    "share_of_step": ms_sum / step_ms_prof, "traffic": load_traffic()}
         fm = flops_model(n_crops, S, cfg)
         names = {1: "gemm", 2: "attention", 3: "norm", 4: "rope", 5: "merge", 6: "im2col", 7: "shuffle"}
         gemm_all = sum(v[0] for v in gemm_shapes.values())

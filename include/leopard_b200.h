@@ -66,7 +66,9 @@ int lp_gemm_set_pair_mode(int enable);
  *   columns of q and k to be exact zeros (the ViT qkv weight is stored zero-padded).
  * out: bf16 [B*T, ldo], head h at cols h*head_dim.  scale = head_dim^-0.5 in the reference.
  * variant bit 0: keep P in TMEM (tcgen05.mma A-from-TMEM) instead of shared memory (one-tile kernel);
- * variant bit 1: two 128-row query tiles per CTA ping-ponged on the tensor pipe (P always in TMEM). */
+ * variant bit 1: two 128-row query tiles per CTA ping-ponged on the tensor pipe (P always in TMEM);
+ * variant bits 2-3 (with bit 1): 0/1/2 of every 4 softmax exponentials evaluated on the FMA pipe (polynomial 2^x,
+ *   rel. error 1.1e-4) instead of MUFU.EX2. */
 int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, int n_kv_heads, int head_dim,
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);
@@ -120,6 +122,13 @@ int lp_embed_merge(const long long* ids, int L, long long image_id, int rows_per
  *   pixels: [N, C, H, W] fp32 (HF eval, EV/...anyres.py:403-405) or bf16 (Megatron). */
 int lp_im2col_patch14(const void* pixels, int pixels_fp32, void* out, long long ldo, int N, int C, int H, int W,
                       void* stream);
+
+/* loss[r] = logsumexp(logits[r, :V]) - logits[r, labels[r]] in fp32 (0 where the label is negative): the per-token
+ * cross entropy GPTModel.forward returns when `labels` is given (post_language_model_processing,
+ * MP/model/llava/gpt_model.py:27-51 -> vocab_parallel_cross_entropy on `.float()` logits; TP = 1).  The caller shifts
+ * labels and applies the loss mask / mean as loss_func does (EX/llava/pretrain_megatron_llava.py:101-121). */
+int lp_cross_entropy(const void* logits, int logits_fp32, long long ld, const long long* labels, float* loss, int rows,
+                     int V, void* stream);
 
 /* Standalone pixel_shuffle(x, scale_factor=2) (EV/llava_multiimg_siglip_anyres.py:165-176): x bf16 [M, D] with
  * M = B*side*side rows -> out [M/4, 4*D].  (The fused path never materialises x: lp_layernorm's shuffle store.) */

@@ -72,6 +72,7 @@ _SIGS = {
     "lp_rope_inplace": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lp_embed_merge": (_i, [_vp, _i, _ll, _i, _vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp]),
     "lp_im2col_patch14": (_i, [_vp, _i, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "lp_cross_entropy": (_i, [_vp, _i, _ll, _vp, _vp, _i, _i, _vp]),
     "lp_pixel_shuffle": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "lp_vit_workspace_bytes": (_sz, [_P(VitDims), _i]),
     "lp_vit_forward": (_i, [_P(VitDims), _P(VitWeights), _vp, _i, _i, _vp, _ll, _i, _vp, _sz, _vp]),

@@ -375,7 +375,7 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
   if (variant & 2) {  // two query tiles per CTA (lp_attn2.cu)
     ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
     note_launch();
-    return launch_attn2(tm, a, head_dim, causal, stream);
+    return launch_attn2(tm, a, head_dim, causal, (variant >> 2) & 3, stream);
   }
   const bool ptm = (variant & 1) != 0;
   ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);

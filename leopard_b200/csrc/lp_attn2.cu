@@ -27,6 +27,19 @@ __device__ __forceinline__ float ex2a(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 1.1e-4 — below the
+// bf16 rounding of P): offloads part of the softmax exponentials from the 16-lane/clk MUFU unit, which is the
+// co-bottleneck of attention on sm_100 (as many MUFU cycles as MMA cycles per tile at head_dim 128).
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.0f);           // f in [-0.5, 0.5]
+  float p = fmaf(f, 0.05459282547f, 0.24221783876f);
+  p = fmaf(p, f, 0.69336861372f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // * 2^round(x)
+}
+
 #define LP_TMEM_ST_16(regs, taddr)                                                                                  \
   asm volatile(                                                                                                     \
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
@@ -36,7 +49,8 @@ __device__ __forceinline__ float ex2a(float x) {
       "r"(regs[14]), "r"(regs[15])                                                                                  \
       : "memory")
 
-template <int DH, bool CAUSAL>
+// EMU: how many of every 4 exponentials are evaluated with ex2_fma instead of MUFU.EX2 (0, 1 or 2)
+template <int DH, bool CAUSAL, int EMU>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) {
   constexpr int NB = (DH + 63) / 64;
@@ -245,8 +259,11 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2a(fmaf(__uint_as_float(v[c * 32 + i]), args.scale_log2, neg_m));
-            const float p1 = ex2a(fmaf(__uint_as_float(v[c * 32 + i + 1]), args.scale_log2, neg_m));
+            const float x0 = fmaf(__uint_as_float(v[c * 32 + i]), args.scale_log2, neg_m);
+            const float x1 = fmaf(__uint_as_float(v[c * 32 + i + 1]), args.scale_log2, neg_m);
+            // compile-time pattern: element (i & 3) < EMU of each group of four goes to the FMA pipe
+            const float p0 = ((i & 3) < EMU) ? ex2_fma(x0) : ex2a(x0);
+            const float p1 = (((i + 1) & 3) < EMU) ? ex2_fma(x1) : ex2a(x1);
             const uint32_t u = pack_bf16x2(p0, p1);
             const float2 f = unpack_bf16x2(u);
             l_sum += f.x + f.y;
@@ -294,11 +311,11 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   }
 }
 
-template <int DH, bool CAUSAL>
+template <int DH, bool CAUSAL, int EMU>
 static int launch2(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream) {
   constexpr int NB = (DH + 63) / 64;
   constexpr int SMEM = 6 * NB * A2_BOX + 256 + 1024;
-  auto kern = attn2_fwd_kernel<DH, CAUSAL>;
+  auto kern = attn2_fwd_kernel<DH, CAUSAL, EMU>;
   static bool configured = false;
   if (!configured) {
     LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -310,9 +327,17 @@ static int launch2(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream
   return 0;
 }
 
-int launch_attn2(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, cudaStream_t stream) {
-  if (head_dim == 72) return launch2<80, false>(tm, a, stream);
-  return causal ? launch2<128, true>(tm, a, stream) : launch2<128, false>(tm, a, stream);
+int launch_attn2(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, int emu, cudaStream_t stream) {
+  if (head_dim == 72) {
+    if (emu == 2) return launch2<80, false, 2>(tm, a, stream);
+    return emu == 1 ? launch2<80, false, 1>(tm, a, stream) : launch2<80, false, 0>(tm, a, stream);
+  }
+  if (causal) {
+    if (emu == 2) return launch2<128, true, 2>(tm, a, stream);
+    return emu == 1 ? launch2<128, true, 1>(tm, a, stream) : launch2<128, true, 0>(tm, a, stream);
+  }
+  if (emu == 2) return launch2<128, false, 2>(tm, a, stream);
+  return emu == 1 ? launch2<128, false, 1>(tm, a, stream) : launch2<128, false, 0>(tm, a, stream);
 }
 
 }  // namespace lp

@@ -253,6 +253,40 @@ pixel_shuffle_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict
   for (int c = threadIdx.x; c < (D >> 3); c += blockDim.x) dp[c] = sp[c];
 }
 
+// ---- per-token cross entropy over the vocabulary (Megatron forward with labels) -----------------------------------
+// loss[r] = logsumexp(logits[r, :V]) - logits[r, label[r]]   (fp32 math; label < 0 -> 0); one CTA per row
+template <typename T>
+__global__ void __launch_bounds__(256)
+cross_entropy_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+                     float* __restrict__ loss, int V) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const T* row = logits + (long long)r * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += 256) mx = fmaxf(mx, (float)row[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += 256) s += __expf((float)row[i] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const long long lab = labels[r];
+    loss[r] = (lab >= 0 && lab < V) ? (logf(t) + mx - (float)row[lab]) : 0.f;
+  }
+}
+
 }  // namespace lp
 
 using namespace lp;
@@ -378,6 +412,20 @@ extern "C" int lp_pixel_shuffle(const void* x, long long ldx, void* out, long lo
   note_launch();
   pixel_shuffle_kernel<<<M, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(out), ldo, side, D);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lp_cross_entropy(const void* logits, int logits_fp32, long long ld, const long long* labels, float* loss,
+                                int rows, int V, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(rows > 0 && V > 0 && logits && labels && loss, "lp_cross_entropy: bad arguments rows=%d V=%d", rows, V);
+  ProfScope prof(9, rows, V, 0, stream);
+  note_launch();
+  if (logits_fp32)
+    cross_entropy_kernel<float><<<rows, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), ld, labels, loss, V);
+  else
+    cross_entropy_kernel<bf16><<<rows, 256, 0, stream>>>(reinterpret_cast<const bf16*>(logits), ld, labels, loss, V);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -520,7 +520,11 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     const double a_bytes = 2.0 * M * K, w_bytes = 2.0 * N * K;
     if (a_bytes <= l2_budget) args.group_m = args.num_m_blk;                 // A resident, W tiles read once
     else if (w_bytes <= l2_budget) args.group_m = max(1, sms / args.num_n_blk);  // W resident, A read once
-    else args.group_m = 16;
+    else {  // neither fits: keep a group's A rows (~half the L2 budget) resident while W streams once per group
+      const double a_blk_bytes = 2.0 * bm_unit * K;
+      args.group_m = (int)(0.5 * l2_budget / a_blk_bytes);
+      if (args.group_m < 1) args.group_m = 1;
+    }
     if (args.group_m > args.num_m_blk) args.group_m = args.num_m_blk;
     args.prefetch_a = a_bytes > l2_budget ? 1 : 0;  // activations that cannot stay L2-resident are prefetched too
   }

@@ -10,7 +10,7 @@ tiles + [global]; ids -100 (padding) read embedding row 0 (vlm_model.py:226); `i
 "no image" dummy (vlm_model.py:518; dummy = zeros(1, 10), pretrain_megatron_llava.py:188); a feature/slot count
 mismatch raises AssertionError with the reference's message (vlm_model.py:528-529).  The attention mask is ignored
 exactly like the flash-attention path of the reference (causal only).  Backward / optimizer (§8f-1) are not part of
-this round: `labels` returns the masked-CE inputs' logits path only via forward(); training raises NotImplementedError.
+this round: forward(labels=...) returns the per-token loss [b, s] (lp_cross_entropy), backward is not available.
 """
 from __future__ import annotations
 
@@ -58,8 +58,6 @@ class GPTModel:
     def forward(self, input_ids, position_ids=None, attention_mask=None, retriever_input_ids=None,
                 retriever_position_ids=None, retriever_attn_mask=None, labels=None, tokentype_ids=None,
                 inference_params=None, images=None):
-        if labels is not None:
-            raise NotImplementedError("loss / backward (SURVEY.md §8f-1) is not part of the prefill path yet")
         eng = self.engine
         b, s = input_ids.shape
         has_img = images is not None and images.shape[-1] > 100  # vlm_model.py:518
@@ -84,7 +82,12 @@ class GPTModel:
         else:
             pos = position_ids.reshape(-1)
         logits, _ = eng.decoder(x, pos, [i * s for i in range(b + 1)], "all", torch.bfloat16)
-        return logits.view(b, s, -1)
+        if labels is None:
+            return logits.view(b, s, -1)
+        # post_language_model_processing (gpt_model.py:27-51): per-token CE of the fp32 logits against `labels`
+        # (already shifted by get_batch, pretrain_megatron_llava.py:86-88); masking / averaging stays in loss_func
+        from . import ops
+        return ops.cross_entropy(logits, labels.reshape(-1).clamp(min=-1)).view(b, s)
 
     __call__ = forward
 

@@ -159,3 +159,14 @@ def attention_cross(q, kv, B, Tq, Tk, n_heads, n_kv_heads, head_dim, k_off, v_of
                                        _lib.stream_ptr())
     _lib.check(rc, "lp_attention_cross")
     return out
+
+
+def cross_entropy(logits, labels):
+    """per-row CE in fp32: logits [R, V] (bf16 or fp32), labels int64 [R] (negative = ignored -> 0) (lp_cross_entropy)."""
+    R, V = logits.shape
+    out = torch.empty((R,), device=logits.device, dtype=torch.float32)
+    labels = labels.to(logits.device, torch.long).contiguous()
+    rc = _lib.lib().lp_cross_entropy(_lib.ptr(logits), 1 if logits.dtype == torch.float32 else 0, logits.stride(0),
+                                     _lib.ptr(labels), _lib.ptr(out), R, V, _lib.stream_ptr())
+    _lib.check(rc, "lp_cross_entropy")
+    return out

@@ -150,3 +150,10 @@ def test_megatron_provider_matches_oracle(small):
         assert rel_err(l2[i], om.decoder_forward(ck, cfg, e2[i], torch.arange(64))) < 3e-2
     with pytest.raises(AssertionError, match="doesn't match"):
         model(tokens, None, None, images=pix[:1].to(torch.bfloat16))
+    # forward with labels -> per-token CE (loss_func masks / averages it, pretrain_megatron_llava.py:101-121)
+    labels = torch.randint(0, cfg.dec.vocab, (1, s))
+    labels[0, 5:20] = -100
+    loss = model(tokens, torch.arange(s)[None], None, labels=labels, images=pix.to(torch.bfloat16))
+    ref_loss = torch.nn.functional.cross_entropy(ref.float(), labels[0], ignore_index=-100, reduction="none")
+    assert loss.shape == (1, s) and float((loss[0].cpu() - ref_loss).abs().max()) < 0.08
+    assert bool((loss[0, 5:20] == 0).all())
