@@ -287,8 +287,10 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             // compile-time pattern: element (i & 3) < EMU of each group of four goes to the FMA pipe
             const float p0 = ((i & 3) < EMU) ? ex2_fma(x0) : ex2a(x0);
             const float p1 = (((i + 1) & 3) < EMU) ? ex2_fma(x1) : ex2a(x1);
-            acc2 = add2(acc2, pk2(p0, p1));      // row sum in fp32 from the unrounded probabilities
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+            const uint32_t u = pack_bf16x2(p0, p1);
+            const float2 f = unpack_bf16x2(u);   // row sum from the bf16-rounded values the MMA will actually use
+            acc2 = add2(acc2, pk2(f.x, f.y));
+            pk[i >> 1] = u;
           }
           LP_TMEM_ST_16(pk, s_addr + c * 16);  // P_q(j) overwrites the first 64 columns of S_q (already in registers)
         }

@@ -4,7 +4,8 @@
 // (evaluations/models/llava_multiimg_siglip_anyres.py:291-320, driven by `generate(..., max_new_tokens=128,
 // use_cache=True)` at :448-452): with B = 1 and no padding the rebuilt mask is all ones and the position is the
 // number of cached rows.  HBM-bound: every weight is streamed once per token (M = 1 rows through
-// the tcgen05 GEMM's TMA pipeline), attention is a SIMT GQA kernel reading the bf16 KV cache once.
+// the tcgen05 GEMM's TMA pipeline), attention is a split-K SIMT GQA kernel (heads x 16 key ranges, 4 keys in flight per
+// warp) reading the bf16 KV cache once, plus a tiny combine pass.
 #include "lp_common.cuh"
 #include "lp_host.h"
 #include "../../include/leopard_b200.h"
@@ -14,58 +15,103 @@ namespace lp {
 int rope_table_base(int pos_base, const float* inv_freq, float* cs, float* sn, int S, int half, cudaStream_t stream);
 
 constexpr int DEC_WARPS = 8;
+constexpr int DEC_SPLITS = 16;  // key ranges per head -> heads * DEC_SPLITS CTAs (>= 1 wave on 148 SMs)
 
-// one CTA per query head; warps stride over cached positions; head_dim = 128 (4 dims per lane)
+// Split-K decode attention, pass 1: CTA (head h, split s) scans keys [s*chunk, (s+1)*chunk) of kv head h/group.
+// A warp handles FOUR keys per step (8 lanes x 16 dims each, two 16-byte loads per lane, 3-step shuffle reduce) so that
+// four independent load->dot->exp chains are in flight; partial (m, l, acc[128]) go to `part` for the combine pass.
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-decode_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc, int n_ctx,
-                   int kv_w, int group, float scale_log2, bf16* __restrict__ out) {
-  const int h = blockIdx.x, g = h / group;
+decode_attn_partial_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+                           int n_ctx, int kv_w, int group, float scale_log2, float* __restrict__ part) {
+  const int h = blockIdx.x, split = blockIdx.y, g = h / group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS], s_acc[DEC_WARPS][128];
-  float qv[4];
+  const int sub = lane >> 3, l8 = lane & 7;  // key slot within the warp step, 16-dim slice of the head
+  const int chunk = (n_ctx + DEC_SPLITS - 1) / DEC_SPLITS;
+  const int t_begin = split * chunk, t_end = min(n_ctx, t_begin + chunk);
+  __shared__ float s_m[DEC_WARPS * 4], s_l[DEC_WARPS * 4], s_acc[DEC_WARPS * 4][128];
+  float qv[16];
   {
-    const uint2 u = *reinterpret_cast<const uint2*>(q + h * 128 + lane * 4);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    qv[0] = a.x * scale_log2; qv[1] = a.y * scale_log2; qv[2] = b.x * scale_log2; qv[3] = b.y * scale_log2;
-  }
-  float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t = warp; t < n_ctx; t += DEC_WARPS) {
-    const uint2 ku = *reinterpret_cast<const uint2*>(kc + (long long)t * kv_w + g * 128 + lane * 4);
-    const uint2 vu = *reinterpret_cast<const uint2*>(vc + (long long)t * kv_w + g * 128 + lane * 4);
-    const float2 k0 = unpack_bf16x2(ku.x), k1 = unpack_bf16x2(ku.y);
-    float s = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y;
+    const uint4 u0 = *reinterpret_cast<const uint4*>(q + h * 128 + l8 * 16);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(q + h * 128 + l8 * 16 + 8);
+    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = unpack_bf16x2(w[i]);
+      qv[2 * i] = f.x * scale_log2;
+      qv[2 * i + 1] = f.y * scale_log2;
+    }
+  }
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int t = t_begin + warp * 4 + sub; t < t_end; t += DEC_WARPS * 4) {
+    const bf16* kp = kc + (long long)t * kv_w + g * 128 + l8 * 16;
+    const bf16* vp = vc + (long long)t * kv_w + g * 128 + l8 * 16;
+    const uint4 k0 = *reinterpret_cast<const uint4*>(kp), k1 = *reinterpret_cast<const uint4*>(kp + 8);
+    const uint4 v0 = *reinterpret_cast<const uint4*>(vp), v1 = *reinterpret_cast<const uint4*>(vp + 8);
+    const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = unpack_bf16x2(kw[i]);
+      s += qv[2 * i] * f.x + qv[2 * i + 1] * f.y;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
     const float mn = fmaxf(m, s);
     const float corr = exp2f(m - mn), p = exp2f(s - mn);
-    const float2 v0 = unpack_bf16x2(vu.x), v1 = unpack_bf16x2(vu.y);
+    const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     l = l * corr + p;
-    acc[0] = acc[0] * corr + p * v0.x; acc[1] = acc[1] * corr + p * v0.y;
-    acc[2] = acc[2] * corr + p * v1.x; acc[3] = acc[3] * corr + p * v1.y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = unpack_bf16x2(vw[i]);
+      acc[2 * i] = acc[2 * i] * corr + p * f.x;
+      acc[2 * i + 1] = acc[2 * i + 1] * corr + p * f.y;
+    }
     m = mn;
   }
-  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  // note: a lane whose key slots were all beyond t_end keeps m = -inf, l = 0 (handled by the combine weights)
+  const int slot = warp * 4 + sub;
+  if (l8 == 0) { s_m[slot] = m; s_l[slot] = l; }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) s_acc[warp][lane * 4 + i] = acc[i];
+  for (int i = 0; i < 16; ++i) s_acc[slot][l8 * 16 + i] = acc[i];
   __syncthreads();
-  if (warp == 0) {
+  if (threadIdx.x < 128) {
+    const int d = threadIdx.x;
     float mm = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) mm = fmaxf(mm, s_m[w]);
-    float ll = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < DEC_WARPS * 4; ++w) mm = fmaxf(mm, s_m[w]);
+    float ll = 0.f, o = 0.f;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) {
+    for (int w = 0; w < DEC_WARPS * 4; ++w) {
       const float c = (s_m[w] == -INFINITY) ? 0.f : exp2f(s_m[w] - mm);
       ll += s_l[w] * c;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] += s_acc[w][lane * 4 + i] * c;
+      o += s_acc[w][d] * c;
     }
-    const float inv = 1.0f / ll;
-    uint2 u;
-    u.x = pack_bf16x2(o[0] * inv, o[1] * inv);
-    u.y = pack_bf16x2(o[2] * inv, o[3] * inv);
-    *reinterpret_cast<uint2*>(out + h * 128 + lane * 4) = u;
+    float* pp = part + ((long long)h * DEC_SPLITS + split) * 130;
+    pp[2 + d] = o;
+    if (d == 0) { pp[0] = mm; pp[1] = ll; }
   }
+}
+
+// pass 2: merge the DEC_SPLITS partials of each head
+__global__ void __launch_bounds__(128)
+decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out) {
+  const int h = blockIdx.x, d = threadIdx.x;
+  const float* pp = part + (long long)h * DEC_SPLITS * 130;
+  float mm = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < DEC_SPLITS; ++s) mm = fmaxf(mm, pp[s * 130]);
+  float ll = 0.f, o = 0.f;
+#pragma unroll
+  for (int s = 0; s < DEC_SPLITS; ++s) {
+    const float m = pp[s * 130];
+    const float c = (m == -INFINITY) ? 0.f : exp2f(m - mm);
+    ll += pp[s * 130 + 1] * c;
+    o += pp[s * 130 + 2 + d] * c;
+  }
+  out[h * 128 + d] = __float2bfloat16(o / ll);
 }
 
 }  // namespace lp
@@ -76,7 +122,8 @@ static inline size_t bf(size_t n) { return n * 2; }
 
 extern "C" size_t lp_decode_workspace_bytes(const lp_dec_dims* d) {
   const size_t qkv_w = (size_t)(d->heads + 2 * d->kv_heads) * d->head_dim;
-  return 256 * 8 + bf(2 * (size_t)d->hidden) * 2 + bf(qkv_w) + bf((size_t)d->ffn) + (size_t)d->head_dim * 4 + 64 * 4;
+  return 256 * 9 + bf(2 * (size_t)d->hidden) * 2 + bf(qkv_w) + bf((size_t)d->ffn) + (size_t)d->head_dim * 4 + 64 * 4 +
+         (size_t)d->heads * DEC_SPLITS * 130 * 4;
 }
 
 extern "C" int lp_decode_step(const lp_dec_dims* d, const lp_dec_weights* w, const void* embed_table, long long ld_embed,
@@ -100,6 +147,7 @@ extern "C" int lp_decode_step(const lp_dec_dims* d, const lp_dec_weights* w, con
   float* cs = (float*)take(hd / 2 * 4);
   float* sn = (float*)take(hd / 2 * 4);
   int* plan = (int*)take(16);
+  float* part = (float*)take((size_t)d->heads * DEC_SPLITS * 130 * 4);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
   int rc;
 #define LP_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
@@ -120,9 +168,10 @@ extern "C" int lp_decode_step(const lp_dec_dims* d, const lp_dec_weights* w, con
                                   stream));
     {
       ProfScope prof(8, position + 1, d->heads, 0, stream);
-      note_launch();
-      decode_attn_kernel<<<d->heads, DEC_WARPS * 32, 0, stream>>>(qkv, kc, vc, position + 1, kv_w,
-                                                                 d->heads / d->kv_heads, scale_log2, att);
+      note_launch(2);
+      decode_attn_partial_kernel<<<dim3(d->heads, DEC_SPLITS), DEC_WARPS * 32, 0, stream>>>(
+          qkv, kc, vc, position + 1, kv_w, d->heads / d->kv_heads, scale_log2, part);
+      decode_attn_combine_kernel<<<d->heads, 128, 0, stream>>>(part, att);
       LP_CHECK_CUDA(cudaGetLastError());
     }
     LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, 1, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 128, stream));

@@ -100,3 +100,42 @@ def model_provider(pre_process=True, post_process=True):
                                "plumbing is outside the hot path)")
     native = load_hf(st["cfg"], st["getter"], st["device"])
     return GPTModel(st["cfg"], native, pre_process, post_process)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Idefics2 provider (Pai-Megatron-Patch/examples/idefics2/pretrain_megatron_idefics2.py:36-54)
+# ----------------------------------------------------------------------------------------------------------------
+class Idefics2GPTModel:
+    """Forward-only stand-in for megatron_patch.model.idefics2.gpt_model.GPTModel (:95-122): same positional /
+    keyword signature, `pixel_values [b, n, 3, H, W]` + `pixel_attention_mask [b, n, H, W]`, logits `[b, s, V]` or the
+    per-token loss `[b, s]` when `labels` is given.  b = 1 (the shipped script runs micro-batch 1)."""
+
+    def __init__(self, cfg, getter, device):
+        from .idefics2 import Idefics2Engine, Idefics2Weights
+        self.cfg = cfg
+        self.engine = Idefics2Engine(cfg, Idefics2Weights(cfg, getter, device))
+
+    def set_input_tensor(self, t):
+        self.input_tensor = t
+
+    @torch.no_grad()
+    def forward(self, input_ids, position_ids=None, attention_mask=None, retriever_input_ids=None,
+                retriever_position_ids=None, retriever_attn_mask=None, labels=None, images=None,
+                inference_params=None, pixel_values=None, pixel_attention_mask=None):
+        logits, _, _ = self.engine.prefill(input_ids, pixel_values, pixel_attention_mask, "all")
+        logits = logits[None]
+        if labels is None:
+            return logits
+        from . import ops
+        b, s, _ = logits.shape
+        return ops.cross_entropy(logits[0].contiguous(), labels.reshape(-1).clamp(min=-1)).view(b, s)
+
+    __call__ = forward
+
+
+def idefics2_model_provider(cfg, hf_getter, device="cuda", pre_process=True, post_process=True):
+    """`model_provider` twin for Idefics2: `cfg` = leopard_b200.config.Idefics2Config, `hf_getter(name)` returns HF
+    Idefics2-layout tensors (the layout `AutoConfig/…from_pretrained(args.load)` refers to in the reference)."""
+    if not (pre_process and post_process):
+        raise NotImplementedError("pipeline parallel stages are out of scope (the reference runs PP = 1)")
+    return Idefics2GPTModel(cfg, hf_getter, device)

@@ -93,3 +93,19 @@ def test_full_resolution_image_tile_counts(small):
     hid = oi.vision_tower(ck, cfg.vit, pv[0].float(), torch.ones(1, 70, 70, dtype=torch.bool))
     ref = oi.connector(ck, cfg.perceiver, hid, torch.ones(1, 4900, dtype=torch.bool))
     assert rel_err(feats, ref[0]) < 3e-2
+
+
+def test_megatron_style_provider_logits_and_loss(small):
+    import gen_idefics2_goldens as gg
+    from leopard_b200.megatron import idefics2_model_provider
+    cfg, ck, _ = small
+    model = idefics2_model_provider(cfg, lambda n: ck[n], "cuda:0")
+    ids, pv, pm, _ = gg.make_inputs(cfg)
+    ref = oi.prefill_logits(ck, cfg, ids, pv, pm)[0]
+    logits = model(ids, None, None, pixel_values=pv, pixel_attention_mask=pm)
+    assert rel_err(logits[0], ref) < 3e-2
+    labels = torch.randint(0, cfg.dec.vocab, ids.shape)
+    labels[0, :5] = -100
+    loss = model(ids, None, None, labels=labels, pixel_values=pv, pixel_attention_mask=pm)
+    ref_loss = torch.nn.functional.cross_entropy(ref.float(), labels[0], ignore_index=-100, reduction="none")
+    assert loss.shape == ids.shape and float((loss[0].cpu() - ref_loss).abs().max()) < 0.08

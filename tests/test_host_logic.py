@@ -141,3 +141,32 @@ def test_bench_workload_bookkeeping():
     assert pix.shape == (28, 3, 364, 364) and float(pix.min()) >= -1 and float(pix.max()) <= 1
     fm = bench.flops_model(n_crops, S, cfg)
     assert abs(fm["total"] / 1e12 - 90.5) < 0.3  # 90.5 TFLOP per cfg3 request
+
+
+def test_from_pretrained_reads_hf_checkpoint_dir(tmp_path):
+    """config.json + safetensors in the HF layout the reference converter writes -> getter -> native re-layout (CPU)."""
+    import json
+    from safetensors.torch import save_file
+    from leopard_b200 import hf
+    cfg = tiny_cfg()
+    ck = SyntheticCheckpoint(cfg)
+    tensors = {n: ck[n].contiguous() for n, _, _ in tensor_specs(cfg)}
+    names = sorted(tensors)
+    save_file({n: tensors[n] for n in names[: len(names) // 2]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({n: tensors[n] for n in names[len(names) // 2:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    (tmp_path / "config.json").write_text(json.dumps({
+        "image_token_index": cfg.image_token_index, "projector_hidden_act": "gelu",
+        "text_config": {"hidden_size": 4096, "intermediate_size": 14336, "num_attention_heads": 32,
+                        "num_key_value_heads": 8, "num_hidden_layers": 1, "vocab_size": 512, "rope_theta": 500000.0,
+                        "rope_scaling": {"factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                                         "original_max_position_embeddings": 8192, "rope_type": "llama3"},
+                        "rms_norm_eps": 1e-5},
+        "vision_config": {"hidden_size": 1152, "intermediate_size": 4304, "num_attention_heads": 16,
+                          "num_hidden_layers": 1, "image_size": 364, "patch_size": 14, "layer_norm_eps": 1e-6}}))
+    m = hf.myLlavaForConditionalGeneration.from_pretrained(str(tmp_path), torch_dtype=torch.float32)
+    assert m.config.dec.layers == 1 and m.config.vit.layers == 1 and m.config.dec.rope_scaling.factor == 8.0
+    nw = load_hf(m.config, m._pending, "cpu")
+    assert torch.equal(nw.embed, ck["language_model.model.embed_tokens.weight"])
+    from leopard_b200._lib import NativeError
+    with pytest.raises(NativeError, match="CUDA"):
+        m.to("cpu")
