@@ -7,7 +7,8 @@
 //   warp 0      TMA producer : Q_A, Q_B once; K_j, V_j (128 rows) into 2-deep rings shared by both tiles
 //   warp 1      MMA issuer   : S_q(j) = Q_q K_j^T  (SS, into TMEM S_q);  O_q += P_q(j) V_j  (A = P from TMEM, V MN-major)
 //   warps 2-5   softmax A    : one thread per row, whole S row in registers (single TMEM pass), exp2 online softmax,
-//   warps 6-9   softmax B      lazy O rescale (threshold 2^8), P -> bf16 -> TMEM (aliases S_q), final O/l -> global
+//   warps 6-9   softmax B      lazy O rescale (threshold 2^8), P -> bf16 -> TMEM (aliases S_q) published in two halves so
+//                              P·V starts before the row is fully exponentiated, final O/l -> global
 // TMEM map (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512).
 // Ordering facts relied upon: tcgen05.mma ops of one thread execute in issue order, and tcgen05.commit covers ALL
 // previously issued MMAs — so s_full_q(j) also implies P_q(j-1)·V has retired (O_q may be rescaled), and S_q(j+1),
@@ -92,8 +93,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   uint64_t* v_full = k_empty + 2;                                   // [2]
   uint64_t* v_empty = v_full + 2;                                   // [2]
   uint64_t* s_full = v_empty + 2;                                   // [2] per q tile
-  uint64_t* p_full = s_full + 2;                                    // [2] per q tile
-  uint64_t* o_done = p_full + 2;                                    // [2] per q tile
+  uint64_t* p_full = s_full + 2;                                    // [4]: q tile x {first, second} half of P
+  uint64_t* o_done = p_full + 4;                                    // [2] per q tile
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -119,7 +120,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[2 * i], 128);
+      mbar_init(&p_full[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
@@ -184,16 +186,21 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       };
       auto issue_PV = [&](int q, int j, int n_q) {
         const int st = j & 1;
-        mbar_wait(&p_full[q], j & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
-        tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + V_OFF + st * HEAD_BYTES);
         const uint32_t d_o = tmem_base + TM_O + (uint32_t)q * 128;
         const uint32_t a_t = tmem_base + TM_S + (uint32_t)q * 128;
 #pragma unroll
-        for (int ks = 0; ks < KS_PV; ++ks) {
-          const uint64_t vdesc = umma_desc_sw128(v_addr + ks * 2048, A2_BOX, 1024);
-          umma_ts(d_o, a_t + ks * 8, vdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        for (int half = 0; half < 2; ++half) {
+          // P arrives in two halves (kv columns 0-63, 64-127): the first four K steps start while the softmax
+          // warpgroup is still exponentiating the second half
+          mbar_wait(&p_full[2 * q + half], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = half * (KS_PV / 2); ks < (half + 1) * (KS_PV / 2); ++ks) {
+            const uint64_t vdesc = umma_desc_sw128(v_addr + ks * 2048, A2_BOX, 1024);
+            umma_ts(d_o, a_t + ks * 8, vdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         const bool last_reader = (q == 1) || !(j < nB);
         if (last_reader) umma_commit(&v_empty[st]);
@@ -293,15 +300,17 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             pk[i >> 1] = u;
           }
           LP_TMEM_ST_16(pk, s_addr + c * 16);  // P_q(j) overwrites the first 64 columns of S_q (already in registers)
+          if (c & 1) {  // half of P complete (chunks 0-1 / 2-3): publish it
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[2 * q + (c >> 1)]);
+          }
         }
         {
           float a0, a1;
           upk2(acc2, a0, a1);
           l_sum += a0 + a1;
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[q]);
       }
       // ---- epilogue
       mbar_wait(&o_done[q], 0);

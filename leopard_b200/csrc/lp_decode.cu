@@ -26,6 +26,7 @@ decode_attn_partial_kernel(const bf16* __restrict__ q, const bf16* __restrict__ 
   const int h = blockIdx.x, split = blockIdx.y, g = h / group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane >> 3, l8 = lane & 7;  // key slot within the warp step, 16-dim slice of the head
+  const unsigned gmask = 0xFFu << (sub * 8);
   const int chunk = (n_ctx + DEC_SPLITS - 1) / DEC_SPLITS;
   const int t_begin = split * chunk, t_end = min(n_ctx, t_begin + chunk);
   __shared__ float s_m[DEC_WARPS * 4], s_l[DEC_WARPS * 4], s_acc[DEC_WARPS * 4][128];
@@ -56,9 +57,10 @@ decode_attn_partial_kernel(const bf16* __restrict__ q, const bf16* __restrict__ 
       const float2 f = unpack_bf16x2(kw[i]);
       s += qv[2 * i] * f.x + qv[2 * i + 1] * f.y;
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    // only the 8 lanes that share this key take part: key slots of one warp run different trip counts at the tail
+    s += __shfl_xor_sync(gmask, s, 4);
+    s += __shfl_xor_sync(gmask, s, 2);
+    s += __shfl_xor_sync(gmask, s, 1);
     const float mn = fmaxf(m, s);
     const float corr = exp2f(m - mn), p = exp2f(s - mn);
     const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};

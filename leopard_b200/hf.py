@@ -294,7 +294,9 @@ class myLlavaForConditionalGeneration:
             lab = labels.to(logits.device)
             if lab.shape[1] != logits.shape[1]:
                 raise ValueError("labels must already be expanded to the merged length")
-            loss = torch.nn.functional.cross_entropy(logits[0, :-1].float(), lab[0, 1:], ignore_index=-100)
+            per_tok = ops.cross_entropy(logits[0, :-1].contiguous(), lab[0, 1:].clamp(min=-1))   # lp_cross_entropy
+            n_valid = (lab[0, 1:] >= 0).sum().clamp(min=1)
+            loss = per_tok.sum() / n_valid
         if return_dict is False:
             return tuple(v for v in (loss, logits, past) if v is not None)
         return LlavaCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past)
