@@ -267,7 +267,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int m_blk, n_blk;
         tile_coords(args, tile, m_blk, n_blk);
         const int a_row = m_blk * BMT + (int)cta_rank * GEMM_BM;
-        const int b_row = n_blk * BN + (int)cta_rank * L::B_ROWS;
+        // ragged last column block: the MMA runs with N = n_rt (multiple of 32), so a pair splits n_rt, not BN
+        const int n_rt = min(BN, ((args.N - n_blk * BN) + 31) & ~31);
+        const int b_row = n_blk * BN + (CTA2 ? (int)cta_rank * (n_rt / 2) : 0);
         for (int kb = 0; kb < args.num_k_blk; ++kb) {
           // (an explicit cp.async.bulk.prefetch.tensor.L2 of the k-block 8 ahead was measured: every CTA of a
           //  row-block group re-requests the same W tile, and the doubled TMA/L2 request rate cost 10-30 %: removed)
@@ -292,12 +294,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BMT, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = unit; tile < num_tiles; tile += n_units) {
+        int m_blk_unused, n_blk;
+        tile_coords(args, tile, m_blk_unused, n_blk);
+        // the last column block of a ragged N issues narrower MMAs (N = valid columns rounded up to 32)
+        const uint32_t idesc = umma_idesc_bf16(BMT, min(BN, ((args.N - n_blk * BN) + 31) & ~31), 0, 0);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
