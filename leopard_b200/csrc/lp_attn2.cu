@@ -111,6 +111,24 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   const int nB = actB ? (CAUSAL ? min(n_total, 2 * qp + 2) : n_total) : 0;
   const int n_kv = max(nA, nB);
 
+  // K/V tile loader (producer thread only): tile j -> ring slot j & 1
+  auto load_kv = [&](int j) {
+    const int st = j & 1;
+    const uint32_t ph = (j >> 1) & 1;
+    mbar_wait(&k_empty[st], ph ^ 1);
+    mbar_arrive_expect_tx(&k_full[st], HEAD_BYTES);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      tma_load_3d(smem + K_OFF + st * HEAD_BYTES + b * A2_BOX, &tmQKV, &k_full[st],
+                  args.k_off + kv_head * args.hs + b * 64, j * 128, batch);
+    mbar_wait(&v_empty[st], ph ^ 1);
+    mbar_arrive_expect_tx(&v_full[st], HEAD_BYTES);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      tma_load_3d(smem + V_OFF + st * HEAD_BYTES + b * A2_BOX, &tmQKV, &v_full[st],
+                  args.v_off + kv_head * args.hs + b * 64, j * 128, batch);
+  };
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int i = 0; i < 2; ++i) {
@@ -125,6 +143,15 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
+    // start the first loads right away: they overlap the TMEM allocation and the CTA-wide barrier below
+    for (int q = 0; q < (actB ? 2 : 1); ++q) {
+      mbar_arrive_expect_tx(&q_full[q], HEAD_BYTES);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        tma_load_3d(smem + Q_OFF + q * HEAD_BYTES + b * A2_BOX, &tmQKV, &q_full[q],
+                    args.q_off + head * args.hs + b * 64, q0A + q * 128, batch);
+    }
+    for (int j = 0; j < min(2, n_kv); ++j) load_kv(j);
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr_smem, 512);
@@ -136,31 +163,9 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (tiles 0, 1 already in flight)
     if (lane == 0) {
-      for (int q = 0; q < (actB ? 2 : 1); ++q) {
-        mbar_arrive_expect_tx(&q_full[q], HEAD_BYTES);
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-          tma_load_3d(smem + Q_OFF + q * HEAD_BYTES + b * A2_BOX, &tmQKV, &q_full[q],
-                      args.q_off + head * args.hs + b * 64, q0A + q * 128, batch);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], HEAD_BYTES);
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-          tma_load_3d(smem + K_OFF + st * HEAD_BYTES + b * A2_BOX, &tmQKV, &k_full[st],
-                      args.k_off + kv_head * args.hs + b * 64, j * 128, batch);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], HEAD_BYTES);
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-          tma_load_3d(smem + V_OFF + st * HEAD_BYTES + b * A2_BOX, &tmQKV, &v_full[st],
-                      args.v_off + kv_head * args.hs + b * 64, j * 128, batch);
-      }
+      for (int j = 2; j < n_kv; ++j) load_kv(j);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
