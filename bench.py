@@ -49,8 +49,7 @@ def load_traffic():
     if not cands:
         return None
     d = json.loads(cands[-1].read_text())
-    return {"dram_bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"],
-            "algorithmic_bytes_per_launch": d["algorithmic_bytes"]["total"], "source": cands[-1].name}
+    return d["dram_bytes_read"] + d["dram_bytes_write"], d["algorithmic_bytes"]["total"], cands[-1].name
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -323,7 +322,10 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel M={m} N={nn} K={k} (x{cnt}/step)", "achieved": ach,
                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
                     "peak_kind": "sustained cuBLAS bf16, " + peaks["source"], "avg_launch_ms": avg_ms,
-                    "share_of_step": ms_sum / step_ms_prof, "traffic": load_traffic()}
+                    "share_of_step": ms_sum / step_ms_prof, "traffic": None}
+        tr = load_traffic()
+        if tr is not None:  # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)
+            roofline.update(traffic=tr[0], traffic_algorithmic_bytes=tr[1], traffic_source="profiles/" + tr[2])
         fm = flops_model(n_crops, S, cfg)
         names = {1: "gemm", 2: "attention", 3: "norm", 4: "rope", 5: "merge", 6: "im2col", 7: "shuffle"}
         gemm_all = sum(v[0] for v in gemm_shapes.values())

@@ -104,12 +104,51 @@ norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__
   }
 }
 
+// RMSNorm for wide rows (D > 1280): the row is NOT kept in registers — pass 1 accumulates sum(x^2), pass 2 re-reads
+// the row (it was just fetched, so this hits L1/L2, HBM traffic stays 2 x rows x D x 2 B) and writes x * rstd * gamma.
+// Few registers -> 8 rows per CTA at full occupancy, which the register-resident variant (16 chunks/lane) cannot reach.
+__global__ void __launch_bounds__(256)
+rmsnorm_reread_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                      bf16* __restrict__ out, long long ldo, int M, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  float s = 0.f;
+#pragma unroll 4
+  for (int c = lane; c < nchunk; c += 32) {
+    const uint4 u = xr[c];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float rstd = rsqrtf(s / (float)D + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo);
+#pragma unroll 4
+  for (int c = lane; c < nchunk; c += 32) {
+    const uint4 u = xr[c];
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    uint4 y;
+    y.x = pack_bf16x2(a.x * rstd * g0.x, a.y * rstd * g0.y);
+    y.y = pack_bf16x2(b.x * rstd * g0.z, b.y * rstd * g0.w);
+    y.z = pack_bf16x2(cc.x * rstd * g1.x, cc.y * rstd * g1.y);
+    y.w = pack_bf16x2(d.x * rstd * g1.z, d.y * rstd * g1.w);
+    orow[c] = y;
+  }
+}
+
 template <bool RMS>
 static void launch_norm(const bf16* x, long long ldx, const float* g, const float* b, bf16* out, long long ldo, int M,
                         int D, float eps, int shuffle_side, cudaStream_t stream) {
   const int grid = (M + NORM_THREADS / 32 - 1) / (NORM_THREADS / 32);
   if (D <= 32 * 8 * 5)
     norm_kernel<RMS, 5><<<grid, NORM_THREADS, 0, stream>>>(x, ldx, g, b, out, ldo, M, D, eps, shuffle_side);
+  else if (RMS && shuffle_side == 0 && x != out)
+    rmsnorm_reread_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, g, out, ldo, M, D, eps);
   else
     norm_kernel<RMS, 16><<<grid, NORM_THREADS, 0, stream>>>(x, ldx, g, b, out, ldo, M, D, eps, shuffle_side);
 }
