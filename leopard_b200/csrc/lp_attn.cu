@@ -33,7 +33,6 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_named_barrier() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 template <int DH, bool CAUSAL, bool P_TMEM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
