@@ -494,7 +494,7 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     // wave-quantisation heuristic: minimise ceil(tiles / SMs) * (BN + per-tile overhead); the narrow tiles are
     // shared-memory-bandwidth bound on one CTA (A 4 KiB + B BN*32 B per K=16 step), hence their penalty
     const int cand[5] = {256, 224, 192, 160, 128};
-    const double pen[5] = {1.0, 1.03, 1.10, 1.15, 1.30};  // measured: wider tiles amortise the epilogue better
+    const double pen[5] = {1.0, 1.15, 1.10, 1.15, 1.30};  // measured: wider tiles amortise the epilogue better
     double best = 1e30;
     for (int i = 0; i < 5; ++i) {
       if (act == LP_ACT_SWIGLU && cand[i] % 64 != 0) continue;
@@ -525,9 +525,9 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     const double a_bytes = 2.0 * M * K, w_bytes = 2.0 * N * K;
     if (a_bytes <= l2_budget) args.group_m = args.num_m_blk;                 // A resident, W tiles read once
     else if (w_bytes <= l2_budget) args.group_m = max(1, sms / args.num_n_blk);  // W resident, A read once
-    else {  // neither fits: keep a group's A rows (~half the L2 budget) resident while W streams once per group
+    else {  // neither fits: keep a group's A rows (~half of the 126 MB L2) resident while W streams once per group
       const double a_blk_bytes = 2.0 * bm_unit * K;
-      args.group_m = (int)(0.5 * l2_budget / a_blk_bytes);
+      args.group_m = (int)(l2_budget / a_blk_bytes);
       if (args.group_m < 1) args.group_m = 1;
     }
     if (args.group_m > args.num_m_blk) args.group_m = args.num_m_blk;
