@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 1
+#define LP_ABI_VERSION 2
 
 enum lp_status { LP_OK = 0, LP_ERR_ARG = -1, LP_ERR_CUDA = -2 };
 
@@ -244,6 +244,55 @@ int lp_decode_step(const lp_dec_dims* dims, const lp_dec_weights* w, const void*
                    const long long* token_id, int position, void* kv_cache, long long kv_capacity, void* logits,
                    void* workspace, size_t ws_bytes, void* stream);
 
+/* The same step with the greedy loop state resident on the DEVICE, so that one step can be captured into a CUDA graph
+ * and replayed per token without host work (GenerationMixin's greedy search driven by `generate(...,
+ * max_new_tokens=128, use_cache=True)`, EV/llava_multiimg_siglip_anyres.py:448-452):
+ *   token_io:    DEVICE int64[1]; in = previously selected token, out = argmax(logits[0:vocab_valid]) (lowest index
+ *                among ties, as torch.argmax);
+ *   position_io: DEVICE int32[1]; in = number of cached rows (row written by this step), out = in + 1.  The caller
+ *                guarantees position < kv_capacity for every replay (out-of-range positions write nothing).
+ *   logits: fp32 [vocab] of the new position (kept for callers that sample differently). */
+int lp_decode_greedy_step(const lp_dec_dims* dims, const lp_dec_weights* w, const void* embed_table, long long ld_embed,
+                          long long* token_io, int* position_io, void* kv_cache, long long kv_capacity, void* logits,
+                          int vocab_valid, void* workspace, size_t ws_bytes, void* stream);
+
+/* The greedy step above captured once into a CUDA graph (on a private stream) and replayed per token: one
+ * cudaGraphLaunch instead of ~200 kernel launches.  All pointers are baked into the graph and must stay valid and
+ * unchanged until lp_decode_graph_destroy; token_io / position_io are read and advanced on the device by every replay.
+ * The handle owns only the cudaGraphExec_t. */
+typedef struct lp_decode_graph lp_decode_graph;
+int lp_decode_graph_create(const lp_dec_dims* dims, const lp_dec_weights* w, const void* embed_table,
+                           long long ld_embed, long long* token_io, int* position_io, void* kv_cache,
+                           long long kv_capacity, void* logits, int vocab_valid, void* workspace, size_t ws_bytes,
+                           lp_decode_graph** out);
+int lp_decode_graph_launch(lp_decode_graph* graph, void* stream);
+void lp_decode_graph_destroy(lp_decode_graph* graph);
+
+/* Decode implementation switch, returns the previous mode.  bit 0: 1 = HBM-streaming GEMV kernels with fused
+ * RMSNorm / RoPE + cache append / SwiGLU / residual (default), 0 = M = 1 rows through lp_gemm_bf16 (first
+ * implementation, lp_decode_step only).  bit 1: launch the step's kernels with programmatic dependent launch
+ * (griddepcontrol): the next kernel prefetches its weights into L2 while the previous one drains. */
+int lp_decode_set_mode(int mode);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * GPU image front-end (SURVEY.md §8 a3 + a5, "next" row f-3): one RGB uint8 image -> the ViT inputs it contributes.
+ *   rgb: DEVICE uint8 [H, W, 3] (what np.asarray(PIL.Image.convert('RGB')) holds), 16-byte aligned base.
+ *   out_global: [3, 364, 364] — SiglipImageProcessor.preprocess(image) (EV/llava_multiimg_siglip_anyres.py:403-404):
+ *     bicubic resize of the whole image to 364 x 364, x * rescale (float64, rounded to float32), (x - mean) / std.
+ *   out_tiles (target_w, target_h > 0, both multiples of 364; NULL otherwise): [(target_h/364)*(target_w/364), 3, 364,
+ *     364] — resize_and_pad_image(image, (target_w, target_h)) (EV/...anyres.py:102-140: aspect-preserving bicubic
+ *     resize pasted centred on black), divide_to_patches (:143-162, row-major tiles), each tile through the same
+ *     rescale / normalise (a 364 x 364 tile is not resized again).
+ *   The resize is Pillow's ImagingResample (bicubic, a = -0.5, horizontal pass first, uint8 intermediate, 22-bit fixed
+ *   point taps): results are bit-identical to Pillow + the PIL-backed SiglipImageProcessor.  Outputs are fp32
+ *   (out_fp32 = 1, the reference's pixel_values dtype) or bf16 (what the patch-embedding GEMM consumes).
+ *   rescale = 1/255, mean = std = {0.5, 0.5, 0.5} for SigLIP (HOST pointers).
+ *   The target resolution comes from the host planner (allocate_patches / select_best_resolution, EV :26-99). */
+size_t lp_image_frontend_workspace_bytes(int H, int W, int target_w, int target_h);
+int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h, void* out_global, void* out_tiles,
+                      int out_fp32, double rescale, const float* mean, const float* std_, void* workspace,
+                      size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Measurement hooks (used by bench.py only).
  * lp_launch_count: kernels this library has launched since load (the bench's "gpu_launches" claim).
@@ -251,7 +300,8 @@ int lp_decode_step(const lp_dec_dims* dims, const lp_dec_weights* w, const void*
  *   bracketed by a CUDA event pair on ITS stream, until `capacity` records are taken; capacity 0 disables.
  * lp_profile_read: synchronises on the recorded events, returns up to `capacity` records and disables profiling.
  *   kind: 1 gemm (a,b,c = M,N,K), 2 attention (a,b,c = B,T,heads*1000+head_dim), 3 norm (a,b = M,D), 4 rope, 5 merge,
- *   6 im2col, 7 pixel-shuffle. */
+ *   6 im2col, 7 pixel-shuffle, 8 decode attention, 10-13 decode GEMV (plain, qkv+rope, swiglu, logits),
+ *   14 image front-end (a,b,c = H, W, tiles). */
 typedef struct lp_profile_record { int kind, a, b, c; float ms; } lp_profile_record;
 long long lp_launch_count(void);
 int lp_profile_enable(int capacity);

@@ -85,6 +85,14 @@ _SIGS = {
                                 _sz, _vp]),
     "lp_decode_workspace_bytes": (_sz, [_P(DecDims)]),
     "lp_decode_step": (_i, [_P(DecDims), _P(DecWeights), _vp, _ll, _vp, _i, _vp, _ll, _vp, _vp, _sz, _vp]),
+    "lp_decode_greedy_step": (_i, [_P(DecDims), _P(DecWeights), _vp, _ll, _vp, _vp, _vp, _ll, _vp, _i, _vp, _sz, _vp]),
+    "lp_decode_graph_create": (_i, [_P(DecDims), _P(DecWeights), _vp, _ll, _vp, _vp, _vp, _ll, _vp, _i, _vp, _sz,
+                                    _P(_vp)]),
+    "lp_decode_graph_launch": (_i, [_vp, _vp]),
+    "lp_decode_graph_destroy": (None, [_vp]),
+    "lp_decode_set_mode": (_i, [_i]),
+    "lp_image_frontend_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "lp_image_frontend": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
     "lp_launch_count": (_ll, []),
     "lp_profile_enable": (_i, [_i]),
     "lp_profile_read": (_i, [_vp, _i]),

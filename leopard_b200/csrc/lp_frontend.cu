@@ -1,0 +1,323 @@
+// leopard_b200 — GPU image front-end: Pillow-exact bicubic resize + pad + 364x364 tiling + SigLIP normalisation.
+//
+// Replaces the per-crop CPU work the reference does before the model sees an image
+// (evaluations/models/llava_multiimg_siglip_anyres.py):
+//   resize_and_pad_image :102-140  aspect-preserving PIL.Image.resize (default BICUBIC) pasted centred on black
+//   divide_to_patches    :143-162  row-major 364 x 364 tiles
+//   image_processor.preprocess :403-404 (SiglipImageProcessor, slow/PIL backend of transformers <= 4.4x):
+//                                  resize to 364 x 364 (bicubic) -> x * 1/255 (float64, rounded to float32)
+//                                  -> (x - mean) / std in float32
+// (training twin: Pai-Megatron-Patch/megatron_patch/data/llava/mm_pretrain_dataset.py:141-201,264-303).
+//
+// The arithmetic is Pillow's ImagingResample (src/libImaging/Resample.c, not vendored by the reference): separable,
+// horizontal pass first, uint8 intermediate; per output sample the filter taps are computed in double precision,
+// normalised, quantised to 22 fractional bits, and each pass computes clip8((sum + 2^21) >> 22).  All of it is integer
+// / byte work bound by HBM traffic, so the kernels are about coalescing:
+//   resample_coeff_kernel   one thread per output sample builds its taps in fp64 with explicitly rounded operations
+//                           (__dmul_rn / __dadd_rn / __ddiv_rn — no FMA contraction), stored transposed [tap][sample]
+//   resample_h_kernel       one CTA per image row: the row is staged in shared memory with 16-byte loads, outputs are
+//                           staged and leave with 16-byte stores into a pitched (16 B aligned) intermediate
+//   resample_v_kernel       one thread per 4 consecutive bytes of an output row: 32-bit coalesced loads per tap, the
+//                           epilogue applies the 256-entry normalisation table and scatters into the planar
+//                           [crop, channel, 364, 364] layout (pad + tile + normalise fused into the store)
+//   pad_fill_kernel         writes the normalised black value outside the pasted rectangle
+// Results are bit-identical to Pillow + the PIL-backed SiglipImageProcessor (tests/test_gpu_frontend.py).
+#include "lp_common.cuh"
+#include "lp_host.h"
+#include "../../include/leopard_b200.h"
+
+namespace lp {
+
+constexpr int FE_PRECISION_BITS = 32 - 8 - 2;
+constexpr int FE_CROP = 364;
+constexpr int FE_MAX_KSIZE = 131;  // downscale factors up to 32x
+
+struct FeLut { float v[3][256]; };  // normalised fp32 value of every uint8 level, per channel
+
+// ---- coefficients (Pillow precompute_coeffs + normalize_coeffs_8bpc, bicubic a = -0.5, whole-image box)
+__device__ __forceinline__ double fe_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0)  // ((a + 2) x - (a + 3)) x x + 1
+    return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(a + 2.0, x), a + 3.0), x), x), 1.0);
+  if (x < 2.0)  // (((x - 5) x + 8) x - 4) a
+    return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), a);
+  return 0.0;
+}
+
+// bounds[o] = (first input sample, tap count); coeffs[t * out_size + o] = tap t of output sample o (0 beyond count).
+// identity != 0: the pass is skipped by Pillow (size unchanged) — a single unit tap reproduces the copy exactly.
+__global__ void resample_coeff_kernel(int in_size, int out_size, int ksize, int identity, int2* __restrict__ bounds,
+                                      int* __restrict__ coeffs) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out_size) return;
+  if (identity) {
+    bounds[o] = make_int2(o, 1);
+    coeffs[o] = 1 << FE_PRECISION_BITS;
+    return;
+  }
+  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = __dmul_rn(2.0, filterscale);
+  const double ss = __ddiv_rn(1.0, filterscale);
+  const double center = __dadd_rn(0.0, __dmul_rn((double)o + 0.5, scale));
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  if (xmax > ksize) xmax = ksize;  // cannot happen (ksize = 2 ceil(support) + 1); keeps stores in range regardless
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    ww = __dadd_rn(ww, fe_bicubic(arg));
+  }
+  for (int x = 0; x < ksize; ++x) {
+    int q = 0;
+    if (x < xmax) {
+      const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+      double k = fe_bicubic(arg);
+      if (ww != 0.0) k = __ddiv_rn(k, ww);
+      const double v = __dmul_rn(k, (double)(1 << FE_PRECISION_BITS));
+      q = k < 0.0 ? (int)__dadd_rn(-0.5, v) : (int)__dadd_rn(0.5, v);
+    }
+    coeffs[(long long)x * out_size + o] = q;
+  }
+  bounds[o] = make_int2(xmin, xmax);
+}
+
+__device__ __forceinline__ int fe_clip8(int acc) {
+  const int v = acc >> FE_PRECISION_BITS;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// ---- horizontal pass: in [rows, w_in, 3] u8 (row pitch in_pitch bytes, any alignment) -> out [rows, w_out, 3] u8 with
+// a 16-byte aligned pitch.  One CTA per row.
+__global__ void __launch_bounds__(256)
+resample_h_kernel(const uint8_t* __restrict__ in, long long in_pitch, long long in_bytes, int w_in,
+                  uint8_t* __restrict__ out, long long out_pitch, int w_out, const int2* __restrict__ bounds,
+                  const int* __restrict__ coeffs) {
+  extern __shared__ uint4 fe_smem[];
+  const int row = blockIdx.x;
+  const int row_bytes = w_in * 3;
+  const uint8_t* src = in + (long long)row * in_pitch;
+  const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);  // stage from the enclosing 16-byte window
+  const uint8_t* win = src - head;
+  const int nvec = (head + row_bytes + 15) >> 4;
+  uint8_t* s_in = reinterpret_cast<uint8_t*>(fe_smem);
+  uint8_t* s_out = s_in + (((size_t)nvec * 16 + 15) & ~size_t(15));
+  const uint8_t* buf_end = in + in_bytes;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint8_t* p = win + (long long)v * 16;
+    if (p + 16 <= buf_end) {
+      fe_smem[v] = *reinterpret_cast<const uint4*>(p);
+    } else {  // last vector of the image: never read past the caller's buffer
+      for (int b = 0; b < 16; ++b) s_in[v * 16 + b] = (p + b < buf_end) ? p[b] : (uint8_t)0;
+    }
+  }
+  __syncthreads();
+  const uint8_t* px = s_in + head;
+  for (int o = threadIdx.x; o < w_out; o += blockDim.x) {
+    const int2 b = bounds[o];
+    int a0 = 1 << (FE_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+    const uint8_t* p = px + b.x * 3;
+    for (int t = 0; t < b.y; ++t) {
+      const int k = coeffs[(long long)t * w_out + o];
+      a0 += (int)p[0] * k; a1 += (int)p[1] * k; a2 += (int)p[2] * k;
+      p += 3;
+    }
+    s_out[o * 3 + 0] = (uint8_t)fe_clip8(a0);
+    s_out[o * 3 + 1] = (uint8_t)fe_clip8(a1);
+    s_out[o * 3 + 2] = (uint8_t)fe_clip8(a2);
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * out_pitch);
+  const uint4* s_out4 = reinterpret_cast<const uint4*>(s_out);
+  const int ovec = (w_out * 3 + 15) >> 4;  // the pitch is a multiple of 16: whole vectors may be written
+  for (int v = threadIdx.x; v < ovec; v += blockDim.x) dst[v] = s_out4[v];
+}
+
+// ---- vertical pass + pad / tile / normalise store.
+// tmp [h_in, w*3 bytes] (pitch multiple of 16) -> resized rows oy in [0, h_out); pixel (oy, x) lands at canvas position
+// (paste_y + oy, paste_x + x) of a canvas that is cut into 364 x 364 tiles, tiles_x per canvas row; tile t is written
+// at out + t * tile_stride elements, planar [3][364][364].
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+resample_v_kernel(const uint8_t* __restrict__ tmp, long long pitch, int w, int h_out, const int2* __restrict__ bounds,
+                  const int* __restrict__ coeffs, int paste_x, int paste_y, int tiles_x, OutT* __restrict__ out,
+                  long long tile_stride, const FeLut lut) {
+  __shared__ float s_lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = lut.v[i >> 8][i & 255];
+  __syncthreads();
+  const int oy = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;  // 4-byte group within the row
+  const int row_bytes = w * 3;
+  if (g * 4 >= row_bytes) return;
+  const int2 b = bounds[oy];
+  int acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = 1 << (FE_PRECISION_BITS - 1);
+  const uint8_t* p = tmp + (long long)b.x * pitch + (long long)g * 4;
+  for (int t = 0; t < b.y; ++t) {
+    const int k = coeffs[(long long)t * h_out + oy];
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    acc[0] += (int)(v & 255u) * k;
+    acc[1] += (int)((v >> 8) & 255u) * k;
+    acc[2] += (int)((v >> 16) & 255u) * k;
+    acc[3] += (int)(v >> 24) * k;
+    p += pitch;
+  }
+  const int cy = paste_y + oy;
+  const int ty = cy / FE_CROP, iy = cy - ty * FE_CROP;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int byte = g * 4 + q;
+    if (byte >= row_bytes) break;
+    const int x = byte / 3, c = byte - x * 3;
+    const int cx = paste_x + x;
+    const int tx = cx / FE_CROP, ix = cx - tx * FE_CROP;
+    OutT* o = out + (long long)(ty * tiles_x + tx) * tile_stride + ((long long)c * FE_CROP + iy) * FE_CROP + ix;
+    *o = (OutT)s_lut[c][fe_clip8(acc[q])];
+  }
+}
+
+// canvas pixels outside the pasted rectangle get the normalised value of black
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+pad_fill_kernel(int canvas_w, int canvas_h, int paste_x, int paste_y, int w, int h, int tiles_x, OutT* __restrict__ out,
+                long long tile_stride, float pad0, float pad1, float pad2) {
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
+  if (cx >= canvas_w || cy >= canvas_h) return;
+  if (cy >= paste_y && cy < paste_y + h && cx >= paste_x && cx < paste_x + w) return;
+  const int ty = cy / FE_CROP, iy = cy - ty * FE_CROP, tx = cx / FE_CROP, ix = cx - tx * FE_CROP;
+  OutT* o = out + (long long)(ty * tiles_x + tx) * tile_stride + (long long)iy * FE_CROP + ix;
+  o[0] = (OutT)pad0;
+  o[(long long)FE_CROP * FE_CROP] = (OutT)pad1;
+  o[2LL * FE_CROP * FE_CROP] = (OutT)pad2;
+}
+
+static int fe_ksize(int in_size, int out_size) {
+  if (in_size == out_size) return 1;
+  double fs = (double)in_size / out_size;
+  if (fs < 1.0) fs = 1.0;
+  return (int)ceil(2.0 * fs) * 2 + 1;
+}
+
+static size_t fe_align(size_t n) { return (n + 255) & ~size_t(255); }
+
+// workspace for one resize (w_in, h_in) -> (w_out, h_out): intermediate + two coefficient tables
+static size_t fe_resize_ws(int w_in, int h_in, int w_out, int h_out) {
+  const size_t pitch = ((size_t)w_out * 3 + 15) & ~size_t(15);
+  return fe_align(pitch * h_in) + fe_align((size_t)w_out * 8) + fe_align((size_t)w_out * fe_ksize(w_in, w_out) * 4) +
+         fe_align((size_t)h_out * 8) + fe_align((size_t)h_out * fe_ksize(h_in, h_out) * 4);
+}
+
+template <typename OutT>
+static int fe_resize_into(const uint8_t* rgb, int H, int W, int w_out, int h_out, int canvas_w, int canvas_h,
+                          int paste_x, int paste_y, OutT* out, const FeLut& lut, uint8_t* ws, cudaStream_t stream) {
+  const int kx = fe_ksize(W, w_out), ky = fe_ksize(H, h_out);
+  LP_REQUIRE(kx <= FE_MAX_KSIZE && ky <= FE_MAX_KSIZE, "lp_image_frontend: downscale factor above 32 (%dx%d -> %dx%d)",
+             W, H, w_out, h_out);
+  const size_t pitch = ((size_t)w_out * 3 + 15) & ~size_t(15);
+  uint8_t* tmp = ws; ws += fe_align(pitch * H);
+  int2* bx = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)w_out * 8);
+  int* cxs = reinterpret_cast<int*>(ws); ws += fe_align((size_t)w_out * kx * 4);
+  int2* by = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)h_out * 8);
+  int* cys = reinterpret_cast<int*>(ws);
+  resample_coeff_kernel<<<(w_out + 127) / 128, 128, 0, stream>>>(W, w_out, kx, W == w_out, bx, cxs);
+  resample_coeff_kernel<<<(h_out + 127) / 128, 128, 0, stream>>>(H, h_out, ky, H == h_out, by, cys);
+  const size_t smem = (((size_t)W * 3 + 15 + 15) / 16 * 16 + 15) / 16 * 16 + pitch + 32;
+  LP_REQUIRE(smem <= 200 * 1024, "lp_image_frontend: image row too wide for the staging buffer (W=%d)", W);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  resample_h_kernel<<<H, 256, smem, stream>>>(rgb, (long long)W * 3, (long long)H * W * 3, W, tmp, (long long)pitch,
+                                              w_out, bx, cxs);
+  const int tiles_x = canvas_w / FE_CROP;
+  const long long tile_stride = 3LL * FE_CROP * FE_CROP;
+  if (w_out != canvas_w || h_out != canvas_h) {
+    pad_fill_kernel<OutT><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
+        canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x, out, tile_stride, lut.v[0][0], lut.v[1][0],
+        lut.v[2][0]);
+    note_launch();
+  }
+  const int groups = (w_out * 3 + 3) / 4;
+  resample_v_kernel<OutT><<<dim3((groups + 255) / 256, h_out), 256, 0, stream>>>(
+      tmp, (long long)pitch, w_out, h_out, by, cys, paste_x, paste_y, tiles_x, out, tile_stride, lut);
+  note_launch(4);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// resize_and_pad_image's geometry (EV/...anyres.py:116-136), same double arithmetic as the Python original
+static void fe_pad_geometry(int w, int h, int tw, int th, int* nw, int* nh, int* px, int* py) {
+  const double scale_w = (double)tw / (double)w, scale_h = (double)th / (double)h;
+  if (scale_w < scale_h) {
+    *nw = tw;
+    const int c = (int)ceil((double)h * scale_w);
+    *nh = c < th ? c : th;
+  } else {
+    *nh = th;
+    const int c = (int)ceil((double)w * scale_h);
+    *nw = c < tw ? c : tw;
+  }
+  *px = (tw - *nw) / 2;
+  *py = (th - *nh) / 2;
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+extern "C" size_t lp_image_frontend_workspace_bytes(int H, int W, int target_w, int target_h) {
+  size_t n = fe_resize_ws(W, H, FE_CROP, FE_CROP);
+  if (target_w > 0 && target_h > 0) {
+    int nw, nh, px, py;
+    fe_pad_geometry(W, H, target_w, target_h, &nw, &nh, &px, &py);
+    n += fe_resize_ws(W, H, nw, nh);
+  }
+  return n + 256;
+}
+
+extern "C" int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h, void* out_global,
+                                 void* out_tiles, int out_fp32, double rescale, const float* mean, const float* std_,
+                                 void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(rgb && out_global && workspace && mean && std_, "lp_image_frontend: null argument");
+  LP_REQUIRE(H > 0 && W > 0 && W <= 16384 && H <= 16384, "lp_image_frontend: bad image size %dx%d", W, H);
+  LP_REQUIRE((reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "lp_image_frontend: image must be 16-byte aligned");
+  const bool tiles = target_w > 0 && target_h > 0;
+  LP_REQUIRE(!tiles || (out_tiles && target_w % FE_CROP == 0 && target_h % FE_CROP == 0),
+             "lp_image_frontend: target resolution %dx%d is not a grid of 364-pixel tiles (or out_tiles is null)",
+             target_w, target_h);
+  LP_REQUIRE(ws_bytes >= lp_image_frontend_workspace_bytes(H, W, target_w, target_h),
+             "lp_image_frontend: workspace too small");
+  FeLut lut;  // SiglipImageProcessor: rescale in float64 rounded to float32, then (x - mean) / std in float32
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < 256; ++i) {
+      const float x = (float)((double)i * rescale);
+      lut.v[c][i] = (x - mean[c]) / std_[c];
+    }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(rgb);
+  ProfScope prof(14, H, W, tiles ? (target_w / FE_CROP) * (target_h / FE_CROP) : 0, stream);
+  int rc;
+  // the original image -> one 364 x 364 crop (aspect ratio not preserved, like the processor's resize)
+  if (out_fp32)
+    rc = fe_resize_into<float>(img, H, W, FE_CROP, FE_CROP, FE_CROP, FE_CROP, 0, 0, reinterpret_cast<float*>(out_global),
+                               lut, ws, stream);
+  else
+    rc = fe_resize_into<bf16>(img, H, W, FE_CROP, FE_CROP, FE_CROP, FE_CROP, 0, 0, reinterpret_cast<bf16*>(out_global),
+                              lut, ws, stream);
+  if (rc || !tiles) return rc;
+  ws += fe_resize_ws(W, H, FE_CROP, FE_CROP);
+  int nw, nh, px, py;
+  fe_pad_geometry(W, H, target_w, target_h, &nw, &nh, &px, &py);
+  if (out_fp32)
+    return fe_resize_into<float>(img, H, W, nw, nh, target_w, target_h, px, py, reinterpret_cast<float*>(out_tiles), lut,
+                                 ws, stream);
+  return fe_resize_into<bf16>(img, H, W, nw, nh, target_w, target_h, px, py, reinterpret_cast<bf16*>(out_tiles), lut, ws,
+                              stream);
+}

@@ -1,47 +1,108 @@
-"""Greedy generation on top of the native prefill: prefill (last-row logits + KV cache) then lp_decode_step per token.
+"""Greedy generation on top of the native prefill: prefill (last-row logits + KV cache), then one native step per token.
 
 Mirrors what `llava.generate(..., max_new_tokens=128, use_cache=True)` does through transformers' GenerationMixin in the
 reference (evaluations/models/llava_multiimg_siglip_anyres.py:448-452): greedy arg-max, stop on any eos id.
-Sampling/stopping is host logic; every tensor op on the path is a C-ABI call.
+
+The loop state (last token, position) lives on the device: `lp_decode_greedy_step` embeds the token, runs the 32 layers
+as HBM-streaming GEMV kernels over the KV cache, picks the arg-max and advances the position.  By default the step is
+captured once into a CUDA graph (`lp_decode_graph_create`) and replayed per token; the only host work per token is
+reading the 8-byte token back for the stopping criterion, like GenerationMixin does.
+  LEOPARD_DECODE_GRAPH=0   launch the step's kernels one by one instead of replaying the graph
+  LEOPARD_DECODE_MODE=n    lp_decode_set_mode(n): bit 0 GEMV kernels (default 1), bit 1 programmatic dependent launch
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Set
 
 import torch
 
 from . import _lib
 
+KV_GRANULE = 2048  # cache capacities are rounded up to this many rows so that one captured graph serves many requests
+
+
+class _DecodeState:
+    """Per-engine device buffers the captured graph points at (stable addresses across generate() calls)."""
+
+    def __init__(self, eng):
+        dev = eng.device
+        self.tok = torch.zeros(1, dtype=torch.long, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.logits = torch.empty((eng.w.vocab_padded,), dtype=torch.float32, device=dev)
+        self.graph = None      # lp_decode_graph*
+        self.graph_key = None
+
+    def drop_graph(self):
+        if self.graph is not None:
+            _lib.lib().lp_decode_graph_destroy(self.graph)
+            self.graph, self.graph_key = None, None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.drop_graph()
+        except Exception:
+            pass
+
 
 class GreedyDecoder:
     def __init__(self, engine):
         self.eng = engine
+        if getattr(engine, "_decode_state", None) is None:
+            engine._decode_state = _DecodeState(engine)
+        self.st = engine._decode_state
+
+    def _kv_buffer(self, rows_needed: int):
+        """A persistent cache buffer [layers, 2, capacity, kv_w] whose capacity only grows (in KV_GRANULE steps)."""
+        d = self.eng.cfg.dec
+        cap = -(-rows_needed // KV_GRANULE) * KV_GRANULE
+        kv = getattr(self.eng, "_decode_kv", None)
+        if kv is None or kv.shape[2] < cap:
+            self.st.drop_graph()
+            self.eng._decode_kv = None
+            kv = torch.empty((d.layers, 2, cap, d.kv_heads * d.head_dim), dtype=torch.bfloat16, device=self.eng.device)
+            self.eng._decode_kv = kv
+        return kv
 
     @torch.no_grad()
     def run(self, ids: torch.Tensor, pixel_values: Optional[torch.Tensor], max_new_tokens: int, eos: Set[int]):
-        eng = self.eng
+        eng, st = self.eng, self.st
         cfg = eng.cfg
         L = _lib.lib()
-        want_cache = max_new_tokens > 1
-        if not want_cache:
+        if max_new_tokens <= 1:
             logits, _, _ = eng.prefill([(ids, pixel_values)], "last")
             return logits.argmax(-1).to(torch.long)
-        logits, kv, cu = eng.prefill([(ids, pixel_values)], "last", want_kv=True, kv_capacity=max_new_tokens)
+        mode = os.environ.get("LEOPARD_DECODE_MODE")
+        if mode is not None:
+            L.lp_decode_set_mode(int(mode))
+        n_rows = eng.merged_length(ids, pixel_values)
+        kv = self._kv_buffer(n_rows + max_new_tokens)
+        logits, kv, cu = eng.prefill([(ids, pixel_values)], "last", want_kv=True, kv_buffer=kv)
         S = cu[-1]
         cap = kv.shape[2]
         ws = eng._workspace("decode", L.lp_decode_workspace_bytes(C.byref(eng.w.dec_dims)))
-        step_logits = torch.empty((eng.w.vocab_padded,), dtype=torch.float32, device=eng.device)
+        st.tok.copy_(logits.argmax(-1).to(torch.long))
+        st.pos.fill_(S)
+        args = (C.byref(eng.w.dec_dims), C.byref(eng.w.dec), _lib.ptr(eng.w.embed), eng.w.embed.stride(0),
+                _lib.ptr(st.tok), _lib.ptr(st.pos), _lib.ptr(kv), cap, _lib.ptr(st.logits), cfg.dec.vocab,
+                _lib.ptr(ws), ws.numel())
+        use_graph = os.environ.get("LEOPARD_DECODE_GRAPH", "1") != "0"
+        if use_graph:
+            key = (kv.data_ptr(), cap, ws.data_ptr(), st.logits.data_ptr(), mode)
+            if st.graph_key != key:
+                st.drop_graph()
+                h = C.c_void_p()
+                _lib.check(L.lp_decode_graph_create(*args, C.byref(h)), "lp_decode_graph_create")
+                st.graph, st.graph_key = h, key
         out = []
-        tok = logits.argmax(-1).to(torch.long)  # [1] on the device
         for i in range(max_new_tokens):
-            t = int(tok.item())                 # host read: stopping criterion, like GenerationMixin
+            t = int(st.tok.item())                 # host read: stopping criterion, like GenerationMixin
             out.append(t)
             if t in eos or i == max_new_tokens - 1:
                 break
-            rc = L.lp_decode_step(C.byref(eng.w.dec_dims), C.byref(eng.w.dec), _lib.ptr(eng.w.embed),
-                                  eng.w.embed.stride(0), _lib.ptr(tok), S + i, _lib.ptr(kv), cap,
-                                  _lib.ptr(step_logits), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
-            _lib.check(rc, "lp_decode_step")
-            tok = step_logits[: cfg.dec.vocab].argmax(-1, keepdim=True).to(torch.long)
+            if use_graph:
+                _lib.check(L.lp_decode_graph_launch(st.graph, _lib.stream_ptr()), "lp_decode_graph_launch")
+            else:
+                _lib.check(L.lp_decode_greedy_step(*args, _lib.stream_ptr()), "lp_decode_greedy_step")
         return torch.tensor(out, dtype=torch.long, device=eng.device)

@@ -95,9 +95,11 @@ class PrefillEngine:
         return out[:S], n_slots
 
     def decoder(self, x: torch.Tensor, pos_ids: torch.Tensor, cu_seqlens: Sequence[int], logits_mode: str = "last",
-                logits_dtype=torch.float32, want_kv: bool = False, kv_capacity: int = 0):
+                logits_dtype=torch.float32, want_kv: bool = False, kv_capacity: int = 0,
+                kv_buffer: Optional[torch.Tensor] = None):
         """x [R, D] packed merged embeddings (overwritten) -> (logits, kv_cache or None).
-        logits: 'last' -> [n_seqs, V]; 'all' -> [R, V]; 'none' -> None."""
+        logits: 'last' -> [n_seqs, V]; 'all' -> [R, V]; 'none' -> None.
+        kv_buffer: caller-owned cache [layers, 2, capacity >= R, kv_w] to fill instead of allocating one."""
         d = self.cfg.dec
         R = x.shape[0]
         n = len(cu_seqlens) - 1
@@ -110,7 +112,12 @@ class PrefillEngine:
         elif mode == _lib.LOGITS_ALL:
             logits = torch.empty((R, vp), dtype=logits_dtype, device=self.device)
         kv = None
-        if want_kv:
+        if want_kv and kv_buffer is not None:
+            if (kv_buffer.dim() != 4 or kv_buffer.shape[0] != d.layers or kv_buffer.shape[2] < R
+                    or kv_buffer.shape[3] != d.kv_heads * d.head_dim or not kv_buffer.is_contiguous()):
+                raise ValueError(f"kv_buffer {tuple(kv_buffer.shape)} cannot hold {R} rows of this decoder")
+            kv = kv_buffer
+        elif want_kv:
             kv = torch.empty((d.layers, 2, max(R, kv_capacity), d.kv_heads * d.head_dim), dtype=torch.bfloat16,
                              device=self.device)
         cu = (C.c_int * (n + 1))(*[int(c) for c in cu_seqlens])
@@ -128,7 +135,8 @@ class PrefillEngine:
     # ------------------------------------------------------------------ whole path
     @torch.no_grad()
     def prefill(self, samples: List[Tuple[torch.Tensor, Optional[torch.Tensor]]], logits_mode: str = "last",
-                logits_dtype=torch.float32, want_kv: bool = False, convention: str = "hf", kv_capacity: int = 0):
+                logits_dtype=torch.float32, want_kv: bool = False, convention: str = "hf", kv_capacity: int = 0,
+                kv_buffer: Optional[torch.Tensor] = None):
         """samples: [(input_ids [L] or [1,L], pixel_values [N_i,3,364,364] or None), ...] — independent requests.
         All crops go through the tower as one batch, every request becomes one packed decoder sequence.
         convention 'hf': one placeholder id per crop, expanded to 169 rows; 'megatron': one -200 per feature row.
@@ -164,5 +172,13 @@ class PrefillEngine:
             self.merge(ids, f, image_id, per_slot, out=x[cu[k]:cu[k + 1]])
             f0 += n_rows
         pos = torch.cat([torch.arange(ln, dtype=torch.int32, device=self.device) for ln in lens])
-        logits, kv = self.decoder(x, pos, cu, logits_mode, logits_dtype, want_kv, cu[-1] + kv_capacity)
+        logits, kv = self.decoder(x, pos, cu, logits_mode, logits_dtype, want_kv, cu[-1] + kv_capacity, kv_buffer)
         return logits, kv, cu
+
+    def merged_length(self, ids: torch.Tensor, pixel_values: Optional[torch.Tensor], convention: str = "hf") -> int:
+        """Decoder rows one request occupies after the merge (L + 168 per image placeholder in the HF convention)."""
+        cfg = self.cfg
+        image_id, per_slot = (cfg.image_token_index, cfg.tokens_per_crop) if convention == "hf" else (
+            cfg.megatron_image_index, 1)
+        flat = ids.reshape(-1)
+        return int(flat.numel() + int((flat == image_id).sum()) * (per_slot - 1))

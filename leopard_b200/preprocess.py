@@ -121,14 +121,17 @@ def preprocess_images(images, image_processor=None):
 
 
 def to_pixel_values(crops, size: int = PATCH):
-    """Restatement of SiglipImageProcessor defaults used by the reference (resize to 364 bicubic, rescale 1/255,
-    normalise mean=std=0.5).  The reference's preprocessor_config.json is not in its tree ("parity unpinned")."""
+    """Host restatement of SiglipImageProcessor (PIL backend) with SigLIP's defaults as the reference uses it
+    (EV/...anyres.py:403-404): bicubic resize to 364, x * (1/255) in float64 rounded to float32, (x - 0.5) / 0.5 in
+    float32.  The reference's preprocessor_config.json is not in its tree ("parity unpinned" for the settings; the
+    arithmetic is pinned by tests/golden/ref_frontend.json).  The GPU path is leopard_b200.frontend.ImageFrontend."""
     import numpy as np
     import torch
     from PIL import Image
+    lut = (np.arange(256).astype(np.float64) * (1 / 255)).astype(np.float32)
+    lut = (lut - np.float32(0.5)) / np.float32(0.5)
     arrs = []
     for c in crops:
         c = c.convert("RGB").resize((size, size), resample=Image.BICUBIC)
-        a = np.asarray(c, dtype=np.float32) / 255.0
-        arrs.append(((a - 0.5) / 0.5).transpose(2, 0, 1))
-    return torch.from_numpy(np.stack(arrs, 0))
+        arrs.append(lut[np.asarray(c)].transpose(2, 0, 1))
+    return torch.from_numpy(np.ascontiguousarray(np.stack(arrs, 0)))
