@@ -67,11 +67,28 @@ int lp_gemm_set_pair_mode(int enable);
  * out: bf16 [B*T, ldo], head h at cols h*head_dim.  scale = head_dim^-0.5 in the reference.
  * variant bit 0: keep P in TMEM (tcgen05.mma A-from-TMEM) instead of shared memory (one-tile kernel);
  * variant bit 1: two 128-row query tiles per CTA ping-ponged on the tensor pipe (P always in TMEM);
- * variant bits 2-3 (with bit 1): 0/1/2 of every 4 softmax exponentials evaluated on the FMA pipe (polynomial 2^x,
- *   rel. error 1.1e-4) instead of MUFU.EX2. */
+ * variant bits 2-3 (with bit 1 or 6): 0/1/2 of every 4 softmax exponentials evaluated on the FMA pipe (polynomial
+ *   2^x, rel. error 1.1e-4) instead of MUFU.EX2;
+ * variant bit 6 (64): v3 kernel (lp_attn3.cu) — two query tiles, S in 64-key halves, one MMA issuer per tile; the
+ *   softmax row sum is taken in fp32 before P is rounded to bf16 (as flash-attention does);
+ * variant bits 4 / 5 (16 / 32): force the softmax turn protocol on / off (see lp_attention_set_pingpong). */
 int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, int n_kv_heads, int head_dim,
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);
+
+/* Softmax turn protocol of the two-tile kernel (variant bit 1): the two softmax warpgroups of a CTA alternate strictly
+ * (named barriers), so one tile's exponentials overlap the other tile's MMAs instead of both tiles sharing the MUFU
+ * unit and then both waiting for the tensor pipe.  Same arithmetic: results are bit-identical with it on or off.
+ * lp_attention_set_pingpong sets the default (returns the previous one); variant bit 4 (16) forces it on and bit 5 (32)
+ * forces it off for one call. */
+int lp_attention_set_pingpong(int enable);
+
+/* Attention kernel the model-level entry points (lp_vit_forward, lp_vit_layers, lp_decoder_prefill) pass to
+ * lp_attention_fwd as `variant`; returns the previous value.  Default 80 = variant bit 6 (64): the v3 kernel — two
+ * query tiles per CTA, S delivered in 64-key halves with their own TMEM columns so QK^T of the next half never waits
+ * for the softmax of the current one, one MMA-issuing thread per query tile — plus bit 4 (16): the turn protocol on
+ * its exp sections.  2 selects the v2 two-tile kernel. */
+int lp_model_set_attention_variant(int variant);
 
 /* Cross-attention with separate query and key/value buffers, non-causal (Idefics2 perceiver resampler: 64 latent
  * queries attend to concat(context, latents); MP/model/idefics2/perceiver_transformer.py:582-706, flash-varlen call

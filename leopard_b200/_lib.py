@@ -65,6 +65,8 @@ _SIGS = {
     "lp_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "lp_gemm_set_pair_mode": (_i, [_i]),
     "lp_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _i, _vp]),
+    "lp_attention_set_pingpong": (_i, [_i]),
+    "lp_model_set_attention_variant": (_i, [_i]),
     "lp_attention_cross": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
     "lp_layernorm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
     "lp_rmsnorm": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _vp]),

@@ -347,6 +347,14 @@ static int launch_attn(const CUtensorMap& tmq, const CUtensorMap& tm, const Attn
 
 using namespace lp;
 
+static int g_attn_pingpong = 0;  // default of the softmax turn protocol when the variant bits 4/5 do not force it
+
+extern "C" int lp_attention_set_pingpong(int enable) {
+  const int old = g_attn_pingpong;
+  g_attn_pingpong = enable ? 1 : 0;
+  return old;
+}
+
 extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, int n_kv_heads, int head_dim,
                                 int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                                 long long ldo, int variant, void* stream_) {
@@ -367,10 +375,16 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
   a.O = reinterpret_cast<bf16*>(out);
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.pingpong = (variant & 16) ? 1 : ((variant & 32) ? 0 : g_attn_pingpong);
   CUtensorMap tm;
   int rc = make_tmap_bf16_3d(&tm, qkv, (uint64_t)ld, (uint64_t)T, (uint64_t)B, (uint64_t)ld, (uint64_t)T * ld, 64,
                              128, 1);
   if (rc) return rc;
+  if (variant & 64) {  // two query tiles, S in 64-key halves, one issuer per tile (lp_attn3.cu)
+    ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
+    note_launch();
+    return launch_attn3(tm, a, head_dim, causal, (variant >> 2) & 3, stream);
+  }
   if (variant & 2) {  // two query tiles per CTA (lp_attn2.cu)
     ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
     note_launch();
@@ -409,6 +423,7 @@ extern "C" int lp_attention_cross(const void* q, long long ldq, const void* kv, 
   a.O = reinterpret_cast<bf16*>(out);
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.pingpong = 0;
   CUtensorMap tq, tkv;
   int rc = make_tmap_bf16_3d(&tq, q, (uint64_t)ldq, (uint64_t)Tq, (uint64_t)B, (uint64_t)ldq, (uint64_t)Tq * ldq, 64, 128, 1);
   if (rc) return rc;

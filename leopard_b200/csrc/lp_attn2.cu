@@ -62,6 +62,10 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// named barriers for the softmax turn protocol (ids 2 and 3; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 #define LP_TMEM_ST_16(regs, taddr)                                                                                  \
   asm volatile(                                                                                                     \
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
@@ -232,7 +236,15 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
     // ------------------------------------------------------------------ softmax warpgroups
     const int q = (warp - 2) >> 2;
     const int n_q = q ? nB : nA;
-    if (n_q > 0) {
+    // Turn protocol (args.pingpong): the two softmax warpgroups alternate strictly — A(j), B(j), A(j+1), ... — so that
+    // one tile's exponentials (MUFU-bound, ~1000 cycles per 128 x 128 tile) run while the tensor pipe works on the
+    // OTHER tile's P·V and next QK^T.  Without it both warpgroups start in phase, share the MUFU unit, finish together
+    // and then both wait for their MMAs: softmax and MMA time add up instead of overlapping (ncu: tensor pipe 47 %).
+    // Barrier 3 = "B's turn" (A arrives, B syncs), barrier 2 = "A's turn" (B arrives, A syncs from its second step);
+    // both warpgroups run n_kv = nB >= nA turns, a finished tile just passes the turn on.
+    const bool turns = args.pingpong != 0 && actB;
+    const int n_turn = turns ? n_kv : n_q;
+    if (n_turn > 0) {
       const int lg = warp & 3;
       const int r = lg * 32 + lane;
       const int q0 = q ? q0B : q0A;
@@ -242,7 +254,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       const uint32_t s_addr = lane_addr + TM_S + (uint32_t)q * 128;
       const uint32_t o_addr = lane_addr + TM_O + (uint32_t)q * 128;
       float m_used = -INFINITY, l_sum = 0.f;
-      for (int j = 0; j < n_q; ++j) {
+      for (int j = 0; j < n_turn; ++j) {
+        if (turns) {
+          if (q == 0) { if (j > 0) named_bar_sync(2, 256); }
+          else named_bar_sync(3, 256);
+        }
+        if (j < n_q) {
         const int kv0 = j * 128;
         mbar_wait(&s_full[q], j & 1);
         tc_fence_after();
@@ -260,9 +277,18 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           for (int i = 0; i < 128; ++i)
             if (i >= lim) v[i] = 0xff800000u;  // -inf
         }
-        float mx = -INFINITY;
+        float mx;
+        {  // four independent max chains (a single chain is 64 dependent FMNMX3)
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 128; i += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
         const float m_new = fmaxf(m_used, mx * args.scale_log2);
         const bool grow = (m_new - m_used) > 8.0f;
         if (j == 0) {
@@ -315,6 +341,11 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           float a0, a1;
           upk2(acc2, a0, a1);
           l_sum += a0 + a1;
+        }
+        }  // j < n_q
+        if (turns) {
+          if (q == 0) named_bar_arrive(3, 256);
+          else if (j + 1 < n_turn) named_bar_arrive(2, 256);
         }
       }
       // ---- epilogue

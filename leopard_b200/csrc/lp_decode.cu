@@ -29,7 +29,7 @@ namespace lp {
 
 int rope_table_base(int pos_base, const float* inv_freq, float* cs, float* sn, int S, int half, cudaStream_t stream);
 
-static int g_decode_mode = 1;  // bit 0: GEMV kernels, bit 1: programmatic dependent launch
+static int g_decode_mode = 5;  // bit 0: GEMV kernels, bit 1: programmatic dependent launch, bit 2: block-cooperative GEMV, bit 3: half-SM footprints
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -223,26 +223,39 @@ gemv_kernel(const GemvArgs a) {
 
 // ---------------------------------------------------------------------------------------------------- attention
 constexpr int DEC_WARPS = 8;
-constexpr int DEC_SPLITS = 16;  // key ranges per head -> heads * DEC_SPLITS CTAs (>= 1 wave on 148 SMs)
+constexpr int DEC_SPLITS = 48;   // key ranges per kv head -> kv_heads * DEC_SPLITS CTAs, all resident in one wave
+constexpr int DEC_GROUP = 4;     // q heads per kv head handled by one CTA (Llama-3.1-8B / Mistral-7B: 32 / 8)
+constexpr int DEC_STREAMS = DEC_WARPS / DEC_GROUP;  // warps per q head, interleaved over the CTA's key range
 
-// Split-K decode attention, pass 1: CTA (head h, split s) scans keys [s*chunk, (s+1)*chunk) of kv head h/group.
-// A warp handles FOUR keys per step (8 lanes x 16 dims each, two 16-byte loads per lane, 3-step shuffle reduce) so that
-// four independent load->dot->exp chains are in flight; partial (m, l, acc[128]) go to `part` for the combine pass.
-// Attends to rows 0 .. position (the row at `position` was appended by this step's QKV kernel).
-__global__ void __launch_bounds__(DEC_WARPS * 32)
-decode_attn_partial_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
-                           const int* __restrict__ pos_dev, int pos_host, int max_ctx, int kv_w, int group,
-                           float scale_log2, float* __restrict__ part) {
+// Split-K GQA decode attention: CTA (kv head g, split s) scans keys [s*chunk, (s+1)*chunk) for the FOUR q heads that
+// share kv head g.  Warp w serves q head 4g + (w & 3) on key stream (w >> 2); the four head-warps of a stream walk the
+// same K/V rows in lock-step, so the rows come from HBM/L2 once per CTA and the other three reads hit L1 (the
+// per-q-head version re-read every row four times from L2 and was L2-bandwidth bound: 16 us for 20 MB).
+// A warp handles FOUR keys per step (8 lanes x 16 dims each, two 16-byte loads per lane, 3-step shuffle reduce) and
+// requests the next step's rows before consuming the current ones.  Per-(head, split) partials (m, l, acc[128]) go to
+// `part`; the LAST CTA of a kv head to finish (atomic ticket) merges its heads' partials and writes the bf16 output
+// rows, so there is no separate combine launch.  `tickets` [kv_heads] must be zero on entry (decode_embed_kernel clears
+// it every step) and is left zero.  Attends to rows 0 .. position (the row at `position` was appended by this step's
+// QKV kernel).
+__global__ void __launch_bounds__(DEC_WARPS * 32, 3)
+decode_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+                   const int* __restrict__ pos_dev, int pos_host, int max_ctx, int kv_w, float scale_log2,
+                   float* __restrict__ part, unsigned* __restrict__ tickets, bf16* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   const int n_ctx = min(decode_position(pos_dev, pos_host) + 1, max_ctx);  // never read past the cache
-  const int h = blockIdx.x, split = blockIdx.y, g = h / group;
+  const int g = blockIdx.x, split = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hh = warp & (DEC_GROUP - 1), stream = warp / DEC_GROUP;
+  const int h = g * DEC_GROUP + hh;
   const int sub = lane >> 3, l8 = lane & 7;  // key slot within the warp step, 16-dim slice of the head
   const unsigned gmask = 0xFFu << (sub * 8);
   const int chunk = (n_ctx + DEC_SPLITS - 1) / DEC_SPLITS;
   const int t_begin = split * chunk, t_end = min(n_ctx, t_begin + chunk);
-  __shared__ float s_m[DEC_WARPS * 4], s_l[DEC_WARPS * 4], s_acc[DEC_WARPS * 4][128];
+  constexpr int SLOTS = DEC_STREAMS * 4;  // partial states per q head inside the CTA
+  __shared__ float s_m[DEC_GROUP][SLOTS], s_l[DEC_GROUP][SLOTS], s_acc[DEC_GROUP][SLOTS][128];
+  __shared__ float s_w[DEC_GROUP][DEC_SPLITS], s_inv[DEC_GROUP];
+  __shared__ unsigned s_ticket;
   float qv[16];
   {
     const uint4 u0 = *reinterpret_cast<const uint4*>(q + h * 128 + l8 * 16);
@@ -258,11 +271,25 @@ decode_attn_partial_kernel(const bf16* __restrict__ q, const bf16* __restrict__ 
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int t = t_begin + warp * 4 + sub; t < t_end; t += DEC_WARPS * 4) {
-    const bf16* kp = kc + (long long)t * kv_w + g * 128 + l8 * 16;
-    const bf16* vp = vc + (long long)t * kv_w + g * 128 + l8 * 16;
-    const uint4 k0 = *reinterpret_cast<const uint4*>(kp), k1 = *reinterpret_cast<const uint4*>(kp + 8);
-    const uint4 v0 = *reinterpret_cast<const uint4*>(vp), v1 = *reinterpret_cast<const uint4*>(vp + 8);
+  const long long col = (long long)g * 128 + l8 * 16;
+  constexpr int STEP = DEC_STREAMS * 4;  // keys per CTA step
+  int t = t_begin + stream * 4 + sub;
+  uint4 k0 = make_uint4(0u, 0u, 0u, 0u), k1 = k0, v0 = k0, v1 = k0;
+  if (t < t_end) {
+    const bf16* kp = kc + (long long)t * kv_w + col;
+    const bf16* vp = vc + (long long)t * kv_w + col;
+    k0 = *reinterpret_cast<const uint4*>(kp); k1 = *reinterpret_cast<const uint4*>(kp + 8);
+    v0 = *reinterpret_cast<const uint4*>(vp); v1 = *reinterpret_cast<const uint4*>(vp + 8);
+  }
+  while (t < t_end) {
+    const int tn = t + STEP;
+    uint4 nk0 = k0, nk1 = k1, nv0 = v0, nv1 = v1;
+    if (tn < t_end) {  // request the next key/value rows before consuming the current ones
+      const bf16* kp = kc + (long long)tn * kv_w + col;
+      const bf16* vp = vc + (long long)tn * kv_w + col;
+      nk0 = *reinterpret_cast<const uint4*>(kp); nk1 = *reinterpret_cast<const uint4*>(kp + 8);
+      nv0 = *reinterpret_cast<const uint4*>(vp); nv1 = *reinterpret_cast<const uint4*>(vp + 8);
+    }
     const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
     float s = 0.f;
 #pragma unroll
@@ -285,59 +312,83 @@ decode_attn_partial_kernel(const bf16* __restrict__ q, const bf16* __restrict__ 
       acc[2 * i + 1] = acc[2 * i + 1] * corr + p * f.y;
     }
     m = mn;
+    k0 = nk0; k1 = nk1; v0 = nv0; v1 = nv1;
+    t = tn;
   }
-  // note: a lane whose key slots were all beyond t_end keeps m = -inf, l = 0 (handled by the combine weights)
-  const int slot = warp * 4 + sub;
-  if (l8 == 0) { s_m[slot] = m; s_l[slot] = l; }
+  // note: a lane whose key slots were all beyond t_end keeps m = -inf, l = 0 (handled by the merge weights)
+  const int slot = stream * 4 + sub;
+  if (l8 == 0) { s_m[hh][slot] = m; s_l[hh][slot] = l; }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s_acc[slot][l8 * 16 + i] = acc[i];
+  for (int i = 0; i < 16; ++i) s_acc[hh][slot][l8 * 16 + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int d = threadIdx.x;
+  {  // merge the CTA's slots: thread -> (head = tid / 64, two adjacent dims)
+    const int mh = threadIdx.x >> 6, d2 = (threadIdx.x & 63) * 2;
     float mm = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS * 4; ++w) mm = fmaxf(mm, s_m[w]);
-    float ll = 0.f, o = 0.f;
+    for (int w = 0; w < SLOTS; ++w) mm = fmaxf(mm, s_m[mh][w]);
+    float ll = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS * 4; ++w) {
-      const float c = (s_m[w] == -INFINITY) ? 0.f : exp2f(s_m[w] - mm);
-      ll += s_l[w] * c;
-      o += s_acc[w][d] * c;
+    for (int w = 0; w < SLOTS; ++w) {
+      const float c = (s_m[mh][w] == -INFINITY) ? 0.f : exp2f(s_m[mh][w] - mm);
+      ll += s_l[mh][w] * c;
+      o0 += s_acc[mh][w][d2] * c;
+      o1 += s_acc[mh][w][d2 + 1] * c;
     }
-    float* pp = part + ((long long)h * DEC_SPLITS + split) * 130;
-    pp[2 + d] = o;
-    if (d == 0) { pp[0] = mm; pp[1] = ll; }
+    float* pp = part + ((long long)(g * DEC_GROUP + mh) * DEC_SPLITS + split) * 130;
+    *reinterpret_cast<float2*>(pp + 2 + d2) = make_float2(o0, o1);
+    if (d2 == 0) { pp[0] = mm; pp[1] = ll; }
   }
-}
-
-// pass 2: merge the DEC_SPLITS partials of each head
-__global__ void __launch_bounds__(128)
-decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int h = blockIdx.x, d = threadIdx.x;
-  const float* pp = part + (long long)h * DEC_SPLITS * 130;
-  float mm = -INFINITY;
-#pragma unroll
-  for (int s = 0; s < DEC_SPLITS; ++s) mm = fmaxf(mm, pp[s * 130]);
-  float ll = 0.f, o = 0.f;
-#pragma unroll
-  for (int s = 0; s < DEC_SPLITS; ++s) {
-    const float m = pp[s * 130];
-    const float c = (m == -INFINITY) ? 0.f : exp2f(m - mm);
-    ll += pp[s * 130 + 1] * c;
-    o += pp[s * 130 + 2 + d] * c;
+  // ---- last CTA of this kv head merges the partials (release: fence + ticket; acquire: ticket + fence)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[g], 1u);
+  __syncthreads();
+  if (s_ticket != DEC_SPLITS - 1) return;
+  __threadfence();
+  const float* pg = part + (long long)g * DEC_GROUP * DEC_SPLITS * 130;
+  if (threadIdx.x < DEC_GROUP * DEC_SPLITS) s_w[threadIdx.x / DEC_SPLITS][threadIdx.x % DEC_SPLITS] =
+      __ldcg(pg + (long long)threadIdx.x * 130);  // m of (head, split)
+  __syncthreads();
+  if (threadIdx.x < DEC_GROUP) {  // weights exp2(m_s - max) and 1 / sum(l_s w_s) per head
+    const int mh = threadIdx.x;
+    float mm = -INFINITY;
+    for (int s2 = 0; s2 < DEC_SPLITS; ++s2) mm = fmaxf(mm, s_w[mh][s2]);
+    float ll = 0.f;
+    for (int s2 = 0; s2 < DEC_SPLITS; ++s2) {
+      const float ms = s_w[mh][s2];
+      const float c = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+      s_w[mh][s2] = c;
+      ll += __ldcg(pg + ((long long)mh * DEC_SPLITS + s2) * 130 + 1) * c;
+    }
+    s_inv[mh] = 1.0f / ll;
   }
-  out[h * 128 + d] = __float2bfloat16(o / ll);
+  __syncthreads();
+  {
+    const int mh = threadIdx.x >> 6, d2 = (threadIdx.x & 63) * 2;
+    const float* po = pg + (long long)mh * DEC_SPLITS * 130 + 2 + d2;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int s0 = 0; s0 < DEC_SPLITS; s0 += 16) {  // 16 independent 8-byte loads in flight per round
+      float2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldcg(reinterpret_cast<const float2*>(po + (long long)(s0 + i) * 130));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { o0 += v[i].x * s_w[mh][s0 + i]; o1 += v[i].y * s_w[mh][s0 + i]; }
+    }
+    const float inv = s_inv[mh];
+    *reinterpret_cast<uint32_t*>(out + (g * DEC_GROUP + mh) * 128 + d2) = pack_bf16x2(o0 * inv, o1 * inv);
+  }
+  if (threadIdx.x == 0) tickets[g] = 0u;  // ready for the next layer / step
 }
 
 // ---------------------------------------------------------------------------------------------------- token plumbing
 // x = table[clamp(token)]  (Embedding.forward, MP/model/llava/vlm_model.py:224-254; HF get_input_embeddings, EV :263)
 __global__ void __launch_bounds__(256)
 decode_embed_kernel(const long long* __restrict__ token, const bf16* __restrict__ table, long long ldt, long long vocab,
-                    bf16* __restrict__ x, int H) {
+                    bf16* __restrict__ x, int H, unsigned* __restrict__ tickets, int n_tickets) {
   pdl_launch_dependents();
   pdl_wait();
+  for (int i = threadIdx.x; i < n_tickets; i += blockDim.x) tickets[i] = 0u;  // attention merge tickets
   long long id = *token;
   if (id < 0) id = 0;
   if (id >= vocab) id = vocab - 1;
@@ -401,8 +452,208 @@ static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- GEMV, block-cooperative
+// The warp-per-row-pair kernel above walks a row in four dependent load rounds, which costs ~10 us of latency chain
+// per launch on the small projections (ncu: 2.7-3.0 TB/s on the 34-50 MB matrices, 6.5 TB/s only on lm_head).  Here a
+// whole CTA reduces R rows at once with the K dimension split over its 256 threads: thread t owns the 16-byte chunks
+// t, t+256, ... of EVERY row, so (a) all R x KCH loads of a block of rows are in flight together (one DRAM round trip
+// per block, 64 KB per CTA), (b) the activation chunks a thread needs never change and live in registers (the RMSNorm
+// prologue is thread-local apart from one block reduction), (c) the first block's weights are requested before the
+// activation row is even read (and before griddepcontrol.wait).  The next block's loads are issued as soon as the
+// dot products have consumed the registers, so they fly during the cross-warp reduction and the epilogue.
+// Row blocks pair each "primary" row with a partner at distance P (64: rotate-half RoPE, 32: gate/up, else adjacent).
+template <int MODE, int R>
+__device__ __forceinline__ void gemv3_block_rows(const GemvArgs& a, int blk, int& r0, int& P) {
+  constexpr int H = R / 2;
+  if (MODE == GV_QKV) {
+    const int per_head = 64 / H;  // blocks per q/k head
+    const int n_rot = (a.heads + a.kv_heads) * per_head;
+    if (blk < n_rot) { r0 = (blk / per_head) * 128 + (blk % per_head) * H; P = 64; }
+    else { r0 = (a.heads + a.kv_heads) * 128 + R * (blk - n_rot); P = H; }
+  } else if (MODE == GV_SWIGLU) {
+    const int per_gran = 32 / H;
+    r0 = (blk / per_gran) * 64 + (blk % per_gran) * H; P = 32;
+  } else {
+    r0 = R * blk; P = H;
+  }
+}
+
+// XS: keep the activation row in shared memory instead of registers (long rows: K = 14336 would cost 28 registers)
+// THREADS / MINB: CTA size and CTAs per SM the register budget is compiled for.  The <256, 4> and <512, 2> shapes
+// use at most half of an SM's registers and threads at one wave, so that with programmatic dependent launch the NEXT
+// kernel's CTAs are resident (and have their first weight rows in flight) while this one is still streaming.
+template <int MODE, int KCH, int R, bool XS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+gemv3_kernel(const GemvArgs a) {
+  constexpr int GV_THREADS = THREADS;
+  constexpr int GV_WARPS = THREADS / 32;
+  constexpr int H = R / 2;
+  extern __shared__ uint4 xs3[];  // XS only: K / 8 chunks
+  __shared__ float s_red[2][GV_WARPS][R];
+  __shared__ float s_ss[GV_WARPS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K8 = a.K >> 3;
+  const int n_blocks = a.N / R;
+  uint4 wreg[R][KCH];
+
+  auto load_block = [&](int blk) {
+    int r0, P;
+    gemv3_block_rows<MODE, R>(a, blk, r0, P);
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int row = r0 + (rr < H ? rr : P + rr - H);
+      const uint4* wp = reinterpret_cast<const uint4*>(a.W + (long long)row * a.ldw);
+#pragma unroll
+      for (int j = 0; j < KCH; ++j) {
+        const int c = tid + j * GV_THREADS;
+        wreg[rr][j] = (c < K8) ? ld_stream16(wp + c) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+
+  int blk = blockIdx.x;
+  if (blk < n_blocks) load_block(blk);  // weights do not depend on the previous kernel
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- this thread's activation chunks (optionally RMS-normalised), kept as packed bf16
+  uint4 xr[XS ? 1 : KCH];
+  if (XS) {  // no RMSNorm on this path (down projection): plain copy, each thread later reads back its own chunks
+    const uint4* xg = reinterpret_cast<const uint4*>(a.x);
+    for (int c = tid; c < K8; c += GV_THREADS) xs3[c] = xg[c];
+    __syncthreads();
+  } else {
+    const uint4* xg = reinterpret_cast<const uint4*>(a.x);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+      const int c = tid + j * GV_THREADS;
+      xr[j] = (c < K8) ? xg[c] : make_uint4(0u, 0u, 0u, 0u);
+      const float2 p = unpack_bf16x2(xr[j].x), q = unpack_bf16x2(xr[j].y), r = unpack_bf16x2(xr[j].z),
+                   s = unpack_bf16x2(xr[j].w);
+      ss += p.x * p.x + p.y * p.y + q.x * q.x + q.y * q.y + r.x * r.x + r.y * r.y + s.x * s.x + s.y * s.y;
+    }
+    if (a.gamma != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) s_ss[warp] = ss;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < GV_WARPS; ++w) tot += s_ss[w];
+      const float rstd = rsqrtf(tot / (float)a.K + a.eps);
+#pragma unroll
+      for (int j = 0; j < KCH; ++j) {
+        const int c = tid + j * GV_THREADS;
+        if (c < K8) {
+          const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + c * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + c * 8 + 4);
+          const float2 p = unpack_bf16x2(xr[j].x), q = unpack_bf16x2(xr[j].y), r = unpack_bf16x2(xr[j].z),
+                       s = unpack_bf16x2(xr[j].w);
+          xr[j].x = pack_bf16x2(p.x * rstd * g0.x, p.y * rstd * g0.y);
+          xr[j].y = pack_bf16x2(q.x * rstd * g0.z, q.y * rstd * g0.w);
+          xr[j].z = pack_bf16x2(r.x * rstd * g1.x, r.y * rstd * g1.y);
+          xr[j].w = pack_bf16x2(s.x * rstd * g1.z, s.y * rstd * g1.w);
+        }
+      }
+    }
+  }
+  const int pos = (MODE == GV_QKV) ? decode_position(a.pos_dev, a.pos_host) : 0;
+
+  int it = 0;
+  for (; blk < n_blocks; blk += gridDim.x, ++it) {
+    float acc[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) acc[rr] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+      uint4 xv;
+      if (XS) { const int c = tid + j * GV_THREADS; xv = (c < K8) ? xs3[c] : make_uint4(0u, 0u, 0u, 0u); }
+      else xv = xr[j];
+      const float2 p = unpack_bf16x2(xv.x), q = unpack_bf16x2(xv.y), r = unpack_bf16x2(xv.z), s = unpack_bf16x2(xv.w);
+      const float xf[8] = {p.x, p.y, q.x, q.y, r.x, r.y, s.x, s.y};
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) acc[rr] = dot8(wreg[rr][j], xf, acc[rr]);
+    }
+    const int next = blk + gridDim.x;
+    if (next < n_blocks) load_block(next);  // in flight during the reduction and the epilogue below
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], o);
+    }
+    float(*red)[R] = s_red[it & 1];
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) red[warp][rr] = acc[rr];
+    }
+    __syncthreads();  // one barrier per block: the partials are double-buffered by iteration parity
+    if (tid < H) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < GV_WARPS; ++w) { v0 += red[w][tid]; v1 += red[w][tid + H]; }
+      int r0, P;
+      gemv3_block_rows<MODE, R>(a, blk, r0, P);
+      const int ra = r0 + tid, rb = r0 + P + tid;
+      if (MODE == GV_PLAIN) {
+        if (a.residual) { v0 += __bfloat162float(a.y[ra]); v1 += __bfloat162float(a.y[rb]); }
+        a.y[ra] = __float2bfloat16(v0);
+        a.y[rb] = __float2bfloat16(v1);
+      } else if (MODE == GV_LOGITS) {
+        a.y32[ra] = v0;
+        a.y32[rb] = v1;
+      } else if (MODE == GV_SWIGLU) {
+        a.y[(ra >> 6) * 32 + (ra & 31)] = __float2bfloat16(silu_f(v0) * v1);
+      } else {  // GV_QKV
+        const int q_w = a.heads * 128, kv_w = a.kv_heads * 128;
+        if (pos >= 0 && pos < a.kv_capacity) {  // host validates; never write outside the cache
+          if (ra < q_w + kv_w) {
+            const float t1 = __bfloat162float(__float2bfloat16(v0)), t2 = __bfloat162float(__float2bfloat16(v1));
+            const float ang = (float)pos * a.inv_freq[ra & 63];
+            const float cs = cosf(ang), sn = sinf(ang);
+            const bf16 o1 = __float2bfloat16(t1 * cs - t2 * sn), o2 = __float2bfloat16(t2 * cs + t1 * sn);
+            if (ra < q_w) { a.q_out[ra] = o1; a.q_out[rb] = o2; }
+            else {
+              bf16* kp = a.kc + (long long)pos * kv_w + (ra - q_w);
+              kp[0] = o1; kp[64] = o2;
+            }
+          } else {
+            bf16* vp = a.vc + (long long)pos * kv_w + (ra - q_w - kv_w);
+            vp[0] = __float2bfloat16(v0);
+            vp[P] = __float2bfloat16(v1);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, int KCH, int R, bool XS, int THREADS, int MINB, int CTAS_PER_SM>
+static int launch_gemv3(const GemvArgs& a, cudaStream_t stream) {
+  const int n_blocks = a.N / R;
+  int grid = n_blocks;
+  const int cap = sm_count() * CTAS_PER_SM;
+  if (grid > cap) grid = cap;
+  ProfScope prof(10 + MODE, a.N, a.K, 3, stream);
+  return launch_pdl(gemv3_kernel<MODE, KCH, R, XS, THREADS, MINB>, dim3(grid), dim3(THREADS),
+                    XS ? (size_t)a.K * 2 : 0, stream, a);
+}
+
 template <int MODE>
 static int launch_gemv(const GemvArgs& a, cudaStream_t stream) {
+  if (g_decode_mode & 4) {  // block-cooperative kernels for the Llama-3.1-8B / Mistral-7B widths
+    const bool n_ok = (MODE == GV_SWIGLU) ? (a.N % 64 == 0) : (a.N % 8 == 0);
+    const bool half_sm = (g_decode_mode & 8) != 0;  // footprints that leave room for the dependent kernel
+    if (a.K == 4096 && n_ok && a.ldw % 8 == 0)
+      return half_sm ? launch_gemv3<MODE, 2, 4, false, 256, 4, 2>(a, stream)
+                     : launch_gemv3<MODE, 2, 8, false, 256, 2, 2>(a, stream);
+    if constexpr (MODE == GV_PLAIN) {
+      if (a.K == 14336 && a.N % 2 == 0 && a.ldw % 8 == 0 && a.gamma == nullptr)
+        return half_sm ? launch_gemv3<MODE, 4, 2, true, 512, 2, 1>(a, stream)
+                       : launch_gemv3<MODE, 7, 2, true, 256, 2, 2>(a, stream);
+    }
+  }
+
   LP_REQUIRE(a.N % 2 == 0 && a.K % 8 == 0 && a.ldw % 8 == 0 && a.K * 2 <= 48 * 1024,
              "decode gemv: unsupported shape N=%d K=%d ldw=%lld", a.N, a.K, a.ldw);
   const int groups = a.N / 2;
@@ -421,14 +672,14 @@ static inline size_t bf(size_t n) { return n * 2; }
 
 extern "C" int lp_decode_set_mode(int mode) {
   const int old = g_decode_mode;
-  g_decode_mode = mode & 3;
+  g_decode_mode = mode & 15;
   return old;
 }
 
 extern "C" size_t lp_decode_workspace_bytes(const lp_dec_dims* d) {
   const size_t qkv_w = (size_t)(d->heads + 2 * d->kv_heads) * d->head_dim;
   return 256 * 9 + bf(2 * (size_t)d->hidden) * 2 + bf(qkv_w) + bf((size_t)d->ffn) + (size_t)d->head_dim * 4 + 64 * 4 +
-         (size_t)d->heads * DEC_SPLITS * 130 * 4;
+         (size_t)d->heads * DEC_SPLITS * 130 * 4 + (size_t)d->heads * 4 + 256;
 }
 
 #define LP_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
@@ -450,8 +701,10 @@ static int decode_step_v1(const lp_dec_dims* d, const lp_dec_weights* w, const v
   float* sn = (float*)take(hd / 2 * 4);
   int* plan = (int*)take(16);
   float* part = (float*)take((size_t)d->heads * DEC_SPLITS * 130 * 4);
+  unsigned* tickets = (unsigned*)take((size_t)d->heads * 4);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
   int rc;
+  LP_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)d->heads * 4, stream));
   // new token's embedding row (ids stay on the device: no host round trip of the sampled token is needed here)
   LP_TRY(lp_embed_merge(token_id, 1, -(1LL << 62), 1, embed_table, ld_embed, d->vocab, nullptr, 0, 0, x, H, 1, H, plan,
                         stream));
@@ -469,10 +722,9 @@ static int decode_step_v1(const lp_dec_dims* d, const lp_dec_weights* w, const v
                                   stream));
     {
       ProfScope prof(8, position + 1, d->heads, 0, stream);
-      note_launch(2);
-      decode_attn_partial_kernel<<<dim3(d->heads, DEC_SPLITS), DEC_WARPS * 32, 0, stream>>>(
-          qkv, kc, vc, nullptr, position, (int)kv_capacity, kv_w, d->heads / d->kv_heads, scale_log2, part);
-      decode_attn_combine_kernel<<<d->heads, 128, 0, stream>>>(part, att);
+      note_launch();
+      decode_attn_kernel<<<dim3(d->kv_heads, DEC_SPLITS), DEC_WARPS * 32, 0, stream>>>(
+          qkv, kc, vc, nullptr, position, (int)kv_capacity, kv_w, scale_log2, part, tickets, att);
       LP_CHECK_CUDA(cudaGetLastError());
     }
     LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, 1, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 128, stream));
@@ -501,10 +753,11 @@ static int decode_step_v2(const lp_dec_dims* d, const lp_dec_weights* w, const v
   bf16* att = (bf16*)take(bf(H));
   bf16* act = (bf16*)take(bf(d->ffn));
   float* part = (float*)take((size_t)d->heads * DEC_SPLITS * 130 * 4);
+  unsigned* tickets = (unsigned*)take((size_t)d->heads * 4);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
   int rc;
   LP_TRY(launch_pdl(decode_embed_kernel, dim3(1), dim3(256), 0, stream, token_id, (const bf16*)embed_table, ld_embed,
-                    (long long)d->vocab, x, H));
+                    (long long)d->vocab, x, H, tickets, d->heads));
   GemvArgs base = {};
   base.eps = d->eps;
   base.heads = d->heads; base.kv_heads = d->kv_heads; base.kv_capacity = kv_capacity;
@@ -519,10 +772,9 @@ static int decode_step_v2(const lp_dec_dims* d, const lp_dec_weights* w, const v
     LP_TRY(launch_gemv<GV_QKV>(a, stream));
     {
       ProfScope prof(8, pos_host + 1, d->heads, 0, stream);
-      LP_TRY(launch_pdl(decode_attn_partial_kernel, dim3(d->heads, DEC_SPLITS), dim3(DEC_WARPS * 32), 0, stream,
+      LP_TRY(launch_pdl(decode_attn_kernel, dim3(d->kv_heads, DEC_SPLITS), dim3(DEC_WARPS * 32), 0, stream,
                         (const bf16*)qb, (const bf16*)kc, (const bf16*)vc, pos_dev, pos_host, (int)kv_capacity, kv_w,
-                        d->heads / d->kv_heads, scale_log2, part));
-      LP_TRY(launch_pdl(decode_attn_combine_kernel, dim3(d->heads), dim3(128), 0, stream, (const float*)part, att));
+                        scale_log2, part, tickets, att));
     }
     a = base;  // x += o_proj(att)
     a.W = (const bf16*)L->o_w; a.ldw = H; a.N = H; a.K = H; a.x = att; a.y = x; a.residual = 1;
@@ -544,7 +796,9 @@ static int decode_step_v2(const lp_dec_dims* d, const lp_dec_weights* w, const v
 static int decode_check(const lp_dec_dims* d, const lp_dec_weights* w, const void* embed_table, const void* token_id,
                         const void* kv_cache, const void* logits, const void* workspace, size_t ws_bytes) {
   LP_REQUIRE(d && w && embed_table && token_id && kv_cache && logits && workspace, "lp_decode_step: null argument");
-  LP_REQUIRE(d->head_dim == 128, "lp_decode_step: head_dim must be 128");
+  LP_REQUIRE(d->head_dim == 128 && d->heads == DEC_GROUP * d->kv_heads,
+             "lp_decode_step: head_dim must be 128 with 4 query heads per kv head (got %d / %d heads)", d->heads,
+             d->kv_heads);
   LP_REQUIRE(d->vocab % 2 == 0 && d->hidden % 8 == 0 && d->ffn % 32 == 0 && d->ffn * 2 <= 48 * 1024,
              "lp_decode_step: unsupported widths hidden=%d ffn=%d vocab=%d", d->hidden, d->ffn, d->vocab);
   LP_REQUIRE(ws_bytes >= lp_decode_workspace_bytes(d), "lp_decode_step: workspace too small");

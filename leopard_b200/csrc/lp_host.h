@@ -48,8 +48,10 @@ struct AttnArgs {
   __nv_bfloat16* O;
   long long ldo;
   float scale_log2;
+  int pingpong;               // lp_attn2: strict A/B alternation of the softmax warpgroups (turn protocol)
 };
 int launch_attn2(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, int emu, cudaStream_t stream);
+int launch_attn3(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, int emu, cudaStream_t stream);
 
 // 2-D / 3-D bf16 tensor maps with 128B swizzle (inner box = 64 elements = 128 B), zero OOB fill.
 // dims/strides are innermost-first; strides are in ELEMENTS for dims >= 1.

@@ -16,6 +16,15 @@
 
 using namespace lp;
 
+// attention kernel used by the layer loops: lp_attention_fwd `variant` (default 80 = v3 kernel with 64-key S halves,
+// one MMA issuer per query tile and the exp-section turn protocol; 2 = v2 two-tile kernel)
+static int g_attn_variant = 80;
+extern "C" int lp_model_set_attention_variant(int variant) {
+  const int old = g_attn_variant;
+  g_attn_variant = variant;
+  return old;
+}
+
 namespace {
 struct Carver {
   uint8_t* p;
@@ -60,15 +69,15 @@ static int vit_layers_impl(const lp_vit_dims* d, const lp_vit_weights* w, void* 
                         LP_ACT_NONE, 0, 0, stream));
     if (cu == nullptr) {
       LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, uniform_T, d->heads, d->heads, d->head_dim, d->head_stride, 0,
-                              d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0, scale, att, d->hidden, 2,
-                              stream));
+                              d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0, scale, att, d->hidden,
+                              g_attn_variant, stream));
     } else {
       for (int s = 0; s < n_seqs; ++s) {  // one launch per image (lengths differ)
         const int r0 = cu[s], T = cu[s + 1] - r0;
         LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->heads,
                                 d->head_dim, d->head_stride, 0, d->heads * d->head_stride,
                                 2 * d->heads * d->head_stride, 0, scale, (__nv_bfloat16*)att + (size_t)r0 * d->hidden,
-                                d->hidden, 2, stream));
+                                d->hidden, g_attn_variant, stream));
       }
     }
     LP_TRY(lp_gemm_bf16(att, d->hidden, L->out_w, d->hidden, x, d->hidden, rows, d->hidden, d->hidden, L->out_b, x,
@@ -204,12 +213,13 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
     LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
     if (uniform) {
       LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, R / n_seqs, d->heads, d->kv_heads, hd, hd, 0, q_w, q_w + kv_w, 1,
-                              scale, att, H, 2, stream));
+                              scale, att, H, g_attn_variant, stream));
     } else {
       for (int s = 0; s < n_seqs; ++s) {
         const int r0 = cu_seqlens_host[s], T = cu_seqlens_host[s + 1] - r0;
         LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->kv_heads, hd,
-                                hd, 0, q_w, q_w + kv_w, 1, scale, (__nv_bfloat16*)att + (size_t)r0 * H, H, 2, stream));
+                                hd, 0, q_w, q_w + kv_w, 1, scale, (__nv_bfloat16*)att + (size_t)r0 * H, H, g_attn_variant,
+                                stream));
       }
     }
     if (kv_cache) {  // [layers][2][R][kv_w]: K (post-RoPE) then V

@@ -60,25 +60,28 @@ def test_decode_step_matches_oracle_and_first_implementation(small):
     emb = table[ids]
     _, kv = eng.decoder(emb[:S].to(torch.bfloat16).cuda(), torch.arange(S), [0, S], "last", want_kv=True,
                         kv_capacity=S + 8)
-    kv1 = kv.clone()
+    kv1, kv2 = kv.clone(), kv.clone()
     for i in range(3):  # three consecutive steps: each attends to the rows the previous ones appended
         tok = ids[S + i:S + i + 1].cuda()
         ref = om.decoder_forward(ck, cfg, emb[:S + i + 1], torch.arange(S + i + 1), last_only=True)[0]
-        got = _step(eng, tok, S + i, kv, mode=1)
-        old = _step(eng, tok, S + i, kv1, mode=0)
-        e_ref, e_old = rel_err(got, ref), rel_err(got, old)
-        print(f"\n[parity] decode step {i}: GEMV vs oracle {e_ref:.4f}, GEMV vs tcgen05 M=1 path {e_old:.4f}")
-        assert e_ref < 3e-2 and e_old < 2e-2
+        got = _step(eng, tok, S + i, kv, mode=5)      # block-cooperative GEMV kernels (default)
+        warp = _step(eng, tok, S + i, kv2, mode=1 if i else 13)  # warp-per-row-pair GEMV / half-SM block GEMV
+        old = _step(eng, tok, S + i, kv1, mode=0)     # first implementation
+        e_ref, e_old, e_warp = rel_err(got, ref), rel_err(got, old), rel_err(got, warp)
+        print(f"\n[parity] decode step {i}: GEMV vs oracle {e_ref:.4f}, vs tcgen05 M=1 path {e_old:.4f}, "
+              f"vs warp GEMV {e_warp:.4f}")
+        assert e_ref < 3e-2 and e_old < 2e-2 and e_warp < 2e-2
     # appended cache rows: same values as the first implementation up to bf16 rounding flips
     new_rows = kv[:, :, S:S + 3].float()
     assert rel_err(new_rows, kv1[:, :, S:S + 3].float()) < 2e-2
+    assert rel_err(new_rows, kv2[:, :, S:S + 3].float()) < 2e-2
     # and as a prefill of the extended sequence (K after RoPE, V)
     _, kv_full = eng.decoder(emb.to(torch.bfloat16).cuda(), torch.arange(S + 3), [0, S + 3], "none", want_kv=True)
     assert rel_err(new_rows, kv_full[:, :, S:S + 3].float()) < 2e-2
     assert torch.equal(kv[:, :, :S], kv_full[:, :, :S])  # prefill rows untouched by the decode steps
 
 
-@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("mode", [1, 3, 5, 7, 13, 15])
 def test_graph_replay_and_pdl_are_bit_identical_to_eager(small, mode, monkeypatch):
     cfg, ck, eng = small
     pix, ids = synth_inputs(cfg, n_crops=1, n_text=20, seed=5)
@@ -89,11 +92,11 @@ def test_graph_replay_and_pdl_are_bit_identical_to_eager(small, mode, monkeypatc
         monkeypatch.setenv("LEOPARD_DECODE_MODE", str(mode))
         toks = GreedyDecoder(eng).run(ids[0].cuda(), pix.cuda(), n_new, set())
         runs[graph] = (toks.tolist(), eng._decode_state.logits.clone(), int(eng._decode_state.pos.item()))
-    monkeypatch.setenv("LEOPARD_DECODE_MODE", "1")
+    monkeypatch.setenv("LEOPARD_DECODE_MODE", str(mode & ~2))   # same kernels without programmatic dependent launch
     monkeypatch.setenv("LEOPARD_DECODE_GRAPH", "0")
     base = GreedyDecoder(eng).run(ids[0].cuda(), pix.cuda(), n_new, set())
     base_logits = eng._decode_state.logits.clone()
-    _lib.lib().lp_decode_set_mode(1)
+    _lib.lib().lp_decode_set_mode(5)
     assert runs["0"][0] == runs["1"][0] == base.tolist()
     assert torch.equal(runs["0"][1], runs["1"][1]) and torch.equal(runs["0"][1], base_logits)
     S = ids.shape[1] + 168

@@ -99,7 +99,7 @@ def _attn_ref(qkv, B, T, H, HK, dh, hs, wq, wk, causal):
     (3, 676, 16, 16, 72, 80, False),
     (2, 100, 16, 16, 72, 80, False),
 ])
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 18, 64, 80, 84])
 def test_attention(native_lib, B, T, H, HK, dh, hs, causal, variant):
     qkv, wq, wk = _qkv(B, T, H, HK, dh, hs, seed=T + H)
     ref = _attn_ref(qkv, B, T, H, HK, dh, hs, wq, wk, causal)

@@ -2,9 +2,11 @@
 decode implementation, against the HBM floor (every decoder weight + the KV cache read once per token).
 
   mode 0 eager : first implementation, M = 1 rows through the tcgen05 GEMM, one launch per op
-  mode 1 eager : GEMV kernels, launched one by one
-  mode 1 graph : GEMV kernels, one CUDA-graph replay per token (default)
-  mode 3 graph : + programmatic dependent launch edges
+  mode 1 graph : warp-per-row-pair GEMV kernels, one CUDA-graph replay per token
+  mode 5 eager : block-cooperative GEMV kernels, launched one by one
+  mode 5 graph : block-cooperative GEMV kernels, CUDA-graph replay (default)
+  mode 7 graph : + programmatic dependent launch edges
+  mode 13 / 15 : block-cooperative GEMV with half-SM footprints (without / with programmatic dependent launch)
 Writes one JSON line per variant to stdout (and to gpurun_out/decode_speed.json when that directory exists).
 """
 import json
@@ -33,7 +35,7 @@ peaks = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json")
 hbm = peaks.get("hbm_gbs", 6500.0)
 N_NEW = 65
 out = []
-for mode, graph in ((0, "0"), (1, "0"), (1, "1"), (3, "1"), (3, "0")):
+for mode, graph in ((0, "0"), (1, "1"), (5, "0"), (5, "1"), (7, "1"), (13, "1"), (15, "1"), (15, "0")):
     os.environ["LEOPARD_DECODE_MODE"] = str(mode)
     os.environ["LEOPARD_DECODE_GRAPH"] = graph if mode else "0"
     if mode == 0:
@@ -62,7 +64,7 @@ for mode, graph in ((0, "0"), (1, "0"), (1, "1"), (3, "1"), (3, "0")):
         steps(N_NEW - 1)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / (N_NEW - 1)
-        L.lp_decode_set_mode(1)
+        L.lp_decode_set_mode(5)
         del kv
     else:
         def gen(n):
@@ -82,7 +84,7 @@ for mode, graph in ((0, "0"), (1, "0"), (1, "1"), (3, "1"), (3, "0")):
            "frac_of_hbm_peak": round((w_bytes + kv_bytes) / ms / 1e6 / hbm, 3)}
     print(json.dumps(rec), flush=True)
     out.append(rec)
-_lib.lib().lp_decode_set_mode(1)
+_lib.lib().lp_decode_set_mode(5)
 od = Path(__file__).resolve().parents[1] / "gpurun_out"
 if od.exists():
     (od / "decode_speed.json").write_text("\n".join(json.dumps(r) for r in out) + "\n")
