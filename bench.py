@@ -219,6 +219,85 @@ def run_reference(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------ extras (rank 0, N = 1)
+def decode_extra(model, ids_h, pix_h, cfg, S, peaks, n_new=33):
+    """Greedy decode after the prefill: ms per generated token from generate(n_new) - generate(1),
+    against the HBM floor (every decoder weight + lm_head + the KV cache read once per token)."""
+    import time
+    import torch
+    d = cfg.dec
+
+    def gen(n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o = model.generate(ids_h, pixel_values=pix_h, max_new_tokens=n)
+        torch.cuda.synchronize()
+        assert o.shape[1] == ids_h.shape[1] + n
+        return time.perf_counter() - t0
+    gen(n_new)  # graph capture, cache buffer
+    t1 = min(gen(1) for _ in range(2))
+    tn = min(gen(n_new) for _ in range(2))
+    ms = (tn - t1) * 1e3 / (n_new - 1)
+    w_bytes = 2 * (d.layers * (d.hidden * (d.heads + 2 * d.kv_heads) * d.head_dim + d.hidden * d.hidden +
+                               3 * d.hidden * d.ffn) + model.engine.w.vocab_padded * d.hidden)
+    kv_bytes = 2 * d.layers * 2 * S * d.kv_heads * d.head_dim
+    ach = (w_bytes + kv_bytes) / (ms * 1e-3) / 1e9
+    return {"ms_per_token": round(ms, 4), "new_tokens": n_new, "context_rows": S, "bound": "hbm",
+            "algorithmic_bytes_per_token": w_bytes + kv_bytes, "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
+            "api": "generate(max_new_tokens=33) minus generate(max_new_tokens=1): CUDA-graph replay of "
+                   "lp_decode_greedy_step per token, 8-byte token read-back per token"}
+
+
+def frontend_extra(model, ids_h, cfg, S, dev, steps):
+    """GPU image front-end on the same request given as raw images: 4 x (896 x 1152) RGB uint8 ->
+    28 crops.  Times the front-end alone (pinned uint8 H2D + kernels), the request end to end from raw images, and the
+    reference's host path (PIL resize/pad/tile + processor arithmetic, 1 thread) on this box; checks bit-exactness."""
+    import time
+    import numpy as np
+    import torch
+    from PIL import Image
+    from leopard_b200.frontend import ImageFrontend
+    from leopard_b200.preprocess import preprocess_images, to_pixel_values
+    rng = np.random.default_rng(7)
+    imgs = [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).pin_memory() for (w, h) in IMAGE_SIZES]
+    fe = ImageFrontend(dev)
+    pv, per_image = fe(imgs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        pv, _ = fe(imgs, dtype=torch.bfloat16)
+    e1.record()
+    torch.cuda.synchronize()
+    fe_ms = e0.elapsed_time(e1) / steps
+
+    def step():
+        p, _ = fe(imgs, dtype=torch.bfloat16)
+        return model.generate(ids_h, pixel_values=p, max_new_tokens=1, use_cache=False).cpu()
+    step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / steps
+    t0 = time.perf_counter()
+    crops, per_image_host = preprocess_images([Image.fromarray(t.numpy(), "RGB") for t in imgs])
+    host = to_pixel_values(crops)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    exact = per_image_host == per_image and bool(torch.equal(fe(imgs)[0].cpu(), host))
+    u8 = sum(t.numel() for t in imgs)
+    return {"images": "4 x (896 x 1152) RGB uint8 -> 28 crops [28, 3, 364, 364] bf16", "gpu_ms_per_request": round(fe_ms, 4),
+            "h2d_bytes_per_request": u8, "bit_exact_vs_pil_host_path": exact,
+            "host_pil_ms_per_request": round(host_ms, 2), "host_threads": 1,
+            "e2e_from_images": {"value": round(S / (e2e_ms * 1e-3), 1), "unit": "tokens/s", "ms_per_step": round(e2e_ms, 3),
+                                "h2d_bytes_per_step": u8 + ids_h.numel() * 8,
+                                "api": "ImageFrontend(host uint8 images) -> generate(host ids, pixel_values, "
+                                       "max_new_tokens=1)"}}
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -343,6 +422,12 @@ def run_ours(args):
             "flops": {kk: float(v) for kk, v in fm.items()},
         }
 
+    # ---- next-row extras (rank 0, N = 1 only): greedy decode and the GPU image front-end
+    decode, frontend = None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        decode = decode_extra(model, ids_h, pix_h, cfg, S, load_peaks())
+        frontend = frontend_extra(model, ids_h, cfg, S, dev, args.steps)
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -361,7 +446,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "leopard_b200.hf.myLlavaForConditionalGeneration.generate(host ids, pixel_values=host fp32, max_new_tokens=1)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "decode": decode, "frontend": frontend,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -376,6 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the decode / image front-end measurements")
     ap.add_argument("--quick", action="store_true", help="1 warm-up, timed loop only (for runs under ncu)")
     ap.add_argument("--gemm-pair", type=int, default=None, help="override the GEMM CTA-pair mode (0/1)")
     args = ap.parse_args()

@@ -285,10 +285,14 @@ int lp_decode_graph_create(const lp_dec_dims* dims, const lp_dec_weights* w, con
 int lp_decode_graph_launch(lp_decode_graph* graph, void* stream);
 void lp_decode_graph_destroy(lp_decode_graph* graph);
 
-/* Decode implementation switch, returns the previous mode.  bit 0: 1 = HBM-streaming GEMV kernels with fused
- * RMSNorm / RoPE + cache append / SwiGLU / residual (default), 0 = M = 1 rows through lp_gemm_bf16 (first
- * implementation, lp_decode_step only).  bit 1: launch the step's kernels with programmatic dependent launch
- * (griddepcontrol): the next kernel prefetches its weights into L2 while the previous one drains. */
+/* Decode implementation switch, returns the previous mode (default 7).
+ *   bit 0: HBM-streaming GEMV kernels with fused RMSNorm / RoPE + cache append / SwiGLU / residual; 0 = M = 1 rows
+ *          through lp_gemm_bf16 (first implementation, lp_decode_step only);
+ *   bit 1: launch the step's kernels with programmatic dependent launch (griddepcontrol): the next kernel's CTAs request
+ *          their first weight rows while the previous kernel drains;
+ *   bit 2: block-cooperative GEMV (a CTA reduces 8 rows with K split over its threads, activations in registers)
+ *          instead of warp-per-row-pair;
+ *   bit 4: lp_decode_greedy_step runs the whole step as ONE persistent cooperative kernel with grid barriers (21). */
 int lp_decode_set_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -321,6 +325,9 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
  *   14 image front-end (a,b,c = H, W, tiles). */
 typedef struct lp_profile_record { int kind, a, b, c; float ms; } lp_profile_record;
 long long lp_launch_count(void);
+/* Debug hook of the single-kernel decode step: when a DEVICE uint64 buffer (>= 2 * (5 * layers + 4) entries) is set,
+ * CTA 0 records %globaltimer before and after every grid barrier (entries 2e, 2e+1 for barrier e = 1, 2, ...). */
+int lp_decode_debug_stamps(void* device_u64_buffer);
 int lp_profile_enable(int capacity);
 int lp_profile_read(lp_profile_record* out, int capacity);
 

@@ -95,6 +95,7 @@ _SIGS = {
     "lp_decode_set_mode": (_i, [_i]),
     "lp_image_frontend_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lp_image_frontend": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
+    "lp_decode_debug_stamps": (_i, [_vp]),
     "lp_launch_count": (_ll, []),
     "lp_profile_enable": (_i, [_i]),
     "lp_profile_read": (_i, [_vp, _i]),

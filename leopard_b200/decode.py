@@ -8,7 +8,8 @@ as HBM-streaming GEMV kernels over the KV cache, picks the arg-max and advances 
 captured once into a CUDA graph (`lp_decode_graph_create`) and replayed per token; the only host work per token is
 reading the 8-byte token back for the stopping criterion, like GenerationMixin does.
   LEOPARD_DECODE_GRAPH=0   launch the step's kernels one by one instead of replaying the graph
-  LEOPARD_DECODE_MODE=n    lp_decode_set_mode(n): bit 0 GEMV kernels (default 1), bit 1 programmatic dependent launch
+  LEOPARD_DECODE_MODE=n    lp_decode_set_mode(n): bit 0 GEMV kernels, bit 1 programmatic dependent launch, bit 2 block-
+                           cooperative GEMV (default 7 = all three), 21 = one persistent kernel per token
 """
 from __future__ import annotations
 

@@ -6,7 +6,7 @@ decode implementation, against the HBM floor (every decoder weight + the KV cach
   mode 5 eager : block-cooperative GEMV kernels, launched one by one
   mode 5 graph : block-cooperative GEMV kernels, CUDA-graph replay (default)
   mode 7 graph : + programmatic dependent launch edges
-  mode 13 / 15 : block-cooperative GEMV with half-SM footprints (without / with programmatic dependent launch)
+  mode 21      : one persistent cooperative kernel per token (eager / graph)
 Writes one JSON line per variant to stdout (and to gpurun_out/decode_speed.json when that directory exists).
 """
 import json
@@ -35,7 +35,7 @@ peaks = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json")
 hbm = peaks.get("hbm_gbs", 6500.0)
 N_NEW = 65
 out = []
-for mode, graph in ((0, "0"), (1, "1"), (5, "0"), (5, "1"), (7, "1"), (13, "1"), (15, "1"), (15, "0")):
+for mode, graph in ((0, "0"), (1, "1"), (5, "0"), (5, "1"), (7, "1"), (21, "0"), (21, "1")):
     os.environ["LEOPARD_DECODE_MODE"] = str(mode)
     os.environ["LEOPARD_DECODE_GRAPH"] = graph if mode else "0"
     if mode == 0:
@@ -64,7 +64,7 @@ for mode, graph in ((0, "0"), (1, "1"), (5, "0"), (5, "1"), (7, "1"), (13, "1"),
         steps(N_NEW - 1)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / (N_NEW - 1)
-        L.lp_decode_set_mode(5)
+        L.lp_decode_set_mode(7)
         del kv
     else:
         def gen(n):
@@ -84,7 +84,7 @@ for mode, graph in ((0, "0"), (1, "1"), (5, "0"), (5, "1"), (7, "1"), (13, "1"),
            "frac_of_hbm_peak": round((w_bytes + kv_bytes) / ms / 1e6 / hbm, 3)}
     print(json.dumps(rec), flush=True)
     out.append(rec)
-_lib.lib().lp_decode_set_mode(5)
+_lib.lib().lp_decode_set_mode(7)
 od = Path(__file__).resolve().parents[1] / "gpurun_out"
 if od.exists():
     (od / "decode_speed.json").write_text("\n".join(json.dumps(r) for r in out) + "\n")
