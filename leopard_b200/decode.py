@@ -80,10 +80,21 @@ class GreedyDecoder:
         n_rows = eng.merged_length(ids, pixel_values)
         kv = self._kv_buffer(n_rows + max_new_tokens)
         logits, kv, cu = eng.prefill([(ids, pixel_values)], "last", want_kv=True, kv_buffer=kv)
-        S = cu[-1]
+        return self.continue_from(logits, kv, cu[-1], max_new_tokens, eos, mode)
+
+    @torch.no_grad()
+    def continue_from(self, logits: torch.Tensor, kv: torch.Tensor, S: int, max_new_tokens: int, eos: Set[int],
+                      mode: Optional[str] = None):
+        """Greedy loop after ANY prefill that left `S` rows in the cache `kv` [layers, 2, capacity, kv_w] and produced the
+        last row's `logits` (shared by the LLaVA and Idefics2 shims).  Returns the new token ids (1-D, on the device)."""
+        eng, st = self.eng, self.st
+        cfg = eng.cfg
+        L = _lib.lib()
         cap = kv.shape[2]
+        if S + max_new_tokens - 1 > cap:
+            raise ValueError(f"KV cache capacity {cap} cannot hold {S} prompt rows + {max_new_tokens - 1} new tokens")
         ws = eng._workspace("decode", L.lp_decode_workspace_bytes(C.byref(eng.w.dec_dims)))
-        st.tok.copy_(logits.argmax(-1).to(torch.long))
+        st.tok.copy_(logits.reshape(-1, logits.shape[-1])[-1:, : cfg.dec.vocab].argmax(-1).to(torch.long))
         st.pos.fill_(S)
         args = (C.byref(eng.w.dec_dims), C.byref(eng.w.dec), _lib.ptr(eng.w.embed), eng.w.embed.stride(0),
                 _lib.ptr(st.tok), _lib.ptr(st.pos), _lib.ptr(kv), cap, _lib.ptr(st.logits), cfg.dec.vocab,

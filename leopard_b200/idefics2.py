@@ -239,19 +239,9 @@ class Idefics2ForConditionalGeneration:
         logits, kv, S = eng.prefill(input_ids, pixel_values, pixel_attention_mask, "last", want_kv=max_new_tokens > 1,
                                     kv_capacity=max_new_tokens)
         base = eng.base
-        tok = logits.argmax(-1).to(torch.long)
-        out = []
-        step_logits = torch.empty((base.w.vocab_padded,), dtype=torch.float32, device=base.device)
-        ws = base._workspace("decode", L.lp_decode_workspace_bytes(C.byref(base.w.dec_dims)))
-        for i in range(max_new_tokens):
-            t = int(tok.item())
-            out.append(t)
-            if t in eos or i == max_new_tokens - 1:
-                break
-            rc = L.lp_decode_step(C.byref(base.w.dec_dims), C.byref(base.w.dec), _lib.ptr(base.w.embed),
-                                  base.w.embed.stride(0), _lib.ptr(tok), S + i, _lib.ptr(kv), kv.shape[2],
-                                  _lib.ptr(step_logits), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
-            _lib.check(rc, "lp_decode_step")
-            tok = step_logits[: self.config.dec.vocab].argmax(-1, keepdim=True).to(torch.long)
-        new = torch.tensor(out, dtype=torch.long, device=base.device)
+        if max_new_tokens <= 1:
+            new = logits[..., : self.config.dec.vocab].argmax(-1).reshape(-1)[-1:].to(torch.long)
+            return torch.cat([input_ids.to(base.device), new[None]], dim=1)
+        from .decode import GreedyDecoder   # same device-resident greedy loop (CUDA-graph replay) as the LLaVA shim
+        new = GreedyDecoder(base).continue_from(logits, kv, S, max_new_tokens, eos)
         return torch.cat([input_ids.to(base.device), new[None]], dim=1)

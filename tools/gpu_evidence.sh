@@ -1,0 +1,28 @@
+#!/bin/bash
+# Round evidence on one B200: GPU test suite, smoke, both bench arms, ncu launch lists (prefill step, decode step, image
+# front-end), ncu --set full of the dominant GEMM and of the v3 attention kernels.  Outputs under gpurun_out/ev_*.
+mkdir -p gpurun_out
+T=${TAG:-ev}
+timeout 1500 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "parity|passed|failed|error" > gpurun_out/${T}_pytest_gpu.log
+tail -2 gpurun_out/${T}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -1 gpurun_out/${T}_smoke.log
+timeout 600 python examples/llava_eval_loop.py --synthetic --layers 2 --max-new-tokens 6 > gpurun_out/${T}_example.log 2>&1; tail -2 gpurun_out/${T}_example.log
+timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err
+tail -c 900 gpurun_out/${T}_bench_n1.json
+KR='regex:gemm_bf16_kernel|attn3_fwd_kernel|attn2_fwd_kernel|attn_fwd_kernel|norm_kernel|rmsnorm_reread|rope_kernel|rope_table_kernel|merge_|im2col_patch14|pixel_shuffle'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -s 455 -c 455 --csv \
+    --log-file gpurun_out/${T}_launches.csv python bench.py --quick --steps 1 > gpurun_out/${T}_prof.log 2>&1
+N_NEW=5 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -k regex:'gemv|decode_' -s 260 -c 130 --csv --log-file gpurun_out/${T}_decode_launches.csv \
+  python tools/gpu_decode_prof.py >> gpurun_out/${T}_prof.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -k regex:'resample_|pad_fill' -s 18 -c 36 --csv --log-file gpurun_out/${T}_frontend_launches.csv \
+  python tools/gpu_frontend_prof.py >> gpurun_out/${T}_prof.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn3_fwd -s 2 -c 1 -f -o gpurun_out/${T}_attn3_dec \
+  python tools/gpu_check_attn.py --case dec_4796_c --variant 80 --time >> gpurun_out/${T}_prof.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn3_fwd -s 2 -c 1 -f -o gpurun_out/${T}_attn3_vit \
+  python tools/gpu_check_attn.py --case vit_28 --variant 80 --time >> gpurun_out/${T}_prof.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:gemv3_kernel -s 262 -c 5 -f -o gpurun_out/${T}_gemv \
+  python tools/gpu_decode_prof.py >> gpurun_out/${T}_prof.log 2>&1
+ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
