@@ -221,7 +221,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ extras (rank 0, N = 1)
-def decode_extra(model, ids_h, pix_h, cfg, S, peaks, n_new=33):
+def decode_extra(model, ids_h, pix_h, cfg, S, peaks, n_new=65):
     """Greedy decode after the prefill: ms per generated token from generate(n_new) - generate(1),
     against the HBM floor (every decoder weight + lm_head + the KV cache read once per token)."""
     import time
@@ -246,7 +246,7 @@ def decode_extra(model, ids_h, pix_h, cfg, S, peaks, n_new=33):
     return {"ms_per_token": round(ms, 4), "new_tokens": n_new, "context_rows": S, "bound": "hbm",
             "algorithmic_bytes_per_token": w_bytes + kv_bytes, "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
-            "api": "generate(max_new_tokens=33) minus generate(max_new_tokens=1): CUDA-graph replay of "
+            "api": "generate(max_new_tokens=65) minus generate(max_new_tokens=1): CUDA-graph replay of "
                    "lp_decode_greedy_step per token, 8-byte token read-back per token"}
 
 

@@ -112,6 +112,10 @@ int lp_layernorm(const void* x, long long ldx, const float* gamma, const float* 
 int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void* out, long long ldo, int M, int D, float eps,
                void* stream);
 
+/* RMSNorm kernel for rows wider than 1280: 1 = packed register-resident (row read once, 16 loads per lane in flight;
+ * default), 0 = two-pass re-read.  Bit-identical results.  Returns the previous value. */
+int lp_norm_set_variant(int variant);
+
 /* cos/sin[s, j] = cos/sin(pos[s] * inv_freq[j]), fp32 [S, half]
  *   (MLM/core/models/common/embeddings/rotary_pos_embedding.py:125-157; inv_freq incl. llama3.1 rescale :48-83 is
  *   computed by the host shim) */

@@ -70,6 +70,7 @@ _SIGS = {
     "lp_attention_cross": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
     "lp_layernorm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
     "lp_rmsnorm": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _vp]),
+    "lp_norm_set_variant": (_i, [_i]),
     "lp_rope_table": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "lp_rope_inplace": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lp_embed_merge": (_i, [_vp, _i, _ll, _i, _vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp]),

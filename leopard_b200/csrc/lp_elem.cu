@@ -141,12 +141,65 @@ rmsnorm_reread_kernel(const bf16* __restrict__ x, long long ldx, const float* __
   }
 }
 
+// RMSNorm for wide rows, register-resident and PACKED: a lane keeps its 16-byte chunks as bf16 (4 registers each, 64 for
+// D = 4096) instead of 8 floats, so the whole row is requested in one batch (16 independent loads per lane in flight,
+// 8 KB per warp), read from memory exactly once, and occupancy stays at 16 warps per SM.  The statistics / normalise
+// arithmetic and rounding points are identical to norm_kernel<true, *> and rmsnorm_reread_kernel.
+template <int CH>
+__global__ void __launch_bounds__(256, 3)  // <= 85 registers: keeps the row packed instead of 128 unpacked floats
+rmsnorm_packed_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                      bf16* __restrict__ out, long long ldo, int M, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  uint4 u[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    u[i] = (c < nchunk) ? xr[c] : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const float2 a = unpack_bf16x2(u[i].x), b = unpack_bf16x2(u[i].y), cc = unpack_bf16x2(u[i].z), d = unpack_bf16x2(u[i].w);
+    s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float rstd = rsqrtf(s / (float)D + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    // opaque to the optimiser: the floats unpacked for the statistics pass must not be kept alive (128 registers);
+    // they are re-derived from the packed registers here (2 ALU ops per pair)
+    asm volatile("" : "+r"(u[i].x), "+r"(u[i].y), "+r"(u[i].z), "+r"(u[i].w));
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+      const float2 a = unpack_bf16x2(u[i].x), b = unpack_bf16x2(u[i].y), cc = unpack_bf16x2(u[i].z), d = unpack_bf16x2(u[i].w);
+      uint4 y;
+      y.x = pack_bf16x2(a.x * rstd * g0.x, a.y * rstd * g0.y);
+      y.y = pack_bf16x2(b.x * rstd * g0.z, b.y * rstd * g0.w);
+      y.z = pack_bf16x2(cc.x * rstd * g1.x, cc.y * rstd * g1.y);
+      y.w = pack_bf16x2(d.x * rstd * g1.z, d.y * rstd * g1.w);
+      orow[c] = y;
+    }
+  }
+}
+
+static int g_norm_variant = 1;  // 1: packed register-resident RMSNorm for wide rows, 0: re-read variant
+
 template <bool RMS>
 static void launch_norm(const bf16* x, long long ldx, const float* g, const float* b, bf16* out, long long ldo, int M,
                         int D, float eps, int shuffle_side, cudaStream_t stream) {
   const int grid = (M + NORM_THREADS / 32 - 1) / (NORM_THREADS / 32);
   if (D <= 32 * 8 * 5)
     norm_kernel<RMS, 5><<<grid, NORM_THREADS, 0, stream>>>(x, ldx, g, b, out, ldo, M, D, eps, shuffle_side);
+  else if (RMS && shuffle_side == 0 && g_norm_variant == 1)
+    rmsnorm_packed_kernel<16><<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, g, out, ldo, M, D, eps);
   else if (RMS && shuffle_side == 0 && x != out)
     rmsnorm_reread_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, g, out, ldo, M, D, eps);
   else
@@ -226,15 +279,17 @@ merge_plan_kernel(const long long* __restrict__ ids, int L, long long image_id, 
   }
 }
 
-// pass 2: one CTA per input token copies its row(s)
+// pass 2: CTA (t, r) copies row r of input token t (text tokens have one row; an image slot has rows_per_slot rows).
+// One CTA per OUTPUT row: a slot's 169 rows used to be copied serially by one CTA (1.4 MB each, 185 us per merge).
 __global__ void __launch_bounds__(128)
 merge_copy_kernel(const long long* __restrict__ ids, const int* __restrict__ dst, const int* __restrict__ src,
                   const bf16* __restrict__ table, long long ldt, long long vocab, const bf16* __restrict__ feats,
                   long long ldf, int n_feat_rows, bf16* __restrict__ out, long long ldo, int D, int rows_per_slot) {
-  const int t = blockIdx.x;
+  const int t = blockIdx.x, r = blockIdx.y;
   const int nchunk = D >> 3;
   const int s = src[t];
   if (s < 0) {
+    if (r != 0) return;
     long long id = ids[t];
     if (id < 0) id = 0;            // Megatron clamps ignore/pad ids to row 0 (vlm_model.py:226)
     if (id >= vocab) id = vocab - 1;
@@ -242,12 +297,10 @@ merge_copy_kernel(const long long* __restrict__ ids, const int* __restrict__ dst
     uint4* dp = reinterpret_cast<uint4*>(out + (long long)dst[t] * ldo);
     for (int c = threadIdx.x; c < nchunk; c += blockDim.x) dp[c] = sp[c];
   } else {
-    for (int r = 0; r < rows_per_slot; ++r) {
-      if (s + r >= n_feat_rows) break;  // count mismatch is reported by the host wrapper
-      const uint4* sp = reinterpret_cast<const uint4*>(feats + (long long)(s + r) * ldf);
-      uint4* dp = reinterpret_cast<uint4*>(out + (long long)(dst[t] + r) * ldo);
-      for (int c = threadIdx.x; c < nchunk; c += blockDim.x) dp[c] = sp[c];
-    }
+    if (s + r >= n_feat_rows) return;  // count mismatch is reported by the host wrapper
+    const uint4* sp = reinterpret_cast<const uint4*>(feats + (long long)(s + r) * ldf);
+    uint4* dp = reinterpret_cast<uint4*>(out + (long long)(dst[t] + r) * ldo);
+    for (int c = threadIdx.x; c < nchunk; c += blockDim.x) dp[c] = sp[c];
   }
 }
 
@@ -361,6 +414,12 @@ extern "C" int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void
   return 0;
 }
 
+extern "C" int lp_norm_set_variant(int variant) {
+  const int old = g_norm_variant;
+  g_norm_variant = variant;
+  return old;
+}
+
 extern "C" int lp_rope_table(const int* pos, const float* inv_freq, float* cos_out, float* sin_out, int S, int half,
                              void* stream) {
   LP_REQUIRE(S > 0 && half > 0 && pos != nullptr, "lp_rope_table: bad S=%d half=%d", S, half);
@@ -416,7 +475,7 @@ extern "C" int lp_embed_merge(const long long* ids, int L, long long image_id, i
   note_launch(2);
   merge_plan_kernel<<<1, 1024, 0, stream>>>(ids, L, image_id, rows_per_slot, dst, src, totals);
   LP_CHECK_CUDA(cudaGetLastError());
-  merge_copy_kernel<<<L, 128, 0, stream>>>(ids, dst, src, reinterpret_cast<const bf16*>(table), ldt, vocab,
+  merge_copy_kernel<<<dim3(L, rows_per_slot), 128, 0, stream>>>(ids, dst, src, reinterpret_cast<const bf16*>(table), ldt, vocab,
                                            reinterpret_cast<const bf16*>(feats), ldf, n_feat_rows,
                                            reinterpret_cast<bf16*>(out), ldo, D, rows_per_slot);
   LP_CHECK_CUDA(cudaGetLastError());
