@@ -53,6 +53,20 @@ CASES = {
     "d_o": (4796, 4096, 4096, False, 0, True, 0, False, 0),
     "d_o_256": (4796, 4096, 4096, False, 0, True, 0, False, 256),
     "d_o_160": (4796, 4096, 4096, False, 0, True, 0, False, 160),
+    "d_o_224": (4796, 4096, 4096, False, 0, True, 0, False, 224),
+    "d_o_192": (4796, 4096, 4096, False, 0, True, 0, False, 192),
+    "d_down_224": (4796, 4096, 14336, False, 0, True, 0, False, 224),
+    "d_down_192": (4796, 4096, 14336, False, 0, True, 0, False, 192),
+    "d_qkv_224": (4796, 6144, 4096, False, 0, False, 0, False, 224),
+    "d_qkv_256": (4796, 6144, 4096, False, 0, False, 0, False, 256),
+    "v_qkv_224": (18928, 3840, 1152, True, 0, False, 0, False, 224),
+    "v_qkv_192": (18928, 3840, 1152, True, 0, False, 0, False, 192),
+    "v_fc1_224": (18928, 4304, 1152, True, 1, False, 0, False, 224),
+    "v_fc1_192": (18928, 4304, 1152, True, 1, False, 0, False, 192),
+    "v_fc2_192": (18928, 1152, 4304, True, 0, True, 0, False, 192),
+    "v_fc2_128": (18928, 1152, 4304, True, 0, True, 0, False, 128),
+    "v_out_192": (18928, 1152, 1152, True, 0, True, 0, False, 192),
+    "v_out_128": (18928, 1152, 1152, True, 0, True, 0, False, 128),
     "d_gateup": (4796, 28672, 4096, False, 3, False, 0, False, 0),
     "d_gateup_192": (4796, 28672, 4096, False, 3, False, 0, False, 192),
     "d_down": (4796, 4096, 14336, False, 0, True, 0, False, 0),
