@@ -57,6 +57,12 @@ int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, voi
  * Results are identical up to fp32 summation order (same K order: bit-identical in practice). */
 int lp_gemm_set_pair_mode(int enable);
 
+/* Launch the hot prefill kernels (GEMM, attention v3, norms, RoPE) with programmatic dependent launch: the next kernel's
+ * CTAs are scheduled as SMs free up and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the
+ * previous kernel drains; each kernel executes griddepcontrol.wait before its first dependent global access.  Results
+ * are unchanged.  Returns the previous setting (default set by the library). */
+int lp_set_prefill_pdl(int enable);
+
 /* O[b,t,h,:] = softmax(scale * Q K^T (+causal)) V          (tcgen05 flash attention, fp32 softmax, bf16 in/out)
  *   replaces flash_attn_varlen_func (MP/model/llava/transformer.py:476-515,869-877; the 4x KV repeat_interleave at
  *   :829-836 is not materialised) and the ViT's TEDotProductAttention / HF SiglipAttention

@@ -64,6 +64,7 @@ _SIGS = {
     "lp_abi_version": (_i, []),
     "lp_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "lp_gemm_set_pair_mode": (_i, [_i]),
+    "lp_set_prefill_pdl": (_i, [_i]),
     "lp_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _i, _vp]),
     "lp_attention_set_pingpong": (_i, [_i]),
     "lp_model_set_attention_variant": (_i, [_i]),
@@ -128,6 +129,9 @@ def lib():
                 raise NativeError(f"{LIB_PATH} does not export {name}: rebuild the library") from e
             fn.argtypes = argtypes
             fn.restype = restype
+        import os
+        if os.environ.get("LEOPARD_PREFILL_PDL") is not None:  # A/B switch for the prefill kernels' launch mode
+            L.lp_set_prefill_pdl(int(os.environ["LEOPARD_PREFILL_PDL"]))
         _lib = L
     return _lib
 

@@ -140,6 +140,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                   args.v_off + kv_head * args.hs + b * 64, j * 128, batch);
   };
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int i = 0; i < 2; ++i) {
@@ -156,6 +157,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       mbar_init(&p_full[i], 128);
     }
     fence_barrier_init();
+    pdl_wait();  // the only thread that reads global memory before the CTA-wide barrier below
     // start the first loads right away: they overlap the TMEM allocation and the CTA-wide barrier below
     for (int q = 0; q < (actB ? 2 : 1); ++q) {
       mbar_arrive_expect_tx(&q_full[q], HEAD_BYTES);
@@ -174,6 +176,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everyone else: before any global store (O rows) or further loads
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (tiles 0, 1 already in flight)
@@ -410,7 +413,7 @@ static int launch3(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream
     configured = true;
   }
   dim3 grid((a.T + 255) / 256, a.n_heads, a.B);
-  kern<<<grid, A3_THREADS, SMEM, stream>>>(tm, a);
+  LP_CHECK_CUDA(launch_ex(kern, grid, dim3(A3_THREADS), SMEM, stream, 1, prefill_pdl(), tm, a));
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -36,6 +36,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute): `wait` blocks until every
+// prerequisite grid has completed and its memory is visible — it must precede the first dependent global access;
+// `launch_dependents` lets the next kernel's CTAs be scheduled as soon as this grid's resources free up
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

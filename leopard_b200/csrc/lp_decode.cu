@@ -31,8 +31,6 @@ int rope_table_base(int pos_base, const float* inv_freq, float* cs, float* sn, i
 
 static int g_decode_mode = 7;  // bit 0: GEMV kernels, bit 1: programmatic dependent launch, bit 2: block-cooperative GEMV, bit 4: one persistent kernel per token
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   uint4 r;

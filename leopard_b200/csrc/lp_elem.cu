@@ -26,6 +26,8 @@ template <bool RMS, int CH>
 __global__ void __launch_bounds__(NORM_THREADS)
 norm_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
             bf16* __restrict__ out, long long ldo, int M, int D, float eps, int shuffle_side) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (NORM_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -149,6 +151,8 @@ template <int CH>
 __global__ void __launch_bounds__(256, 3)  // <= 85 registers: keeps the row packed instead of 128 unpacked floats
 rmsnorm_packed_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                       bf16* __restrict__ out, long long ldo, int M, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -197,9 +201,11 @@ static void launch_norm(const bf16* x, long long ldx, const float* g, const floa
                         int D, float eps, int shuffle_side, cudaStream_t stream) {
   const int grid = (M + NORM_THREADS / 32 - 1) / (NORM_THREADS / 32);
   if (D <= 32 * 8 * 5)
-    norm_kernel<RMS, 5><<<grid, NORM_THREADS, 0, stream>>>(x, ldx, g, b, out, ldo, M, D, eps, shuffle_side);
+    launch_ex(norm_kernel<RMS, 5>, dim3(grid), dim3(NORM_THREADS), 0, stream, 1, prefill_pdl(), x, ldx, g, b, out, ldo, M, D,
+              eps, shuffle_side);
   else if (RMS && shuffle_side == 0 && g_norm_variant == 1)
-    rmsnorm_packed_kernel<16><<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, g, out, ldo, M, D, eps);
+    launch_ex(rmsnorm_packed_kernel<16>, dim3((M + 7) / 8), dim3(256), 0, stream, 1, prefill_pdl(), x, ldx, g, out, ldo, M, D,
+              eps);
   else if (RMS && shuffle_side == 0 && x != out)
     rmsnorm_reread_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, g, out, ldo, M, D, eps);
   else
@@ -221,6 +227,8 @@ __global__ void rope_table_kernel(const int* __restrict__ pos, int pos_base, con
 // one thread per (row, head, 8-wide chunk pair): x1 = cols [c, c+8), x2 = cols [c + half, c + half + 8)
 __global__ void rope_kernel(bf16* __restrict__ x, long long ld, int S, int col0, int n_heads, int half,
                             const float* __restrict__ cs, const float* __restrict__ sn) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cpr = half >> 3;  // chunk pairs per head
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)S * n_heads * cpr;
@@ -451,8 +459,8 @@ extern "C" int lp_rope_inplace(void* x, long long ld, int S, int col0, int n_hea
   const long long total = (long long)S * n_heads * (half / 8);
   ProfScope prof(4, S, n_heads, 1, reinterpret_cast<cudaStream_t>(stream));
   note_launch();
-  rope_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<bf16*>(x), ld, S, col0, n_heads, half, cos_t, sin_t);
+  launch_ex(rope_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1,
+            prefill_pdl(), reinterpret_cast<bf16*>(x), ld, S, col0, n_heads, half, cos_t, sin_t);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -255,6 +255,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel's tail; nothing below may
+  // touch global memory before the prerequisite grids have completed
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_tiles = args.num_m_blk * args.num_n_blk;
 
@@ -442,22 +446,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int tiles = args.num_m_blk * args.num_n_blk;
   if (!CTA2) {
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, args);
+    LP_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, 1, prefill_pdl(), tmA, tmB, tmC, args));
   } else {
     const int pairs = sm_count() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = L::TOTAL;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, args));
+    LP_CHECK_CUDA(launch_ex(kern, dim3(2 * (tiles < pairs ? tiles : pairs)), dim3(GEMM_THREADS), L::TOTAL, stream, 2,
+                            prefill_pdl(), tmA, tmB, tmC, args));
   }
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;

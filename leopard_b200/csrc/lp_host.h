@@ -30,6 +30,38 @@ const char* get_error();
 
 int sm_count();
 
+// prefill kernels are launched with the programmatic-dependent-launch attribute when this is on (lp_set_prefill_pdl):
+// every such kernel calls griddepcontrol.wait before its first dependent global access
+bool prefill_pdl();
+
+// kernel launch with optional cluster dimension and optional programmatic dependent launch
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                             bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // launch accounting + optional per-launch CUDA-event timing (off by default; see lp_profile_* in the public header)
 void note_launch(int n = 1);
 struct ProfScope {

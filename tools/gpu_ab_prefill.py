@@ -27,6 +27,8 @@ def apply(setting):
         L.lp_model_set_attention_variant(v)
     elif k == "pair":
         L.lp_gemm_set_pair_mode(v)
+    elif k == "pdl":
+        L.lp_set_prefill_pdl(v)
     elif k == "norm":
         L.lp_norm_set_variant(v)
     else:
