@@ -255,6 +255,53 @@ __global__ void rope_kernel(bf16* __restrict__ x, long long ld, int S, int col0,
   *reinterpret_cast<uint4*>(p2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
 }
 
+// RoPE on the q and k heads of the fused QKV buffer AND the KV-cache append of the same rows in one pass (prefill with
+// a cache): k heads are written rotated both in place (attention reads them there) and to kc[row], v heads are copied
+// to vc[row].  Replaces rope_kernel + two strided cudaMemcpy2DAsync per layer (64 copy launches per prefill).
+// Layout of x: [n_q heads | n_kv k heads | n_kv v heads] x 2*half columns; cache rows have n_kv * 2*half columns.
+__global__ void rope_kv_kernel(bf16* __restrict__ x, long long ld, int S, int n_q, int n_kv, int half,
+                               const float* __restrict__ cs, const float* __restrict__ sn, bf16* __restrict__ kc,
+                               bf16* __restrict__ vc, long long ld_cache) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cpr = half >> 3;  // chunk pairs per head
+  const int n_heads = n_q + 2 * n_kv;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)S * n_heads * cpr;
+  if (i >= total) return;
+  const int c = (int)(i % cpr);
+  const int h = (int)((i / cpr) % n_heads);
+  const int s = (int)(i / ((long long)cpr * n_heads));
+  bf16* p1 = x + (long long)s * ld + h * 2 * half + c * 8;
+  bf16* p2 = p1 + half;
+  const uint4 u1 = *reinterpret_cast<const uint4*>(p1), u2 = *reinterpret_cast<const uint4*>(p2);
+  if (h >= n_q + n_kv) {  // v head: plain copy into the cache
+    bf16* d = vc + (long long)s * ld_cache + (h - n_q - n_kv) * 2 * half + c * 8;
+    *reinterpret_cast<uint4*>(d) = u1;
+    *reinterpret_cast<uint4*>(d + half) = u2;
+    return;
+  }
+  const float* cp = cs + (long long)s * half + c * 8;
+  const float* sp = sn + (long long)s * half + c * 8;
+  const uint32_t a1[4] = {u1.x, u1.y, u1.z, u1.w}, a2[4] = {u2.x, u2.y, u2.z, u2.w};
+  uint32_t o1[4], o2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f1 = unpack_bf16x2(a1[j]), f2 = unpack_bf16x2(a2[j]);
+    const float c0 = cp[2 * j], c1 = cp[2 * j + 1], s0 = sp[2 * j], s1 = sp[2 * j + 1];
+    o1[j] = pack_bf16x2(f1.x * c0 - f2.x * s0, f1.y * c1 - f2.y * s1);   // same arithmetic as rope_kernel
+    o2[j] = pack_bf16x2(f2.x * c0 + f1.x * s0, f2.y * c1 + f1.y * s1);
+  }
+  const uint4 r1 = make_uint4(o1[0], o1[1], o1[2], o1[3]), r2 = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  *reinterpret_cast<uint4*>(p1) = r1;
+  *reinterpret_cast<uint4*>(p2) = r2;
+  if (h >= n_q) {  // k head: also into the cache (K is cached after RoPE)
+    bf16* d = kc + (long long)s * ld_cache + (h - n_q) * 2 * half + c * 8;
+    *reinterpret_cast<uint4*>(d) = r1;
+    *reinterpret_cast<uint4*>(d + half) = r2;
+  }
+}
+
 // ---- embedding + merge -------------------------------------------------------------------------------------------
 // pass 1 (single CTA): per input token t, dst[t] = first output row, src[t] = first feature row (or -1 for text)
 __global__ void __launch_bounds__(1024)
@@ -464,6 +511,23 @@ extern "C" int lp_rope_inplace(void* x, long long ld, int S, int col0, int n_hea
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+namespace lp {
+// RoPE in place on the q|k heads of x [S, ld] + append K (rotated) and V rows 0 .. S-1 to the cache (see rope_kv_kernel)
+int rope_kv_append(void* x, long long ld, int S, int n_q, int n_kv, int head_dim, const float* cos_t, const float* sin_t,
+                   void* kc, void* vc, long long ld_cache, cudaStream_t stream) {
+  LP_REQUIRE(S > 0 && head_dim % 16 == 0 && ld % 8 == 0 && ld_cache % 8 == 0 && aligned16(x) && aligned16(kc) && aligned16(vc),
+             "rope_kv_append: bad S=%d head_dim=%d or alignment", S, head_dim);
+  const int half = head_dim / 2;
+  const long long total = (long long)S * (n_q + 2 * n_kv) * (half / 8);
+  ProfScope prof(4, S, n_q + n_kv, 2, stream);
+  note_launch();
+  LP_CHECK_CUDA(launch_ex(rope_kv_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, 1, prefill_pdl(),
+                          reinterpret_cast<bf16*>(x), ld, S, n_q, n_kv, half, cos_t, sin_t, reinterpret_cast<bf16*>(kc),
+                          reinterpret_cast<bf16*>(vc), ld_cache));
+  return 0;
+}
+}  // namespace lp
 
 extern "C" int lp_embed_merge(const long long* ids, int L, long long image_id, int rows_per_slot, const void* table,
                               long long ldt, long long vocab, const void* feats, long long ldf, int n_feat_rows,

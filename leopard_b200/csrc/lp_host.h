@@ -71,6 +71,10 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// RoPE in place on the q|k heads of x [S, ld] fused with the KV-cache append of the same rows (lp_elem.cu)
+int rope_kv_append(void* x, long long ld, int S, int n_q, int n_kv, int head_dim, const float* cos_t, const float* sin_t,
+                   void* kc, void* vc, long long ld_cache, cudaStream_t stream);
+
 // attention launch arguments (shared by lp_attn.cu and lp_attn2.cu)
 struct AttnArgs {
   int T, B, n_heads, group;   // T = query rows per sequence

@@ -209,8 +209,15 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
     const lp_dec_layer_weights* L = &w->layers[l];
     LP_TRY(lp_rmsnorm(x, H, L->ln1_g, h, H, R, H, d->eps, stream));
     LP_TRY(lp_gemm_bf16(h, H, L->qkv_w, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE, 0, 0, stream));
-    // q heads and k heads are contiguous column-wise: one RoPE launch covers heads + kv_heads
-    LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
+    // q heads and k heads are contiguous column-wise: one RoPE launch covers heads + kv_heads; with a cache the same
+    // launch appends K (after RoPE) and V of rows 0..R-1: [layers][2][capacity][kv_w]
+    if (kv_cache) {
+      __nv_bfloat16* kc = (__nv_bfloat16*)kv_cache + (size_t)l * 2 * kv_capacity * kv_w;
+      LP_TRY(rope_kv_append(qkv, qkv_w, R, d->heads, d->kv_heads, hd, cs, sn, kc, kc + (size_t)kv_capacity * kv_w, kv_w,
+                            stream));
+    } else {
+      LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
+    }
     if (uniform) {
       LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, R / n_seqs, d->heads, d->kv_heads, hd, hd, 0, q_w, q_w + kv_w, 1,
                               scale, att, H, g_attn_variant, stream));
@@ -221,13 +228,6 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
                                 hd, 0, q_w, q_w + kv_w, 1, scale, (__nv_bfloat16*)att + (size_t)r0 * H, H, g_attn_variant,
                                 stream));
       }
-    }
-    if (kv_cache) {  // [layers][2][R][kv_w]: K (post-RoPE) then V
-      __nv_bfloat16* kc = (__nv_bfloat16*)kv_cache + (size_t)l * 2 * kv_capacity * kv_w;
-      LP_CHECK_CUDA(cudaMemcpy2DAsync(kc, bf(kv_w), (const __nv_bfloat16*)qkv + q_w, bf(qkv_w), bf(kv_w), R,
-                                      cudaMemcpyDeviceToDevice, stream));
-      LP_CHECK_CUDA(cudaMemcpy2DAsync(kc + (size_t)kv_capacity * kv_w, bf(kv_w), (const __nv_bfloat16*)qkv + q_w + kv_w,
-                                      bf(qkv_w), bf(kv_w), R, cudaMemcpyDeviceToDevice, stream));
     }
     LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, R, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 0, stream));
     LP_TRY(lp_rmsnorm(x, H, L->ln2_g, h, H, R, H, d->eps, stream));
