@@ -91,6 +91,24 @@ class LlavaCausalLMOutputWithPast:
         return tuple(v for v in (self.loss, self.logits, self.past_key_values) if v is not None)[i]
 
 
+class NativeKVCache(tuple):
+    """`past_key_values` as the reference reads it — a tuple over layers of (key, value), each `[1, kv_heads, S,
+    head_dim]` (…anyres.py:294 indexes `[0][0][:, :, :, 0]`) — whose entries are VIEWS of the native cache buffer
+    `[layers, 2, capacity, kv_w]`.  Passing it back to `forward(input_ids=[1, 1], past_key_values=...)` lets the cached
+    single-token branch (…anyres.py:291-320) append in place instead of re-importing the tensors."""
+
+    def __new__(cls, kv: torch.Tensor, length: int, kv_heads: int, head_dim: int):
+        views = tuple((kv[l, 0, :length].view(length, kv_heads, head_dim).permute(1, 0, 2)[None],
+                       kv[l, 1, :length].view(length, kv_heads, head_dim).permute(1, 0, 2)[None])
+                      for l in range(kv.shape[0]))
+        self = super().__new__(cls, views)
+        self.kv, self.length = kv, length
+        return self
+
+    def get_seq_length(self):
+        return self.length
+
+
 def _config_from_hf_json(d: dict) -> LeopardConfig:
     t, v = d.get("text_config", {}), d.get("vision_config", {})
     rs = t.get("rope_scaling")
@@ -262,8 +280,39 @@ class myLlavaForConditionalGeneration:
         """[layers, 2, cap, kv_w] -> tuple-of-tuples [layer][k|v] shaped [1, kv_heads, S, head_dim] (views), the legacy
         format the reference indexes directly (…anyres.py:294)."""
         d = self.config.dec
-        return tuple((kv[l, 0, :S].view(S, d.kv_heads, d.head_dim).permute(1, 0, 2)[None],
-                      kv[l, 1, :S].view(S, d.kv_heads, d.head_dim).permute(1, 0, 2)[None]) for l in range(d.layers))
+        return NativeKVCache(kv, int(S), d.kv_heads, d.head_dim)
+
+    def _native_cache(self, past, room: int) -> "NativeKVCache":
+        """Any legacy `past_key_values` -> a native cache with room for `room` more rows (copying when it is a foreign
+        tuple of `[1, kv_heads, S, head_dim]` tensors, e.g. produced by transformers, or when capacity is exhausted)."""
+        d = self.config.dec
+        if isinstance(past, NativeKVCache) and past.kv.shape[2] >= past.length + room:
+            return past
+        S = int(past[0][0].shape[2])
+        cap = -(-(S + max(room, 64)) // 256) * 256
+        kv = torch.empty((d.layers, 2, cap, d.kv_heads * d.head_dim), dtype=torch.bfloat16, device=self.engine.device)
+        for l in range(d.layers):
+            for j in (0, 1):
+                t = past[l][j].to(self.engine.device, torch.bfloat16)
+                kv[l, j, :S] = t[0].permute(1, 0, 2).reshape(S, -1)
+        return NativeKVCache(kv, S, d.kv_heads, d.head_dim)
+
+    def _cached_step(self, input_ids, past):
+        """The cached branch of the reference forward (…anyres.py:291-320) for B = 1 without padding: the new token's
+        position is the number of cached rows; one native decode step over the cache."""
+        import ctypes as C
+        eng = self.engine
+        L = _lib.lib()
+        cache = self._native_cache(past, 1)
+        tok = input_ids.reshape(-1)[-1:].to(eng.device, torch.long).contiguous()
+        ws = eng._workspace("decode", L.lp_decode_workspace_bytes(C.byref(eng.w.dec_dims)))
+        logits = torch.empty((eng.w.vocab_padded,), dtype=torch.float32, device=eng.device)
+        rc = L.lp_decode_step(C.byref(eng.w.dec_dims), C.byref(eng.w.dec), _lib.ptr(eng.w.embed), eng.w.embed.stride(0),
+                              _lib.ptr(tok), cache.length, _lib.ptr(cache.kv), cache.kv.shape[2], _lib.ptr(logits),
+                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "lp_decode_step")
+        d = self.config.dec
+        return logits[: d.vocab].view(1, 1, -1), NativeKVCache(cache.kv, cache.length + 1, d.kv_heads, d.head_dim)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -274,7 +323,12 @@ class myLlavaForConditionalGeneration:
         if output_attentions or output_hidden_states:
             raise NotImplementedError("attention maps / hidden states are not materialised by the fused path")
         if past_key_values is not None:
-            raise NotImplementedError("cached single-token steps are driven by .generate()")
+            if input_ids is None or input_ids.shape[0] != 1 or input_ids.shape[1] != 1:
+                raise NotImplementedError("with past_key_values the reference feeds ONE new token (…anyres.py:291)")
+            logits, past = self._cached_step(input_ids, past_key_values)
+            if return_dict is False:
+                return (logits, past)
+            return LlavaCausalLMOutputWithPast(logits=logits, past_key_values=past)
         if inputs_embeds is not None:
             out = self.language_model(inputs_embeds=inputs_embeds, position_ids=position_ids, use_cache=use_cache)
             logits, past = out.logits, out.past_key_values
@@ -285,7 +339,8 @@ class myLlavaForConditionalGeneration:
                 raise NotImplementedError("padded prompts are outside the reference's usage (…anyres.py:443-446)")
             pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
             ids = input_ids.to(eng.device, non_blocking=True)
-            logits, kv, cu = eng.prefill([(ids[0], pix)], "all", torch.float32, want_kv=bool(use_cache))
+            # room for the cached single-token steps a caller may drive through forward(past_key_values=...)
+            logits, kv, cu = eng.prefill([(ids[0], pix)], "all", torch.float32, want_kv=bool(use_cache), kv_capacity=128)
             logits = logits[None]
             past = self._legacy_cache(kv, cu[-1]) if kv is not None else None
         loss = None

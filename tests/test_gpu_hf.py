@@ -113,6 +113,34 @@ def test_decode_step_logits_match_prefill_of_longer_sequence(small):
     assert toks.tolist() == gen[0, ids.shape[1]:].tolist()
 
 
+def test_forward_with_past_key_values_is_the_cached_decode_branch(small):
+    """forward(input_ids=[1, 1], past_key_values=...) — the branch at …anyres.py:291-320 that GenerationMixin drives —
+    against the oracle's recomputation of the extended sequence; native cache objects and foreign legacy tuples."""
+    cfg, ck, model = small
+    pix, ids = synth_inputs(cfg, n_crops=1, n_text=14, seed=8)
+    out = model(input_ids=ids, pixel_values=pix, use_cache=True)
+    S = ids.shape[1] + 168
+    tok = out.logits[0, -1].argmax().view(1, 1)
+    out2 = model(input_ids=tok, past_key_values=out.past_key_values, use_cache=True)
+    assert out2.logits.shape == (1, 1, cfg.dec.vocab) and out2.past_key_values[0][0].shape == (1, 8, S + 1, 128)
+    feats = om.projector(ck, cfg, om.vit_forward(ck, cfg, pix.to(torch.bfloat16).float()))
+    emb, _ = om.merge_hf_expand(ck, cfg, ids, feats)
+    table = ck.f32("language_model.model.embed_tokens.weight")
+    x = torch.cat([emb[0], table[int(tok):int(tok) + 1]], 0)
+    ref = om.decoder_forward(ck, cfg, x, torch.arange(x.shape[0]), last_only=True)[0]
+    assert rel_err(out2.logits[0, 0], ref) < 3e-2
+    # a second step continues in place on the same buffer
+    tok2 = out2.logits[0, -1].argmax().view(1, 1)
+    out3 = model(input_ids=tok2, past_key_values=out2.past_key_values)
+    assert out3.past_key_values[0][0].shape[2] == S + 2 and out3.past_key_values.kv.data_ptr() == out2.past_key_values.kv.data_ptr()
+    # a foreign legacy tuple (plain tensors, as transformers would hand back) is imported by copy: same logits
+    foreign = tuple((k.clone(), v.clone()) for k, v in out.past_key_values)
+    out4 = model(input_ids=tok, past_key_values=foreign, return_dict=False)
+    assert torch.equal(out4[0], out2.logits)
+    with pytest.raises(NotImplementedError):
+        model(input_ids=ids, past_key_values=out.past_key_values)
+
+
 def test_cpu_tensors_are_moved_but_cpu_model_is_refused(small):
     cfg, ck, model = small
     from leopard_b200._lib import NativeError
