@@ -387,8 +387,20 @@ def run_ours(args):
         n = L.lp_profile_read(C.cast(recs, C.c_void_p), cap)
         by_kind = {}
         gemm_shapes = {}
+        stage_ms = {"vit": 0.0, "projector": 0.0, "decoder": 0.0}
+        vit_rows = n_crops * cfg.vit.tokens
         for r in recs[:n]:
             by_kind[r.kind] = by_kind.get(r.kind, 0.0) + r.ms
+            # stage attribution: ViT kernels run on 28 x 676 rows / T = 676 / width 1152, the projector on 28 x 169 rows
+            if r.kind == 1:
+                st = "vit" if r.a == vit_rows else ("projector" if r.a == n_crops * cfg.tokens_per_crop else "decoder")
+            elif r.kind == 2:
+                st = "vit" if r.b == cfg.vit.tokens else "decoder"
+            elif r.kind == 3:
+                st = "vit" if r.b == cfg.vit.hidden else "decoder"
+            else:
+                st = "vit" if r.kind in (6, 7) else "decoder"
+            stage_ms[st] += r.ms
             if r.kind == 1:
                 key = (r.a, r.b, r.c)
                 g = gemm_shapes.setdefault(key, [0.0, 0])
@@ -420,6 +432,14 @@ def run_ours(args):
                              "tflops": round(2.0 * a * b * c * v[1] / (v[0] * 1e-3) / 1e12, 1)}
                             for (a, b, c), v in sorted(gemm_shapes.items(), key=lambda kv: -kv[1][0])],
             "flops": {kk: float(v) for kk, v in fm.items()},
+            # BASELINE.json's "ViT+decoder % roofline": algorithmic FLOPs of the stage / its summed kernel time (CUDA
+            # events inside a real step) against the measured sustained cuBLAS bf16 peak
+            "roofline_by_stage": {
+                st: {"ms": round(ms, 3), "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
+                     "frac_of_sustained_peak": round(fl / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], 4)}
+                for st, ms, fl in (("vit", stage_ms["vit"], fm["vit"]), ("projector", stage_ms["projector"], fm["proj"]),
+                                   ("decoder", stage_ms["decoder"], fm["dec_linear"] + fm["dec_attn"] + fm["lm_head_last"]))
+                if ms > 0},
         }
 
     # ---- next-row extras (rank 0, N = 1 only): greedy decode and the GPU image front-end
