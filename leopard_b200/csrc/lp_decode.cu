@@ -5,21 +5,25 @@
 // use_cache=True)` at :448-452): with B = 1 and no padding the rebuilt mask is all ones and the position is the
 // number of cached rows.
 //
-// The step is HBM-bound: every decoder weight (16.06 GB for Llama-3.1-8B) is read exactly once per token, so the
-// floor is weights / HBM bandwidth (~2.5 ms on a B200) and the design is about keeping the memory system saturated
-// across ~200 short kernels:
-//   gemv_kernel<MODE>   y = W x for ONE activation row: a warp owns two weight rows at a time and streams them with
-//                       8 x 16-byte non-allocating loads in flight per lane; x is staged once per CTA in shared memory.
-//                       Fused prologue: RMSNorm of the residual stream (MLM/legacy/model/rms_norm.py:26-31).
-//                       Fused epilogues: QKV -> rotate-half RoPE on (i, i+64) row pairs + append K/V to the cache
+// The step is HBM-bound: every decoder weight (15.0 GB for Llama-3.1-8B incl. lm_head) is read exactly once per token,
+// so the floor is weights / HBM bandwidth (~2.4 ms on a B200) and the design is about keeping the memory system
+// saturated across ~160 short kernels (measured: 3.2 ms/token at S = 4796 = 75 % of the HBM copy peak):
+//   gemv3_kernel<MODE,..> y = W x for ONE activation row, block-cooperative: a CTA reduces 8 weight rows at a time with
+//                       K split over its 256 threads — 16 x 16-byte non-allocating loads in flight per thread, the
+//                       activation chunks in registers (default, mode bit 2).
+//   gemv_kernel<MODE>   the first GEMV: a warp owns two weight rows and walks them in four load rounds (mode bit 2 = 0).
+//                       Both: fused prologue RMSNorm of the residual stream (MLM/legacy/model/rms_norm.py:26-31);
+//                       fused epilogues QKV -> rotate-half RoPE on (i, i+64) row pairs + append K/V to the cache
 //                       (MP/model/llava/transformer.py:853-856); gate/up -> silu(gate)*up (:129-139); o/down -> residual
 //                       add in place; lm_head -> fp32 logits.
-//   decode_attn_*       split-K GQA attention over the bf16 KV cache (heads x 16 key ranges) + combine.
+//   decode_attn_kernel  split-K GQA attention over the bf16 KV cache: CTA = (kv head, 1 of 37 key ranges) for the four
+//                       q heads of the group, cp.async K/V pipeline, last CTA per kv head merges the partials.
 //   argmax / embed      greedy token selection and the next embedding row, device-resident, so that a whole step
 //                       (lp_decode_greedy_step) reads its position and token from device memory and can be captured
-//                       once into a CUDA graph and replayed per token with no host work.
+//                       once into a CUDA graph (lp_decode_graph_*) and replayed per token with no host work.
+//   decode_mega_kernel  the same step as ONE persistent cooperative kernel with grid barriers (mode bit 4; slower).
 // All kernels start with griddepcontrol.wait and may be launched with programmatic dependent launch (mode bit 1): the
-// next kernel's CTAs become resident and prefetch their first weight rows into L2 while the previous kernel drains.
+// next kernel's CTAs request their first weight rows while the previous kernel drains.
 // Mode bit 0 = 0 selects the first implementation (M = 1 rows through the tcgen05 GEMM), kept for A/B measurements.
 #include "lp_common.cuh"
 #include "lp_host.h"
