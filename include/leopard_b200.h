@@ -315,7 +315,8 @@ int lp_decode_set_mode(int mode);
  *     resize pasted centred on black), divide_to_patches (:143-162, row-major tiles), each tile through the same
  *     rescale / normalise (a 364 x 364 tile is not resized again).
  *   The resize is Pillow's ImagingResample (bicubic, a = -0.5, horizontal pass first, uint8 intermediate, 22-bit fixed
- *   point taps): results are bit-identical to Pillow + the PIL-backed SiglipImageProcessor.  Outputs are fp32
+ *   point taps; vertical pass first for images more than 100x taller than wide that shrink vertically, as Pillow >= 11
+ *   does): results are bit-identical to Pillow 12.2 + the PIL-backed SiglipImageProcessor.  Outputs are fp32
  *   (out_fp32 = 1, the reference's pixel_values dtype) or bf16 (what the patch-embedding GEMM consumes).
  *   rescale = 1/255, mean = std = {0.5, 0.5, 0.5} for SigLIP (HOST pointers).
  *   The target resolution comes from the host planner (allocate_patches / select_best_resolution, EV :26-99). */

@@ -181,6 +181,33 @@ resample_v_kernel(const uint8_t* __restrict__ tmp, long long pitch, int w, int h
   }
 }
 
+// vertical pass with a uint8 result (no normalisation / tiling): used when the vertical pass has to run FIRST.
+// tmp [h_in, w*3 bytes] (pitch multiple of 16) -> out [h_out, w*3 bytes] with the same pitch.
+__global__ void __launch_bounds__(256)
+resample_v_raw_kernel(const uint8_t* __restrict__ tmp, long long pitch, int w, int h_out, const int2* __restrict__ bounds,
+                      const int* __restrict__ coeffs, uint8_t* __restrict__ out) {
+  const int oy = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 4 >= w * 3) return;
+  const int2 b = bounds[oy];
+  int acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = 1 << (FE_PRECISION_BITS - 1);
+  const uint8_t* p = tmp + (long long)b.x * pitch + (long long)g * 4;
+  for (int t = 0; t < b.y; ++t) {
+    const int k = coeffs[(long long)t * h_out + oy];
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    acc[0] += (int)(v & 255u) * k;
+    acc[1] += (int)((v >> 8) & 255u) * k;
+    acc[2] += (int)((v >> 16) & 255u) * k;
+    acc[3] += (int)(v >> 24) * k;
+    p += pitch;
+  }
+  const uint32_t r = (uint32_t)fe_clip8(acc[0]) | ((uint32_t)fe_clip8(acc[1]) << 8) | ((uint32_t)fe_clip8(acc[2]) << 16) |
+                     ((uint32_t)fe_clip8(acc[3]) << 24);
+  *reinterpret_cast<uint32_t*>(out + (long long)oy * pitch + (long long)g * 4) = r;
+}
+
 // canvas pixels outside the pasted rectangle get the normalised value of black
 template <typename OutT>
 __global__ void __launch_bounds__(256)
@@ -205,11 +232,21 @@ static int fe_ksize(int in_size, int out_size) {
 
 static size_t fe_align(size_t n) { return (n + 255) & ~size_t(255); }
 
-// workspace for one resize (w_in, h_in) -> (w_out, h_out): intermediate + two coefficient tables
+// Pillow >= 11 resamples vertically FIRST when the image is more than 100x taller than wide and shrinks vertically
+// (Image.resize, Python side); the order is observable because the intermediate is rounded to uint8
+static bool fe_vertical_first(int w_in, int h_in, int h_out) { return (long long)h_in > 100LL * w_in && h_out < h_in; }
+
+// workspace for one resize (w_in, h_in) -> (w_out, h_out): intermediate(s) + coefficient tables
 static size_t fe_resize_ws(int w_in, int h_in, int w_out, int h_out) {
   const size_t pitch = ((size_t)w_out * 3 + 15) & ~size_t(15);
-  return fe_align(pitch * h_in) + fe_align((size_t)w_out * 8) + fe_align((size_t)w_out * fe_ksize(w_in, w_out) * 4) +
-         fe_align((size_t)h_out * 8) + fe_align((size_t)h_out * fe_ksize(h_in, h_out) * 4);
+  size_t n = fe_align(pitch * h_in) + fe_align((size_t)w_out * 8) + fe_align((size_t)w_out * fe_ksize(w_in, w_out) * 4) +
+             fe_align((size_t)h_out * 8) + fe_align((size_t)h_out * fe_ksize(h_in, h_out) * 4);
+  if (fe_vertical_first(w_in, h_in, h_out)) {  // + pitched copy of the source, vertical result, identity tables
+    const size_t p0 = ((size_t)w_in * 3 + 15) & ~size_t(15);
+    n += fe_align(p0 * h_in) + fe_align(p0 * h_out) + fe_align(pitch * h_out) + fe_align((size_t)w_in * 12) +
+         fe_align((size_t)h_out * 12);
+  }
+  return n;
 }
 
 template <typename OutT>
@@ -219,6 +256,48 @@ static int fe_resize_into(const uint8_t* rgb, int H, int W, int w_out, int h_out
   LP_REQUIRE(kx <= FE_MAX_KSIZE && ky <= FE_MAX_KSIZE, "lp_image_frontend: downscale factor above 32 (%dx%d -> %dx%d)",
              W, H, w_out, h_out);
   const size_t pitch = ((size_t)w_out * 3 + 15) & ~size_t(15);
+  if (fe_vertical_first(W, H, h_out)) {
+    // rare order (aspect > 100): pitched copy of the source (identity horizontal pass) -> vertical pass to uint8 ->
+    // horizontal pass -> identity vertical pass whose store applies normalisation / tiling.  Identity passes are exact.
+    const size_t p0 = ((size_t)W * 3 + 15) & ~size_t(15);
+    uint8_t* t0 = ws; ws += fe_align(p0 * H);
+    uint8_t* t1 = ws; ws += fe_align(p0 * h_out);
+    uint8_t* t2 = ws; ws += fe_align(pitch * h_out);
+    int2* bxi = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)W * 8);
+    int* cxi = reinterpret_cast<int*>(ws); ws += fe_align((size_t)W * 4);
+    int2* byi = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)h_out * 8);
+    int* cyi = reinterpret_cast<int*>(ws); ws += fe_align((size_t)h_out * 4);
+    int2* bx = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)w_out * 8);
+    int* cxs = reinterpret_cast<int*>(ws); ws += fe_align((size_t)w_out * kx * 4);
+    int2* by = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)h_out * 8);
+    int* cys = reinterpret_cast<int*>(ws);
+    resample_coeff_kernel<<<(W + 127) / 128, 128, 0, stream>>>(W, W, 1, 1, bxi, cxi);
+    resample_coeff_kernel<<<(h_out + 127) / 128, 128, 0, stream>>>(h_out, h_out, 1, 1, byi, cyi);
+    resample_coeff_kernel<<<(w_out + 127) / 128, 128, 0, stream>>>(W, w_out, kx, W == w_out, bx, cxs);
+    resample_coeff_kernel<<<(h_out + 127) / 128, 128, 0, stream>>>(H, h_out, ky, 0, by, cys);
+    const size_t smem = 2 * p0 + pitch + 64;
+    LP_REQUIRE(smem <= 48 * 1024, "lp_image_frontend: image row too wide for the vertical-first path (W=%d)", W);
+    resample_h_kernel<<<H, 256, smem, stream>>>(rgb, (long long)W * 3, (long long)H * W * 3, W, t0, (long long)p0, W, bxi,
+                                                cxi);
+    const int g0 = (W * 3 + 3) / 4;
+    resample_v_raw_kernel<<<dim3((g0 + 255) / 256, h_out), 256, 0, stream>>>(t0, (long long)p0, W, h_out, by, cys, t1);
+    resample_h_kernel<<<h_out, 256, smem, stream>>>(t1, (long long)p0, (long long)p0 * h_out, W, t2, (long long)pitch,
+                                                    w_out, bx, cxs);
+    const int tiles_x1 = canvas_w / FE_CROP;
+    const long long tile_stride1 = 3LL * FE_CROP * FE_CROP;
+    if (w_out != canvas_w || h_out != canvas_h) {
+      pad_fill_kernel<OutT><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
+          canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x1, out, tile_stride1, lut.v[0][0], lut.v[1][0],
+          lut.v[2][0]);
+      note_launch();
+    }
+    const int g2 = (w_out * 3 + 3) / 4;
+    resample_v_kernel<OutT><<<dim3((g2 + 255) / 256, h_out), 256, 0, stream>>>(
+        t2, (long long)pitch, w_out, h_out, byi, cyi, paste_x, paste_y, tiles_x1, out, tile_stride1, lut);
+    note_launch(8);
+    LP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   uint8_t* tmp = ws; ws += fe_align(pitch * H);
   int2* bx = reinterpret_cast<int2*>(ws); ws += fe_align((size_t)w_out * 8);
   int* cxs = reinterpret_cast<int*>(ws); ws += fe_align((size_t)w_out * kx * 4);

@@ -29,8 +29,11 @@ def _as_uint8_hwc(img) -> torch.Tensor:
         t = img
     else:
         if hasattr(img, "convert"):          # PIL.Image: same conversion the reference applies at load (EV :385)
-            img = np.asarray(img.convert("RGB"))
-        t = torch.from_numpy(np.ascontiguousarray(img))
+            img = np.array(img.convert("RGB"))   # a writable copy (PIL exposes a read-only buffer)
+        img = np.ascontiguousarray(img)
+        if not img.flags.writeable:
+            img = img.copy()
+        t = torch.from_numpy(img)
     if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
         raise ValueError(f"image must be uint8 [H, W, 3], got {t.dtype} {tuple(t.shape)}")
     return t.contiguous()

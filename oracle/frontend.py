@@ -94,9 +94,17 @@ def _resample_axis0(img: np.ndarray, out_size: int) -> np.ndarray:
 
 def pil_resize_bicubic(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
     """`PIL.Image.fromarray(img).resize((out_w, out_h))` for an RGB uint8 array [H, W, 3] (default BICUBIC, no box,
-    no reducing_gap): horizontal pass first, then vertical, each skipped when that size is unchanged."""
+    no reducing_gap): horizontal pass first, then vertical, each skipped when that size is unchanged — except for
+    images more than 100x taller than wide (see below)."""
     h, w = img.shape[:2]
     cur = img
+    if h > w * 100 and out_h < h:
+        # Pillow >= 11 (Image.resize, Python side): very tall images that shrink vertically are resampled vertically
+        # FIRST at full width, then horizontally — observable in the result because of the uint8 intermediate
+        cur = _resample_axis0(cur, out_h)
+        if out_w != w:
+            cur = _resample_axis0(cur.transpose(1, 0, 2), out_w).transpose(1, 0, 2)
+        return np.ascontiguousarray(cur)
     if out_w != w:
         cur = _resample_axis0(cur.transpose(1, 0, 2), out_w).transpose(1, 0, 2)
     if out_h != h:

@@ -41,7 +41,8 @@ def test_oracle_matches_reference_executed_goldens(gold):
 
 @pytest.mark.parametrize("w,h,ow,oh", [(500, 700, 364, 364), (100, 80, 364, 364), (896, 1152, 728, 936),
                                        (37, 991, 364, 364), (300, 300, 301, 299), (364, 364, 364, 364),
-                                       (1000, 10, 10, 1000), (1277, 958, 617, 329)])
+                                       (1000, 10, 10, 1000), (1277, 958, 617, 329), (3, 2, 364, 364), (9, 2000, 364, 364),
+                                       (728, 364, 728, 364), (2200, 1700, 2184, 1688), (1, 1, 5, 7)])
 def test_resize_is_bit_identical_to_pillow(w, h, ow, oh):
     from PIL import Image
     rng = np.random.default_rng(w * 7 + h)

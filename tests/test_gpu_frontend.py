@@ -46,6 +46,7 @@ def test_golden_cases_bit_exact(fe):
     [(364, 364)], [(365, 363)],          # identity / near-identity passes
     [(5, 5)],                            # tiny image, pure upscaling
     [(3001, 700)],                       # odd widths: unaligned source rows, wide downscale
+    [(9, 2000)], [(5, 900), (41, 4101)],  # > 100x taller than wide: Pillow resamples vertically FIRST
 ])
 def test_random_images_bit_exact_full_sizes(fe, sizes):
     rng = np.random.default_rng(len(sizes) * 1000 + sizes[0][0])
