@@ -25,6 +25,8 @@ class PrefillEngine:
         self.w = weights
         self.device = weights.device
         self._ws = {}
+        self._decode_state = None   # device-resident greedy-loop state + captured CUDA graph (leopard_b200/decode.py)
+        self._decode_kv = None      # persistent KV-cache buffer of generate() (capacity grows in KV_GRANULE steps)
         _lib.lib()  # fail early and loudly when the extension is missing
 
     # ------------------------------------------------------------------ buffers
