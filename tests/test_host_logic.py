@@ -170,3 +170,23 @@ def test_from_pretrained_reads_hf_checkpoint_dir(tmp_path):
     from leopard_b200._lib import NativeError
     with pytest.raises(NativeError, match="CUDA"):
         m.to("cpu")
+
+
+def test_native_kv_cache_is_the_legacy_tuple_the_reference_indexes():
+    """`past_key_values[l][k|v]` must look like transformers' legacy cache — [1, kv_heads, S, head_dim] per layer, as
+    read at evaluations/models/llava_multiimg_siglip_anyres.py:294 — while staying a VIEW of the native buffer."""
+    import torch
+    from leopard_b200.hf import NativeKVCache
+    layers, cap, kvh, hd, S = 3, 16, 8, 128, 11
+    kv = torch.arange(layers * 2 * cap * kvh * hd, dtype=torch.float32).view(layers, 2, cap, kvh * hd)
+    pkv = NativeKVCache(kv, S, kvh, hd)
+    assert isinstance(pkv, tuple) and len(pkv) == layers and pkv.length == S and pkv.get_seq_length() == S
+    k0, v0 = pkv[0]
+    assert k0.shape == (1, kvh, S, hd) and v0.shape == (1, kvh, S, hd)
+    assert pkv[0][0][:, :, :, 0].shape == (1, kvh, S)            # the reference's mask probe
+    # element (head h, row s, dim d) of layer l is kv[l, 0, s, h*hd + d]; and it is a view, not a copy
+    assert float(pkv[2][1][0, 5, 7, 9]) == float(kv[2, 1, 7, 5 * hd + 9])
+    kv[1, 0, 3, 2 * hd + 4] = -1.0
+    assert float(pkv[1][0][0, 2, 3, 4]) == -1.0
+    grown = NativeKVCache(kv, S + 1, kvh, hd)
+    assert grown[0][0].shape[2] == S + 1 and grown.kv.data_ptr() == pkv.kv.data_ptr()
