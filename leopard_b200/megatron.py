@@ -11,6 +11,7 @@ tiles + [global]; ids -100 (padding) read embedding row 0 (vlm_model.py:226); `i
 mismatch raises AssertionError with the reference's message (vlm_model.py:528-529).  The attention mask is ignored
 exactly like the flash-attention path of the reference (causal only).  Backward / optimizer (§8f-1) are not part of
 this round: forward(labels=...) returns the per-token loss [b, s] (lp_cross_entropy), backward is not available.
+Checkpoint surface: state_dict_for_save_checkpoint() / load_state_dict() speak the reference's nested Megatron layout.
 """
 from __future__ import annotations
 
@@ -21,12 +22,51 @@ import torch
 from . import _lib
 from .config import LeopardConfig, leopard_llava
 from .engine import PrefillEngine
-from .native_weights import NativeWeights, load_hf, megatron_to_hf
+from .native_weights import NativeWeights, hf_to_megatron, load_hf, megatron_to_hf
 
 IMAGE_TOKEN_INDEX = -200
 IGNORE_INDEX = -100
 
 _provider_state = {"cfg": None, "getter": None, "device": None}
+
+_LM_KEY = "language_model"   # GPTModel._language_model_key (megatron_patch/model/llava/gpt_model.py:115-123)
+
+
+def nest_language_model_state(flat: dict) -> dict:
+    """Flat Megatron keys ('encoder.layers.0.mlp.dense_h_to_4h.weight', ...) -> the nested dict the reference saves under
+    state['model']['language_model'] (TransformerLanguageModel.state_dict_for_save_checkpoint,
+    megatron_patch/model/llava/vlm_model.py:684-711): one sub-dict per component with that component's own state_dict
+    keys — `embedding` is nested once more ({'word_embeddings': {'weight': ...}}, as Embedding saves itself), the SigLIP
+    tower's keys carry no 'vision_tower.' prefix (the converter re-adds it, hf2megatron_llava.py:1310-1315)."""
+    out: dict = {}
+    for k, v in flat.items():
+        top, rest = k.split(".", 1)
+        if top == "embedding":
+            mod, leaf = rest.split(".", 1)
+            out.setdefault(top, {}).setdefault(mod, {})[leaf] = v
+        else:
+            out.setdefault(top, {})[rest] = v
+    return out
+
+
+def flatten_language_model_state(state: dict) -> dict:
+    """Inverse of nest_language_model_state; accepts the full {'language_model': {...}} checkpoint entry, the inner
+    nested dict, or an already flat dict.  TransformerEngine `_extra_state` entries are dropped (vlm_model.py:729-731)."""
+    if _LM_KEY in state and isinstance(state[_LM_KEY], dict):
+        state = state[_LM_KEY]
+    flat: dict = {}
+
+    def walk(prefix, node):
+        for k, v in node.items():
+            name = f"{prefix}.{k}" if prefix else k
+            if isinstance(v, dict):
+                walk(name, v)
+            elif not name.endswith("_extra_state"):
+                flat[name] = v
+    walk("", state)
+    # older checkpoints: `final_layernorm` -> `final_norm`, '.attention.' -> '.self_attention.' (vlm_model.py:752-760)
+    return {k.replace("encoder.final_layernorm.", "encoder.final_norm.").replace(".attention.", ".self_attention.")
+            if k.startswith("encoder.") else k: v for k, v in flat.items()}
 
 
 def configure_provider(cfg: Optional[LeopardConfig] = None, hf_getter: Optional[Callable] = None,
@@ -44,12 +84,31 @@ def configure_provider(cfg: Optional[LeopardConfig] = None, hf_getter: Optional[
 class GPTModel:
     """Forward-only native stand-in for megatron_patch.model.llava.gpt_model.GPTModel."""
 
-    def __init__(self, cfg: LeopardConfig, native: NativeWeights, pre_process=True, post_process=True):
+    def __init__(self, cfg: LeopardConfig, native: NativeWeights, pre_process=True, post_process=True,
+                 hf_getter: Optional[Callable] = None):
         if not (pre_process and post_process):
             raise NotImplementedError("pipeline parallel stages are out of scope (the reference runs PP = 1)")
         self.cfg = cfg
         self.engine = PrefillEngine(cfg, native)
         self.input_tensor = None
+        self._hf_getter = hf_getter   # source tensors (HF layout) for state_dict_for_save_checkpoint
+
+    # ---- checkpoint surface (gpt_model.py:115-137, vlm_model.py:684-791); TP = 1
+    def state_dict_for_save_checkpoint(self, prefix="", keep_vars=False):
+        """{'language_model': {'embedding', 'vision_tower', 'mm_projector', 'encoder', 'output_layer'}} in Megatron's own
+        layouts (group-interleaved QKV, [gate; up], [head, (q,k,v), 72]) — what Megatron's checkpointing writes under
+        state['model'] and what hf2megatron_llava.py reads back."""
+        if self._hf_getter is None:
+            raise _lib.NativeError("this model was built from native weights only; no source tensors to export")
+        return {_LM_KEY: nest_language_model_state(hf_to_megatron(self.cfg, self._hf_getter))}
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Customized load like the reference's (accepts the nested checkpoint entry with or without the
+        'language_model' level): converts the Megatron layouts back and rebuilds the native weights on the device."""
+        hf = megatron_to_hf(self.cfg, flatten_language_model_state(state_dict))
+        device = self.engine.device
+        self._hf_getter = hf.__getitem__
+        self.engine = PrefillEngine(self.cfg, load_hf(self.cfg, self._hf_getter, device))
 
     def set_input_tensor(self, t):  # gpt_model.py:86-88
         self.input_tensor = t
@@ -99,7 +158,7 @@ def model_provider(pre_process=True, post_process=True):
         raise _lib.NativeError("model_provider(): call configure_provider(...) first (Megatron's args/checkpoint "
                                "plumbing is outside the hot path)")
     native = load_hf(st["cfg"], st["getter"], st["device"])
-    return GPTModel(st["cfg"], native, pre_process, post_process)
+    return GPTModel(st["cfg"], native, pre_process, post_process, hf_getter=st["getter"])
 
 
 # ----------------------------------------------------------------------------------------------------------------

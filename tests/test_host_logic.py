@@ -190,3 +190,36 @@ def test_native_kv_cache_is_the_legacy_tuple_the_reference_indexes():
     assert float(pkv[1][0][0, 2, 3, 4]) == -1.0
     grown = NativeKVCache(kv, S + 1, kvh, hd)
     assert grown[0][0].shape[2] == S + 1 and grown.kv.data_ptr() == pkv.kv.data_ptr()
+
+
+def test_megatron_checkpoint_nesting_round_trip():
+    """state_dict_for_save_checkpoint / load_state_dict plumbing of the Megatron shim (gpt_model.py:115-137,
+    vlm_model.py:684-791): flat Megatron keys <-> the nested dict saved under state['model']['language_model']."""
+    import torch
+    from dataclasses import replace
+    from leopard_b200.config import leopard_llava, reduced
+    from leopard_b200.megatron import flatten_language_model_state, nest_language_model_state
+    from leopard_b200.native_weights import hf_to_megatron, megatron_to_hf
+    from leopard_b200.weights import SyntheticCheckpoint
+    cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=1024)
+    ck = SyntheticCheckpoint(cfg, seed=5)
+    flat = hf_to_megatron(cfg, lambda n: ck[n])
+    nested = nest_language_model_state(flat)
+    assert set(nested) == {"embedding", "vision_tower", "mm_projector", "encoder", "output_layer"}
+    assert set(nested["embedding"]) == {"word_embeddings"} and "weight" in nested["embedding"]["word_embeddings"]
+    assert "conv1.weight" in nested["vision_tower"]                     # no 'vision_tower.' prefix inside (converter :1313)
+    assert "encoder.linear_fc2.bias" in nested["mm_projector"]          # converter reads exactly this key (:1091)
+    assert "layers.0.self_attention.query_key_value.weight" in nested["encoder"] and "weight" in nested["output_layer"]
+    # every spelling load_state_dict accepts flattens back to the same tensors
+    nested["vision_tower"]["transformer.layers.0.self_attention.linear_qkv._extra_state"] = torch.zeros(1)   # TE metadata
+    for form in ({"language_model": nested}, nested, dict(flat)):
+        back = flatten_language_model_state(form)
+        assert set(back) == set(flat) and all(torch.equal(back[k], flat[k]) for k in flat)
+    # legacy spellings (vlm_model.py:752-760)
+    legacy = {k.replace("final_norm", "final_layernorm").replace(".self_attention.", ".attention.")
+              if k.startswith("encoder.") else k: v for k, v in flat.items()}
+    assert set(flatten_language_model_state(legacy)) == set(flat)
+    hf = megatron_to_hf(cfg, flatten_language_model_state({"language_model": nested}))
+    for name in ("language_model.model.layers.0.self_attn.k_proj.weight", "multi_modal_projector.linear_2.bias",
+                 "vision_tower.vision_model.encoder.layers.0.self_attn.q_proj.weight"):
+        assert torch.equal(hf[name], ck[name])
