@@ -64,8 +64,9 @@ def flatten_language_model_state(state: dict) -> dict:
             elif not name.endswith("_extra_state"):
                 flat[name] = v
     walk("", state)
-    # older checkpoints: `final_layernorm` -> `final_norm`, '.attention.' -> '.self_attention.' (vlm_model.py:752-760)
-    return {k.replace("encoder.final_layernorm.", "encoder.final_norm.").replace(".attention.", ".self_attention.")
+    # older checkpoints: '.attention.' -> '.self_attention.' (vlm_model.py:752-760) and `layernorm` -> `norm` in every
+    # decoder component name (ParallelTransformer.load_state_dict, megatron_patch/model/llava/transformer.py:1862-1873)
+    return {k.replace("layernorm", "norm").replace(".attention.", ".self_attention.")
             if k.startswith("encoder.") else k: v for k, v in flat.items()}
 
 

@@ -216,8 +216,9 @@ def test_megatron_checkpoint_nesting_round_trip():
         back = flatten_language_model_state(form)
         assert set(back) == set(flat) and all(torch.equal(back[k], flat[k]) for k in flat)
     # legacy spellings (vlm_model.py:752-760)
-    legacy = {k.replace("final_norm", "final_layernorm").replace(".self_attention.", ".attention.")
+    legacy = {k.replace("_norm", "_layernorm").replace(".self_attention.", ".attention.")
               if k.startswith("encoder.") else k: v for k, v in flat.items()}
+    assert "encoder.layers.0.input_layernorm.weight" in legacy and "encoder.final_layernorm.weight" in legacy
     assert set(flatten_language_model_state(legacy)) == set(flat)
     hf = megatron_to_hf(cfg, flatten_language_model_state({"language_model": nested}))
     for name in ("language_model.model.layers.0.self_attn.k_proj.weight", "multi_modal_projector.linear_2.bias",
