@@ -4,8 +4,9 @@ with leopard_b200 under it — what a maintainer's script looks like after the s
 Reference lines                              here
   :373-375  from_pretrained / eval / to      hf.myLlavaForConditionalGeneration (same calls; synthetic weights with --synthetic)
   :385-405  PIL crop pipeline + processor    leopard_b200.frontend.ImageFrontend (GPU, bit-identical pixel_values)
-  :407-446  prompt with image placeholders   build_input_ids() below (the tokenizer is not available offline: the 195
-                                             placeholder id and the per-image crop counts are what the model consumes)
+  :407-446  prompt with image placeholders   leopard_b200.prompt.build_eval_prompt gives the exact prompt STRING; the
+                                             tokenizer is not available offline, so build_input_ids() below emits the ids
+                                             that string tokenises to around the images (195 placeholder id per crop)
   :448-454  llava.generate + slice           unchanged
 Run:  python examples/llava_eval_loop.py --synthetic --layers 2          (needs a B200; no CPU fallback)
 """

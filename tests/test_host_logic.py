@@ -224,3 +224,24 @@ def test_megatron_checkpoint_nesting_round_trip():
     for name in ("language_model.model.layers.0.self_attn.k_proj.weight", "multi_modal_projector.linear_2.bias",
                  "vision_tower.vision_model.encoder.layers.0.self_attn.q_proj.weight"):
         assert torch.equal(hf[name], ck[name])
+
+
+def test_eval_prompt_builder_matches_reference_executed_goldens():
+    """leopard_b200.prompt.build_eval_prompt == the reference's own lines 412-442 (executed by
+    tests/golden/gen_prompt_goldens.py), quirks and failure modes included."""
+    import json
+    from pathlib import Path
+    from leopard_b200.prompt import build_eval_prompt, get_instruction, image_placeholder
+    cases = json.loads((Path(__file__).resolve().parent / "golden" / "ref_prompts.json").read_text())
+    assert len(cases) >= 9
+    for c in cases:
+        instr = get_instruction(c["setting"], c["ques_type"])
+        if "raises" in c:
+            with pytest.raises(IndexError):
+                build_eval_prompt(c["question"], instr, c["image_num"], c["tiles"])
+            assert c["raises"] == "IndexError"
+        else:
+            assert build_eval_prompt(c["question"], instr, c["image_num"], c["tiles"]) == c["prompt"], c["question"]
+    # one placeholder per crop: a 4-image cfg3 request has 4 x (1 + 6) slots = 28 crops
+    p = build_eval_prompt(cases[0]["question"], "", 4, [6, 6, 6, 6])
+    assert p.count("<|reserved_special_token_195|>") == 28 and image_placeholder(2, 7) in p
