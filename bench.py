@@ -121,8 +121,9 @@ def make_workload(cfg):
 
 def workload_config(per_image, S, world, parallelism):
     return {"workload": "cfg3: LLaVA 4x(896x1152) -> adaptive allocation -> 28 crops, 92 prompt ids -> S=4796 merged "
-                        "rows, 1 request per GPU per step, last-token logits",
-            "crops_per_image": per_image, "S": S, "model": "SigLIP-SO400M/14-364 + Llama-3.1-8B (synthetic)",
+                        "rows, 1 request per GPU per step, last-token logits; SigLIP-SO400M/14-364 tower + projector + "
+                        "Llama-3.1-8B decoder at full size, synthetic weights",
+            "crops_per_image": per_image, "S": S,
             "l2_policy": "inputs larger than L2: 17 GB of weights stream from HBM every step (L2 = 126 MB)",
             "parallelism": parallelism}
 
