@@ -66,3 +66,68 @@ def build_eval_prompt(question: str, instruction: str, image_num: int,
             crops += num_patchs_per_images_real[k - 1]
         prompt = prompt.replace(DEFAULT_IMAGE_TOKEN, image_placeholder(k, crops), 1)
     return prompt.replace("\r\n\t\t\r\n\t\t", " ")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# training twin (Pai-Megatron-Patch/megatron_patch/data/llava/mm_pretrain_dataset.py:769-874, `preprocess_llama3`)
+# ----------------------------------------------------------------------------------------------------------------
+MEGATRON_IMAGE_TOKEN_INDEX = -200          # data/llava/constants.py:8; one per FEATURE ROW (169 per crop)
+TRAIN_IMAGE_SLOT = "<|reserved_special_token_250|>"
+_PROMPT_ROLES = ("玩家", "system", "策略", "领域知识", "长期记忆", "user")   # turns that carry no loss (:836)
+
+
+def train_image_placeholder(k: int, per_image_token: int, tiles, slot: str = TRAIN_IMAGE_SLOT) -> str:
+    """Placeholder text of image k in a training sample: the crops arrive as tiles + [global] (…:247-253), every crop
+    is `per_image_token` slot tokens, tile t is closed by the tag `<|reserved_special_token_{22+t}|>`, the global view
+    by `<|reserved_special_token_21|>` (:801-809).  `tiles` None = no any-res plan (one crop)."""
+    text = f"image {k}: {IMG_OPEN}"
+    if tiles is not None:
+        for t in range(tiles):
+            text += slot * per_image_token + f"<|reserved_special_token_{22 + t}|>"
+    return text + slot * per_image_token + IMG_CLOSE
+
+
+def build_train_sample(sources, tokenizer, num_image: int = 1, per_image_token: int = 576,
+                       num_patches_per_image: Sequence[int] = (), img_special_token: str = TRAIN_IMAGE_SLOT):
+    """Token ids / labels / loss weights / preference tags of one Llama-3 chat sample, as `preprocess_llama3` builds
+    them: `<image>` tags are stripped from each turn and their placeholders prepended to it (images numbered across
+    turns), missing tags are prepended to the first turn, a sample with MORE tags than images is dropped (None); every
+    slot token becomes -200; only assistant message bodies (incl. `<|eot_id|>`) carry weight 1 / preference 2.
+    `tokenizer(text, add_special_tokens=False).input_ids` and `.bos_token_id` are all that is used of the tokenizer.
+    Returns dict(input_ids, labels, weights, preferences) of [n_samples, L] tensors (torch.stack, like the reference)."""
+    import torch
+    role_of = {"human": "user", "gpt": "assistant"}
+    plans = list(num_patches_per_image)
+    slot_id = tokenizer(img_special_token, add_special_tokens=False).input_ids[0]
+    rows = {"input_ids": [], "labels": [], "weights": [], "preferences": []}
+    for turns in sources:
+        if "from" in sources[0] and turns[0]["from"] != "human":
+            turns = turns[1:]                                  # a leading non-human turn is skipped (:785-787)
+        text_of = lambda t: t["content"] if "content" in t else t["value"]  # noqa: E731
+        n_tags = sum(text_of(t).count(DEFAULT_IMAGE_TOKEN) for t in turns)
+        if num_image > n_tags:
+            turns[0]["content"] = DEFAULT_IMAGE_TOKEN * (num_image - n_tags) + turns[0]["content"]
+        elif num_image < n_tags:
+            return None
+        ids, weights, prefs = [tokenizer.bos_token_id], [0.0], [0]
+        k = 1
+        for t in turns:
+            role = role_of[t["from"]] if "from" in t else t["role"]
+            raw = t["value"] if "value" in t else t["content"]
+            prefix = ""
+            for _ in range(raw.count(DEFAULT_IMAGE_TOKEN)):
+                prefix += train_image_placeholder(k, per_image_token, plans[k - 1] if plans else None, img_special_token)
+                k += 1
+            body = prefix + raw.replace(DEFAULT_IMAGE_TOKEN, "")
+            head = tokenizer(f"<|start_header_id|>{role}<|end_header_id|>\n\n", add_special_tokens=False).input_ids
+            tail = tokenizer(f"{body}<|eot_id|>", add_special_tokens=False).input_ids
+            ids += head + tail
+            learn = role not in _PROMPT_ROLES
+            weights += [0.0] * len(head) + [1.0 if learn else 0.0] * len(tail)
+            prefs += [0] * len(head) + [2 if learn else 0] * len(tail)
+        rows["labels"].append(torch.tensor(ids, dtype=torch.long))       # labels keep the slot id (shifted later)
+        rows["input_ids"].append(torch.tensor([MEGATRON_IMAGE_TOKEN_INDEX if i == slot_id else i for i in ids],
+                                              dtype=torch.long))
+        rows["weights"].append(torch.tensor(weights, dtype=torch.float))
+        rows["preferences"].append(torch.tensor(prefs, dtype=torch.long))
+    return {name: torch.stack(v, dim=0) for name, v in rows.items()}

@@ -245,3 +245,39 @@ def test_eval_prompt_builder_matches_reference_executed_goldens():
     # one placeholder per crop: a 4-image cfg3 request has 4 x (1 + 6) slots = 28 crops
     p = build_eval_prompt(cases[0]["question"], "", 4, [6, 6, 6, 6])
     assert p.count("<|reserved_special_token_195|>") == 28 and image_placeholder(2, 7) in p
+
+
+def test_train_sample_builder_matches_reference_executed_goldens():
+    """leopard_b200.prompt.build_train_sample == the reference's preprocess_llama3 (executed unmodified by
+    tests/golden/gen_train_goldens.py with the toy tokenizer): placeholder layout tiles + [global] with tile tags,
+    -200 per feature row, loss weights only on assistant bodies, dropped / failing samples alike."""
+    import copy
+    import json
+    import sys
+    from pathlib import Path
+    G = Path(__file__).resolve().parent / "golden"
+    sys.path.insert(0, str(G))
+    from toy_tokenizer import ToyTokenizer
+    from leopard_b200.prompt import build_train_sample, train_image_placeholder
+    tok = ToyTokenizer()
+    cases = json.loads((G / "ref_train_samples.json").read_text())
+    assert len(cases) >= 6
+    for c in cases:
+        kw = dict(num_image=c["num_image"], per_image_token=c["per_image_token"],
+                  num_patches_per_image=c["num_patches_per_image"])
+        if "raises" in c:
+            with pytest.raises(Exception) as ei:
+                build_train_sample(copy.deepcopy(c["sources"]), tok, **kw)
+            assert type(ei.value).__name__ == c["raises"]
+            continue
+        got = build_train_sample(copy.deepcopy(c["sources"]), tok, **kw)
+        if c["result"] is None:
+            assert got is None
+            continue
+        assert set(got) == set(c["result"])
+        for k, v in c["result"].items():
+            assert got[k].tolist() == v, (k, c["sources"])
+    # 2 tiles + global, 3 slots per crop: <20> sss<22> sss<23> sss<21>
+    s = "<|reserved_special_token_250|>" * 3
+    assert train_image_placeholder(1, 3, 2) == (f"image 1: <|reserved_special_token_20|>{s}<|reserved_special_token_22|>"
+                                                f"{s}<|reserved_special_token_23|>{s}<|reserved_special_token_21|>")
