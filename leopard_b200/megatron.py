@@ -152,6 +152,26 @@ class GPTModel:
     __call__ = forward
 
 
+def loss_func(loss_mask: torch.Tensor, labels: torch.Tensor, output_tensor: torch.Tensor):
+    """Same signature and arithmetic as the script's `loss_func` (examples/llava/pretrain_megatron_llava.py:101-121, bound
+    with `partial(loss_func, loss_mask, labels)` in forward_step :160): logits of position t are scored against the
+    label at t + 1 (the shift happens HERE, not in get_batch), per-token cross entropy of the fp32 logits
+    (`lp_cross_entropy` replaces vocab_parallel_cross_entropy, TP = 1), weighted by `loss_mask[:, 1:]`, divided by the sum
+    of the weights.  Returns (loss, {'lm loss': loss}) — the data-parallel average of the logging copy is the caller's
+    (Megatron's) business.  Labels equal to the image slot id (-200) or to ignore ids never carry weight in the
+    reference's batches; negative labels score 0 here instead of indexing out of range."""
+    from . import ops
+    b, s, v = output_tensor.shape
+    logits = output_tensor[:, :-1, :].reshape(b * (s - 1), v)
+    if logits.dtype not in (torch.float32, torch.bfloat16):
+        logits = logits.float()
+    tgt = labels[:, 1:].reshape(-1).to(logits.device).clamp(min=-1)
+    w = loss_mask[:, 1:].reshape(-1).to(logits.device).float()
+    per_token = ops.cross_entropy(logits.contiguous(), tgt.contiguous())
+    loss = torch.sum(per_token.view(-1) * w) / w.sum()
+    return loss, {"lm loss": loss}
+
+
 def model_provider(pre_process=True, post_process=True):
     """Same signature as examples/llava/pretrain_megatron_llava.py:37-50."""
     st = _provider_state

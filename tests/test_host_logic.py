@@ -281,3 +281,37 @@ def test_train_sample_builder_matches_reference_executed_goldens():
     s = "<|reserved_special_token_250|>" * 3
     assert train_image_placeholder(1, 3, 2) == (f"image 1: <|reserved_special_token_20|>{s}<|reserved_special_token_22|>"
                                                 f"{s}<|reserved_special_token_23|>{s}<|reserved_special_token_21|>")
+
+
+def test_loss_func_matches_reference_executed_goldens(monkeypatch):
+    """megatron.loss_func: shift / weight / normalise arithmetic against the reference's own loss_func, executed by
+    tests/golden/gen_loss_goldens.py.  The per-token cross entropy is the native kernel on a GPU (parity: test_gpu_ops);
+    here it is swapped for a torch stand-in so that only the host arithmetic around it is under test."""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from leopard_b200 import megatron, ops
+
+    g = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("gen_loss_goldens", g / "gen_loss_goldens.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+
+    seen = {}
+
+    def ce(logits, labels):
+        seen["shape"] = tuple(logits.shape)
+        assert logits.is_contiguous() and labels.is_contiguous() and int(labels.min()) >= -1
+        x = logits.float()
+        keep = labels >= 0
+        picked = x.gather(-1, labels.clamp(min=0).unsqueeze(-1)).squeeze(-1)
+        return torch.where(keep, torch.logsumexp(x, -1) - picked, torch.zeros(()))   # negative label -> 0, like lp_cross_entropy
+
+    monkeypatch.setattr(ops, "cross_entropy", ce)
+    for rec in json.loads((g / "ref_loss.json").read_text()):
+        logits, labels, weights = gen.make_case(rec["seed"], rec["batch"], rec["seq"], rec["vocab"], rec["frac"])
+        loss, logged = megatron.loss_func(weights, labels, logits)
+        assert seen["shape"] == (rec["batch"] * (rec["seq"] - 1), rec["vocab"])
+        assert abs(float(loss) - rec["loss"]) <= 2e-6 * abs(rec["loss"]), (float(loss), rec["loss"])
+        assert float(logged["lm loss"]) == float(loss)
