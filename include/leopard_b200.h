@@ -326,6 +326,58 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
                       size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * SFT step (FIRST IMPLEMENTATION, specification = oracle/train.py): the HBM-bound half of the backward
+ * pass, the masked LM loss and the optimizer.  In the reference all of this is torch autograd + apex inside Megatron's
+ * train_step (Pai-Megatron-Patch/examples/llava/pretrain_megatron_llava.py:101-160,
+ * Megatron-LM-240424/megatron/core/optimizer/optimizer.py:300-370, clip_grads.py:103-141).  The dgrad / wgrad
+ * contractions run on lp_gemm_bf16 over operands re-laid out by lp_transpose_bf16 (it contracts the contiguous
+ * dimension): dX = gemm(dY, W^T), dW = gemm(dY^T, X^T) with fp32 output.
+ *
+ * lp_transpose_bf16: out[c, r] = in[r, c]; 4-byte aligned bases, even leading dimensions.
+ * lp_rmsnorm_bwd:    dx = r (dy g) - x r^3 mean(dy g x) (+ add, the residual branch's gradient; may be NULL; dx may
+ *                    alias add or dy), dgamma[D] = sum_rows dy x r (overwritten; fixed summation order).
+ * lp_swiglu_fwd/bwd: m = silu(g) u on the [M, 2F] output of the fused gate/up weight (32-column granules, see
+ *                    lp_gemm_bf16) and its gradient, written in the same interleaved layout.
+ * lp_gelu_bwd:       dz = dy gelu'(z), act = LP_ACT_GELU_TANH or LP_ACT_GELU_ERF (projector, :187-192).
+ * lp_colsum_bf16:    out[c] = sum_r dy[r, c] in fp32 (bias gradients).
+ * lp_ce_fwd_bwd:     loss_func :101-121 on rows already shifted by the caller: loss[r] = lse - logits[r, target[r]],
+ *                    dlogits[r] = (softmax - onehot) * weight[r] with weight = loss_mask / sum(loss_mask); weight-0 rows
+ *                    cost one zero-fill; columns V..Vp-1 (vocabulary padding) receive 0.
+ * lp_embed_bwd:      dE[id] += d[r] for ids >= 0; ids == image_id pass nothing (vlm_model.py:526-533 overwrites those
+ *                    rows); other negative ids feed row 0 (the forward's clamp, vlm_model.py:226).  fp32 atomics.
+ * lp_gather_rows_bf16: out[i] = in[idx[i]] — gradient of the image-feature scatter.
+ * lp_softmax_bwd:    attention backward over materialised score rows: P = softmax(scale * scores, causal),
+ *                    dS = scale * P * (dp - sum_j P dp); bf16 outputs, zeros beyond the causal limit.
+ * lp_sumsq_accum / lp_grad_norm_finish: global L2 norm over fp32 gradients (partial[] must be zeroed per step;
+ *                    lp_grad_norm_workspace_bytes() bytes) -> out2 = {norm, clip coefficient} in device memory.
+ * lp_adamw_step:     FusedAdam (adam_w_mode) on fp32 main params with the gradient scaled by out2[1]; also refreshes
+ *                    the bf16 model copy (p_bf16 may be NULL).  step counts from 1. */
+int lp_transpose_bf16(const void* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream);
+size_t lp_rmsnorm_bwd_workspace_bytes(int D);
+int lp_rmsnorm_bwd(const void* x, long long ldx, const float* gamma, const void* dy, long long lddy, const void* add,
+                   long long ldadd, void* dx, long long lddx, float* dgamma, int M, int D, float eps, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int lp_swiglu_fwd(const void* gu, long long ldgu, void* out, long long ldo, int M, int F, void* stream);
+int lp_swiglu_bwd(const void* gu, long long ldgu, const void* dm, long long lddm, void* dgu, long long lddgu, int M, int F,
+                  void* stream);
+int lp_gelu_bwd(const void* z, long long ldz, const void* dy, long long lddy, void* dz, long long lddz, int M, int N, int act,
+                void* stream);
+int lp_colsum_bf16(const void* dy, long long ld, int M, int N, float* out, void* stream);
+int lp_ce_fwd_bwd(const void* logits, int logits_fp32, long long ld, const long long* target, const float* weight, float* loss,
+                  void* dlogits, long long ldd, int rows, int V, int Vp, void* stream);
+int lp_embed_bwd(const void* d, long long ldd, const long long* ids, int S, long long image_id, float* dE, long long ldE, int D,
+                 void* stream);
+int lp_gather_rows_bf16(const void* in, long long ld_in, const int* idx, int n, int D, void* out, long long ld_out,
+                        void* stream);
+int lp_softmax_bwd(const float* scores, long long lds, const float* dp, long long lddp, void* P, long long ldp, void* dS,
+                   long long ldds, int Sq, int Sk, int causal, float scale, void* stream);
+size_t lp_grad_norm_workspace_bytes(void);
+int lp_sumsq_accum(const float* x, long long n, float* partial, void* stream);
+int lp_grad_norm_finish(const float* partial, float max_norm, float* out2, void* stream);
+int lp_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, const float* norm_and_clip, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Measurement hooks (used by bench.py only).
  * lp_launch_count: kernels this library has launched since load (the bench's "gpu_launches" claim).
  * lp_profile_enable(capacity > 0): from now on every lp_gemm_bf16 / lp_attention_fwd / norm / rope / merge launch is

@@ -98,6 +98,21 @@ _SIGS = {
     "lp_image_frontend_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lp_image_frontend": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
     "lp_decode_debug_stamps": (_i, [_vp]),
+    "lp_transpose_bf16": (_i, [_vp, _ll, _i, _i, _vp, _ll, _vp]),
+    "lp_rmsnorm_bwd_workspace_bytes": (_sz, [_i]),
+    "lp_rmsnorm_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i, _f, _vp, _sz, _vp]),
+    "lp_swiglu_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "lp_swiglu_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "lp_gelu_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "lp_colsum_bf16": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
+    "lp_ce_fwd_bwd": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "lp_embed_bwd": (_i, [_vp, _ll, _vp, _i, _ll, _vp, _ll, _i, _vp]),
+    "lp_gather_rows_bf16": (_i, [_vp, _ll, _vp, _i, _i, _vp, _ll, _vp]),
+    "lp_softmax_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "lp_grad_norm_workspace_bytes": (_sz, []),
+    "lp_sumsq_accum": (_i, [_vp, _ll, _vp, _vp]),
+    "lp_grad_norm_finish": (_i, [_vp, _f, _vp, _vp]),
+    "lp_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp]),
     "lp_launch_count": (_ll, []),
     "lp_profile_enable": (_i, [_i]),
     "lp_profile_read": (_i, [_vp, _i]),

@@ -51,6 +51,7 @@ class NativeWeights:
         self.cfg = cfg
         self.device = torch.device(device)
         self._keep = []          # every device tensor referenced by a struct
+        self.named = {}          # name -> device tensor, for the tensors the SFT step updates in place (train.py)
         self.embed = None        # [vocab, hidden] bf16
         self.vocab_padded = (cfg.dec.vocab + 7) // 8 * 8
         v, d = cfg.vit, cfg.dec
@@ -65,15 +66,19 @@ class NativeWeights:
         self.dec = _lib.DecWeights()
 
     # -- helpers
-    def _bf(self, t: torch.Tensor) -> torch.Tensor:
+    def _bf(self, t: torch.Tensor, name: str = None) -> torch.Tensor:
         t = t.to(device=self.device, dtype=torch.bfloat16).contiguous()
         self._keep.append(t)
+        if name is not None:
+            self.named[name] = t
         return t
 
-    def _f32(self, t: torch.Tensor) -> torch.Tensor:
+    def _f32(self, t: torch.Tensor, name: str = None) -> torch.Tensor:
         # vectors are kept as fp32 holding the checkpoint's (bf16-rounded) values
         t = t.to(device=self.device).to(torch.bfloat16).float().contiguous()
         self._keep.append(t)
+        if name is not None:
+            self.named[name] = t
         return t
 
     @staticmethod
@@ -129,36 +134,37 @@ def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda
 
     # ---- projector (Leopard-LLaVA only; Idefics2 has its own connector, see idefics2.py)
     if with_projector:
-        nw.proj.w1 = nw._p(nw._bf(get(P + "linear_1.weight")))
-        nw.proj.b1 = nw._p(nw._f32(get(P + "linear_1.bias")))
-        nw.proj.w2 = nw._p(nw._bf(get(P + "linear_2.weight")))
-        nw.proj.b2 = nw._p(nw._f32(get(P + "linear_2.bias")))
+        nw.proj.w1 = nw._p(nw._bf(get(P + "linear_1.weight"), "proj.w1"))
+        nw.proj.b1 = nw._p(nw._f32(get(P + "linear_1.bias"), "proj.b1"))
+        nw.proj.w2 = nw._p(nw._bf(get(P + "linear_2.weight"), "proj.w2"))
+        nw.proj.b2 = nw._p(nw._f32(get(P + "linear_2.bias"), "proj.b2"))
         nw.proj.act = _lib.ACT_GELU_ERF if cfg.projector_act == "gelu" else _lib.ACT_GELU_TANH
 
     # ---- decoder
-    nw.embed = nw._bf(get(LM + "embed_tokens.weight"))
+    nw.embed = nw._bf(get(LM + "embed_tokens.weight"), "embed")
     for i in range(d.layers):
         b = f"{LM}layers.{i}."
         L = nw.dec_layers[i]
-        L.ln1_g = nw._p(nw._f32(get(b + "input_layernorm.weight")))
-        L.ln2_g = nw._p(nw._f32(get(b + "post_attention_layernorm.weight")))
+        L.ln1_g = nw._p(nw._f32(get(b + "input_layernorm.weight"), f"dec.{i}.ln1_g"))
+        L.ln2_g = nw._p(nw._f32(get(b + "post_attention_layernorm.weight"), f"dec.{i}.ln2_g"))
         qkv = torch.cat([get(b + f"self_attn.{n}_proj.weight").to(dev) for n in "qkv"], 0)
-        L.qkv_w = nw._p(nw._bf(qkv))
+        L.qkv_w = nw._p(nw._bf(qkv, f"dec.{i}.qkv_w"))
         del qkv
-        L.o_w = nw._p(nw._bf(get(b + "self_attn.o_proj.weight")))
+        L.o_w = nw._p(nw._bf(get(b + "self_attn.o_proj.weight"), f"dec.{i}.o_w"))
         g = get(b + "mlp.gate_proj.weight").to(dev).reshape(d.ffn // 32, 1, 32, d.hidden)
         u = get(b + "mlp.up_proj.weight").to(dev).reshape(d.ffn // 32, 1, 32, d.hidden)
-        L.gateup_w = nw._p(nw._bf(torch.cat([g, u], 1).reshape(2 * d.ffn, d.hidden)))
+        L.gateup_w = nw._p(nw._bf(torch.cat([g, u], 1).reshape(2 * d.ffn, d.hidden), f"dec.{i}.gateup_w"))
         del g, u
-        L.down_w = nw._p(nw._bf(get(b + "mlp.down_proj.weight")))
+        L.down_w = nw._p(nw._bf(get(b + "mlp.down_proj.weight"), f"dec.{i}.down_w"))
     nw.dec.layers = C.cast(nw.dec_layers, C.POINTER(_lib.DecLayerWeights))
-    nw.dec.final_g = nw._p(nw._f32(get(LM + "norm.weight")))
+    nw.dec.final_g = nw._p(nw._f32(get(LM + "norm.weight"), "dec.final_g"))
     head = get("language_model.lm_head.weight").to(dev)
     if nw.vocab_padded != d.vocab:
         head = torch.nn.functional.pad(head, (0, 0, 0, nw.vocab_padded - d.vocab))
-    nw.dec.lm_head = nw._p(nw._bf(head))
+    nw.dec.lm_head = nw._p(nw._bf(head, "dec.lm_head"))
     inv = rope_inv_freq(d).to(dev).contiguous()
     nw._keep.append(inv)
+    nw.named["dec.inv_freq"] = inv
     nw.dec.inv_freq = nw._p(inv)
     return nw
 

@@ -170,3 +170,158 @@ def cross_entropy(logits, labels):
                                      _lib.ptr(labels), _lib.ptr(out), R, V, _lib.stream_ptr())
     _lib.check(rc, "lp_cross_entropy")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SFT step (lp_train.cu): backward of the glue ops, masked LM loss, optimizer.  Same rule: allocation and checks only.
+# ------------------------------------------------------------------------------------------------------------------
+def transpose(x, out=None):
+    """out[c, r] = x[r, c] for a bf16 matrix view (last dim contiguous, even leading dimension) (lp_transpose_bf16)."""
+    _chk_bf16(x, "x")
+    rows, cols = x.shape
+    if out is None:   # leading dimension padded to 8 elements (the GEMM's TMA maps need 16-byte row strides)
+        out = torch.empty((cols, -(-rows // 8) * 8), device=x.device, dtype=torch.bfloat16)[:, :rows]
+    rc = _lib.lib().lp_transpose_bf16(_lib.ptr(x), x.stride(0), rows, cols, _lib.ptr(out), out.stride(0), _lib.stream_ptr())
+    _lib.check(rc, "lp_transpose_bf16")
+    return out
+
+
+_rms_bwd_ws = {}
+
+
+def rmsnorm_bwd(x, gamma, dy, eps, dgamma, add=None, out=None):
+    """dx = rmsnorm'(x; gamma) dy (+ add); dgamma (fp32 [D]) is overwritten (lp_rmsnorm_bwd)."""
+    _chk_bf16(x, "x")
+    _chk_bf16(dy, "dy")
+    _chk_f32(gamma, "gamma")
+    _chk_f32(dgamma, "dgamma")
+    M, D = x.shape
+    L = _lib.lib()
+    ws = _rms_bwd_ws.get((x.device, D))
+    if ws is None:
+        ws = torch.empty(L.lp_rmsnorm_bwd_workspace_bytes(D), dtype=torch.uint8, device=x.device)
+        _rms_bwd_ws[(x.device, D)] = ws
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    rc = L.lp_rmsnorm_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(gamma), _lib.ptr(dy), dy.stride(0), _lib.ptr(add),
+                          add.stride(0) if add is not None else 0, _lib.ptr(out), out.stride(0), _lib.ptr(dgamma), M, D,
+                          float(eps), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "lp_rmsnorm_bwd")
+    return out
+
+
+def swiglu_fwd(gu, out=None):
+    """gu bf16 [M, 2F] in the fused weight's interleaved column order -> silu(gate) * up [M, F] (lp_swiglu_fwd)."""
+    _chk_bf16(gu, "gu")
+    M, F2 = gu.shape
+    if out is None:
+        out = torch.empty((M, F2 // 2), device=gu.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_swiglu_fwd(_lib.ptr(gu), gu.stride(0), _lib.ptr(out), out.stride(0), M, F2 // 2, _lib.stream_ptr())
+    _lib.check(rc, "lp_swiglu_fwd")
+    return out
+
+
+def swiglu_bwd(gu, dm, out=None):
+    """gradient w.r.t. gu (same interleaved layout) given dm [M, F] (lp_swiglu_bwd)."""
+    _chk_bf16(gu, "gu")
+    _chk_bf16(dm, "dm")
+    M, F2 = gu.shape
+    if out is None:
+        out = torch.empty((M, F2), device=gu.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_swiglu_bwd(_lib.ptr(gu), gu.stride(0), _lib.ptr(dm), dm.stride(0), _lib.ptr(out), out.stride(0), M,
+                                  F2 // 2, _lib.stream_ptr())
+    _lib.check(rc, "lp_swiglu_bwd")
+    return out
+
+
+def gelu_bwd(z, dy, act, out=None):
+    _chk_bf16(z, "z")
+    _chk_bf16(dy, "dy")
+    M, N = z.shape
+    if out is None:
+        out = torch.empty((M, N), device=z.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_gelu_bwd(_lib.ptr(z), z.stride(0), _lib.ptr(dy), dy.stride(0), _lib.ptr(out), out.stride(0), M, N,
+                                act, _lib.stream_ptr())
+    _lib.check(rc, "lp_gelu_bwd")
+    return out
+
+
+def colsum(dy, out):
+    """out[c] = sum_r dy[r, c] (fp32 [N], overwritten) (lp_colsum_bf16)."""
+    _chk_bf16(dy, "dy")
+    _chk_f32(out, "out")
+    M, N = dy.shape
+    rc = _lib.lib().lp_colsum_bf16(_lib.ptr(dy), dy.stride(0), M, N, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lp_colsum_bf16")
+    return out
+
+
+def ce_fwd_bwd(logits, target, weight, vocab):
+    """logits [R, Vp] (fp32 or bf16; columns >= vocab are padding), target int64 [R], weight fp32 [R] ->
+    (loss [R] fp32, dlogits bf16 [R, Vp]) (lp_ce_fwd_bwd)."""
+    R, Vp = logits.shape
+    loss = torch.empty((R,), device=logits.device, dtype=torch.float32)
+    d = torch.empty((R, Vp), device=logits.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_ce_fwd_bwd(_lib.ptr(logits), 1 if logits.dtype == torch.float32 else 0, logits.stride(0),
+                                  _lib.ptr(target), _lib.ptr(weight), _lib.ptr(loss), _lib.ptr(d), d.stride(0), R, vocab, Vp,
+                                  _lib.stream_ptr())
+    _lib.check(rc, "lp_ce_fwd_bwd")
+    return loss, d
+
+
+def embed_bwd(d, ids, image_id, dE):
+    """dE[id] += d[r] for text rows (lp_embed_bwd); dE fp32 [V, D] must hold the running gradient (zeroed per step)."""
+    _chk_bf16(d, "d")
+    rc = _lib.lib().lp_embed_bwd(_lib.ptr(d), d.stride(0), _lib.ptr(ids), ids.numel(), image_id, _lib.ptr(dE), dE.stride(0),
+                                 d.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "lp_embed_bwd")
+
+
+def gather_rows(x, idx):
+    """x bf16 [R, D], idx int32 [n] -> [n, D] (lp_gather_rows_bf16)."""
+    _chk_bf16(x, "x")
+    out = torch.empty((idx.numel(), x.shape[1]), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_gather_rows_bf16(_lib.ptr(x), x.stride(0), _lib.ptr(idx), idx.numel(), x.shape[1], _lib.ptr(out),
+                                        out.stride(0), _lib.stream_ptr())
+    _lib.check(rc, "lp_gather_rows_bf16")
+    return out
+
+
+def softmax_bwd(scores, dp, causal, scale, P=None, dS=None):
+    """scores, dp fp32 [Sq, Sk] -> (P, dS) bf16 [Sq, Sk] (lp_softmax_bwd)."""
+    Sq, Sk = scores.shape
+    if P is None:
+        P = torch.empty((Sq, Sk), device=scores.device, dtype=torch.bfloat16)
+    if dS is None:
+        dS = torch.empty((Sq, Sk), device=scores.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_softmax_bwd(_lib.ptr(scores), scores.stride(0), _lib.ptr(dp), dp.stride(0), _lib.ptr(P), P.stride(0),
+                                   _lib.ptr(dS), dS.stride(0), Sq, Sk, 1 if causal else 0, float(scale), _lib.stream_ptr())
+    _lib.check(rc, "lp_softmax_bwd")
+    return P, dS
+
+
+def grad_norm(flat_grads, max_norm, partial=None, out2=None):
+    """Global L2 norm of the fp32 tensors in `flat_grads` -> device tensor [norm, clip coefficient]."""
+    L = _lib.lib()
+    dev = flat_grads[0].device
+    if partial is None:
+        partial = torch.empty(L.lp_grad_norm_workspace_bytes() // 4, dtype=torch.float32, device=dev)
+    if out2 is None:
+        out2 = torch.empty(2, dtype=torch.float32, device=dev)
+    partial.zero_()
+    for g in flat_grads:
+        _chk_f32(g, "grad")
+        _lib.check(L.lp_sumsq_accum(_lib.ptr(g), g.numel(), _lib.ptr(partial), _lib.stream_ptr()), "lp_sumsq_accum")
+    _lib.check(L.lp_grad_norm_finish(_lib.ptr(partial), float(max_norm), _lib.ptr(out2), _lib.stream_ptr()),
+               "lp_grad_norm_finish")
+    return out2
+
+
+def adamw_step(p, g, m, v, p16, step, lr, beta1, beta2, eps, weight_decay, norm_and_clip):
+    """In-place FusedAdam (adam_w_mode) update of fp32 p / m / v from fp32 g; refreshes the bf16 copy p16 (or None)."""
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _chk_f32(t, n)
+    rc = _lib.lib().lp_adamw_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.ptr(p16), p.numel(), float(lr),
+                                  float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                  _lib.ptr(norm_and_clip), _lib.stream_ptr())
+    _lib.check(rc, "lp_adamw_step")

@@ -1,0 +1,377 @@
+"""SFT step on the native kernels — FIRST IMPLEMENTATION, not yet measured on a B200.
+
+What Megatron's `train_step` does for Pai-Megatron-Patch/examples/llava/pretrain_megatron_llava.py, sequenced on the host
+over C-ABI calls (allocation, shapes and ordering only; every contraction, reduction and update is a native kernel):
+
+  forward_step :124-160   ViT (frozen: --freeze-clip-vision-tower) -> pixel shuffle -> projector -> scatter into the token
+                          embeddings -> 32 decoder layers -> final norm -> fp32 logits            (same kernels as prefill)
+  loss_func    :101-121   lp_ce_fwd_bwd on rows shifted by one (weights = loss_mask / sum(loss_mask) / dp_world)
+  backward                layer by layer with full recompute from the saved layer inputs (--recompute-granularity full
+                          --recompute-method uniform --recompute-num-layers 1, run_pretrain_megatron_llava.sh:96-100):
+                          dgrad = lp_gemm_bf16(dY, W^T), wgrad = lp_gemm_bf16(dY^T, X^T) -> fp32 main grads
+                          (lp_transpose_bf16 supplies the re-laid-out operands), norm / SwiGLU / GELU / RoPE / merge
+                          backward in lp_train.cu; attention backward over materialised [T, T] score tiles per head
+                          (lp_softmax_bwd) — a flash-style tcgen05 backward replaces it next
+  reduce                  data-parallel all-reduce of the flat fp32 gradient buffer, one bucket per decoder layer issued
+                          as soon as that layer's backward is enqueued (NCCL on its own stream overlaps the next layer)
+  optimizer.step          clip_grads.py:103-141 (global L2 norm) + FusedAdam adam_w_mode on fp32 main params
+                          (optimizer.py:300-370), bf16 model weights refreshed in the same kernel
+
+Specification and checker: oracle/train.py (closed forms pinned to autograd; end-to-end step by autograd over the prefill
+oracle).  tools/gpu_check_train.py compares this module with it on a B200.  There is no CPU fallback.
+Not covered yet: vision-tower backward (the tower must stay frozen), gradient accumulation over micro-batches, TP > 1.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+
+ALIGN = 64  # fp32 elements: every tensor's slice of the flat buffers starts on a 256-byte boundary
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host helpers (pure; tested on the CPU)
+# ----------------------------------------------------------------------------------------------------------------
+def plan_flat(sizes: Sequence[Tuple[str, int]]) -> Tuple[Dict[str, Tuple[int, int]], int]:
+    """[(name, numel)] in bucket order -> ({name: (offset, numel)}, total) with ALIGN-element alignment."""
+    off, out = 0, {}
+    for name, n in sizes:
+        out[name] = (off, n)
+        off += -(-n // ALIGN) * ALIGN
+    return out, off
+
+
+def shifted_targets(labels: torch.Tensor, loss_mask: torch.Tensor, dp_world: int = 1):
+    """loss_func's shift (pretrain_megatron_llava.py:103-105) as per-row targets and weights for lp_ce_fwd_bwd:
+    row (b, t) scores labels[b, t + 1] with weight loss_mask[b, t + 1] / sum(loss_mask[:, 1:]) / dp_world; the last row of
+    every sequence has weight 0.  Returns (targets int64 [b * s], weights fp32 [b * s])."""
+    b, s = labels.shape
+    tgt = torch.full((b, s), -1, dtype=torch.long, device=labels.device)
+    tgt[:, :-1] = labels[:, 1:]
+    w = torch.zeros((b, s), dtype=torch.float32, device=labels.device)
+    w[:, :-1] = loss_mask[:, 1:].float()
+    w = w / (w.sum() * dp_world)
+    return tgt.reshape(-1).contiguous(), w.reshape(-1).contiguous()
+
+
+def layer_buckets(names: Sequence[str], layout: Dict[str, Tuple[int, int]], total: int) -> List[Tuple[int, int]]:
+    """Contiguous [start, end) ranges of the flat gradient buffer, one per name prefix ('dec.31', ..., 'proj', ...) in
+    the order the backward pass completes them (the order of `names`)."""
+    out: List[Tuple[str, int, int]] = []
+    for n in names:
+        key = ".".join(n.split(".")[:2]) if n.startswith("dec.") and n.split(".")[1].isdigit() else n.split(".")[0]
+        off, cnt = layout[n]
+        end = off + -(-cnt // ALIGN) * ALIGN
+        if out and out[-1][0] == key and out[-1][2] == off:
+            out[-1] = (key, out[-1][1], end)
+        else:
+            out.append((key, off, end))
+    assert out[-1][2] == total
+    return [(a, b) for _, a, b in out]
+
+
+def cosine_lr(it: int, lr: float, min_lr: float, warmup_iters: int, decay_iters: int) -> float:
+    """OptimizerParamScheduler.get_lr, 'cosine' (Megatron-LM-240424/megatron/training/optimizer_param_scheduler.py:79-126)."""
+    if warmup_iters > 0 and it <= warmup_iters:
+        return lr * it / warmup_iters
+    if it > decay_iters:
+        return min_lr
+    ratio = (it - warmup_iters) / (decay_iters - warmup_iters)
+    return min_lr + (lr - min_lr) * 0.5 * (math.cos(math.pi * ratio) + 1.0)
+
+
+def trainable_names(n_layers: int, freeze_llm: bool = False, with_projector: bool = True) -> List[str]:
+    """Names (NativeWeights.named) in the order their gradients are completed by the backward pass."""
+    names: List[str] = []
+    if not freeze_llm:
+        names += ["dec.lm_head", "dec.final_g"]
+        for i in reversed(range(n_layers)):
+            names += [f"dec.{i}.down_w", f"dec.{i}.gateup_w", f"dec.{i}.ln2_g", f"dec.{i}.o_w", f"dec.{i}.qkv_w",
+                      f"dec.{i}.ln1_g"]
+        names += ["embed"]
+    if with_projector:
+        names += ["proj.w2", "proj.b2", "proj.w1", "proj.b1"]
+    return names
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class SFTTrainer:
+    """`tr = SFTTrainer(engine, lr=1e-5); loss, grad_norm = tr.step(tokens, labels, loss_mask, images)`
+
+    tokens / labels / loss_mask: [b, s] in the Megatron convention of mm_collate_fn (one -200 per image feature row,
+    labels not shifted, loss_mask = the dataset's 'weights'); every sequence of the micro-batch has the same length s,
+    s % 8 == 0.  images: [N, 3, 364, 364] crops of the whole micro-batch in slot order."""
+
+    def __init__(self, engine, lr: float = 1e-5, min_lr: float = 0.0, warmup_iters: int = 0, decay_iters: int = 0,
+                 beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
+                 clip_grad: float = 1.0, freeze_llm: bool = False, process_group=None):
+        if not torch.cuda.is_available():
+            raise _lib.NativeError("leopard_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _lib.lib()
+        self.eng, self.cfg, self.w = engine, engine.cfg, engine.w
+        self.dev = engine.device
+        self.hp = dict(lr=lr, min_lr=min_lr, warmup=warmup_iters, decay=decay_iters, beta1=beta1, beta2=beta2, eps=eps,
+                       wd=weight_decay, clip=clip_grad)
+        self.freeze_llm = freeze_llm
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.iteration = 0
+        d = self.cfg.dec
+        self.names = trainable_names(d.layers, freeze_llm)
+        named = self.w.named
+        self.layout, total = plan_flat([(n, named[n].numel()) for n in self.names])
+        self.buckets = layer_buckets(self.names, self.layout, total)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.flat_grad = torch.zeros(total, **f32)
+        self.flat_m = torch.zeros(total, **f32)
+        self.flat_v = torch.zeros(total, **f32)
+        # fp32 main copies of the bf16 matrices; fp32 vectors (norm weights, biases) are their own main copy
+        mat = [n for n in self.names if named[n].dtype == torch.bfloat16]
+        self.master_layout, mtotal = plan_flat([(n, named[n].numel()) for n in mat])
+        self.flat_master = torch.empty(mtotal, **f32)
+        for n in mat:
+            self._view(self.flat_master, self.master_layout, n).copy_(named[n].float())
+        self._norm_ws = torch.empty(_lib.lib().lp_grad_norm_workspace_bytes() // 4, **f32)
+        self._norm_out = torch.zeros(2, **f32)
+        self.q_w = d.heads * d.head_dim
+        self.kv_w = d.kv_heads * d.head_dim
+        self.qkv_w = self.q_w + 2 * self.kv_w
+        self._scratch_g = None
+
+    # ------------------------------------------------------------------ views
+    def _view(self, flat: torch.Tensor, layout, name: str) -> torch.Tensor:
+        off, n = layout[name]
+        return flat[off:off + n].view(self.w.named[name].shape)
+
+    def grad(self, name: str) -> torch.Tensor:
+        return self._view(self.flat_grad, self.layout, name)
+
+    # ------------------------------------------------------------------ GEMM forms
+    @staticmethod
+    def _dgrad(dy: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
+        """dX[M, K] = dY[M, N] W[N, K]: the GEMM contracts contiguous dims, so it is fed W^T [K, N]."""
+        return ops.gemm(dy, ops.transpose(w), out=out)
+
+    def _wgrad(self, name: str, dy: torch.Tensor, x: torch.Tensor):
+        """grad[name][N, K] (fp32, overwritten) = dY^T[N, M] X[M, K], fed dY^T and X^T [K, M]; skipped when frozen."""
+        if name in self.layout:
+            ops.gemm(ops.transpose(dy), ops.transpose(x), out=self.grad(name))
+
+    def _dgamma(self, name: str) -> torch.Tensor:
+        """Where a norm's weight gradient goes: its slice of the flat buffer, or scratch when the weight is frozen."""
+        if name in self.layout:
+            return self.grad(name)
+        if self._scratch_g is None:
+            self._scratch_g = torch.empty(self.cfg.dec.hidden, dtype=torch.float32, device=self.dev)
+        return self._scratch_g
+
+    # ------------------------------------------------------------------ decoder layer
+    def _layer_weights(self, i: int):
+        n = self.w.named
+        return (n[f"dec.{i}.ln1_g"], n[f"dec.{i}.qkv_w"], n[f"dec.{i}.o_w"], n[f"dec.{i}.ln2_g"], n[f"dec.{i}.gateup_w"],
+                n[f"dec.{i}.down_w"])
+
+    def _attention(self, qkv: torch.Tensor, b: int, s: int) -> torch.Tensor:
+        d = self.cfg.dec
+        return ops.attention(qkv, b, s, d.heads, d.kv_heads, d.head_dim, d.head_dim, 0, self.q_w, self.q_w + self.kv_w,
+                             True, variant=self._attn_variant)
+
+    def _layer_forward(self, i: int, x: torch.Tensor, b: int, s: int, keep: bool):
+        """Same kernel sequence as lp_decoder_prefill's layer body (csrc/lp_model.cu), out of place.  keep = True returns
+        the intermediates the backward needs."""
+        d = self.cfg.dec
+        ln1, wqkv, wo, ln2, wgu, wd = self._layer_weights(i)
+        h1 = ops.rmsnorm(x, ln1, d.eps)
+        qkv = ops.gemm(h1, wqkv)
+        ops.rope_inplace(qkv, 0, d.heads + d.kv_heads, d.head_dim, self._cos, self._sin)
+        att = self._attention(qkv, b, s)
+        x2 = ops.gemm(att, wo, residual=x)
+        h2 = ops.rmsnorm(x2, ln2, d.eps)
+        if not keep:
+            m = ops.gemm(h2, wgu, act=ops.ACT_SWIGLU)
+            return ops.gemm(m, wd, residual=x2)
+        gu = ops.gemm(h2, wgu)
+        m = ops.swiglu_fwd(gu)
+        return h1, qkv, att, x2, h2, gu, m
+
+    def _attention_backward(self, qkv: torch.Tensor, datt: torch.Tensor, b: int, s: int) -> torch.Tensor:
+        """dqkv [R, qkv_w] from datt [R, hidden]: per sequence and kv group, score tiles materialised per q head.
+        dQ_h = dS_h K_g;  dK_g = sum_h dS_h^T Q_h;  dV_g = sum_h P_h^T dO_h (the sums run inside one GEMM over the
+        concatenated contraction dimension)."""
+        d = self.cfg.dec
+        hd, rep = d.head_dim, d.heads // d.kv_heads
+        scale = hd ** -0.5
+        dqkv = torch.empty_like(qkv)
+        bf = dict(dtype=torch.bfloat16, device=self.dev)
+        sc = torch.empty((s, s), dtype=torch.float32, device=self.dev)
+        dp = torch.empty_like(sc)
+        P = torch.empty((s, s), **bf)
+        dS = torch.empty((s, s), **bf)
+        pt_cat = torch.empty((s, rep * s), **bf)
+        dst_cat = torch.empty((s, rep * s), **bf)
+        dot_cat = torch.empty((hd, rep * s), **bf)
+        qt_cat = torch.empty((hd, rep * s), **bf)
+        kt = torch.empty((hd, s), **bf)
+        for bi in range(b):
+            rows = slice(bi * s, (bi + 1) * s)
+            for g in range(d.kv_heads):
+                k_g = qkv[rows, self.q_w + g * hd: self.q_w + (g + 1) * hd]
+                v_g = qkv[rows, self.q_w + self.kv_w + g * hd: self.q_w + self.kv_w + (g + 1) * hd]
+                ops.transpose(k_g, out=kt)
+                for j in range(rep):
+                    h = g * rep + j
+                    q_h = qkv[rows, h * hd:(h + 1) * hd]
+                    do_h = datt[rows, h * hd:(h + 1) * hd]
+                    ops.gemm(q_h, k_g, out=sc, out_fp32=True)
+                    ops.gemm(do_h, v_g, out=dp, out_fp32=True)
+                    ops.softmax_bwd(sc, dp, True, scale, P=P, dS=dS)
+                    ops.gemm(dS, kt, out=dqkv[rows, h * hd:(h + 1) * hd])
+                    ops.transpose(P, out=pt_cat[:, j * s:(j + 1) * s])
+                    ops.transpose(dS, out=dst_cat[:, j * s:(j + 1) * s])
+                    ops.transpose(do_h, out=dot_cat[:, j * s:(j + 1) * s])
+                    ops.transpose(q_h, out=qt_cat[:, j * s:(j + 1) * s])
+                ops.gemm(dst_cat, qt_cat, out=dqkv[rows, self.q_w + g * hd: self.q_w + (g + 1) * hd])
+                ops.gemm(pt_cat, dot_cat,
+                         out=dqkv[rows, self.q_w + self.kv_w + g * hd: self.q_w + self.kv_w + (g + 1) * hd])
+        return dqkv
+
+    def _layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, b: int, s: int) -> torch.Tensor:
+        d = self.cfg.dec
+        ln1, wqkv, wo, ln2, wgu, wd = self._layer_weights(i)
+        h1, qkv, att, x2, h2, gu, m = self._layer_forward(i, x, b, s, keep=True)
+        # MLP
+        self._wgrad(f"dec.{i}.down_w", dy, m)
+        dm = self._dgrad(dy, wd)
+        del m
+        dgu = ops.swiglu_bwd(gu, dm)
+        del gu, dm
+        self._wgrad(f"dec.{i}.gateup_w", dgu, h2)
+        dh2 = self._dgrad(dgu, wgu)
+        del dgu, h2
+        dx2 = ops.rmsnorm_bwd(x2, ln2, dh2, d.eps, self._dgamma(f"dec.{i}.ln2_g"), add=dy)
+        del dh2, x2
+        # attention
+        self._wgrad(f"dec.{i}.o_w", dx2, att)
+        datt = self._dgrad(dx2, wo)
+        del att
+        dqkv = self._attention_backward(qkv, datt, b, s)
+        del datt, qkv
+        ops.rope_inplace(dqkv, 0, d.heads + d.kv_heads, d.head_dim, self._cos, self._neg_sin)   # adjoint rotation
+        self._wgrad(f"dec.{i}.qkv_w", dqkv, h1)
+        dh1 = self._dgrad(dqkv, wqkv)
+        del dqkv, h1
+        return ops.rmsnorm_bwd(x, ln1, dh1, d.eps, self._dgamma(f"dec.{i}.ln1_g"), add=dx2)
+
+    # ------------------------------------------------------------------ gradient reduction
+    def _reduce_bucket(self, k: int, handles: list):
+        if self.world > 1:
+            a, e = self.buckets[k]
+            handles.append(torch.distributed.all_reduce(self.flat_grad[a:e], group=self.pg, async_op=True))
+
+    # ------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step(self, tokens: torch.Tensor, labels: torch.Tensor, loss_mask: torch.Tensor, images: Optional[torch.Tensor]):
+        """One iteration.  Returns (loss, grad_norm) as Python floats (one device -> host read at the end)."""
+        cfg, d, w = self.cfg, self.cfg.dec, self.w.named
+        L = _lib.lib()
+        self._attn_variant = 80
+        b, s = tokens.shape
+        if s % 8:
+            raise ValueError(f"sequence length {s} must be a multiple of 8")
+        R = b * s
+        ids = tokens.reshape(-1).to(self.dev, torch.long).contiguous()
+        self.iteration += 1
+        self.flat_grad.zero_()
+        handles: list = []
+
+        # ---- vision tower (frozen) + projector, keeping what the projector's backward needs
+        n_img_rows = int((ids == cfg.megatron_image_index).sum())
+        have_images = images is not None and images.shape[-1] > 100 and n_img_rows > 0
+        feats = shuf = z1 = a1 = None
+        if have_images:
+            shuf = self.eng.vit(images, shuffle=True)
+            z1 = ops.gemm(shuf, w["proj.w1"], bias=w["proj.b1"])
+            a1 = ops.gemm(shuf, w["proj.w1"], bias=w["proj.b1"], act=self.w.proj.act)
+            feats = ops.gemm(a1, w["proj.w2"], bias=w["proj.b2"])
+            if feats.shape[0] != n_img_rows:
+                raise AssertionError("The number of image features doesn't match the number of image tokens. "
+                                     f"{feats.shape[0]} != {n_img_rows}")
+        # ---- scatter into the embeddings (vlm_model.py:516-533), all sequences packed [R, hidden]
+        x = torch.empty((R, d.hidden), dtype=torch.bfloat16, device=self.dev)
+        self.eng.merge(ids, feats, cfg.megatron_image_index, 1, out=x)
+        pos = torch.arange(s, dtype=torch.int32, device=self.dev).repeat(b)
+        self._cos, self._sin = ops.rope_table(pos, w["dec.inv_freq"])
+        self._neg_sin = -self._sin
+
+        # ---- decoder forward, layer inputs kept for the recompute
+        xs = []
+        for i in range(d.layers):
+            xs.append(x)
+            x = self._layer_forward(i, x, b, s, keep=False)
+        hN = ops.rmsnorm(x, w["dec.final_g"], d.eps)
+        logits = ops.gemm(hN, w["dec.lm_head"], out_fp32=True)                    # [R, vocab_padded] fp32
+
+        # ---- loss and its gradient
+        tgt, wt = shifted_targets(labels.to(self.dev), loss_mask.to(self.dev), self.world)
+        loss_rows, dlogits = ops.ce_fwd_bwd(logits, tgt, wt, d.vocab)
+        del logits
+        loss = torch.dot(loss_rows, wt) * self.world          # this rank's masked mean (the scalar that is reported)
+
+        # ---- backward (buckets of the flat gradient buffer are reduced in the order they complete)
+        self._wgrad("dec.lm_head", dlogits, hN)
+        dh = self._dgrad(dlogits, w["dec.lm_head"])
+        del dlogits
+        dx = ops.rmsnorm_bwd(x, w["dec.final_g"], dh, d.eps, self._dgamma("dec.final_g"))
+        del dh, hN
+        bucket = 0
+        if not self.freeze_llm:
+            self._reduce_bucket(bucket, handles)      # 'dec.lm_head' + 'dec.final_g'
+            bucket += 1
+        for i in reversed(range(d.layers)):
+            dx = self._layer_backward(i, xs.pop(), dx, b, s)
+            if not self.freeze_llm:
+                self._reduce_bucket(bucket, handles)
+                bucket += 1
+        # ---- merge backward: text rows feed the embedding table, image rows feed the projector
+        if not self.freeze_llm:
+            ops.embed_bwd(dx, ids, cfg.megatron_image_index, self.grad("embed"))
+            self._reduce_bucket(bucket, handles)
+            bucket += 1
+        if have_images:
+            idx = torch.nonzero(ids == cfg.megatron_image_index).reshape(-1).to(torch.int32)
+            dfe = ops.gather_rows(dx, idx)
+            self._wgrad("proj.w2", dfe, a1)
+            ops.colsum(dfe, self.grad("proj.b2"))
+            da1 = self._dgrad(dfe, w["proj.w2"])
+            dz1 = ops.gelu_bwd(z1, da1, self.w.proj.act)
+            self._wgrad("proj.w1", dz1, shuf)
+            ops.colsum(dz1, self.grad("proj.b1"))
+        self._reduce_bucket(bucket, handles)
+        assert bucket == len(self.buckets) - 1
+        for h in handles:
+            h.wait()
+
+        # ---- clip + AdamW
+        hp = self.hp
+        lr = hp["lr"] if hp["decay"] <= 0 else cosine_lr(self.iteration, hp["lr"], hp["min_lr"], hp["warmup"], hp["decay"])
+        ops.grad_norm([self.flat_grad], hp["clip"], self._norm_ws, self._norm_out)
+        for n in self.names:
+            model_t = w[n]
+            g = self.grad(n).reshape(-1)
+            m = self._view(self.flat_m, self.layout, n).reshape(-1)
+            v = self._view(self.flat_v, self.layout, n).reshape(-1)
+            if model_t.dtype == torch.bfloat16:
+                p = self._view(self.flat_master, self.master_layout, n).reshape(-1)
+                ops.adamw_step(p, g, m, v, model_t, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"], hp["wd"],
+                               self._norm_out)
+            else:
+                ops.adamw_step(model_t.reshape(-1), g, m, v, None, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"],
+                               hp["wd"], self._norm_out)
+        out = torch.cat([loss.reshape(1), self._norm_out[:1]]).tolist()
+        return out[0], out[1]

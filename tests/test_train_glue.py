@@ -1,0 +1,164 @@
+"""The SFT step's host sequencing (leopard_b200/train.py) executed on the CPU with every native op replaced by its
+contract restatement (oracle/native_ops.py), against autograd over the model oracle (oracle/train.py).
+
+This pins everything train.py decides — which operand is transposed, which column slice is which head, the interleaved
+gate/up layout, the loss shift and weights, where each gradient lands in the flat buffer, bucket order, the optimizer
+call — independently of the CUDA kernels, whose own parity is checked per kernel on the GPU (tools/gpu_check_train.py)."""
+import types
+
+import pytest
+import torch
+
+from leopard_b200 import train as T
+from leopard_b200.config import leopard_llava, reduced
+from leopard_b200.native_weights import load_hf
+from leopard_b200.weights import SyntheticCheckpoint
+from oracle import model as OM
+from oracle import native_ops
+from oracle import train as OT
+
+
+class _FakeEngine:
+    """The two PrefillEngine methods the trainer calls, restated on the CPU."""
+
+    def __init__(self, cfg, ck, nw):
+        self.cfg, self.ck, self.w, self.device = cfg, ck, nw, torch.device("cpu")
+
+    def vit(self, images, shuffle=True):
+        with torch.no_grad():
+            out = OM.pixel_shuffle(OM.vit_forward(self.ck, self.cfg, images.float()), self.cfg.shuffle)
+        return out.reshape(-1, out.shape[-1]).to(torch.bfloat16)
+
+    def merge(self, ids, feats, image_id, rows_per_slot, out=None):
+        emb = self.w.embed[ids.clamp(min=0)].clone()
+        slots = ids == image_id
+        if feats is not None:
+            emb[slots] = feats
+        out.copy_(emb)
+        return out, int(slots.sum())
+
+
+@pytest.fixture()
+def cpu_trainer(monkeypatch):
+    cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=2, vocab=324)     # 324 -> padded to 328: padding rows exist
+    ck = SyntheticCheckpoint(cfg, seed=11)
+    nw = load_hf(cfg, lambda n: ck[n], device="cpu")
+    monkeypatch.setattr(T, "ops", native_ops)
+    monkeypatch.setattr(T._lib, "lib", lambda: types.SimpleNamespace(lp_grad_norm_workspace_bytes=lambda: 4096))
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    return cfg, ck, nw, _FakeEngine(cfg, ck, nw)
+
+
+def _batch(cfg, b, n_text, seed):
+    g = torch.Generator().manual_seed(seed)
+    rows = cfg.tokens_per_crop
+    toks, labs, wts = [], [], []
+    for _ in range(b):
+        text = torch.randint(0, cfg.dec.vocab, (n_text,), generator=g)
+        t = torch.cat([text[:4], torch.full((rows,), cfg.megatron_image_index), text[4:]])
+        lab = t.clone()
+        lab[t < 0] = -100
+        w = torch.zeros(t.shape)
+        w[-6:] = 1.0
+        toks.append(t), labs.append(lab), wts.append(w)
+    images = torch.rand((b, 3, 364, 364), generator=g) * 2 - 1
+    return torch.stack(toks), torch.stack(labs), torch.stack(wts), images
+
+
+def _native_layout(cfg, grads, name):
+    """Oracle gradients (HF names) re-laid out like NativeWeights.named[name]."""
+    d = cfg.dec
+    LM, P = OM.LM, OM.P
+    if name == "embed":
+        return grads[LM + "embed_tokens.weight"]
+    if name == "dec.final_g":
+        return grads[LM + "norm.weight"]
+    if name == "dec.lm_head":
+        g = grads["language_model.lm_head.weight"]
+        return torch.nn.functional.pad(g, (0, 0, 0, (d.vocab + 7) // 8 * 8 - d.vocab))
+    if name.startswith("proj."):
+        return grads[P + {"w1": "linear_1.weight", "b1": "linear_1.bias", "w2": "linear_2.weight", "b2": "linear_2.bias"}[name[5:]]]
+    _, i, kind = name.split(".")
+    b = f"{LM}layers.{i}."
+    if kind == "qkv_w":
+        return torch.cat([grads[b + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0)
+    if kind == "gateup_w":
+        g = grads[b + "mlp.gate_proj.weight"].reshape(d.ffn // 32, 1, 32, d.hidden)
+        u = grads[b + "mlp.up_proj.weight"].reshape(d.ffn // 32, 1, 32, d.hidden)
+        return torch.cat([g, u], 1).reshape(2 * d.ffn, d.hidden)
+    return grads[b + {"o_w": "self_attn.o_proj.weight", "down_w": "mlp.down_proj.weight", "ln1_g": "input_layernorm.weight",
+                      "ln2_g": "post_attention_layernorm.weight"}[kind]]
+
+
+def test_sft_step_sequencing_matches_autograd_oracle(cpu_trainer):
+    cfg, ck, nw, eng = cpu_trainer
+    tokens, labels, weights, images = _batch(cfg, b=2, n_text=15, seed=3)        # s = 169 + 15 = 184 (multiple of 8)
+    ock = OT.TrainableCheckpoint(ck, trainable=lambda n: not n.startswith("vision_tower."))
+    ref_loss, ref = OT.sft_loss_and_grads(ock, cfg, tokens, labels, weights, images)
+    ref_norm = OT.global_grad_norm(ref.values())
+
+    before = {n: t.clone() for n, t in nw.named.items()}
+    tr = T.SFTTrainer(eng, lr=1e-5, clip_grad=1.0)
+    assert len(tr.buckets) == 1 + cfg.dec.layers + 2 and tr.buckets[-1][1] == tr.flat_grad.numel()
+    loss, norm = tr.step(tokens, labels, weights, images)
+
+    assert abs(loss - ref_loss) < 0.02 * abs(ref_loss), (loss, ref_loss)
+    assert abs(norm - ref_norm) < 0.03 * ref_norm, (norm, ref_norm)
+    worst = {}
+    for n in tr.names:
+        want, got = _native_layout(cfg, ref, n).float(), tr.grad(n).float()
+        assert want.shape == got.shape, n
+        worst[n] = float((got - want).norm() / (want.norm() + 1e-12))
+    bad = {n: e for n, e in worst.items() if e > 0.05}
+    assert not bad, bad
+    # vocabulary padding rows and unused embedding rows stay exactly zero, and so do their updates
+    assert float(tr.grad("dec.lm_head")[cfg.dec.vocab:].abs().max()) == 0.0
+    assert torch.equal(nw.named["dec.lm_head"][cfg.dec.vocab:], before["dec.lm_head"][cfg.dec.vocab:])
+    # the optimizer moved every trainable tensor, by about lr per element (first Adam step), in the descent direction
+    coeff = OT.clip_coefficient(ref_norm, 1.0)
+    for n in ("dec.1.o_w", "dec.0.ln1_g", "proj.b1", "dec.final_g"):
+        delta = nw.named[n].float() - before[n].float()
+        if nw.named[n].dtype == torch.float32:
+            g = _native_layout(cfg, ref, n) * coeff
+            big = g.abs() > 0.05 * g.abs().max()            # away from zero the bf16 noise cannot flip the sign
+            assert torch.allclose(delta[big], -1e-5 * torch.sign(g[big]), rtol=0.05, atol=0), n   # m / (sqrt(v) + eps)
+        else:
+            assert float(delta.abs().max()) > 0.0, n
+    # frozen tower: untouched
+    assert tr.iteration == 1 and not any(n.startswith("vit") for n in tr.names)
+
+
+def test_projector_only_stage_skips_decoder_gradients(cpu_trainer):
+    cfg, ck, nw, eng = cpu_trainer
+    tokens, labels, weights, images = _batch(cfg, b=1, n_text=15, seed=5)
+    ock = OT.TrainableCheckpoint(ck, trainable=lambda n: n.startswith("multi_modal_projector."))
+    ref_loss, ref = OT.sft_loss_and_grads(ock, cfg, tokens, labels, weights, images)
+    before = {n: t.clone() for n, t in nw.named.items()}
+    tr = T.SFTTrainer(eng, lr=1e-5, freeze_llm=True)
+    assert tr.names == ["proj.w2", "proj.b2", "proj.w1", "proj.b1"] and len(tr.buckets) == 1
+    loss, _ = tr.step(tokens, labels, weights, images)
+    assert abs(loss - ref_loss) < 0.02 * abs(ref_loss)
+    for n in tr.names:
+        want, got = _native_layout(cfg, ref, n).float(), tr.grad(n).float()
+        assert float((got - want).norm() / want.norm()) < 0.05, n
+    for n, t in nw.named.items():
+        if not n.startswith("proj."):
+            assert torch.equal(t, before[n]), n
+
+
+def test_shifted_targets_and_schedule_helpers():
+    labels = torch.tensor([[5, 6, 7, 8], [1, 2, 3, 4]])
+    mask = torch.tensor([[0.0, 0.0, 1.0, 1.0], [1.0, 0.0, 0.0, 1.0]])
+    tgt, w = T.shifted_targets(labels, mask, dp_world=2)
+    assert tgt.tolist() == [6, 7, 8, -1, 2, 3, 4, -1]
+    assert torch.allclose(w, torch.tensor([0, 1, 1, 0, 0, 0, 1, 0]) / 3 / 2)
+    # same loss as the oracle's loss_func restatement for random logits
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn((2, 4, 11), generator=g)
+    ref, dref = OT.masked_lm_loss(logits, labels, mask)
+    tgt, w = T.shifted_targets(labels, mask)
+    rows, d = native_ops.ce_fwd_bwd(logits.reshape(8, 11), tgt, w, 11)
+    assert abs(float(torch.dot(rows, w)) - float(ref)) < 1e-6
+    assert torch.allclose(d.float().view(2, 4, 11), dref, atol=4e-3)
+    assert T.cosine_lr(5, 1e-3, 1e-4, 10, 100) == OT.cosine_lr(5, 1e-3, 1e-4, 10, 100)
+    assert T.cosine_lr(60, 1e-3, 1e-4, 10, 100) == OT.cosine_lr(60, 1e-3, 1e-4, 10, 100)
