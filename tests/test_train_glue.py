@@ -162,3 +162,84 @@ def test_shifted_targets_and_schedule_helpers():
     assert torch.allclose(d.float().view(2, 4, 11), dref, atol=4e-3)
     assert T.cosine_lr(5, 1e-3, 1e-4, 10, 100) == OT.cosine_lr(5, 1e-3, 1e-4, 10, 100)
     assert T.cosine_lr(60, 1e-3, 1e-4, 10, 100) == OT.cosine_lr(60, 1e-3, 1e-4, 10, 100)
+
+
+# ---- data parallel: two gloo ranks, one micro-batch each, gradients averaged bucket by bucket ----------------------------
+def _text_batch(cfg, seed):
+    g = torch.Generator().manual_seed(seed)
+    tokens = torch.randint(0, cfg.dec.vocab, (1, 16), generator=g)
+    weights = torch.zeros(1, 16)
+    weights[0, 8 + seed % 3:] = 1.0            # ranks weight a different number of tokens
+    return tokens, tokens.clone(), weights
+
+
+def _fingerprint(tr, flat=None):
+    """Three numbers per trainable tensor (sum, sum of squares, projection on a fixed vector): small enough for a queue."""
+    flat = tr.flat_grad if flat is None else flat
+    out = []
+    for n in tr.names:
+        off, cnt = tr.layout[n]
+        g = flat[off:off + cnt].double()
+        out.append([float(g.sum()), float(g.pow(2).sum()), float(torch.dot(g, torch.cos(torch.arange(cnt, dtype=torch.float64) * 0.37)))])
+    return torch.tensor(out, dtype=torch.float64)
+
+
+def _patch_cpu():
+    T.ops = native_ops
+    T._lib.lib = lambda: types.SimpleNamespace(lp_grad_norm_workspace_bytes=lambda: 4096)
+    torch.cuda.is_available = lambda: True
+
+
+def _small_cpu_engine():
+    cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=320)
+    ck = SyntheticCheckpoint(cfg, seed=5)
+    nw = load_hf(cfg, lambda n: ck[n], device="cpu")
+    return cfg, _FakeEngine(cfg, ck, nw)
+
+
+def _dp_train_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _patch_cpu()
+        cfg, eng = _small_cpu_engine()
+        tr = T.SFTTrainer(eng, lr=1e-5, clip_grad=1.0)
+        assert tr.world == world
+        loss, norm = tr.step(*_text_batch(cfg, seed=rank), None)
+        q.put((rank, loss, norm, _fingerprint(tr), eng.w.named["dec.0.o_w"].float().sum().item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_step_averages_gradients_world2_gloo(cpu_trainer):
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, l0, n0, g0, w0), (_, l1, n1, g1, w1) = got
+    assert torch.equal(g0, g1) and n0 == n1 and w0 == w1          # ranks hold the same reduced gradient and stay in sync
+    assert l0 != l1                                               # each reports the loss of its own micro-batch
+    # single-rank gradients of the two micro-batches, averaged
+    singles = []
+    for seed in (0, 1):
+        cfg, eng = _small_cpu_engine()
+        tr = T.SFTTrainer(eng, lr=1e-5)
+        loss, _ = tr.step(*_text_batch(cfg, seed=seed), None)
+        assert abs(loss - (l0, l1)[seed]) < 1e-3 * abs(loss)
+        singles.append(tr.flat_grad.clone())
+    want = _fingerprint(tr, 0.5 * (singles[0] + singles[1]))
+    # sums and projections are linear in the gradient: they must match the average up to the bf16 noise of the
+    # pre-scaled loss weights; the square sums agree to the same order
+    scale = want[:, 1].sqrt()[:, None] + 1e-30
+    assert float(((g0[:, [0, 2]] - want[:, [0, 2]]) / scale).abs().max()) < 0.05
+    assert float(((g0[:, 1] - want[:, 1]) / (want[:, 1] + 1e-30)).abs().max()) < 0.05
