@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from .config import LeopardConfig, leopard_llava
 from .engine import PrefillEngine
-from .native_weights import NativeWeights, hf_to_megatron, load_hf, megatron_to_hf
+from .native_weights import NativeWeights, hf_to_megatron, load_hf, megatron_to_hf, named_to_hf
 
 IMAGE_TOKEN_INDEX = -200
 IGNORE_INDEX = -100
@@ -101,7 +101,16 @@ class GPTModel:
         state['model'] and what hf2megatron_llava.py reads back."""
         if self._hf_getter is None:
             raise _lib.NativeError("this model was built from native weights only; no source tensors to export")
-        return {_LM_KEY: nest_language_model_state(hf_to_megatron(self.cfg, self._hf_getter))}
+        # tensors the SFT step updates in place are read back from the device (kernel layout -> HF names); the frozen
+        # rest (vision tower) comes from the source checkpoint
+        live = named_to_hf(self.cfg, self.engine.w.named)
+        src = self._hf_getter
+
+        def get(name):
+            t = live.get(name)
+            return src(name) if t is None else t.detach().to("cpu", torch.bfloat16)
+
+        return {_LM_KEY: nest_language_model_state(hf_to_megatron(self.cfg, get))}
 
     def load_state_dict(self, state_dict, strict=True):
         """Customized load like the reference's (accepts the nested checkpoint entry with or without the
@@ -170,6 +179,46 @@ def loss_func(loss_mask: torch.Tensor, labels: torch.Tensor, output_tensor: torc
     per_token = ops.cross_entropy(logits.contiguous(), tgt.contiguous())
     loss = torch.sum(per_token.view(-1) * w) / w.sum()
     return loss, {"lm loss": loss}
+
+
+IGNORE_INDEX = -100
+
+
+def mm_collate_fn(batch):
+    """The script's collate function (pretrain_megatron_llava.py:163-191), same output dict: drops None samples (None for
+    an empty batch), right-pads input_ids / labels with IGNORE_INDEX and weights / preferences with 0 up to the longest
+    sample rounded UP to a multiple of 8, concatenates the per-sample crop tensors along dim 0, and substitutes the
+    `[1, 10]` bf16 dummy (the `images.shape[-1] > 100` sentinel of vlm_model.py:518) when no sample has an image."""
+    batch = [item for item in batch if item is not None]
+    if len(batch) == 0:
+        return None
+    max_len = -(-max(len(item["input_ids"]) for item in batch) // 8) * 8
+    n = len(batch)
+    out = {"input_ids": torch.full((n, max_len), IGNORE_INDEX, dtype=torch.long),
+           "labels": torch.full((n, max_len), IGNORE_INDEX, dtype=torch.long),
+           "weights": torch.zeros(n, max_len, dtype=torch.float),
+           "preferences": torch.zeros(n, max_len, dtype=torch.float)}
+    for i, item in enumerate(batch):
+        for key in ("input_ids", "labels", "weights", "preferences"):
+            out[key][i, : len(item[key])] = item[key]
+    images = [item["image"] for item in batch if "image" in item and item["image"] is not None]
+    out["image"] = torch.cat(images, dim=0) if images else torch.zeros(1, 10, dtype=torch.bfloat16)
+    return out
+
+
+def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_scheduler=None, config=None):
+    """Megatron's `train_step` (Megatron-LM-240424/megatron/training/training.py:544-607) for this path: same signature,
+    same return tuple (loss_reduced, skipped_iter, grad_norm, num_zeros_in_grad).  `optimizer` is a
+    leopard_b200.train.SFTTrainer built on `model[0].engine`: zero-grad, forward, loss_func, backward, the data-parallel
+    reduce, clipping and the Adam update all happen inside its `step`, on native kernels, so `forward_step_func` is not
+    called; the batch is read with get_batch's keys (:52-99): 'input_ids', 'labels', 'weights' (the loss mask), 'image'.
+    The learning-rate schedule lives in the trainer (cosine with warm-up, as the launch script configures)."""
+    data = next(data_iterator)
+    while data is None:                      # get_batch :59-62 skips empty collates
+        data = next(data_iterator)
+    loss, grad_norm = optimizer.step(data["input_ids"].long(), data["labels"].long(), data["weights"].float(),
+                                     data["image"])
+    return {"lm loss": loss}, 0, grad_norm, None
 
 
 def model_provider(pre_process=True, post_process=True):

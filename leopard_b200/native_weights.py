@@ -169,6 +169,40 @@ def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda
     return nw
 
 
+def named_to_hf(cfg: LeopardConfig, named: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Inverse of load_hf for the tensors the SFT step updates (NativeWeights.named): kernel layout -> HF-named tensors
+    (split the fused qkv rows, undo the 32-row gate/up interleave, drop the vocabulary padding).  Pure data movement;
+    returns views / reshapes of the live device tensors, so a checkpoint written from them holds the trained values."""
+    d = cfg.dec
+    out: Dict[str, torch.Tensor] = {}
+    q_w, kv_w = d.heads * d.head_dim, d.kv_heads * d.head_dim
+    for name, t in named.items():
+        if name == "embed":
+            out[LM + "embed_tokens.weight"] = t
+        elif name == "dec.final_g":
+            out[LM + "norm.weight"] = t
+        elif name == "dec.lm_head":
+            out["language_model.lm_head.weight"] = t[: d.vocab]
+        elif name.startswith("proj."):
+            out[P + {"w1": "linear_1.weight", "b1": "linear_1.bias", "w2": "linear_2.weight", "b2": "linear_2.bias"}[
+                name[5:]]] = t
+        elif name.startswith("dec.") and name.split(".")[1].isdigit():
+            _, i, kind = name.split(".")
+            b = f"{LM}layers.{i}."
+            if kind == "qkv_w":
+                out[b + "self_attn.q_proj.weight"] = t[:q_w]
+                out[b + "self_attn.k_proj.weight"] = t[q_w: q_w + kv_w]
+                out[b + "self_attn.v_proj.weight"] = t[q_w + kv_w:]
+            elif kind == "gateup_w":
+                g = t.reshape(d.ffn // 32, 2, 32, d.hidden)
+                out[b + "mlp.gate_proj.weight"] = g[:, 0].reshape(d.ffn, d.hidden)
+                out[b + "mlp.up_proj.weight"] = g[:, 1].reshape(d.ffn, d.hidden)
+            else:
+                out[b + {"o_w": "self_attn.o_proj.weight", "down_w": "mlp.down_proj.weight",
+                         "ln1_g": "input_layernorm.weight", "ln2_g": "post_attention_layernorm.weight"}[kind]] = t
+    return out
+
+
 def random_native(cfg: LeopardConfig, device="cuda", seed: int = 1234) -> NativeWeights:
     """Benchmark-only initialisation: same distributions as weights.synth_tensor but drawn ON the device (fast);
     values differ from the CPU-seeded checkpoint, so this is for throughput runs, never for parity."""

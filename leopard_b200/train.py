@@ -152,6 +152,36 @@ class SFTTrainer:
     def grad(self, name: str) -> torch.Tensor:
         return self._view(self.flat_grad, self.layout, name)
 
+    # ------------------------------------------------------------------ optimizer state (checkpoint / resume)
+    def state_dict(self) -> dict:
+        """What Megatron keeps under state['optimizer'] for this path: the step count, Adam moments and the fp32 main
+        params, per tensor name (kernel layout; model weights themselves are exported by the Megatron shim's
+        state_dict_for_save_checkpoint).  fp32 vectors are their own main copy and are saved as such."""
+        named = self.w.named
+        out = {"iteration": self.iteration, "hyper": dict(self.hp), "exp_avg": {}, "exp_avg_sq": {}, "main": {}}
+        for n in self.names:
+            out["exp_avg"][n] = self._view(self.flat_m, self.layout, n).detach().cpu().clone()
+            out["exp_avg_sq"][n] = self._view(self.flat_v, self.layout, n).detach().cpu().clone()
+            main = self._view(self.flat_master, self.master_layout, n) if n in self.master_layout else named[n]
+            out["main"][n] = main.detach().cpu().clone()
+        return out
+
+    def load_state_dict(self, sd: dict):
+        """Resume: restores step count, moments and main params, and refreshes the bf16 model weights from the latter."""
+        named = self.w.named
+        missing = [n for n in self.names if n not in sd["main"]]
+        if missing:
+            raise KeyError(f"optimizer state lacks {missing[:3]}{'...' if len(missing) > 3 else ''}")
+        self.iteration = int(sd["iteration"])
+        for n in self.names:
+            self._view(self.flat_m, self.layout, n).copy_(sd["exp_avg"][n])
+            self._view(self.flat_v, self.layout, n).copy_(sd["exp_avg_sq"][n])
+            if n in self.master_layout:
+                self._view(self.flat_master, self.master_layout, n).copy_(sd["main"][n])
+                named[n].copy_(sd["main"][n])          # fp32 -> bf16, round to nearest even like the update kernel
+            else:
+                named[n].copy_(sd["main"][n])
+
     # ------------------------------------------------------------------ GEMM forms
     @staticmethod
     def _dgrad(dy: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:

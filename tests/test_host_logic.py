@@ -315,3 +315,61 @@ def test_loss_func_matches_reference_executed_goldens(monkeypatch):
         assert seen["shape"] == (rec["batch"] * (rec["seq"] - 1), rec["vocab"])
         assert abs(float(loss) - rec["loss"]) <= 2e-6 * abs(rec["loss"]), (float(loss), rec["loss"])
         assert float(logged["lm loss"]) == float(loss)
+
+
+def test_named_to_hf_inverts_the_kernel_layout():
+    """Checkpoint export of the tensors the SFT step updates: kernel layout -> HF names is the exact inverse of load_hf."""
+    import torch
+    from leopard_b200.config import leopard_llava, reduced
+    from leopard_b200.native_weights import load_hf, named_to_hf
+    from leopard_b200.weights import SyntheticCheckpoint, tensor_specs
+    cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=2, vocab=324)       # padded vocabulary
+    ck = SyntheticCheckpoint(cfg, seed=9)
+    nw = load_hf(cfg, lambda n: ck[n], device="cpu")
+    back = named_to_hf(cfg, nw.named)
+    want = [n for n, _, _ in tensor_specs(cfg) if not n.startswith("vision_tower.")]
+    assert sorted(back) == sorted(want)
+    for n in want:
+        assert back[n].shape == ck[n].shape and torch.equal(back[n].to(torch.bfloat16), ck[n]), n
+    # an in-place update of a native tensor shows up in the export (views, not copies)
+    nw.named["dec.1.gateup_w"][40].fill_(3.0)          # granule 0, second half -> up_proj row 8
+    assert float(named_to_hf(cfg, nw.named)["language_model.model.layers.1.mlp.up_proj.weight"][8].min()) == 3.0
+
+
+def test_collate_and_train_step_shims_match_the_script():
+    """megatron.mm_collate_fn against batches collated by the reference's own function (gen_collate_goldens.py), and
+    megatron.train_step's plumbing (get_batch keys, None batches skipped, Megatron's return tuple)."""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    import torch
+    from leopard_b200 import megatron
+
+    g = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("gen_collate_goldens", g / "gen_collate_goldens.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    recs = json.loads((g / "ref_collate.json").read_text())
+    assert len(recs) == len(gen.CASES)
+    for k, (case, want) in enumerate(zip(gen.CASES, recs)):
+        got = megatron.mm_collate_fn(gen.make_batch(case, seed=k))
+        if want is None:
+            assert got is None
+            continue
+        assert set(got) == set(want)
+        for key, w in want.items():
+            assert list(got[key].shape) == w["shape"] and str(got[key].dtype) == w["dtype"], (k, key)
+            assert got[key].float().flatten().tolist() == w["data"], (k, key)
+        assert got["input_ids"].shape[1] % 8 == 0
+
+    class Recorder:
+        def step(self, tokens, labels, loss_mask, images):
+            self.seen = (tokens.dtype, labels.dtype, loss_mask.dtype, tuple(tokens.shape), tuple(images.shape))
+            return 1.25, 0.5
+
+    rec = Recorder()
+    batches = iter([None, megatron.mm_collate_fn(gen.make_batch(gen.CASES[0]))])
+    out = megatron.train_step(None, batches, [object()], rec, None, None)
+    assert out == ({"lm loss": 1.25}, 0, 0.5, None)
+    assert rec.seen == (torch.long, torch.long, torch.float32, (2, 16), (3, 3, 4, 4))

@@ -243,3 +243,23 @@ def test_data_parallel_step_averages_gradients_world2_gloo(cpu_trainer):
     scale = want[:, 1].sqrt()[:, None] + 1e-30
     assert float(((g0[:, [0, 2]] - want[:, [0, 2]]) / scale).abs().max()) < 0.05
     assert float(((g0[:, 1] - want[:, 1]) / (want[:, 1] + 1e-30)).abs().max()) < 0.05
+
+
+def test_optimizer_state_round_trip_resumes_identically(cpu_trainer):
+    """Two steps in one trainer == one step, state_dict -> fresh model + trainer -> load_state_dict, second step."""
+    cfg, eng = _small_cpu_engine()
+    batch = _text_batch(cfg, seed=2)
+    tr = T.SFTTrainer(eng, lr=1e-4)
+    tr.step(*batch, None)
+    sd = tr.state_dict()
+    assert sd["iteration"] == 1 and set(sd["main"]) == set(tr.names)
+    loss_a, norm_a = tr.step(*batch, None)
+
+    cfg2, eng2 = _small_cpu_engine()                     # fresh (untrained) weights; everything comes from the state
+    tr2 = T.SFTTrainer(eng2, lr=1e-4)
+    tr2.load_state_dict(sd)
+    loss_b, norm_b = tr2.step(*batch, None)
+    assert (loss_a, norm_a) == (loss_b, norm_b) and tr2.iteration == 2
+    for n in tr.names:
+        assert torch.equal(eng.w.named[n], eng2.w.named[n]), n
+    assert torch.equal(tr.flat_master, tr2.flat_master) and torch.equal(tr.flat_v, tr2.flat_v)
