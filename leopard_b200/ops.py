@@ -325,3 +325,30 @@ def adamw_step(p, g, m, v, p16, step, lr, beta1, beta2, eps, weight_decay, norm_
                                   float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
                                   _lib.ptr(norm_and_clip), _lib.stream_ptr())
     _lib.check(rc, "lp_adamw_step")
+
+
+_attn_bwd_ws = {}
+
+
+def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_off, v_off, causal, scale=None, dqkv=None):
+    """Flash-style backward of `attention` (lp_attention_bwd): returns dqkv in the qkv column layout."""
+    _chk_bf16(qkv, "qkv")
+    _chk_bf16(out, "out")
+    _chk_bf16(dout, "dout")
+    if out.stride(0) != dout.stride(0):
+        raise ValueError("out and dout must share their leading dimension")
+    if scale is None:
+        scale = head_dim ** -0.5
+    if dqkv is None:
+        dqkv = torch.zeros_like(qkv)
+    L = _lib.lib()
+    need = L.lp_attention_bwd_workspace_bytes(B, T, n_heads)
+    ws = _attn_bwd_ws.get(qkv.device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=qkv.device)
+        _attn_bwd_ws[qkv.device] = ws
+    rc = L.lp_attention_bwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(out), _lib.ptr(dout), out.stride(0), B, T, n_heads,
+                            n_kv_heads, head_dim, q_off, k_off, v_off, 1 if causal else 0, float(scale), _lib.ptr(dqkv),
+                            dqkv.stride(0), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "lp_attention_bwd")
+    return dqkv

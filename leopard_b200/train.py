@@ -24,6 +24,7 @@ Not covered yet: vision-tower backward (the tower must stay frozen), gradient ac
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -108,7 +109,7 @@ class SFTTrainer:
 
     def __init__(self, engine, lr: float = 1e-5, min_lr: float = 0.0, warmup_iters: int = 0, decay_iters: int = 0,
                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
-                 clip_grad: float = 1.0, freeze_llm: bool = False, process_group=None):
+                 clip_grad: float = 1.0, freeze_llm: bool = False, process_group=None, attn_bwd: Optional[str] = None):
         if not torch.cuda.is_available():
             raise _lib.NativeError("leopard_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         _lib.lib()
@@ -143,6 +144,10 @@ class SFTTrainer:
         self.kv_w = d.kv_heads * d.head_dim
         self.qkv_w = self.q_w + 2 * self.kv_w
         self._scratch_g = None
+        # attention backward: 'materialized' (verified composition of GEMMs + lp_softmax_bwd) or 'flash' (lp_attention_bwd)
+        self.attn_bwd = attn_bwd or os.environ.get("LEOPARD_ATTN_BWD", "materialized")
+        if self.attn_bwd not in ("materialized", "flash"):
+            raise ValueError(f"attn_bwd must be 'materialized' or 'flash', got {self.attn_bwd!r}")
 
     # ------------------------------------------------------------------ views
     def _view(self, flat: torch.Tensor, layout, name: str) -> torch.Tensor:
@@ -289,9 +294,12 @@ class SFTTrainer:
         # attention
         self._wgrad(f"dec.{i}.o_w", dx2, att)
         datt = self._dgrad(dx2, wo)
-        del att
-        dqkv = self._attention_backward(qkv, datt, b, s)
-        del datt, qkv
+        if self.attn_bwd == "flash":      # tcgen05 flash-style backward (lp_attn_bwd.cu)
+            dqkv = ops.attention_bwd(qkv, att, datt, b, s, d.heads, d.kv_heads, d.head_dim, 0, self.q_w,
+                                     self.q_w + self.kv_w, True)
+        else:                             # materialised score tiles per head (lp_softmax_bwd)
+            dqkv = self._attention_backward(qkv, datt, b, s)
+        del att, datt, qkv
         ops.rope_inplace(dqkv, 0, d.heads + d.kv_heads, d.head_dim, self._cos, self._neg_sin)   # adjoint rotation
         self._wgrad(f"dec.{i}.qkv_w", dqkv, h1)
         dh1 = self._dgrad(dqkv, wqkv)

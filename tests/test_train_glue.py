@@ -128,6 +128,20 @@ def test_sft_step_sequencing_matches_autograd_oracle(cpu_trainer):
     assert tr.iteration == 1 and not any(n.startswith("vit") for n in tr.names)
 
 
+def test_flash_backward_call_is_equivalent_to_the_materialised_path(cpu_trainer):
+    """train.py's two attention-backward routes (per-head materialised tiles vs one lp_attention_bwd call) must be fed
+    consistently: with the op contracts in place of the kernels they give the same gradients."""
+    cfg, ck, nw, eng = cpu_trainer
+    tokens, labels, weights, images = _batch(cfg, b=2, n_text=15, seed=4)
+    grads = {}
+    for mode in ("materialized", "flash"):
+        tr = T.SFTTrainer(eng, lr=0.0, attn_bwd=mode)          # lr 0: the second run sees the same weights
+        tr.step(tokens, labels, weights, images)
+        grads[mode] = tr.flat_grad.clone()
+    rel = float((grads["flash"] - grads["materialized"]).norm() / grads["materialized"].norm())
+    assert rel < 0.02, rel
+
+
 def test_projector_only_stage_skips_decoder_gradients(cpu_trainer):
     cfg, ck, nw, eng = cpu_trainer
     tokens, labels, weights, images = _batch(cfg, b=1, n_text=15, seed=5)
