@@ -348,6 +348,7 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
  * lp_gather_rows_bf16: out[i] = in[idx[i]] — gradient of the image-feature scatter.
  * lp_softmax_bwd:    attention backward over materialised score rows: P = softmax(scale * scores, causal),
  *                    dS = scale * P * (dp - sum_j P dp); bf16 outputs, zeros beyond the causal limit.
+ * lp_accumulate_f32:  dst += src (fp32) — gradient accumulation over micro-batches.
  * lp_sumsq_accum / lp_grad_norm_finish: global L2 norm over fp32 gradients (partial[] must be zeroed per step;
  *                    lp_grad_norm_workspace_bytes() bytes) -> out2 = {norm, clip coefficient} in device memory.
  * lp_adamw_step:     FusedAdam (adam_w_mode) on fp32 main params with the gradient scaled by out2[1]; also refreshes
@@ -381,6 +382,7 @@ int lp_gather_rows_bf16(const void* in, long long ld_in, const int* idx, int n, 
                         void* stream);
 int lp_softmax_bwd(const float* scores, long long lds, const float* dp, long long lddp, void* P, long long ldp, void* dS,
                    long long ldds, int Sq, int Sk, int causal, float scale, void* stream);
+int lp_accumulate_f32(float* dst, const float* src, long long n, void* stream);
 size_t lp_grad_norm_workspace_bytes(void);
 int lp_sumsq_accum(const float* x, long long n, float* partial, void* stream);
 int lp_grad_norm_finish(const float* partial, float max_norm, float* out2, void* stream);

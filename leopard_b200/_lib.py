@@ -111,6 +111,7 @@ _SIGS = {
     "lp_embed_bwd": (_i, [_vp, _ll, _vp, _i, _ll, _vp, _ll, _i, _vp]),
     "lp_gather_rows_bf16": (_i, [_vp, _ll, _vp, _i, _i, _vp, _ll, _vp]),
     "lp_softmax_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "lp_accumulate_f32": (_i, [_vp, _vp, _ll, _vp]),
     "lp_grad_norm_workspace_bytes": (_sz, []),
     "lp_sumsq_accum": (_i, [_vp, _ll, _vp, _vp]),
     "lp_grad_norm_finish": (_i, [_vp, _f, _vp, _vp]),

@@ -426,6 +426,22 @@ grad_norm_finish_kernel(const float* __restrict__ partial, int nb, float max_nor
   }
 }
 
+// dst += src (fp32): gradient accumulation over micro-batches (the wgrad GEMM overwrites its output)
+__global__ void __launch_bounds__(256)
+accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  const long long n4 = n >> 2;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 a = d4[i];
+    const float4 b = s4[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    d4[i] = a;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 256) dst[i] += src[i];
+}
+
 // FusedAdam, adam_w_mode: m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2; p -= lr (m / bc1 / (sqrt(v / bc2) + eps) + wd p)
 // g is scaled by the clip coefficient read from device memory; the bf16 model copy is refreshed in the same pass.
 __global__ void __launch_bounds__(256)
@@ -604,6 +620,15 @@ extern "C" int lp_softmax_bwd(const float* scores, long long lds, const float* d
   note_launch();
   softmax_bwd_kernel<<<Sq, 256, 0, stream>>>(scores, lds, dp, lddp, reinterpret_cast<bf16*>(P), ldp, reinterpret_cast<bf16*>(dS),
                                              ldds, Sk, causal, scale);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lp_accumulate_f32(float* dst, const float* src, long long n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(dst && src && n > 0 && al16(dst) && al16(src), "lp_accumulate_f32: bad arguments n=%lld", n);
+  note_launch();
+  accumulate_kernel<<<grid_for((n + 3) / 4), 256, 0, stream>>>(dst, src, n);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -300,6 +300,17 @@ def softmax_bwd(scores, dp, causal, scale, P=None, dS=None):
     return P, dS
 
 
+def accumulate(dst, src):
+    """dst += src for contiguous fp32 tensors of equal size (lp_accumulate_f32)."""
+    _chk_f32(dst, "dst")
+    _chk_f32(src, "src")
+    if dst.numel() != src.numel():
+        raise ValueError("size mismatch")
+    _lib.check(_lib.lib().lp_accumulate_f32(_lib.ptr(dst), _lib.ptr(src), dst.numel(), _lib.stream_ptr()),
+               "lp_accumulate_f32")
+    return dst
+
+
 def grad_norm(flat_grads, max_norm, partial=None, out2=None):
     """Global L2 norm of the fp32 tensors in `flat_grads` -> device tensor [norm, clip coefficient]."""
     L = _lib.lib()

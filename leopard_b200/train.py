@@ -19,7 +19,7 @@ over C-ABI calls (allocation, shapes and ordering only; every contraction, reduc
 
 Specification and checker: oracle/train.py (closed forms pinned to autograd; end-to-end step by autograd over the prefill
 oracle).  tools/gpu_check_train.py compares this module with it on a B200.  There is no CPU fallback.
-Not covered yet: vision-tower backward (the tower must stay frozen), gradient accumulation over micro-batches, TP > 1.
+Not covered yet: vision-tower backward (the tower must stay frozen), TP > 1.
 """
 from __future__ import annotations
 
@@ -144,6 +144,8 @@ class SFTTrainer:
         self.kv_w = d.kv_heads * d.head_dim
         self.qkv_w = self.q_w + 2 * self.kv_w
         self._scratch_g = None
+        self._accum = False        # True while a micro-batch after the first is being back-propagated
+        self._acc_scratch = {}
         # attention backward: 'materialized' (verified composition of GEMMs + lp_softmax_bwd) or 'flash' (lp_attention_bwd)
         self.attn_bwd = attn_bwd or os.environ.get("LEOPARD_ATTN_BWD", "materialized")
         if self.attn_bwd not in ("materialized", "flash"):
@@ -193,18 +195,48 @@ class SFTTrainer:
         """dX[M, K] = dY[M, N] W[N, K]: the GEMM contracts contiguous dims, so it is fed W^T [K, N]."""
         return ops.gemm(dy, ops.transpose(w), out=out)
 
-    def _wgrad(self, name: str, dy: torch.Tensor, x: torch.Tensor):
-        """grad[name][N, K] (fp32, overwritten) = dY^T[N, M] X[M, K], fed dY^T and X^T [K, M]; skipped when frozen."""
-        if name in self.layout:
-            ops.gemm(ops.transpose(dy), ops.transpose(x), out=self.grad(name))
-
-    def _dgamma(self, name: str) -> torch.Tensor:
-        """Where a norm's weight gradient goes: its slice of the flat buffer, or scratch when the weight is frozen."""
-        if name in self.layout:
+    def _sink(self, name: str) -> Optional[torch.Tensor]:
+        """Where a kernel that OVERWRITES its output should write the gradient of `name`: the tensor's slice of the flat
+        buffer on the first micro-batch, a scratch tensor of the same shape afterwards (added in by `_commit`), None when
+        the tensor is frozen."""
+        if name not in self.layout:
+            return None
+        if not self._accum:
             return self.grad(name)
-        if self._scratch_g is None:
-            self._scratch_g = torch.empty(self.cfg.dec.hidden, dtype=torch.float32, device=self.dev)
-        return self._scratch_g
+        shape = self.w.named[name].shape
+        buf = self._acc_scratch.get(shape)
+        if buf is None:
+            buf = torch.empty(shape, dtype=torch.float32, device=self.dev)
+            self._acc_scratch[shape] = buf
+        return buf
+
+    def _commit(self, name: str, sink: Optional[torch.Tensor]):
+        if sink is not None and self._accum:
+            ops.accumulate(self.grad(name).reshape(-1), sink.reshape(-1))
+
+    def _wgrad(self, name: str, dy: torch.Tensor, x: torch.Tensor):
+        """grad[name][N, K] (fp32) (+)= dY^T[N, M] X[M, K], fed dY^T and X^T [K, M]; skipped when frozen."""
+        sink = self._sink(name)
+        if sink is not None:
+            ops.gemm(ops.transpose(dy), ops.transpose(x), out=sink)
+            self._commit(name, sink)
+
+    def _rms_bwd(self, name: str, x, gamma, dy, add=None) -> torch.Tensor:
+        """RMSNorm backward; the weight gradient goes to `name` (scratch when that weight is frozen)."""
+        sink = self._sink(name)
+        if sink is None:
+            if self._scratch_g is None:
+                self._scratch_g = torch.empty(self.cfg.dec.hidden, dtype=torch.float32, device=self.dev)
+            return ops.rmsnorm_bwd(x, gamma, dy, self.cfg.dec.eps, self._scratch_g, add=add)
+        dx = ops.rmsnorm_bwd(x, gamma, dy, self.cfg.dec.eps, sink, add=add)
+        self._commit(name, sink)
+        return dx
+
+    def _colsum(self, name: str, dy: torch.Tensor):
+        sink = self._sink(name)
+        if sink is not None:
+            ops.colsum(dy, sink)
+            self._commit(name, sink)
 
     # ------------------------------------------------------------------ decoder layer
     def _layer_weights(self, i: int):
@@ -289,7 +321,7 @@ class SFTTrainer:
         self._wgrad(f"dec.{i}.gateup_w", dgu, h2)
         dh2 = self._dgrad(dgu, wgu)
         del dgu, h2
-        dx2 = ops.rmsnorm_bwd(x2, ln2, dh2, d.eps, self._dgamma(f"dec.{i}.ln2_g"), add=dy)
+        dx2 = self._rms_bwd(f"dec.{i}.ln2_g", x2, ln2, dh2, add=dy)
         del dh2, x2
         # attention
         self._wgrad(f"dec.{i}.o_w", dx2, att)
@@ -304,7 +336,7 @@ class SFTTrainer:
         self._wgrad(f"dec.{i}.qkv_w", dqkv, h1)
         dh1 = self._dgrad(dqkv, wqkv)
         del dqkv, h1
-        return ops.rmsnorm_bwd(x, ln1, dh1, d.eps, self._dgamma(f"dec.{i}.ln1_g"), add=dx2)
+        return self._rms_bwd(f"dec.{i}.ln1_g", x, ln1, dh1, add=dx2)
 
     # ------------------------------------------------------------------ gradient reduction
     def _reduce_bucket(self, k: int, handles: list):
@@ -314,19 +346,56 @@ class SFTTrainer:
 
     # ------------------------------------------------------------------ the step
     @torch.no_grad()
-    def step(self, tokens: torch.Tensor, labels: torch.Tensor, loss_mask: torch.Tensor, images: Optional[torch.Tensor]):
-        """One iteration.  Returns (loss, grad_norm) as Python floats (one device -> host read at the end)."""
+    def step(self, tokens, labels, loss_mask, images):
+        """One iteration.  Each argument is a tensor (one micro-batch) or a list of them (gradient accumulation over
+        get_num_microbatches() micro-batches, as Megatron's forward_backward_func does: every micro-batch loss is its own
+        masked mean, divided by the number of micro-batches).  Returns (loss, grad_norm) as Python floats — the mean of the
+        micro-batch losses of this rank, and the global gradient norm before clipping; one device -> host read."""
+        if isinstance(tokens, (list, tuple)):
+            micro = list(zip(tokens, labels, loss_mask, images))
+        else:
+            micro = [(tokens, labels, loss_mask, images)]
+        self.iteration += 1
+        self.flat_grad.zero_()
+        handles: list = []
+        losses = []
+        for k, mb in enumerate(micro):
+            self._accum = k > 0
+            losses.append(self._forward_backward(*mb, n_micro=len(micro), last=k == len(micro) - 1, handles=handles))
+        self._accum = False
+        for h in handles:
+            h.wait()
+
+        # ---- clip + AdamW
+        w, hp = self.w.named, self.hp
+        lr = hp["lr"] if hp["decay"] <= 0 else cosine_lr(self.iteration, hp["lr"], hp["min_lr"], hp["warmup"], hp["decay"])
+        ops.grad_norm([self.flat_grad], hp["clip"], self._norm_ws, self._norm_out)
+        for n in self.names:
+            model_t = w[n]
+            g = self.grad(n).reshape(-1)
+            m = self._view(self.flat_m, self.layout, n).reshape(-1)
+            v = self._view(self.flat_v, self.layout, n).reshape(-1)
+            if model_t.dtype == torch.bfloat16:
+                p = self._view(self.flat_master, self.master_layout, n).reshape(-1)
+                ops.adamw_step(p, g, m, v, model_t, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"], hp["wd"],
+                               self._norm_out)
+            else:
+                ops.adamw_step(model_t.reshape(-1), g, m, v, None, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"],
+                               hp["wd"], self._norm_out)
+        loss = torch.stack(losses).mean()
+        out = torch.cat([loss.reshape(1), self._norm_out[:1]]).tolist()
+        return out[0], out[1]
+
+    def _forward_backward(self, tokens, labels, loss_mask, images, n_micro: int, last: bool, handles: list):
+        """Forward, loss and backward of one micro-batch; gradients are written (first micro-batch) or added (later ones)
+        into the flat buffer; on the last micro-batch every bucket's all-reduce is issued as soon as it is complete."""
         cfg, d, w = self.cfg, self.cfg.dec, self.w.named
-        L = _lib.lib()
         self._attn_variant = 80
         b, s = tokens.shape
         if s % 8:
             raise ValueError(f"sequence length {s} must be a multiple of 8")
         R = b * s
         ids = tokens.reshape(-1).to(self.dev, torch.long).contiguous()
-        self.iteration += 1
-        self.flat_grad.zero_()
-        handles: list = []
 
         # ---- vision tower (frozen) + projector, keeping what the projector's backward needs
         n_img_rows = int((ids == cfg.megatron_image_index).sum())
@@ -356,60 +425,44 @@ class SFTTrainer:
         logits = ops.gemm(hN, w["dec.lm_head"], out_fp32=True)                    # [R, vocab_padded] fp32
 
         # ---- loss and its gradient
-        tgt, wt = shifted_targets(labels.to(self.dev), loss_mask.to(self.dev), self.world)
+        tgt, wt = shifted_targets(labels.to(self.dev), loss_mask.to(self.dev), self.world * n_micro)
         loss_rows, dlogits = ops.ce_fwd_bwd(logits, tgt, wt, d.vocab)
         del logits
-        loss = torch.dot(loss_rows, wt) * self.world          # this rank's masked mean (the scalar that is reported)
+        loss = torch.dot(loss_rows, wt) * (self.world * n_micro)     # this micro-batch's masked mean (what is reported)
 
         # ---- backward (buckets of the flat gradient buffer are reduced in the order they complete)
+        def reduce(k):
+            if last:
+                self._reduce_bucket(k, handles)
+
         self._wgrad("dec.lm_head", dlogits, hN)
         dh = self._dgrad(dlogits, w["dec.lm_head"])
         del dlogits
-        dx = ops.rmsnorm_bwd(x, w["dec.final_g"], dh, d.eps, self._dgamma("dec.final_g"))
+        dx = self._rms_bwd("dec.final_g", x, w["dec.final_g"], dh)
         del dh, hN
         bucket = 0
         if not self.freeze_llm:
-            self._reduce_bucket(bucket, handles)      # 'dec.lm_head' + 'dec.final_g'
+            reduce(bucket)      # 'dec.lm_head' + 'dec.final_g'
             bucket += 1
         for i in reversed(range(d.layers)):
             dx = self._layer_backward(i, xs.pop(), dx, b, s)
             if not self.freeze_llm:
-                self._reduce_bucket(bucket, handles)
+                reduce(bucket)
                 bucket += 1
         # ---- merge backward: text rows feed the embedding table, image rows feed the projector
         if not self.freeze_llm:
-            ops.embed_bwd(dx, ids, cfg.megatron_image_index, self.grad("embed"))
-            self._reduce_bucket(bucket, handles)
+            ops.embed_bwd(dx, ids, cfg.megatron_image_index, self.grad("embed"))     # adds: accumulates by construction
+            reduce(bucket)
             bucket += 1
         if have_images:
             idx = torch.nonzero(ids == cfg.megatron_image_index).reshape(-1).to(torch.int32)
             dfe = ops.gather_rows(dx, idx)
             self._wgrad("proj.w2", dfe, a1)
-            ops.colsum(dfe, self.grad("proj.b2"))
+            self._colsum("proj.b2", dfe)
             da1 = self._dgrad(dfe, w["proj.w2"])
             dz1 = ops.gelu_bwd(z1, da1, self.w.proj.act)
             self._wgrad("proj.w1", dz1, shuf)
-            ops.colsum(dz1, self.grad("proj.b1"))
-        self._reduce_bucket(bucket, handles)
+            self._colsum("proj.b1", dz1)
+        reduce(bucket)
         assert bucket == len(self.buckets) - 1
-        for h in handles:
-            h.wait()
-
-        # ---- clip + AdamW
-        hp = self.hp
-        lr = hp["lr"] if hp["decay"] <= 0 else cosine_lr(self.iteration, hp["lr"], hp["min_lr"], hp["warmup"], hp["decay"])
-        ops.grad_norm([self.flat_grad], hp["clip"], self._norm_ws, self._norm_out)
-        for n in self.names:
-            model_t = w[n]
-            g = self.grad(n).reshape(-1)
-            m = self._view(self.flat_m, self.layout, n).reshape(-1)
-            v = self._view(self.flat_v, self.layout, n).reshape(-1)
-            if model_t.dtype == torch.bfloat16:
-                p = self._view(self.flat_master, self.master_layout, n).reshape(-1)
-                ops.adamw_step(p, g, m, v, model_t, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"], hp["wd"],
-                               self._norm_out)
-            else:
-                ops.adamw_step(model_t.reshape(-1), g, m, v, None, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"],
-                               hp["wd"], self._norm_out)
-        out = torch.cat([loss.reshape(1), self._norm_out[:1]]).tolist()
-        return out[0], out[1]
+        return loss

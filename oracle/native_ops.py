@@ -167,6 +167,11 @@ def softmax_bwd(scores, dp, causal, scale, P=None, dS=None):
     return _store(p, P), _store(g, dS)
 
 
+def accumulate(dst, src):
+    dst.add_(src.view(dst.shape))
+    return dst
+
+
 def grad_norm(flat_grads, max_norm, partial=None, out2=None):
     norm = math.sqrt(sum(float(g.double().pow(2).sum()) for g in flat_grads))
     c = 1.0

@@ -277,3 +277,21 @@ def test_optimizer_state_round_trip_resumes_identically(cpu_trainer):
     for n in tr.names:
         assert torch.equal(eng.w.named[n], eng2.w.named[n]), n
     assert torch.equal(tr.flat_master, tr2.flat_master) and torch.equal(tr.flat_v, tr2.flat_v)
+
+
+def test_gradient_accumulation_over_micro_batches(cpu_trainer):
+    """step([mb0, mb1]) == the average of the two single-micro-batch gradients; reported loss = mean of the two."""
+    cfg, eng = _small_cpu_engine()
+    mbs = [_text_batch(cfg, seed=s) for s in (0, 1)]
+    singles, losses = [], []
+    for mb in mbs:
+        tr = T.SFTTrainer(eng, lr=0.0)
+        loss, _ = tr.step(*mb, None)
+        singles.append(tr.flat_grad.clone())
+        losses.append(loss)
+    tr = T.SFTTrainer(eng, lr=0.0)
+    loss, norm = tr.step([m[0] for m in mbs], [m[1] for m in mbs], [m[2] for m in mbs], [None, None])
+    want = 0.5 * (singles[0] + singles[1])
+    assert abs(loss - 0.5 * (losses[0] + losses[1])) < 1e-3 * abs(loss)
+    assert float((tr.flat_grad - want).norm() / want.norm()) < 0.01
+    assert abs(norm - float(want.double().norm())) < 1e-4 * norm and tr.iteration == 1     # fp64: 2e8 addends
