@@ -206,18 +206,25 @@ def mm_collate_fn(batch):
     return out
 
 
-def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_scheduler=None, config=None):
+def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_scheduler=None, config=None,
+               num_microbatches: int = 1):
     """Megatron's `train_step` (Megatron-LM-240424/megatron/training/training.py:544-607) for this path: same signature,
     same return tuple (loss_reduced, skipped_iter, grad_norm, num_zeros_in_grad).  `optimizer` is a
     leopard_b200.train.SFTTrainer built on `model[0].engine`: zero-grad, forward, loss_func, backward, the data-parallel
     reduce, clipping and the Adam update all happen inside its `step`, on native kernels, so `forward_step_func` is not
     called; the batch is read with get_batch's keys (:52-99): 'input_ids', 'labels', 'weights' (the loss mask), 'image'.
-    The learning-rate schedule lives in the trainer (cosine with warm-up, as the launch script configures)."""
-    data = next(data_iterator)
-    while data is None:                      # get_batch :59-62 skips empty collates
+    The learning-rate schedule lives in the trainer (cosine with warm-up, as the launch script configures);
+    `num_microbatches` = Megatron's get_num_microbatches() (global batch / (micro batch x data-parallel size))."""
+    micro = []
+    for _ in range(num_microbatches):        # get_num_microbatches() batches per iteration, gradients accumulated
         data = next(data_iterator)
-    loss, grad_norm = optimizer.step(data["input_ids"].long(), data["labels"].long(), data["weights"].float(),
-                                     data["image"])
+        while data is None:                  # get_batch :59-62 skips empty collates
+            data = next(data_iterator)
+        micro.append((data["input_ids"].long(), data["labels"].long(), data["weights"].float(), data["image"]))
+    if num_microbatches == 1:
+        loss, grad_norm = optimizer.step(*micro[0])
+    else:
+        loss, grad_norm = optimizer.step(*[list(col) for col in zip(*micro)])
     return {"lm loss": loss}, 0, grad_norm, None
 
 

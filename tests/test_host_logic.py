@@ -373,3 +373,14 @@ def test_collate_and_train_step_shims_match_the_script():
     out = megatron.train_step(None, batches, [object()], rec, None, None)
     assert out == ({"lm loss": 1.25}, 0, 0.5, None)
     assert rec.seen == (torch.long, torch.long, torch.float32, (2, 16), (3, 3, 4, 4))
+
+    class ListRecorder:
+        def step(self, tokens, labels, loss_mask, images):
+            self.n = (len(tokens), len(labels), len(loss_mask), len(images), tuple(tokens[1].shape))
+            return 2.0, 1.0
+
+    lrec = ListRecorder()
+    b0 = megatron.mm_collate_fn(gen.make_batch(gen.CASES[0]))
+    b1 = megatron.mm_collate_fn(gen.make_batch(gen.CASES[4]))
+    assert megatron.train_step(None, iter([b0, None, b1]), [object()], lrec, num_microbatches=2)[0] == {"lm loss": 2.0}
+    assert lrec.n == (2, 2, 2, 2, (1, 24))
