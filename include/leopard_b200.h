@@ -364,6 +364,15 @@ int lp_attention_bwd(const void* qkv, long long ld, const void* out, const void*
                      int n_heads, int n_kv_heads, int head_dim, int q_off, int k_off, int v_off, int causal, float scale,
                      void* dqkv, long long ldd, void* workspace, size_t ws_bytes, void* stream);
 int lp_transpose_bf16(const void* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream);
+/* Vision-tower backward pieces: LayerNorm backward (dx (+ add), dgamma, dbeta; fixed summation order), the inverse of the
+ * pixel shuffle (gradient of lp_pixel_shuffle / lp_layernorm's shuffled store, EV :165-176), and the position-embedding
+ * gradient out[t] = sum_n d[n * T + t] (the forward adds pos[row % T], idefics_vision_tower.py:147-150). */
+size_t lp_layernorm_bwd_workspace_bytes(int D);
+int lp_layernorm_bwd(const void* x, long long ldx, const float* gamma, const void* dy, long long lddy, const void* add,
+                     long long ldadd, void* dx, long long lddx, float* dgamma, float* dbeta, int M, int D, float eps,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int lp_pixel_unshuffle(const void* d, long long ldd, void* out, long long ldo, int M, int D, int side, void* stream);
+int lp_rowmod_sum(const void* d, long long ldd, int n_rep, int T, int D, float* out, void* stream);
 size_t lp_rmsnorm_bwd_workspace_bytes(int D);
 int lp_rmsnorm_bwd(const void* x, long long ldx, const float* gamma, const void* dy, long long lddy, const void* add,
                    long long ldadd, void* dx, long long lddx, float* dgamma, int M, int D, float eps, void* workspace,

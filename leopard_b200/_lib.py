@@ -101,6 +101,10 @@ _SIGS = {
     "lp_attention_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "lp_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp, _sz, _vp]),
     "lp_transpose_bf16": (_i, [_vp, _ll, _i, _i, _vp, _ll, _vp]),
+    "lp_layernorm_bwd_workspace_bytes": (_sz, [_i]),
+    "lp_layernorm_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _sz, _vp]),
+    "lp_pixel_unshuffle": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "lp_rowmod_sum": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
     "lp_rmsnorm_bwd_workspace_bytes": (_sz, [_i]),
     "lp_rmsnorm_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i, _f, _vp, _sz, _vp]),
     "lp_swiglu_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),

@@ -187,6 +187,139 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __res
   }
 }
 
+// ---- LayerNorm backward (vision tower) ------------------------------------------------------------------------------
+// y = xh g + b, xh = (x - mu) r:  dx = r (gh - mean(gh) - xh mean(gh xh)) (+ add), gh = dy g;  dg = sum dy xh;  db = sum dy.
+// Same walk as rmsnorm_bwd_kernel; statistics two-pass (mean, then centred variance) like the forward kernel.  The
+// partial buffer holds [dg | db] rows of width 2 D per CTA.
+template <int J>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma, const bf16* __restrict__ dy,
+                     long long lddy, const bf16* __restrict__ add, long long ldadd, bf16* __restrict__ dx, long long lddx,
+                     float* __restrict__ partial, int M, int D, float eps) {
+  __shared__ float red[8];
+  const int t = threadIdx.x;
+  float gm[J][8], accg[J][8], accb[J][8];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c = (t + 256 * j) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gm[j][e] = (c < D) ? gamma[c + e] : 0.f;
+      accg[j][e] = 0.f;
+      accb[j][e] = 0.f;
+    }
+  }
+  const float invD = 1.f / (float)D;
+  for (int r = blockIdx.x; r < M; r += gridDim.x) {
+    uint4 xu[J], du[J];
+    float sx = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (t + 256 * j) * 8;
+      xu[j] = make_uint4(0, 0, 0, 0);
+      du[j] = make_uint4(0, 0, 0, 0);
+      if (c < D) {
+        xu[j] = *reinterpret_cast<const uint4*>(x + (long long)r * ldx + c);
+        du[j] = *reinterpret_cast<const uint4*>(dy + (long long)r * lddy + c);
+        float xf[8];
+        unpack8(xu[j], xf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sx += xf[e];
+      }
+    }
+    const float mu = block_sum_256(sx, red) * invD;
+    float sv = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (t + 256 * j) * 8;
+      if (c < D) {
+        float xf[8];
+        unpack8(xu[j], xf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sv += (xf[e] - mu) * (xf[e] - mu);
+      }
+    }
+    const float rinv = rsqrtf(block_sum_256(sv, red) * invD + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (t + 256 * j) * 8;
+      if (c < D) {
+        float xf[8], df[8];
+        unpack8(xu[j], xf);
+        unpack8(du[j], df);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float gh = df[e] * gm[j][e];
+          sg += gh;
+          sgx += gh * (xf[e] - mu) * rinv;
+        }
+      }
+    }
+    const float mg = block_sum_256(sg, red) * invD;
+    const float mgx = block_sum_256(sgx, red) * invD;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (t + 256 * j) * 8;
+      if (c < D) {
+        float xf[8], df[8], o[8];
+        unpack8(xu[j], xf);
+        unpack8(du[j], df);
+        float af[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (add != nullptr) unpack8(*reinterpret_cast<const uint4*>(add + (long long)r * ldadd + c), af);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xf[e] - mu) * rinv;
+          o[e] = rinv * (df[e] * gm[j][e] - mg - xh * mgx) + af[e];
+          accg[j][e] += df[e] * xh;
+          accb[j][e] += df[e];
+        }
+        *reinterpret_cast<uint4*>(dx + (long long)r * lddx + c) = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c = (t + 256 * j) * 8;
+    if (c < D) {
+      float4* pg = reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 2 * D + c);
+      float4* pb = reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 2 * D + D + c);
+      pg[0] = make_float4(accg[j][0], accg[j][1], accg[j][2], accg[j][3]);
+      pg[1] = make_float4(accg[j][4], accg[j][5], accg[j][6], accg[j][7]);
+      pb[0] = make_float4(accb[j][0], accb[j][1], accb[j][2], accb[j][3]);
+      pb[1] = make_float4(accb[j][4], accb[j][5], accb[j][6], accb[j][7]);
+    }
+  }
+}
+
+// ---- pixel-shuffle backward: x_grad[b, (2oh+dy)*side + 2ow+dx, :] = d[b, oh*half + ow, (dy*2+dx)*D : +D]; one CTA per row of x
+__global__ void __launch_bounds__(128)
+pixel_unshuffle_kernel(const bf16* __restrict__ d, long long ldd, bf16* __restrict__ out, long long ldo, int side, int D) {
+  const int row = blockIdx.x;
+  const int per = side * side, half = side >> 1;
+  const int b = row / per, t = row % per, h = t / side, w = t % side;
+  const long long srow = (long long)b * (half * half) + (h >> 1) * half + (w >> 1);
+  const uint4* sp = reinterpret_cast<const uint4*>(d + srow * ldd + (((h & 1) << 1) | (w & 1)) * D);
+  uint4* dp = reinterpret_cast<uint4*>(out + (long long)row * ldo);
+  for (int c = threadIdx.x; c < (D >> 3); c += blockDim.x) dp[c] = sp[c];
+}
+
+// ---- position-embedding gradient: out[t, c] = sum_n d[n * T + t, c]  (fp32, fixed order) --------------------------------
+__global__ void __launch_bounds__(256)
+rowmod_sum_kernel(const bf16* __restrict__ d, long long ldd, int n_rep, int T, int D, float* __restrict__ out) {
+  const int t = blockIdx.x;
+  for (int c = threadIdx.x * 2; c < D; c += 512) {
+    float2 s = make_float2(0.f, 0.f);
+    for (int n = 0; n < n_rep; ++n) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + ((long long)n * T + t) * ldd + c));
+      s.x += v.x;
+      s.y += v.y;
+    }
+    out[(long long)t * D + c] = s.x;
+    out[(long long)t * D + c + 1] = s.y;
+  }
+}
+
 // out[c] = sum_b partial[b, c]   (fixed order: deterministic)
 __global__ void __launch_bounds__(256)
 partial_reduce_kernel(const float* __restrict__ partial, int nb, int D, float* __restrict__ out) {
@@ -195,6 +328,16 @@ partial_reduce_kernel(const float* __restrict__ partial, int nb, int D, float* _
   float s = 0.f;
   for (int b = 0; b < nb; ++b) s += partial[(long long)b * D + c];
   out[c] = s;
+}
+
+// the LayerNorm variant: partial rows are [dg | db] (width 2 D)
+__global__ void __launch_bounds__(256)
+partial_reduce2_kernel(const float* __restrict__ partial, int nb, int D, float* __restrict__ dg, float* __restrict__ db) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= 2 * D) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partial[(long long)b * 2 * D + c];
+  if (c < D) dg[c] = s; else db[c - D] = s;
 }
 
 // ---- SwiGLU on the interleaved gate/up layout of the fused weight (32-column granules: gate_0..31, up_0..31, ...) ----
@@ -517,6 +660,59 @@ extern "C" int lp_rmsnorm_bwd(const void* x, long long ldx, const float* gamma, 
     rmsnorm_bwd_kernel<4><<<nb, 256, 0, stream>>>(xb, ldx, gamma, dyb, lddy, ab, ldadd, dxb, lddx, partial, M, D, eps);
   LP_CHECK_CUDA(cudaGetLastError());
   partial_reduce_kernel<<<(D + 255) / 256, 256, 0, stream>>>(partial, nb, D, dgamma);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" size_t lp_layernorm_bwd_workspace_bytes(int D) { return (size_t)NB_PARTIAL * 2 * (size_t)D * sizeof(float); }
+
+extern "C" int lp_layernorm_bwd(const void* x, long long ldx, const float* gamma, const void* dy, long long lddy,
+                                const void* add, long long ldadd, void* dx, long long lddx, float* dgamma, float* dbeta, int M,
+                                int D, float eps, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && workspace && M > 0, "lp_layernorm_bwd: null argument or M=%d", M);
+  LP_REQUIRE(D % 8 == 0 && D >= 8 && D <= 4096, "lp_layernorm_bwd: D=%d must be a multiple of 8, at most 4096", D);
+  LP_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (add == nullptr || ldadd % 8 == 0) && al16(x) && al16(dy) &&
+                 al16(dx) && (add == nullptr || al16(add)) && al16(workspace),
+             "lp_layernorm_bwd: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
+  LP_REQUIRE(workspace_bytes >= lp_layernorm_bwd_workspace_bytes(D), "lp_layernorm_bwd: workspace too small");
+  const int nb = M < NB_PARTIAL ? M : NB_PARTIAL;
+  float* partial = reinterpret_cast<float*>(workspace);
+  const bf16 *xb = reinterpret_cast<const bf16*>(x), *dyb = reinterpret_cast<const bf16*>(dy),
+             *ab = reinterpret_cast<const bf16*>(add);
+  bf16* dxb = reinterpret_cast<bf16*>(dx);
+  note_launch(3);
+  if (D <= 2048)
+    layernorm_bwd_kernel<1><<<nb, 256, 0, stream>>>(xb, ldx, gamma, dyb, lddy, ab, ldadd, dxb, lddx, partial, M, D, eps);
+  else
+    layernorm_bwd_kernel<2><<<nb, 256, 0, stream>>>(xb, ldx, gamma, dyb, lddy, ab, ldadd, dxb, lddx, partial, M, D, eps);
+  LP_CHECK_CUDA(cudaGetLastError());
+  // partial rows are [dg | db] of width 2 D: reduce both halves with one launch over 2 D columns, then split
+  partial_reduce2_kernel<<<(2 * D + 255) / 256, 256, 0, stream>>>(partial, nb, D, dgamma, dbeta);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lp_pixel_unshuffle(const void* d, long long ldd, void* out, long long ldo, int M, int D, int side,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(d && out && M > 0 && D > 0 && D % 8 == 0 && side > 0 && side % 2 == 0 && M % (side * side) == 0,
+             "lp_pixel_unshuffle: bad arguments M=%d D=%d side=%d", M, D, side);
+  LP_REQUIRE(al16(d) && al16(out) && ldd % 8 == 0 && ldo % 8 == 0 && ldd >= 4LL * D && ldo >= D,
+             "lp_pixel_unshuffle: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
+  note_launch();
+  pixel_unshuffle_kernel<<<M, 128, 0, stream>>>(reinterpret_cast<const bf16*>(d), ldd, reinterpret_cast<bf16*>(out), ldo, side,
+                                                D);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lp_rowmod_sum(const void* d, long long ldd, int n_rep, int T, int D, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(d && out && n_rep > 0 && T > 0 && D > 0 && D % 2 == 0 && ldd % 2 == 0 && al4(d),
+             "lp_rowmod_sum: bad arguments n_rep=%d T=%d D=%d", n_rep, T, D);
+  note_launch();
+  rowmod_sum_kernel<<<T, 256, 0, stream>>>(reinterpret_cast<const bf16*>(d), ldd, n_rep, T, D, out);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -99,9 +99,9 @@ def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda
     # ---- SigLIP tower
     pw = get(V + "embeddings.patch_embedding.weight").to(dev).reshape(v.hidden, v.patch_k)
     pw = torch.nn.functional.pad(pw, (0, PATCH_K_PAD - v.patch_k))
-    nw.vit.patch_w = nw._p(nw._bf(pw))
-    nw.vit.patch_b = nw._p(nw._f32(get(V + "embeddings.patch_embedding.bias")))
-    nw.vit.pos = nw._p(nw._bf(get(V + "embeddings.position_embedding.weight")))
+    nw.vit.patch_w = nw._p(nw._bf(pw, "vit.patch_w"))
+    nw.vit.patch_b = nw._p(nw._f32(get(V + "embeddings.patch_embedding.bias"), "vit.patch_b"))
+    nw.vit.pos = nw._p(nw._bf(get(V + "embeddings.position_embedding.weight"), "vit.pos"))
     pad_rows = HEAD_STRIDE - v.head_dim
 
     def pad_heads(w):  # [heads*72, ...] -> [heads*80, ...] with zero rows after each head
@@ -114,23 +114,23 @@ def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda
     for i in range(v.layers):
         b = f"{V}encoder.layers.{i}."
         L = nw.vit_layers[i]
-        L.ln1_g = nw._p(nw._f32(get(b + "layer_norm1.weight")))
-        L.ln1_b = nw._p(nw._f32(get(b + "layer_norm1.bias")))
-        L.ln2_g = nw._p(nw._f32(get(b + "layer_norm2.weight")))
-        L.ln2_b = nw._p(nw._f32(get(b + "layer_norm2.bias")))
+        L.ln1_g = nw._p(nw._f32(get(b + "layer_norm1.weight"), f"vit.{i}.ln1_g"))
+        L.ln1_b = nw._p(nw._f32(get(b + "layer_norm1.bias"), f"vit.{i}.ln1_b"))
+        L.ln2_g = nw._p(nw._f32(get(b + "layer_norm2.weight"), f"vit.{i}.ln2_g"))
+        L.ln2_b = nw._p(nw._f32(get(b + "layer_norm2.bias"), f"vit.{i}.ln2_b"))
         qkv_w = torch.cat([pad_heads(get(b + f"self_attn.{n}_proj.weight")) for n in "qkv"], 0)
         qkv_b = torch.cat([pad_heads(get(b + f"self_attn.{n}_proj.bias")) for n in "qkv"], 0)
-        L.qkv_w = nw._p(nw._bf(qkv_w))
-        L.qkv_b = nw._p(nw._f32(qkv_b))
-        L.out_w = nw._p(nw._bf(get(b + "self_attn.out_proj.weight")))
-        L.out_b = nw._p(nw._f32(get(b + "self_attn.out_proj.bias")))
-        L.fc1_w = nw._p(nw._bf(get(b + "mlp.fc1.weight")))
-        L.fc1_b = nw._p(nw._f32(get(b + "mlp.fc1.bias")))
-        L.fc2_w = nw._p(nw._bf(get(b + "mlp.fc2.weight")))
-        L.fc2_b = nw._p(nw._f32(get(b + "mlp.fc2.bias")))
+        L.qkv_w = nw._p(nw._bf(qkv_w, f"vit.{i}.qkv_w"))
+        L.qkv_b = nw._p(nw._f32(qkv_b, f"vit.{i}.qkv_b"))
+        L.out_w = nw._p(nw._bf(get(b + "self_attn.out_proj.weight"), f"vit.{i}.out_w"))
+        L.out_b = nw._p(nw._f32(get(b + "self_attn.out_proj.bias"), f"vit.{i}.out_b"))
+        L.fc1_w = nw._p(nw._bf(get(b + "mlp.fc1.weight"), f"vit.{i}.fc1_w"))
+        L.fc1_b = nw._p(nw._f32(get(b + "mlp.fc1.bias"), f"vit.{i}.fc1_b"))
+        L.fc2_w = nw._p(nw._bf(get(b + "mlp.fc2.weight"), f"vit.{i}.fc2_w"))
+        L.fc2_b = nw._p(nw._f32(get(b + "mlp.fc2.bias"), f"vit.{i}.fc2_b"))
     nw.vit.layers = C.cast(nw.vit_layers, C.POINTER(_lib.VitLayerWeights))
-    nw.vit.post_g = nw._p(nw._f32(get(V + "post_layernorm.weight")))
-    nw.vit.post_b = nw._p(nw._f32(get(V + "post_layernorm.bias")))
+    nw.vit.post_g = nw._p(nw._f32(get(V + "post_layernorm.weight"), "vit.post_g"))
+    nw.vit.post_b = nw._p(nw._f32(get(V + "post_layernorm.bias"), "vit.post_b"))
 
     # ---- projector (Leopard-LLaVA only; Idefics2 has its own connector, see idefics2.py)
     if with_projector:
@@ -173,12 +173,36 @@ def named_to_hf(cfg: LeopardConfig, named: Dict[str, torch.Tensor]) -> Dict[str,
     """Inverse of load_hf for the tensors the SFT step updates (NativeWeights.named): kernel layout -> HF-named tensors
     (split the fused qkv rows, undo the 32-row gate/up interleave, drop the vocabulary padding).  Pure data movement;
     returns views / reshapes of the live device tensors, so a checkpoint written from them holds the trained values."""
-    d = cfg.dec
+    d, v = cfg.dec, cfg.vit
     out: Dict[str, torch.Tensor] = {}
     q_w, kv_w = d.heads * d.head_dim, d.kv_heads * d.head_dim
     for name, t in named.items():
-        if name == "embed":
+        if name.startswith("vit."):
+            parts = name.split(".")
+            if len(parts) == 2:
+                key = {"patch_w": "embeddings.patch_embedding.weight", "patch_b": "embeddings.patch_embedding.bias",
+                       "pos": "embeddings.position_embedding.weight", "post_g": "post_layernorm.weight",
+                       "post_b": "post_layernorm.bias"}[parts[1]]
+                if parts[1] == "patch_w":       # drop the K padding, back to the conv kernel shape
+                    t = t[:, : v.patch_k].reshape(v.hidden, 3, v.patch_size, v.patch_size)
+                out[V + key] = t
+                continue
+            b = f"{V}encoder.layers.{parts[1]}."
+            kind = parts[2]
+            if kind in ("qkv_w", "qkv_b"):      # [3, heads, 80 (72 + zero pad), ...] -> three [heads * 72, ...] tensors
+                g = t.reshape(3, v.heads, HEAD_STRIDE, *t.shape[1:])[:, :, : v.head_dim]
+                for j, n in enumerate("qkv"):
+                    out[b + f"self_attn.{n}_proj." + ("weight" if kind == "qkv_w" else "bias")] = g[j].reshape(
+                        v.hidden, *t.shape[1:])
+            else:
+                out[b + {"ln1_g": "layer_norm1.weight", "ln1_b": "layer_norm1.bias", "ln2_g": "layer_norm2.weight",
+                         "ln2_b": "layer_norm2.bias", "out_w": "self_attn.out_proj.weight", "out_b": "self_attn.out_proj.bias",
+                         "fc1_w": "mlp.fc1.weight", "fc1_b": "mlp.fc1.bias", "fc2_w": "mlp.fc2.weight",
+                         "fc2_b": "mlp.fc2.bias"}[kind]] = t
+        elif name == "embed":
             out[LM + "embed_tokens.weight"] = t
+        elif name == "dec.inv_freq":
+            continue
         elif name == "dec.final_g":
             out[LM + "norm.weight"] = t
         elif name == "dec.lm_head":

@@ -210,6 +210,50 @@ def rmsnorm_bwd(x, gamma, dy, eps, dgamma, add=None, out=None):
     return out
 
 
+_ln_bwd_ws = {}
+
+
+def layernorm_bwd(x, gamma, dy, eps, dgamma, dbeta, add=None, out=None):
+    """dx = layernorm'(x; gamma) dy (+ add); dgamma, dbeta (fp32 [D]) are overwritten (lp_layernorm_bwd)."""
+    _chk_bf16(x, "x")
+    _chk_bf16(dy, "dy")
+    for t, n in ((gamma, "gamma"), (dgamma, "dgamma"), (dbeta, "dbeta")):
+        _chk_f32(t, n)
+    M, D = x.shape
+    L = _lib.lib()
+    ws = _ln_bwd_ws.get((x.device, D))
+    if ws is None:
+        ws = torch.empty(L.lp_layernorm_bwd_workspace_bytes(D), dtype=torch.uint8, device=x.device)
+        _ln_bwd_ws[(x.device, D)] = ws
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    rc = L.lp_layernorm_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(gamma), _lib.ptr(dy), dy.stride(0), _lib.ptr(add),
+                            add.stride(0) if add is not None else 0, _lib.ptr(out), out.stride(0), _lib.ptr(dgamma),
+                            _lib.ptr(dbeta), M, D, float(eps), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "lp_layernorm_bwd")
+    return out
+
+
+def pixel_unshuffle(d, side):
+    """d bf16 [M/4, 4*D] (gradient of the shuffled layout) -> [M, D] (lp_pixel_unshuffle)."""
+    _chk_bf16(d, "d")
+    M4, D4 = d.shape
+    out = torch.empty((M4 * 4, D4 // 4), device=d.device, dtype=torch.bfloat16)
+    rc = _lib.lib().lp_pixel_unshuffle(_lib.ptr(d), d.stride(0), _lib.ptr(out), out.stride(0), M4 * 4, D4 // 4, side,
+                                       _lib.stream_ptr())
+    _lib.check(rc, "lp_pixel_unshuffle")
+    return out
+
+
+def rowmod_sum(d, T, out):
+    """out[t] = sum_n d[n*T + t] (fp32 [T, D], overwritten) (lp_rowmod_sum)."""
+    _chk_bf16(d, "d")
+    _chk_f32(out, "out")
+    rc = _lib.lib().lp_rowmod_sum(_lib.ptr(d), d.stride(0), d.shape[0] // T, T, d.shape[1], _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lp_rowmod_sum")
+    return out
+
+
 def swiglu_fwd(gu, out=None):
     """gu bf16 [M, 2F] in the fused weight's interleaved column order -> silu(gate) * up [M, F] (lp_swiglu_fwd)."""
     _chk_bf16(gu, "gu")

@@ -19,7 +19,8 @@ over C-ABI calls (allocation, shapes and ordering only; every contraction, reduc
 
 Specification and checker: oracle/train.py (closed forms pinned to autograd; end-to-end step by autograd over the prefill
 oracle).  tools/gpu_check_train.py compares this module with it on a B200.  There is no CPU fallback.
-Not covered yet: vision-tower backward (the tower must stay frozen), TP > 1.
+The vision tower is frozen by default (--freeze-clip-vision-tower); freeze_vision_tower=False back-propagates through it
+with the materialised attention backward per (crop, head) — functional, launch-bound.  Not covered yet: TP > 1.
 """
 from __future__ import annotations
 
@@ -85,8 +86,9 @@ def cosine_lr(it: int, lr: float, min_lr: float, warmup_iters: int, decay_iters:
     return min_lr + (lr - min_lr) * 0.5 * (math.cos(math.pi * ratio) + 1.0)
 
 
-def trainable_names(n_layers: int, freeze_llm: bool = False, with_projector: bool = True) -> List[str]:
-    """Names (NativeWeights.named) in the order their gradients are completed by the backward pass."""
+def trainable_names(n_layers: int, freeze_llm: bool = False, with_projector: bool = True, vit_layers: int = 0) -> List[str]:
+    """Names (NativeWeights.named) in the order their gradients are completed by the backward pass; vit_layers > 0 adds the
+    vision tower (one bucket: it is 5 % of the parameters)."""
     names: List[str] = []
     if not freeze_llm:
         names += ["dec.lm_head", "dec.final_g"]
@@ -96,6 +98,12 @@ def trainable_names(n_layers: int, freeze_llm: bool = False, with_projector: boo
         names += ["embed"]
     if with_projector:
         names += ["proj.w2", "proj.b2", "proj.w1", "proj.b1"]
+    if vit_layers > 0:
+        names += ["vit.post_g", "vit.post_b"]
+        for i in reversed(range(vit_layers)):
+            names += [f"vit.{i}.{k}" for k in ("fc2_w", "fc2_b", "fc1_w", "fc1_b", "ln2_g", "ln2_b", "out_w", "out_b", "qkv_w",
+                                               "qkv_b", "ln1_g", "ln1_b")]
+        names += ["vit.pos", "vit.patch_b", "vit.patch_w"]
     return names
 
 
@@ -109,7 +117,8 @@ class SFTTrainer:
 
     def __init__(self, engine, lr: float = 1e-5, min_lr: float = 0.0, warmup_iters: int = 0, decay_iters: int = 0,
                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
-                 clip_grad: float = 1.0, freeze_llm: bool = False, process_group=None, attn_bwd: Optional[str] = None):
+                 clip_grad: float = 1.0, freeze_llm: bool = False, freeze_vision_tower: bool = True, process_group=None,
+                 attn_bwd: Optional[str] = None):
         if not torch.cuda.is_available():
             raise _lib.NativeError("leopard_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         _lib.lib()
@@ -124,7 +133,8 @@ class SFTTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.iteration = 0
         d = self.cfg.dec
-        self.names = trainable_names(d.layers, freeze_llm)
+        self.freeze_vit = freeze_vision_tower
+        self.names = trainable_names(d.layers, freeze_llm, vit_layers=0 if freeze_vision_tower else self.cfg.vit.layers)
         named = self.w.named
         self.layout, total = plan_flat([(n, named[n].numel()) for n in self.names])
         self.buckets = layer_buckets(self.names, self.layout, total)
@@ -267,46 +277,141 @@ class SFTTrainer:
         m = ops.swiglu_fwd(gu)
         return h1, qkv, att, x2, h2, gu, m
 
-    def _attention_backward(self, qkv: torch.Tensor, datt: torch.Tensor, b: int, s: int) -> torch.Tensor:
-        """dqkv [R, qkv_w] from datt [R, hidden]: per sequence and kv group, score tiles materialised per q head.
+    def _attention_backward(self, qkv: torch.Tensor, datt: torch.Tensor, b: int, s: int, heads: Optional[int] = None,
+                            kv_heads: Optional[int] = None, hd: Optional[int] = None, stride: Optional[int] = None,
+                            causal: bool = True) -> torch.Tensor:
+        """dqkv (layout of qkv) from datt [R, heads * hd]: per sequence and kv group, score tiles materialised per q head.
         dQ_h = dS_h K_g;  dK_g = sum_h dS_h^T Q_h;  dV_g = sum_h P_h^T dO_h (the sums run inside one GEMM over the
-        concatenated contraction dimension)."""
+        concatenated contraction dimension).  qkv holds [q heads | k heads | v heads] with `stride` columns per head of
+        which the first `hd` are used (decoder: 128 / 128; vision tower: 80 / 72, the pad columns keep a zero gradient)."""
         d = self.cfg.dec
-        hd, rep = d.head_dim, d.heads // d.kv_heads
+        heads = d.heads if heads is None else heads
+        kv_heads = d.kv_heads if kv_heads is None else kv_heads
+        hd = d.head_dim if hd is None else hd
+        stride = hd if stride is None else stride
+        rep = heads // kv_heads
+        k0, v0 = heads * stride, (heads + kv_heads) * stride
         scale = hd ** -0.5
-        dqkv = torch.empty_like(qkv)
+        sp = -(-s // 8) * 8                 # leading dimensions padded to 8 elements (TMA row-stride rule)
+        dqkv = torch.zeros_like(qkv) if (stride != hd) else torch.empty_like(qkv)
         bf = dict(dtype=torch.bfloat16, device=self.dev)
-        sc = torch.empty((s, s), dtype=torch.float32, device=self.dev)
-        dp = torch.empty_like(sc)
-        P = torch.empty((s, s), **bf)
-        dS = torch.empty((s, s), **bf)
-        pt_cat = torch.empty((s, rep * s), **bf)
-        dst_cat = torch.empty((s, rep * s), **bf)
-        dot_cat = torch.empty((hd, rep * s), **bf)
-        qt_cat = torch.empty((hd, rep * s), **bf)
-        kt = torch.empty((hd, s), **bf)
+        sc = torch.empty((s, sp), dtype=torch.float32, device=self.dev)[:, :s]
+        dp = torch.empty((s, sp), dtype=torch.float32, device=self.dev)[:, :s]
+        P = torch.empty((s, sp), **bf)[:, :s]
+        dS = torch.empty((s, sp), **bf)[:, :s]
+        # concatenated-contraction operands: the gap columns [s, sp) of every block stay zero on both sides
+        pt_cat = torch.zeros((s, rep * sp), **bf)
+        dst_cat = torch.zeros((s, rep * sp), **bf)
+        dot_cat = torch.zeros((hd, rep * sp), **bf)
+        qt_cat = torch.zeros((hd, rep * sp), **bf)
+        kt = torch.empty((hd, sp), **bf)[:, :s]
         for bi in range(b):
             rows = slice(bi * s, (bi + 1) * s)
-            for g in range(d.kv_heads):
-                k_g = qkv[rows, self.q_w + g * hd: self.q_w + (g + 1) * hd]
-                v_g = qkv[rows, self.q_w + self.kv_w + g * hd: self.q_w + self.kv_w + (g + 1) * hd]
+            for g in range(kv_heads):
+                k_g = qkv[rows, k0 + g * stride: k0 + g * stride + hd]
+                v_g = qkv[rows, v0 + g * stride: v0 + g * stride + hd]
                 ops.transpose(k_g, out=kt)
                 for j in range(rep):
                     h = g * rep + j
-                    q_h = qkv[rows, h * hd:(h + 1) * hd]
+                    q_h = qkv[rows, h * stride: h * stride + hd]
                     do_h = datt[rows, h * hd:(h + 1) * hd]
                     ops.gemm(q_h, k_g, out=sc, out_fp32=True)
                     ops.gemm(do_h, v_g, out=dp, out_fp32=True)
-                    ops.softmax_bwd(sc, dp, True, scale, P=P, dS=dS)
-                    ops.gemm(dS, kt, out=dqkv[rows, h * hd:(h + 1) * hd])
-                    ops.transpose(P, out=pt_cat[:, j * s:(j + 1) * s])
-                    ops.transpose(dS, out=dst_cat[:, j * s:(j + 1) * s])
-                    ops.transpose(do_h, out=dot_cat[:, j * s:(j + 1) * s])
-                    ops.transpose(q_h, out=qt_cat[:, j * s:(j + 1) * s])
-                ops.gemm(dst_cat, qt_cat, out=dqkv[rows, self.q_w + g * hd: self.q_w + (g + 1) * hd])
-                ops.gemm(pt_cat, dot_cat,
-                         out=dqkv[rows, self.q_w + self.kv_w + g * hd: self.q_w + self.kv_w + (g + 1) * hd])
+                    ops.softmax_bwd(sc, dp, causal, scale, P=P, dS=dS)
+                    ops.gemm(dS, kt, out=dqkv[rows, h * stride: h * stride + hd])
+                    ops.transpose(P, out=pt_cat[:, j * sp: j * sp + s])
+                    ops.transpose(dS, out=dst_cat[:, j * sp: j * sp + s])
+                    ops.transpose(do_h, out=dot_cat[:, j * sp: j * sp + s])
+                    ops.transpose(q_h, out=qt_cat[:, j * sp: j * sp + s])
+                ops.gemm(dst_cat, qt_cat, out=dqkv[rows, k0 + g * stride: k0 + g * stride + hd])
+                ops.gemm(pt_cat, dot_cat, out=dqkv[rows, v0 + g * stride: v0 + g * stride + hd])
         return dqkv
+
+    # ------------------------------------------------------------------ vision tower (trainable: freeze_vision_tower=False)
+    def _vit_weights(self, i: int):
+        n = self.w.named
+        return {k: n[f"vit.{i}.{k}"] for k in ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_g", "ln2_b", "fc1_w",
+                                               "fc1_b", "fc2_w", "fc2_b")}
+
+    def _vit_layer_forward(self, i: int, x: torch.Tensor, n_img: int, keep: bool):
+        """Same kernel sequence as vit_layers_impl (csrc/lp_model.cu), out of place."""
+        v, L = self.cfg.vit, self._vit_weights(i)
+        hs = self.w.vit_dims.head_stride
+        h = ops.layernorm(x, L["ln1_g"], L["ln1_b"], v.eps)
+        qkv = ops.gemm(h, L["qkv_w"], bias=L["qkv_b"])
+        att = ops.attention(qkv, n_img, v.tokens, v.heads, v.heads, v.head_dim, hs, 0, v.heads * hs, 2 * v.heads * hs, False,
+                            variant=self._attn_variant)
+        x2 = ops.gemm(att, L["out_w"], bias=L["out_b"], residual=x)
+        h2 = ops.layernorm(x2, L["ln2_g"], L["ln2_b"], v.eps)
+        a = ops.gemm(h2, L["fc1_w"], bias=L["fc1_b"], act=ops.ACT_GELU_TANH)
+        if not keep:
+            return ops.gemm(a, L["fc2_w"], bias=L["fc2_b"], residual=x2)
+        z = ops.gemm(h2, L["fc1_w"], bias=L["fc1_b"])         # pre-activation, for gelu'
+        return h, qkv, att, x2, h2, z, a
+
+    def _ln_bwd(self, gname: str, bname: str, x, gamma, dy, add=None) -> torch.Tensor:
+        v = self.cfg.vit
+        sg, sb = self._sink(gname), self._sink(bname)
+        if sb is sg and sg is not None:      # the two scratch tensors have the same shape while accumulating
+            sb = torch.empty_like(sg)
+        dx = ops.layernorm_bwd(x, gamma, dy, v.eps, sg, sb, add=add)
+        self._commit(gname, sg)
+        self._commit(bname, sb)
+        return dx
+
+    def _vit_layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, n_img: int) -> torch.Tensor:
+        v, L = self.cfg.vit, self._vit_weights(i)
+        hs = self.w.vit_dims.head_stride
+        p = f"vit.{i}."
+        h, qkv, att, x2, h2, z, a = self._vit_layer_forward(i, x, n_img, keep=True)
+        self._wgrad(p + "fc2_w", dy, a)
+        self._colsum(p + "fc2_b", dy)
+        da = self._dgrad(dy, L["fc2_w"])
+        dz = ops.gelu_bwd(z, da, ops.ACT_GELU_TANH)
+        del a, z, da
+        self._wgrad(p + "fc1_w", dz, h2)
+        self._colsum(p + "fc1_b", dz)
+        dh2 = self._dgrad(dz, L["fc1_w"])
+        del dz, h2
+        dx2 = self._ln_bwd(p + "ln2_g", p + "ln2_b", x2, L["ln2_g"], dh2, add=dy)
+        del dh2, x2
+        self._wgrad(p + "out_w", dx2, att)
+        self._colsum(p + "out_b", dx2)
+        datt = self._dgrad(dx2, L["out_w"])
+        dqkv = self._attention_backward(qkv, datt, n_img, v.tokens, heads=v.heads, kv_heads=v.heads, hd=v.head_dim,
+                                        stride=hs, causal=False)
+        del att, datt, qkv
+        self._wgrad(p + "qkv_w", dqkv, h)
+        self._colsum(p + "qkv_b", dqkv)
+        dh = self._dgrad(dqkv, L["qkv_w"])
+        del dqkv, h
+        return self._ln_bwd(p + "ln1_g", p + "ln1_b", x, L["ln1_g"], dh, add=dx2)
+
+    def _vit_forward_train(self, images: torch.Tensor):
+        """lp_vit_forward's sequence (im2col -> patch GEMM + bias + position rows -> layers -> ln_post with the shuffled
+        store), keeping the im2col matrix, the layer inputs and the final residual stream."""
+        v, w = self.cfg.vit, self.w.named
+        n_img = images.shape[0]
+        A = ops.im2col_patch14(images.to(self.dev).contiguous(), self.w.vit_dims.patch_k_pad)
+        x = ops.gemm(A, w["vit.patch_w"], bias=w["vit.patch_b"], residual=w["vit.pos"], res_row_mod=v.tokens)
+        xs = []
+        for i in range(v.layers):
+            xs.append(x)
+            x = self._vit_layer_forward(i, x, n_img, keep=False)
+        shuf = ops.layernorm(x, w["vit.post_g"], w["vit.post_b"], v.eps, shuffle_side=v.grid)
+        return shuf, (A, xs, x, n_img)
+
+    def _vit_backward(self, saved, dshuf: torch.Tensor, reduce):
+        v, w = self.cfg.vit, self.w.named
+        A, xs, x_last, n_img = saved
+        dx = self._ln_bwd("vit.post_g", "vit.post_b", x_last, w["vit.post_g"], ops.pixel_unshuffle(dshuf, v.grid))
+        for i in reversed(range(v.layers)):
+            dx = self._vit_layer_backward(i, xs.pop(), dx, n_img)
+        sink = self._sink("vit.pos")                    # the forward adds pos[row % tokens] to every crop
+        ops.rowmod_sum(dx, v.tokens, sink)
+        self._commit("vit.pos", sink)
+        self._colsum("vit.patch_b", dx)
+        self._wgrad("vit.patch_w", dx, A)               # [hidden, patch_k_pad]; the K-padding columns of A are zero
 
     def _layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, b: int, s: int) -> torch.Tensor:
         d = self.cfg.dec
@@ -401,8 +506,12 @@ class SFTTrainer:
         n_img_rows = int((ids == cfg.megatron_image_index).sum())
         have_images = images is not None and images.shape[-1] > 100 and n_img_rows > 0
         feats = shuf = z1 = a1 = None
+        vit_saved = None
         if have_images:
-            shuf = self.eng.vit(images, shuffle=True)
+            if self.freeze_vit:
+                shuf = self.eng.vit(images, shuffle=True)
+            else:
+                shuf, vit_saved = self._vit_forward_train(images)
             z1 = ops.gemm(shuf, w["proj.w1"], bias=w["proj.b1"])
             a1 = ops.gemm(shuf, w["proj.w1"], bias=w["proj.b1"], act=self.w.proj.act)
             feats = ops.gemm(a1, w["proj.w2"], bias=w["proj.b2"])
@@ -464,5 +573,10 @@ class SFTTrainer:
             self._wgrad("proj.w1", dz1, shuf)
             self._colsum("proj.b1", dz1)
         reduce(bucket)
+        if not self.freeze_vit:
+            bucket += 1
+            if have_images:
+                self._vit_backward(vit_saved, self._dgrad(dz1, w["proj.w1"]), reduce)
+            reduce(bucket)
         assert bucket == len(self.buckets) - 1
         return loss

@@ -69,6 +69,52 @@ def rmsnorm(x, gamma, eps, out=None):
     return _store(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * gamma, out)
 
 
+def _shuffle(y, side):
+    m, d = y.shape
+    half = side // 2
+    g = y.view(m // (side * side), half, 2, half, 2, d)
+    return g.permute(0, 1, 3, 2, 4, 5).reshape(m // 4, 4 * d)
+
+
+def layernorm(x, gamma, beta, eps, shuffle_side=0, out=None):
+    y = F.layer_norm(x.float(), (x.shape[1],), gamma, beta, eps)
+    return _store(_shuffle(y, shuffle_side) if shuffle_side else y, out)
+
+
+def layernorm_bwd(x, gamma, dy, eps, dgamma, dbeta, add=None, out=None):
+    xf, df = x.float(), dy.float()
+    mu = xf.mean(-1, keepdim=True)
+    r = torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+    xh = (xf - mu) * r
+    g = df * gamma
+    dx = r * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if add is not None:
+        dx = dx + add.float()
+    dgamma.copy_((df * xh).sum(0))
+    dbeta.copy_(df.sum(0))
+    return _store(dx, out)
+
+
+def pixel_unshuffle(d, side):
+    m4, d4 = d.shape
+    dd, half = d4 // 4, side // 2
+    g = d.view(m4 // (half * half), half, half, 2, 2, dd)          # [b, oh, ow, dy, dx, e]
+    return g.permute(0, 1, 3, 2, 4, 5).reshape(m4 * 4, dd).clone()  # [b, oh, dy, ow, dx, e]
+
+
+def rowmod_sum(d, T, out):
+    out.copy_(d.float().view(-1, T, d.shape[1]).sum(0))
+    return out
+
+
+def im2col_patch14(pixels, ldo=592):
+    n, c, h, w = pixels.shape
+    p = pixels.float().view(n, c, h // 14, 14, w // 14, 14).permute(0, 2, 4, 1, 3, 5).reshape(n * (h // 14) * (w // 14), c * 196)
+    out = torch.zeros((p.shape[0], ldo), dtype=BF)
+    out[:, : p.shape[1]] = p.to(BF)
+    return out
+
+
 def rope_table(pos, inv_freq):
     f = pos.float()[:, None] * inv_freq.float()[None, :]
     return f.cos(), f.sin()

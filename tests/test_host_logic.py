@@ -327,7 +327,7 @@ def test_named_to_hf_inverts_the_kernel_layout():
     ck = SyntheticCheckpoint(cfg, seed=9)
     nw = load_hf(cfg, lambda n: ck[n], device="cpu")
     back = named_to_hf(cfg, nw.named)
-    want = [n for n, _, _ in tensor_specs(cfg) if not n.startswith("vision_tower.")]
+    want = [n for n, _, _ in tensor_specs(cfg)]
     assert sorted(back) == sorted(want)
     for n in want:
         assert back[n].shape == ck[n].shape and torch.equal(back[n].to(torch.bfloat16), ck[n]), n

@@ -295,3 +295,46 @@ def test_gradient_accumulation_over_micro_batches(cpu_trainer):
     assert abs(loss - 0.5 * (losses[0] + losses[1])) < 1e-3 * abs(loss)
     assert float((tr.flat_grad - want).norm() / want.norm()) < 0.01
     assert abs(norm - float(want.double().norm())) < 1e-4 * norm and tr.iteration == 1     # fp64: 2e8 addends
+
+
+def test_unfrozen_vision_tower_backward_matches_autograd_oracle(cpu_trainer):
+    """freeze_vision_tower=False: the tower's forward is re-sequenced in train.py (saved layer inputs) and its backward runs
+    through LayerNorm / GELU / bias / position-embedding / patch-embedding gradients and the per-(crop, head) attention
+    backward on the zero-padded 80-wide head layout."""
+    cfg = reduced(leopard_llava(), vit_layers=2, dec_layers=1, vocab=320)
+    ck = SyntheticCheckpoint(cfg, seed=13)
+    nw = load_hf(cfg, lambda n: ck[n], device="cpu")
+    eng = _FakeEngine(cfg, ck, nw)
+    tokens, labels, weights, images = _batch(cfg, b=1, n_text=15, seed=6)
+    ock = OT.TrainableCheckpoint(ck)
+    ref_loss, ref = OT.sft_loss_and_grads(ock, cfg, tokens, labels, weights, images)
+    ref_hf = {k: v for k, v in ref.items()}
+
+    tr = T.SFTTrainer(eng, lr=0.0, freeze_vision_tower=False)
+    assert len(tr.buckets) == 1 + cfg.dec.layers + 3
+    loss, norm = tr.step(tokens, labels, weights, images)
+    assert abs(loss - ref_loss) < 0.02 * abs(ref_loss)
+    assert abs(norm - OT.global_grad_norm(ref.values())) < 0.03 * norm
+
+    # bring the trainer's gradients back to HF names with the same inverse re-layout the checkpoint export uses
+    from leopard_b200.native_weights import named_to_hf
+    got = named_to_hf(cfg, {n: tr.grad(n) for n in tr.names})
+    bad = {}
+    for name, want in ref_hf.items():
+        g = got[name].float()
+        assert g.shape == want.shape, name
+        if name.endswith("self_attn.k_proj.bias"):
+            # softmax is invariant to a per-query constant, so this gradient is exactly 0 in exact arithmetic: what is left
+            # on both sides is rounding noise — it only has to be small next to the query bias's gradient
+            qn = float(ref_hf[name.replace("k_proj", "q_proj")].norm())
+            assert float(want.norm()) < 1e-3 * qn and float(g.norm()) < 0.05 * qn, (name, float(g.norm()), qn)
+            continue
+        e = float((g - want).norm() / (want.norm() + 1e-12))
+        if e > 0.06:
+            bad[name] = e
+    assert not bad, bad
+    # the zero padding of the 80-wide head layout and of the patch-embedding K dimension receives exactly zero gradient
+    qg = tr.grad("vit.1.qkv_w").view(3, cfg.vit.heads, 80, -1)
+    assert float(qg[:, :, 72:].abs().max()) == 0.0
+    assert float(tr.grad("vit.0.qkv_b").view(3, cfg.vit.heads, 80)[:, :, 72:].abs().max()) == 0.0
+    assert float(tr.grad("vit.patch_w")[:, cfg.vit.patch_k:].abs().max()) == 0.0
