@@ -154,6 +154,50 @@ def test_whole_sft_step_against_autograd_oracle(native_lib):
     assert loss2 < loss
 
 
+def test_vision_tower_backward_kernels(native_lib):
+    for M, D in ((676, 1152), (50, 4096), (3, 64)):
+        x, dy, add = _rand(M, D, seed=1, scale=3.0), _rand(M, D, seed=2), _rand(M, D, seed=3)
+        gamma = 1 + _rand(D, seed=4, scale=0.1, dtype=torch.float32)
+        wg, wb = torch.empty(D), torch.empty(D)
+        gg, gb = torch.empty(D, device=DEV), torch.empty(D, device=DEV)
+        want = ref_ops.layernorm_bwd(x, gamma, dy, 1e-6, wg, wb, add=add)
+        got = ops.layernorm_bwd(x.to(DEV), gamma.to(DEV), dy.to(DEV), 1e-6, gg, gb, add=add.to(DEV))
+        assert _err(got, want) < 1e-2 and _err(gg, wg) < 2e-3 and _err(gb, wb) < 2e-3, (M, D)
+    d = _rand(2 * 169, 4 * 1152, seed=5)
+    un = ops.pixel_unshuffle(d.to(DEV), 26)
+    assert torch.equal(un.cpu(), ref_ops.pixel_unshuffle(d, 26))
+    assert torch.equal(ops.pixel_shuffle(un, 26).cpu(), d)                      # inverse of the forward kernel
+    dx = _rand(3 * 676, 1152, seed=6)
+    got = ops.rowmod_sum(dx.to(DEV), 676, torch.empty((676, 1152), device=DEV))
+    assert _err(got, dx.float().view(3, 676, 1152).sum(0)) < 1e-6
+    a, b = _rand(1_000_003, seed=7, dtype=torch.float32), _rand(1_000_003, seed=8, dtype=torch.float32)
+    assert torch.equal(ops.accumulate(a.to(DEV), b.to(DEV)).cpu(), a + b)
+
+
+def test_whole_sft_step_with_trainable_vision_tower(native_lib):
+    from leopard_b200.engine import PrefillEngine
+    from leopard_b200.native_weights import named_to_hf
+    from leopard_b200.train import SFTTrainer
+    from test_train_glue import _batch
+    cfg = reduced(leopard_llava(), vit_layers=2, dec_layers=1, vocab=320)
+    ck = SyntheticCheckpoint(cfg, seed=13)
+    eng = PrefillEngine(cfg, load_hf(cfg, lambda n: ck[n], DEV))
+    tokens, labels, weights, images = _batch(cfg, b=1, n_text=15, seed=6)
+    ref_loss, ref = OT.sft_loss_and_grads(OT.TrainableCheckpoint(ck), cfg, tokens, labels, weights, images)
+    tr = SFTTrainer(eng, lr=0.0, freeze_vision_tower=False)
+    loss, norm = tr.step(tokens, labels, weights, images.to(DEV))
+    assert abs(loss - ref_loss) < 0.03 * abs(ref_loss)
+    got = named_to_hf(cfg, {n: tr.grad(n) for n in tr.names})
+    bad = {}
+    for name, want in ref.items():
+        if name.endswith("self_attn.k_proj.bias"):       # exactly zero in exact arithmetic (see test_train_glue.py)
+            continue
+        e = float((got[name].float().cpu() - want).norm() / (want.norm() + 1e-12))
+        if e > 0.08:
+            bad[name] = e
+    assert not bad, bad
+
+
 # ---- flash-style attention backward (lp_attn_bwd.cu): kept LAST — a wedged tcgen05 pipeline traps and poisons the context
 def _attn_case(B, T, heads, kv_heads, seed):
     hd = 128
