@@ -353,16 +353,18 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
  *                    lp_grad_norm_workspace_bytes() bytes) -> out2 = {norm, clip coefficient} in device memory.
  * lp_adamw_step:     FusedAdam (adam_w_mode) on fp32 main params with the gradient scaled by out2[1]; also refreshes
  *                    the bf16 model copy (p_bf16 may be NULL).  step counts from 1. */
-/* Flash-style attention backward (tcgen05; causal or full, head_dim 128) — SECOND implementation of attention backward,
+/* Flash-style attention backward (tcgen05; (head_dim, head_stride) = (128, 128) causal or full, or (72, 80) full — the
+ * vision tower's zero-padded head layout, whose padding columns of dqkv are written as zeros) — SECOND implementation,
  * compiled but not yet run on hardware; train.py selects it with LEOPARD_ATTN_BWD=flash.  Replaces autograd through
  * flash_attn_varlen_func (MP/model/llava/transformer.py:476-515,869-877).  qkv / dqkv: [B*T, ld] rows with the q heads at
- * q_off, k heads at k_off, v heads at v_off (head stride 128); out / dout: [B*T, ldo] forward output and its gradient.
+ * q_off, k heads at k_off, v heads at v_off (head_stride columns each); out / dout: [B*T, ldo] forward output and its
+ * gradient (head_dim columns per head).
  * dqkv receives dQ, dK, dV in the qkv column layout (dK / dV summed over the q heads of each kv group, scale applied).
  * Deterministic (no atomics).  The row log-sum-exp is recomputed inside (no forward change needed). */
 size_t lp_attention_bwd_workspace_bytes(int B, int T, int n_heads);
 int lp_attention_bwd(const void* qkv, long long ld, const void* out, const void* dout, long long ldo, int B, int T,
-                     int n_heads, int n_kv_heads, int head_dim, int q_off, int k_off, int v_off, int causal, float scale,
-                     void* dqkv, long long ldd, void* workspace, size_t ws_bytes, void* stream);
+                     int n_heads, int n_kv_heads, int head_dim, int head_stride, int q_off, int k_off, int v_off, int causal,
+                     float scale, void* dqkv, long long ldd, void* workspace, size_t ws_bytes, void* stream);
 int lp_transpose_bf16(const void* in, long long ld_in, int rows, int cols, void* out, long long ld_out, void* stream);
 /* Vision-tower backward pieces: LayerNorm backward (dx (+ add), dgamma, dbeta; fixed summation order), the inverse of the
  * pixel shuffle (gradient of lp_pixel_shuffle / lp_layernorm's shuffled store, EV :165-176), and the position-embedding

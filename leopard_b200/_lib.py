@@ -99,7 +99,7 @@ _SIGS = {
     "lp_image_frontend": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
     "lp_decode_debug_stamps": (_i, [_vp]),
     "lp_attention_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
-    "lp_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp, _sz, _vp]),
+    "lp_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp, _sz, _vp]),
     "lp_transpose_bf16": (_i, [_vp, _ll, _i, _i, _vp, _ll, _vp]),
     "lp_layernorm_bwd_workspace_bytes": (_sz, [_i]),
     "lp_layernorm_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _sz, _vp]),

@@ -1,4 +1,5 @@
-// leopard_b200 — tcgen05 flash-attention BACKWARD for the decoder's causal GQA attention (head_dim 128), sm_100a.
+// leopard_b200 — tcgen05 flash-attention BACKWARD, sm_100a: the decoder's causal GQA attention (head_dim 128) and the vision
+// tower's full attention (head_dim 72 in the zero-padded 80-wide head layout of the fused qkv buffer).
 //
 // STATUS: written and compiled after the round's GPU budget was spent — NOT yet run on hardware.  train.py keeps using
 // the materialised per-head backward (lp_softmax_bwd) until this one has passed tools/gpu_check_attn_bwd.py.
@@ -32,7 +33,9 @@ constexpr int AB_KS = 8;                  // K = 16 steps per 128-deep contracti
 struct AttnBwdArgs {
   int T, B, n_heads, group, Tpad;
   int q_off, k_off, v_off;                // column offsets of the q / k / v blocks inside a qkv (and dqkv) row
-  const bf16* O;                          // forward output [B*T, n_heads*128]
+  int hs;                                 // columns per head in qkv / dqkv (128, or 80 = 72 + zero padding)
+  int dho;                                // columns per head in O / dO (128 or 72)
+  const bf16* O;                          // forward output [B*T, n_heads*dho]
   const bf16* dO;                         // its gradient, same layout
   long long ldo;
   bf16* dqkv;                             // [B*T, ldd], same column layout as qkv
@@ -57,40 +60,46 @@ __device__ __forceinline__ float bw_ex2(float x) {
       "r"(regs[14]), "r"(regs[15])                                                                                  \
       : "memory")
 
-// D[128 x 128] (+)= A[128 x 128] B^T, both K-major 128B-swizzled tiles of two boxes (the forward's S = Q K^T form)
+// D[128 x 128] (+)= A[128 x DH] B[128 x DH]^T, both K-major 128B-swizzled tiles of two boxes (the forward's S = Q K^T form)
+template <int DH>
 __device__ __forceinline__ void mma_ss_kmajor(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
   constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_T, 0, 0);
 #pragma unroll
-  for (int ks = 0; ks < AB_KS; ++ks) {
+  for (int ks = 0; ks < DH / 16; ++ks) {   // contraction over the head dimension: DH / 16 steps (8, or 5 for the 80-wide layout)
     const uint32_t off = (ks >> 2) * AB_BOX + (ks & 3) * 32;
     umma_ss(d_tmem, umma_desc_sw128(a_addr + off, 0, 1024), umma_desc_sw128(b_addr + off, 0, 1024), idesc, ks > 0 ? 1u : 0u);
   }
 }
-// D[128 x 128] (+)= A[128 x 128 bf16 in TMEM, 64 columns] B, B = a [128 rows = contraction, 128 contiguous] tile read as an
+// D[128 x DH] (+)= A[128 x 128 bf16 in TMEM, 64 columns] B, B = a [128 rows = contraction, DH contiguous] tile read as an
 // MN-major operand (the forward's O += P V form: 16 contraction rows = 2 KiB per K step, LBO = next 64-wide slab)
+template <int DH>
 __device__ __forceinline__ void mma_ts_mnmajor(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, bool accumulate) {
-  constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_T, 0, 1);
+  constexpr uint32_t idesc = umma_idesc_bf16(AB_T, DH, 0, 1);
 #pragma unroll
   for (int ks = 0; ks < AB_KS; ++ks)
     umma_ts(d_tmem, a_tmem + ks * 8, umma_desc_sw128(b_addr + ks * 2048, AB_BOX, 1024), idesc,
             (accumulate || ks > 0) ? 1u : 0u);
 }
 
-// one thread's 128 fp32 accumulators (TMEM lane) -> bf16 row in global memory
-__device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok) {
+// one thread's DH fp32 accumulators (TMEM lane) -> bf16 row in global memory; columns >= valid are written as zeros
+// (dV of the 80-wide layout: its last 8 columns would otherwise carry the next head's dO through the wide TMA box)
+template <int DH>
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok, int valid) {
 #pragma unroll 1
-  for (int c = 0; c < AB_T / 16; ++c) {
+  for (int c = 0; c < DH / 16; ++c) {
     uint32_t o[16];
     LP_TMEM_LD_16(o, taddr + c * 16);
     tmem_wait_ld();
     if (ok) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
-        u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
-        u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
-        u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (c * 16 + g * 8 < valid) {    // valid is a multiple of 8
+          u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+        }
         *reinterpret_cast<uint4*>(dst + c * 16 + g * 8) = u;
       }
     }
@@ -98,7 +107,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok
 }
 
 // ---------------------------------------------------------------------------------------------------------------- dQ
-template <bool CAUSAL>
+template <int DH, bool CAUSAL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdArgs args) {
@@ -161,8 +170,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_arrive_expect_tx(q_full, 2 * AB_HEAD);
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        tma_load_3d(smem + Q_OFF + b * AB_BOX, &tmQKV, q_full, args.q_off + head * AB_T + b * 64, q0, batch);
-        tma_load_3d(smem + DO_OFF + b * AB_BOX, &tmDO, q_full, head * AB_T + b * 64, q0, batch);
+        tma_load_3d(smem + Q_OFF + b * AB_BOX, &tmQKV, q_full, args.q_off + head * args.hs + b * 64, q0, batch);
+        tma_load_3d(smem + DO_OFF + b * AB_BOX, &tmDO, q_full, head * args.dho + b * 64, q0, batch);
       }
       int kt = 0;   // K tiles loaded so far (both passes share the ring)
       for (int pass = 0; pass < 2; ++pass) {
@@ -173,7 +182,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
           for (int b = 0; b < 2; ++b)
             tma_load_3d(smem + K_OFF + st * AB_HEAD + b * AB_BOX, &tmQKV, &k_full[st],
-                        args.k_off + kv_head * AB_T + b * 64, j * AB_T, batch);
+                        args.k_off + kv_head * args.hs + b * 64, j * AB_T, batch);
           if (pass == 1) {
             const int vs = j & 1;
             mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
@@ -181,7 +190,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
             for (int b = 0; b < 2; ++b)
               tma_load_3d(smem + V_OFF + vs * AB_HEAD + b * AB_BOX, &tmQKV, &v_full[vs],
-                          args.v_off + kv_head * AB_T + b * 64, j * AB_T, batch);
+                          args.v_off + kv_head * args.hs + b * 64, j * AB_T, batch);
           }
         }
       }
@@ -198,7 +207,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(&k_full[st], (kt >> 1) & 1);
         if (j >= 2) mbar_wait(&s_done[j & 1], ((j - 2) >> 1) & 1);
         tc_fence_after();
-        mma_ss_kmajor(tmem_base + (uint32_t)(j & 1) * 128, q_addr, smem_u32(smem + K_OFF + st * AB_HEAD));
+        mma_ss_kmajor<DH>(tmem_base + (uint32_t)(j & 1) * 128, q_addr, smem_u32(smem + K_OFF + st * AB_HEAD));
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
       }
@@ -215,12 +224,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(&v_full[vs], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem + K_OFF + st * AB_HEAD);
-        mma_ss_kmajor(tmem_base + TM_S, q_addr, k_addr);                                   // S_j  = Q  K_j^T
-        mma_ss_kmajor(tmem_base + TM_DP, do_addr, smem_u32(smem + V_OFF + vs * AB_HEAD));  // dP_j = dO V_j^T
+        mma_ss_kmajor<DH>(tmem_base + TM_S, q_addr, k_addr);                                   // S_j  = Q  K_j^T
+        mma_ss_kmajor<DH>(tmem_base + TM_DP, do_addr, smem_u32(smem + V_OFF + vs * AB_HEAD));  // dP_j = dO V_j^T
         umma_commit(sdp_full);
         mbar_wait(ds_full, j & 1);
         tc_fence_after();
-        mma_ts_mnmajor(tmem_base + TM_DQ, tmem_base + TM_S, k_addr, j > 0);                // dQ += dS_j K_j
+        mma_ts_mnmajor<DH>(tmem_base + TM_DQ, tmem_base + TM_S, k_addr, j > 0);                // dQ += dS_j K_j
         umma_commit(&k_empty[st]);
         umma_commit(&v_empty[vs]);
         umma_commit(dq_done);
@@ -269,13 +278,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_arrive(&s_done[j & 1]);
     }
     const float lse2 = (l > 0.f) ? m + log2f(l) : 0.f;   // l == 0 only for rows without a valid key (padding rows)
-    // ---- delta = rowsum(dO * O) from global memory (two 256-byte rows per thread)
+    // ---- delta = rowsum(dO * O) from global memory (two head rows of 256 or 144 bytes per thread)
     float delta = 0.f;
     if (row_ok) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(args.O + ((long long)batch * T + q_idx) * args.ldo + head * AB_T);
-      const uint4* d4 = reinterpret_cast<const uint4*>(args.dO + ((long long)batch * T + q_idx) * args.ldo + head * AB_T);
+      const uint4* o4 = reinterpret_cast<const uint4*>(args.O + ((long long)batch * T + q_idx) * args.ldo + head * args.dho);
+      const uint4* d4 = reinterpret_cast<const uint4*>(args.dO + ((long long)batch * T + q_idx) * args.ldo + head * args.dho);
+      const int n8 = args.dho >> 3;   // 16 or 9 sixteen-byte chunks per head row
 #pragma unroll 4
-      for (int c = 0; c < AB_T / 8; ++c) {
+      for (int c = 0; c < n8; ++c) {
         const uint4 a = o4[c], b = d4[c];
         const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
         const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
@@ -320,8 +330,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     // ---- epilogue: dQ row -> global
     mbar_wait(dq_done, (n_kv - 1) & 1);
     tc_fence_after();
-    store_acc_row(lane_addr + TM_DQ,
-                  args.dqkv + ((long long)batch * T + q_idx) * args.ldd + args.q_off + (long long)head * AB_T, row_ok);
+    store_acc_row<DH>(lane_addr + TM_DQ,
+                      args.dqkv + ((long long)batch * T + q_idx) * args.ldd + args.q_off + (long long)head * args.hs, row_ok, DH);
   }
 
   tc_fence_before();
@@ -333,7 +343,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------- dK, dV
-template <bool CAUSAL>
+template <int DH, bool CAUSAL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdArgs args) {
@@ -391,8 +401,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_arrive_expect_tx(kv_full, 2 * AB_HEAD);
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        tma_load_3d(smem + K_OFF + b * AB_BOX, &tmQKV, kv_full, args.k_off + kv_head * AB_T + b * 64, kv0, batch);
-        tma_load_3d(smem + V_OFF + b * AB_BOX, &tmQKV, kv_full, args.v_off + kv_head * AB_T + b * 64, kv0, batch);
+        tma_load_3d(smem + K_OFF + b * AB_BOX, &tmQKV, kv_full, args.k_off + kv_head * args.hs + b * 64, kv0, batch);
+        tma_load_3d(smem + V_OFF + b * AB_BOX, &tmQKV, kv_full, args.v_off + kv_head * args.hs + b * 64, kv0, batch);
       }
       for (int t = 0; t < n_steps; ++t) {
         const int st = t & 1;
@@ -401,9 +411,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         mbar_arrive_expect_tx(&qd_full[st], 2 * AB_HEAD);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          tma_load_3d(smem + Q_OFF + st * AB_HEAD + b * AB_BOX, &tmQKV, &qd_full[st], args.q_off + head * AB_T + b * 64,
+          tma_load_3d(smem + Q_OFF + st * AB_HEAD + b * AB_BOX, &tmQKV, &qd_full[st], args.q_off + head * args.hs + b * 64,
                       qi * AB_T, batch);
-          tma_load_3d(smem + DO_OFF + st * AB_HEAD + b * AB_BOX, &tmDO, &qd_full[st], head * AB_T + b * 64, qi * AB_T, batch);
+          tma_load_3d(smem + DO_OFF + st * AB_HEAD + b * AB_BOX, &tmDO, &qd_full[st], head * args.dho + b * 64, qi * AB_T, batch);
         }
       }
     }
@@ -417,13 +427,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         mbar_wait(&qd_full[st], (t >> 1) & 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(smem + Q_OFF + st * AB_HEAD), do_addr = smem_u32(smem + DO_OFF + st * AB_HEAD);
-        mma_ss_kmajor(tmem_base + TM_ST, k_addr, q_addr);      // S^T  = K  Q^T   (kv rows on the lanes)
-        mma_ss_kmajor(tmem_base + TM_DPT, v_addr, do_addr);    // dP^T = V dO^T
+        mma_ss_kmajor<DH>(tmem_base + TM_ST, k_addr, q_addr);      // S^T  = K  Q^T   (kv rows on the lanes)
+        mma_ss_kmajor<DH>(tmem_base + TM_DPT, v_addr, do_addr);    // dP^T = V dO^T
         umma_commit(st_full);
         mbar_wait(pd_full, t & 1);
         tc_fence_after();
-        mma_ts_mnmajor(tmem_base + TM_DV, tmem_base + TM_ST, do_addr, t > 0);   // dV += P^T  dO
-        mma_ts_mnmajor(tmem_base + TM_DK, tmem_base + TM_DPT, q_addr, t > 0);   // dK += dS^T Q
+        mma_ts_mnmajor<DH>(tmem_base + TM_DV, tmem_base + TM_ST, do_addr, t > 0);   // dV += P^T  dO
+        mma_ts_mnmajor<DH>(tmem_base + TM_DK, tmem_base + TM_DPT, q_addr, t > 0);   // dK += dS^T Q
         umma_commit(&qd_empty[st]);
         umma_commit(acc_done);
       }
@@ -479,9 +489,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     }
     mbar_wait(acc_done, (n_steps - 1) & 1);
     tc_fence_after();
-    bf16* row = args.dqkv + ((long long)batch * T + kv_idx) * args.ldd + (long long)kv_head * AB_T;
-    store_acc_row(lane_addr + TM_DV, row + args.v_off, kv_ok);
-    store_acc_row(lane_addr + TM_DK, row + args.k_off, kv_ok);
+    bf16* row = args.dqkv + ((long long)batch * T + kv_idx) * args.ldd + (long long)kv_head * args.hs;
+    store_acc_row<DH>(lane_addr + TM_DV, row + args.v_off, kv_ok, args.dho);   // columns dho .. DH-1 (padding): zeros
+    store_acc_row<DH>(lane_addr + TM_DK, row + args.k_off, kv_ok, DH);
   }
 
   tc_fence_before();
@@ -501,14 +511,36 @@ extern "C" size_t lp_attention_bwd_workspace_bytes(int B, int T, int n_heads) {
   return 2 * (size_t)B * (size_t)n_heads * tpad * sizeof(float) + 256;
 }
 
+template <int DH, bool CAUSAL>
+static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& td, const AttnBwdArgs& a, int n_kv_heads,
+                           cudaStream_t stream) {
+  constexpr int SMEM_DQ = 6 * AB_HEAD + 256 + 1024;
+  constexpr int SMEM_DKV = 6 * AB_HEAD + 2 * 2 * AB_T * 4 + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
+    LP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
+    configured = true;
+  }
+  const int tiles = (a.T + AB_T - 1) / AB_T;
+  attn_bwd_dq_kernel<DH, CAUSAL><<<dim3(tiles, a.n_heads, a.B), AB_THREADS, SMEM_DQ, stream>>>(tq, td, a);
+  LP_CHECK_CUDA(cudaGetLastError());
+  attn_bwd_dkv_kernel<DH, CAUSAL><<<dim3(tiles, n_kv_heads, a.B), AB_THREADS, SMEM_DKV, stream>>>(tq, td, a);
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lp_attention_bwd(const void* qkv, long long ld, const void* out, const void* dout, long long ldo, int B, int T,
-                                int n_heads, int n_kv_heads, int head_dim, int q_off, int k_off, int v_off, int causal,
-                                float scale, void* dqkv, long long ldd, void* workspace, size_t ws_bytes, void* stream_) {
+                                int n_heads, int n_kv_heads, int head_dim, int head_stride, int q_off, int k_off, int v_off,
+                                int causal, float scale, void* dqkv, long long ldd, void* workspace, size_t ws_bytes,
+                                void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LP_REQUIRE(qkv && out && dout && dqkv && workspace, "lp_attention_bwd: null argument");
   LP_REQUIRE(B > 0 && T > 0 && n_heads > 0 && n_kv_heads > 0 && n_heads % n_kv_heads == 0,
              "lp_attention_bwd: bad sizes B=%d T=%d heads=%d/%d", B, T, n_heads, n_kv_heads);
-  LP_REQUIRE(head_dim == 128, "lp_attention_bwd: head_dim must be 128 (got %d)", head_dim);
+  LP_REQUIRE((head_dim == 72 && head_stride == 80) || (head_dim == 128 && head_stride == 128),
+             "lp_attention_bwd: supported (head_dim, head_stride) are (72, 80) [zero-padded] and (128, 128); got (%d, %d)",
+             head_dim, head_stride);
   LP_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ldd % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
              "lp_attention_bwd: leading dimensions and offsets must be multiples of 8 elements");
   LP_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
@@ -520,6 +552,8 @@ extern "C" int lp_attention_bwd(const void* qkv, long long ld, const void* out, 
   a.T = T; a.B = B; a.n_heads = n_heads; a.group = n_heads / n_kv_heads;
   a.Tpad = (T + AB_T - 1) / AB_T * AB_T;
   a.q_off = q_off; a.k_off = k_off; a.v_off = v_off;
+  a.hs = head_stride;
+  a.dho = head_dim;
   a.O = reinterpret_cast<const bf16*>(out);
   a.dO = reinterpret_cast<const bf16*>(dout);
   a.ldo = ldo;
@@ -534,27 +568,11 @@ extern "C" int lp_attention_bwd(const void* qkv, long long ld, const void* out, 
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&td, dout, (uint64_t)ldo, (uint64_t)T, (uint64_t)B, (uint64_t)ldo, (uint64_t)T * ldo, 64, 128, 1);
   if (rc) return rc;
-  constexpr int SMEM_DQ = 6 * AB_HEAD + 256 + 1024;
-  constexpr int SMEM_DKV = 6 * AB_HEAD + 2 * 2 * AB_T * 4 + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    LP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
-    LP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
-    LP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
-    LP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
-    configured = true;
-  }
-  const int tiles = (T + AB_T - 1) / AB_T;
   note_launch(2);
-  if (causal) {
-    attn_bwd_dq_kernel<true><<<dim3(tiles, n_heads, B), AB_THREADS, SMEM_DQ, stream>>>(tq, td, a);
-    LP_CHECK_CUDA(cudaGetLastError());
-    attn_bwd_dkv_kernel<true><<<dim3(tiles, n_kv_heads, B), AB_THREADS, SMEM_DKV, stream>>>(tq, td, a);
-  } else {
-    attn_bwd_dq_kernel<false><<<dim3(tiles, n_heads, B), AB_THREADS, SMEM_DQ, stream>>>(tq, td, a);
-    LP_CHECK_CUDA(cudaGetLastError());
-    attn_bwd_dkv_kernel<false><<<dim3(tiles, n_kv_heads, B), AB_THREADS, SMEM_DKV, stream>>>(tq, td, a);
+  if (head_dim == 72) {
+    LP_REQUIRE(!causal, "lp_attention_bwd: head_dim 72 is the (non-causal) vision-tower configuration");
+    return launch_attn_bwd<80, false>(tq, td, a, n_kv_heads, stream);
   }
-  LP_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return causal ? launch_attn_bwd<128, true>(tq, td, a, n_kv_heads, stream)
+                : launch_attn_bwd<128, false>(tq, td, a, n_kv_heads, stream);
 }

@@ -385,7 +385,8 @@ def adamw_step(p, g, m, v, p16, step, lr, beta1, beta2, eps, weight_decay, norm_
 _attn_bwd_ws = {}
 
 
-def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_off, v_off, causal, scale=None, dqkv=None):
+def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_off, v_off, causal, scale=None, dqkv=None,
+                  head_stride=None):
     """Flash-style backward of `attention` (lp_attention_bwd): returns dqkv in the qkv column layout."""
     _chk_bf16(qkv, "qkv")
     _chk_bf16(out, "out")
@@ -403,7 +404,8 @@ def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_
         ws = torch.empty(need, dtype=torch.uint8, device=qkv.device)
         _attn_bwd_ws[qkv.device] = ws
     rc = L.lp_attention_bwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(out), _lib.ptr(dout), out.stride(0), B, T, n_heads,
-                            n_kv_heads, head_dim, q_off, k_off, v_off, 1 if causal else 0, float(scale), _lib.ptr(dqkv),
+                            n_kv_heads, head_dim, head_stride or head_dim, q_off, k_off, v_off, 1 if causal else 0,
+                            float(scale), _lib.ptr(dqkv),
                             dqkv.stride(0), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "lp_attention_bwd")
     return dqkv

@@ -378,8 +378,12 @@ class SFTTrainer:
         self._wgrad(p + "out_w", dx2, att)
         self._colsum(p + "out_b", dx2)
         datt = self._dgrad(dx2, L["out_w"])
-        dqkv = self._attention_backward(qkv, datt, n_img, v.tokens, heads=v.heads, kv_heads=v.heads, hd=v.head_dim,
-                                        stride=hs, causal=False)
+        if self.attn_bwd == "flash":
+            dqkv = ops.attention_bwd(qkv, att, datt, n_img, v.tokens, v.heads, v.heads, v.head_dim, 0, v.heads * hs,
+                                     2 * v.heads * hs, False, head_stride=hs)
+        else:
+            dqkv = self._attention_backward(qkv, datt, n_img, v.tokens, heads=v.heads, kv_heads=v.heads, hd=v.head_dim,
+                                            stride=hs, causal=False)
         del att, datt, qkv
         self._wgrad(p + "qkv_w", dqkv, h)
         self._colsum(p + "qkv_b", dqkv)

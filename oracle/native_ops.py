@@ -240,22 +240,32 @@ def adamw_step(p, g, m, v, p16, step, lr, beta1, beta2, eps, weight_decay, norm_
         p16.copy_(p.view(p16.shape))
 
 
-def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_off, v_off, causal, scale=None, dqkv=None):
-    """dqkv in the qkv column layout (head stride = head_dim): closed form of oracle/train.py attention_bwd per sequence."""
+def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_off, v_off, causal, scale=None, dqkv=None,
+                  head_stride=None):
+    """dqkv in the qkv column layout (head_stride columns per head, the first head_dim used; padding columns get zeros):
+    closed form of oracle/train.py attention_bwd per sequence."""
     from . import train as OT
     scale = head_dim ** -0.5 if scale is None else scale
+    hs = head_stride or head_dim
     if dqkv is None:
         dqkv = torch.zeros_like(qkv)
     x = qkv.float().view(B, T, -1)
     do = dout.float().view(B, T, n_heads, head_dim)
+
+    def heads(xb, off, n):
+        return xb[:, off: off + n * hs].reshape(T, n, hs)[:, :, :head_dim]
+
+    def put(rows, off, n, g):
+        full = torch.zeros((T, n, hs))
+        full[:, :, :head_dim] = g
+        dqkv[rows, off: off + n * hs] = full.reshape(T, -1).to(dqkv.dtype)
+
     for b in range(B):
-        q = x[b, :, q_off: q_off + n_heads * head_dim].reshape(T, n_heads, head_dim)
-        k = x[b, :, k_off: k_off + n_kv_heads * head_dim].reshape(T, n_kv_heads, head_dim)
-        v = x[b, :, v_off: v_off + n_kv_heads * head_dim].reshape(T, n_kv_heads, head_dim)
+        q, k, v = heads(x[b], q_off, n_heads), heads(x[b], k_off, n_kv_heads), heads(x[b], v_off, n_kv_heads)
         o, lse = OT.attention_fwd(q, k, v, causal, scale)
         dq, dk, dv = OT.attention_bwd(q, k, v, o, lse, do[b], causal, scale)
         rows = slice(b * T, (b + 1) * T)
-        dqkv[rows, q_off: q_off + n_heads * head_dim] = dq.reshape(T, -1).to(dqkv.dtype)
-        dqkv[rows, k_off: k_off + n_kv_heads * head_dim] = dk.reshape(T, -1).to(dqkv.dtype)
-        dqkv[rows, v_off: v_off + n_kv_heads * head_dim] = dv.reshape(T, -1).to(dqkv.dtype)
+        put(rows, q_off, n_heads, dq)
+        put(rows, k_off, n_kv_heads, dk)
+        put(rows, v_off, n_kv_heads, dv)
     return dqkv

@@ -338,3 +338,7 @@ def test_unfrozen_vision_tower_backward_matches_autograd_oracle(cpu_trainer):
     assert float(qg[:, :, 72:].abs().max()) == 0.0
     assert float(tr.grad("vit.0.qkv_b").view(3, cfg.vit.heads, 80)[:, :, 72:].abs().max()) == 0.0
     assert float(tr.grad("vit.patch_w")[:, cfg.vit.patch_k:].abs().max()) == 0.0
+    # the flash route (one lp_attention_bwd call per layer, (72, 80) head layout) is fed consistently with the per-head one
+    tr2 = T.SFTTrainer(eng, lr=0.0, freeze_vision_tower=False, attn_bwd="flash")
+    tr2.step(tokens, labels, weights, images)
+    assert float((tr2.flat_grad - tr.flat_grad).norm() / tr.flat_grad.norm()) < 0.02

@@ -220,6 +220,22 @@ def test_flash_attention_backward_against_closed_form(native_lib, B, T, heads, k
     assert torch.equal(got, again)                                  # deterministic: no atomics
 
 
+def test_flash_attention_backward_vision_tower_layout(native_lib):
+    """(head_dim, head_stride) = (72, 80), full attention over 676 tokens, several crops; zero padding columns in qkv."""
+    B, T, heads = 2, 676, 16
+    qkv = _rand(B * T, 3 * heads * 80, seed=3).view(B * T, 3 * heads, 80)
+    qkv[:, :, 72:] = 0
+    qkv = qkv.reshape(B * T, 3 * heads * 80).contiguous()
+    dout = _rand(B * T, heads * 72, seed=4)
+    out = ops.attention(qkv.to(DEV), B, T, heads, heads, 72, 80, 0, heads * 80, 2 * heads * 80, False)
+    got = ops.attention_bwd(qkv.to(DEV), out, dout.to(DEV), B, T, heads, heads, 72, 0, heads * 80, 2 * heads * 80, False,
+                            head_stride=80)
+    want = ref_ops.attention_bwd(qkv, out.cpu(), dout, B, T, heads, heads, 72, 0, heads * 80, 2 * heads * 80, False,
+                                 head_stride=80)
+    assert _err(got, want) < 3e-2
+    assert float(got.view(B * T, 3 * heads, 80)[:, :, 72:].abs().max()) == 0.0
+
+
 def test_whole_sft_step_with_flash_backward_matches_materialised(native_lib):
     from leopard_b200.engine import PrefillEngine
     from leopard_b200.train import SFTTrainer
