@@ -384,3 +384,29 @@ def test_collate_and_train_step_shims_match_the_script():
     b1 = megatron.mm_collate_fn(gen.make_batch(gen.CASES[4]))
     assert megatron.train_step(None, iter([b0, None, b1]), [object()], lrec, num_microbatches=2)[0] == {"lm loss": 2.0}
     assert lrec.n == (2, 2, 2, 2, (1, 24))
+
+
+def test_checkpoint_export_reads_the_live_trained_tensors():
+    """GPTModel.state_dict_for_save_checkpoint after training: the nested Megatron dict holds what is on the device
+    (kernel layout inverted, Megatron's interleaves applied), not the tensors the model was loaded from."""
+    import types
+    import torch
+    from leopard_b200 import megatron
+    from leopard_b200.config import leopard_llava, reduced
+    from leopard_b200.native_weights import load_hf
+    from leopard_b200.weights import SyntheticCheckpoint
+    cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=324)
+    ck = SyntheticCheckpoint(cfg, seed=21)
+    nw = load_hf(cfg, lambda n: ck[n], device="cpu")
+    model = types.SimpleNamespace(cfg=cfg, engine=types.SimpleNamespace(w=nw), _hf_getter=lambda n: ck[n])
+    sd = megatron.GPTModel.state_dict_for_save_checkpoint(model)["language_model"]
+    flat0 = megatron.flatten_language_model_state(sd)
+    ref = megatron.hf_to_megatron(cfg, lambda n: ck[n])
+    assert set(flat0) == set(ref) and all(torch.equal(flat0[k], ref[k].to(flat0[k].dtype)) for k in ref)
+    # "train": bump the fused gate/up weight's first up-projection row and one projector bias in place
+    nw.named["dec.0.gateup_w"][32].fill_(0.5)
+    nw.named["proj.b2"][7] = 0.25
+    flat1 = megatron.flatten_language_model_state(megatron.GPTModel.state_dict_for_save_checkpoint(model)["language_model"])
+    h4 = flat1["encoder.layers.0.mlp.dense_h_to_4h.weight"]           # [gate ; up]
+    assert float(h4[cfg.dec.ffn].float().min()) == 0.5 and torch.equal(h4[: cfg.dec.ffn], flat0["encoder.layers.0.mlp.dense_h_to_4h.weight"][: cfg.dec.ffn])
+    assert float(flat1["mm_projector.encoder.linear_fc2.bias"][7]) == 0.25
