@@ -1,0 +1,117 @@
+// Test infrastructure: a minimal thread-per-CUDA-thread emulator so that the SOURCE of the element-wise / reduction
+// kernels in leopard_b200/csrc/lp_train.cu can be compiled with g++ and executed on the CPU (tests/test_train_kernels_emulated.py).
+// It emulates exactly what those kernels use: threadIdx / blockIdx / blockDim / gridDim, __shared__ (function-local statics;
+// blocks run one after another), __syncthreads, __shfl_xor_sync, atomicAdd(float), bf16 types with round-to-nearest-even,
+// the vector types and a few math intrinsics.  Nothing here is part of the product; nothing tcgen05 / TMA can run here.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __grid_constant__
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
+inline float2 make_float2(float a, float b) { return {a, b}; }
+inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+// ---- bf16 ------------------------------------------------------------------------------------------------------------
+struct __nv_bfloat16 {
+  uint16_t bits;
+  __nv_bfloat16() = default;
+  operator float() const {
+    uint32_t u = (uint32_t)bits << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+  }
+};
+inline __nv_bfloat16 __float2bfloat16(float f) {   // round to nearest even, NaN kept quiet
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  __nv_bfloat16 r;
+  if ((u & 0x7fffffffu) > 0x7f800000u) { r.bits = 0x7fff; return r; }
+  u += 0x7fffu + ((u >> 16) & 1u);
+  r.bits = (uint16_t)(u >> 16);
+  return r;
+}
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+inline __nv_bfloat162 __floats2bfloat162_rn(float lo, float hi) { return {__float2bfloat16(lo), __float2bfloat16(hi)}; }
+inline float2 __bfloat1622float2(__nv_bfloat162 v) { return {(float)v.x, (float)v.y}; }
+
+// ---- math ------------------------------------------------------------------------------------------------------------
+inline float __expf(float x) { return std::exp(x); }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+using std::min;
+using std::max;
+
+// ---- block / warp synchronisation ----------------------------------------------------------------------------------------
+namespace emu {
+struct BlockCtx {
+  std::unique_ptr<std::barrier<>> block_bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  std::vector<float> warp_buf;   // [warps][32]
+};
+inline BlockCtx* g_ctx = nullptr;
+
+template <typename F>
+void launch(dim3 grid, dim3 block, F&& body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        BlockCtx ctx;
+        ctx.block_bar = std::make_unique<std::barrier<>>(nthreads);
+        const unsigned nwarps = (nthreads + 31) / 32;
+        for (unsigned w = 0; w < nwarps; ++w)
+          ctx.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - w * 32)));
+        ctx.warp_buf.assign(nwarps * 32, 0.f);
+        g_ctx = &ctx;
+        std::vector<std::thread> ts;
+        ts.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t)
+          ts.emplace_back([&, t] {
+            threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            blockIdx = {bx, by, bz};
+            blockDim = block;
+            gridDim = grid;
+            body();
+            ctx.block_bar->arrive_and_drop();   // a thread that has returned no longer takes part in __syncthreads
+          });
+        for (auto& th : ts) th.join();
+      }
+  g_ctx = nullptr;
+}
+inline unsigned linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+}  // namespace emu
+
+inline void __syncthreads() { emu::g_ctx->block_bar->arrive_and_wait(); }
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  const unsigned t = emu::linear_tid(), w = t >> 5, l = t & 31;
+  float* buf = emu::g_ctx->warp_buf.data() + w * 32;
+  buf[l] = v;
+  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  const float r = buf[l ^ (unsigned)lane_mask];
+  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  return r;
+}
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
