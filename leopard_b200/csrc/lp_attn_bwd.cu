@@ -18,9 +18,14 @@
 //                        lanes), then dV += P^T dO and dK += dS^T Q with TMEM A operands and the dO / Q tiles as MN-major
 //                        B operands; the sums over the group's heads never leave TMEM (4 x 128 columns = all 512).
 // Warp roles as in lp_attn.cu: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2-5 one thread per row.
+#ifdef LP_EMULATE                  // CPU emulation build (tests/test_attn_bwd_emulated.py): same kernel source, the
+#include "tc_emu.h"                // tcgen05 / TMA / mbarrier wrappers replaced by functional stand-ins (tests/emu/)
+#include "emu_helpers.inc"         // descriptor builders + numerics helpers, cut from lp_common.cuh by the test
+#else
 #include "lp_common.cuh"
 #include "lp_host.h"
 #include "../../include/leopard_b200.h"
+#endif
 
 namespace lp {
 
@@ -45,11 +50,17 @@ struct AttnBwdArgs {
   float scale, scale_log2;
 };
 
+#ifdef LP_EMULATE
+__device__ __forceinline__ float bw_ex2(float x) { return exp2f(x); }
+__device__ __forceinline__ void row_threads_barrier() { emu_tc::g_named->arrive_and_wait(); }
+#else
 __device__ __forceinline__ float bw_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// named barrier 1: the four row warps (128 threads) only
+__device__ __forceinline__ void row_threads_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 #define LP_TMEM_ST_16(regs, taddr)                                                                                  \
   asm volatile(                                                                                                     \
@@ -59,6 +70,7 @@ __device__ __forceinline__ float bw_ex2(float x) {
       "r"(regs[7]), "r"(regs[8]), "r"(regs[9]), "r"(regs[10]), "r"(regs[11]), "r"(regs[12]), "r"(regs[13]),         \
       "r"(regs[14]), "r"(regs[15])                                                                                  \
       : "memory")
+#endif
 
 // D[128 x 128] (+)= A[128 x DH] B[128 x DH]^T, both K-major 128B-swizzled tiles of two boxes (the forward's S = Q K^T form)
 template <int DH>
@@ -454,7 +466,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         st_lse[r] = args.lse2[si];
         st_del[r] = args.delta[si];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four row warps only; the other stage is still being read
+      row_threads_barrier();   // the four row warps only; the other stage is still being read
       mbar_wait(st_full, t & 1);
       if (t > 0) mbar_wait(acc_done, (t - 1) & 1);
       tc_fence_after();
@@ -504,6 +516,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
 }  // namespace lp
 
+#ifndef LP_EMULATE
 using namespace lp;
 
 extern "C" size_t lp_attention_bwd_workspace_bytes(int B, int T, int n_heads) {
@@ -576,3 +589,4 @@ extern "C" int lp_attention_bwd(const void* qkv, long long ld, const void* out, 
   return causal ? launch_attn_bwd<128, true>(tq, td, a, n_kv_heads, stream)
                 : launch_attn_bwd<128, false>(tq, td, a, n_kv_heads, stream);
 }
+#endif  // !LP_EMULATE

@@ -72,6 +72,7 @@ struct BlockCtx {
   std::vector<float> warp_buf;   // [warps][32]
 };
 inline BlockCtx* g_ctx = nullptr;
+inline std::function<void()> g_block_hook;   // run before each block's threads start (per-CTA state reset)
 
 template <typename F>
 void launch(dim3 grid, dim3 block, F&& body) {
@@ -86,6 +87,7 @@ void launch(dim3 grid, dim3 block, F&& body) {
           ctx.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - w * 32)));
         ctx.warp_buf.assign(nwarps * 32, 0.f);
         g_ctx = &ctx;
+        if (g_block_hook) g_block_hook();
         std::vector<std::thread> ts;
         ts.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t)

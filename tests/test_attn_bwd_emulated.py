@@ -1,0 +1,77 @@
+"""The SOURCE of the flash-style attention backward (leopard_b200/csrc/lp_attn_bwd.cu, compiled with -DLP_EMULATE) executed on
+the CPU: one OS thread per CUDA thread, the tcgen05 / TMEM / TMA / mbarrier wrappers replaced by the functional stand-ins of
+tests/emu/tc_emu.h.  Checks the kernels' logic — the producer / issuer / row-thread protocol (a wedged barrier aborts the run),
+tile indexing, causal and ragged masks, the GQA group accumulation, the operand roles of the seven MMAs per tile pair, the
+zero-padded 80-wide head layout — against the closed form of oracle/train.py.  It does not check the hardware: the emulator's
+memory layouts are the same reading of the hardware the GPU-verified forward kernels are built on."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import native_ops as ref
+
+ROOT = Path(__file__).resolve().parents[1]
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emu_attn")
+    common = (ROOT / "leopard_b200/csrc/lp_common.cuh").read_text()
+    a = common.rindex("// ----", 0, common.index("// UMMA descriptors"))
+    (out / "emu_helpers.inc").write_text("namespace lp {\n" + common[a:common.rindex("}  // namespace lp")] + "\n}\n")
+    lib = out / "libattn.so"
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-shared", "-fPIC", "-I", str(out), "-I", str(ROOT / "tests/emu"),
+                        str(ROOT / "tests/emu/attn_bwd_emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(str(lib))
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _err(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("B,T,heads,kv_heads,causal,hd,hs", [
+    (1, 128, 1, 1, True, 128, 128),      # one tile
+    (2, 200, 4, 2, True, 128, 128),      # ragged length, two sequences, GQA groups of 2
+    (1, 384, 2, 2, False, 128, 128),     # full attention, three tiles
+    (1, 520, 8, 2, True, 128, 128),      # the decoder's group of 4, five tiles (S buffers wrap, barrier phases flip twice)
+    (2, 300, 3, 3, False, 72, 80),       # vision-tower layout: 72 used of 80 columns per head
+])
+def test_flash_backward_kernels_under_emulation(emu, B, T, heads, kv_heads, causal, hd, hs):
+    g = torch.Generator().manual_seed(T + heads)
+    q_w, kv_w = heads * hs, kv_heads * hs
+    qkv = torch.randn((B * T, q_w + 2 * kv_w), generator=g).to(BF)
+    if hs != hd:
+        v = qkv.view(B * T, heads + 2 * kv_heads, hs)
+        v[:, :, hd:] = 0
+        qkv = v.reshape(B * T, -1).contiguous()
+    dout = torch.randn((B * T, heads * hd), generator=g).to(BF)
+    out = ref.attention(qkv, B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, causal)
+    want = ref.attention_bwd(qkv, out, dout, B, T, heads, kv_heads, hd, 0, q_w, q_w + kv_w, causal, head_stride=hs)
+    got = torch.full_like(qkv, float("nan"))
+    t_pad = -(-T // 128) * 128
+    lse, delta = torch.zeros(B * heads * t_pad), torch.zeros(B * heads * t_pad)
+    emu.emu_attention_bwd(P(qkv), C.c_longlong(qkv.stride(0)), P(out), P(dout), C.c_longlong(out.stride(0)), B, T, heads,
+                          kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal), C.c_float(hd ** -0.5), P(got),
+                          C.c_longlong(got.stride(0)), P(lse), P(delta), 3)
+    assert not bool(torch.isnan(got.float()).any())                      # every element of dqkv is written
+    for name, sl in (("dq", slice(0, q_w)), ("dk", slice(q_w, q_w + kv_w)), ("dv", slice(q_w + kv_w, None))):
+        assert _err(got[:, sl], want[:, sl]) < 1.5e-2, name
+    if hs != hd:
+        assert float(got.view(B * T, heads + 2 * kv_heads, hs)[:, :, hd:].abs().max()) == 0.0
+    # the row statistics the first kernel hands to the second: natural-log lse = lse2 * ln 2
+    x = qkv.float().view(B, T, -1)
+    q0 = x[0, :, :hd]
+    k0 = x[0, :, q_w: q_w + hd]
+    s = (q0 @ k0.t()) * hd ** -0.5
+    if causal:
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1), float("-inf"))
+    assert torch.allclose(lse[:T] * 0.6931471805599453, torch.logsumexp(s, -1), atol=2e-3)
