@@ -116,4 +116,14 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   emu::g_ctx->warp_bar[w]->arrive_and_wait();
   return r;
 }
+inline bool __any_sync(unsigned, bool pred) {
+  const unsigned t = emu::linear_tid(), w = t >> 5, l = t & 31;
+  float* buf = emu::g_ctx->warp_buf.data() + w * 32;
+  buf[l] = pred ? 1.f : 0.f;
+  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  bool any = false;
+  for (int i = 0; i < 32; ++i) any |= buf[i] != 0.f;
+  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  return any;
+}
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }

@@ -5,6 +5,7 @@ tile indexing, causal and ragged masks, the GQA group accumulation, the operand 
 zero-padded 80-wide head layout — against the closed form of oracle/train.py.  It does not check the hardware: the emulator's
 memory layouts are the same reading of the hardware the GPU-verified forward kernels are built on."""
 import ctypes as C
+import re
 import subprocess
 from pathlib import Path
 
@@ -75,3 +76,49 @@ def test_flash_backward_kernels_under_emulation(emu, B, T, heads, kv_heads, caus
     if causal:
         s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1), float("-inf"))
     assert torch.allclose(lse[:T] * 0.6931471805599453, torch.logsumexp(s, -1), atol=2e-3)
+
+
+# ---- the emulator's own credibility check: the forward kernel that is parity-green on the B200 must be green here too ------
+@pytest.fixture(scope="module")
+def emu_fwd(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emu_fwd")
+    common = (ROOT / "leopard_b200/csrc/lp_common.cuh").read_text()
+    a = common.rindex("// ----", 0, common.index("// UMMA descriptors"))
+    (out / "emu_helpers.inc").write_text("namespace lp {\n" + common[a:common.rindex("}  // namespace lp")] + "\n}\n")
+    args = re.search(r"struct AttnArgs \{.*?\n\};", (ROOT / "leopard_b200/csrc/lp_host.h").read_text(), re.S).group(0)
+    src = (ROOT / "leopard_b200/csrc/lp_attn.cu").read_text()
+    body = src[src.index("namespace lp {"):src.index("template <int DH, bool CAUSAL, bool P_TMEM>\nstatic int launch_attn(")]
+    # the kernel's two inline-PTX statements -> functional equivalents (everything else goes through lp_common.cuh wrappers)
+    ex2 = 'asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));'
+    assert ex2 in body
+    body = body.replace(ex2, "y = exp2f(x);")
+    st16 = re.compile(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?::\s*"r"\(([^,]*?)\),\s*"r"\((\w+)\[0\]\).*?'
+                      r':\s*"memory"\);', re.S)
+    body, n = st16.subn(lambda m: f"lp::tmem_st({m.group(2)}, {m.group(1)}, 16);", body)
+    assert n == 2 and "asm" not in body
+    (out / "attn_fwd.inc").write_text("namespace lp {\n" + args + "\n}\n" + body + "\n}  // namespace lp\n")
+    lib = out / "libfwd.so"
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-shared", "-fPIC", "-I", str(out), "-I", str(ROOT / "tests/emu"),
+                        str(ROOT / "tests/emu/attn_fwd_emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(str(lib))
+
+
+@pytest.mark.parametrize("B,T,heads,kv_heads,causal,hd,hs,p_tmem", [
+    (2, 200, 4, 2, True, 128, 128, 0),      # P through shared memory (manual 128-byte swizzle writes)
+    (1, 520, 4, 1, True, 128, 128, 1),      # P aliased over S in TMEM, five kv tiles
+    (2, 300, 2, 2, False, 72, 80, 1),       # vision-tower layout
+])
+def test_gpu_verified_forward_kernel_is_green_under_the_emulator(emu_fwd, B, T, heads, kv_heads, causal, hd, hs, p_tmem):
+    g = torch.Generator().manual_seed(T)
+    q_w, kv_w = heads * hs, kv_heads * hs
+    qkv = torch.randn((B * T, q_w + 2 * kv_w), generator=g).to(BF)
+    if hs != hd:
+        v = qkv.view(B * T, heads + 2 * kv_heads, hs)
+        v[:, :, hd:] = 0
+        qkv = v.reshape(B * T, -1).contiguous()
+    want = ref.attention(qkv, B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, causal)
+    got = torch.full((B * T, heads * hd), float("nan")).to(BF)
+    emu_fwd.emu_attention_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal),
+                              C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), p_tmem)
+    assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2
