@@ -55,7 +55,7 @@ def main():
         torch.cuda.synchronize()
         out.append(dict(ms=e0.elapsed_time(e1), wall_ms=(time.perf_counter() - t0) * 1e3, loss=loss, grad_norm=norm,
                         launches=L.lp_launch_count() - n0))
-    timed = out[1:]
+    timed = out[1:] or out          # --steps 0: a single (cold) step, for profiler runs
     ms = sum(o["ms"] for o in timed) / len(timed)
     print(json.dumps(dict(metric="sft_tokens_per_s", value=a.seq / ms * 1e3, ms_per_step=ms, seq=a.seq, crops=a.crops,
                           layers=a.layers, freeze_llm=a.freeze_llm, launches_per_step=timed[-1]["launches"],
