@@ -131,12 +131,12 @@ def test_sft_step_sequencing_matches_autograd_oracle(cpu_trainer):
 def test_flash_backward_call_is_equivalent_to_the_materialised_path(cpu_trainer):
     """train.py's two attention-backward routes (per-head materialised tiles vs one lp_attention_bwd call) must be fed
     consistently: with the op contracts in place of the kernels they give the same gradients."""
-    cfg, ck, nw, eng = cpu_trainer
-    tokens, labels, weights, images = _batch(cfg, b=2, n_text=15, seed=4)
+    cfg, eng = _small_cpu_engine()
+    tokens, labels, weights = _text_batch(cfg, seed=4)
     grads = {}
     for mode in ("materialized", "flash"):
         tr = T.SFTTrainer(eng, lr=0.0, attn_bwd=mode)          # lr 0: the second run sees the same weights
-        tr.step(tokens, labels, weights, images)
+        tr.step(tokens, labels, weights, None)
         grads[mode] = tr.flat_grad.clone()
     rel = float((grads["flash"] - grads["materialized"]).norm() / grads["materialized"].norm())
     assert rel < 0.02, rel
@@ -204,10 +204,20 @@ def _patch_cpu():
     torch.cuda.is_available = lambda: True
 
 
+_SMALL_CACHE = {}
+
+
 def _small_cpu_engine():
+    """Fresh native weights every call (trainers update them in place); the synthetic tensors are drawn once per process."""
     cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=320)
     ck = SyntheticCheckpoint(cfg, seed=5)
-    nw = load_hf(cfg, lambda n: ck[n], device="cpu")
+
+    def get(name):
+        if name not in _SMALL_CACHE:
+            _SMALL_CACHE[name] = ck[name]
+        return _SMALL_CACHE[name]
+
+    nw = load_hf(cfg, get, device="cpu")
     return cfg, _FakeEngine(cfg, ck, nw)
 
 

@@ -157,7 +157,8 @@ def test_grad_norm_adamw_accumulate(emu):
     emu.emu_grad_norm(P(x), LL(x.numel()), I(3), F(1.0), P(out))               # the harness feeds the tensor twice
     norm = OT.global_grad_norm([x, x])
     assert abs(float(out[0]) - norm) < 1e-5 * norm and abs(float(out[1]) - OT.clip_coefficient(norm, 1.0)) < 1e-7
-    emu.emu_grad_norm(P(x * 1e-4), LL(x.numel()), I(2), F(1.0), P(out))
+    small = x * 1e-4                                                            # (kept alive: P() only takes the address)
+    emu.emu_grad_norm(P(small), LL(small.numel()), I(2), F(1.0), P(out))
     assert float(out[1]) == 1.0
     p = rnd(1001, seed=3, dtype=torch.float32)
     pr, m, v = p.clone(), torch.zeros(1001), torch.zeros(1001)
