@@ -352,7 +352,8 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
  * lp_sumsq_accum / lp_grad_norm_finish: global L2 norm over fp32 gradients (partial[] must be zeroed per step;
  *                    lp_grad_norm_workspace_bytes() bytes) -> out2 = {norm, clip coefficient} in device memory.
  * lp_adamw_step:     FusedAdam (adam_w_mode) on fp32 main params with the gradient scaled by out2[1]; also refreshes
- *                    the bf16 model copy (p_bf16 may be NULL).  step counts from 1. */
+ *                    the bf16 model copy (p_bf16 may be NULL).  step counts from 1.  A non-finite out2[0] (inf / NaN
+ *                    gradients) makes the call a no-op: the iteration is skipped as in Megatron's found-inf path. */
 /* Flash-style attention backward (tcgen05; (head_dim, head_stride) = (128, 128) causal or full, or (72, 80) full — the
  * vision tower's zero-padded head layout, whose padding columns of dqkv are written as zeros) — SECOND implementation,
  * compiled but not yet run on hardware; train.py selects it with LEOPARD_ATTN_BWD=flash.  Replaces autograd through

@@ -591,6 +591,9 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, long long n, float lr, float b1, float b2, float eps, float wd, float inv_bc1,
              float inv_bc2, const float* __restrict__ clip) {
+  // a non-finite gradient norm skips the whole update (Megatron's found-inf path: optimizer.py:313-340 returns without
+  // stepping); NaN fails the comparison as well
+  if (clip != nullptr && !(clip[0] < INFINITY)) return;
   const float cs = clip != nullptr ? clip[1] : 1.f;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float gi = g[i] * cs;

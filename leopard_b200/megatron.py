@@ -225,7 +225,7 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
         loss, grad_norm = optimizer.step(*micro[0])
     else:
         loss, grad_norm = optimizer.step(*[list(col) for col in zip(*micro)])
-    return {"lm loss": loss}, 0, grad_norm, None
+    return {"lm loss": loss}, int(getattr(optimizer, "skipped_last", False)), grad_norm, None
 
 
 def model_provider(pre_process=True, post_process=True):

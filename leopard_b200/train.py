@@ -155,6 +155,7 @@ class SFTTrainer:
         self.qkv_w = self.q_w + 2 * self.kv_w
         self._scratch_g = None
         self._accum = False        # True while a micro-batch after the first is being back-propagated
+        self.skipped_last = False  # the last step() found non-finite gradients and left the weights untouched
         self._acc_scratch = {}
         # attention backward: 'materialized' (verified composition of GEMMs + lp_softmax_bwd) or 'flash' (lp_attention_bwd)
         self.attn_bwd = attn_bwd or os.environ.get("LEOPARD_ATTN_BWD", "materialized")
@@ -493,6 +494,9 @@ class SFTTrainer:
                                hp["wd"], self._norm_out)
         loss = torch.stack(losses).mean()
         out = torch.cat([loss.reshape(1), self._norm_out[:1]]).tolist()
+        self.skipped_last = not math.isfinite(out[1])
+        if self.skipped_last:        # inf / NaN gradients: the update kernels returned without touching anything
+            self.iteration -= 1      # (Megatron's found-inf path: the step does not count, optimizer.py:313-340)
         return out[0], out[1]
 
     def _forward_backward(self, tokens, labels, loss_mask, images, n_micro: int, last: bool, handles: list):

@@ -230,6 +230,8 @@ def grad_norm(flat_grads, max_norm, partial=None, out2=None):
 
 
 def adamw_step(p, g, m, v, p16, step, lr, beta1, beta2, eps, weight_decay, norm_and_clip):
+    if norm_and_clip is not None and not math.isfinite(float(norm_and_clip[0])):
+        return                                       # non-finite gradient norm: the update is skipped
     gi = g * (float(norm_and_clip[1]) if norm_and_clip is not None else 1.0)
     m.mul_(beta1).add_(gi, alpha=1 - beta1)
     v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)

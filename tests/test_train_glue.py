@@ -4,6 +4,7 @@ contract restatement (oracle/native_ops.py), against autograd over the model ora
 This pins everything train.py decides — which operand is transposed, which column slice is which head, the interleaved
 gate/up layout, the loss shift and weights, where each gradient lands in the flat buffer, bucket order, the optimizer
 call — independently of the CUDA kernels, whose own parity is checked per kernel on the GPU (tools/gpu_check_train.py)."""
+import math
 import types
 
 import pytest
@@ -352,3 +353,24 @@ def test_unfrozen_vision_tower_backward_matches_autograd_oracle(cpu_trainer):
     tr2 = T.SFTTrainer(eng, lr=0.0, freeze_vision_tower=False, attn_bwd="flash")
     tr2.step(tokens, labels, weights, images)
     assert float((tr2.flat_grad - tr.flat_grad).norm() / tr.flat_grad.norm()) < 0.02
+
+
+def test_non_finite_gradients_skip_the_iteration(cpu_trainer):
+    """inf / NaN in the gradients: weights, moments and the step counter stay untouched and train_step reports the skip
+    (Megatron's found-inf path)."""
+    from leopard_b200 import megatron
+    cfg, eng = _small_cpu_engine()
+    tokens, labels, weights = _text_batch(cfg, seed=3)
+    tr = T.SFTTrainer(eng, lr=1e-4)
+    before = {n: t.clone() for n, t in eng.w.named.items()}
+    eng.w.named["dec.lm_head"][5, 7] = float("inf")            # poisons the logits of every row
+    poisoned = eng.w.named["dec.lm_head"].clone()
+    batch = {"input_ids": tokens, "labels": labels, "weights": weights, "image": torch.zeros(1, 10, dtype=torch.bfloat16)}
+    loss, skipped, norm, _ = megatron.train_step(None, iter([batch]), [object()], tr)
+    assert skipped == 1 and not math.isfinite(norm) and tr.iteration == 0
+    assert torch.equal(eng.w.named["dec.lm_head"], poisoned) and float(tr.flat_m.abs().max()) == 0.0
+    for n in ("dec.0.o_w", "proj.b1", "embed"):
+        assert torch.equal(eng.w.named[n], before[n]), n
+    eng.w.named["dec.lm_head"].copy_(before["dec.lm_head"])     # healthy again: the next step counts as iteration 1
+    loss, skipped, norm, _ = megatron.train_step(None, iter([batch]), [object()], tr)
+    assert skipped == 0 and math.isfinite(norm) and tr.iteration == 1

@@ -170,6 +170,13 @@ def test_grad_norm_adamw_accumulate(emu):
         emu.emu_adamw(P(pd), P(g), P(md), P(vd), P(p16), LL(1001), F(1e-3), F(0.9), F(0.999), F(1e-8), F(0.01),
                       F(1 / (1 - 0.9 ** step)), F(1 / (1 - 0.999 ** step)), P(clip), I(2))
     assert torch.allclose(pd, pr, rtol=1e-5, atol=1e-6) and torch.equal(p16, pd.to(BF))
+    # a non-finite gradient norm turns the update into a no-op (found-inf path)
+    keep = (pd.clone(), md.clone(), vd.clone(), p16.clone())
+    for bad in (float("inf"), float("nan")):
+        bad_norm = torch.tensor([bad, 1.0])
+        emu.emu_adamw(P(pd), P(g), P(md), P(vd), P(p16), LL(1001), F(1e-3), F(0.9), F(0.999), F(1e-8), F(0.01), F(1.0), F(1.0),
+                      P(bad_norm), I(2))
+        assert all(torch.equal(x, y) for x, y in zip((pd, md, vd, p16), keep))
     a, b = rnd(1003, seed=7, dtype=torch.float32), rnd(1003, seed=8, dtype=torch.float32)
     want = a + b
     emu.emu_accumulate(P(a), P(b), LL(1003), I(2))
