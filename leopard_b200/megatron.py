@@ -1,4 +1,5 @@
-"""Drop-in for the Megatron plugin surface of the reference (second row) — forward / prefill only.
+"""Drop-in for the Megatron plugin surface of the reference (second row): forward / prefill, and the training
+iteration's entry points (mm_collate_fn, loss_func, train_step over leopard_b200.train.SFTTrainer).
 
     model_provider(pre_process=True, post_process=True) -> model         (Pai-Megatron-Patch/examples/llava/
                                                                           pretrain_megatron_llava.py:37-50)
@@ -9,9 +10,11 @@ Conventions kept from the reference: image slots are ids == -200, one per featur
 tiles + [global]; ids -100 (padding) read embedding row 0 (vlm_model.py:226); `images` with last dim <= 100 is the
 "no image" dummy (vlm_model.py:518; dummy = zeros(1, 10), pretrain_megatron_llava.py:188); a feature/slot count
 mismatch raises AssertionError with the reference's message (vlm_model.py:528-529).  The attention mask is ignored
-exactly like the flash-attention path of the reference (causal only).  Backward / optimizer (§8f-1) are not part of
-this round: forward(labels=...) returns the per-token loss [b, s] (lp_cross_entropy), backward is not available.
-Checkpoint surface: state_dict_for_save_checkpoint() / load_state_dict() speak the reference's nested Megatron layout.
+exactly like the flash-attention path of the reference (causal only).  forward(labels=...) returns the per-token loss
+[b, s] (lp_cross_entropy).  There is no autograd graph: the training iteration (§8f-1, first implementation — DESIGN.md §6b)
+is `train_step`, which hands the batch to SFTTrainer.step (forward, loss_func, backward, reduce, clip, AdamW on native
+kernels).  Checkpoint surface: state_dict_for_save_checkpoint() / load_state_dict() speak the reference's nested Megatron
+layout and export the live (trained) tensors.
 """
 from __future__ import annotations
 
@@ -83,7 +86,8 @@ def configure_provider(cfg: Optional[LeopardConfig] = None, hf_getter: Optional[
 
 
 class GPTModel:
-    """Forward-only native stand-in for megatron_patch.model.llava.gpt_model.GPTModel."""
+    """Native stand-in for megatron_patch.model.llava.gpt_model.GPTModel: forward (logits / per-token loss) here; the training
+    iteration runs through `train_step` + leopard_b200.train.SFTTrainer on this model's engine (no autograd graph)."""
 
     def __init__(self, cfg: LeopardConfig, native: NativeWeights, pre_process=True, post_process=True,
                  hf_getter: Optional[Callable] = None):
