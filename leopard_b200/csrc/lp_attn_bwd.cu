@@ -18,7 +18,7 @@
 //                        lanes), then dV += P^T dO and dK += dS^T Q with TMEM A operands and the dO / Q tiles as MN-major
 //                        B operands; the sums over the group's heads never leave TMEM (4 x 128 columns = all 512).
 // Warp roles as in lp_attn.cu: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2-5 one thread per row.
-#ifdef LP_EMULATE                  // CPU emulation build (tests/test_attn_bwd_emulated.py): same kernel source, the
+#ifdef LP_EMULATE                  // CPU emulation build (tests/test_attention_kernels_emulated.py): same kernel source, the
 #include "tc_emu.h"                // tcgen05 / TMA / mbarrier wrappers replaced by functional stand-ins (tests/emu/)
 #include "emu_helpers.inc"         // descriptor builders + numerics helpers, cut from lp_common.cuh by the test
 #else

@@ -1,5 +1,5 @@
 // Test infrastructure: functional stand-ins for the tcgen05 / TMEM / TMA / mbarrier wrappers of leopard_b200/csrc/lp_common.cuh,
-// on top of cuda_emu.h, so that the SOURCE of lp_attn_bwd.cu can run on the CPU (tests/test_attn_bwd_emulated.py).
+// on top of cuda_emu.h, so that the SOURCE of lp_attn_bwd.cu can run on the CPU (tests/test_attention_kernels_emulated.py).
 // What is modelled — and only as far as the kernels rely on it:
 //   mbarrier   arrival count + transaction bytes + phase parity; try_wait(parity) is true once the phase of that parity has
 //              completed (a fresh barrier passes parity 1); a wait that makes no progress for EMU_DEADLOCK_MS aborts the run
@@ -44,9 +44,12 @@ inline std::mutex g_mu;
 inline std::unordered_map<uint32_t, Mbar> g_bars;
 inline uint32_t g_tmem[128][512];
 inline std::unique_ptr<std::barrier<>> g_named;   // named barrier 1 of the kernels: the 128 row threads
+struct NamedBar { int count = 0; long gen = 0; };
+inline NamedBar g_nbar[16];                        // bar.sync / bar.arrive id, n: completes when n threads have arrived
 inline void reset() {
   std::lock_guard<std::mutex> l(g_mu);
   g_bars.clear();
+  for (auto& b : g_nbar) b = NamedBar();
   g_named = std::make_unique<std::barrier<>>(128);
   std::memset(g_tmem, 0xff, sizeof(g_tmem));     // NaN pattern: reading an accumulator that was never written shows up
 }
@@ -111,6 +114,36 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+
+// ---- named barriers (bar.sync id, n waits for the n-th arrival of the current generation; bar.arrive id, n only arrives)
+inline void named_bar(int id, int n, bool wait) {
+  long my_gen;
+  {
+    std::lock_guard<std::mutex> l(emu_tc::g_mu);
+    auto& b = emu_tc::g_nbar[id];
+    my_gen = b.gen;
+    if (++b.count == n) {
+      b.count = 0;
+      b.gen++;
+      return;
+    }
+  }
+  if (!wait) return;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> l(emu_tc::g_mu);
+      if (emu_tc::g_nbar[id].gen != my_gen) return;
+    }
+    std::this_thread::yield();
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(EMU_DEADLOCK_MS)) {
+      std::fprintf(stderr, "emu: DEADLOCK thread %u waits named barrier %d\n", threadIdx.x, id);
+      std::abort();
+    }
+  }
+}
+inline void pdl_wait() {}
+inline void pdl_launch_dependents() {}
 
 // ---- TMA
 inline void tma_prefetch_desc(const CUtensorMap*) {}
@@ -194,3 +227,5 @@ inline int __shfl_sync(unsigned, int v, int) { return v; }   // only used to bro
 inline void __syncwarp() {}
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }

@@ -1,5 +1,5 @@
-"""The SOURCE of the flash-style attention backward (leopard_b200/csrc/lp_attn_bwd.cu, compiled with -DLP_EMULATE) executed on
-the CPU: one OS thread per CUDA thread, the tcgen05 / TMEM / TMA / mbarrier wrappers replaced by the functional stand-ins of
+"""The SOURCE of the tcgen05 attention kernels executed on the CPU — the flash-style backward (leopard_b200/csrc/lp_attn_bwd.cu,
+compiled with -DLP_EMULATE), and as the emulator's credibility check the two GPU-verified forward kernels (lp_attn.cu, lp_attn3.cu): one OS thread per CUDA thread, the tcgen05 / TMEM / TMA / mbarrier wrappers replaced by the functional stand-ins of
 tests/emu/tc_emu.h.  Checks the kernels' logic — the producer / issuer / row-thread protocol (a wedged barrier aborts the run),
 tile indexing, causal and ragged masks, the GQA group accumulation, the operand roles of the seven MMAs per tile pair, the
 zero-padded 80-wide head layout — against the closed form of oracle/train.py.  It does not check the hardware: the emulator's
@@ -121,4 +121,48 @@ def test_gpu_verified_forward_kernel_is_green_under_the_emulator(emu_fwd, B, T, 
     got = torch.full((B * T, heads * hd), float("nan")).to(BF)
     emu_fwd.emu_attention_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal),
                               C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), p_tmem)
+    assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2
+
+
+@pytest.fixture(scope="module")
+def emu_v3(tmp_path_factory):
+    """lp_attn3.cu: the kernel template is cut out verbatim (it contains no PTX); its few inline-PTX helpers (a3_*) are restated
+    in tests/emu/attn3_fwd_emu.cpp."""
+    out = tmp_path_factory.mktemp("emu_v3")
+    common = (ROOT / "leopard_b200/csrc/lp_common.cuh").read_text()
+    a = common.rindex("// ----", 0, common.index("// UMMA descriptors"))
+    (out / "emu_helpers.inc").write_text("namespace lp {\n" + common[a:common.rindex("}  // namespace lp")] + "\n}\n")
+    host = (ROOT / "leopard_b200/csrc/lp_host.h").read_text()
+    (out / "attn_args.inc").write_text(re.search(r"struct AttnArgs \{.*?\n\};", host, re.S).group(0) + "\n")
+    src = (ROOT / "leopard_b200/csrc/lp_attn3.cu").read_text()
+    body = src[src.index("template <int DH, bool CAUSAL, int EMU>\n__global__"):
+               src.index("template <int DH, bool CAUSAL, int EMU>\nstatic int launch3(")]
+    assert "asm" not in body
+    (out / "attn3_kernel.inc").write_text(body)
+    lib = out / "liba3.so"
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-shared", "-fPIC", "-I", str(out), "-I", str(ROOT / "tests/emu"),
+                        str(ROOT / "tests/emu/attn3_fwd_emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(str(lib))
+
+
+@pytest.mark.parametrize("B,T,heads,kv_heads,causal,hd,hs,pingpong", [
+    (2, 200, 4, 2, True, 128, 128, 1),      # one query-tile pair, the second tile ragged; exp-section turn protocol on
+    (1, 520, 4, 1, True, 128, 128, 0),      # three pairs (the last one half empty), turn protocol off
+    (2, 300, 2, 2, False, 72, 80, 1),       # vision-tower layout
+    (1, 640, 2, 2, False, 128, 128, 1),     # full attention, five kv tiles for both query tiles
+])
+def test_default_prefill_attention_kernel_is_green_under_the_emulator(emu_v3, B, T, heads, kv_heads, causal, hd, hs, pingpong):
+    """attn3_fwd_kernel is what every prefill runs (variant 80); parity-green on the B200, and a CPU regression check here."""
+    g = torch.Generator().manual_seed(T + 1)
+    q_w, kv_w = heads * hs, kv_heads * hs
+    qkv = torch.randn((B * T, q_w + 2 * kv_w), generator=g).to(BF)
+    if hs != hd:
+        v = qkv.view(B * T, heads + 2 * kv_heads, hs)
+        v[:, :, hd:] = 0
+        qkv = v.reshape(B * T, -1).contiguous()
+    want = ref.attention(qkv, B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, causal)
+    got = torch.full((B * T, heads * hd), float("nan")).to(BF)
+    emu_v3.emu_attention3_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal),
+                              C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), pingpong)
     assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2
