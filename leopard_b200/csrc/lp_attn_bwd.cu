@@ -52,7 +52,7 @@ struct AttnBwdArgs {
 
 #ifdef LP_EMULATE
 __device__ __forceinline__ float bw_ex2(float x) { return exp2f(x); }
-__device__ __forceinline__ void row_threads_barrier() { emu_tc::g_named->arrive_and_wait(); }
+__device__ __forceinline__ void row_threads_barrier() { named_bar(1, 128, true); }
 #else
 __device__ __forceinline__ float bw_ex2(float x) {
   float y;

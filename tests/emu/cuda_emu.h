@@ -71,7 +71,7 @@ struct BlockCtx {
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<float> warp_buf;   // [warps][32]
 };
-inline BlockCtx* g_ctx = nullptr;
+inline thread_local BlockCtx* t_ctx = nullptr;   // the block this OS thread belongs to
 inline std::function<void()> g_block_hook;   // run before each block's threads start (per-CTA state reset)
 
 template <typename F>
@@ -86,12 +86,12 @@ void launch(dim3 grid, dim3 block, F&& body) {
         for (unsigned w = 0; w < nwarps; ++w)
           ctx.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - w * 32)));
         ctx.warp_buf.assign(nwarps * 32, 0.f);
-        g_ctx = &ctx;
         if (g_block_hook) g_block_hook();
         std::vector<std::thread> ts;
         ts.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t)
           ts.emplace_back([&, t] {
+            t_ctx = &ctx;
             threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
             blockIdx = {bx, by, bz};
             blockDim = block;
@@ -101,29 +101,29 @@ void launch(dim3 grid, dim3 block, F&& body) {
           });
         for (auto& th : ts) th.join();
       }
-  g_ctx = nullptr;
 }
 inline unsigned linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
 }  // namespace emu
 
-inline void __syncthreads() { emu::g_ctx->block_bar->arrive_and_wait(); }
+inline void __syncthreads() { emu::t_ctx->block_bar->arrive_and_wait(); }
 inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   const unsigned t = emu::linear_tid(), w = t >> 5, l = t & 31;
-  float* buf = emu::g_ctx->warp_buf.data() + w * 32;
+  float* buf = emu::t_ctx->warp_buf.data() + w * 32;
   buf[l] = v;
-  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  emu::t_ctx->warp_bar[w]->arrive_and_wait();
   const float r = buf[l ^ (unsigned)lane_mask];
-  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  emu::t_ctx->warp_bar[w]->arrive_and_wait();
   return r;
 }
 inline bool __any_sync(unsigned, bool pred) {
   const unsigned t = emu::linear_tid(), w = t >> 5, l = t & 31;
-  float* buf = emu::g_ctx->warp_buf.data() + w * 32;
+  float* buf = emu::t_ctx->warp_buf.data() + w * 32;
   buf[l] = pred ? 1.f : 0.f;
-  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  emu::t_ctx->warp_bar[w]->arrive_and_wait();
   bool any = false;
   for (int i = 0; i < 32; ++i) any |= buf[i] != 0.f;
-  emu::g_ctx->warp_bar[w]->arrive_and_wait();
+  emu::t_ctx->warp_bar[w]->arrive_and_wait();
   return any;
 }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_ctx->warp_bar[emu::linear_tid() >> 5]->arrive_and_wait(); }
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
