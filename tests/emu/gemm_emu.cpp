@@ -1,0 +1,66 @@
+// Test infrastructure: the persistent tcgen05 GEMM (leopard_b200/csrc/lp_gemm.cu, gemm_bf16_kernel) run on the CPU under
+// tests/emu/tc_emu.h, one CTA per tile and as CTA PAIRS (cluster of 2, cta_group::2).  `gemm_kernel.inc` is the kernel part of
+// lp_gemm.cu, cut by the test; three lines are rewritten there: the dynamic shared-memory declaration (per-CTA buffer), the
+// epilogue's named-barrier PTX statement and the hardware tanh of the GELU helper.
+#include "tc_emu.h"
+enum { LP_ACT_NONE = 0, LP_ACT_GELU_TANH = 1, LP_ACT_GELU_ERF = 2, LP_ACT_SWIGLU = 3 };
+#include "emu_helpers.inc"
+#include "gemm_kernel.inc"
+
+using namespace lp;
+
+static CUtensorMap tmap2(const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t b0, uint32_t b1, int elem, int swz) {
+  CUtensorMap m;
+  m.base = reinterpret_cast<const uint8_t*>(base);
+  m.dims[0] = inner; m.dims[1] = outer; m.dims[2] = 1;
+  m.strides[0] = ld * elem; m.strides[1] = 0;
+  m.box[0] = b0; m.box[1] = b1; m.box[2] = 1;
+  m.elem_bytes = elem; m.swizzle = swz;
+  return m;
+}
+
+template <int BN, int STAGES, bool CTA2>
+static void run(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& args, int ctas) {
+  if constexpr (CTA2) {
+    emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_kernel<BN, STAGES, true>(a, b, c, args); });
+  } else {
+    emu::g_block_hook = [] { emu_tc::reset(); };
+    emu::launch(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_kernel<BN, STAGES, false>(a, b, c, args); });
+    emu::g_block_hook = nullptr;
+  }
+}
+
+// Same argument preparation as lp_gemm_bf16 (host part of lp_gemm.cu) for an explicit block_n / pair / grid choice.
+extern "C" void emu_gemm(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                         const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
+                         int block_n, int pair, int group_m, int ctas) {
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32;
+  args.bias = bias;
+  args.residual = reinterpret_cast<const bf16*>(residual);
+  args.ldr = ldr; args.res_row_mod = res_row_mod;
+  args.act = act;
+  const int bm = pair ? 2 * GEMM_BM : GEMM_BM;
+  args.num_m_blk = (M + bm - 1) / bm;
+  args.num_n_blk = (N + block_n - 1) / block_n;
+  args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+  args.group_m = group_m > args.num_m_blk ? args.num_m_blk : group_m;
+  args.prefetch_a = 0;
+  CUtensorMap tmC = tmap2(C, act == LP_ACT_SWIGLU ? N / 2 : N, M, ldc, 32, 32, 2, 64);
+  CUtensorMap tmA = tmap2(A, K, M, lda, GEMM_BK, GEMM_BM, 2, 128);
+  CUtensorMap tmB = tmap2(W, K, N, ldw, GEMM_BK, pair ? block_n / 2 : block_n, 2, 128);
+  if (pair) {
+    switch (block_n) {
+      case 256: run<256, 6, true>(tmA, tmB, tmC, args, ctas); break;
+      case 192: run<192, 7, true>(tmA, tmB, tmC, args, ctas); break;
+      default: run<128, 8, true>(tmA, tmB, tmC, args, ctas); break;
+    }
+  } else {
+    switch (block_n) {
+      case 256: run<256, 4, false>(tmA, tmB, tmC, args, ctas); break;
+      case 160: run<160, 5, false>(tmA, tmB, tmC, args, ctas); break;
+      default: run<128, 6, false>(tmA, tmB, tmC, args, ctas); break;
+    }
+  }
+}
