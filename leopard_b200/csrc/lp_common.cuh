@@ -242,6 +242,27 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// 4-CTA clusters (two CTA pairs sharing an operand): a cta_group::2 TMA load multicast to the CTAs in `cta_mask`; the data
+// lands at the same shared-memory offset in every destination CTA and the transaction bytes are counted on the barrier at
+// `bar_cluster_addr`'s offset in each destination's PAIR LEADER (the address names the issuing pair's leader, i.e. has
+// the peer bit cleared — CUTLASS SM100_TMA_2SM_LOAD_MULTICAST).
+__device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                       int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// commit arriving on the barrier at the same smem offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 #define LP_TMEM_LD_32(regs, taddr)                                                                                \
   asm volatile(                                                                                                   \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                   \

@@ -6,6 +6,7 @@
 enum { LP_ACT_NONE = 0, LP_ACT_GELU_TANH = 1, LP_ACT_GELU_ERF = 2, LP_ACT_SWIGLU = 3 };
 #include "emu_helpers.inc"
 #include "gemm_kernel.inc"
+#include "gemm4_kernel.inc"
 
 using namespace lp;
 
@@ -62,5 +63,37 @@ extern "C" void emu_gemm(const void* A, long long lda, const void* W, long long 
       case 160: run<160, 5, false>(tmA, tmB, tmC, args, ctas); break;
       default: run<128, 6, false>(tmA, tmB, tmC, args, ctas); break;
     }
+  }
+}
+
+
+// 4-CTA clusters (lp_gemm4.cu): argument preparation as in lp_gemm_bf16's mode-2 branch
+template <int BN, int STAGES>
+static void run4(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& args, int ctas) {
+  emu_tc::launch_clusters(dim3(ctas), dim3(GEMM_THREADS), 4, [&] { gemm4_bf16_kernel<BN, STAGES>(a, b, c, args); });
+}
+
+extern "C" void emu_gemm4(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                          const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
+                          int block_n, int group_m, int ctas) {
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K;
+  args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32;
+  args.bias = bias;
+  args.residual = reinterpret_cast<const bf16*>(residual);
+  args.ldr = ldr; args.res_row_mod = res_row_mod;
+  args.act = act;
+  args.num_m_blk = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  args.num_n_blk = ((N + block_n - 1) / block_n + 1) / 2;      // column-block PAIRS
+  args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+  args.group_m = group_m > args.num_m_blk ? args.num_m_blk : group_m;
+  args.prefetch_a = 0;
+  CUtensorMap tmC = tmap2(C, act == LP_ACT_SWIGLU ? N / 2 : N, M, ldc, 32, 32, 2, 64);
+  CUtensorMap tmAh = tmap2(A, K, M, lda, GEMM_BK, GEMM_BM / 2, 2, 128);
+  CUtensorMap tmB = tmap2(W, K, N, ldw, GEMM_BK, block_n / 2, 2, 128);
+  switch (block_n) {
+    case 256: run4<256, 6>(tmAh, tmB, tmC, args, ctas); break;
+    case 192: run4<192, 7>(tmAh, tmB, tmC, args, ctas); break;
+    default: run4<128, 8>(tmAh, tmB, tmC, args, ctas); break;
   }
 }

@@ -10,8 +10,9 @@
 //              (start, LBO, SBO) with the swizzle applied to the absolute address bits; cta_group::2: M = 256 over the two
 //              CTAs of a pair (A rows and B rows split between their shared memories, D rows between their TMEMs)
 //   TMEM       128 lanes x 512 columns of 32-bit cells per CTA; 32x32b loads / stores address lane = base lane + lane id
-//   cluster    pairs of CTAs run concurrently (emu_tc::launch_pairs): %cluster_ctarank, mapa, remote mbarrier arrive,
-//              barrier.cluster, commit multicast to both CTAs
+//   cluster    clusters of 2 or 4 CTAs run concurrently (emu_tc::launch_clusters): %cluster_ctarank, mapa, remote mbarrier
+//              arrive, barrier.cluster, masked multicast commits, cta_group::2 multicast TMA loads (bytes counted on each
+//              destination's pair leader)
 //   named barriers  bar.sync / bar.arrive id, n
 // The layouts are the author's reading of the hardware, the same reading the GPU-verified kernels are built on; the emulator
 // checks a kernel's LOGIC (protocol, indexing, masks, operand roles), not the hardware.
@@ -59,16 +60,16 @@ struct Cta {
   uint32_t rank = 0;
 };
 inline std::mutex g_mu;
-inline Cta g_cta[2];
-alignas(1024) inline uint8_t g_smem1[232448];
-inline uint32_t g_tmem_store[2][128][512];
+inline Cta g_cta[4];
+alignas(1024) inline uint8_t g_smem_peers[3][232448];
+inline uint32_t g_tmem_store[4][128][512];
 inline thread_local Cta* t_cta = &g_cta[0];
 inline std::unique_ptr<std::barrier<>> g_cluster_bar;
 inline Cta& cta() { return *t_cta; }
 
 inline void reset_cta(int r) {
   Cta& c = g_cta[r];
-  c.smem = r == 0 ? smem_raw : g_smem1;
+  c.smem = r == 0 ? smem_raw : g_smem_peers[r - 1];
   c.tmem = g_tmem_store[r];
   c.bars.clear();
   for (auto& b : c.nbar) b = NamedBar();
@@ -99,30 +100,29 @@ inline uint32_t swz(uint32_t a, int mode) { return mode == 128 ? swz128(a) : mod
 inline Cta& cta_of(uint32_t addr) { return (addr >> 28) ? g_cta[(addr >> 28) - 1] : cta(); }
 inline uint32_t off_of(uint32_t addr) { return addr & 0x0fffffffu; }
 
-// Runs the grid as concurrent PAIRS of CTAs (cluster dimension 2): blocks 2k and 2k + 1 together.
+// Runs the grid as concurrent CLUSTERS of `csize` CTAs (2 or 4): blocks csize k .. csize k + csize - 1 together.
 template <typename F>
-void launch_pairs(dim3 grid, dim3 block, F&& body) {
+void launch_clusters(dim3 grid, dim3 block, unsigned csize, F&& body) {
   const unsigned nthreads = block.x;
-  for (unsigned p = 0; p < grid.x / 2; ++p) {
+  for (unsigned p = 0; p < grid.x / csize; ++p) {
     {
       std::lock_guard<std::mutex> l(g_mu);
-      reset_cta(0);
-      reset_cta(1);
+      for (unsigned r = 0; r < csize; ++r) reset_cta((int)r);
     }
-    g_cluster_bar = std::make_unique<std::barrier<>>(2 * nthreads);
-    ::emu::BlockCtx ctx[2];
-    for (int r = 0; r < 2; ++r) {
+    g_cluster_bar = std::make_unique<std::barrier<>>(csize * nthreads);
+    std::vector<::emu::BlockCtx> ctx(csize);
+    for (unsigned r = 0; r < csize; ++r) {
       ctx[r].block_bar = std::make_unique<std::barrier<>>(nthreads);
       for (unsigned w = 0; w < (nthreads + 31) / 32; ++w)
         ctx[r].warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - w * 32)));
       ctx[r].warp_buf.assign(((nthreads + 31) / 32) * 32, 0.f);
     }
     std::vector<std::thread> ts;
-    for (int r = 0; r < 2; ++r)
+    for (unsigned r = 0; r < csize; ++r)
       for (unsigned t = 0; t < nthreads; ++t)
         ts.emplace_back([&, r, t] {
           threadIdx = {t, 0, 0};
-          blockIdx = {2 * p + (unsigned)r, 0, 0};
+          blockIdx = {csize * p + r, 0, 0};
           blockDim = block;
           gridDim = grid;
           t_cta = &g_cta[r];
@@ -133,6 +133,8 @@ void launch_pairs(dim3 grid, dim3 block, F&& body) {
     for (auto& th : ts) th.join();
   }
 }
+template <typename F>
+void launch_pairs(dim3 grid, dim3 block, F&& body) { launch_clusters(grid, block, 2, body); }
 }  // namespace emu_tc
 
 inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - emu_tc::cta().smem); }
@@ -223,10 +225,9 @@ inline uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) { return emu_tc::of
 // ---- TMA
 inline void tma_prefetch_desc(const CUtensorMap*) {}
 inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
-inline void tma_load_tile(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, int c2) {
-  const uint32_t dst = smem_u32(smem_dst);
+inline void tma_load_tile_to(emu_tc::Cta& dst_cta, uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2) {
   const uint32_t row_bytes = m->box[0] * m->elem_bytes;
-  uint8_t* sm = emu_tc::cta().smem;
+  uint8_t* sm = dst_cta.smem;
   for (uint32_t r = 0; r < m->box[1]; ++r)
     for (uint32_t e = 0; e < m->box[0]; ++e) {
       const long col = (long)c0 + e, row = (long)c1 + r;
@@ -235,7 +236,20 @@ inline void tma_load_tile(void* smem_dst, const CUtensorMap* m, uint32_t bar_add
         std::memcpy(&v, m->base + col * 2 + row * m->strides[0] + (uint64_t)c2 * m->strides[1], 2);
       std::memcpy(sm + emu_tc::swz(dst + r * row_bytes + e * 2, m->swizzle), &v, 2);
     }
+}
+inline void tma_load_tile(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, int c2) {
+  tma_load_tile_to(emu_tc::cta(), smem_u32(smem_dst), m, c0, c1, c2);
   mbar_complete_tx_addr(bar_addr, m->box[0] * m->box[1] * m->elem_bytes);
+}
+// cta_group::2 multicast: the box lands at the same offset in every CTA of the mask; each destination's bytes are counted on
+// the barrier at the given offset in that destination's PAIR LEADER (even rank)
+inline void tma_load_2d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, uint16_t mask) {
+  const uint32_t dst = smem_u32(smem_dst), boff = emu_tc::off_of(bar_cluster_addr);
+  for (uint32_t d = 0; d < 4; ++d)
+    if (mask & (1u << d)) {
+      tma_load_tile_to(emu_tc::g_cta[d], dst, m, c0, c1, 0);
+      mbar_complete_tx_addr(boff | (((d & ~1u) + 1u) << 28), m->box[0] * m->box[1] * m->elem_bytes);
+    }
 }
 inline void tma_load_3d(void* d, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) { tma_load_tile(d, m, smem_u32(bar), c0, c1, c2); }
 inline void tma_load_2d(void* d, const CUtensorMap* m, uint64_t* bar, int c0, int c1) { tma_load_tile(d, m, smem_u32(bar), c0, c1, 0); }
@@ -304,7 +318,7 @@ inline void umma_exec(uint32_t tmem_d, bool a_in_tmem, uint32_t tmem_a, uint64_t
   const uint32_t dcol = tmem_d & 0xffff, acol = tmem_a & 0xffff;
   const int nb = pair ? N / 2 : N;   // B rows held by one CTA
   for (int m = 0; m < M; ++m) {
-    emu_tc::Cta& cm = pair ? emu_tc::g_cta[m >> 7] : self;
+    emu_tc::Cta& cm = pair ? emu_tc::g_cta[(self.rank & ~1u) + (m >> 7)] : self;
     const int ml = m & 127;
     float a[16];
     for (int k = 0; k < 16; ++k) {
@@ -316,7 +330,7 @@ inline void umma_exec(uint32_t tmem_d, bool a_in_tmem, uint32_t tmem_a, uint64_t
       }
     }
     for (int n = 0; n < N; ++n) {
-      const uint8_t* bs = pair ? emu_tc::g_cta[n / nb].smem : self.smem;
+      const uint8_t* bs = pair ? emu_tc::g_cta[(self.rank & ~1u) + n / nb].smem : self.smem;
       const int nl = n % nb;
       float acc = 0.f;
       if (accumulate) std::memcpy(&acc, &cm.tmem[ml][dcol + n], 4);
@@ -333,11 +347,12 @@ inline void umma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32
 inline void umma_ts(uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) { umma_exec(d, true, a, 0, db, idesc, acc, false); }
 inline void umma_ss_pair(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { umma_exec(d, false, 0, da, db, idesc, acc, true); }
 inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }   // MMAs run synchronously: everything issued has retired
-inline void umma_commit_pair(uint64_t* bar) {                  // arrives at the same offset in both CTAs of the pair
+inline void umma_commit_mask(uint64_t* bar, uint16_t mask) {   // arrives at the same offset in every CTA of the mask
   const uint32_t off = smem_u32(bar);
-  mbar_arrive_addr(mapa_u32(off, 0));
-  mbar_arrive_addr(mapa_u32(off, 1));
+  for (uint32_t d = 0; d < 4; ++d)
+    if (mask & (1u << d)) mbar_arrive_addr(mapa_u32(off, d));
 }
+inline void umma_commit_pair(uint64_t* bar) { umma_commit_mask(bar, (uint16_t)(3u << (emu_tc::cta().rank & ~1u))); }
 }  // namespace lp
 
 // ---- the few CUDA built-ins these kernels use beyond cuda_emu.h

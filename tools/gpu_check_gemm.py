@@ -170,7 +170,11 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--pair", action="store_true", help="CTA-pair (cta_group::2) GEMM mode")
     ap.add_argument("--single", action="store_true", help="one CTA per tile")
+    ap.add_argument("--quad", action="store_true", help="4-CTA clusters with A multicast (lp_gemm4.cu, mode 2)")
     args = ap.parse_args()
+    if args.quad:
+        from leopard_b200 import _lib
+        _lib.lib().lp_gemm_set_pair_mode(2)
     if args.pair:
         from leopard_b200 import _lib
         _lib.lib().lp_gemm_set_pair_mode(1)
