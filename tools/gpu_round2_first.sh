@@ -23,7 +23,7 @@ LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash python tools/gpu_train_spee
 # 4b. the 4-CTA multicast GEMM (lp_gemm4.cu): correctness sweep + timing against the pair kernel, then the prefill A/B
 TMO=900 run gemm_quad python tools/gpu_check_gemm.py --quad --time
 TMO=900 run gemm_pair python tools/gpu_check_gemm.py --pair --time
-TMO=900 run ab_quad python tools/gpu_ab_prefill.py pair=1 pair=2 pair=1 pair=2
+TMO=900 run ab_quad python tools/gpu_ab_prefill.py pair=1 pair=2
 # 5. the example loop (Megatron-shim surface) and the regression suite
 TMO=900 run example python examples/llava_sft_loop.py --layers 2 --iters 4
 TMO=1500 run suite python -m pytest tests -m gpu -q -x
