@@ -255,8 +255,28 @@ static int launch4(const CUtensorMap& tmAh, const CUtensorMap& tmB, const CUtens
     LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
+  // persistent kernel with a static round-robin schedule: the grid must not exceed the clusters that are co-resident (GPC
+  // boundaries can leave fewer than SMs / 4 slots for 4-CTA clusters)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * (sm_count() / 4));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    LP_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
   const int tiles = args.num_m_blk * args.num_n_blk;
-  const int clusters = sm_count() / 4;
+  int clusters = sm_count() / 4;
+  if (clusters > max_clusters) clusters = max_clusters;
   LP_CHECK_CUDA(launch_ex(kern, dim3(4 * (tiles < clusters ? tiles : clusters)), dim3(GEMM_THREADS), L::TOTAL, stream, 4,
                           prefill_pdl(), tmAh, tmB, tmC, args));
   LP_CHECK_CUDA(cudaGetLastError());
