@@ -508,10 +508,10 @@ class SFTTrainer:
         if s % 8:
             raise ValueError(f"sequence length {s} must be a multiple of 8")
         R = b * s
+        n_img_rows = int((tokens == cfg.megatron_image_index).sum())      # counted where the batch lives (the host): no device sync
         ids = tokens.reshape(-1).to(self.dev, torch.long).contiguous()
 
         # ---- vision tower (frozen) + projector, keeping what the projector's backward needs
-        n_img_rows = int((ids == cfg.megatron_image_index).sum())
         have_images = images is not None and images.shape[-1] > 100 and n_img_rows > 0
         feats = shuf = z1 = a1 = None
         vit_saved = None
