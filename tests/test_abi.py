@@ -79,3 +79,47 @@ def test_engine_refuses_cpu():
     cfg = reduced(leopard_llava(), 1, 1, 1024)
     with pytest.raises(_lib.NativeError, match="no CPU fallback"):
         PrefillEngine(cfg, NativeWeights(cfg, "cpu"))
+
+
+def _header_prototypes():
+    """name -> list of C parameter type strings, parsed from the header (comments stripped)."""
+    txt = (ROOT / "include" / "leopard_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(lp_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", txt, flags=re.S):
+        params = " ".join(m.group(2).split())
+        protos[m.group(1)] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and argument class (pointer / 64-bit / int / float / double / size_t) of every binding against the C prototype: a
+    mismatch would not fail to load — it would corrupt arguments on the GPU box."""
+    from leopard_b200 import _lib
+
+    def klass(ctype_decl: str) -> str:
+        d = ctype_decl
+        if "*" in d:
+            return "ptr"
+        base = d.rsplit(" ", 1)[0] if " " in d else d
+        if "long long" in base:
+            return "ll"
+        if "size_t" in base:
+            return "sz"
+        if "double" in base:
+            return "f64"
+        if "float" in base:
+            return "f32"
+        return "int"
+
+    def klass_ct(t) -> str:
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) not in (None, "q", "i", "f", "d", "Q", "L", "l"):
+            return "ptr"
+        return {C.c_longlong: "ll", C.c_int: "int", C.c_float: "f32", C.c_double: "f64", C.c_size_t: "sz"}[t]
+
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib._SIGS)
+    for name, (_, argtypes) in _lib._SIGS.items():
+        want = [klass(p) for p in protos[name]]
+        got = [klass_ct(t) for t in argtypes]
+        assert got == want, (name, got, want)
