@@ -19,6 +19,15 @@ from oracle import native_ops
 from oracle import train as OT
 
 
+def _narrow(cfg):
+    """Same architecture at a quarter of the widths (decoder 1024 / 8 q heads x 128 / 2 kv heads / ffn 2048, tower 4 heads x 72):
+    train.py's sequencing does not depend on the widths, the kernels' width-specific paths are covered under the emulator
+    (tests/test_train_kernels_emulated.py), and the CPU suite stays short."""
+    from dataclasses import replace
+    return replace(cfg, dec=replace(cfg.dec, hidden=1024, heads=8, kv_heads=2, ffn=2048),
+                   vit=replace(cfg.vit, hidden=288, heads=4, ffn=512))
+
+
 class _FakeEngine:
     """The two PrefillEngine methods the trainer calls, restated on the CPU."""
 
@@ -39,9 +48,11 @@ class _FakeEngine:
         return out, int(slots.sum())
 
 
-@pytest.fixture()
-def cpu_trainer(monkeypatch):
+@pytest.fixture(params=["narrow"])
+def cpu_trainer(request, monkeypatch):
     cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=2, vocab=324)     # 324 -> padded to 328: padding rows exist
+    if request.param == "narrow":
+        cfg = _narrow(cfg)
     ck = SyntheticCheckpoint(cfg, seed=11)
     nw = load_hf(cfg, lambda n: ck[n], device="cpu")
     monkeypatch.setattr(T, "ops", native_ops)
@@ -91,6 +102,7 @@ def _native_layout(cfg, grads, name):
                       "ln2_g": "post_attention_layernorm.weight"}[kind]]
 
 
+@pytest.mark.parametrize("cpu_trainer", ["narrow", "full"], indirect=True)     # once at Leopard-LLaVA's real widths as well
 def test_sft_step_sequencing_matches_autograd_oracle(cpu_trainer):
     cfg, ck, nw, eng = cpu_trainer
     tokens, labels, weights, images = _batch(cfg, b=2, n_text=15, seed=3)        # s = 169 + 15 = 184 (multiple of 8)
@@ -210,7 +222,7 @@ _SMALL_CACHE = {}
 
 def _small_cpu_engine():
     """Fresh native weights every call (trainers update them in place); the synthetic tensors are drawn once per process."""
-    cfg = reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=320)
+    cfg = _narrow(reduced(leopard_llava(), vit_layers=1, dec_layers=1, vocab=320))
     ck = SyntheticCheckpoint(cfg, seed=5)
 
     def get(name):
@@ -312,7 +324,7 @@ def test_unfrozen_vision_tower_backward_matches_autograd_oracle(cpu_trainer):
     """freeze_vision_tower=False: the tower's forward is re-sequenced in train.py (saved layer inputs) and its backward runs
     through LayerNorm / GELU / bias / position-embedding / patch-embedding gradients and the per-(crop, head) attention
     backward on the zero-padded 80-wide head layout."""
-    cfg = reduced(leopard_llava(), vit_layers=2, dec_layers=1, vocab=320)
+    cfg = _narrow(reduced(leopard_llava(), vit_layers=2, dec_layers=1, vocab=320))
     ck = SyntheticCheckpoint(cfg, seed=13)
     nw = load_hf(cfg, lambda n: ck[n], device="cpu")
     eng = _FakeEngine(cfg, ck, nw)
