@@ -7,7 +7,8 @@ over C-ABI calls (allocation, shapes and ordering only; every contraction, reduc
                           embeddings -> 32 decoder layers -> final norm -> fp32 logits            (same kernels as prefill)
   loss_func    :101-121   lp_ce_fwd_bwd on rows shifted by one (weights = loss_mask / sum(loss_mask) / dp_world)
   backward                layer by layer with full recompute from the saved layer inputs (--recompute-granularity full
-                          --recompute-method uniform --recompute-num-layers 1, run_pretrain_megatron_llava.sh:96-100):
+                          --recompute-method uniform --recompute-num-layers 1, run_pretrain_megatron_llava.sh:96-100;
+                          recompute="none" keeps the activations instead — they fit a B200 — and skips that quarter of the work):
                           dgrad = lp_gemm_bf16(dY, W^T), wgrad = lp_gemm_bf16(dY^T, X^T) -> fp32 main grads
                           (lp_transpose_bf16 supplies the re-laid-out operands), norm / SwiGLU / GELU / RoPE / merge
                           backward in lp_train.cu; attention backward over materialised [T, T] score tiles per head
@@ -118,7 +119,7 @@ class SFTTrainer:
     def __init__(self, engine, lr: float = 1e-5, min_lr: float = 0.0, warmup_iters: int = 0, decay_iters: int = 0,
                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
                  clip_grad: float = 1.0, freeze_llm: bool = False, freeze_vision_tower: bool = True, process_group=None,
-                 attn_bwd: Optional[str] = None):
+                 attn_bwd: Optional[str] = None, recompute: str = "full"):
         if not torch.cuda.is_available():
             raise _lib.NativeError("leopard_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         _lib.lib()
@@ -154,6 +155,13 @@ class SFTTrainer:
         self.kv_w = d.kv_heads * d.head_dim
         self.qkv_w = self.q_w + 2 * self.kv_w
         self._scratch_g = None
+        # "full": keep only each layer's input and recompute the layer in the backward pass (the reference's setting,
+        # --recompute-granularity full).  "none": keep every layer's activations — ~0.53 GB per decoder layer at S = 4096,
+        # 17 GB for the 32 layers, which the 180 GB of a B200 has room for next to the 144 GB of weights and optimizer state
+        # — and skip the recompute, a quarter of the step's GEMM work.
+        if recompute not in ("full", "none"):
+            raise ValueError(f"recompute must be 'full' or 'none', got {recompute!r}")
+        self.recompute = recompute
         self._accum = False        # True while a micro-batch after the first is being back-propagated
         self.skipped_last = False  # the last step() found non-finite gradients and left the weights untouched
         self._acc_scratch = {}
@@ -360,11 +368,11 @@ class SFTTrainer:
         self._commit(bname, sb)
         return dx
 
-    def _vit_layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, n_img: int) -> torch.Tensor:
+    def _vit_layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, n_img: int, acts=None) -> torch.Tensor:
         v, L = self.cfg.vit, self._vit_weights(i)
         hs = self.w.vit_dims.head_stride
         p = f"vit.{i}."
-        h, qkv, att, x2, h2, z, a = self._vit_layer_forward(i, x, n_img, keep=True)
+        h, qkv, att, x2, h2, z, a = acts if acts is not None else self._vit_layer_forward(i, x, n_img, keep=True)
         self._wgrad(p + "fc2_w", dy, a)
         self._colsum(p + "fc2_b", dy)
         da = self._dgrad(dy, L["fc2_w"])
@@ -401,8 +409,13 @@ class SFTTrainer:
         x = ops.gemm(A, w["vit.patch_w"], bias=w["vit.patch_b"], residual=w["vit.pos"], res_row_mod=v.tokens)
         xs = []
         for i in range(v.layers):
-            xs.append(x)
-            x = self._vit_layer_forward(i, x, n_img, keep=False)
+            if self.recompute == "none":
+                acts = self._vit_layer_forward(i, x, n_img, keep=True)
+                xs.append((x, acts))
+                x = ops.gemm(acts[6], self._vit_weights(i)["fc2_w"], bias=self._vit_weights(i)["fc2_b"], residual=acts[3])
+            else:
+                xs.append((x, None))
+                x = self._vit_layer_forward(i, x, n_img, keep=False)
         shuf = ops.layernorm(x, w["vit.post_g"], w["vit.post_b"], v.eps, shuffle_side=v.grid)
         return shuf, (A, xs, x, n_img)
 
@@ -411,17 +424,18 @@ class SFTTrainer:
         A, xs, x_last, n_img = saved
         dx = self._ln_bwd("vit.post_g", "vit.post_b", x_last, w["vit.post_g"], ops.pixel_unshuffle(dshuf, v.grid))
         for i in reversed(range(v.layers)):
-            dx = self._vit_layer_backward(i, xs.pop(), dx, n_img)
+            x_in, acts = xs.pop()
+            dx = self._vit_layer_backward(i, x_in, dx, n_img, acts)
         sink = self._sink("vit.pos")                    # the forward adds pos[row % tokens] to every crop
         ops.rowmod_sum(dx, v.tokens, sink)
         self._commit("vit.pos", sink)
         self._colsum("vit.patch_b", dx)
         self._wgrad("vit.patch_w", dx, A)               # [hidden, patch_k_pad]; the K-padding columns of A are zero
 
-    def _layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, b: int, s: int) -> torch.Tensor:
+    def _layer_backward(self, i: int, x: torch.Tensor, dy: torch.Tensor, b: int, s: int, acts=None) -> torch.Tensor:
         d = self.cfg.dec
         ln1, wqkv, wo, ln2, wgu, wd = self._layer_weights(i)
-        h1, qkv, att, x2, h2, gu, m = self._layer_forward(i, x, b, s, keep=True)
+        h1, qkv, att, x2, h2, gu, m = acts if acts is not None else self._layer_forward(i, x, b, s, keep=True)
         # MLP
         self._wgrad(f"dec.{i}.down_w", dy, m)
         dm = self._dgrad(dy, wd)
@@ -533,11 +547,16 @@ class SFTTrainer:
         self._cos, self._sin = ops.rope_table(pos, w["dec.inv_freq"])
         self._neg_sin = -self._sin
 
-        # ---- decoder forward, layer inputs kept for the recompute
+        # ---- decoder forward; kept: every layer's input (recompute = 'full') or all of its activations ('none')
         xs = []
         for i in range(d.layers):
-            xs.append(x)
-            x = self._layer_forward(i, x, b, s, keep=False)
+            if self.recompute == "none":
+                acts = self._layer_forward(i, x, b, s, keep=True)
+                xs.append((x, acts))
+                x = ops.gemm(acts[6], w[f"dec.{i}.down_w"], residual=acts[3])       # m W_down^T + x2
+            else:
+                xs.append((x, None))
+                x = self._layer_forward(i, x, b, s, keep=False)
         hN = ops.rmsnorm(x, w["dec.final_g"], d.eps)
         logits = ops.gemm(hN, w["dec.lm_head"], out_fp32=True)                    # [R, vocab_padded] fp32
 
@@ -562,7 +581,9 @@ class SFTTrainer:
             reduce(bucket)      # 'dec.lm_head' + 'dec.final_g'
             bucket += 1
         for i in reversed(range(d.layers)):
-            dx = self._layer_backward(i, xs.pop(), dx, b, s)
+            x_in, acts = xs.pop()
+            dx = self._layer_backward(i, x_in, dx, b, s, acts)
+            del acts
             if not self.freeze_llm:
                 reduce(bucket)
                 bucket += 1

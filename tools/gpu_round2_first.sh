@@ -20,6 +20,7 @@ run step_flash python -m pytest $ZZ --runxfail -q -k "flash_backward_matches_mat
 TMO=900 run speed_l4_mat   python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
 LEOPARD_ATTN_BWD=flash TMO=900 run speed_l4_flash python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
 LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash python tools/gpu_train_speed.py --steps 2
+LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash_norecompute python tools/gpu_train_speed.py --steps 2 --recompute none
 # 4b. the 4-CTA multicast GEMM (lp_gemm4.cu): correctness sweep + timing against the pair kernel, then the prefill A/B
 TMO=900 run gemm_quad python tools/gpu_check_gemm.py --quad --time
 TMO=900 run gemm_pair python tools/gpu_check_gemm.py --pair --time

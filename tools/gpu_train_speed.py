@@ -26,13 +26,14 @@ def main():
     ap.add_argument("--seq", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--freeze-llm", action="store_true")
+    ap.add_argument("--recompute", default="full", choices=["full", "none"])
     a = ap.parse_args()
     cfg = leopard_llava()
     if a.layers != 32 or a.vit_layers != 27:
         cfg = reduced(cfg, vit_layers=a.vit_layers, dec_layers=a.layers)
     dev = "cuda:0"
     eng = PrefillEngine(cfg, random_native(cfg, dev))
-    tr = SFTTrainer(eng, lr=1e-5, freeze_llm=a.freeze_llm)
+    tr = SFTTrainer(eng, lr=1e-5, freeze_llm=a.freeze_llm, recompute=a.recompute)
     rows = a.crops * cfg.tokens_per_crop
     assert rows < a.seq
     g = torch.Generator().manual_seed(0)
@@ -58,7 +59,7 @@ def main():
     timed = out[1:] or out          # --steps 0: a single (cold) step, for profiler runs
     ms = sum(o["ms"] for o in timed) / len(timed)
     print(json.dumps(dict(metric="sft_tokens_per_s", value=a.seq / ms * 1e3, ms_per_step=ms, seq=a.seq, crops=a.crops,
-                          layers=a.layers, freeze_llm=a.freeze_llm, launches_per_step=timed[-1]["launches"],
+                          layers=a.layers, freeze_llm=a.freeze_llm, recompute=a.recompute, launches_per_step=timed[-1]["launches"],
                           peak_gb=torch.cuda.max_memory_allocated() / 2 ** 30, steps=out)))
 
 
