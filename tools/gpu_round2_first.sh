@@ -20,7 +20,9 @@ run step_flash python -m pytest $ZZ --runxfail -q -k "flash_backward_matches_mat
 TMO=900 run speed_l4_mat   python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
 LEOPARD_ATTN_BWD=flash TMO=900 run speed_l4_flash python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
 LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash python tools/gpu_train_speed.py --steps 2
-LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash_norecompute python tools/gpu_train_speed.py --steps 2 --recompute none
+# recompute on / off at 16 layers (the full model + kept activations needs ~172 GB: too close to the 180 GB for a first run)
+LEOPARD_ATTN_BWD=flash TMO=900 run speed_l16_flash_full python tools/gpu_train_speed.py --layers 16 --steps 2
+LEOPARD_ATTN_BWD=flash TMO=900 run speed_l16_flash_none python tools/gpu_train_speed.py --layers 16 --steps 2 --recompute none
 # 4b. the 4-CTA multicast GEMM (lp_gemm4.cu): correctness sweep + timing against the pair kernel, then the prefill A/B
 TMO=900 run gemm_quad python tools/gpu_check_gemm.py --quad --time
 TMO=900 run gemm_pair python tools/gpu_check_gemm.py --pair --time
