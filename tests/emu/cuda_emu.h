@@ -35,9 +35,12 @@ inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
 // ---- bf16 ------------------------------------------------------------------------------------------------------------
+struct __nv_bfloat16;
+inline __nv_bfloat16 __float2bfloat16(float f);
 struct __nv_bfloat16 {
   uint16_t bits;
   __nv_bfloat16() = default;
+  explicit __nv_bfloat16(float f);
   operator float() const {
     uint32_t u = (uint32_t)bits << 16;
     float f;
@@ -54,6 +57,7 @@ inline __nv_bfloat16 __float2bfloat16(float f) {   // round to nearest even, NaN
   r.bits = (uint16_t)(u >> 16);
   return r;
 }
+inline __nv_bfloat16::__nv_bfloat16(float f) { bits = __float2bfloat16(f).bits; }
 struct __nv_bfloat162 { __nv_bfloat16 x, y; };
 inline __nv_bfloat162 __floats2bfloat162_rn(float lo, float hi) { return {__float2bfloat16(lo), __float2bfloat16(hi)}; }
 inline float2 __bfloat1622float2(__nv_bfloat162 v) { return {(float)v.x, (float)v.y}; }
@@ -74,33 +78,40 @@ struct BlockCtx {
 inline thread_local BlockCtx* t_ctx = nullptr;   // the block this OS thread belongs to
 inline std::function<void()> g_block_hook;   // run before each block's threads start (per-CTA state reset)
 
+// One pool of `nthreads` OS threads walks the grid block by block (blocks run one after another); per block, thread 0 rebuilds
+// the block context (fresh __syncthreads / warp barriers) between two pool-wide barriers.
 template <typename F>
 void launch(dim3 grid, dim3 block, F&& body) {
   const unsigned nthreads = block.x * block.y * block.z;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        BlockCtx ctx;
-        ctx.block_bar = std::make_unique<std::barrier<>>(nthreads);
-        const unsigned nwarps = (nthreads + 31) / 32;
-        for (unsigned w = 0; w < nwarps; ++w)
-          ctx.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - w * 32)));
-        ctx.warp_buf.assign(nwarps * 32, 0.f);
-        if (g_block_hook) g_block_hook();
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t)
-          ts.emplace_back([&, t] {
-            t_ctx = &ctx;
-            threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-            blockIdx = {bx, by, bz};
-            blockDim = block;
-            gridDim = grid;
-            body();
-            ctx.block_bar->arrive_and_drop();   // a thread that has returned no longer takes part in __syncthreads
-          });
-        for (auto& th : ts) th.join();
+  const unsigned nwarps = (nthreads + 31) / 32;
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  std::barrier<> pool_bar(nthreads);
+  std::unique_ptr<BlockCtx> ctx;
+  std::vector<std::thread> ts;
+  ts.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    ts.emplace_back([&, t] {
+      threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      blockDim = block;
+      gridDim = grid;
+      for (unsigned long long b = 0; b < nblocks; ++b) {
+        pool_bar.arrive_and_wait();              // every thread has left the previous block
+        if (t == 0) {
+          ctx = std::make_unique<BlockCtx>();
+          ctx->block_bar = std::make_unique<std::barrier<>>(nthreads);
+          for (unsigned w = 0; w < nwarps; ++w)
+            ctx->warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - w * 32)));
+          ctx->warp_buf.assign(nwarps * 32, 0.f);
+          if (g_block_hook) g_block_hook();
+        }
+        pool_bar.arrive_and_wait();              // the block's context is ready
+        t_ctx = ctx.get();
+        blockIdx = {(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
+        body();
+        ctx->block_bar->arrive_and_drop();       // a thread that has returned no longer takes part in __syncthreads
       }
+    });
+  for (auto& th : ts) th.join();
 }
 inline unsigned linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
 }  // namespace emu
