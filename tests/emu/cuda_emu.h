@@ -8,8 +8,12 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -74,6 +78,16 @@ struct BlockCtx {
   std::unique_ptr<std::barrier<>> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<float> warp_buf;   // [warps][32]
+  // shuffles with a partial member mask synchronise only the lanes named in the mask (one barrier per (warp, mask))
+  std::mutex sub_mu;
+  std::map<std::pair<unsigned, unsigned>, std::unique_ptr<std::barrier<>>> sub_bar;
+  std::barrier<>& group(unsigned warp, unsigned mask) {
+    if (mask == 0xffffffffu) return *warp_bar[warp];
+    std::lock_guard<std::mutex> l(sub_mu);
+    auto& b = sub_bar[{warp, mask}];
+    if (!b) b = std::make_unique<std::barrier<>>(__builtin_popcount(mask));
+    return *b;
+  }
 };
 inline thread_local BlockCtx* t_ctx = nullptr;   // the block this OS thread belongs to
 inline std::function<void()> g_block_hook;   // run before each block's threads start (per-CTA state reset)
@@ -85,6 +99,7 @@ void launch(dim3 grid, dim3 block, F&& body) {
   const unsigned nthreads = block.x * block.y * block.z;
   const unsigned nwarps = (nthreads + 31) / 32;
   const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  if (std::getenv("EMU_TRACE")) std::fprintf(stderr, "emu: launch grid (%u,%u,%u) block %u\n", grid.x, grid.y, grid.z, nthreads);
   std::barrier<> pool_bar(nthreads);
   std::unique_ptr<BlockCtx> ctx;
   std::vector<std::thread> ts;
@@ -117,13 +132,14 @@ inline unsigned linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + 
 }  // namespace emu
 
 inline void __syncthreads() { emu::t_ctx->block_bar->arrive_and_wait(); }
-inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+inline float __shfl_xor_sync(unsigned mask, float v, int lane_mask) {
   const unsigned t = emu::linear_tid(), w = t >> 5, l = t & 31;
   float* buf = emu::t_ctx->warp_buf.data() + w * 32;
+  std::barrier<>& bar = emu::t_ctx->group(w, mask);
   buf[l] = v;
-  emu::t_ctx->warp_bar[w]->arrive_and_wait();
+  bar.arrive_and_wait();
   const float r = buf[l ^ (unsigned)lane_mask];
-  emu::t_ctx->warp_bar[w]->arrive_and_wait();
+  bar.arrive_and_wait();
   return r;
 }
 inline bool __any_sync(unsigned, bool pred) {
