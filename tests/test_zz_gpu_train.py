@@ -251,3 +251,26 @@ def test_whole_sft_step_with_flash_backward_matches_materialised(native_lib):
         grads[mode] = tr.flat_grad.clone()
     rel = float((grads["flash"] - grads["materialized"]).norm() / grads["materialized"].norm())
     assert rel < 0.03, rel
+
+
+# ---- 4-CTA-cluster GEMM with A multicast (lp_gemm4.cu, opt-in mode 2): the very last test — a wedged cluster traps
+def test_four_cta_multicast_gemm_matches_pair_mode(native_lib):
+    """Same K order as the pair kernel, so the results must be bit-identical; shapes large enough for pair mode (>= 74 tiles),
+    one with an odd number of column blocks (the second pair idles on the last one), one through the SwiGLU epilogue."""
+    from leopard_b200 import _lib
+    L = _lib.lib()
+    cases = [(4096, 4096, 1024, 0, False), (4096, 3840, 512, 0, True), (2048, 8192, 1024, ops.ACT_SWIGLU, True)]
+    try:
+        for M, N, K, act, use_res in cases:
+            a, w = _rand(M, K, seed=M).to(DEV), (_rand(N, K, seed=N) * K ** -0.5).to(DEV)
+            bias = _rand(N, seed=3, dtype=torch.float32).to(DEV)
+            n_out = N // 2 if act == ops.ACT_SWIGLU else N
+            res = _rand(M, n_out, seed=4).to(DEV) if use_res else None
+            L.lp_gemm_set_pair_mode(1)
+            want = ops.gemm(a, w, bias=bias, residual=res, act=act, block_n=256)
+            L.lp_gemm_set_pair_mode(2)
+            got = ops.gemm(a, w, bias=bias, residual=res, act=act, block_n=256)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), (M, N, K, act, float((got.float() - want.float()).abs().max()))
+    finally:
+        L.lp_gemm_set_pair_mode(1)

@@ -24,6 +24,7 @@ LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash python tools/gpu_train_spee
 LEOPARD_ATTN_BWD=flash TMO=900 run speed_l16_flash_full python tools/gpu_train_speed.py --layers 16 --steps 2
 LEOPARD_ATTN_BWD=flash TMO=900 run speed_l16_flash_none python tools/gpu_train_speed.py --layers 16 --steps 2 --recompute none
 # 4b. the 4-CTA multicast GEMM (lp_gemm4.cu): correctness sweep + timing against the pair kernel, then the prefill A/B
+TMO=600 run gemm_quad_eq python -m pytest $ZZ --runxfail -q -k four_cta_multicast
 TMO=900 run gemm_quad python tools/gpu_check_gemm.py --quad --time
 TMO=900 run gemm_pair python tools/gpu_check_gemm.py --pair --time
 TMO=900 run ab_quad python tools/gpu_ab_prefill.py pair=1 pair=2
