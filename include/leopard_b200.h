@@ -346,7 +346,8 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
  *                    dlogits[r] = (softmax - onehot) * weight[r] with weight = loss_mask / sum(loss_mask); weight-0 rows
  *                    cost one zero-fill; columns V..Vp-1 (vocabulary padding) receive 0.
  * lp_embed_bwd:      dE[id] += d[r] for ids >= 0; ids == image_id pass nothing (vlm_model.py:526-533 overwrites those
- *                    rows); other negative ids feed row 0 (the forward's clamp, vlm_model.py:226).  fp32 atomics.
+ *                    rows); other negative ids feed row 0 (the forward's clamp, vlm_model.py:226), ids >= vocab (rows of dE) feed row
+ *                    vocab - 1 like the forward gather.  fp32 atomics.
  * lp_gather_rows_bf16: out[i] = in[idx[i]] — gradient of the image-feature scatter.
  * lp_softmax_bwd:    attention backward over materialised score rows: P = softmax(scale * scores, causal),
  *                    dS = scale * P * (dp - sum_j P dp); bf16 outputs, zeros beyond the causal limit.
@@ -391,7 +392,7 @@ int lp_colsum_bf16(const void* dy, long long ld, int M, int N, float* out, void*
 int lp_ce_fwd_bwd(const void* logits, int logits_fp32, long long ld, const long long* target, const float* weight, float* loss,
                   void* dlogits, long long ldd, int rows, int V, int Vp, void* stream);
 int lp_embed_bwd(const void* d, long long ldd, const long long* ids, int S, long long image_id, float* dE, long long ldE, int D,
-                 void* stream);
+                 long long vocab, void* stream);
 int lp_gather_rows_bf16(const void* in, long long ld_in, const int* idx, int n, int D, void* out, long long ld_out,
                         void* stream);
 int lp_softmax_bwd(const float* scores, long long lds, const float* dp, long long lddp, void* P, long long ldp, void* dS,

@@ -112,7 +112,7 @@ _SIGS = {
     "lp_gelu_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "lp_colsum_bf16": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
     "lp_ce_fwd_bwd": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
-    "lp_embed_bwd": (_i, [_vp, _ll, _vp, _i, _ll, _vp, _ll, _i, _vp]),
+    "lp_embed_bwd": (_i, [_vp, _ll, _vp, _i, _ll, _vp, _ll, _i, _ll, _vp]),
     "lp_gather_rows_bf16": (_i, [_vp, _ll, _vp, _i, _i, _vp, _ll, _vp]),
     "lp_softmax_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _vp]),
     "lp_accumulate_f32": (_i, [_vp, _vp, _ll, _vp]),

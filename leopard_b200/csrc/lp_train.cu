@@ -470,11 +470,12 @@ ce_fwd_bwd_kernel(const T* __restrict__ logits, long long ld, const long long* _
 // pass nothing; other negative ids (pads) read row 0 in the forward (clamp, vlm_model.py:226) and so feed row 0 --------
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const bf16* __restrict__ d, long long ldd, const long long* __restrict__ ids, long long image_id,
-                 float* __restrict__ dE, long long ldE, int D) {
+                 float* __restrict__ dE, long long ldE, int D, long long vocab) {
   const int r = blockIdx.x;
   long long id = ids[r];
   if (id == image_id) return;
   if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;   // the forward gather clamps the same way (merge_copy_kernel)
   for (int c = threadIdx.x * 2; c < D; c += 512) {
     const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + (long long)r * ldd + c));
     atomicAdd(dE + id * ldE + c, v.x);
@@ -792,11 +793,12 @@ extern "C" int lp_ce_fwd_bwd(const void* logits, int logits_fp32, long long ld, 
 }
 
 extern "C" int lp_embed_bwd(const void* d, long long ldd, const long long* ids, int S, long long image_id, float* dE,
-                            long long ldE, int D, void* stream_) {
+                            long long ldE, int D, long long vocab, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LP_REQUIRE(d && ids && dE && S > 0 && D > 0 && D % 2 == 0 && ldd % 2 == 0 && al4(d), "lp_embed_bwd: bad arguments S=%d D=%d", S, D);
+  LP_REQUIRE(vocab > 0, "lp_embed_bwd: vocab=%lld", vocab);
   note_launch();
-  embed_bwd_kernel<<<S, 256, 0, stream>>>(reinterpret_cast<const bf16*>(d), ldd, ids, image_id, dE, ldE, D);
+  embed_bwd_kernel<<<S, 256, 0, stream>>>(reinterpret_cast<const bf16*>(d), ldd, ids, image_id, dE, ldE, D, vocab);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -122,7 +122,22 @@ class GPTModel:
         hf = megatron_to_hf(self.cfg, flatten_language_model_state(state_dict))
         device = self.engine.device
         self._hf_getter = hf.__getitem__
-        self.engine = PrefillEngine(self.cfg, load_hf(self.cfg, self._hf_getter, device))
+        # IN PLACE: an SFTTrainer built before the load (Megatron's order is setup_model_and_optimizer, then
+        # load_checkpoint) keeps pointing at this engine's tensors, the ctypes weight structs and any captured CUDA graph
+        # stay valid; the trainer's fp32 main copies are re-seeded from the loaded weights
+        fresh = load_hf(self.cfg, self._hf_getter, device)
+        old = self.engine.w
+        if len(fresh._keep) != len(old._keep):
+            raise _lib.NativeError("load_state_dict: checkpoint does not match this model's tensor inventory")
+        for dst, src in zip(old._keep, fresh._keep):
+            if dst.shape != src.shape or dst.dtype != src.dtype:
+                raise _lib.NativeError(f"load_state_dict: tensor mismatch {tuple(dst.shape)} vs {tuple(src.shape)}")
+            dst.copy_(src)
+        del fresh
+        for ref in getattr(self.engine, "_trainers", []):
+            tr = ref()
+            if tr is not None:
+                tr.resync_master()
 
     def set_input_tensor(self, t):  # gpt_model.py:86-88
         self.input_tensor = t

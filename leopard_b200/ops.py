@@ -317,7 +317,7 @@ def embed_bwd(d, ids, image_id, dE):
     """dE[id] += d[r] for text rows (lp_embed_bwd); dE fp32 [V, D] must hold the running gradient (zeroed per step)."""
     _chk_bf16(d, "d")
     rc = _lib.lib().lp_embed_bwd(_lib.ptr(d), d.stride(0), _lib.ptr(ids), ids.numel(), image_id, _lib.ptr(dE), dE.stride(0),
-                                 d.shape[1], _lib.stream_ptr())
+                                 d.shape[1], dE.shape[0], _lib.stream_ptr())
     _lib.check(rc, "lp_embed_bwd")
 
 

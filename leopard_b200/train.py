@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -81,7 +82,7 @@ def cosine_lr(it: int, lr: float, min_lr: float, warmup_iters: int, decay_iters:
     """OptimizerParamScheduler.get_lr, 'cosine' (Megatron-LM-240424/megatron/training/optimizer_param_scheduler.py:79-126)."""
     if warmup_iters > 0 and it <= warmup_iters:
         return lr * it / warmup_iters
-    if it > decay_iters:
+    if it > decay_iters or decay_iters <= warmup_iters:
         return min_lr
     ratio = (it - warmup_iters) / (decay_iters - warmup_iters)
     return min_lr + (lr - min_lr) * 0.5 * (math.cos(math.pi * ratio) + 1.0)
@@ -166,7 +167,12 @@ class SFTTrainer:
         self.skipped_last = False  # the last step() found non-finite gradients and left the weights untouched
         self._acc_scratch = {}
         # attention backward: 'materialized' (verified composition of GEMMs + lp_softmax_bwd) or 'flash' (lp_attention_bwd)
-        self.attn_bwd = attn_bwd or os.environ.get("LEOPARD_ATTN_BWD", "materialized")
+        # the model shim re-seeds the fp32 main copies when a checkpoint is loaded into the engine after this trainer was built
+        # (Megatron's order: setup_model_and_optimizer, then load_checkpoint)
+        if not hasattr(engine, "_trainers"):
+            engine._trainers = []
+        engine._trainers.append(weakref.ref(self))
+        self.attn_bwd = attn_bwd or os.environ.get("LEOPARD_ATTN_BWD", "flash")   # flash: 73 vs 102 ms per 4-layer step on a B200
         if self.attn_bwd not in ("materialized", "flash"):
             raise ValueError(f"attn_bwd must be 'materialized' or 'flash', got {self.attn_bwd!r}")
 
@@ -177,6 +183,11 @@ class SFTTrainer:
 
     def grad(self, name: str) -> torch.Tensor:
         return self._view(self.flat_grad, self.layout, name)
+
+    def resync_master(self):
+        """Re-seed the fp32 main copies from the engine's (re-loaded) bf16 weights; Adam moments are kept."""
+        for n in self.master_layout:
+            self._view(self.flat_master, self.master_layout, n).copy_(self.w.named[n].float())
 
     # ------------------------------------------------------------------ optimizer state (checkpoint / resume)
     def state_dict(self) -> dict:
@@ -304,8 +315,14 @@ class SFTTrainer:
         sp = -(-s // 8) * 8                 # leading dimensions padded to 8 elements (TMA row-stride rule)
         dqkv = torch.zeros_like(qkv) if (stride != hd) else torch.empty_like(qkv)
         bf = dict(dtype=torch.bfloat16, device=self.dev)
-        sc = torch.empty((s, sp), dtype=torch.float32, device=self.dev)[:, :s]
-        dp = torch.empty((s, sp), dtype=torch.float32, device=self.dev)[:, :s]
+        sc_full = torch.empty((s, sp), dtype=torch.float32, device=self.dev)
+        dp_full = torch.empty((s, sp), dtype=torch.float32, device=self.dev)
+        sc, dp = sc_full[:, :s], dp_full[:, :s]
+        # the GEMM stores 16-byte groups (N % 8 == 0): a sequence length like 676 (vision tower) gets key / value
+        # operands copied into sp zero-padded rows; the extra score columns [s, sp) are never read
+        pad_kv = sp != s
+        if pad_kv:
+            kpad, vpad = torch.zeros((sp, hd), **bf), torch.zeros((sp, hd), **bf)
         P = torch.empty((s, sp), **bf)[:, :s]
         dS = torch.empty((s, sp), **bf)[:, :s]
         # concatenated-contraction operands: the gap columns [s, sp) of every block stay zero on both sides
@@ -320,12 +337,15 @@ class SFTTrainer:
                 k_g = qkv[rows, k0 + g * stride: k0 + g * stride + hd]
                 v_g = qkv[rows, v0 + g * stride: v0 + g * stride + hd]
                 ops.transpose(k_g, out=kt)
+                if pad_kv:
+                    kpad[:s].copy_(k_g)
+                    vpad[:s].copy_(v_g)
                 for j in range(rep):
                     h = g * rep + j
                     q_h = qkv[rows, h * stride: h * stride + hd]
                     do_h = datt[rows, h * hd:(h + 1) * hd]
-                    ops.gemm(q_h, k_g, out=sc, out_fp32=True)
-                    ops.gemm(do_h, v_g, out=dp, out_fp32=True)
+                    ops.gemm(q_h, kpad if pad_kv else k_g, out=sc_full if pad_kv else sc, out_fp32=True)
+                    ops.gemm(do_h, vpad if pad_kv else v_g, out=dp_full if pad_kv else dp, out_fp32=True)
                     ops.softmax_bwd(sc, dp, causal, scale, P=P, dS=dS)
                     ops.gemm(dS, kt, out=dqkv[rows, h * stride: h * stride + hd])
                     ops.transpose(P, out=pt_cat[:, j * sp: j * sp + s])
@@ -492,7 +512,10 @@ class SFTTrainer:
 
         # ---- clip + AdamW
         w, hp = self.w.named, self.hp
-        lr = hp["lr"] if hp["decay"] <= 0 else cosine_lr(self.iteration, hp["lr"], hp["min_lr"], hp["warmup"], hp["decay"])
+        # Megatron sets the rate from the number of COMPLETED steps (OptimizerParamScheduler.step runs after optimizer.step,
+        # training.py:590-596), so iteration k uses lr(k - 1) and the first warm-up step has lr = 0; Adam's bias correction
+        # keeps the 1-based count
+        lr = hp["lr"] if hp["decay"] <= 0 else cosine_lr(self.iteration - 1, hp["lr"], hp["min_lr"], hp["warmup"], hp["decay"])
         ops.grad_norm([self.flat_grad], hp["clip"], self._norm_ws, self._norm_out)
         for n in self.names:
             model_t = w[n]
@@ -507,6 +530,10 @@ class SFTTrainer:
                 ops.adamw_step(model_t.reshape(-1), g, m, v, None, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"],
                                hp["wd"], self._norm_out)
         loss = torch.stack(losses).mean()
+        if self.world > 1:           # the logged loss is the data-parallel average (average_losses_across_data_parallel_group,
+            loss = loss.clone()      # pretrain_megatron_llava.py:119)
+            torch.distributed.all_reduce(loss, group=self.pg)
+            loss /= self.world
         out = torch.cat([loss.reshape(1), self._norm_out[:1]]).tolist()
         self.skipped_last = not math.isfinite(out[1])
         if self.skipped_last:        # inf / NaN gradients: the update kernels returned without touching anything
@@ -529,6 +556,10 @@ class SFTTrainer:
         have_images = images is not None and images.shape[-1] > 100 and n_img_rows > 0
         feats = shuf = z1 = a1 = None
         vit_saved = None
+        if not have_images:
+            # dummy [1, 10] image (pretrain_megatron_llava.py:188): the reference skips the scatter (vlm_model.py:518), so any
+            # -200 slot keeps the embedding of clamp(id, 0) = row 0 and its gradient flows there
+            ids = ids.clamp(min=0)
         if have_images:
             if self.freeze_vit:
                 shuf = self.eng.vit(images, shuffle=True)

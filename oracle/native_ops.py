@@ -197,7 +197,7 @@ def ce_fwd_bwd(logits, target, weight, vocab):
 
 def embed_bwd(d, ids, image_id, dE):
     keep = ids != image_id
-    dE.index_add_(0, ids[keep].clamp(min=0), d.float()[keep])
+    dE.index_add_(0, ids[keep].clamp(min=0, max=dE.shape[0] - 1), d.float()[keep])
 
 
 def gather_rows(x, idx):

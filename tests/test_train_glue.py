@@ -265,15 +265,16 @@ def test_data_parallel_step_averages_gradients_world2_gloo(cpu_trainer):
         assert p.exitcode == 0
     (_, l0, n0, g0, w0), (_, l1, n1, g1, w1) = got
     assert torch.equal(g0, g1) and n0 == n1 and w0 == w1          # ranks hold the same reduced gradient and stay in sync
-    assert l0 != l1                                               # each reports the loss of its own micro-batch
+    assert l0 == l1                  # the logged loss is the data-parallel average (pretrain_megatron_llava.py:119)
     # single-rank gradients of the two micro-batches, averaged
-    singles = []
+    singles, single_losses = [], []
     for seed in (0, 1):
         cfg, eng = _small_cpu_engine()
         tr = T.SFTTrainer(eng, lr=1e-5)
         loss, _ = tr.step(*_text_batch(cfg, seed=seed), None)
-        assert abs(loss - (l0, l1)[seed]) < 1e-3 * abs(loss)
+        single_losses.append(loss)
         singles.append(tr.flat_grad.clone())
+    assert single_losses[0] != single_losses[1] and abs(0.5 * sum(single_losses) - l0) < 1e-3 * abs(l0)
     want = _fingerprint(tr, 0.5 * (singles[0] + singles[1]))
     # sums and projections are linear in the gradient: they must match the average up to the bf16 noise of the
     # pre-scaled loss weights; the square sums agree to the same order
@@ -400,3 +401,28 @@ def test_no_recompute_mode_gives_the_same_gradients(cpu_trainer):
     # the two differ only by where SwiGLU is rounded in the forward that produces the loss (fused epilogue vs materialised)
     assert abs(losses["full"] - losses["none"]) < 5e-3 * abs(losses["full"])
     assert float((grads["none"] - grads["full"]).norm() / grads["full"].norm()) < 0.02
+
+
+def test_checkpoint_loaded_after_the_trainer_was_built_is_what_gets_trained(cpu_trainer, monkeypatch):
+    """Megatron's order is setup_model_and_optimizer, then load_checkpoint: GPTModel.load_state_dict must load IN PLACE so
+    that the trainer's tensors, its fp32 main copies and the exported checkpoint all refer to the loaded weights."""
+    from leopard_b200 import megatron as M
+    from leopard_b200.native_weights import hf_to_megatron
+    cfg, ck, nw, eng = cpu_trainer
+    model = M.GPTModel.__new__(M.GPTModel)
+    model.cfg, model.engine, model.input_tensor, model._hf_getter = cfg, eng, None, (lambda n: ck[n])
+    tr = T.SFTTrainer(eng, lr=1e-2, clip_grad=1.0)                       # built BEFORE the checkpoint is loaded
+    other = SyntheticCheckpoint(cfg, seed=99)
+    state = {"language_model": M.nest_language_model_state(hf_to_megatron(cfg, lambda n: other[n]))}
+    ptr = eng.w.named["dec.0.o_w"].data_ptr()
+    model.load_state_dict(state)
+    assert model.engine is eng and eng.w.named["dec.0.o_w"].data_ptr() == ptr            # same objects, new values
+    want = load_hf(cfg, lambda n: other[n], device="cpu").named
+    assert all(torch.equal(eng.w.named[n], want[n]) for n in want)
+    assert torch.equal(tr._view(tr.flat_master, tr.master_layout, "dec.0.o_w"), want["dec.0.o_w"].float())
+    loaded = model.state_dict_for_save_checkpoint()["language_model"]["encoder"]["layers.0.self_attention.dense.weight"].clone()
+    tokens, labels, weights, images = _batch(cfg, b=1, n_text=15, seed=4)
+    tr.step(tokens, labels, weights, images)
+    trained = model.state_dict_for_save_checkpoint()["language_model"]["encoder"]["layers.0.self_attention.dense.weight"]
+    assert not torch.equal(trained, loaded)                                # the export sees the update
+    assert torch.equal(trained, eng.w.named["dec.0.o_w"].cpu())            # ... of the tensors forward() uses

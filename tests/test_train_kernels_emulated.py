@@ -118,11 +118,11 @@ def test_masked_loss_forward_backward(emu):
 
 
 def test_embedding_scatter_gather_unshuffle_rowsum(emu):
-    ids = torch.tensor([3, -200, 3, 7, -100, 0, -200, 9])
+    ids = torch.tensor([3, -200, 3, 7, -100, 0, -200, 12345])       # 12345: beyond the table -> last row, like the forward
     d = rnd(8, 64, seed=2)
     want, got = torch.zeros(12, 64), torch.zeros(12, 64)
     ref.embed_bwd(d, ids, -200, want)
-    emu.emu_embed_bwd(P(d), LL(64), P(ids), I(8), LL(-200), P(got), LL(64), I(64))
+    emu.emu_embed_bwd(P(d), LL(64), P(ids), I(8), LL(-200), P(got), LL(64), I(64), LL(12))
     assert err(got, want) < 1e-6 and float(got[1].abs().max()) == 0.0
     src = rnd(20, 64, seed=3)
     idx = torch.tensor([5, 0, 5, 19], dtype=torch.int32)
