@@ -30,8 +30,15 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-IMAGE_SIZES = [(896, 1152)] * 4   # (width, height) x 4 — SlideVQA-shape, BASELINE.json configs[2]
 N_TEXT = 64
+# (width, height) lists — BASELINE.json configs[2] (the metric's configuration) and configs[1]
+WORKLOADS = {
+    "cfg3": {"images": [(896, 1152)] * 4,
+             "label": "cfg3: LLaVA 4x(896x1152) -> adaptive allocation -> 28 crops, 92 prompt ids -> S=4796 merged rows"},
+    "cfg2": {"images": [(1344, 1344)],
+             "label": "cfg2: LLaVA 1x(1344x1344) -> adaptive allocation -> 17 crops, 81 prompt ids -> S=2937 merged rows"},
+}
+IMAGE_SIZES = WORKLOADS["cfg3"]["images"]
 
 
 def load_peaks():
@@ -105,10 +112,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(cfg):
+def make_workload(cfg, name: str = "cfg3"):
     import torch
     from leopard_b200.preprocess import plan_crops
-    per_image = plan_crops(IMAGE_SIZES)          # [7, 7, 7, 7] from the reference allocator
+    per_image = plan_crops(WORKLOADS[name]["images"])          # cfg3: [7, 7, 7, 7] from the reference allocator
     n_crops = sum(per_image)
     g = torch.Generator().manual_seed(1)
     pix = torch.rand((n_crops, 3, cfg.vit.image_size, cfg.vit.image_size), generator=g) * 2 - 1   # U(-1, 1), fp32
@@ -119,13 +126,13 @@ def make_workload(cfg):
     return pix, ids, n_crops, S, per_image
 
 
-def workload_config(per_image, S, world, parallelism):
-    return {"workload": "cfg3: LLaVA 4x(896x1152) -> adaptive allocation -> 28 crops, 92 prompt ids -> S=4796 merged "
-                        "rows, 1 request per GPU per step, last-token logits; SigLIP-SO400M/14-364 tower + projector + "
-                        "Llama-3.1-8B decoder at full size, synthetic weights",
+def workload_config(name, per_image, S, world):
+    """Identical for both arms (the driver compares it)."""
+    return {"workload": WORKLOADS[name]["label"] + ", 1 request per GPU per step, last-token logits; SigLIP-SO400M/14-364 "
+                        "tower + projector + Llama-3.1-8B decoder at full size, synthetic weights",
             "crops_per_image": per_image, "S": S,
             "l2_policy": "inputs larger than L2: 17 GB of weights stream from HBM every step (L2 = 126 MB)",
-            "parallelism": parallelism}
+            "parallelism": f"dp{world}: independent requests, one per GPU per step"}
 
 
 def flops_model(n_crops, S, cfg):
@@ -141,84 +148,39 @@ def flops_model(n_crops, S, cfg):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_sample(cfg, n_crops, S, threads=None):
-    """Time the oracle (restated reference forward, torch-cpu fp32) on a bounded sample of the SAME workload:
-    1 of 27 ViT layers over all crops, projector on all crops, 1 of 32 decoder layers at the full S, final norm +
-    last-row lm_head; extrapolate x27 / x32 (BASELINE.md §3 fallback).  Returns (tokens_per_s, seconds_measured, info)."""
-    import torch
-    from oracle import model as om
-    if threads:
-        torch.set_num_threads(threads)
-    torch.manual_seed(0)
-
-    class ShapeCK:
-        """random tensor per distinct shape (values do not affect dense CPU timing)"""
-        def __init__(self, cfg):
-            from leopard_b200.weights import tensor_specs
-            self.specs = {n: s for n, s, _ in tensor_specs(cfg)}
-            self.cache = {}
-
-        def f32(self, name):
-            s = self.specs[name]
-            if s not in self.cache:
-                self.cache[s] = torch.randn(s) * 0.02
-            return self.cache[s]
-
-    ck = ShapeCK(cfg)
-    t_all = time.perf_counter()
-    with torch.no_grad():
-        pix = torch.rand(n_crops, 3, cfg.vit.image_size, cfg.vit.image_size)
-        t0 = time.perf_counter(); x = om.vit_embed(ck, cfg, pix); t_embed = time.perf_counter() - t0
-        t0 = time.perf_counter(); x = om.vit_layer(ck, cfg, x, 0); t_vl = time.perf_counter() - t0
-        t0 = time.perf_counter(); f = om.projector(ck, cfg, x); t_proj = time.perf_counter() - t0
-        emb = torch.randn(S, cfg.dec.hidden) * 0.1
-        cos, sin = om.rope_cos_sin(cfg.dec, torch.arange(S))
-        t0 = time.perf_counter(); y = om.decoder_layer(ck, cfg, emb, 0, cos, sin); t_dl = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        h = om.rmsnorm(y[-1:], ck.f32("language_model.model.norm.weight"), cfg.dec.eps)
-        torch.nn.functional.linear(h, ck.f32("language_model.lm_head.weight"))
-        t_head = time.perf_counter() - t0
-    measured = time.perf_counter() - t_all
-    est = t_embed + cfg.vit.layers * t_vl + t_proj + cfg.dec.layers * t_dl + t_head
-    info = {"t_vit_layer_s": round(t_vl, 3), "t_decoder_layer_s": round(t_dl, 3), "t_projector_s": round(t_proj, 3),
-            "estimated_full_step_s": round(est, 2)}
-    return S / est, measured, info
+METRIC = "prefill tokens/sec (Leopard-LLaVA multi-image prefill, whole job)"
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own (CPU) implementation of the path = the oracle port, on host cores."""
+    """`--impl reference`: the reference's own (CPU) implementation of the path = the oracle port, on host cores.  Honours
+    --steps / --warmup: every step is one complete full-depth forward of a proportional slice of the workload
+    (benchmarks/cpu_reference.py says what the slice is and what it leaves out); nothing is extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import torch
+    from benchmarks.cpu_reference import CpuSample
     from leopard_b200.config import leopard_llava
     cfg = leopard_llava()
-    _, _, n_crops, S, per_image_ref = make_workload(cfg)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    vals, secs, info = [], [], {}
-    steps = max(1, min(args.steps, 2))       # each step is ~20-40 s of CPU work; keep the whole run to minutes
-    for i in range(min(args.warmup, 1) + steps):
-        v, s, info = cpu_reference_sample(cfg, n_crops, S, cores)
-        if i >= min(args.warmup, 1):
-            vals.append(v); secs.append(s)
-    value = statistics.mean(vals)
-    sample = ("1 of 27 ViT layers on all 28 crops + projector + 1 of 32 decoder layers at S=4796 + last-row lm_head, "
-              "torch-cpu fp32 oracle port, extrapolated x27/x32 to a full step")
+    _, _, n_crops, S, per_image = make_workload(cfg, args.workload)
+    sample = CpuSample(cfg, n_crops, S, sample_crops=args.cpu_sample_crops)
+    for _ in range(args.warmup):
+        sample.step()
+    secs = [sample.step() for _ in range(args.steps)]
+    value = sample.rows * len(secs) / sum(secs)
     line = {
-        "impl": "reference", "metric": "prefill tokens/sec (Leopard-LLaVA 4-image prefill, whole job)", "value": value,
-        "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": 1000.0 * S / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": workload_config(per_image_ref, S, 1, "CPU oracle port on rank 0's host cores"),
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, per_image, S, args.gpus),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample, **info},
+                         "sample": sample.desc, "rows_per_step": sample.rows,
+                         "step_seconds_min_max": [round(min(secs), 3), round(max(secs), 3)]},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
-
 
 
 # ------------------------------------------------------------------------------------------------ extras (rank 0, N = 1)
@@ -300,6 +262,34 @@ def frontend_extra(model, ids_h, cfg, S, dev, steps):
                                        "max_new_tokens=1)"}}
 
 # ------------------------------------------------------------------------------------------------ our arm
+def library_leg(eng, cfg, ids_d, pix_d, S, native_last, steps):
+    """The library competitor on the same box, same weights, same request (benchmarks/library_gpu.py): cuBLAS + flash-attn 2
+    (or SDPA) + eager torch in bf16.  Reported beside the native number; its last-row logits cross-check the native path."""
+    import torch
+    from benchmarks.library_gpu import LibraryPrefill
+    lib = LibraryPrefill(cfg, eng.w.named)
+    pix = pix_d.to(torch.bfloat16)
+    out = None
+    for _ in range(2):
+        out = lib.prefill(ids_d[0], pix)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        out = lib.prefill(ids_d[0], pix)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    diff = float((out[0].float() - native_last[0].float()).abs().max())
+    impl = lib.attention_impl
+    del lib
+    torch.cuda.empty_cache()
+    return {"value": S / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "steps": steps,
+            "what": f"torch bf16 on the same B200: F.linear (cuBLAS) + {impl} + eager element-wise ops, same weight tensors "
+                    "and inputs, inputs resident",
+            "max_abs_diff_vs_native_last_row_logits": diff, "native_abs_max": float(native_last.abs().max())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -312,7 +302,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from leopard_b200 import _lib
+    from benchmarks.dp_bench import DpHarness, make_strong_queue
+    from leopard_b200 import _lib, dp
     from leopard_b200.config import leopard_llava
     from leopard_b200.hf import myLlavaForConditionalGeneration
     from leopard_b200.native_weights import random_native
@@ -323,13 +314,21 @@ def run_ours(args):
         L.lp_gemm_set_pair_mode(int(args.gemm_pair))
     model = myLlavaForConditionalGeneration.from_native(cfg, random_native(cfg, dev, seed=1234))
     eng = model.engine
-    pix_h, ids_h, n_crops, S, per_image = make_workload(cfg)
+    pix_h, ids_h, n_crops, S, per_image = make_workload(cfg, args.workload)
     pix_h, ids_h = pix_h.pin_memory(), ids_h.pin_memory()
     pix_d, ids_d = pix_h.to(dev), ids_h.to(dev)
+    harness = DpHarness(eng, dev, world, rank)
+    if world > 1:
+        # the queue of `world` requests lives in rank 0's HBM (bf16 crops, 22 MB per cfg3 request); request r goes to rank r
+        q = [(ids_d[0], pix_d.to(torch.bfloat16)) for _ in range(world)] if rank == 0 else None
+        harness.set_queue(q, world, bins=[[r] for r in range(world)])
 
-    def step_resident():
+    def step_replica():
         logits, _, _ = eng.prefill([(ids_d[0], pix_d)], "last")
         return logits
+
+    # N = 1: the request is resident; N > 1: NCCL scatter from rank 0 -> prefill -> NCCL gather, all inside the step
+    step_resident = step_replica if world == 1 else harness.step
 
     def step_e2e():
         out = model.generate(ids_h, pixel_values=pix_h, attention_mask=None, max_new_tokens=1, use_cache=False)
@@ -356,6 +355,7 @@ def run_ours(args):
     warm = 1 if args.quick else max(args.warmup, 3)
     for _ in range(warm):
         step_resident()
+    harness.events = []
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -364,12 +364,21 @@ def run_ours(args):
     launches = L.lp_launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     value = world * args.steps * S / (total_ms / 1000.0)
+    dp_info = None
+    if world > 1:
+        sc, co, ga = harness.phase_ms()
+        rep_ms = timed(step_replica, args.steps) / args.steps
+        dp_info = {"scatter_ms": round(sc, 3), "compute_ms": round(co, 3), "gather_ms": round(ga, 3),
+                   "collectives": "per step: 1 header broadcast + NCCL send/recv of ids and bf16 crops from rank 0's HBM to "
+                                  "each owner (22.3 MB per cfg3 request), all-gather of the greedy tokens",
+                   "replicas_no_collective_ms_per_step": round(rep_ms, 3)}
 
     if args.quick:  # profiler runs (ncu): the timed loop only, no JSON contract
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": total_ms / args.steps, "gpu_launches": int(launches)}))
         return 0
-    # ---- e2e through the plugin API with host buffers
+    # ---- e2e through the plugin API with host buffers (every rank calls generate() on its own host request, the way the
+    # reference shards an evaluation set: one process per GPU, evaluations/models/run_eval_llava_siglip_multiimg.sh:9-13)
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
@@ -377,13 +386,36 @@ def run_ours(args):
     h2d = pix_h.numel() * pix_h.element_size() + ids_h.numel() * ids_h.element_size()
     d2h = (ids_h.shape[1] + 1) * 8
 
+    # ---- strong scaling: a fixed queue of 8 mixed-size requests (1 .. 28 crops) on rank 0, cost-balanced over the ranks,
+    # one varlen batch per rank, scatter / gather inside the step
+    strong = None
+    if not args.no_extras:
+        sq, meta = make_strong_queue(cfg, dev) if rank == 0 or world == 1 else (None, None)
+        if world > 1:
+            box = [meta]
+            dist.broadcast_object_list(box, src=0)
+            meta = box[0]
+        harness.set_queue(sq, len(meta))
+        mine = harness.step()
+        harness.step()
+        harness.events = []
+        k_strong = max(3, min(args.steps, 6))
+        ms_strong = timed(harness.step, k_strong) / k_strong
+        sc, co, ga = harness.phase_ms()
+        tokens = sum(m["S"] for m in meta)
+        bins = dp.assign([m["gflop"] for m in meta], world)
+        strong = {"queue": meta, "requests": len(meta), "tokens_per_step": tokens, "ms_per_step": round(ms_strong, 3),
+                  "value": tokens / (ms_strong * 1e-3), "unit": "tokens/s", "scaling": "strong",
+                  "assignment": bins, "gflop_per_rank": [round(sum(meta[i]["gflop"] for i in b), 1) for b in bins],
+                  "scatter_ms": round(sc, 3), "compute_ms_max_rank": round(co, 3), "gather_ms": round(ga, 3)}
+
     # ---- per-kernel event timing of one more step (rank 0): roofline of the dominant kernel
     roofline, stages = None, None
     if rank == 0:
         peaks = load_peaks()
         cap = 4096
         _lib.check(L.lp_profile_enable(cap), "lp_profile_enable")
-        step_resident()
+        step_replica()
         recs = (_lib.ProfileRecord * cap)()
         n = L.lp_profile_read(C.cast(recs, C.c_void_p), cap)
         by_kind = {}
@@ -392,7 +424,7 @@ def run_ours(args):
         vit_rows = n_crops * cfg.vit.tokens
         for r in recs[:n]:
             by_kind[r.kind] = by_kind.get(r.kind, 0.0) + r.ms
-            # stage attribution: ViT kernels run on 28 x 676 rows / T = 676 / width 1152, the projector on 28 x 169 rows
+            # stage attribution: ViT kernels run on n_crops x 676 rows / T = 676 / width 1152, the projector on n_crops x 169 rows
             if r.kind == 1:
                 st = "vit" if r.a == vit_rows else ("projector" if r.a == n_crops * cfg.tokens_per_crop else "decoder")
             elif r.kind == 2:
@@ -416,19 +448,20 @@ def run_ours(args):
                     "peak_kind": "sustained cuBLAS bf16, " + peaks["source"], "avg_launch_ms": avg_ms,
                     "share_of_step": ms_sum / step_ms_prof, "traffic": None}
         tr = load_traffic()
-        if tr is not None:  # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)
+        if tr is not None and args.workload == "cfg3":  # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)
             roofline.update(traffic=tr[0], traffic_algorithmic_bytes=tr[1], traffic_source="profiles/" + tr[2])
         fm = flops_model(n_crops, S, cfg)
         names = {1: "gemm", 2: "attention", 3: "norm", 4: "rope", 5: "merge", 6: "im2col", 7: "shuffle"}
         gemm_all = sum(v[0] for v in gemm_shapes.values())
         gemm_flops = sum(2.0 * a * b * c * v[1] for (a, b, c), v in gemm_shapes.items())
+        step_ms_repl = total_ms / args.steps if world == 1 else dp_info["replicas_no_collective_ms_per_step"]
         stages = {
             "kernel_ms": {names.get(kk, str(kk)): round(v, 3) for kk, v in sorted(by_kind.items())},
             "sum_kernel_ms": round(step_ms_prof, 3),
             "all_gemms_tflops": gemm_flops / (gemm_all * 1e-3) / 1e12,
             "attention_tflops": (fm["dec_attn"] + n_crops * 27 * 4608 * 676 * 676) / (by_kind.get(2, 1e9) * 1e-3) / 1e12,
-            "step_tflops_algorithmic": fm["total"] / ((total_ms / args.steps) * 1e-3) / 1e12,
-            "frac_of_sustained_peak": fm["total"] / ((total_ms / args.steps) * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "step_tflops_algorithmic": fm["total"] / (step_ms_repl * 1e-3) / 1e12,
+            "frac_of_sustained_peak": fm["total"] / (step_ms_repl * 1e-3) / 1e12 / peaks["bf16_sustained"],
             "gemm_shapes": [{"M": a, "N": b, "K": c, "count": v[1], "ms_total": round(v[0], 3),
                              "tflops": round(2.0 * a * b * c * v[1] / (v[0] * 1e-3) / 1e12, 1)}
                             for (a, b, c), v in sorted(gemm_shapes.items(), key=lambda kv: -kv[1][0])],
@@ -443,31 +476,35 @@ def run_ours(args):
                 if ms > 0},
         }
 
-    # ---- next-row extras (rank 0, N = 1 only): greedy decode and the GPU image front-end
-    decode, frontend = None, None
+    # ---- rank 0, N = 1 only: the library competitor on this GPU, greedy decode, the GPU image front-end, the CPU baseline
+    decode, frontend, library, cpu = None, None, None, None
     if rank == 0 and world == 1 and not args.no_extras:
+        library = library_leg(eng, cfg, ids_d, pix_d, S, step_replica(), max(3, min(args.steps, 10)))
         decode = decode_extra(model, ids_h, pix_h, cfg, S, load_peaks())
-        frontend = frontend_extra(model, ids_h, cfg, S, dev, args.steps)
-
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only)
-    cpu = None
+        if args.workload == "cfg3":
+            frontend = frontend_extra(model, ids_h, cfg, S, dev, args.steps)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, secs, info = cpu_reference_sample(cfg, n_crops, S, os.cpu_count())
-        cpu = {"value": v, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "1/27 ViT layers (28 crops) + projector + 1/32 decoder layers (S=4796) + last-row lm_head, "
-                         "oracle torch-cpu fp32, extrapolated to a full step", "seconds_measured": round(secs, 1), **info}
+        from benchmarks.cpu_reference import CpuSample
+        sample = CpuSample(cfg, n_crops, S, sample_crops=args.cpu_sample_crops)
+        sample.step()                                   # warm-up (materialises the weights)
+        secs = [sample.step() for _ in range(3)]
+        cpu = {"value": sample.rows * len(secs) / sum(secs), "unit": "tokens/s", "cores": torch.get_num_threads(),
+               "kind": "port", "sample": sample.desc + "; 1 warm-up + 3 timed steps", "seconds_measured": round(sum(secs), 1)}
 
     if rank == 0:
         line = {
-            "metric": "prefill tokens/sec (Leopard-LLaVA 4-image prefill, whole job)", "value": value, "unit": "tokens/s",
+            "metric": METRIC, "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(per_image, S, world, f"dp{world}, no data-path collective"),
+            "config": workload_config(args.workload, per_image, S, world),
+            "timed_region": ("one resident request: tower -> projector -> merge -> decoder -> last-row logits" if world == 1 else
+                             "queue of N requests resident in rank 0's HBM: NCCL scatter -> prefill on every rank -> NCCL gather "
+                             "of the greedy tokens (max over ranks)"),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "leopard_b200.hf.myLlavaForConditionalGeneration.generate(host ids, pixel_values=host fp32, max_new_tokens=1)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
-            "cpu_baseline": cpu, "decode": decode, "frontend": frontend,
+            "cpu_baseline": cpu, "library_gpu": library, "dp": dp_info, "strong": strong, "decode": decode, "frontend": frontend,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -481,20 +518,27 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4", "cfg5"],
+                    help="cfg3 (default) = the metric's configuration; cfg2 = 1 x 1344^2; cfg4 = Idefics2 8 x 980^2; cfg5 = SFT step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the decode / image front-end measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the library / strong-scaling / decode / front-end legs")
     ap.add_argument("--quick", action="store_true", help="1 warm-up, timed loop only (for runs under ncu)")
     ap.add_argument("--gemm-pair", type=int, default=None, help="override the GEMM CTA-pair mode (0/1)")
+    ap.add_argument("--cpu-sample-crops", type=int, default=1, help="crops in the CPU arm's proportional slice")
+    ap.add_argument("--sft-freeze-vit", action="store_true", help="cfg5: freeze the vision tower (--freeze-clip-vision-tower)")
+    ap.add_argument("--sft-recompute", default="full", choices=["full", "none"], help="cfg5: activation recompute")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", "29511", __file__, "--gpus", str(args.gpus), "--steps",
-               str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               "--master-addr", "127.0.0.1", "--master-port", "29511", __file__] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.workload in ("cfg4", "cfg5"):
+        from benchmarks import other_workloads
+        return other_workloads.run(args)
+    if args.impl == "reference":
+        return run_reference(args)
     return run_ours(args)
 
 

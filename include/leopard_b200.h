@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 2
+#define LP_ABI_VERSION 3
 
 enum lp_status { LP_OK = 0, LP_ERR_ARG = -1, LP_ERR_CUDA = -2 };
 
@@ -51,6 +51,41 @@ int lp_abi_version(void);
 int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
                  int K, const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
                  int block_n, void* stream);
+
+/* Extended GEMM: the same kernel with three epilogue fusions that remove the standalone HBM-bound glue kernels of the layer loops
+ * (SURVEY.md §2.3 K2/K5 "LN prologue + GEMM", K9 "RMSNorm fused into the next GEMM", K10/K11 "RoPE in the QKV epilogue";
+ * reference: TELayerNormColumnParallelLinear MP/model/llava/clip_encoder.py:51-72, RMSNorm MLM/legacy/model/rms_norm.py:26-31,
+ * RoPE MLM/core/models/common/embeddings/rotary_pos_embedding.py:197-239).
+ *   norm_mode != NONE (consumer): C = act(norm(A) W^T + b).  The norm's gain is folded into W offline (W' = W diag(gamma), what
+ *     `W` must point at), so norm(A) W^T = rs[row] * (A W'^T - mu[row] * colsum[col]), with mu / rs from `stats_in`: per row
+ *     `stats_in_parts` float2 partials (sum, sum of squares over the K features) written by the producing GEMM (or lp_row_stats),
+ *     summed in index order.  LAYER mode: colsum[n] = sum_k W'[n,k] (fp32) and bias must already hold beta W^T + b.
+ *   stats_out (producer): float2 [M, stats_out_parts], stats_out_parts == 2 * ceil(N / block_n) (lp_gemm_pick_block_n gives the
+ *     block_n a block_n = 0 call will use): (sum, sum of squares) of the bf16-rounded outputs per (column block, epilogue half).
+ *   rope_heads > 0: columns are 128-wide heads; heads [0, rope_heads) get rotate-half RoPE with cos / sin tables fp32 [M, 64]
+ *     (lp_rope_table) applied to the fp32 accumulators before the single bf16 rounding.  bf16 output, no bias / act / residual. */
+enum lp_norm_mode { LP_NORM_NONE = 0, LP_NORM_RMS = 1, LP_NORM_LAYER = 2 };
+typedef struct lp_gemm_desc {
+  const void* A; long long lda;
+  const void* W; long long ldw;
+  void* C; long long ldc;
+  int M, N, K;
+  const float* bias;
+  const void* residual; long long ldr; int res_row_mod;
+  int act, out_fp32, block_n;
+  int norm_mode; const float* stats_in; int stats_in_parts; const float* colsum; float norm_eps;
+  float* stats_out; int stats_out_parts;
+  const float* rope_cos; const float* rope_sin; int rope_heads;
+} lp_gemm_desc;
+int lp_gemm_bf16_ex(const lp_gemm_desc* desc, void* stream);
+/* the tile width a block_n = 0 launch of this problem uses under the current scheduling mode */
+int lp_gemm_pick_block_n(int M, int N, int act);
+/* (sum, sum of squares) per row of x bf16 [rows, width] -> stats float2 [rows] (one partial per row): the producer of
+ * `stats_in` when the rows were not written by a GEMM (merged embeddings entering decoder layer 0). */
+int lp_row_stats(const void* x, long long ldx, int rows, int width, float* stats, void* stream);
+/* layer loops (lp_vit_forward / lp_vit_layers / lp_decoder_prefill): 1 (default) = norms and RoPE fused into the GEMM epilogues
+ * when the weight structs carry the folded matrices, 0 = standalone norm / RoPE kernels.  Returns the previous setting. */
+int lp_model_set_fused_norm(int enable);
 
 /* GEMM scheduling mode: 0 = one CTA per 128-row tile; 1 = CTA pairs (thread-block cluster of 2, tcgen05
  * cta_group::2, 256-row tiles) for problems with at least one tile per SM pair.  Returns the previous mode.
@@ -184,6 +219,10 @@ typedef struct lp_vit_layer_weights {
   const float* fc1_b;
   const void* fc2_w;  /* [hidden, ffn] */
   const float* fc2_b;
+  /* optional (NULL = standalone LayerNorm kernels): LayerNorm folded into the consuming GEMM, see lp_gemm_bf16_ex.
+   * qkv_wf = bf16(qkv_w * ln1_g[None, :]), qkv_c1[n] = sum_k qkv_wf[n, k], qkv_c2 = qkv_w ln1_b + qkv_b; fc1_* likewise with ln2 */
+  const void* qkv_wf; const float* qkv_c1; const float* qkv_c2;
+  const void* fc1_wf; const float* fc1_c1; const float* fc1_c2;
 } lp_vit_layer_weights;
 
 typedef struct lp_vit_weights {
@@ -215,6 +254,9 @@ typedef struct lp_dec_layer_weights {
   const float* ln2_g;
   const void* gateup_w; /* [2*ffn, hidden], 32-row granules interleaved gate/up (see lp_gemm_bf16, LP_ACT_SWIGLU) */
   const void* down_w;   /* [hidden, ffn] */
+  /* optional (NULL = standalone RMSNorm kernels): qkv_wf = bf16(qkv_w * ln1_g[None, :]), gateup_wf = bf16(gateup_w * ln2_g[None, :]) */
+  const void* qkv_wf;
+  const void* gateup_wf;
 } lp_dec_layer_weights;
 
 typedef struct lp_dec_weights {

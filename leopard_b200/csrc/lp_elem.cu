@@ -194,6 +194,31 @@ rmsnorm_packed_kernel(const bf16* __restrict__ x, long long ldx, const float* __
   }
 }
 
+// (sum, sum of squares) of each row: the `stats_in` producer for rows that no GEMM epilogue wrote (lp_gemm_bf16_ex).
+// One warp per row, 16-byte loads, fixed shuffle-tree order (deterministic).
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const bf16* __restrict__ x, long long ldx, int M, int D, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < (D >> 3); c += 32) {
+    const uint4 u = xr[c];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    s1 += ((a.x + a.y) + (b.x + b.y)) + ((cc.x + cc.y) + (d.x + d.y));
+    s2 += ((a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y)) + ((cc.x * cc.x + cc.y * cc.y) + (d.x * d.x + d.y * d.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) stats[row] = make_float2(s1, s2);
+}
+
 static int g_norm_variant = 1;  // 1: packed register-resident RMSNorm for wide rows, 0: re-read variant
 
 template <bool RMS>
@@ -466,6 +491,18 @@ extern "C" int lp_rmsnorm(const void* x, long long ldx, const float* gamma, void
   launch_norm<true>(reinterpret_cast<const bf16*>(x), ldx, gamma, nullptr, reinterpret_cast<bf16*>(out), ldo, M, D, eps, 0,
                     reinterpret_cast<cudaStream_t>(stream));
   LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lp_row_stats(const void* x, long long ldx, int rows, int width, float* stats, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(x && stats && rows > 0 && width > 0 && width % 8 == 0 && ldx % 8 == 0 && aligned16(x) &&
+                 (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+             "lp_row_stats: bad arguments rows=%d width=%d", rows, width);
+  ProfScope prof(3, rows, width, 2, stream);
+  note_launch();
+  LP_CHECK_CUDA(launch_ex(row_stats_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, 1, prefill_pdl(),
+                          reinterpret_cast<const bf16*>(x), ldx, rows, width, reinterpret_cast<float2*>(stats)));
   return 0;
 }
 

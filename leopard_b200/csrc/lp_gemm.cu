@@ -48,6 +48,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_smem = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+  float* colsum_smem = reinterpret_cast<float*>(smem + L::COLSUM_OFF);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -165,21 +166,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tile_coords(args, tile, m_blk, n_blk);
       const int m0 = m_blk * BMT + (int)cta_rank * GEMM_BM, n0 = n_blk * BN;
       float* bs = bias_smem + as * BN;
+      float* cs = colsum_smem + as * BN;
       if (args.bias) {
         for (int i = et; i < BN; i += GEMM_EPI_THREADS) bs[i] = (n0 + i < args.N) ? args.bias[n0 + i] : 0.f;
       }
+      if (args.norm_mode == LP_NORM_LAYER_) {
+        for (int i = et; i < BN; i += GEMM_EPI_THREADS) cs[i] = (n0 + i < args.N) ? args.colsum[n0 + i] : 0.f;
+      }
+      const int row = m0 + lg * 32 + lane;
+      const bool row_ok = row < args.M;
+      // row statistics of the A operand are fetched while the tile's MMAs are still running
+      float rs, nmu;
+      row_norm_coeffs(args, row, row_ok, rs, nmu);
       epi_named_barrier();
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int row = m0 + lg * 32 + lane;
-      const bool row_ok = row < args.M;
       const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
       uint8_t* stage = smem + L::STAGE_OUT_OFF + (warp - 2) * 2048;
       const int row_base = m0 + lg * 32;
       const bool has_res = args.residual != nullptr;
+      float2 ostat = make_float2(0.f, 0.f);
+      float2* ostat_p = args.stats_out != nullptr ? &ostat : nullptr;
       if (!swiglu) {
         const int c_begin = wg == 0 ? 0 : (NC + 1) / 2, c_end = wg == 0 ? (NC + 1) / 2 : NC;
+        // RoPE tiles (BN = 256): each warpgroup owns one 128-column head = chunks c_begin .. c_begin + 3; column i pairs with i + 64
+        const bool rope_tile = BN == 256 && args.rope_heads > 0 && ((n0 >> 7) + wg) < args.rope_heads;
+        if (rope_tile) {
+#pragma unroll 1
+          for (int p = 0; p < 2; ++p) {
+            uint32_t rl[32], rh[32];
+            LP_TMEM_LD_32(rl, taddr0 + (c_begin + p) * 32);
+            LP_TMEM_LD_32(rh, taddr0 + (c_begin + p + 2) * 32);
+            tmem_wait_ld();
+            float lo[32], hi[32];
+            const float* cp = args.rope_cos + (long long)(row_ok ? row : 0) * 64 + p * 32;
+            const float* sp = args.rope_sin + (long long)(row_ok ? row : 0) * 64 + p * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cp + j);
+              const float4 s4 = *reinterpret_cast<const float4*>(sp + j);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float a = rs * __uint_as_float(rl[j + t]), b = rs * __uint_as_float(rh[j + t]);
+                lo[j + t] = a * cc[t] - b * ss[t];
+                hi[j + t] = b * cc[t] + a * ss[t];
+              }
+            }
+            staged_store_chunk(args, &tmC, stage, lo, nullptr, row_base, n0 + (c_begin + p) * 32, lane, ostat_p);
+            staged_store_chunk(args, &tmC, stage, hi, nullptr, row_base, n0 + (c_begin + p + 2) * 32, lane, ostat_p);
+          }
+        } else {
         ResidualRegs rr;
         if (has_res && !args.out_fp32 && n0 + c_begin * 32 < args.N)
           residual_fetch(args, rr, row_base, n0 + c_begin * 32, args.N, lane);
@@ -193,6 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          apply_row_norm(args, v, cs + c * 32, rs, nmu);
           if (args.out_fp32) {
             epilogue_store_chunk(args, v, bs + c * 32, row, rrow, row_ok, col0, args.N);
           } else {
@@ -200,8 +239,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ResidualRegs cur = rr;
             if (has_res && c + 1 < c_end && col0 + 32 < args.N)  // prefetch the next chunk's residual
               residual_fetch(args, rr, row_base, col0 + 32, args.N, lane);
-            staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0, lane);
+            staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0, lane, ostat_p);
           }
+        }
         }
       } else {
         // columns are interleaved in 32-wide granules [gate | up | gate | up ...]; output has N/2 columns
@@ -220,7 +260,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+            float g = rs * __uint_as_float(rg[j]), u = rs * __uint_as_float(ru[j]);   // rs = 1 without a fused RMSNorm
             if (args.bias) { g += bs[c * 64 + j]; u += bs[c * 64 + 32 + j]; }
             v[j] = silu_f(g) * u;
           }
@@ -230,6 +270,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0 / 2, lane);
         }
       }
+      if (args.stats_out != nullptr && row_ok)
+        args.stats_out[(long long)row * (2 * args.num_n_blk) + 2 * n_blk + wg] = ostat;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -281,10 +323,40 @@ static int g_gemm_pair_mode = 1;  // 0 = one CTA per tile, 1 = CTA pairs where t
 
 using namespace lp;
 
-extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
-                            int N, int K, const float* bias, const void* residual, long long ldr, int res_row_mod,
-                            int act, int out_fp32, int block_n, void* stream_) {
+namespace lp {
+// tile width for a problem: wave-quantisation heuristic — minimise ceil(tiles / units) * (BN + per-tile overhead); the narrow
+// tiles are shared-memory-bandwidth bound on one CTA (A 4 KiB + B BN*32 B per K=16 step), hence their penalty
+static int pick_block_n(int M, int N, int act, bool pair, int sms) {
+  const int units = pair ? sms / 2 : sms;
+  const int bm_unit = pair ? 2 * GEMM_BM : GEMM_BM;
+  const long long mb = (M + bm_unit - 1) / bm_unit;
+  const int cand[5] = {256, 224, 192, 160, 128};
+  const double pen[5] = {1.0, 1.15, 1.10, 1.15, 1.30};  // measured: wider tiles amortise the epilogue better
+  double best = 1e30;
+  int block_n = 256;
+  for (int i = 0; i < 5; ++i) {
+    if (act == LP_ACT_SWIGLU && cand[i] % 64 != 0) continue;
+    if (pair && cand[i] == 160) continue;  // pair kernels are instantiated for 128 / 192 / 224 / 256
+    const long long tiles = mb * ((N + cand[i] - 1) / cand[i]);
+    const double cost = (double)((tiles + units - 1) / units) * (cand[i] + 12) * pen[i];
+    if (cost < best) { best = cost; block_n = cand[i]; }
+  }
+  return block_n;
+}
+}  // namespace lp
+
+extern "C" int lp_gemm_pick_block_n(int M, int N, int act) {
+  return pick_block_n(M, N, act, g_gemm_pair_mode != 0 && M > GEMM_BM, sm_count());
+}
+
+extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(d != nullptr, "lp_gemm_bf16_ex: null descriptor");
+  const void* A = d->A; const void* W = d->W; void* C = d->C;
+  const long long lda = d->lda, ldw = d->ldw, ldc = d->ldc, ldr = d->ldr;
+  const int M = d->M, N = d->N, K = d->K, act = d->act, out_fp32 = d->out_fp32, res_row_mod = d->res_row_mod;
+  const float* bias = d->bias; const void* residual = d->residual;
+  int block_n = d->block_n;
   LP_REQUIRE(M > 0 && N > 0 && K > 0, "lp_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   LP_REQUIRE(N % 8 == 0, "lp_gemm_bf16: N=%d must be a multiple of 8", N);
   LP_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "lp_gemm_bf16: lda/ldw must be multiples of 8 elements (TMA 16 B rule)");
@@ -296,41 +368,52 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
              "lp_gemm_bf16: residual must be 16-byte aligned with ldr %% 8 == 0");
   LP_REQUIRE(act >= LP_ACT_NONE && act <= LP_ACT_SWIGLU, "lp_gemm_bf16: bad act %d", act);
   LP_REQUIRE(act != LP_ACT_SWIGLU || N % 64 == 0, "lp_gemm_bf16: SwiGLU needs N %% 64 == 0 (32-wide gate/up granules)");
+  LP_REQUIRE(d->norm_mode >= LP_NORM_NONE && d->norm_mode <= LP_NORM_LAYER, "lp_gemm_bf16_ex: bad norm_mode %d", d->norm_mode);
+  LP_REQUIRE(d->norm_mode == LP_NORM_NONE || (d->stats_in != nullptr && d->stats_in_parts > 0 &&
+                                              (reinterpret_cast<uintptr_t>(d->stats_in) & 7) == 0),
+             "lp_gemm_bf16_ex: fused normalisation needs the producer's row statistics");
+  LP_REQUIRE(d->norm_mode != LP_NORM_LAYER || (d->colsum != nullptr && act != LP_ACT_SWIGLU),
+             "lp_gemm_bf16_ex: layer-norm mode needs the column sums of the folded weight (and no SwiGLU)");
+  LP_REQUIRE(d->stats_out == nullptr || (!out_fp32 && act != LP_ACT_SWIGLU && (reinterpret_cast<uintptr_t>(d->stats_out) & 7) == 0),
+             "lp_gemm_bf16_ex: row statistics are produced by bf16-output, non-SwiGLU epilogues");
+  LP_REQUIRE(d->rope_heads == 0 || (d->rope_cos && d->rope_sin && !out_fp32 && act == LP_ACT_NONE && bias == nullptr &&
+                                    residual == nullptr && N % 128 == 0 && d->rope_heads * 128 <= N &&
+                                    d->norm_mode != LP_NORM_LAYER && (block_n == 0 || block_n == 256)),
+             "lp_gemm_bf16_ex: fused RoPE needs 128-column heads, bf16 output, no bias / activation / residual, block_n 256");
   const int sms = sm_count();
   // CTA pairs (256-row tiles) when asked for and the problem has at least one tile per pair
   bool pair = g_gemm_pair_mode != 0 && M > GEMM_BM;
   const int units = pair ? sms / 2 : sms;
   const int bm_unit = pair ? 2 * GEMM_BM : GEMM_BM;
   const long long mb = (M + bm_unit - 1) / bm_unit;
-  if (block_n == 0) {
-    // wave-quantisation heuristic: minimise ceil(tiles / SMs) * (BN + per-tile overhead); the narrow tiles are
-    // shared-memory-bandwidth bound on one CTA (A 4 KiB + B BN*32 B per K=16 step), hence their penalty
-    const int cand[5] = {256, 224, 192, 160, 128};
-    const double pen[5] = {1.0, 1.15, 1.10, 1.15, 1.30};  // measured: wider tiles amortise the epilogue better
-    double best = 1e30;
-    for (int i = 0; i < 5; ++i) {
-      if (act == LP_ACT_SWIGLU && cand[i] % 64 != 0) continue;
-      if (pair && cand[i] == 160) continue;  // pair kernels are instantiated for 128 / 192 / 224 / 256
-      const long long tiles = mb * ((N + cand[i] - 1) / cand[i]);
-      const double cost = (double)((tiles + units - 1) / units) * (cand[i] + 12) * pen[i];
-      if (cost < best) { best = cost; block_n = cand[i]; }
-    }
-  }
+  if (d->rope_heads > 0) block_n = 256;
+  if (block_n == 0) block_n = pick_block_n(M, N, act, pair, sms);
   LP_REQUIRE(block_n == 128 || block_n == 160 || block_n == 192 || block_n == 224 || block_n == 256,
              "lp_gemm_bf16: block_n must be 0, 128, 160, 192, 224 or 256");
   LP_REQUIRE(act != LP_ACT_SWIGLU || block_n % 64 == 0, "lp_gemm_bf16: SwiGLU needs block_n %% 64 == 0");
 
-  GemmArgs args;
+  GemmArgs args = {};
   args.M = M; args.N = N; args.K = K;
   args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32;
   args.bias = bias;
   args.residual = reinterpret_cast<const bf16*>(residual);
   args.ldr = ldr; args.res_row_mod = res_row_mod;
   args.act = act;
+  args.norm_mode = d->norm_mode;
+  args.stats_in = reinterpret_cast<const float2*>(d->stats_in);
+  args.stats_in_parts = d->stats_in_parts;
+  args.colsum = d->colsum;
+  args.norm_eps = d->norm_eps;
+  args.norm_inv_k = 1.0f / (float)K;
+  args.stats_out = reinterpret_cast<float2*>(d->stats_out);
+  args.rope_cos = d->rope_cos; args.rope_sin = d->rope_sin; args.rope_heads = d->rope_heads;
   if (pair && (block_n == 160 || mb * ((N + block_n - 1) / block_n) < units)) pair = false;
   args.num_m_blk = pair ? (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) : (M + GEMM_BM - 1) / GEMM_BM;
   args.num_n_blk = (N + block_n - 1) / block_n;
   args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+  LP_REQUIRE(d->stats_out == nullptr || d->stats_out_parts == 2 * args.num_n_blk,
+             "lp_gemm_bf16_ex: stats_out_parts=%d, this launch writes %d per row (2 x column blocks of %d)", d->stats_out_parts,
+             2 * args.num_n_blk, block_n);
   {
     // L2-aware rasterisation: keep the operand that fits L2 resident, stream the other from HBM once
     const double l2_budget = 56e6;
@@ -361,7 +444,8 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   if (rc) return rc;
   ProfScope prof(1, M, N, K, stream);
   note_launch();
-  if (pair && g_gemm_pair_mode == 2 && (block_n == 256 || block_n == 192 || block_n == 128) && args.num_n_blk >= 2) {
+  const bool plain = d->norm_mode == LP_NORM_NONE && d->stats_out == nullptr && d->rope_heads == 0;
+  if (plain && pair && g_gemm_pair_mode == 2 && (block_n == 256 || block_n == 192 || block_n == 128) && args.num_n_blk >= 2) {
     // two pairs per 4-CTA cluster on column-adjacent tiles, A multicast between them (lp_gemm4.cu): work units are
     // (row block, column-block pair); A is requested in 64-row boxes
     GemmArgs a4 = args;
@@ -386,6 +470,17 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
     case 160: return launch_gemm<160, 5, false>(tmA, tmB, tmC, args, stream);
     default: return launch_gemm<128, 6, false>(tmA, tmB, tmC, args, stream);
   }
+}
+
+extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                            int N, int K, const float* bias, const void* residual, long long ldr, int res_row_mod,
+                            int act, int out_fp32, int block_n, void* stream_) {
+  lp_gemm_desc d = {};
+  d.A = A; d.lda = lda; d.W = W; d.ldw = ldw; d.C = C; d.ldc = ldc;
+  d.M = M; d.N = N; d.K = K;
+  d.bias = bias; d.residual = residual; d.ldr = ldr; d.res_row_mod = res_row_mod;
+  d.act = act; d.out_fp32 = out_fp32; d.block_n = block_n;
+  return lp_gemm_bf16_ex(&d, stream_);
 }
 
 extern "C" int lp_gemm_set_pair_mode(int enable) {

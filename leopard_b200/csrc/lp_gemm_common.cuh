@@ -26,7 +26,24 @@ struct GemmArgs {
   int num_m_blk, num_n_blk, num_k_blk;
   int group_m;
   int prefetch_a;
+  // ---- fused row normalisation of the A operand (consumer side; SURVEY.md K2/K5/K9: LayerNorm / RMSNorm folded into the GEMM).
+  // The gain is folded into W offline (W' = W diag(gamma)), so norm(x) W^T = rs[row] * (x W'^T - mu[row] * colsum[col]) (+ beta W^T
+  // + b, passed as `bias`).  mu / rs come from per-row partial (sum, sum of squares) pairs the PRODUCING GEMM's epilogue wrote.
+  int norm_mode;                 // LP_NORM_NONE / LP_NORM_RMS / LP_NORM_LAYER
+  const float2* stats_in;        // [M, stats_in_parts]
+  int stats_in_parts;
+  const float* colsum;           // [N] fp32: sum_k W'[n, k] (layer norm only)
+  float norm_eps, norm_inv_k;    // 1 / (features per normalised row)
+  // ---- producer side: per-row (sum, sum of squares) of the bf16-ROUNDED outputs of this GEMM, one pair per (column block,
+  // epilogue warpgroup): stats_out[row * 2 * num_n_blk + 2 * n_blk + wg]; summed in index order by the consumer (deterministic)
+  float2* stats_out;
+  // ---- rotate-half RoPE on the first `rope_heads` 128-column heads (decoder QKV; tables [M, 64] fp32; BN = 256 only)
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_heads;
 };
+
+enum { LP_NORM_NONE_ = 0, LP_NORM_RMS_ = 1, LP_NORM_LAYER_ = 2 };
 
 #ifndef LP_EMULATE
 // 4-CTA-cluster variant (lp_gemm4.cu); args.num_n_blk counts column-block pairs, tmAh has 64-row boxes
@@ -42,7 +59,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = BAR_OFF + 256;
-  static constexpr int STAGE_OUT_OFF = (BIAS_OFF + 2 * BN * 4 + 1023) & ~1023;  // 8 warps x 2 KiB output staging
+  static constexpr int COLSUM_OFF = BIAS_OFF + 2 * BN * 4;                         // layer-norm column sums, double-buffered like bias
+  static constexpr int STAGE_OUT_OFF = (COLSUM_OFF + 2 * BN * 4 + 1023) & ~1023;  // 8 warps x 2 KiB output staging
   static constexpr int TOTAL = STAGE_OUT_OFF + 8 * 2048 + 1024;  // +1024: manual 1 KiB alignment of the base
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
@@ -140,7 +158,8 @@ __device__ __forceinline__ void residual_fetch(const GemmArgs& args, ResidualReg
 }
 
 __device__ __forceinline__ void staged_store_chunk(const GemmArgs& args, const CUtensorMap* tmC, uint8_t* stage,
-                                                   float* v, const ResidualRegs* rr, int row_base, int col0, int lane) {
+                                                   float* v, const ResidualRegs* rr, int row_base, int col0, int lane,
+                                                   float2* row_stats = nullptr) {
   // previous TMA store of this warp must have finished reading the staging tile
   if (lane == 0) tma_store_wait_read<0>();
   __syncwarp();
@@ -167,12 +186,55 @@ __device__ __forceinline__ void staged_store_chunk(const GemmArgs& args, const C
     u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
     u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
     *reinterpret_cast<uint4*>(stage + stage_off(lane, g)) = u;
+    if (row_stats != nullptr) {  // statistics of what the consumer will read: the rounded values
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      row_stats->x += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      row_stats->y += ((f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y)) +
+                      ((f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y));
+    }
   }
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
     tma_store_2d(tmC, stage, col0, row_base);
     tma_store_commit();
+  }
+}
+
+// mu / rstd of one A row from the producer's partial sums (fixed summation order -> bit-deterministic)
+__device__ __forceinline__ void row_norm_coeffs(const GemmArgs& args, int row, bool row_ok, float& rs, float& nmu) {
+  rs = 1.f;
+  nmu = 0.f;
+  if (args.norm_mode == LP_NORM_NONE_ || !row_ok) return;
+  const float2* p = args.stats_in + (long long)row * args.stats_in_parts;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < args.stats_in_parts; ++i) {
+    const float2 t = p[i];
+    s1 += t.x;
+    s2 += t.y;
+  }
+  if (args.norm_mode == LP_NORM_RMS_) {
+    rs = rsqrtf(s2 * args.norm_inv_k + args.norm_eps);
+  } else {
+    const float mu = s1 * args.norm_inv_k;
+    const float var = fmaxf(s2 * args.norm_inv_k - mu * mu, 0.f);
+    rs = rsqrtf(var + args.norm_eps);
+    nmu = -rs * mu;
+  }
+}
+
+// v = rs * acc + nmu * colsum  (before bias / activation)
+__device__ __forceinline__ void apply_row_norm(const GemmArgs& args, float* v, const float* colsum_s, float rs, float nmu) {
+  if (args.norm_mode == LP_NORM_RMS_) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rs;
+  } else if (args.norm_mode == LP_NORM_LAYER_) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(colsum_s + j);
+      v[j] = fmaf(rs, v[j], nmu * c.x); v[j + 1] = fmaf(rs, v[j + 1], nmu * c.y);
+      v[j + 2] = fmaf(rs, v[j + 2], nmu * c.z); v[j + 3] = fmaf(rs, v[j + 3], nmu * c.w);
+    }
   }
 }
 

@@ -25,7 +25,39 @@ extern "C" int lp_model_set_attention_variant(int variant) {
   return old;
 }
 
+// norms (and RoPE) fused into the GEMM epilogues when the weight structs carry the gain-folded matrices (lp_gemm_bf16_ex)
+static int g_fused_norm = 1;
+extern "C" int lp_model_set_fused_norm(int enable) {
+  const int old = g_fused_norm;
+  g_fused_norm = enable ? 1 : 0;
+  return old;
+}
+
 namespace {
+// row-statistics buffer handed from a producing GEMM epilogue to the consuming one: float2 [rows, parts]
+struct RowStats {
+  float* buf;
+  int parts;
+};
+constexpr int kMaxStatParts = 64;   // N <= 4096 with 128-wide tiles: 2 x 32 partials per row
+
+inline lp_gemm_desc gemm_desc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                              int K, const float* bias, const void* residual, long long ldr, int res_row_mod, int act) {
+  lp_gemm_desc d = {};
+  d.A = A; d.lda = lda; d.W = W; d.ldw = ldw; d.C = C; d.ldc = ldc;
+  d.M = M; d.N = N; d.K = K;
+  d.bias = bias; d.residual = residual; d.ldr = ldr; d.res_row_mod = res_row_mod; d.act = act;
+  return d;
+}
+inline void consume_stats(lp_gemm_desc& d, int mode, const RowStats& st, const float* colsum, float eps) {
+  d.norm_mode = mode; d.stats_in = st.buf; d.stats_in_parts = st.parts; d.colsum = colsum; d.norm_eps = eps;
+}
+inline void produce_stats(lp_gemm_desc& d, RowStats& st) {
+  d.block_n = lp_gemm_pick_block_n(d.M, d.N, d.act);
+  st.parts = 2 * ((d.N + d.block_n - 1) / d.block_n);
+  d.stats_out = st.buf; d.stats_out_parts = st.parts;
+}
+
 struct Carver {
   uint8_t* p;
   size_t used = 0, cap;
@@ -41,7 +73,7 @@ inline size_t bf(size_t n) { return n * 2; }
 
 // ------------------------------------------------------------------------------------------------ ViT
 static size_t vit_ws(const lp_vit_dims* d, int N, Carver* c, void** A, void** x, void** h, void** qkv, void** att,
-                     void** mlp) {
+                     void** mlp, float** st0 = nullptr, float** st1 = nullptr) {
   const size_t rows = (size_t)N * d->tokens;
   Carver tmp(nullptr, 0);
   Carver& cv = c ? *c : tmp;
@@ -51,35 +83,81 @@ static size_t vit_ws(const lp_vit_dims* d, int N, Carver* c, void** A, void** x,
   void* q = cv.take(bf(rows * 3 * d->heads * d->head_stride));
   void* at = cv.take(bf(rows * d->hidden));
   void* m = cv.take(bf(rows * d->ffn));
+  float* s0 = (float*)cv.take(rows * kMaxStatParts * 8);
+  float* s1 = (float*)cv.take(rows * kMaxStatParts * 8);
   if (A) { *A = a; *x = xx; *h = hh; *qkv = q; *att = at; *mlp = m; }
+  if (st0) { *st0 = s0; *st1 = s1; }
   return cv.used + 256;
 }
 
-static int vit_layers_impl(const lp_vit_dims* d, const lp_vit_weights* w, void* x, void* h, void* qkv, void* att,
-                           void* mlp, int rows, const int* cu, int n_seqs, int uniform_T, void* out, long long ldo,
-                           int shuffle_side, void* stream) {
+static int vit_attention(const lp_vit_dims* d, void* qkv, void* att, const int* cu, int n_seqs, int uniform_T, void* stream) {
   const int qkv_w = 3 * d->heads * d->head_stride;
   const float scale = 1.0f / sqrtf((float)d->head_dim);
   int rc;
 #define LP_TRY(call) do { rc = (call); if (rc) return rc; } while (0)
+  if (cu == nullptr) {
+    LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, uniform_T, d->heads, d->heads, d->head_dim, d->head_stride, 0,
+                            d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0, scale, att, d->hidden,
+                            g_attn_variant, stream));
+  } else {
+    for (int s = 0; s < n_seqs; ++s) {  // one launch per image (lengths differ)
+      const int r0 = cu[s], T = cu[s + 1] - r0;
+      LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->heads,
+                              d->head_dim, d->head_stride, 0, d->heads * d->head_stride,
+                              2 * d->heads * d->head_stride, 0, scale, (__nv_bfloat16*)att + (size_t)r0 * d->hidden,
+                              d->hidden, g_attn_variant, stream));
+    }
+  }
+  return 0;
+}
+
+static bool vit_can_fuse(const lp_vit_dims* d, const lp_vit_weights* w) {
+  if (!g_fused_norm) return false;
+  for (int l = 0; l < d->layers; ++l)
+    if (!w->layers[l].qkv_wf || !w->layers[l].fc1_wf) return false;
+  return d->layers > 0;
+}
+
+// st_in: statistics of x's rows when the caller's producer (patch-embedding GEMM) already wrote them, else parts == 0
+static int vit_layers_impl(const lp_vit_dims* d, const lp_vit_weights* w, void* x, void* h, void* qkv, void* att,
+                           void* mlp, int rows, const int* cu, int n_seqs, int uniform_T, void* out, long long ldo,
+                           int shuffle_side, RowStats stA, RowStats stB, void* stream) {
+  const int qkv_w = 3 * d->heads * d->head_stride;
+  int rc;
+  if (vit_can_fuse(d, w) && stA.buf && stB.buf) {
+    // LayerNorm folded into the consuming GEMM: 4 GEMMs + attention per layer, no norm launches
+    if (stA.parts == 0) {
+      LP_TRY(lp_row_stats(x, d->hidden, rows, d->hidden, stA.buf, stream));
+      stA.parts = 1;
+    }
+    for (int l = 0; l < d->layers; ++l) {
+      const lp_vit_layer_weights* L = &w->layers[l];
+      lp_gemm_desc g = gemm_desc(x, d->hidden, L->qkv_wf, d->hidden, qkv, qkv_w, rows, qkv_w, d->hidden, L->qkv_c2, nullptr, 0, 0,
+                                 LP_ACT_NONE);
+      consume_stats(g, LP_NORM_LAYER, stA, L->qkv_c1, d->eps);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+      LP_TRY(vit_attention(d, qkv, att, cu, n_seqs, uniform_T, stream));
+      g = gemm_desc(att, d->hidden, L->out_w, d->hidden, x, d->hidden, rows, d->hidden, d->hidden, L->out_b, x, d->hidden, 0,
+                    LP_ACT_NONE);
+      produce_stats(g, stB);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+      g = gemm_desc(x, d->hidden, L->fc1_wf, d->hidden, mlp, d->ffn, rows, d->ffn, d->hidden, L->fc1_c2, nullptr, 0, 0,
+                    LP_ACT_GELU_TANH);
+      consume_stats(g, LP_NORM_LAYER, stB, L->fc1_c1, d->eps);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+      g = gemm_desc(mlp, d->ffn, L->fc2_w, d->ffn, x, d->hidden, rows, d->hidden, d->ffn, L->fc2_b, x, d->hidden, 0, LP_ACT_NONE);
+      if (l + 1 < d->layers) produce_stats(g, stA);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+    }
+    LP_TRY(lp_layernorm(x, d->hidden, w->post_g, w->post_b, out, ldo, rows, d->hidden, d->eps, shuffle_side, stream));
+    return 0;
+  }
   for (int l = 0; l < d->layers; ++l) {
     const lp_vit_layer_weights* L = &w->layers[l];
     LP_TRY(lp_layernorm(x, d->hidden, L->ln1_g, L->ln1_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
     LP_TRY(lp_gemm_bf16(h, d->hidden, L->qkv_w, d->hidden, qkv, qkv_w, rows, qkv_w, d->hidden, L->qkv_b, nullptr, 0, 0,
                         LP_ACT_NONE, 0, 0, stream));
-    if (cu == nullptr) {
-      LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, uniform_T, d->heads, d->heads, d->head_dim, d->head_stride, 0,
-                              d->heads * d->head_stride, 2 * d->heads * d->head_stride, 0, scale, att, d->hidden,
-                              g_attn_variant, stream));
-    } else {
-      for (int s = 0; s < n_seqs; ++s) {  // one launch per image (lengths differ)
-        const int r0 = cu[s], T = cu[s + 1] - r0;
-        LP_TRY(lp_attention_fwd((const __nv_bfloat16*)qkv + (size_t)r0 * qkv_w, qkv_w, 1, T, d->heads, d->heads,
-                                d->head_dim, d->head_stride, 0, d->heads * d->head_stride,
-                                2 * d->heads * d->head_stride, 0, scale, (__nv_bfloat16*)att + (size_t)r0 * d->hidden,
-                                d->hidden, g_attn_variant, stream));
-      }
-    }
+    LP_TRY(vit_attention(d, qkv, att, cu, n_seqs, uniform_T, stream));
     LP_TRY(lp_gemm_bf16(att, d->hidden, L->out_w, d->hidden, x, d->hidden, rows, d->hidden, d->hidden, L->out_b, x,
                         d->hidden, 0, LP_ACT_NONE, 0, 0, stream));
     LP_TRY(lp_layernorm(x, d->hidden, L->ln2_g, L->ln2_b, h, d->hidden, rows, d->hidden, d->eps, 0, stream));
@@ -108,15 +186,19 @@ extern "C" int lp_vit_forward(const lp_vit_dims* d, const lp_vit_weights* w, con
              lp_vit_workspace_bytes(d, N));
   Carver cv(workspace, ws_bytes);
   void *A, *x, *h, *qkv, *att, *mlp;
-  vit_ws(d, N, &cv, &A, &x, &h, &qkv, &att, &mlp);
+  RowStats stA = {nullptr, 0}, stB = {nullptr, 0};
+  vit_ws(d, N, &cv, &A, &x, &h, &qkv, &att, &mlp, &stA.buf, &stB.buf);
   const int rows = N * d->tokens;
   const int img = d->grid * 14;
   int rc;
   LP_TRY(lp_im2col_patch14(pixels, pixels_fp32, A, d->patch_k_pad, N, 3, img, img, stream));
-  // patch embedding GEMM + bias + learned position embedding (row % tokens)
-  LP_TRY(lp_gemm_bf16(A, d->patch_k_pad, w->patch_w, d->patch_k_pad, x, d->hidden, rows, d->hidden, d->patch_k_pad,
-                      w->patch_b, w->pos, d->hidden, d->tokens, LP_ACT_NONE, 0, 0, stream));
-  return vit_layers_impl(d, w, x, h, qkv, att, mlp, rows, nullptr, N, d->tokens, out, ldo, shuffle ? d->grid : 0,
+  // patch embedding GEMM + bias + learned position embedding (row % tokens); with fused norms its epilogue also writes the
+  // row statistics layer 0's LayerNorm needs
+  lp_gemm_desc g = gemm_desc(A, d->patch_k_pad, w->patch_w, d->patch_k_pad, x, d->hidden, rows, d->hidden, d->patch_k_pad,
+                             w->patch_b, w->pos, d->hidden, d->tokens, LP_ACT_NONE);
+  if (vit_can_fuse(d, w)) produce_stats(g, stA);
+  LP_TRY(lp_gemm_bf16_ex(&g, stream));
+  return vit_layers_impl(d, w, x, h, qkv, att, mlp, rows, nullptr, N, d->tokens, out, ldo, shuffle ? d->grid : 0, stA, stB,
                          stream);
 }
 
@@ -125,7 +207,7 @@ extern "C" int lp_vit_forward(const lp_vit_dims* d, const lp_vit_weights* w, con
 // which is what the reference's key-padding mask / flash-varlen unpad achieve).
 extern "C" size_t lp_vit_layers_workspace_bytes(const lp_vit_dims* d, int total_rows) {
   const size_t r = (size_t)total_rows;
-  return bf(r * d->hidden) * 2 + bf(r * 3 * d->heads * d->head_stride) + bf(r * d->ffn) + 5 * 256 + 256;
+  return bf(r * d->hidden) * 2 + bf(r * 3 * d->heads * d->head_stride) + bf(r * d->ffn) + 2 * r * kMaxStatParts * 8 + 7 * 256 + 256;
 }
 
 extern "C" int lp_vit_layers(const lp_vit_dims* d, const lp_vit_weights* w, void* x, const int* cu_seqlens_host,
@@ -139,7 +221,8 @@ extern "C" int lp_vit_layers(const lp_vit_dims* d, const lp_vit_weights* w, void
   void* qkv = cv.take(bf((size_t)R * 3 * d->heads * d->head_stride));
   void* att = cv.take(bf((size_t)R * d->hidden));
   void* mlp = cv.take(bf((size_t)R * d->ffn));
-  return vit_layers_impl(d, w, x, h, qkv, att, mlp, R, cu_seqlens_host, n_seqs, 0, out, ldo, 0, stream);
+  RowStats stA = {(float*)cv.take((size_t)R * kMaxStatParts * 8), 0}, stB = {(float*)cv.take((size_t)R * kMaxStatParts * 8), 0};
+  return vit_layers_impl(d, w, x, h, qkv, att, mlp, R, cu_seqlens_host, n_seqs, 0, out, ldo, 0, stA, stB, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ projector
@@ -161,7 +244,7 @@ extern "C" int lp_project(const lp_proj_weights* w, const void* shuffled, int ro
 
 // ------------------------------------------------------------------------------------------------ decoder
 static size_t dec_ws(const lp_dec_dims* d, int R, int n_seq, Carver* c, void** h, void** qkv, void** att, void** act,
-                     float** cs, float** sn, void** last) {
+                     float** cs, float** sn, void** last, float** st0 = nullptr, float** st1 = nullptr) {
   Carver tmp(nullptr, 0);
   Carver& cv = c ? *c : tmp;
   const int qkv_w = (d->heads + 2 * d->kv_heads) * d->head_dim;
@@ -172,7 +255,10 @@ static size_t dec_ws(const lp_dec_dims* d, int R, int n_seq, Carver* c, void** h
   float* c1 = (float*)cv.take((size_t)R * (d->head_dim / 2) * 4);
   float* s1 = (float*)cv.take((size_t)R * (d->head_dim / 2) * 4);
   void* la = cv.take(bf((size_t)n_seq * d->hidden));
+  float* sa = (float*)cv.take((size_t)R * kMaxStatParts * 8);
+  float* sb = (float*)cv.take((size_t)R * kMaxStatParts * 8);
   if (h) { *h = hh; *qkv = q; *att = at; *act = ac; *cs = c1; *sn = s1; *last = la; }
+  if (st0) { *st0 = sa; *st1 = sb; }
   return cv.used + 256;
 }
 
@@ -196,7 +282,8 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
   Carver cv(workspace, ws_bytes);
   void *h, *qkv, *att, *act, *last;
   float *cs, *sn;
-  dec_ws(d, R, n_seqs, &cv, &h, &qkv, &att, &act, &cs, &sn, &last);
+  RowStats stA = {nullptr, 0}, stB = {nullptr, 0};
+  dec_ws(d, R, n_seqs, &cv, &h, &qkv, &att, &act, &cs, &sn, &last, &stA.buf, &stB.buf);
   const int H = d->hidden, hd = d->head_dim;
   const int q_w = d->heads * hd, kv_w = d->kv_heads * hd, qkv_w = q_w + 2 * kv_w;
   const float scale = 1.0f / sqrtf((float)hd);
@@ -205,18 +292,34 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
     uniform &= (cu_seqlens_host[s + 1] - cu_seqlens_host[s]) == (cu_seqlens_host[1] - cu_seqlens_host[0]);
   int rc;
   LP_TRY(lp_rope_table(pos_ids, w->inv_freq, cs, sn, R, hd / 2, stream));
+  bool fused = g_fused_norm != 0 && d->layers > 0;
+  for (int l = 0; l < d->layers; ++l) fused = fused && w->layers[l].qkv_wf && w->layers[l].gateup_wf;
+  if (fused) {  // RMSNorm of the merged embeddings entering layer 0: no GEMM wrote these rows
+    LP_TRY(lp_row_stats(x, H, R, H, stA.buf, stream));
+    stA.parts = 1;
+  }
   for (int l = 0; l < d->layers; ++l) {
     const lp_dec_layer_weights* L = &w->layers[l];
-    LP_TRY(lp_rmsnorm(x, H, L->ln1_g, h, H, R, H, d->eps, stream));
-    LP_TRY(lp_gemm_bf16(h, H, L->qkv_w, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE, 0, 0, stream));
-    // q heads and k heads are contiguous column-wise: one RoPE launch covers heads + kv_heads; with a cache the same
-    // launch appends K (after RoPE) and V of rows 0..R-1: [layers][2][capacity][kv_w]
-    if (kv_cache) {
-      __nv_bfloat16* kc = (__nv_bfloat16*)kv_cache + (size_t)l * 2 * kv_capacity * kv_w;
-      LP_TRY(rope_kv_append(qkv, qkv_w, R, d->heads, d->kv_heads, hd, cs, sn, kc, kc + (size_t)kv_capacity * kv_w, kv_w,
-                            stream));
+    __nv_bfloat16* kc = kv_cache ? (__nv_bfloat16*)kv_cache + (size_t)l * 2 * kv_capacity * kv_w : nullptr;
+    if (fused) {
+      // RMSNorm folded into the QKV GEMM (gain in the weights, rstd in the epilogue) together with rotate-half RoPE on the
+      // q and k heads; with a KV cache the append kernel applies RoPE instead (it writes K after RoPE)
+      lp_gemm_desc g = gemm_desc(x, H, L->qkv_wf, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE);
+      consume_stats(g, LP_NORM_RMS, stA, nullptr, d->eps);
+      if (!kc) { g.rope_cos = cs; g.rope_sin = sn; g.rope_heads = d->heads + d->kv_heads; }
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+      if (kc) LP_TRY(rope_kv_append(qkv, qkv_w, R, d->heads, d->kv_heads, hd, cs, sn, kc, kc + (size_t)kv_capacity * kv_w, kv_w, stream));
     } else {
-      LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
+      LP_TRY(lp_rmsnorm(x, H, L->ln1_g, h, H, R, H, d->eps, stream));
+      LP_TRY(lp_gemm_bf16(h, H, L->qkv_w, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE, 0, 0, stream));
+      // q heads and k heads are contiguous column-wise: one RoPE launch covers heads + kv_heads; with a cache the same
+      // launch appends K (after RoPE) and V of rows 0..R-1: [layers][2][capacity][kv_w]
+      if (kc) {
+        LP_TRY(rope_kv_append(qkv, qkv_w, R, d->heads, d->kv_heads, hd, cs, sn, kc, kc + (size_t)kv_capacity * kv_w, kv_w,
+                              stream));
+      } else {
+        LP_TRY(lp_rope_inplace(qkv, qkv_w, R, 0, d->heads + d->kv_heads, hd, cs, sn, stream));
+      }
     }
     if (uniform) {
       LP_TRY(lp_attention_fwd(qkv, qkv_w, n_seqs, R / n_seqs, d->heads, d->kv_heads, hd, hd, 0, q_w, q_w + kv_w, 1,
@@ -229,12 +332,24 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
                                 stream));
       }
     }
-    LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, R, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 0, stream));
-    LP_TRY(lp_rmsnorm(x, H, L->ln2_g, h, H, R, H, d->eps, stream));
-    LP_TRY(lp_gemm_bf16(h, H, L->gateup_w, H, act, d->ffn, R, 2 * d->ffn, H, nullptr, nullptr, 0, 0, LP_ACT_SWIGLU, 0,
-                        0, stream));
-    LP_TRY(lp_gemm_bf16(act, d->ffn, L->down_w, d->ffn, x, H, R, H, d->ffn, nullptr, x, H, 0, LP_ACT_NONE, 0, 0,
-                        stream));
+    if (fused) {
+      lp_gemm_desc g = gemm_desc(att, H, L->o_w, H, x, H, R, H, H, nullptr, x, H, 0, LP_ACT_NONE);
+      produce_stats(g, stB);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+      g = gemm_desc(x, H, L->gateup_wf, H, act, d->ffn, R, 2 * d->ffn, H, nullptr, nullptr, 0, 0, LP_ACT_SWIGLU);
+      consume_stats(g, LP_NORM_RMS, stB, nullptr, d->eps);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+      g = gemm_desc(act, d->ffn, L->down_w, d->ffn, x, H, R, H, d->ffn, nullptr, x, H, 0, LP_ACT_NONE);
+      if (l + 1 < d->layers) produce_stats(g, stA);
+      LP_TRY(lp_gemm_bf16_ex(&g, stream));
+    } else {
+      LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, R, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 0, stream));
+      LP_TRY(lp_rmsnorm(x, H, L->ln2_g, h, H, R, H, d->eps, stream));
+      LP_TRY(lp_gemm_bf16(h, H, L->gateup_w, H, act, d->ffn, R, 2 * d->ffn, H, nullptr, nullptr, 0, 0, LP_ACT_SWIGLU, 0,
+                          0, stream));
+      LP_TRY(lp_gemm_bf16(act, d->ffn, L->down_w, d->ffn, x, H, R, H, d->ffn, nullptr, x, H, 0, LP_ACT_NONE, 0, 0,
+                          stream));
+    }
   }
   if (logits_mode == LP_LOGITS_ALL) {
     LP_TRY(lp_rmsnorm(x, H, w->final_g, h, H, R, H, d->eps, stream));

@@ -33,3 +33,17 @@ def native_lib():
     if not _lib.LIB_PATH.exists():
         build.build_native()
     return _lib.lib()
+
+
+@pytest.fixture(scope="session")
+def seeded_full_engine(native_lib):
+    """Full-size Leopard-LLaVA (27 + 32 layers) on the seeded synthetic checkpoint (seed 1234) — the weights the
+    committed full-depth oracle fixtures (tests/golden/fullsize_goldens.npz) and the cfg1 full-depth test were computed with.
+    Built once per session: materialising 8.5 G parameters on the host takes a minute or two."""
+    from leopard_b200.config import leopard_llava
+    from leopard_b200.engine import PrefillEngine
+    from leopard_b200.native_weights import load_hf
+    from leopard_b200.weights import SyntheticCheckpoint
+    cfg = leopard_llava()
+    ck = SyntheticCheckpoint(cfg, seed=1234)
+    return cfg, ck, PrefillEngine(cfg, load_hf(cfg, lambda n: ck[n], "cuda"))

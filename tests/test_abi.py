@@ -22,7 +22,7 @@ def test_header_symbols_are_exported_and_bound(native_lib):
     assert syms == _lib.declared_symbols(), "ctypes table and header disagree"
     for s in syms:
         assert hasattr(native_lib, s), s
-    assert native_lib.lp_abi_version() == 2
+    assert native_lib.lp_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

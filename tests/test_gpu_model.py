@@ -120,12 +120,10 @@ def test_determinism_and_causality(small):
 
 
 @pytest.mark.timeout(1500)
-def test_full_depth_cfg1_parity(native_lib):
+def test_full_depth_cfg1_parity(seeded_full_engine):
     """BASELINE config 1 shape at FULL depth (27 ViT + 32 decoder layers): 1 crop, 8 question + 24 frame ids ->
     S = 201; logits of every position vs the fp32 oracle."""
-    cfg = leopard_llava()
-    ck = SyntheticCheckpoint(cfg, seed=1234)
-    eng = PrefillEngine(cfg, load_hf(cfg, lambda n: ck[n], "cuda"))
+    cfg, ck, eng = seeded_full_engine
     pix, ids = synth_inputs(cfg, n_crops=1, n_text=32)
     assert ids.shape[1] + 168 == 201
     stages = {}
