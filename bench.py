@@ -324,7 +324,7 @@ def run_ours(args):
         harness.set_queue(q, world, bins=[[r] for r in range(world)])
 
     def step_replica():
-        logits, _, _ = eng.prefill([(ids_d[0], pix_d)], "last")
+        logits, _, _ = eng.prefill([(ids_d[0], pix_d)], "last", slots=[n_crops])   # ids are resident: slot count from the host plan
         return logits
 
     # N = 1: the request is resident; N > 1: NCCL scatter from rank 0 -> prefill -> NCCL gather, all inside the step

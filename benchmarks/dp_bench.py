@@ -30,7 +30,8 @@ class DpHarness:
             local, mine = self.queue, list(range(self.n))
         ev[1].record()
         if local:
-            logits, _, _ = self.eng.prefill(local, "last")
+            # HF convention: one placeholder per crop, so the slot counts are known from the shapes (no device sync per request)
+            logits, _, _ = self.eng.prefill(local, "last", slots=[0 if p is None else p.shape[0] for _, p in local])
             tok = logits.argmax(-1, keepdim=True)
         else:
             tok = torch.zeros((0, 1), dtype=torch.int64, device=self.dev)

@@ -463,6 +463,28 @@ int lp_decode_debug_stamps(void* device_u64_buffer);
 int lp_profile_enable(int capacity);
 int lp_profile_read(lp_profile_record* out, int capacity);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * PARITY MODE (leopard_b200/parity.py): the fp32-equivalent forward that answers BASELINE.json's "logits within 1e-3 max-abs of
+ * the reference forward" — the reference's HF evaluation is fp32 end to end (EV/llava_multiimg_siglip_anyres.py:373).  Activations
+ * stay fp32; every contraction runs on lp_gemm_bf16 with the fp32 operand split into three bf16 terms laid out along K
+ * (lp_parity_split), fp32 accumulation in TMEM, fp32 output; the glue between the GEMMs are these fp32 kernels.
+ *   lp_parity_split   x fp32 [M, K] -> bf16 [M, 3K] = [hi | mid | lo] (layout 0; pairs with a bf16 weight tiled 3x along K), or
+ *                     [M, 6K] = [h h h m m l] (layout 1, A side) / [h m l h m h] (layout 2, B side) for fp32 x fp32 products
+ *                     (attention): the six column blocks pair up as the products hh, hm, hl, mh, mm, lh.
+ *   lp_parity_norm    LayerNorm (rms = 0, beta may be NULL) / RMSNorm (rms = 1) over fp32 rows.
+ *   lp_parity_act     GELU tanh / GELU erf (out may alias x) or SwiGLU on 32-column gate / up granules (out [M, N/2]).
+ *   lp_parity_add     y += x (x_row_mod > 0: x row = row % x_row_mod, the position embedding).
+ *   lp_parity_rope    rotate-half RoPE in place on heads [0, n_heads) of x fp32 [S, ld].
+ *   lp_parity_softmax softmax(scale * scores) per row in place, causal: keys 0 .. row only.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int lp_parity_split(const float* x, long long ldx, int M, int K, void* out, long long ldo, int layout, void* stream);
+int lp_parity_norm(const float* x, long long ldx, const float* gamma, const float* beta, float* out, long long ldo, int M, int D,
+                   float eps, int rms, void* stream);
+int lp_parity_act(const float* x, long long ldx, float* out, long long ldo, int M, int N, int act, void* stream);
+int lp_parity_add(float* y, long long ldy, const float* x, long long ldx, int M, int N, int x_row_mod, void* stream);
+int lp_parity_rope(float* x, long long ld, int S, int n_heads, int head_dim, const float* cs, const float* sn, void* stream);
+int lp_parity_softmax(float* scores, long long ld, int Tq, int Tk, float scale, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ class VitDims(C.Structure):
 
 class VitLayerWeights(C.Structure):
     _fields_ = [(n, _vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_w", "qkv_b", "out_w", "out_b", "fc1_w",
-                                   "fc1_b", "fc2_w", "fc2_b")]
+                                   "fc1_b", "fc2_w", "fc2_b", "qkv_wf", "qkv_c1", "qkv_c2", "fc1_wf", "fc1_c1", "fc1_c2")]
 
 
 class VitWeights(C.Structure):
@@ -45,11 +45,23 @@ class DecDims(C.Structure):
 
 
 class DecLayerWeights(C.Structure):
-    _fields_ = [(n, _vp) for n in ("ln1_g", "qkv_w", "o_w", "ln2_g", "gateup_w", "down_w")]
+    _fields_ = [(n, _vp) for n in ("ln1_g", "qkv_w", "o_w", "ln2_g", "gateup_w", "down_w", "qkv_wf", "gateup_wf")]
 
 
 class DecWeights(C.Structure):
     _fields_ = [("layers", C.POINTER(DecLayerWeights)), ("final_g", _vp), ("lm_head", _vp), ("inv_freq", _vp)]
+
+
+class GemmDesc(C.Structure):
+    """lp_gemm_desc (include/leopard_b200.h)."""
+    _fields_ = [("A", _vp), ("lda", _ll), ("W", _vp), ("ldw", _ll), ("C", _vp), ("ldc", _ll), ("M", _i), ("N", _i), ("K", _i),
+                ("bias", _vp), ("residual", _vp), ("ldr", _ll), ("res_row_mod", _i), ("act", _i), ("out_fp32", _i),
+                ("block_n", _i), ("norm_mode", _i), ("stats_in", _vp), ("stats_in_parts", _i), ("colsum", _vp),
+                ("norm_eps", _f), ("stats_out", _vp), ("stats_out_parts", _i), ("rope_cos", _vp), ("rope_sin", _vp),
+                ("rope_heads", _i)]
+
+
+NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
 
 
 class ProfileRecord(C.Structure):
@@ -63,7 +75,17 @@ _SIGS = {
     "lp_last_error": (C.c_char_p, []),
     "lp_abi_version": (_i, []),
     "lp_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "lp_gemm_bf16_ex": (_i, [C.POINTER(GemmDesc), _vp]),
+    "lp_gemm_pick_block_n": (_i, [_i, _i, _i]),
+    "lp_row_stats": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
+    "lp_model_set_fused_norm": (_i, [_i]),
     "lp_gemm_set_pair_mode": (_i, [_i]),
+    "lp_parity_split": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _vp]),
+    "lp_parity_norm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
+    "lp_parity_act": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "lp_parity_add": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "lp_parity_rope": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "lp_parity_softmax": (_i, [_vp, _ll, _i, _i, _f, _i, _vp]),
     "lp_set_prefill_pdl": (_i, [_i]),
     "lp_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _i, _vp]),
     "lp_attention_set_pingpong": (_i, [_i]),

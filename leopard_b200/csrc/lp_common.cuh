@@ -91,6 +91,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// cross-CTA / cross-GPU flags in global memory (tensor-parallel fusions: peers are other GPUs over NVLink)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded spin (a peer that never arrives traps this kernel instead of hanging the GPU)
+__device__ __forceinline__ void spin_until_sys(const unsigned* p, unsigned target) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - target) < 0) {
+    __nanosleep(64);
+    if (clock64() - t0 > LP_WATCHDOG_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void spin_until_gpu(const unsigned* p, unsigned target) {
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(32);
+    if (clock64() - t0 > LP_WATCHDOG_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — global -> shared, completion on an mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

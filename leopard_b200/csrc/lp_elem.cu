@@ -299,7 +299,16 @@ __global__ void rope_kv_kernel(bf16* __restrict__ x, long long ld, int S, int n_
   const int s = (int)(i / ((long long)cpr * n_heads));
   bf16* p1 = x + (long long)s * ld + h * 2 * half + c * 8;
   bf16* p2 = p1 + half;
+  if (cs == nullptr && h < n_q) return;  // append-only mode (RoPE already applied by the QKV GEMM's epilogue): q heads untouched
   const uint4 u1 = *reinterpret_cast<const uint4*>(p1), u2 = *reinterpret_cast<const uint4*>(p2);
+  if (cs == nullptr) {  // k head, already rotated: copy into the cache
+    if (h < n_q + n_kv) {
+      bf16* d = kc + (long long)s * ld_cache + (h - n_q) * 2 * half + c * 8;
+      *reinterpret_cast<uint4*>(d) = u1;
+      *reinterpret_cast<uint4*>(d + half) = u2;
+      return;
+    }
+  }
   if (h >= n_q + n_kv) {  // v head: plain copy into the cache
     bf16* d = vc + (long long)s * ld_cache + (h - n_q - n_kv) * 2 * half + c * 8;
     *reinterpret_cast<uint4*>(d) = u1;
@@ -550,7 +559,8 @@ extern "C" int lp_rope_inplace(void* x, long long ld, int S, int col0, int n_hea
 }
 
 namespace lp {
-// RoPE in place on the q|k heads of x [S, ld] + append K (rotated) and V rows 0 .. S-1 to the cache (see rope_kv_kernel)
+// RoPE in place on the q|k heads of x [S, ld] + append K (rotated) and V rows 0 .. S-1 to the cache (see rope_kv_kernel);
+// cos_t == nullptr: append only (x already holds rotated q / k)
 int rope_kv_append(void* x, long long ld, int S, int n_q, int n_kv, int head_dim, const float* cos_t, const float* sin_t,
                    void* kc, void* vc, long long ld_cache, cudaStream_t stream) {
   LP_REQUIRE(S > 0 && head_dim % 16 == 0 && ld % 8 == 0 && ld_cache % 8 == 0 && aligned16(x) && aligned16(kc) && aligned16(vc),

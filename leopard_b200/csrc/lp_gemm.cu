@@ -206,13 +206,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 32; j += 4) {
               const float4 c4 = *reinterpret_cast<const float4*>(cp + j);
               const float4 s4 = *reinterpret_cast<const float4*>(sp + j);
-              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float a = rs * __uint_as_float(rl[j + t]), b = rs * __uint_as_float(rh[j + t]);
-                lo[j + t] = a * cc[t] - b * ss[t];
-                hi[j + t] = b * cc[t] + a * ss[t];
-              }
+#define LP_ROPE_PAIR(T, CV, SV)                                                                                       \
+  {                                                                                                                    \
+    const float a = rs * __uint_as_float(rl[j + T]), b = rs * __uint_as_float(rh[j + T]);                              \
+    lo[j + T] = a * (CV) - b * (SV);                                                                                   \
+    hi[j + T] = b * (CV) + a * (SV);                                                                                   \
+  }
+              LP_ROPE_PAIR(0, c4.x, s4.x) LP_ROPE_PAIR(1, c4.y, s4.y) LP_ROPE_PAIR(2, c4.z, s4.z) LP_ROPE_PAIR(3, c4.w, s4.w)
+#undef LP_ROPE_PAIR
             }
             staged_store_chunk(args, &tmC, stage, lo, nullptr, row_base, n0 + (c_begin + p) * 32, lane, ostat_p);
             staged_store_chunk(args, &tmC, stage, hi, nullptr, row_base, n0 + (c_begin + p + 2) * 32, lane, ostat_p);

@@ -41,6 +41,29 @@ struct GemmArgs {
   const float* rope_cos;
   const float* rope_sin;
   int rope_heads;
+  // ---- tensor-parallel fusions (lp_gemm_bf16_tp).  tp_size > 0: the M rows are tp_size segments of seg_rows rows,
+  // segment r owned by rank r (Megatron sequence parallelism); tiles never straddle a segment (seg_m_blk row blocks per segment)
+  // and the rank's own segment is scheduled first.
+  int tp_size, tp_rank, seg_rows, seg_m_blk;
+  unsigned epoch;                 // call number: what the cross-rank signal words are compared with
+  // all-gather prologue (ag_counter != null): the epilogue warps of all CTAs copy the other ranks' rows of A from peer memory
+  // (ag_src[r] = rank r's copy of the A buffer, NVLink loads) into the local A buffer while the first tiles (own rows) run
+  const void* ag_src[8];
+  void* ag_dst;
+  long long ag_ld;                // row stride (elements) of the A buffers, identical on every rank
+  int ag_cols;                    // columns to copy (K)
+  unsigned* ag_counter;           // local, zero on entry: CTAs that finished their share of the copy
+  const unsigned* ag_wait[8];     // local signal words, written by rank r: >= epoch once its rows may be read
+  unsigned* ag_post[8];           // rank r's signal word for THIS rank (remote store): "my rows are ready"
+  // reduce-scatter epilogue (rs_counter != null): the tile of segment r is stored through GemmSegMaps.m[r] (rank r's staging memory,
+  // TMA stores over NVLink); the last CTA to finish posts `epoch` to every owner
+  unsigned* rs_counter;           // local, zero on entry
+  unsigned* rs_post[8];           // rank r's "partials from this rank have landed" word (remote store)
+  unsigned* recycle;              // a counter slot of an older call to zero for reuse
+};
+
+struct GemmSegMaps {
+  CUtensorMap m[8];
 };
 
 enum { LP_NORM_NONE_ = 0, LP_NORM_RMS_ = 1, LP_NORM_LAYER_ = 2 };
@@ -76,6 +99,21 @@ __device__ __forceinline__ void tile_coords(const GemmArgs& a, int tile, int& m_
   n_blk = r / gsz;
   m_blk = m0 + (r - n_blk * gsz);
 }
+
+// first row of a row block, its segment (tensor-parallel launches: own segment first) and the row limit of that segment
+__device__ __forceinline__ int tile_row0(const GemmArgs& a, int m_blk, int rows_per_blk, int& seg, int& row_limit) {
+  if (a.tp_size <= 0) {
+    seg = 0;
+    row_limit = a.M;
+    return m_blk * rows_per_blk;
+  }
+  const int s = m_blk / a.seg_m_blk;
+  seg = (s + a.tp_rank) % a.tp_size;
+  row_limit = min(a.M, (seg + 1) * a.seg_rows);
+  return seg * a.seg_rows + (m_blk - s * a.seg_m_blk) * rows_per_blk;
+}
+
+
 
 // applies bias/activation/residual to 32 accumulator columns of one row and stores them
 __device__ __forceinline__ void epilogue_store_chunk(const GemmArgs& args, float* v, const float* bias_s, int row,

@@ -53,7 +53,9 @@ inline void consume_stats(lp_gemm_desc& d, int mode, const RowStats& st, const f
   d.norm_mode = mode; d.stats_in = st.buf; d.stats_in_parts = st.parts; d.colsum = colsum; d.norm_eps = eps;
 }
 inline void produce_stats(lp_gemm_desc& d, RowStats& st) {
-  d.block_n = lp_gemm_pick_block_n(d.M, d.N, d.act);
+  // fixed tile width: the column partition of a row's partial sums (and with it the consumer's summation order) must not depend
+  // on M, or a request packed with others would no longer be bit-identical to the same request alone
+  d.block_n = 256;
   st.parts = 2 * ((d.N + d.block_n - 1) / d.block_n);
   d.stats_out = st.buf; d.stats_out_parts = st.parts;
 }
@@ -303,12 +305,13 @@ extern "C" int lp_decoder_prefill(const lp_dec_dims* d, const lp_dec_weights* w,
     __nv_bfloat16* kc = kv_cache ? (__nv_bfloat16*)kv_cache + (size_t)l * 2 * kv_capacity * kv_w : nullptr;
     if (fused) {
       // RMSNorm folded into the QKV GEMM (gain in the weights, rstd in the epilogue) together with rotate-half RoPE on the
-      // q and k heads; with a KV cache the append kernel applies RoPE instead (it writes K after RoPE)
+      // q and k heads
       lp_gemm_desc g = gemm_desc(x, H, L->qkv_wf, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE);
       consume_stats(g, LP_NORM_RMS, stA, nullptr, d->eps);
-      if (!kc) { g.rope_cos = cs; g.rope_sin = sn; g.rope_heads = d->heads + d->kv_heads; }
+      g.rope_cos = cs; g.rope_sin = sn; g.rope_heads = d->heads + d->kv_heads;
       LP_TRY(lp_gemm_bf16_ex(&g, stream));
-      if (kc) LP_TRY(rope_kv_append(qkv, qkv_w, R, d->heads, d->kv_heads, hd, cs, sn, kc, kc + (size_t)kv_capacity * kv_w, kv_w, stream));
+      // with a cache: K (already rotated) and V rows are appended by a pure copy, so cached and cache-less prefills agree bit for bit
+      if (kc) LP_TRY(rope_kv_append(qkv, qkv_w, R, d->heads, d->kv_heads, hd, nullptr, nullptr, kc, kc + (size_t)kv_capacity * kv_w, kv_w, stream));
     } else {
       LP_TRY(lp_rmsnorm(x, H, L->ln1_g, h, H, R, H, d->eps, stream));
       LP_TRY(lp_gemm_bf16(h, H, L->qkv_w, H, qkv, qkv_w, R, qkv_w, H, nullptr, nullptr, 0, 0, LP_ACT_NONE, 0, 0, stream));

@@ -48,6 +48,7 @@ class PrefillEngine:
         pixel_values = pixel_values.to(self.device).contiguous()
         n = pixel_values.shape[0]
         L = _lib.lib()
+        self.w.sync_folded("vit")
         if shuffle:
             out = torch.empty((n * self.cfg.tokens_per_crop, self.cfg.proj_in), dtype=torch.bfloat16, device=self.device)
         else:
@@ -78,11 +79,13 @@ class PrefillEngine:
         return self.project(self.vit(pixel_values, shuffle=True)).view(n, self.cfg.tokens_per_crop, -1)
 
     def merge(self, ids: torch.Tensor, feats: Optional[torch.Tensor], image_id: int, rows_per_slot: int,
-              out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
-        """One sequence: ids [L] int64 (device), feats [rows, D] -> (embeds [S, D], n_slots)."""
+              out: Optional[torch.Tensor] = None, n_slots: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+        """One sequence: ids [L] int64, feats [rows, D] -> (embeds [S, D], n_slots).  `n_slots` = number of image slots when the
+        caller already knows it (counting them on device ids costs a device -> host sync)."""
+        if n_slots is None:
+            n_slots = int((ids == image_id).sum())      # free for host ids; one sync for device ids
         ids = ids.to(self.device, torch.long).contiguous()
         Lt = ids.numel()
-        n_slots = int((ids == image_id).sum())
         n_feat = 0 if feats is None else feats.shape[0]
         S = Lt + n_slots * (rows_per_slot - 1)
         D = self.cfg.dec.hidden
@@ -106,6 +109,7 @@ class PrefillEngine:
         R = x.shape[0]
         n = len(cu_seqlens) - 1
         L = _lib.lib()
+        self.w.sync_folded("dec")
         mode = {"none": _lib.LOGITS_NONE, "last": _lib.LOGITS_LAST, "all": _lib.LOGITS_ALL}[logits_mode]
         vp = self.w.vocab_padded
         logits = None
@@ -138,7 +142,7 @@ class PrefillEngine:
     @torch.no_grad()
     def prefill(self, samples: List[Tuple[torch.Tensor, Optional[torch.Tensor]]], logits_mode: str = "last",
                 logits_dtype=torch.float32, want_kv: bool = False, convention: str = "hf", kv_capacity: int = 0,
-                kv_buffer: Optional[torch.Tensor] = None):
+                kv_buffer: Optional[torch.Tensor] = None, slots: Optional[Sequence[int]] = None):
         """samples: [(input_ids [L] or [1,L], pixel_values [N_i,3,364,364] or None), ...] — independent requests.
         All crops go through the tower as one batch, every request becomes one packed decoder sequence.
         convention 'hf': one placeholder id per crop, expanded to 169 rows; 'megatron': one -200 per feature row.
@@ -151,9 +155,13 @@ class PrefillEngine:
             feats_all = self.project(self.vit(allp, shuffle=True))  # [sum N * 169, D]
         image_id, per_slot = (cfg.image_token_index, cfg.tokens_per_crop) if convention == "hf" else (
             cfg.megatron_image_index, 1)
-        # plan lengths on the host (shapes depend on the ids, exactly as in the reference's merge)
-        ids_list = [i.reshape(-1).to(self.device, torch.long) for i, _ in samples]
-        slots = [int((i == image_id).sum()) for i in ids_list]
+        # plan lengths on the host (shapes depend on the ids, exactly as in the reference's merge): ids that arrive as host
+        # tensors — every caller on the plugin surfaces — are counted on the host, so no device -> host sync happens per request;
+        # device ids can bring their slot counts (`slots`), else they cost one sync each
+        host_ids = [i.reshape(-1) for i, _ in samples]
+        if slots is None:
+            slots = [int((i == image_id).sum()) for i in host_ids]
+        ids_list = [i.to(self.device, torch.long, non_blocking=True) for i in host_ids]
         lens = [i.numel() + s * (per_slot - 1) for i, s in zip(ids_list, slots)]
         cu = [0]
         for ln in lens:
@@ -171,9 +179,10 @@ class PrefillEngine:
                 raise AssertionError("The number of image features doesn't match the number of image tokens. "
                                      f"{n_rows} != {slots[k]}")
             f = feats_all[f0:f0 + n_rows] if n_rows else None
-            self.merge(ids, f, image_id, per_slot, out=x[cu[k]:cu[k + 1]])
+            self.merge(ids, f, image_id, per_slot, out=x[cu[k]:cu[k + 1]], n_slots=slots[k])
             f0 += n_rows
-        pos = torch.cat([torch.arange(ln, dtype=torch.int32, device=self.device) for ln in lens])
+        pos = torch.cat([torch.arange(ln, dtype=torch.int32) for ln in lens]).to(self.device, non_blocking=True) \
+            if len(lens) > 1 else torch.arange(lens[0], dtype=torch.int32, device=self.device)
         logits, kv = self.decoder(x, pos, cu, logits_mode, logits_dtype, want_kv, cu[-1] + kv_capacity, kv_buffer)
         return logits, kv, cu
 

@@ -247,6 +247,16 @@ class myLlavaForConditionalGeneration:
         self.training = False
         return self
 
+    def set_precision(self, precision: str):
+        """"bf16" (default): the fast path — bf16 activations, fp32 accumulation.  "fp32": PARITY MODE for forward() without
+        a cache — the fp32-equivalent arithmetic of the reference's `torch_dtype=torch.float32` evaluation (…anyres.py:373) on
+        the same tensor-core GEMM with three-term operand splitting (leopard_b200/parity.py); seconds per request, meant for
+        checking logits against the reference, not for throughput.  generate() always decodes on the fast path."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self._precision = precision
+        return self
+
     def to(self, device):
         device = torch.device(device)
         if device.type != "cuda":
@@ -339,8 +349,14 @@ class myLlavaForConditionalGeneration:
                 raise NotImplementedError("padded prompts are outside the reference's usage (…anyres.py:443-446)")
             pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
             ids = input_ids.to(eng.device, non_blocking=True)
+            if getattr(self, "_precision", "bf16") == "fp32" and not use_cache:
+                from .parity import ParityForward
+                logits = ParityForward(eng).prefill_logits(ids[0], None if pix is None else pix.float())[None]
+                if return_dict is False:
+                    return (logits,)
+                return LlavaCausalLMOutputWithPast(logits=logits)
             # room for the cached single-token steps a caller may drive through forward(past_key_values=...)
-            logits, kv, cu = eng.prefill([(ids[0], pix)], "all", torch.float32, want_kv=bool(use_cache), kv_capacity=128)
+            logits, kv, cu = eng.prefill([(input_ids[0], pix)], "all", torch.float32, want_kv=bool(use_cache), kv_capacity=128)
             logits = logits[None]
             past = self._legacy_cache(kv, cu[-1]) if kv is not None else None
         loss = None
@@ -374,5 +390,6 @@ class myLlavaForConditionalGeneration:
         pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
         from .decode import GreedyDecoder
         dec = GreedyDecoder(eng)
-        new_tokens = dec.run(ids[0], pix, max_new_tokens, eos)
+        # the ids the CALLER holds (normally host memory) plan the merge: counting placeholders there costs no device sync
+        new_tokens = dec.run(input_ids[0], pix, max_new_tokens, eos)
         return torch.cat([ids, new_tokens[None]], dim=1)

@@ -52,6 +52,8 @@ class NativeWeights:
         self.device = torch.device(device)
         self._keep = []          # every device tensor referenced by a struct
         self.named = {}          # name -> device tensor, for the tensors the SFT step updates in place (train.py)
+        self.folded = {}         # gain-folded matrices / column sums / folded biases (refresh_folded)
+        self.folded_dirty = set()   # parts ("vit", "dec") whose base weights changed since the last refresh
         self.embed = None        # [vocab, hidden] bf16
         self.vocab_padded = (cfg.dec.vocab + 7) // 8 * 8
         v, d = cfg.vit, cfg.dec
@@ -88,9 +90,56 @@ class NativeWeights:
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._keep)
 
+    # -- gain-folded matrices for the fused-norm layer loops (lp_gemm_bf16_ex; include/leopard_b200.h)
+    def _fold_set(self, key: str, value: torch.Tensor) -> torch.Tensor:
+        cur = self.folded.get(key)
+        if cur is None:
+            cur = value.contiguous()
+            self.folded[key] = cur
+            self._keep.append(cur)
+        else:
+            cur.copy_(value)
+        return cur
+
+    @torch.no_grad()
+    def refresh_folded(self, parts=("vit", "dec")):
+        """(Re)derive, from the live tensors, what the fused layer loops read instead of running norm kernels:
+        tower   qkv_wf = bf16(qkv_w * ln1_g), qkv_c1 = rowsum(qkv_wf), qkv_c2 = qkv_w ln1_b + qkv_b (fc1 likewise with ln2);
+        decoder qkv_wf = bf16(qkv_w * ln1_g), gateup_wf = bf16(gateup_w * ln2_g).
+        Pure weight preparation (the reference's TELayerNormColumnParallelLinear keeps LN and GEMM weights together the same
+        way, clip_encoder.py:51-72).  First call allocates and publishes the pointers; later calls update in place, so the
+        ctypes structs stay valid (call after the base weights changed, e.g. an optimizer step)."""
+        n, v, d = self.named, self.cfg.vit, self.cfg.dec
+        bf = torch.bfloat16
+        if "vit" in parts:
+            for i in range(v.layers):
+                L = self.vit_layers[i]
+                for mat, ln, tag in (("qkv", "ln1", "qkv"), ("fc1", "ln2", "fc1")):
+                    w, b = n[f"vit.{i}.{mat}_w"], n[f"vit.{i}.{mat}_b"]
+                    g, beta = n[f"vit.{i}.{ln}_g"], n[f"vit.{i}.{ln}_b"]
+                    wf = self._fold_set(f"vit.{i}.{tag}_wf", (w.float() * g[None, :]).to(bf))
+                    c1 = self._fold_set(f"vit.{i}.{tag}_c1", wf.float().sum(1))
+                    c2 = self._fold_set(f"vit.{i}.{tag}_c2", w.float() @ beta + b)
+                    setattr(L, f"{tag}_wf", self._p(wf))
+                    setattr(L, f"{tag}_c1", self._p(c1))
+                    setattr(L, f"{tag}_c2", self._p(c2))
+            self.folded_dirty.discard("vit")
+        if "dec" in parts:
+            for i in range(d.layers):
+                L = self.dec_layers[i]
+                L.qkv_wf = self._p(self._fold_set(f"dec.{i}.qkv_wf", (n[f"dec.{i}.qkv_w"].float() * n[f"dec.{i}.ln1_g"][None, :]).to(bf)))
+                L.gateup_wf = self._p(self._fold_set(f"dec.{i}.gateup_wf",
+                                                    (n[f"dec.{i}.gateup_w"].float() * n[f"dec.{i}.ln2_g"][None, :]).to(bf)))
+            self.folded_dirty.discard("dec")
+
+    def sync_folded(self, part: str):
+        """Called by the engine before a stage runs: refresh the folded copies of `part` if the trainer touched its weights."""
+        if part in self.folded_dirty:
+            self.refresh_folded((part,))
+
 
 def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda",
-            with_projector: bool = True) -> NativeWeights:
+            with_projector: bool = True, fold: bool = True) -> NativeWeights:
     """Build NativeWeights from HF-layout tensors; `get(name)` returns one tensor (any float dtype, any device)."""
     nw = NativeWeights(cfg, device)
     v, d = cfg.vit, cfg.dec
@@ -166,6 +215,8 @@ def load_hf(cfg: LeopardConfig, get: Callable[[str], torch.Tensor], device="cuda
     nw._keep.append(inv)
     nw.named["dec.inv_freq"] = inv
     nw.dec.inv_freq = nw._p(inv)
+    if fold:
+        nw.refresh_folded()
     return nw
 
 

@@ -4,10 +4,12 @@ These add shape/dtype checks and output allocation only; no arithmetic happens i
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SWIGLU  # noqa: F401
+from ._lib import ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SWIGLU, NORM_NONE, NORM_RMS, NORM_LAYER  # noqa: F401
 
 
 def _chk_bf16(t, name):
@@ -38,6 +40,58 @@ def gemm(a, w, bias=None, residual=None, act=ACT_NONE, out=None, out_fp32=False,
         act, 1 if out.dtype == torch.float32 else 0, block_n, _lib.stream_ptr())
     _lib.check(rc, "lp_gemm_bf16")
     return out
+
+
+def gemm_pick_block_n(M, N, act=ACT_NONE):
+    return int(_lib.lib().lp_gemm_pick_block_n(M, N, act))
+
+
+def row_stats(x, out=None):
+    """(sum, sum of squares) per row of x bf16 [rows, width] -> fp32 [rows, 1, 2] (lp_row_stats): one partial per row."""
+    _chk_bf16(x, "x")
+    rows, width = x.shape
+    if out is None:
+        out = torch.empty((rows, 1, 2), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().lp_row_stats(_lib.ptr(x), x.stride(0), rows, width, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lp_row_stats")
+    return out
+
+
+def gemm_ex(a, w, bias=None, residual=None, act=ACT_NONE, out=None, out_fp32=False, res_row_mod=0, block_n=0, norm_mode=0,
+            stats_in=None, colsum=None, eps=0.0, want_stats=False, rope=None, rope_heads=0):
+    """lp_gemm_bf16_ex: lp_gemm_bf16 plus the epilogue fusions — `norm_mode` (NORM_RMS / NORM_LAYER) normalises the rows of
+    `a` from `stats_in` fp32 [M, parts, 2] (w must be the gain-folded matrix; LAYER also needs `colsum` and the folded bias),
+    `want_stats` returns (out, stats [M, parts, 2]) of the bf16 outputs, `rope` = (cos, sin) fp32 [M, 64] rotates the first
+    `rope_heads` 128-column heads."""
+    _chk_bf16(a, "a")
+    _chk_bf16(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    d = _lib.GemmDesc()
+    d.A, d.lda, d.W, d.ldw, d.C, d.ldc = _lib.ptr(a), a.stride(0), _lib.ptr(w), w.stride(0), _lib.ptr(out), out.stride(0)
+    d.M, d.N, d.K = M, N, K
+    d.bias = _lib.ptr(bias)
+    d.residual, d.ldr, d.res_row_mod = _lib.ptr(residual), (residual.stride(0) if residual is not None else 0), res_row_mod
+    d.act, d.out_fp32, d.block_n = act, 1 if out.dtype == torch.float32 else 0, block_n
+    d.norm_mode = norm_mode
+    if stats_in is not None:
+        d.stats_in, d.stats_in_parts = _lib.ptr(stats_in), stats_in.shape[1]
+    d.colsum, d.norm_eps = _lib.ptr(colsum), float(eps)
+    stats = None
+    if want_stats:
+        bn = block_n or gemm_pick_block_n(M, N, act)
+        d.block_n = bn
+        parts = 2 * (-(-N // bn))
+        stats = torch.empty((M, parts, 2), device=a.device, dtype=torch.float32)
+        d.stats_out, d.stats_out_parts = _lib.ptr(stats), parts
+    if rope is not None:
+        d.rope_cos, d.rope_sin, d.rope_heads = _lib.ptr(rope[0]), _lib.ptr(rope[1]), rope_heads
+    rc = _lib.lib().lp_gemm_bf16_ex(C.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "lp_gemm_bf16_ex")
+    return (out, stats) if want_stats else out
 
 
 def attention(qkv, B, T, n_heads, n_kv_heads, head_dim, head_stride, q_off, k_off, v_off, causal, scale=None,
@@ -409,3 +463,58 @@ def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_
                             dqkv.stride(0), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "lp_attention_bwd")
     return dqkv
+
+
+# ---- parity mode (csrc/lp_parity.cu; sequencing in leopard_b200/parity.py) ---------------------------------------------------
+def _chk_f32_rows(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise TypeError(f"{name} must be a CUDA fp32 matrix with contiguous rows")
+
+
+def parity_split(x, out, layout):
+    """x fp32 [M, K] (row stride arbitrary: column slices allowed) -> out bf16 [>= M, >= n K] three-term split along K
+    (lp_parity_split; layouts in the header)."""
+    _chk_f32_rows(x, "x")
+    M, K = x.shape
+    _lib.check(_lib.lib().lp_parity_split(_lib.ptr(x), x.stride(0), M, K, _lib.ptr(out), out.stride(0), layout, _lib.stream_ptr()),
+               "lp_parity_split")
+    return out
+
+
+def parity_norm(x, gamma, beta, eps, rms):
+    _chk_f32(x, "x")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().lp_parity_norm(_lib.ptr(x), x.stride(0), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out), out.stride(0),
+                                         x.shape[0], x.shape[1], float(eps), 1 if rms else 0, _lib.stream_ptr()), "lp_parity_norm")
+    return out
+
+
+def parity_act(x, kind):
+    _chk_f32(x, "x")
+    n_out = x.shape[1] // 2 if kind == ACT_SWIGLU else x.shape[1]
+    out = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().lp_parity_act(_lib.ptr(x), x.stride(0), _lib.ptr(out), out.stride(0), x.shape[0], x.shape[1], kind,
+                                        _lib.stream_ptr()), "lp_parity_act")
+    return out
+
+
+def parity_add_(y, x, row_mod=0):
+    _chk_f32(y, "y")
+    _chk_f32(x, "x")
+    _lib.check(_lib.lib().lp_parity_add(_lib.ptr(y), y.stride(0), _lib.ptr(x), x.stride(0), y.shape[0], y.shape[1], row_mod,
+                                        _lib.stream_ptr()), "lp_parity_add")
+    return y
+
+
+def parity_rope_(x, n_heads, head_dim, cs, sn):
+    _chk_f32(x, "x")
+    _lib.check(_lib.lib().lp_parity_rope(_lib.ptr(x), x.stride(0), x.shape[0], n_heads, head_dim, _lib.ptr(cs), _lib.ptr(sn),
+                                         _lib.stream_ptr()), "lp_parity_rope")
+    return x
+
+
+def parity_softmax_(scores, Tk, scale, causal):
+    _chk_f32(scores, "scores")
+    _lib.check(_lib.lib().lp_parity_softmax(_lib.ptr(scores), scores.stride(0), scores.shape[0], Tk, float(scale),
+                                            1 if causal else 0, _lib.stream_ptr()), "lp_parity_softmax")
+    return scores

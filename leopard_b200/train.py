@@ -529,6 +529,11 @@ class SFTTrainer:
             else:
                 ops.adamw_step(model_t.reshape(-1), g, m, v, None, self.iteration, lr, hp["beta1"], hp["beta2"], hp["eps"],
                                hp["wd"], self._norm_out)
+        # the engine's gain-folded copies of these weights (fused-norm prefill) are stale now; re-derived on next use
+        if not self.freeze_llm:
+            self.w.folded_dirty.add("dec")
+        if not self.freeze_vit:
+            self.w.folded_dirty.add("vit")
         loss = torch.stack(losses).mean()
         if self.world > 1:           # the logged loss is the data-parallel average (average_losses_across_data_parallel_group,
             loss = loss.clone()      # pretrain_megatron_llava.py:119)

@@ -271,3 +271,56 @@ def attention_bwd(qkv, out, dout, B, T, n_heads, n_kv_heads, head_dim, q_off, k_
         put(rows, k_off, n_kv_heads, dk)
         put(rows, v_off, n_kv_heads, dv)
     return dqkv
+
+
+# ---- parity mode (csrc/lp_parity.cu): contracts of the fp32 glue kernels ------------------------------------------------------
+def _split3(x):
+    h = x.to(BF)
+    r = x - h.float()
+    m = r.to(BF)
+    return h, m, (r - m.float()).to(BF)
+
+
+def parity_split(x, out, layout):
+    M, K = x.shape
+    h, m, l = _split3(x.float())
+    blocks = {0: (h, m, l), 1: (h, h, h, m, m, l), 2: (h, m, l, h, m, h)}[layout]
+    for j, b in enumerate(blocks):
+        out[:M, j * K:(j + 1) * K] = b
+    return out
+
+
+def parity_norm(x, gamma, beta, eps, rms):
+    if rms:
+        return x * torch.rsqrt((x * x).mean(-1, keepdim=True) + eps) * gamma
+    return F.layer_norm(x, (x.shape[1],), gamma, beta, eps)
+
+
+def parity_act(x, kind):
+    if kind == ACT_SWIGLU:
+        m, n = x.shape
+        g = x.view(m, n // 64, 2, 32)
+        return (F.silu(g[:, :, 0]) * g[:, :, 1]).reshape(m, n // 2)
+    return F.gelu(x, approximate="tanh") if kind == ACT_GELU_TANH else F.gelu(x)
+
+
+def parity_add_(y, x, row_mod=0):
+    y += x[torch.arange(y.shape[0]) % row_mod] if row_mod else x
+    return y
+
+
+def parity_rope_(x, n_heads, head_dim, cs, sn):
+    half = head_dim // 2
+    v = x[:, : n_heads * head_dim].reshape(x.shape[0], n_heads, 2, half).clone()
+    x1, x2 = v[:, :, 0], v[:, :, 1]
+    c, s = cs[:, None, :], sn[:, None, :]
+    x[:, : n_heads * head_dim] = torch.stack([x1 * c - x2 * s, x2 * c + x1 * s], 2).reshape(x.shape[0], n_heads * head_dim)
+    return x
+
+
+def parity_softmax_(scores, Tk, scale, causal):
+    s = scores[:, :Tk] * scale
+    if causal:
+        s = s.masked_fill(torch.ones(s.shape, dtype=torch.bool).triu(1), float("-inf"))
+    scores[:, :Tk] = torch.softmax(s, -1)
+    return scores

@@ -4,6 +4,7 @@
 // epilogue's named-barrier PTX statement and the hardware tanh of the GELU helper.
 #include "tc_emu.h"
 enum { LP_ACT_NONE = 0, LP_ACT_GELU_TANH = 1, LP_ACT_GELU_ERF = 2, LP_ACT_SWIGLU = 3 };
+enum { LP_NORM_NONE = 0, LP_NORM_RMS = 1, LP_NORM_LAYER = 2 };
 #include "emu_helpers.inc"
 #include "gemm_kernel.inc"
 #include "gemm4_kernel.inc"
@@ -32,10 +33,22 @@ static void run(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
 }
 
 // Same argument preparation as lp_gemm_bf16 (host part of lp_gemm.cu) for an explicit block_n / pair / grid choice.
-extern "C" void emu_gemm(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
-                         const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
-                         int block_n, int pair, int group_m, int ctas) {
-  GemmArgs args;
+struct EmuFusions {   // the epilogue fusions of lp_gemm_bf16_ex
+  int norm_mode; const float* stats_in; int stats_in_parts; const float* colsum; float norm_eps;
+  float* stats_out; const float* rope_cos; const float* rope_sin; int rope_heads;
+};
+
+extern "C" void emu_gemm_ex(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                            const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
+                            int block_n, int pair, int group_m, int ctas, const EmuFusions* fx) {
+  GemmArgs args = {};
+  if (fx) {
+    args.norm_mode = fx->norm_mode; args.stats_in = reinterpret_cast<const float2*>(fx->stats_in);
+    args.stats_in_parts = fx->stats_in_parts; args.colsum = fx->colsum; args.norm_eps = fx->norm_eps;
+    args.norm_inv_k = 1.0f / (float)K;
+    args.stats_out = reinterpret_cast<float2*>(fx->stats_out);
+    args.rope_cos = fx->rope_cos; args.rope_sin = fx->rope_sin; args.rope_heads = fx->rope_heads;
+  }
   args.M = M; args.N = N; args.K = K;
   args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32;
   args.bias = bias;
@@ -66,6 +79,13 @@ extern "C" void emu_gemm(const void* A, long long lda, const void* W, long long 
   }
 }
 
+extern "C" void emu_gemm(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                         const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
+                         int block_n, int pair, int group_m, int ctas) {
+  emu_gemm_ex(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_row_mod, act, out_fp32, block_n, pair, group_m, ctas,
+              nullptr);
+}
+
 
 // 4-CTA clusters (lp_gemm4.cu): argument preparation as in lp_gemm_bf16's mode-2 branch
 template <int BN, int STAGES>
@@ -76,7 +96,7 @@ static void run4(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
 extern "C" void emu_gemm4(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                           const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
                           int block_n, int group_m, int ctas) {
-  GemmArgs args;
+  GemmArgs args = {};
   args.M = M; args.N = N; args.K = K;
   args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32;
   args.bias = bias;

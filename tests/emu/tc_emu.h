@@ -149,6 +149,12 @@ inline void mbar_init(uint64_t* bar, uint32_t count) {
 }
 inline void fence_barrier_init() {}
 inline void fence_proxy_async_smem() {}
+inline void fence_proxy_async_all() {}
+inline unsigned ld_acquire_sys(const unsigned* p) { return std::atomic_ref<unsigned>(*const_cast<unsigned*>(p)).load(); }
+inline unsigned ld_acquire_gpu(const unsigned* p) { return ld_acquire_sys(p); }
+inline void st_release_sys(unsigned* p, unsigned v) { std::atomic_ref<unsigned>(*p).store(v); }
+inline void spin_until_sys(const unsigned* p, unsigned target) { while ((int)(ld_acquire_sys(p) - target) < 0) std::this_thread::yield(); }
+inline void spin_until_gpu(const unsigned* p, unsigned target) { while (ld_acquire_gpu(p) < target) std::this_thread::yield(); }
 inline void mbar_arrive_addr(uint32_t addr) {
   std::lock_guard<std::mutex> l(emu_tc::g_mu);
   auto& b = mbar_at(addr);

@@ -101,3 +101,102 @@ def test_four_cta_multicast_gemm_under_emulation(emu, M, N, K, bn, ctas, act, bi
     assert not bool(torch.isnan(out.float()).any())
     err = float((out.float() - want.float()).abs().max() / want.float().abs().max())
     assert err < (1e-5 if fp32 else 8e-3), err
+
+
+# ---- epilogue fusions of lp_gemm_bf16_ex: row statistics (producer), folded LayerNorm / RMSNorm (consumer), RoPE -------------
+class _Fx(C.Structure):
+    _fields_ = [("norm_mode", C.c_int), ("stats_in", C.c_void_p), ("stats_in_parts", C.c_int), ("colsum", C.c_void_p),
+                ("norm_eps", C.c_float), ("stats_out", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+                ("rope_heads", C.c_int)]
+
+
+def _gemm_ex(emu, a, w, out, bias=None, res=None, act=0, bn=128, pair=False, ctas=2, fx=None):
+    M, K = a.shape
+    N = w.shape[0]
+    emu.emu_gemm_ex(P(a), LL(a.stride(0)), P(w), LL(w.stride(0)), P(out), LL(out.stride(0)), M, N, K, P(bias), P(res),
+                    LL(res.stride(0) if res is not None else 0), 0, act, int(out.dtype == torch.float32), bn, int(pair), 1, ctas,
+                    C.byref(fx) if fx is not None else None)
+
+
+def _split_stats(x, parts):
+    """Row (sum, sum of squares) of x split into `parts` arbitrary column groups -> [M, parts, 2] fp32."""
+    cols = torch.tensor_split(x.float(), parts, dim=1)
+    return torch.stack([torch.stack([c.sum(1), (c * c).sum(1)], -1) for c in cols], 1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,bn,pair,ctas", [(300, 384, 136, 128, False, 2), (600, 1152, 200, 256, True, 4)])
+def test_producer_epilogue_writes_row_statistics_of_the_rounded_outputs(emu, M, N, K, bn, pair, ctas):
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    b = torch.randn(N, generator=g)
+    r = torch.randn((M, N), generator=g).to(BF)
+    parts = 2 * (-(-N // bn))
+    out = torch.full((M, N), float("nan"), dtype=BF)
+    stats = torch.full((M, parts, 2), float("nan"))
+    fx = _Fx(stats_out=stats.data_ptr())
+    _gemm_ex(emu, a, w, out, bias=b, res=r, bn=bn, pair=pair, ctas=ctas, fx=fx)
+    want = ref.gemm(a, w, bias=b, residual=r)
+    assert float((out.float() - want.float()).abs().max() / want.float().abs().max()) < 8e-3
+    assert not bool(torch.isnan(stats).any())                    # every (row, slot) written, also for ragged column blocks
+    tot = stats.sum(1)
+    o = out.float()
+    assert torch.allclose(tot[:, 0], o.sum(1), rtol=1e-4, atol=1e-3) and torch.allclose(tot[:, 1], (o * o).sum(1), rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode,act,pair,bn", [(2, 1, False, 128), (2, 0, True, 256), (1, 3, True, 128), (1, 0, False, 256)])
+def test_consumer_epilogue_applies_folded_norm(emu, mode, act, pair, bn):
+    """norm(x) W^T (+ b) == rs * (x W'^T - mu * colsum) + (beta W^T + b) with W' = W diag(gamma): LayerNorm (+GELU) and RMSNorm
+    (+SwiGLU) against the unfused arithmetic on the same bf16 inputs."""
+    M, N, K, eps = 300, 512, 264, 1e-5
+    g = torch.Generator().manual_seed(11 + mode)
+    x = (torch.randn((M, K), generator=g) * 1.5 + 0.3).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    gamma, beta = 1 + 0.1 * torch.randn(K, generator=g), 0.1 * torch.randn(K, generator=g)
+    b = torch.randn(N, generator=g) * 0.1
+    xf, wf32 = x.float(), w.float()
+    if mode == 2:
+        h = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, eps)
+        bias_f = wf32 @ beta + b
+    else:
+        h = xf * torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps) * gamma
+        bias_f = None
+    y = h @ wf32.t() + (b if mode == 2 else 0)
+    if act == 1:
+        y = torch.nn.functional.gelu(y, approximate="tanh")
+    elif act == 3:
+        yy = y.view(M, N // 64, 2, 32)
+        y = (torch.nn.functional.silu(yy[:, :, 0]) * yy[:, :, 1]).reshape(M, N // 2)
+    wfold = (wf32 * gamma[None]).to(BF)
+    colsum = wfold.float().sum(1).contiguous()
+    stats = _split_stats(x, 5)
+    out = torch.full(y.shape, float("nan"), dtype=BF)
+    fx = _Fx(norm_mode=mode, stats_in=stats.data_ptr(), stats_in_parts=5, colsum=colsum.data_ptr(), norm_eps=eps)
+    _gemm_ex(emu, x, wfold, out, bias=bias_f, act=act, bn=bn, pair=pair, ctas=2, fx=fx)
+    err = float((out.float() - y).abs().max() / y.abs().max())
+    assert err < 1.5e-2, err
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_rope_epilogue_rotates_the_leading_heads(emu, pair):
+    """QKV GEMM with fused RMSNorm + rotate-half RoPE on the first 3 of 4 heads (128 columns each), BN = 256."""
+    M, K, heads, rot, eps = 300, 136, 4, 3, 1e-5
+    N = heads * 128
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    ang = torch.rand((M, 64), generator=g) * 6.28
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    xf = x.float()
+    rs = torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps)
+    y = (rs * (xf @ w.float().t())).view(M, heads, 128)
+    lo, hi = y[..., :64], y[..., 64:]
+    rotd = torch.cat([lo * cos[:, None] - hi * sin[:, None], hi * cos[:, None] + lo * sin[:, None]], -1)
+    want = torch.cat([rotd[:, :rot], y[:, rot:]], 1).reshape(M, N)
+    stats = _split_stats(x, 1)
+    out = torch.full((M, N), float("nan"), dtype=BF)
+    fx = _Fx(norm_mode=1, stats_in=stats.data_ptr(), stats_in_parts=1, norm_eps=eps, rope_cos=cos.data_ptr(),
+             rope_sin=sin.data_ptr(), rope_heads=rot)
+    _gemm_ex(emu, x, w, out, bn=256, pair=pair, ctas=2, fx=fx)
+    err = float((out.float() - want).abs().max() / want.abs().max())
+    assert err < 8e-3, err

@@ -140,3 +140,31 @@ def test_full_depth_cfg1_parity(seeded_full_engine):
     assert e_img < 4e-2
     assert e < 6e-2
     assert top > 0.9
+
+
+def test_fused_norm_layer_loops_match_the_standalone_norm_kernels(small):
+    """lp_model_set_fused_norm(1) (default: LayerNorm / RMSNorm folded into the GEMM epilogues, RoPE in the QKV epilogue) against
+    the standalone-kernel sequencing on the same weights: both within the oracle tolerance and close to each other; the KV
+    cache path (RoPE applied by the append kernel) agrees with the cache-less path."""
+    from leopard_b200 import _lib
+    cfg, ck, eng = small
+    pix, ids = synth_inputs(cfg, n_crops=2, n_text=24)
+    ref = om.prefill_logits(ck, cfg, ids, pix.to(torch.bfloat16).float())[0]
+    L = _lib.lib()
+    try:
+        assert L.lp_model_set_fused_norm(1) in (0, 1)
+        n0 = L.lp_launch_count()
+        fused, _, _ = eng.prefill([(ids[0], pix.cuda())], "all")
+        n_fused = L.lp_launch_count() - n0
+        with_kv, kv, _ = eng.prefill([(ids[0], pix.cuda())], "all", want_kv=True)
+        L.lp_model_set_fused_norm(0)
+        n0 = L.lp_launch_count()
+        plain, _, _ = eng.prefill([(ids[0], pix.cuda())], "all")
+        n_plain = L.lp_launch_count() - n0
+        plain_kv, kv0, _ = eng.prefill([(ids[0], pix.cuda())], "all", want_kv=True)
+    finally:
+        L.lp_model_set_fused_norm(1)
+    assert n_fused < n_plain                      # 2 norm launches per tower layer, 2 norms + RoPE per decoder layer are gone
+    assert rel_err(fused, ref) < 3e-2 and rel_err(plain, ref) < 3e-2
+    assert rel_err(fused, plain.cpu()) < 2e-2 and rel_err(with_kv, fused.cpu()) < 2e-2
+    assert rel_err(kv.float(), kv0.float().cpu()) < 2e-2 and rel_err(with_kv, plain_kv.cpu()) < 2e-2

@@ -202,3 +202,71 @@ def test_bad_arguments_report_errors(native_lib):
         ops.gemm(a[:, :60], torch.zeros(16, 60, dtype=torch.bfloat16, device="cuda"))
     with pytest.raises(NativeError, match="head_dim"):
         ops.attention(torch.zeros(4, 192, dtype=torch.bfloat16, device="cuda"), 1, 4, 1, 1, 64, 64, 0, 64, 128, True)
+
+
+# ---- lp_gemm_bf16_ex: epilogue fusions (row statistics -> folded LayerNorm / RMSNorm, RoPE) ---------------------------------
+def test_gemm_ex_row_statistics_and_folded_layernorm_chain(native_lib):
+    """Producer GEMM (bias + residual) writes per-row (sum, sum of squares) partials; the consumer GEMM normalises its A rows
+    from them with the LayerNorm gain folded into the weight: == layer_norm(x) @ W^T + b (+ GELU) on the same bf16 values."""
+    from leopard_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    M, K0, D, N, eps = 1400, 592, 1152, 4304, 1e-6
+    a = torch.randn((M, K0), generator=g).to(torch.bfloat16).cuda()
+    w0 = (torch.randn((D, K0), generator=g) * K0 ** -0.5).to(torch.bfloat16).cuda()
+    b0 = (torch.randn(D, generator=g) * 0.1).cuda()
+    res = torch.randn((M, D), generator=g).to(torch.bfloat16).cuda()
+    x, stats = ops.gemm_ex(a, w0, bias=b0, residual=res, want_stats=True)
+    xf = x.float()
+    tot = stats.sum(1)
+    assert torch.allclose(tot[:, 0], xf.sum(1), rtol=1e-4, atol=2e-3) and torch.allclose(tot[:, 1], (xf * xf).sum(1), rtol=1e-4)
+    assert torch.equal(x, ops.gemm(a, w0, bias=b0, residual=res))          # statistics do not change the outputs
+    w = (torch.randn((N, D), generator=g) * D ** -0.5).to(torch.bfloat16).cuda()
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).cuda(), (0.1 * torch.randn(D, generator=g)).cuda()
+    b = (torch.randn(N, generator=g) * 0.1).cuda()
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xf, (D,), gamma, beta, eps) @ w.float().t() + b,
+                                    approximate="tanh")
+    wfold = (w.float() * gamma[None]).to(torch.bfloat16)
+    got = ops.gemm_ex(x, wfold, bias=w.float() @ beta + b, act=ops.ACT_GELU_TANH, norm_mode=ops.NORM_LAYER, stats_in=stats,
+                      colsum=wfold.float().sum(1).contiguous(), eps=eps)
+    assert float((got.float() - want).abs().max() / want.abs().max()) < 1.5e-2
+    # lp_row_stats is the stand-alone producer: same consumer result up to summation order
+    got2 = ops.gemm_ex(x, wfold, bias=w.float() @ beta + b, act=ops.ACT_GELU_TANH, norm_mode=ops.NORM_LAYER,
+                       stats_in=ops.row_stats(x), colsum=wfold.float().sum(1).contiguous(), eps=eps)
+    assert float((got2.float() - got.float()).abs().max()) < 2e-2 * float(want.abs().max())
+
+
+def test_gemm_ex_rmsnorm_swiglu_and_rope(native_lib):
+    from leopard_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    M, D, F, eps = 700, 4096, 1024, 1e-5
+    x = torch.randn((M, D), generator=g).to(torch.bfloat16).cuda()
+    gamma = (1 + 0.1 * torch.randn(D, generator=g)).cuda()
+    xf = x.float()
+    rs = torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps)
+    stats = ops.row_stats(x)
+    # gate/up with SwiGLU on 32-row granules
+    wgu = (torch.randn((2 * F, D), generator=g) * D ** -0.5).to(torch.bfloat16).cuda()
+    y = (xf * rs * gamma) @ wgu.float().t()
+    yy = y.view(M, 2 * F // 64, 2, 32)
+    want = (torch.nn.functional.silu(yy[:, :, 0]) * yy[:, :, 1]).reshape(M, F)
+    got = ops.gemm_ex(x, (wgu.float() * gamma[None]).to(torch.bfloat16), act=ops.ACT_SWIGLU, norm_mode=ops.NORM_RMS, stats_in=stats,
+                      eps=eps)
+    assert float((got.float() - want).abs().max() / want.abs().max()) < 1.5e-2
+    # QKV with RoPE on 6 of 8 heads
+    heads, rot = 8, 6
+    wq = (torch.randn((heads * 128, D), generator=g) * D ** -0.5).to(torch.bfloat16).cuda()
+    pos = torch.arange(M, dtype=torch.int32).cuda()
+    inv = (1.0 / (10000.0 ** (torch.arange(0, 128, 2).float() / 128))).cuda()
+    cos, sin = ops.rope_table(pos, inv)
+    yq = ((xf * rs * gamma) @ wq.float().t()).view(M, heads, 128)
+    lo, hi = yq[..., :64], yq[..., 64:]
+    rotd = torch.cat([lo * cos[:, None] - hi * sin[:, None], hi * cos[:, None] + lo * sin[:, None]], -1)
+    want = torch.cat([rotd[:, :rot], yq[:, rot:]], 1).reshape(M, heads * 128)
+    got = ops.gemm_ex(x, (wq.float() * gamma[None]).to(torch.bfloat16), norm_mode=ops.NORM_RMS, stats_in=stats, eps=eps,
+                      rope=(cos, sin), rope_heads=rot)
+    assert float((got.float() - want).abs().max() / want.abs().max()) < 1.5e-2
+    # == the unfused kernels (norm -> GEMM -> in-place RoPE) within bf16 rounding of the intermediate
+    h = ops.rmsnorm(x, gamma, eps)
+    ref2 = ops.gemm(h, wq)
+    ops.rope_inplace(ref2, 0, rot, 128, cos, sin)
+    assert float((got.float() - ref2.float()).abs().max() / want.abs().max()) < 2e-2

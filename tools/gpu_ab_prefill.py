@@ -31,6 +31,8 @@ def apply(setting):
         L.lp_set_prefill_pdl(v)
     elif k == "norm":
         L.lp_norm_set_variant(v)
+    elif k == "fused":
+        L.lp_model_set_fused_norm(v)
     else:
         raise SystemExit(f"unknown switch {k}")
 
@@ -59,3 +61,4 @@ for s in settings:
     print(json.dumps({"setting": s, "ms_per_step": res[s], "best": min(res[s]), "tokens_per_s": round(S / min(res[s]) * 1e3, 1)}))
 L.lp_model_set_attention_variant(80)
 L.lp_gemm_set_pair_mode(1)
+L.lp_model_set_fused_norm(1)
