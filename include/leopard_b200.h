@@ -87,6 +87,36 @@ int lp_row_stats(const void* x, long long ldx, int rows, int width, float* stats
  * when the weight structs carry the folded matrices, 0 = standalone norm / RoPE kernels.  Returns the previous setting. */
 int lp_model_set_fused_norm(int enable);
 
+/* Tensor parallel + sequence parallel launches (reference: ColumnParallelLinear / RowParallelLinear with
+ * sequence_parallel, MLM/core/tensor_parallel/layers.py:387-454, mappings.py:119-199).  The M rows are tp_size segments of
+ * seg_rows rows, segment r owned by rank r.  One kernel does the collective AND the GEMM over NVLink peer memory:
+ *   LP_TP_ALLGATHER       C[M, N'] = act(A W^T): A is this rank's [M, lda] gather buffer of which only its own segment is valid
+ *                         on entry; peer_A[r] is rank r's buffer (peer pointer).  The epilogue warps of all CTAs pull the peers'
+ *                         segments in while the tiles of the own segment are multiplied; tiles of a peer segment wait for the copy.
+ *   LP_TP_REDUCE_SCATTER  partial sums A W^T (K is this rank's shard) leave the epilogue as TMA stores into the OWNER's staging
+ *                         buffer peer_stage[r] = rank r's bf16 [tp_size, seg_rows, ldc] at slot [tp_rank]; the last CTA posts
+ *                         `epoch` to every owner; lp_tp_reduce on the owner sums the slots in rank order (+ residual).  C unused.
+ * Cross-rank signalling: 16 u32 words per rank (signal_local; signal_peer[r] = rank r's words as peer pointers): word [r] = rank
+ * r's all-gather readiness, word [8 + r] = rank r's reduce-scatter completion, compared with `epoch` (monotonic call number, the
+ * same on every rank).  counter: a zeroed local u32 for this call; recycle: an older call's counter to re-zero (or NULL).
+ * Waits are bounded (a missing peer traps the kernel instead of hanging the GPU). */
+enum lp_tp_mode { LP_TP_ALLGATHER = 1, LP_TP_REDUCE_SCATTER = 2 };
+typedef struct lp_tp_desc {
+  int tp_size, tp_rank, seg_rows, mode;
+  unsigned epoch;
+  const void* peer_A[8];
+  void* peer_stage[8];
+  unsigned* counter;
+  unsigned* recycle;
+  unsigned* signal_local;
+  unsigned* signal_peer[8];
+} lp_tp_desc;
+int lp_gemm_bf16_tp(const lp_gemm_desc* desc, const lp_tp_desc* tp, void* stream);
+/* out[seg_rows, cols] = residual + sum_r stage[r] (fp32 sum in rank order, one bf16 rounding) once every rank's word [8 + r] of
+ * signal_local has reached `epoch`.  stage: this rank's bf16 [tp_size, seg_rows, ld]. */
+int lp_tp_reduce(const lp_tp_desc* tp, const void* stage, long long ld, const void* residual, long long ldr, void* out, long long ldo,
+                 int cols, void* stream);
+
 /* GEMM scheduling mode: 0 = one CTA per 128-row tile; 1 = CTA pairs (thread-block cluster of 2, tcgen05
  * cta_group::2, 256-row tiles) for problems with at least one tile per SM pair.  Returns the previous mode.
  * Results are identical up to fp32 summation order (same K order: bit-identical in practice).

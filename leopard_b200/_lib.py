@@ -62,6 +62,13 @@ class GemmDesc(C.Structure):
 
 
 NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
+TP_ALLGATHER, TP_REDUCE_SCATTER = 1, 2
+
+
+class TpDesc(C.Structure):
+    """lp_tp_desc (include/leopard_b200.h)."""
+    _fields_ = [("tp_size", _i), ("tp_rank", _i), ("seg_rows", _i), ("mode", _i), ("epoch", C.c_uint), ("peer_A", _vp * 8),
+                ("peer_stage", _vp * 8), ("counter", _vp), ("recycle", _vp), ("signal_local", _vp), ("signal_peer", _vp * 8)]
 
 
 class ProfileRecord(C.Structure):
@@ -80,6 +87,8 @@ _SIGS = {
     "lp_row_stats": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
     "lp_model_set_fused_norm": (_i, [_i]),
     "lp_gemm_set_pair_mode": (_i, [_i]),
+    "lp_gemm_bf16_tp": (_i, [C.POINTER(GemmDesc), C.POINTER(TpDesc), _vp]),
+    "lp_tp_reduce": (_i, [C.POINTER(TpDesc), _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp]),
     "lp_parity_split": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _vp]),
     "lp_parity_norm": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
     "lp_parity_act": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp]),

@@ -29,10 +29,11 @@ namespace lp {
 // [m0 + 128 r, +128) of A and rows [n0 + r BN/2, + BN/2) of W, the leader's MMA thread issues M = 256 MMAs that read
 // both CTAs' shared memory and write each CTA's 128 accumulator rows into its own TMEM.  Halving the W bytes staged
 // per SM relieves the per-SM L2->SMEM bandwidth (the 1-CTA kernel runs at ~75 % of it) and deepens the ring.
-template <int BN, int STAGES, bool CTA2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
+// TP = true: tensor-parallel launch (lp_gemm_bf16_tp) — segmented rows, output through per-segment tensor maps `segC`, optional
+// all-gather prologue and reduce-scatter signalling (see GemmArgs)
+template <int BN, int STAGES, bool CTA2, bool TP>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                          const CUtensorMap* segC, const GemmArgs& args) {
   using L = GemmSmem<BN, STAGES, CTA2>;
   constexpr int BMT = CTA2 ? 2 * GEMM_BM : GEMM_BM;  // rows per work unit
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
@@ -87,10 +88,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool gathered = false;
       for (int tile = unit; tile < num_tiles; tile += n_units) {
-        int m_blk, n_blk;
+        int m_blk, n_blk, seg, row_limit;
         tile_coords(args, tile, m_blk, n_blk);
-        const int a_row = m_blk * BMT + (int)cta_rank * GEMM_BM;
+        const int a_row = tile_row0(args, m_blk, BMT, seg, row_limit) + (int)cta_rank * GEMM_BM;
+        if (TP && args.ag_counter != nullptr && seg != args.tp_rank && !gathered) {
+          // rows of other ranks: wait until every CTA's epilogue warps have finished copying them in (all-gather prologue)
+          spin_until_gpu(args.ag_counter, gridDim.x);
+          fence_proxy_async_all();
+          gathered = true;
+        }
         // ragged last column block: the MMA runs with N = n_rt (multiple of 32), so a pair splits n_rt, not BN
         const int n_rt = min(BN, ((args.N - n_blk * BN) + 31) & ~31);
         const int b_row = n_blk * BN + (CTA2 ? (int)cta_rank * (n_rt / 2) : 0);
@@ -161,10 +169,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool swiglu = args.act == LP_ACT_SWIGLU;
     constexpr int NC = BN / 32;         // 32-column chunks per tile
     constexpr int NP = BN / 64;         // 64-column gate/up pairs per tile
+    if (TP && args.ag_counter != nullptr) {
+      // ---- all-gather prologue: while the MMA warps work on this rank's own rows, the 256 epilogue threads of every CTA pull
+      // the other ranks' rows of A over NVLink (16-byte loads from peer memory) into the local A buffer.
+      if (blockIdx.x == 0 && et == 0) {      // this rank's rows are final (stream order): tell the peers
+        for (int r = 1; r < args.tp_size; ++r) st_release_sys(args.ag_post[(args.tp_rank + r) % args.tp_size], args.epoch);
+      }
+      const int vec_per_row = args.ag_cols >> 3;
+      const long long total = (long long)args.seg_rows * vec_per_row;
+      const long long ldv = args.ag_ld >> 3;
+      for (int r = 1; r < args.tp_size; ++r) {
+        const int p = (args.tp_rank + r) % args.tp_size;
+        if (et == 0) spin_until_sys(args.ag_wait[p], args.epoch);
+        epi_named_barrier();
+        const uint4* src = reinterpret_cast<const uint4*>(args.ag_src[p]) + (long long)p * args.seg_rows * ldv;
+        uint4* dst = reinterpret_cast<uint4*>(args.ag_dst) + (long long)p * args.seg_rows * ldv;
+        const long long stride = (long long)gridDim.x * GEMM_EPI_THREADS;
+        long long i = (long long)blockIdx.x * GEMM_EPI_THREADS + et;
+        for (; i + 3 * stride < total; i += 4 * stride) {       // four independent 16-byte loads in flight per thread
+          long long o[4];
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const long long j = i + u * stride;
+            o[u] = (j / vec_per_row) * ldv + (j % vec_per_row);
+            v[u] = src[o[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dst[o[u]] = v[u];
+        }
+        for (; i < total; i += stride) {
+          const long long o = (i / vec_per_row) * ldv + (i % vec_per_row);
+          dst[o] = src[o];
+        }
+      }
+      __threadfence();
+      fence_proxy_async_all();     // the copied rows are read by TMA (async proxy)
+      epi_named_barrier();
+      if (et == 0) atomicAdd(args.ag_counter, 1u);
+    }
     for (int tile = unit; tile < num_tiles; tile += n_units) {
-      int m_blk, n_blk;
+      int m_blk, n_blk, seg, row_limit;
       tile_coords(args, tile, m_blk, n_blk);
-      const int m0 = m_blk * BMT + (int)cta_rank * GEMM_BM, n0 = n_blk * BN;
+      const int m0 = tile_row0(args, m_blk, BMT, seg, row_limit) + (int)cta_rank * GEMM_BM, n0 = n_blk * BN;
+      // tensor-parallel launches store through the segment's own map (rows clipped at the segment end; a reduce-scatter
+      // launch's maps point at the owner rank's staging memory), with row coordinates relative to the segment
+      const CUtensorMap* tmc = TP ? &segC[seg] : &tmC;
+      const int st_shift = TP ? seg * args.seg_rows : 0;
       float* bs = bias_smem + as * BN;
       float* cs = colsum_smem + as * BN;
       if (args.bias) {
@@ -174,7 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = et; i < BN; i += GEMM_EPI_THREADS) cs[i] = (n0 + i < args.N) ? args.colsum[n0 + i] : 0.f;
       }
       const int row = m0 + lg * 32 + lane;
-      const bool row_ok = row < args.M;
+      const bool row_ok = row < row_limit;
       // row statistics of the A operand are fetched while the tile's MMAs are still running
       float rs, nmu;
       row_norm_coeffs(args, row, row_ok, rs, nmu);
@@ -215,8 +266,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               LP_ROPE_PAIR(0, c4.x, s4.x) LP_ROPE_PAIR(1, c4.y, s4.y) LP_ROPE_PAIR(2, c4.z, s4.z) LP_ROPE_PAIR(3, c4.w, s4.w)
 #undef LP_ROPE_PAIR
             }
-            staged_store_chunk(args, &tmC, stage, lo, nullptr, row_base, n0 + (c_begin + p) * 32, lane, ostat_p);
-            staged_store_chunk(args, &tmC, stage, hi, nullptr, row_base, n0 + (c_begin + p + 2) * 32, lane, ostat_p);
+            staged_store_chunk(args, tmc, stage, lo, nullptr, row_base - st_shift, n0 + (c_begin + p) * 32, lane, ostat_p);
+            staged_store_chunk(args, tmc, stage, hi, nullptr, row_base - st_shift, n0 + (c_begin + p + 2) * 32, lane, ostat_p);
           }
         } else {
         ResidualRegs rr;
@@ -240,7 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ResidualRegs cur = rr;
             if (has_res && c + 1 < c_end && col0 + 32 < args.N)  // prefetch the next chunk's residual
               residual_fetch(args, rr, row_base, col0 + 32, args.N, lane);
-            staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0, lane, ostat_p);
+            staged_store_chunk(args, tmc, stage, v, has_res ? &cur : nullptr, row_base - st_shift, col0, lane, ostat_p);
           }
         }
         }
@@ -268,7 +319,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ResidualRegs cur = rr;
           if (has_res && c + 1 < c_end && col0 + 64 < args.N)
             residual_fetch(args, rr, row_base, (col0 + 64) / 2, args.N / 2, lane);
-          staged_store_chunk(args, &tmC, stage, v, has_res ? &cur : nullptr, row_base, col0 / 2, lane);
+          staged_store_chunk(args, tmc, stage, v, has_res ? &cur : nullptr, row_base - st_shift, col0 / 2, lane);
         }
       }
       if (args.stats_out != nullptr && row_ok)
@@ -293,6 +344,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (CTA2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (TP && threadIdx.x == 0) {
+    if (args.rs_counter != nullptr) {
+      // reduce-scatter: every epilogue warp has waited for its bulk stores (partial tiles in the owners' memory); the last CTA to
+      // get here tells every owner that this rank's partial sums have landed
+      fence_proxy_async_all();
+      __threadfence_system();
+      if (atomicAdd(args.rs_counter, 1u) == gridDim.x - 1) {
+        for (int r = 0; r < args.tp_size; ++r) st_release_sys(args.rs_post[r], args.epoch);
+        if (args.recycle != nullptr) *args.recycle = 0u;
+      }
+    } else if (blockIdx.x == 0 && args.recycle != nullptr) {
+      *args.recycle = 0u;
+    }
+  }
+}
+
+template <int BN, int STAGES, bool CTA2>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
+  gemm_body<BN, STAGES, CTA2, false>(tmA, tmB, tmC, nullptr, args);
+}
+
+template <int BN, int STAGES, bool CTA2>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ GemmSegMaps segs, const GemmArgs args) {
+  gemm_body<BN, STAGES, CTA2, true>(tmA, tmB, segs.m[0], segs.m, args);
 }
 
 template <int BN, int STAGES, bool CTA2>
@@ -482,6 +561,85 @@ extern "C" int lp_gemm_bf16(const void* A, long long lda, const void* W, long lo
   d.bias = bias; d.residual = residual; d.ldr = ldr; d.res_row_mod = res_row_mod;
   d.act = act; d.out_fp32 = out_fp32; d.block_n = block_n;
   return lp_gemm_bf16_ex(&d, stream_);
+}
+
+// ---- tensor-parallel launches: all-gather -> GEMM and GEMM -> reduce-scatter in ONE kernel over NVLink peer memory
+extern "C" int lp_gemm_bf16_tp(const lp_gemm_desc* d, const lp_tp_desc* t, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LP_REQUIRE(d && t, "lp_gemm_bf16_tp: null descriptor");
+  LP_REQUIRE(t->tp_size >= 2 && t->tp_size <= 8 && t->tp_rank >= 0 && t->tp_rank < t->tp_size, "lp_gemm_bf16_tp: tp_size=%d rank=%d",
+             t->tp_size, t->tp_rank);
+  LP_REQUIRE(t->mode == LP_TP_ALLGATHER || t->mode == LP_TP_REDUCE_SCATTER, "lp_gemm_bf16_tp: bad mode %d", t->mode);
+  LP_REQUIRE(d->M == t->tp_size * t->seg_rows && t->seg_rows > 0, "lp_gemm_bf16_tp: M=%d must be tp_size * seg_rows (%d x %d)", d->M,
+             t->tp_size, t->seg_rows);
+  LP_REQUIRE(d->N % 8 == 0 && d->K % 8 == 0 && d->lda % 8 == 0 && d->ldw % 8 == 0 && d->ldc % 8 == 0 && !d->out_fp32,
+             "lp_gemm_bf16_tp: bf16 output, 16-byte aligned strides");
+  LP_REQUIRE(d->residual == nullptr && d->norm_mode == LP_NORM_NONE && d->stats_out == nullptr && d->rope_heads == 0,
+             "lp_gemm_bf16_tp: residual / norm / RoPE fusions are not combined with the tensor-parallel launches");
+  LP_REQUIRE(d->act == LP_ACT_NONE || (d->act == LP_ACT_SWIGLU && d->N % 64 == 0 && t->mode == LP_TP_ALLGATHER),
+             "lp_gemm_bf16_tp: act must be NONE (or SWIGLU after an all-gather)");
+  LP_REQUIRE(t->counter != nullptr && t->signal_local != nullptr, "lp_gemm_bf16_tp: counter / signal words missing");
+  constexpr int BN = 256;
+  GemmArgs args = {};
+  args.M = d->M; args.N = d->N; args.K = d->K;
+  args.C = d->C; args.ldc = d->ldc; args.out_fp32 = 0;
+  args.bias = d->bias; args.act = d->act;
+  args.tp_size = t->tp_size; args.tp_rank = t->tp_rank; args.seg_rows = t->seg_rows;
+  args.seg_m_blk = (t->seg_rows + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  args.num_m_blk = t->tp_size * args.seg_m_blk;
+  args.num_n_blk = (d->N + BN - 1) / BN;
+  args.num_k_blk = (d->K + GEMM_BK - 1) / GEMM_BK;
+  args.group_m = args.seg_m_blk;          // one segment per raster group: the rank's own rows (all column blocks) come first
+  args.epoch = t->epoch;
+  args.recycle = t->recycle;
+  const int n_out = d->act == LP_ACT_SWIGLU ? d->N / 2 : d->N;
+  GemmSegMaps segs;
+  int rc = 0;
+  if (t->mode == LP_TP_ALLGATHER) {
+    args.ag_counter = t->counter;
+    args.ag_dst = const_cast<void*>(d->A);
+    args.ag_ld = d->lda; args.ag_cols = d->K;
+    for (int r = 0; r < t->tp_size; ++r) {
+      LP_REQUIRE(r == t->tp_rank || (t->peer_A[r] != nullptr && t->signal_peer[r] != nullptr), "lp_gemm_bf16_tp: peer %d pointers missing", r);
+      args.ag_src[r] = t->peer_A[r];
+      args.ag_wait[r] = t->signal_local + r;                                   // written by rank r
+      args.ag_post[r] = t->signal_peer[r] ? t->signal_peer[r] + t->tp_rank : nullptr;   // my word on rank r
+      rc = make_tmap_2d(&segs.m[r], reinterpret_cast<__nv_bfloat16*>(d->C) + (size_t)r * t->seg_rows * d->ldc, 2, (uint64_t)n_out,
+                        (uint64_t)t->seg_rows, (uint64_t)d->ldc, 32, 32, 64);
+      if (rc) return rc;
+    }
+  } else {
+    args.rs_counter = t->counter;
+    for (int r = 0; r < t->tp_size; ++r) {
+      LP_REQUIRE(t->peer_stage[r] != nullptr && t->signal_peer[r] != nullptr, "lp_gemm_bf16_tp: peer %d staging / signal pointers missing", r);
+      args.rs_post[r] = t->signal_peer[r] + 8 + t->tp_rank;
+      // rank r's staging [tp_size, seg_rows, ldc]: this rank's partial sums for r's rows go to slot [tp_rank]
+      rc = make_tmap_2d(&segs.m[r], reinterpret_cast<__nv_bfloat16*>(t->peer_stage[r]) + (size_t)t->tp_rank * t->seg_rows * d->ldc, 2,
+                        (uint64_t)n_out, (uint64_t)t->seg_rows, (uint64_t)d->ldc, 32, 32, 64);
+      if (rc) return rc;
+    }
+  }
+  for (int r = t->tp_size; r < 8; ++r) segs.m[r] = segs.m[0];
+  CUtensorMap tmA, tmB;
+  rc = make_tmap_bf16_2d(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, GEMM_BK, GEMM_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, d->W, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldw, GEMM_BK, BN / 2);
+  if (rc) return rc;
+  using L = GemmSmem<BN, 6, true>;
+  auto kern = gemm_bf16_tp_kernel<BN, 6, true>;
+  static bool configured = false;
+  if (!configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = args.num_m_blk * args.num_n_blk;
+  const int pairs = sm_count() / 2;
+  ProfScope prof(1, d->M, d->N, d->K, stream);
+  note_launch();
+  LP_CHECK_CUDA(launch_ex(kern, dim3(2 * (tiles < pairs ? tiles : pairs)), dim3(GEMM_THREADS), L::TOTAL, stream, 2, false, tmA, tmB, segs,
+                          args));
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int lp_gemm_set_pair_mode(int enable) {

@@ -39,7 +39,7 @@ struct RowStats {
   float* buf;
   int parts;
 };
-constexpr int kMaxStatParts = 64;   // N <= 4096 with 128-wide tiles: 2 x 32 partials per row
+constexpr int kMaxStatParts = 32;   // producers use 256-wide tiles (produce_stats): N <= 4096 -> 2 x 16 partials per row
 
 inline lp_gemm_desc gemm_desc(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
                               int K, const float* bias, const void* residual, long long ldr, int res_row_mod, int act) {

@@ -178,10 +178,29 @@ class _LanguageModel:
         return out
 
 
-class myLlavaForConditionalGeneration:
-    """Native-backed stand-in for the reference class of the same name (…anyres.py:195-361)."""
+class _NativeParameters(nn.Module):
+    """Holds the kernel-layout weight tensors as (frozen) nn.Parameters that SHARE storage with the pointers the native library
+    reads, so `model.parameters()`, `named_parameters()`, parameter counting and hooks see the real weights."""
+
+    def __init__(self, named: dict):
+        super().__init__()
+        self.names = {}
+        for k, t in named.items():
+            if not t.is_floating_point():
+                continue
+            attr = k.replace(".", "__")
+            self.names[attr] = k
+            self.register_parameter(attr, nn.Parameter(t, requires_grad=False))
+
+
+class myLlavaForConditionalGeneration(nn.Module):
+    """Native-backed stand-in for the reference class of the same name (…anyres.py:195-361).  An `nn.Module` like the
+    `LlavaForConditionalGeneration` it replaces: `parameters()` / `named_parameters()` enumerate the kernel-layout weights,
+    `state_dict()` / `load_state_dict()` speak the reference's HF key layout (re-laid-out on the fly, loads are IN PLACE),
+    `eval()` / `train()` / hooks / `__call__` behave as usual; `.to()` accepts CUDA devices only (no CPU fallback)."""
 
     def __init__(self, config: Union[LeopardConfig, dict, None] = None):
+        super().__init__()
         if config is None:
             config = leopard_llava()
         if isinstance(config, dict):
@@ -193,16 +212,52 @@ class myLlavaForConditionalGeneration:
         self.device = torch.device("cpu")
         self.dtype = torch.float32
         self.training = False
+        self._precision = "bf16"
+        self.native = None       # _NativeParameters once the weights are on a device
         self.vision_tower = _VisionTower(self)
         self.multi_modal_projector = _Projector(self)
         self.language_model = _LanguageModel(self)
+
+    def _bind(self, native: NativeWeights):
+        self._native, self.device = native, native.device
+        self.engine = PrefillEngine(self.config, native)
+        self.native = _NativeParameters(native.named)
+
+    # ------------------------------------------------------------------ nn.Module surface over the native weights
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """HF-layout tensors (the reference checkpoint's keys; views / re-layouts of the live device tensors)."""
+        if self._native is None:
+            return {} if destination is None else destination
+        from .native_weights import named_to_hf
+        out = {prefix + k: v for k, v in named_to_hf(self.config, self._native.named).items()}
+        if destination is not None:
+            destination.update(out)
+            return destination
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Load HF-layout tensors IN PLACE (device pointers, ctypes structs and captured graphs stay valid)."""
+        get = lambda name: state_dict[name]  # noqa: E731
+        if self._native is None:
+            self._pending = get
+            return nn.modules.module._IncompatibleKeys([], [])
+        fresh = load_hf(self.config, get, self._native.device)
+        for dst, src in zip(self._native._keep, fresh._keep):
+            if dst.shape != src.shape or dst.dtype != src.dtype:
+                raise _lib.NativeError(f"load_state_dict: tensor mismatch {tuple(dst.shape)} vs {tuple(src.shape)}")
+            dst.copy_(src)
+        return nn.modules.module._IncompatibleKeys([], [])
+
+    def half(self):
+        return self      # the native path computes in bf16 with fp32 accumulation whatever the caller's dtype request
+
+    float = bfloat16 = half
 
     # ------------------------------------------------------------------ construction
     @classmethod
     def from_native(cls, cfg: LeopardConfig, native: NativeWeights):
         m = cls(cfg)
-        m._native, m.device = native, native.device
-        m.engine = PrefillEngine(cfg, native)
+        m._bind(native)
         return m
 
     @classmethod
@@ -243,10 +298,6 @@ class myLlavaForConditionalGeneration:
             m.dtype = torch_dtype
         return m
 
-    def eval(self):
-        self.training = False
-        return self
-
     def set_precision(self, precision: str):
         """"bf16" (default): the fast path — bf16 activations, fp32 accumulation.  "fp32": PARITY MODE for forward() without
         a cache — the fp32-equivalent arithmetic of the reference's `torch_dtype=torch.float32` evaluation (…anyres.py:373) on
@@ -257,15 +308,16 @@ class myLlavaForConditionalGeneration:
         self._precision = precision
         return self
 
-    def to(self, device):
+    def to(self, device=None, *args, **kwargs):
+        if device is None or isinstance(device, torch.dtype):      # .to(dtype): the native path's arithmetic type is fixed
+            return self
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.NativeError("myLlavaForConditionalGeneration.to(): only CUDA devices are supported (no CPU fallback)")
         if self._native is None or self._native.device != device:
             if self._pending is None:
                 raise _lib.NativeError("no weights to move: construct with from_pretrained/from_state_dict/from_native")
-            self._native = load_hf(self.config, self._pending, device)
-            self.engine = PrefillEngine(self.config, self._native)
+            self._bind(load_hf(self.config, self._pending, device))
         self.device = device
         return self
 
@@ -349,7 +401,7 @@ class myLlavaForConditionalGeneration:
                 raise NotImplementedError("padded prompts are outside the reference's usage (…anyres.py:443-446)")
             pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
             ids = input_ids.to(eng.device, non_blocking=True)
-            if getattr(self, "_precision", "bf16") == "fp32" and not use_cache:
+            if self._precision == "fp32" and not use_cache:
                 from .parity import ParityForward
                 logits = ParityForward(eng).prefill_logits(ids[0], None if pix is None else pix.float())[None]
                 if return_dict is False:
@@ -371,8 +423,6 @@ class myLlavaForConditionalGeneration:
         if return_dict is False:
             return tuple(v for v in (loss, logits, past) if v is not None)
         return LlavaCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past)
-
-    __call__ = forward
 
     # ------------------------------------------------------------------ generate (greedy, as the reference calls it)
     @torch.no_grad()

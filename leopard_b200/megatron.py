@@ -85,16 +85,25 @@ def configure_provider(cfg: Optional[LeopardConfig] = None, hf_getter: Optional[
     _provider_state.update(cfg=cfg, getter=hf_getter, device=device)
 
 
-class GPTModel:
-    """Native stand-in for megatron_patch.model.llava.gpt_model.GPTModel: forward (logits / per-token loss) here; the training
-    iteration runs through `train_step` + leopard_b200.train.SFTTrainer on this model's engine (no autograd graph)."""
+class GPTModel(torch.nn.Module):
+    """Native stand-in for megatron_patch.model.llava.gpt_model.GPTModel (a MegatronModule, gpt_model.py:54): forward (logits /
+    per-token loss) here; the training iteration runs through `train_step` + leopard_b200.train.SFTTrainer on this model's engine
+    (no autograd graph).  MegatronModule surface kept: `config`, `pre_process` / `post_process`,
+    `share_embeddings_and_output_weights` (False: Leopard unties the lm_head), `set_input_tensor`,
+    `state_dict_for_save_checkpoint`, `load_state_dict`, and — being an nn.Module — `parameters()` over the kernel-layout
+    weights, `.cuda()`, `.eval()` / `.train()`, so Megatron's wrappers can hold it."""
 
     def __init__(self, cfg: LeopardConfig, native: NativeWeights, pre_process=True, post_process=True,
                  hf_getter: Optional[Callable] = None):
+        super().__init__()
         if not (pre_process and post_process):
             raise NotImplementedError("pipeline parallel stages are out of scope (the reference runs PP = 1)")
-        self.cfg = cfg
+        self.cfg = self.config = cfg
+        self.pre_process, self.post_process = pre_process, post_process
+        self.share_embeddings_and_output_weights = False
         self.engine = PrefillEngine(cfg, native)
+        from .hf import _NativeParameters
+        self.native = _NativeParameters(native.named)
         self.input_tensor = None
         self._hf_getter = hf_getter   # source tensors (HF layout) for state_dict_for_save_checkpoint
 
@@ -116,7 +125,7 @@ class GPTModel:
 
         return {_LM_KEY: nest_language_model_state(hf_to_megatron(self.cfg, get))}
 
-    def load_state_dict(self, state_dict, strict=True):
+    def load_state_dict(self, state_dict, strict=True, assign=False):
         """Customized load like the reference's (accepts the nested checkpoint entry with or without the
         'language_model' level): converts the Megatron layouts back and rebuilds the native weights on the device."""
         hf = megatron_to_hf(self.cfg, flatten_language_model_state(state_dict))
@@ -177,8 +186,6 @@ class GPTModel:
         from . import ops
         return ops.cross_entropy(logits, labels.reshape(-1).clamp(min=-1)).view(b, s)
 
-    __call__ = forward
-
 
 def loss_func(loss_mask: torch.Tensor, labels: torch.Tensor, output_tensor: torch.Tensor):
     """Same signature and arithmetic as the script's `loss_func` (examples/llava/pretrain_megatron_llava.py:101-121, bound
@@ -225,17 +232,52 @@ def mm_collate_fn(batch):
     return out
 
 
+class _BatchRecorder:
+    """What `forward_step_func` sees as the model: records the arguments of `model(tokens, position_ids, attention_mask,
+    images=images)` (pretrain_megatron_llava.py:157-158) instead of computing — the fused native step does the arithmetic."""
+
+    def __init__(self, real):
+        self._real, self.call = real, None
+
+    def __call__(self, tokens, position_ids=None, attention_mask=None, **kw):
+        self.call = dict(tokens=tokens, position_ids=position_ids, attention_mask=attention_mask, **kw)
+        return None
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+def _batch_from_forward_step(forward_step_func, data_iterator, model):
+    """Run the script's own `forward_step(data_iterator, model)` (get_batch incl. its broadcast / masks, :124-160) against a
+    recorder and read the micro-batch back: tokens and images from the model call, loss mask and labels from the returned
+    `partial(loss_func, loss_mask, labels)` (:160)."""
+    rec = _BatchRecorder(model[0] if isinstance(model, (list, tuple)) else model)
+    out = forward_step_func(data_iterator, rec)
+    loss_closure = out[1] if isinstance(out, tuple) else None
+    if rec.call is None or loss_closure is None or not hasattr(loss_closure, "args") or len(loss_closure.args) < 2:
+        raise _lib.NativeError("train_step: forward_step_func must call model(tokens, position_ids, attention_mask, images=...) and "
+                               "return (output, partial(loss_func, loss_mask, labels)) as examples/llava/pretrain_megatron_llava.py does")
+    loss_mask, labels = loss_closure.args[0], loss_closure.args[1]
+    return rec.call["tokens"].long(), labels.long(), loss_mask.float(), rec.call.get("images")
+
+
 def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_scheduler=None, config=None,
                num_microbatches: int = 1):
     """Megatron's `train_step` (Megatron-LM-240424/megatron/training/training.py:544-607) for this path: same signature,
     same return tuple (loss_reduced, skipped_iter, grad_norm, num_zeros_in_grad).  `optimizer` is a
     leopard_b200.train.SFTTrainer built on `model[0].engine`: zero-grad, forward, loss_func, backward, the data-parallel
-    reduce, clipping and the Adam update all happen inside its `step`, on native kernels, so `forward_step_func` is not
-    called; the batch is read with get_batch's keys (:52-99): 'input_ids', 'labels', 'weights' (the loss mask), 'image'.
+    reduce, clipping and the Adam update all happen inside its `step`, on native kernels.  `forward_step_func` — the script's
+    own forward_step — IS called, once per micro-batch, against a recorder in place of the model: its get_batch supplies the
+    batch (tokens / images from the model call, loss mask and labels from the returned loss closure); the arithmetic it would
+    have triggered through autograd runs in the fused step instead.  With forward_step_func=None the batch is read directly
+    with get_batch's keys (:52-99): 'input_ids', 'labels', 'weights' (the loss mask), 'image'.
     The learning-rate schedule lives in the trainer (cosine with warm-up, as the launch script configures);
     `num_microbatches` = Megatron's get_num_microbatches() (global batch / (micro batch x data-parallel size))."""
     micro = []
     for _ in range(num_microbatches):        # get_num_microbatches() batches per iteration, gradients accumulated
+        if forward_step_func is not None:
+            micro.append(_batch_from_forward_step(forward_step_func, data_iterator, model))
+            continue
         data = next(data_iterator)
         while data is None:                  # get_batch :59-62 skips empty collates
             data = next(data_iterator)

@@ -182,10 +182,12 @@ class TPDecoder:
         cs, sn = ops.rope_table(torch.arange(S, dtype=torch.int32, device=dev), w["inv_freq"])
         x = x_local
         for L in w["layers"]:
-            h = ops.rmsnorm(x, L["ln1_g"], d.eps)                                  # sequence-parallel region: local rows only
+            # sequence-parallel region: RMSNorm on the local rows only
             if self.comm == "fused":
-                qkv = self.fused.allgather_gemm(h, L["qkv_w"])                       # all-gather inside the GEMM kernel
+                ops.rmsnorm(x, L["ln1_g"], d.eps, out=self.fused.local_rows())
+                qkv = self.fused.allgather_gemm(L["qkv_w"])                          # all-gather inside the GEMM kernel
             else:
+                h = ops.rmsnorm(x, L["ln1_g"], d.eps)
                 qkv = ops.gemm(self._all_gather_rows(h), L["qkv_w"])                # [S, (hq + 2 hk) * hd]
             ops.rope_inplace(qkv, 0, hq + hk, hd, cs, sn)
             att = ops.attention(qkv, 1, S, hq, hk, hd, hd, 0, q_w, q_w + kv_w, True)           # [S, hq * hd]
@@ -193,19 +195,18 @@ class TPDecoder:
                 x = self.fused.gemm_reduce_scatter(att, L["o_w"], x)
             else:
                 x = self._reduce_scatter_rows(ops.gemm(att, L["o_w"]), x)
-            h = ops.rmsnorm(x, L["ln2_g"], d.eps)
             if self.comm == "fused":
-                m = self.fused.allgather_gemm(h, L["gateup_w"], act=ops.ACT_SWIGLU)
+                ops.rmsnorm(x, L["ln2_g"], d.eps, out=self.fused.local_rows())
+                m = self.fused.allgather_gemm(L["gateup_w"], act=ops.ACT_SWIGLU)
                 x = self.fused.gemm_reduce_scatter(m, L["down_w"], x)
             else:
+                h = ops.rmsnorm(x, L["ln2_g"], d.eps)
                 m = ops.gemm(self._all_gather_rows(h), L["gateup_w"], act=ops.ACT_SWIGLU)       # [S, ffn / tp]
                 x = self._reduce_scatter_rows(ops.gemm(m, L["down_w"]), x)
         # final norm on local rows; the rows needed for logits are gathered, the lm_head is vocabulary-parallel
         h = ops.rmsnorm(x, w["final_g"], d.eps)
         full = self._all_gather_rows(h)
         rows = full[-1:].contiguous() if last_only else full
-        if rows.shape[0] < 8:                                                      # GEMM rows: keep M >= 1, any M works
-            pass
         logits_local = ops.gemm(rows, w["lm_head"], out_fp32=True)                # [rows, vocab / tp]
         parts = [torch.empty_like(logits_local) for _ in range(tp)]
         dist.all_gather(parts, logits_local.contiguous(), group=self.group)

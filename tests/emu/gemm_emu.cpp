@@ -117,3 +117,41 @@ extern "C" void emu_gemm4(const void* A, long long lda, const void* W, long long
     default: run4<128, 8>(tmAh, tmB, tmC, args, ctas); break;
   }
 }
+
+
+// Tensor-parallel launches (lp_gemm_bf16_tp): ONE rank's kernel with the peers' buffers living in this process.  mode 1 = all-gather
+// (peer_A[r] = rank r's copy of the A buffer, signal words pre-set by the test = the peers are ready), mode 2 = reduce-scatter
+// (stage[r] = rank r's staging [tp, seg_rows, ldc]).  Argument preparation as in lp_gemm_bf16_tp.
+extern "C" void emu_gemm_tp(void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K, int act,
+                            int tp, int rank, int mode, void* const* peer_A, void* const* stage, unsigned* counter,
+                            unsigned* signal_local, unsigned* const* signal_peer, unsigned epoch, int ctas) {
+  constexpr int BN = 256;
+  GemmArgs args = {};
+  args.M = M; args.N = N; args.K = K; args.C = C; args.ldc = ldc; args.act = act;
+  args.tp_size = tp; args.tp_rank = rank; args.seg_rows = M / tp;
+  args.seg_m_blk = (args.seg_rows + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  args.num_m_blk = tp * args.seg_m_blk;
+  args.num_n_blk = (N + BN - 1) / BN;
+  args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+  args.group_m = args.seg_m_blk;
+  args.epoch = epoch;
+  const int n_out = act == LP_ACT_SWIGLU ? N / 2 : N;
+  GemmSegMaps segs;
+  for (int r = 0; r < 8; ++r) {
+    const int rr = r < tp ? r : 0;
+    if (mode == 1) {
+      args.ag_src[r] = peer_A[rr];
+      args.ag_wait[r] = signal_local + rr;
+      args.ag_post[r] = signal_peer[rr] + rank;
+      segs.m[r] = tmap2(reinterpret_cast<bf16*>(C) + (size_t)rr * args.seg_rows * ldc, n_out, args.seg_rows, ldc, 32, 32, 2, 64);
+    } else {
+      args.rs_post[r] = signal_peer[rr] + 8 + rank;
+      segs.m[r] = tmap2(reinterpret_cast<bf16*>(stage[rr]) + (size_t)rank * args.seg_rows * ldc, n_out, args.seg_rows, ldc, 32, 32, 2, 64);
+    }
+  }
+  if (mode == 1) { args.ag_counter = counter; args.ag_dst = A; args.ag_ld = lda; args.ag_cols = K; }
+  else args.rs_counter = counter;
+  CUtensorMap tmA = tmap2(A, K, M, lda, GEMM_BK, GEMM_BM, 2, 128);
+  CUtensorMap tmB = tmap2(W, K, N, ldw, GEMM_BK, BN / 2, 2, 128);
+  emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_tp_kernel<BN, 6, true>(tmA, tmB, segs, args); });
+}

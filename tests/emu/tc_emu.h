@@ -150,6 +150,11 @@ inline void mbar_init(uint64_t* bar, uint32_t count) {
 inline void fence_barrier_init() {}
 inline void fence_proxy_async_smem() {}
 inline void fence_proxy_async_all() {}
+#ifndef EMU_HOST_ATOMICS       // host_emu.h (never included together with this header) has its own
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+#endif
 inline unsigned ld_acquire_sys(const unsigned* p) { return std::atomic_ref<unsigned>(*const_cast<unsigned*>(p)).load(); }
 inline unsigned ld_acquire_gpu(const unsigned* p) { return ld_acquire_sys(p); }
 inline void st_release_sys(unsigned* p, unsigned v) { std::atomic_ref<unsigned>(*p).store(v); }

@@ -25,16 +25,30 @@ def test_header_symbols_are_exported_and_bound(native_lib):
     assert native_lib.lp_abi_version() == 3
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors have the size and field offsets a C compiler gives the header's structs (gcc on include/leopard_b200.h)."""
+    import subprocess
     from leopard_b200 import _lib
-    # sizes implied by the C declarations (LP64): ints are 4 bytes, pointers 8
-    assert C.sizeof(_lib.VitDims) == 11 * 4
-    assert C.sizeof(_lib.VitLayerWeights) == 12 * 8
-    assert C.sizeof(_lib.VitWeights) == 6 * 8
-    assert C.sizeof(_lib.ProjWeights) == 4 * 8 + 8
-    assert C.sizeof(_lib.DecDims) == 8 * 4
-    assert C.sizeof(_lib.DecLayerWeights) == 6 * 8
-    assert C.sizeof(_lib.DecWeights) == 4 * 8
+    pairs = {"lp_vit_dims": _lib.VitDims, "lp_vit_layer_weights": _lib.VitLayerWeights, "lp_vit_weights": _lib.VitWeights,
+             "lp_proj_weights": _lib.ProjWeights, "lp_dec_dims": _lib.DecDims, "lp_dec_layer_weights": _lib.DecLayerWeights,
+             "lp_dec_weights": _lib.DecWeights, "lp_gemm_desc": _lib.GemmDesc, "lp_tp_desc": _lib.TpDesc,
+             "lp_profile_record": _lib.ProfileRecord}
+    lines = []
+    for cname, ct in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "leopard_b200.h"\nint main(void) {\n' + "\n".join(lines)
+                   + "\nreturn 0; }\n")
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c11", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
 
 
 def test_argument_errors_are_status_codes(native_lib):
@@ -54,7 +68,8 @@ def test_workspace_queries_are_host_only(native_lib):
     vd = _lib.VitDims(v.layers, v.hidden, v.ffn, v.heads, v.head_dim, HEAD_STRIDE, v.grid, v.tokens, v.patch_k,
                       PATCH_K_PAD, v.eps)
     n28 = native_lib.lp_vit_workspace_bytes(C.byref(vd), 28)
-    assert 28 * 676 * (592 + 1152 * 3 + 3840 + 4304) * 2 <= n28 < 1.01 * 28 * 676 * (592 + 1152 * 3 + 3840 + 4304) * 2 + 4096
+    base = 28 * 676 * (592 + 1152 * 3 + 3840 + 4304) * 2          # activations; + two row-statistics buffers (32 float2 per row)
+    assert base <= n28 < 1.01 * (base + 2 * 28 * 676 * 32 * 8) + 4096
     dd = _lib.DecDims(d.layers, d.hidden, d.ffn, d.heads, d.kv_heads, d.head_dim, d.vocab, d.eps)
     n = native_lib.lp_decoder_workspace_bytes(C.byref(dd), 4796, 1)
     assert n >= 4796 * (4096 * 2 + 6144 + 14336) * 2

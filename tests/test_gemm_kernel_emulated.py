@@ -200,3 +200,68 @@ def test_rope_epilogue_rotates_the_leading_heads(emu, pair):
     _gemm_ex(emu, x, w, out, bn=256, pair=pair, ctas=2, fx=fx)
     err = float((out.float() - want).abs().max() / want.abs().max())
     assert err < 8e-3, err
+
+
+# ---- tensor-parallel launches (lp_gemm_bf16_tp): one rank's kernel, the peers' buffers in the same process ----------------------
+def _ptr_array(tensors):
+    arr = (C.c_void_p * 8)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+@pytest.mark.parametrize("tp,rank,act", [(2, 1, 0), (2, 0, 3), (4, 2, 0)])
+def test_allgather_gemm_pulls_peer_rows_and_clips_segments(emu, tp, rank, act):
+    """All-gather prologue + segmented rows: only the rank's own rows are valid in its A buffer on entry; the kernel copies the
+    peers' segments from their buffers, multiplies own-segment tiles first, stores through per-segment maps (no row of another
+    segment is ever written from a stale A tile) and posts its readiness to the peers."""
+    sl, K, N = 300, 136, 512                                   # 300 rows per rank: tiles straddle nothing, last tile is ragged
+    M = tp * sl
+    g = torch.Generator().manual_seed(tp * 10 + rank)
+    full = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    bufs = []
+    for r in range(tp):                                        # rank r's buffer: its own rows valid, the rest poison
+        b = torch.full((M, K), float("nan"), dtype=BF)
+        b[r * sl:(r + 1) * sl] = full[r * sl:(r + 1) * sl]
+        bufs.append(b)
+    n_out = N // 2 if act == 3 else N
+    out = torch.full((M, n_out), float("nan"), dtype=BF)
+    counter = torch.zeros(1, dtype=torch.int32)
+    epoch = 7
+    sig_local = torch.full((16,), epoch, dtype=torch.int32)     # every peer has announced its rows
+    sig_peers = [torch.zeros(16, dtype=torch.int32) for _ in range(tp)]
+    ctas = 2          # ONE pair: the emulator runs pairs one after another, and the prologue's counter needs every CTA of the grid
+    emu.emu_gemm_tp(P(bufs[rank]), LL(K), P(w), LL(K), P(out), LL(n_out), M, N, K, act, tp, rank, 1, _ptr_array(bufs), None,
+                    P(counter), P(sig_local), _ptr_array(sig_peers), epoch, ctas)
+    want = ref.gemm(full, w, act=act)
+    assert torch.equal(bufs[rank], full)                       # gathered
+    assert not bool(torch.isnan(out.float()).any())
+    assert float((out.float() - want.float()).abs().max() / want.float().abs().max()) < 8e-3
+    assert int(counter) == ctas
+    for r in range(tp):
+        assert int(sig_peers[r][rank]) == (epoch if r != rank else 0)
+
+
+@pytest.mark.parametrize("tp,rank", [(2, 0), (4, 3)])
+def test_gemm_reduce_scatter_stores_partials_into_the_owners_slots(emu, tp, rank):
+    sl, K, N = 300, 200, 512
+    M = tp * sl
+    g = torch.Generator().manual_seed(tp + rank)
+    a = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    stages = [torch.full((tp, sl, N), float("nan"), dtype=BF) for _ in range(tp)]
+    counter = torch.zeros(1, dtype=torch.int32)
+    sig_local = torch.zeros(16, dtype=torch.int32)
+    sig_peers = [torch.zeros(16, dtype=torch.int32) for _ in range(tp)]
+    epoch, ctas = 3, 4
+    emu.emu_gemm_tp(P(a), LL(K), P(w), LL(K), None, LL(N), M, N, K, 0, tp, rank, 2, None, _ptr_array(stages), P(counter), P(sig_local),
+                    _ptr_array(sig_peers), epoch, ctas)
+    want = ref.gemm(a, w)
+    for r in range(tp):                                        # owner r received this rank's partial sums for ITS rows in slot [rank]
+        got = stages[r][rank]
+        assert float((got.float() - want[r * sl:(r + 1) * sl].float()).abs().max() / want.float().abs().max()) < 8e-3
+        others = [s for s in range(tp) if s != rank]
+        assert bool(torch.isnan(stages[r][others].float()).all())              # nothing else was touched
+        assert int(sig_peers[r][8 + rank]) == epoch                            # completion posted to every owner
+    assert int(counter) == ctas
