@@ -124,6 +124,23 @@ int lp_tp_reduce(const lp_tp_desc* tp, const void* stage, long long ld, const vo
  *     opt-in, verified under the CPU emulator only so far. */
 int lp_gemm_set_pair_mode(int enable);
 
+/* Stream-K tail of lp_gemm_bf16 / lp_gemm_bf16_ex (large problems whose last wave of tiles would leave most SMs idle, e.g. the
+ * decoder's N = 4096 projections at S = 4796: 304 tiles on 74 CTA pairs): the k loops of the last 1 + fraction waves of tiles are
+ * cut into equal ranges, one per CTA pair; a tile shared by two pairs is started by one (fp32 accumulator dumped to the workspace)
+ * and finished by the next (accumulator loaded back into TMEM, k loop continued) — the summation order of every output element is
+ * that of the unsplit kernel, results are bit-identical with it on or off.  The library never allocates: the caller provides
+ * `ws` = ZERO-FILLED device memory of lp_gemm_streamk_workspace_bytes() bytes, 256-byte aligned, used by one stream at a time and
+ * valid until replaced (NULL = off, the default).  lp_gemm_set_streamk(0/1) switches it without dropping the workspace and
+ * returns the previous setting. */
+size_t lp_gemm_streamk_workspace_bytes(void);
+int lp_gemm_set_streamk_workspace(void* ws, size_t bytes);
+int lp_gemm_set_streamk(int enable);
+/* Residual launches (C = A W^T + bias + residual, bf16, the o / down / out-proj / fc2 GEMMs of the layer loops) in CTA-pair mode:
+ * 1 (default) = the residual tile is fetched by TMA into a per-warp ring one 32-column chunk ahead, added in place and stored
+ * from the same buffer; 0 = the earlier register path (coalesced loads handed through the staging tile).  Same arithmetic:
+ * results are bit-identical.  Returns the previous setting. */
+int lp_gemm_set_tma_residual(int enable);
+
 /* Launch the hot prefill kernels (GEMM, attention v3, norms, RoPE) with programmatic dependent launch: the next kernel's
  * CTAs are scheduled as SMs free up and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the
  * previous kernel drains; each kernel executes griddepcontrol.wait before its first dependent global access.  Results

@@ -87,6 +87,10 @@ _SIGS = {
     "lp_row_stats": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
     "lp_model_set_fused_norm": (_i, [_i]),
     "lp_gemm_set_pair_mode": (_i, [_i]),
+    "lp_gemm_streamk_workspace_bytes": (_sz, []),
+    "lp_gemm_set_streamk_workspace": (_i, [_vp, _sz]),
+    "lp_gemm_set_streamk": (_i, [_i]),
+    "lp_gemm_set_tma_residual": (_i, [_i]),
     "lp_gemm_bf16_tp": (_i, [C.POINTER(GemmDesc), C.POINTER(TpDesc), _vp]),
     "lp_tp_reduce": (_i, [C.POINTER(TpDesc), _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp]),
     "lp_parity_split": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _vp]),
@@ -187,6 +191,30 @@ def lib():
             L.lp_set_prefill_pdl(int(os.environ["LEOPARD_PREFILL_PDL"]))
         _lib = L
     return _lib
+
+
+_streamk_ws = None   # the device buffer handed to lp_gemm_set_streamk_workspace (kept alive here)
+
+
+def ensure_streamk_workspace(device=None):
+    """Give the GEMM its stream-K workspace (include/leopard_b200.h: lp_gemm_set_streamk_workspace) on the process's GPU — one
+    process per GPU, one compute stream, as everywhere in this package.  LEOPARD_STREAMK=0 leaves the stream-K tail off."""
+    global _streamk_ws
+    import os
+    import torch
+    L = lib()
+    if os.environ.get("LEOPARD_STREAMK", "1") == "0" or not torch.cuda.is_available():
+        return None
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if _streamk_ws is not None:
+        if _streamk_ws.device != dev:      # a second device in one process: the single workspace cannot serve both
+            check(L.lp_gemm_set_streamk_workspace(None, 0), "lp_gemm_set_streamk_workspace")
+        return _streamk_ws
+    with torch.cuda.device(dev):
+        ws = torch.zeros(int(L.lp_gemm_streamk_workspace_bytes()), dtype=torch.uint8, device=dev)
+    check(L.lp_gemm_set_streamk_workspace(C.c_void_p(ws.data_ptr()), ws.numel()), "lp_gemm_set_streamk_workspace")
+    _streamk_ws = ws
+    return ws
 
 
 def check(rc: int, what: str):

@@ -22,6 +22,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// 16-byte shared-memory accesses by shared-window address (pointers derived from the manually aligned dynamic buffer are generic
+// to the compiler, which would otherwise emit generic LD / ST)
+__device__ __forceinline__ uint4 lds_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u4(void* p, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -105,6 +115,21 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 16-byte global accesses that bypass L1 (data produced / consumed by another SM inside the same kernel: stream-K partial sums)
+__device__ __forceinline__ uint4 ld_cg_u4(const float* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_cg_u4(float* p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // bounded spin (a peer that never arrives traps this kernel instead of hanging the GPU)
 __device__ __forceinline__ void spin_until_sys(const unsigned* p, unsigned target) {

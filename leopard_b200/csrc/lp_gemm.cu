@@ -31,10 +31,16 @@ namespace lp {
 // per SM relieves the per-SM L2->SMEM bandwidth (the 1-CTA kernel runs at ~75 % of it) and deepens the ring.
 // TP = true: tensor-parallel launch (lp_gemm_bf16_tp) — segmented rows, output through per-segment tensor maps `segC`, optional
 // all-gather prologue and reduce-scatter signalling (see GemmArgs)
-template <int BN, int STAGES, bool CTA2, bool TP>
+// TMARES = true: the residual launch of the layer loops (bf16 output, residual rows == output rows, no SwiGLU / RoPE): the residual
+// tile travels by TMA (map tmR) into a 3-deep per-warp ring one chunk ahead of its use, is added in place and leaves from the same
+// buffer — no residual registers, no global-load latency in the epilogue's dependency chain
+// RES: 0 = the kernel has no residual path at all (leaner epilogue for the qkv / fc1 / gate-up launches), 1 = residual through
+// registers (any layout: fp32 output, row-modulo residual = position embedding, one CTA per tile), 2 = TMARES
+template <int BN, int STAGES, bool CTA2, bool TP, int RES>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                                          const CUtensorMap* segC, const GemmArgs& args) {
-  using L = GemmSmem<BN, STAGES, CTA2>;
+                                          const CUtensorMap* segC, const CUtensorMap& tmR, const GemmArgs& args) {
+  constexpr bool TMARES = RES == 2;
+  using L = GemmSmem<BN, STAGES, CTA2, TMARES ? 3 : 1>;
   constexpr int BMT = CTA2 ? 2 * GEMM_BM : GEMM_BM;  // rows per work unit
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -48,6 +54,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tpre_bar = tempty_bar + 3;   // stream-K: the END item's accumulator has been loaded back into TMEM
   float* bias_smem = reinterpret_cast<float*>(smem + L::BIAS_OFF);
   float* colsum_smem = reinterpret_cast<float*>(smem + L::COLSUM_OFF);
 
@@ -66,6 +73,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CTA2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
+    mbar_init(tpre_bar, CTA2 ? 16 : 8);
+    if (TMARES) {
+      tma_prefetch_desc(&tmR);
+      for (int i = 0; i < 24; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + L::RES_BAR_OFF) + i, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -81,7 +93,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   pdl_launch_dependents();
   pdl_wait();
 
-  const int num_tiles = args.num_m_blk * args.num_n_blk;
+  const GemmSchedule sch = gemm_schedule(args, unit, n_units);   // this unit's work items (whole tiles + stream-K pieces)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -89,9 +101,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       int stage = 0;
       uint32_t phase = 0;
       bool gathered = false;
-      for (int tile = unit; tile < num_tiles; tile += n_units) {
+      for (int it = 0; it < sch.n_items; ++it) {
+        const GemmItem w = gemm_item(args, sch, it);
         int m_blk, n_blk, seg, row_limit;
-        tile_coords(args, tile, m_blk, n_blk);
+        tile_coords(args, w.tile, m_blk, n_blk);
         const int a_row = tile_row0(args, m_blk, BMT, seg, row_limit) + (int)cta_rank * GEMM_BM;
         if (TP && args.ag_counter != nullptr && seg != args.tp_rank && !gathered) {
           // rows of other ranks: wait until every CTA's epilogue warps have finished copying them in (all-gather prologue)
@@ -102,7 +115,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         // ragged last column block: the MMA runs with N = n_rt (multiple of 32), so a pair splits n_rt, not BN
         const int n_rt = min(BN, ((args.N - n_blk * BN) + 31) & ~31);
         const int b_row = n_blk * BN + (CTA2 ? (int)cta_rank * (n_rt / 2) : 0);
-        for (int kb = 0; kb < args.num_k_blk; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           // (an explicit cp.async.bulk.prefetch.tensor.L2 of the k-block 8 ahead was measured: every CTA of a
           //  row-block group re-requests the same W tile, and the doubled TMA/L2 request rate cost 10-30 %: removed)
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -130,15 +143,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = unit; tile < num_tiles; tile += n_units) {
+      for (int it = 0; it < sch.n_items; ++it) {
+        const GemmItem w = gemm_item(args, sch, it);
         int m_blk_unused, n_blk;
-        tile_coords(args, tile, m_blk_unused, n_blk);
+        tile_coords(args, w.tile, m_blk_unused, n_blk);
         // the last column block of a ragged N issues narrower MMAs (N = valid columns rounded up to 32)
         const uint32_t idesc = umma_idesc_bf16(BMT, min(BN, ((args.N - n_blk * BN) + 31) & ~31), 0, 0);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
+        const bool resume = w.kind == GEMM_ITEM_END;   // the accumulator continues another unit's partial sums
+        if (resume) mbar_wait(tpre_bar, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < args.num_k_blk; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -146,8 +162,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           const uint64_t bdesc = umma_desc_sw128(a_addr + L::A_BYTES, 0, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {  // +32 B per K=16 step inside the 128 B swizzle row
-            if (CTA2) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t acc = (resume || kb > w.kb0 || k > 0) ? 1u : 0u;
+            if (CTA2) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
           }
           // smem slot reusable once these MMAs retire (in both CTAs of a pair)
           if (CTA2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -208,9 +225,100 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       epi_named_barrier();
       if (et == 0) atomicAdd(args.ag_counter, 1u);
     }
-    for (int tile = unit; tile < num_tiles; tile += n_units) {
+    const int sk_c0 = wg == 0 ? 0 : (NC + 1) / 2, sk_c1 = wg == 0 ? (NC + 1) / 2 : NC;   // chunk split of the stream-K dump / reload
+    const int sk_slot = unit * (CTA2 ? 2 : 1) + (int)cta_rank;
+    bool sk_reloaded = false;
+    int stat_row = -1;
+    float rs = 1.f, nmu = 0.f;
+    // bias / layer-norm column sums of a tile sit in shared memory (double-buffered with the accumulator stage); the values of item
+    // it + 1 are fetched into a register while item it is processed, so their global-load latency is off the epilogue's critical path
+    const bool col_thread = et < BN;
+    auto fetch_cols = [&](const GemmItem& wi, float& bv, float& cv) {
+      int mb, nb;
+      tile_coords(args, wi.tile, mb, nb);
+      const int col = nb * BN + et;
+      const bool ok = col_thread && col < args.N;
+      bv = (ok && args.bias) ? args.bias[col] : 0.f;
+      cv = (ok && args.norm_mode == LP_NORM_LAYER_) ? args.colsum[col] : 0.f;
+    };
+    {
+      const int first = sch.has_start ? 1 : 0;          // the START item has no epilogue
+      if (first < sch.n_items && col_thread) {
+        float bv, cv;
+        fetch_cols(gemm_item(args, sch, first), bv, cv);
+        bias_smem[(first & 1) * BN + et] = bv;
+        colsum_smem[(first & 1) * BN + et] = cv;
+      }
+    }
+    // TMARES: residual ring of this warp (3 x 2 KiB) and its barriers; rg counts the chunks this warp has sent through it
+    uint8_t* ring = smem + L::STAGE_OUT_OFF + (warp - 2) * (TMARES ? 3 : 1) * 2048;
+    uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + L::RES_BAR_OFF) + (warp - 2) * 3;
+    uint32_t rg = 0;
+    auto sk_reload = [&]() {
+        // ---- stream-K END item (always the last one): the unit before this one computed k-blocks [0, kb0) of the tile and dumped its
+        // accumulator; load it into the TMEM stage the END item will use (free: its previous user's epilogue is behind us) while
+        // the MMA warp still works on the item before it
+        sk_reloaded = true;
+        if (et == 0) {
+          spin_until_gpu(args.sk_flags + sk_slot - (CTA2 ? 2 : 1), 1u);
+          st_relaxed_gpu(args.sk_flags + sk_slot - (CTA2 ? 2 : 1), 0u);   // consumed: ready for the next launch
+        }
+        epi_named_barrier();
+        const float* src = args.sk_ws + (size_t)(sk_slot - (CTA2 ? 2 : 1)) * (BN * GEMM_BM) + (size_t)(lg * 32 + lane) * 4;
+        const uint32_t tdst = tmem_base + ((uint32_t)(lg * 32) << 16) + ((sch.n_items - 1) & 1) * BN;
+#pragma unroll 1
+        for (int c = sk_c0; c < sk_c1; ++c) {
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = ld_cg_u4(src + (size_t)(c * 8 + j) * (GEMM_BM * 4));
+            r[4 * j] = u.x; r[4 * j + 1] = u.y; r[4 * j + 2] = u.z; r[4 * j + 3] = u.w;
+          }
+          LP_TMEM_ST_32(r, tdst + c * 32);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2 && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(tpre_bar), 0));
+          else mbar_arrive(tpre_bar);
+        }
+          };
+    for (int it = 0; it < sch.n_items; ++it) {
+      const GemmItem w = gemm_item(args, sch, it);
+      if (sch.has_end && !sk_reloaded && it + 2 >= sch.n_items && w.kind != GEMM_ITEM_START) sk_reload();
+      if (w.kind == GEMM_ITEM_START) {
+        // ---- stream-K START item (always the first one): k-blocks [0, kb1) only; the raw fp32 accumulator goes to this unit's slot
+        // of the workspace ([chunk][4-column group][row][4]: every warp store covers 512 contiguous bytes) for the next unit
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        float* dst = args.sk_ws + (size_t)sk_slot * (BN * GEMM_BM) + (size_t)(lg * 32 + lane) * 4;
+        const uint32_t tsrc = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+#pragma unroll 1
+        for (int c = sk_c0; c < sk_c1; ++c) {
+          uint32_t r[32];
+          LP_TMEM_LD_32(r, tsrc + c * 32);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_cg_u4(dst + (size_t)(c * 8 + j) * (GEMM_BM * 4), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2 && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+          else mbar_arrive(&tempty_bar[as]);
+        }
+        __threadfence();
+        epi_named_barrier();
+        if (et == 0) st_release_gpu(args.sk_flags + sk_slot, 1u);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+        if (sch.has_end && !sk_reloaded && it + 2 >= sch.n_items) sk_reload();   // [START, END] only: own dump first (no chain of waits)
+        continue;
+      }
       int m_blk, n_blk, seg, row_limit;
-      tile_coords(args, tile, m_blk, n_blk);
+      tile_coords(args, w.tile, m_blk, n_blk);
       const int m0 = tile_row0(args, m_blk, BMT, seg, row_limit) + (int)cta_rank * GEMM_BM, n0 = n_blk * BN;
       // tensor-parallel launches store through the segment's own map (rows clipped at the segment end; a reduce-scatter
       // launch's maps point at the owner rank's staging memory), with row coordinates relative to the segment
@@ -218,25 +326,37 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const int st_shift = TP ? seg * args.seg_rows : 0;
       float* bs = bias_smem + as * BN;
       float* cs = colsum_smem + as * BN;
-      if (args.bias) {
-        for (int i = et; i < BN; i += GEMM_EPI_THREADS) bs[i] = (n0 + i < args.N) ? args.bias[n0 + i] : 0.f;
-      }
-      if (args.norm_mode == LP_NORM_LAYER_) {
-        for (int i = et; i < BN; i += GEMM_EPI_THREADS) cs[i] = (n0 + i < args.N) ? args.colsum[n0 + i] : 0.f;
-      }
       const int row = m0 + lg * 32 + lane;
       const bool row_ok = row < row_limit;
-      // row statistics of the A operand are fetched while the tile's MMAs are still running
-      float rs, nmu;
-      row_norm_coeffs(args, row, row_ok, rs, nmu);
-      epi_named_barrier();
+      // row statistics of the A operand are fetched while the tile's MMAs are still running (and kept while the unit stays in
+      // the same row block, which is every tile when A is L2-resident and the raster walks the column blocks of one row block)
+      if (row != stat_row) {
+        row_norm_coeffs(args, row, row_ok, rs, nmu);
+        stat_row = row;
+      }
+      const int row_base = m0 + lg * 32;
+      const int c_begin_n = wg == 0 ? 0 : (NC + 1) / 2, c_end_n = wg == 0 ? (NC + 1) / 2 : NC;   // this warp's 32-column chunks
+      auto res_issue = [&](uint32_t g, int col0) {      // lane 0: residual tile of chunk g -> ring buffer g % 3
+        mbar_arrive_expect_tx(&rbar[g % 3], 2048);
+        tma_load_2d(ring + (g % 3) * 2048, &tmR, &rbar[g % 3], col0, row_base);
+      };
+      if (TMARES && lane == 0) {
+        // the first two residual chunks of the tile are requested before the accumulator is even complete; buffers g % 3 and
+        // (g + 1) % 3 were last read by the stores of chunks g - 3 and g - 2: at most the newest store may still be reading
+        tma_store_wait_read<1>();
+        if (n0 + c_begin_n * 32 < args.N) res_issue(rg, n0 + c_begin_n * 32);
+        if (c_begin_n + 1 < c_end_n && n0 + (c_begin_n + 1) * 32 < args.N) res_issue(rg + 1, n0 + (c_begin_n + 1) * 32);
+      }
+      epi_named_barrier();   // bias / column sums of this item (written during the previous item) are visible
+      float nbv = 0.f, ncv = 0.f;
+      const bool prefetch_cols = it + 1 < sch.n_items;
+      if (prefetch_cols) fetch_cols(gemm_item(args, sch, it + 1), nbv, ncv);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
-      uint8_t* stage = smem + L::STAGE_OUT_OFF + (warp - 2) * 2048;
-      const int row_base = m0 + lg * 32;
-      const bool has_res = args.residual != nullptr;
+      uint8_t* stage = ring;
+      const bool has_res = RES == 1 && args.residual != nullptr;
       float2 ostat = make_float2(0.f, 0.f);
       float2* ostat_p = args.stats_out != nullptr ? &ostat : nullptr;
       if (!swiglu) {
@@ -269,6 +389,31 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             staged_store_chunk(args, tmc, stage, lo, nullptr, row_base - st_shift, n0 + (c_begin + p) * 32, lane, ostat_p);
             staged_store_chunk(args, tmc, stage, hi, nullptr, row_base - st_shift, n0 + (c_begin + p + 2) * 32, lane, ostat_p);
           }
+        } else if (TMARES) {
+          uint32_t done = 0;
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= args.N) break;
+            const uint32_t g = rg + done;
+            if (c > c_begin && lane == 0) {
+              // chunk c + 1's residual goes to the buffer chunk c - 2 was stored from: all but the newest store must have been read
+              tma_store_wait_read<1>();
+              if (c + 1 < c_end && col0 + 32 < args.N) res_issue(g + 1, col0 + 32);
+            }
+            uint32_t r[32];
+            LP_TMEM_LD_32(r, taddr0 + c * 32);
+            tmem_wait_ld();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            apply_row_norm(args, v, cs + c * 32, rs, nmu);
+            apply_bias_act(args, v, bs + c * 32);
+            mbar_wait(&rbar[g % 3], (g / 3) & 1);
+            ring_add_store_chunk(tmc, ring + (g % 3) * 2048, v, row_base, col0, lane, ostat_p);
+            ++done;
+          }
+          rg += done;
         } else {
         ResidualRegs rr;
         if (has_res && !args.out_fp32 && n0 + c_begin * 32 < args.N)
@@ -324,6 +469,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       }
       if (args.stats_out != nullptr && row_ok)
         args.stats_out[(long long)row * (2 * args.num_n_blk) + 2 * n_blk + wg] = ostat;
+      if (prefetch_cols && col_thread) {   // the other buffer: last read during item it - 1, which every warp has left (barrier above)
+        bias_smem[(as ^ 1) * BN + et] = nbv;
+        colsum_smem[(as ^ 1) * BN + et] = ncv;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -364,24 +513,41 @@ template <int BN, int STAGES, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
-  gemm_body<BN, STAGES, CTA2, false>(tmA, tmB, tmC, nullptr, args);
+  gemm_body<BN, STAGES, CTA2, false, 0>(tmA, tmB, tmC, nullptr, tmC, args);
+}
+
+// residual through registers (see RES above)
+template <int BN, int STAGES, bool CTA2>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_lres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
+  gemm_body<BN, STAGES, CTA2, false, 1>(tmA, tmB, tmC, nullptr, tmC, args);
+}
+
+// residual launches of the layer loops: residual tile by TMA (tmR; equal to tmC for the in-place residual stream)
+template <int BN, int STAGES, bool CTA2>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs args) {
+  gemm_body<BN, STAGES, CTA2, false, 2>(tmA, tmB, tmC, nullptr, tmR, args);
 }
 
 template <int BN, int STAGES, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ GemmSegMaps segs, const GemmArgs args) {
-  gemm_body<BN, STAGES, CTA2, true>(tmA, tmB, segs.m[0], segs.m, args);
+  gemm_body<BN, STAGES, CTA2, true, 0>(tmA, tmB, segs.m[0], segs.m, segs.m[0], args);
 }
 
 template <int BN, int STAGES, bool CTA2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& args,
                        cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, CTA2>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, CTA2>;
+  auto kern = args.residual != nullptr ? gemm_bf16_lres_kernel<BN, STAGES, CTA2> : gemm_bf16_kernel<BN, STAGES, CTA2>;
   static bool configured = false;
   if (!configured) {
-    LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    LP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    LP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_lres_kernel<BN, STAGES, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   const int tiles = args.num_m_blk * args.num_n_blk;
@@ -397,7 +563,32 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return 0;
 }
 
+// residual launches in pair mode: same structure, residual tile by TMA into a per-warp ring (gemm_bf16_res_kernel)
+template <int BN, int STAGES>
+static int launch_gemm_res(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                           const GemmArgs& args, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES, true, 3>;
+  auto kern = gemm_bf16_res_kernel<BN, STAGES, true>;
+  static bool configured = false;
+  if (!configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = args.num_m_blk * args.num_n_blk;
+  const int pairs = sm_count() / 2;
+  LP_CHECK_CUDA(launch_ex(kern, dim3(2 * (tiles < pairs ? tiles : pairs)), dim3(GEMM_THREADS), L::TOTAL, stream, 2, prefill_pdl(), tmA,
+                          tmB, tmC, tmR, args));
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int g_gemm_tma_residual = 1;  // pair-mode residual launches fetch the residual tile by TMA (0 = register path, for A/B)
 static int g_gemm_pair_mode = 1;  // 0 = one CTA per tile, 1 = CTA pairs where the problem is large enough (default)
+// stream-K tail (GemmArgs::sk_*): caller-provided workspace (flags in the first 4 KiB, fp32 partial accumulators after them)
+static void* g_sk_ws = nullptr;
+static size_t g_sk_bytes = 0;
+static int g_sk_enable = 1;
+constexpr size_t SK_FLAG_BYTES = 4096;
 
 }  // namespace lp
 
@@ -535,6 +726,35 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
     if (rc) return rc;
     return launch_gemm4(tmAh, tmB, tmC, a4, block_n, stream);
   }
+  if (g_sk_enable && g_sk_ws != nullptr && M >= 1024) {
+    // stream-K tail: when the last wave would be mostly idle, the last 1 + fraction waves of tiles are cut along K so that every
+    // unit gets the same number of k-blocks (gemm_schedule); bit-identical results (the accumulator is handed over, not re-added)
+    const int T = args.num_m_blk * args.num_n_blk;
+    const int n_units = pair ? sms / 2 : sms, per_unit = pair ? 2 : 1;
+    if (T > n_units && T % n_units != 0 && args.num_k_blk >= 8) {
+      const int waves = (T + n_units - 1) / n_units;
+      const double fill = (double)T / ((double)waves * n_units);
+      const size_t need = SK_FLAG_BYTES + (size_t)n_units * per_unit * GEMM_BM * block_n * sizeof(float);
+      if (fill < 0.97 && need <= g_sk_bytes) {
+        args.dp_tiles = (T / n_units - 1) * n_units;
+        args.sk_tiles = T - args.dp_tiles;
+        args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);
+        args.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + SK_FLAG_BYTES);
+      }
+    }
+  }
+  if (pair && g_gemm_tma_residual && residual != nullptr && res_row_mod == 0 && !out_fp32 && act != LP_ACT_SWIGLU &&
+      d->rope_heads == 0) {
+    CUtensorMap tmR;
+    rc = make_tmap_2d(&tmR, residual, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldr, 32, 32, 64);
+    if (rc) return rc;
+    switch (block_n) {
+      case 256: return launch_gemm_res<256, 5>(tmA, tmB, tmC, tmR, args, stream);
+      case 224: return launch_gemm_res<224, 5>(tmA, tmB, tmC, tmR, args, stream);
+      case 192: return launch_gemm_res<192, 6>(tmA, tmB, tmC, tmR, args, stream);
+      default: return launch_gemm_res<128, 7>(tmA, tmB, tmC, tmR, args, stream);
+    }
+  }
   if (pair) {
     switch (block_n) {
       case 256: return launch_gemm<256, 6, true>(tmA, tmB, tmC, args, stream);
@@ -640,6 +860,29 @@ extern "C" int lp_gemm_bf16_tp(const lp_gemm_desc* d, const lp_tp_desc* t, void*
                           args));
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Stream-K workspace: `ws` = zero-filled device memory of at least lp_gemm_streamk_workspace_bytes() bytes that stays valid (and is
+// used by ONE stream at a time) until it is replaced; NULL switches the stream-K tail off.
+extern "C" size_t lp_gemm_streamk_workspace_bytes(void) {
+  return SK_FLAG_BYTES + (size_t)sm_count() * GEMM_BM * 256 * sizeof(float);
+}
+extern "C" int lp_gemm_set_streamk_workspace(void* ws, size_t bytes) {
+  LP_REQUIRE(ws == nullptr || ((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && bytes > SK_FLAG_BYTES),
+             "lp_gemm_set_streamk_workspace: workspace must be 256-byte aligned and larger than %zu bytes", SK_FLAG_BYTES);
+  g_sk_ws = ws;
+  g_sk_bytes = ws ? bytes : 0;
+  return 0;
+}
+extern "C" int lp_gemm_set_tma_residual(int enable) {
+  const int old = g_gemm_tma_residual;
+  g_gemm_tma_residual = enable ? 1 : 0;
+  return old;
+}
+extern "C" int lp_gemm_set_streamk(int enable) {
+  const int old = g_sk_enable;
+  g_sk_enable = enable ? 1 : 0;
+  return old;
 }
 
 extern "C" int lp_gemm_set_pair_mode(int enable) {

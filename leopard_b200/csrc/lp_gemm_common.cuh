@@ -60,7 +60,80 @@ struct GemmArgs {
   unsigned* rs_counter;           // local, zero on entry
   unsigned* rs_post[8];           // rank r's "partials from this rank have landed" word (remote store)
   unsigned* recycle;              // a counter slot of an older call to zero for reuse
+  // ---- stream-K tail (sk_tiles > 0; lp_gemm_set_streamk_workspace): the first dp_tiles tiles (a multiple of the unit count) are
+  // scheduled one tile per unit per wave as usual; the K loops of the last sk_tiles tiles (n_units <= sk_tiles < 2 n_units) are
+  // laid end to end and cut into n_units equal ranges, so every unit ends at the same time instead of a mostly idle last wave.
+  // A tile cut between units u and u + 1 is STARTED by u (its first work item: k-blocks [0, b), raw fp32 accumulator dumped to
+  // sk_ws) and FINISHED by u + 1 (its last item: the dump is loaded back into TMEM and the k loop continues at b) — the
+  // accumulation order of every output element is exactly that of the unsplit kernel, so results are bit-identical to it.
+  int sk_tiles, dp_tiles;
+  float* sk_ws;                   // [n_units][CTAs per unit][BN / 32 chunks][8][128 rows][4] fp32
+  unsigned* sk_flags;             // [n_units][CTAs per unit]: 1 while the unit's START dump waits to be consumed
 };
+
+// ---- work items of one unit (a CTA or a CTA pair)
+enum { GEMM_ITEM_FULL = 0, GEMM_ITEM_START = 1, GEMM_ITEM_END = 2 };
+struct GemmItem {
+  int tile, kb0, kb1, kind;
+};
+struct GemmSchedule {
+  int n_items, unit, n_units;
+  int dp_items;                   // data-parallel tiles of this unit: tile = unit + i * n_units
+  int has_start, has_end, n_whole;
+  int start_tile, start_kb1;      // START piece: k-blocks [0, start_kb1) of start_tile
+  int end_tile, end_kb0;          // END piece: k-blocks [end_kb0, num_k_blk) of end_tile
+  int whole0;                     // first whole stream-K tile
+};
+
+__device__ __forceinline__ GemmSchedule gemm_schedule(const GemmArgs& a, int unit, int n_units) {
+  GemmSchedule s = {};
+  s.unit = unit;
+  s.n_units = n_units;
+  const int num_tiles = a.num_m_blk * a.num_n_blk;
+  if (a.sk_tiles <= 0) {
+    s.dp_items = unit < num_tiles ? (num_tiles - unit + n_units - 1) / n_units : 0;
+    s.n_items = s.dp_items;
+    return s;
+  }
+  const int KB = a.num_k_blk;
+  const long long total = (long long)a.sk_tiles * KB;
+  const long long b = (long long)unit * total / n_units, e = (long long)(unit + 1) * total / n_units;  // e - b >= KB
+  const int t_first = (int)(b / KB), b_off = (int)(b - (long long)t_first * KB);
+  const int t_last = (int)((e - 1) / KB), e_off = (int)(e - (long long)t_last * KB);   // 1 .. KB
+  s.dp_items = a.dp_tiles / n_units;
+  s.has_end = b_off > 0;
+  s.has_start = e_off < KB;
+  s.end_tile = a.dp_tiles + t_first;
+  s.end_kb0 = b_off;
+  s.start_tile = a.dp_tiles + t_last;
+  s.start_kb1 = e_off;
+  s.whole0 = a.dp_tiles + t_first + s.has_end;
+  s.n_whole = (t_last - s.has_start) - (t_first + s.has_end) + 1;
+  s.n_items = s.has_start + s.dp_items + s.n_whole + s.has_end;
+  return s;
+}
+
+// item order: [START piece] [data-parallel tiles] [whole stream-K tiles] [END piece].  The START piece comes first so that its dump
+// is in memory long before the neighbouring unit needs it for its (last) END item; unit 0 never has an END item, and units are
+// co-resident (persistent grid), so the waits cannot form a cycle.
+__device__ __forceinline__ GemmItem gemm_item(const GemmArgs& a, const GemmSchedule& s, int i) {
+  GemmItem w;
+  w.kb0 = 0;
+  w.kb1 = a.num_k_blk;
+  w.kind = GEMM_ITEM_FULL;
+  if (s.has_start) {
+    if (i == 0) {
+      w.tile = s.start_tile; w.kb1 = s.start_kb1; w.kind = GEMM_ITEM_START;
+      return w;
+    }
+    --i;
+  }
+  if (i < s.dp_items) { w.tile = s.unit + i * s.n_units; return w; }
+  i -= s.dp_items;
+  if (i < s.n_whole) { w.tile = s.whole0 + i; return w; }
+  w.tile = s.end_tile; w.kb0 = s.end_kb0; w.kind = GEMM_ITEM_END;
+  return w;
+}
 
 struct GemmSegMaps {
   CUtensorMap m[8];
@@ -74,17 +147,20 @@ int launch_gemm4(const CUtensorMap& tmAh, const CUtensorMap& tmB, const CUtensor
                  cudaStream_t stream);
 #endif
 
-template <int BN, int STAGES, bool CTA2 = false>
+// EPI_BUFS: 2 KiB staging tiles per epilogue warp — 1 = output staging only; 3 = ring shared by the TMA-loaded residual tile and
+// the output tile (the TMARES kernels: residual chunk g + 1 lands while chunk g is added in place and chunk g - 1 is stored)
+template <int BN, int STAGES, bool CTA2 = false, int EPI_BUFS = 1>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;  // CTA pair: each CTA stages half of the W tile
   static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BIAS_OFF = BAR_OFF + 256;
+  static constexpr int RES_BAR_OFF = BAR_OFF + 256;                                // 8 warps x 3 residual-tile barriers
+  static constexpr int BIAS_OFF = BAR_OFF + 512;
   static constexpr int COLSUM_OFF = BIAS_OFF + 2 * BN * 4;                         // layer-norm column sums, double-buffered like bias
-  static constexpr int STAGE_OUT_OFF = (COLSUM_OFF + 2 * BN * 4 + 1023) & ~1023;  // 8 warps x 2 KiB output staging
-  static constexpr int TOTAL = STAGE_OUT_OFF + 8 * 2048 + 1024;  // +1024: manual 1 KiB alignment of the base
+  static constexpr int STAGE_OUT_OFF = (COLSUM_OFF + 2 * BN * 4 + 1023) & ~1023;  // 8 warps x EPI_BUFS x 2 KiB staging
+  static constexpr int TOTAL = STAGE_OUT_OFF + 8 * EPI_BUFS * 2048 + 1024;  // +1024: manual 1 KiB alignment of the base
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
@@ -239,6 +315,36 @@ __device__ __forceinline__ void staged_store_chunk(const GemmArgs& args, const C
   }
 }
 
+// TMARES kernels: `buf` (32 x 32 bf16, SWIZZLE_64B) holds the residual tile delivered by TMA; every thread adds its own row to the
+// 32 finished values, writes the rounded sums back in place (a thread touches only its own row: no intra-warp ordering needed) and
+// the tile leaves from the same buffer with one TMA store
+__device__ __forceinline__ void ring_add_store_chunk(const CUtensorMap* tmC, uint8_t* buf, float* v, int row_base, int col0, int lane,
+                                                     float2* row_stats) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint8_t* p = buf + stage_off(lane, g);
+    const uint4 r = lds_u4(p);
+    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z), r3 = unpack_bf16x2(r.w);
+    const float* w = v + g * 8;
+    uint4 u;
+    u.x = pack_bf16x2(w[0] + r0.x, w[1] + r0.y); u.y = pack_bf16x2(w[2] + r1.x, w[3] + r1.y);
+    u.z = pack_bf16x2(w[4] + r2.x, w[5] + r2.y); u.w = pack_bf16x2(w[6] + r3.x, w[7] + r3.y);
+    sts_u4(p, u);
+    if (row_stats != nullptr) {  // statistics of what the consumer will read: the rounded values (same order as staged_store_chunk)
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      row_stats->x += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      row_stats->y += ((f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y)) +
+                      ((f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y));
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, buf, col0, row_base);
+    tma_store_commit();
+  }
+}
+
 // mu / rstd of one A row from the producer's partial sums (fixed summation order -> bit-deterministic)
 __device__ __forceinline__ void row_norm_coeffs(const GemmArgs& args, int row, bool row_ok, float& rs, float& nmu) {
   rs = 1.f;
@@ -246,7 +352,15 @@ __device__ __forceinline__ void row_norm_coeffs(const GemmArgs& args, int row, b
   if (args.norm_mode == LP_NORM_NONE_ || !row_ok) return;
   const float2* p = args.stats_in + (long long)row * args.stats_in_parts;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < args.stats_in_parts; ++i) {
+  int i = 0;
+  for (; i + 4 <= args.stats_in_parts; i += 4) {   // four partials in flight at once; the additions keep the index order
+    const float2 t0 = p[i], t1 = p[i + 1], t2 = p[i + 2], t3 = p[i + 3];
+    s1 += t0.x; s2 += t0.y;
+    s1 += t1.x; s2 += t1.y;
+    s1 += t2.x; s2 += t2.y;
+    s1 += t3.x; s2 += t3.y;
+  }
+  for (; i < args.stats_in_parts; ++i) {
     const float2 t = p[i];
     s1 += t.x;
     s2 += t.y;

@@ -28,6 +28,7 @@ class PrefillEngine:
         self._decode_state = None   # device-resident greedy-loop state + captured CUDA graph (leopard_b200/decode.py)
         self._decode_kv = None      # persistent KV-cache buffer of generate() (capacity grows in KV_GRANULE steps)
         _lib.lib()  # fail early and loudly when the extension is missing
+        _lib.ensure_streamk_workspace(self.device)
 
     # ------------------------------------------------------------------ buffers
     def _workspace(self, key: str, nbytes: int) -> torch.Tensor:

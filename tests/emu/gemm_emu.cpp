@@ -23,11 +23,16 @@ static CUtensorMap tmap2(const void* base, uint64_t inner, uint64_t outer, uint6
 
 template <int BN, int STAGES, bool CTA2>
 static void run(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& args, int ctas) {
+  const bool lres = args.residual != nullptr;     // launch_gemm's choice: the register-residual kernel when there is a residual
   if constexpr (CTA2) {
-    emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_kernel<BN, STAGES, true>(a, b, c, args); });
+    emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] {
+      if (lres) gemm_bf16_lres_kernel<BN, STAGES, true>(a, b, c, args); else gemm_bf16_kernel<BN, STAGES, true>(a, b, c, args);
+    });
   } else {
     emu::g_block_hook = [] { emu_tc::reset(); };
-    emu::launch(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_kernel<BN, STAGES, false>(a, b, c, args); });
+    emu::launch(dim3(ctas), dim3(GEMM_THREADS), [&] {
+      if (lres) gemm_bf16_lres_kernel<BN, STAGES, false>(a, b, c, args); else gemm_bf16_kernel<BN, STAGES, false>(a, b, c, args);
+    });
     emu::g_block_hook = nullptr;
   }
 }
@@ -37,6 +42,17 @@ struct EmuFusions {   // the epilogue fusions of lp_gemm_bf16_ex
   int norm_mode; const float* stats_in; int stats_in_parts; const float* colsum; float norm_eps;
   float* stats_out; const float* rope_cos; const float* rope_sin; int rope_heads;
 };
+
+template <int BN, int STAGES>
+static void run_res(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& r, const GemmArgs& args, int ctas) {
+  emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_res_kernel<BN, STAGES, true>(a, b, c, r, args); });
+}
+static int g_tma_res = 0;   // pair-mode residual launches through gemm_bf16_res_kernel (lp_gemm_set_tma_residual)
+extern "C" void emu_gemm_set_tma_residual(int on) { g_tma_res = on; }
+
+// stream-K tail (lp_gemm_set_streamk_workspace): set by emu_gemm_set_streamk before a launch, same split rule as lp_gemm_bf16_ex
+static void* g_sk_ws = nullptr;
+extern "C" void emu_gemm_set_streamk(void* ws) { g_sk_ws = ws; }
 
 extern "C" void emu_gemm_ex(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                             const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
@@ -61,9 +77,27 @@ extern "C" void emu_gemm_ex(const void* A, long long lda, const void* W, long lo
   args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
   args.group_m = group_m > args.num_m_blk ? args.num_m_blk : group_m;
   args.prefetch_a = 0;
+  if (g_sk_ws != nullptr) {
+    const int T = args.num_m_blk * args.num_n_blk, n_units = pair ? ctas / 2 : ctas;
+    if (T > n_units && T % n_units != 0) {
+      args.dp_tiles = (T / n_units - 1) * n_units;
+      args.sk_tiles = T - args.dp_tiles;
+      args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);
+      args.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + 4096);
+    }
+  }
   CUtensorMap tmC = tmap2(C, act == LP_ACT_SWIGLU ? N / 2 : N, M, ldc, 32, 32, 2, 64);
   CUtensorMap tmA = tmap2(A, K, M, lda, GEMM_BK, GEMM_BM, 2, 128);
   CUtensorMap tmB = tmap2(W, K, N, ldw, GEMM_BK, pair ? block_n / 2 : block_n, 2, 128);
+  if (pair && g_tma_res && residual != nullptr && res_row_mod == 0 && !out_fp32 && act != LP_ACT_SWIGLU && !(fx && fx->rope_heads)) {
+    CUtensorMap tmR = tmap2(residual, N, M, ldr, 32, 32, 2, 64);
+    switch (block_n) {
+      case 256: run_res<256, 5>(tmA, tmB, tmC, tmR, args, ctas); break;
+      case 192: run_res<192, 6>(tmA, tmB, tmC, tmR, args, ctas); break;
+      default: run_res<128, 7>(tmA, tmB, tmC, tmR, args, ctas); break;
+    }
+    return;
+  }
   if (pair) {
     switch (block_n) {
       case 256: run<256, 6, true>(tmA, tmB, tmC, args, ctas); break;

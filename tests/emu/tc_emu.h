@@ -158,6 +158,12 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsi
 inline unsigned ld_acquire_sys(const unsigned* p) { return std::atomic_ref<unsigned>(*const_cast<unsigned*>(p)).load(); }
 inline unsigned ld_acquire_gpu(const unsigned* p) { return ld_acquire_sys(p); }
 inline void st_release_sys(unsigned* p, unsigned v) { std::atomic_ref<unsigned>(*p).store(v); }
+inline void st_release_gpu(unsigned* p, unsigned v) { st_release_sys(p, v); }
+inline void st_relaxed_gpu(unsigned* p, unsigned v) { st_release_sys(p, v); }
+inline uint4 lds_u4(const void* p) { uint4 v; std::memcpy(&v, p, 16); return v; }
+inline void sts_u4(void* p, uint4 v) { std::memcpy(p, &v, 16); }
+inline uint4 ld_cg_u4(const float* p) { uint4 v; std::memcpy(&v, p, 16); return v; }
+inline void st_cg_u4(float* p, uint4 v) { std::memcpy(p, &v, 16); }
 inline void spin_until_sys(const unsigned* p, unsigned target) { while ((int)(ld_acquire_sys(p) - target) < 0) std::this_thread::yield(); }
 inline void spin_until_gpu(const unsigned* p, unsigned target) { while (ld_acquire_gpu(p) < target) std::this_thread::yield(); }
 inline void mbar_arrive_addr(uint32_t addr) {
@@ -305,6 +311,7 @@ inline void tmem_st(const uint32_t* regs, uint32_t taddr, int n) {
 #define LP_TMEM_LD_32(regs, taddr) lp::tmem_ld(regs, taddr, 32)
 #define LP_TMEM_LD_16(regs, taddr) lp::tmem_ld(regs, taddr, 16)
 #define LP_TMEM_ST_16(regs, taddr) lp::tmem_st(regs, taddr, 16)
+#define LP_TMEM_ST_32(regs, taddr) lp::tmem_st(regs, taddr, 32)
 
 // ---- UMMA (descriptor bit layouts: see umma_desc_sw128 / umma_idesc_bf16, taken from lp_common.cuh by the tests)
 // pair = false: one CTA, M = 128.  pair = true (cta_group::2): M = 256; accumulator / A row m lives in CTA m / 128, B row n

@@ -265,3 +265,115 @@ def test_gemm_reduce_scatter_stores_partials_into_the_owners_slots(emu, tp, rank
         assert bool(torch.isnan(stages[r][others].float()).all())              # nothing else was touched
         assert int(sig_peers[r][8 + rank]) == epoch                            # completion posted to every owner
     assert int(counter) == ctas
+
+
+# ---- stream-K tail (lp_gemm_set_streamk_workspace): the accumulator of a tile cut along K is handed from unit u to unit u + 1 -----
+@pytest.mark.parametrize("M,N,K,bn,pair,ctas,act,bias,res,stats", [
+    (600, 384, 320, 128, True, 4, 0, True, True, True),        # pairs: 9 tiles on 2 units -> unit 0 starts tile 7, unit 1 finishes it; residual + row statistics
+    (600, 384, 330, 128, False, 4, 1, True, False, False),     # one CTA per tile: 15 tiles on 4 units, ragged K, GELU
+    (520, 760, 456, 256, True, 4, 0, False, True, False),      # 256-wide tiles, ragged last column block (narrow MMA) inside the stream-K range
+    (384, 1024, 200, 128, True, 6, 3, True, True, False),      # SwiGLU granules, 3 units
+    (200, 256, 192, 128, False, 3, 0, True, False, False),     # 4 tiles on 3 units: unit 1 has only a START and an END piece
+])
+def test_stream_k_tail_is_bit_identical_to_the_unsplit_schedule(emu, M, N, K, bn, pair, ctas, act, bias, res, stats):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    b = torch.randn(N, generator=g) if bias else None
+    n_out = N // 2 if act == 3 else N
+    r = torch.randn((M, n_out), generator=g).to(BF) if res else None
+    parts = 2 * (-(-N // bn))
+    outs, sts = [], []
+    ws = torch.zeros(4096 + ctas * 128 * bn * 4, dtype=torch.uint8)
+    for sk in (False, True):
+        out = torch.full((M, n_out), float("nan"), dtype=BF)
+        st = torch.full((M, parts, 2), float("nan"))
+        fx = _Fx(stats_out=st.data_ptr()) if stats else None
+        emu.emu_gemm_set_streamk(P(ws) if sk else None)
+        try:
+            _gemm_ex(emu, a, w, out, bias=b, res=r, act=act, bn=bn, pair=pair, ctas=ctas, fx=fx)
+        finally:
+            emu.emu_gemm_set_streamk(None)
+        outs.append(out)
+        sts.append(st)
+    want = ref.gemm(a, w, bias=b, residual=r, act=act)
+    assert not bool(torch.isnan(outs[1].float()).any())
+    assert float((outs[1].float() - want.float()).abs().max() / want.float().abs().max()) < 8e-3
+    assert torch.equal(outs[0], outs[1])                        # same summation order -> same bits
+    if stats:
+        assert torch.equal(sts[0], sts[1])
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0    # every hand-over flag consumed: the workspace is ready for the next launch
+    assert float(ws[4096:].view(torch.float32).nan_to_num().abs().sum()) > 0   # and partial accumulators really went through it
+
+
+def test_stream_k_schedule_covers_every_k_block_exactly_once():
+    """Host-side restatement of gemm_schedule / gemm_item (lp_gemm_common.cuh): for the bench shapes, every (tile, k-block) is
+    owned by exactly one unit, ranges differ by at most one k-block, a cut tile is shared by units u and u + 1 only."""
+    def schedule(T, KB, P):
+        dp = (T // P - 1) * P
+        sk = T - dp
+        total = sk * KB
+        items = {u: [] for u in range(P)}
+        for u in range(P):
+            b, e = u * total // P, (u + 1) * total // P
+            t_first, b_off = divmod(b, KB)
+            t_last, e_off = (e - 1) // KB, e - ((e - 1) // KB) * KB
+            has_end, has_start = b_off > 0, e_off < KB
+            if has_start:
+                items[u].append((dp + t_last, 0, e_off, "start"))
+            items[u] += [(u + i * P, 0, KB, "full") for i in range(dp // P)]
+            items[u] += [(dp + t, 0, KB, "full") for t in range(t_first + has_end, t_last - has_start + 1)]
+            if has_end:
+                items[u].append((dp + t_first, b_off, KB, "end"))
+        return items
+    for T, KB, P in [(304, 64, 74), (304, 224, 74), (456, 64, 74), (192, 64, 74), (15, 6, 4), (9, 5, 2), (149, 18, 148)]:
+        items = schedule(T, KB, P)
+        seen = {}
+        for u, its in items.items():
+            for t, k0, k1, kind in its:
+                for k in range(k0, k1):
+                    assert (t, k) not in seen
+                    seen[(t, k)] = u
+                if kind == "end":
+                    assert seen[(t, 0)] == u - 1 and items[u - 1][0][0] == t and items[u - 1][0][2] == k0
+        assert len(seen) == T * KB
+        loads = [sum(k1 - k0 for _, k0, k1, _ in its) for its in items.values()]
+        assert max(loads) - min(loads) <= 1
+
+
+# ---- residual tile by TMA (gemm_bf16_res_kernel, lp_gemm_set_tma_residual): same bits as the register path ------------------------
+@pytest.mark.parametrize("M,N,K,bn,ctas,bias,stats,sk,inplace", [
+    (600, 384, 320, 128, 4, True, True, False, True),      # in-place residual stream (C == residual), row statistics
+    (520, 1160, 200, 256, 2, True, False, False, False),   # 256-wide tiles, ragged M and N (half-empty last column block), persistent over 15 tiles
+    (600, 760, 456, 192, 4, False, True, True, True),      # 192-wide tiles (chunk split 3 + 3), stream-K tail on top
+    (300, 72, 136, 128, 2, True, False, False, False),     # N < one chunk pair: warpgroup 1 has nothing to do
+])
+def test_tma_residual_ring_matches_the_register_path(emu, M, N, K, bn, ctas, bias, stats, sk, inplace):
+    g = torch.Generator().manual_seed(M * 3 + N)
+    a = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    b = torch.randn(N, generator=g) if bias else None
+    r = torch.randn((M, N), generator=g).to(BF)
+    parts = 2 * (-(-N // bn))
+    ws = torch.zeros(4096 + ctas * 128 * bn * 4, dtype=torch.uint8)
+    outs, sts = [], []
+    for tma in (0, 1):
+        out = r.clone() if inplace else torch.full((M, N), float("nan"), dtype=BF)
+        res = out if inplace else r
+        st = torch.full((M, parts, 2), float("nan"))
+        fx = _Fx(stats_out=st.data_ptr()) if stats else None
+        emu.emu_gemm_set_tma_residual(tma)
+        emu.emu_gemm_set_streamk(P(ws) if sk else None)
+        try:
+            _gemm_ex(emu, a, w, out, bias=b, res=res, bn=bn, pair=True, ctas=ctas, fx=fx)
+        finally:
+            emu.emu_gemm_set_tma_residual(0)
+            emu.emu_gemm_set_streamk(None)
+        outs.append(out)
+        sts.append(st)
+    want = ref.gemm(a, w, bias=b, residual=r)
+    assert not bool(torch.isnan(outs[1].float()).any())
+    assert float((outs[1].float() - want.float()).abs().max() / want.float().abs().max()) < 8e-3
+    assert torch.equal(outs[0], outs[1])
+    if stats:
+        assert torch.equal(sts[0], sts[1])

@@ -270,3 +270,52 @@ def test_gemm_ex_rmsnorm_swiglu_and_rope(native_lib):
     ref2 = ops.gemm(h, wq)
     ops.rope_inplace(ref2, 0, rot, 128, cos, sin)
     assert float((got.float() - ref2.float()).abs().max() / want.abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K,res,act,stats", [
+    (4796, 4096, 4096, True, 0, True),       # decoder o-proj at cfg3: 304 tiles on 74 CTA pairs -> stream-K tail, residual by TMA, row statistics
+    (4796, 6144, 4096, False, 0, False),     # qkv: 456 tiles
+    (2937, 4096, 14336, True, 0, False),     # down-proj at cfg2: 192 tiles (2.6 waves), K = 224 k-blocks
+    (2937, 28672, 4096, False, 3, False),    # gate/up at cfg2 with SwiGLU: 1344 tiles (18.2 waves)
+    (18928, 1152, 1152, True, 0, True),      # ViT out-proj: no tail (74 x 5 tiles), residual ring only
+    (4796, 1536, 2048, True, 0, False),      # 114 tiles on 74 pairs: fewer than two waves, every tile belongs to the stream-K range
+])
+def test_gemm_stream_k_and_tma_residual_do_not_change_a_bit(native_lib, M, N, K, res, act, stats):
+    """lp_gemm_set_streamk / lp_gemm_set_tma_residual are pure scheduling / data-path switches: every combination must give
+    the bits of the plain schedule (and those must match fp32 torch)."""
+    from leopard_b200 import _lib
+    L = _lib.lib()
+    assert _lib.ensure_streamk_workspace("cuda:0") is not None
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.5 if act == 0 else None
+    n_out = N // 2 if act == 3 else N
+    r = _bf(torch.randn(M, n_out, device="cuda", generator=g)) if res else None
+    outs = {}
+    try:
+        for sk in (0, 1):
+            for tma in (0, 1):
+                L.lp_gemm_set_streamk(sk)
+                L.lp_gemm_set_tma_residual(tma)
+                x = r.clone() if res else None        # in place, as the layer loops use it
+                o = ops.gemm_ex(a, w, bias=bias, residual=x, act=act, out=x, block_n=256, want_stats=stats)
+                outs[(sk, tma)] = o if stats else (o, None)
+    finally:
+        L.lp_gemm_set_streamk(1)
+        L.lp_gemm_set_tma_residual(1)
+    torch.cuda.synchronize()
+    base, base_st = outs[(0, 0)]
+    ref = a.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if act == 3:
+        yy = ref.view(M, N // 64, 2, 32)
+        ref = (torch.nn.functional.silu(yy[:, :, 0]) * yy[:, :, 1]).reshape(M, N // 2)
+    if res:
+        ref = ref + r.float()
+    _close(base, ref, BF, 1.0)
+    for key, (o, st) in outs.items():
+        assert torch.equal(o, base), f"streamk={key[0]} tma_residual={key[1]} changed the output"
+        if stats:
+            assert torch.equal(st, base_st), f"streamk={key[0]} tma_residual={key[1]} changed the row statistics"

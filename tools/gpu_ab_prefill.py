@@ -33,6 +33,10 @@ def apply(setting):
         L.lp_norm_set_variant(v)
     elif k == "fused":
         L.lp_model_set_fused_norm(v)
+    elif k == "sk":
+        L.lp_gemm_set_streamk(v)
+    elif k == "tmares":
+        L.lp_gemm_set_tma_residual(v)
     else:
         raise SystemExit(f"unknown switch {k}")
 
@@ -62,3 +66,5 @@ for s in settings:
 L.lp_model_set_attention_variant(80)
 L.lp_gemm_set_pair_mode(1)
 L.lp_model_set_fused_norm(1)
+L.lp_gemm_set_streamk(1)
+L.lp_gemm_set_tma_residual(1)
