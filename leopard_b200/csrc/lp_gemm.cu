@@ -241,14 +241,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       bv = (ok && args.bias) ? args.bias[col] : 0.f;
       cv = (ok && args.norm_mode == LP_NORM_LAYER_) ? args.colsum[col] : 0.f;
     };
-    {
-      const int first = sch.has_start ? 1 : 0;          // the START item has no epilogue
-      if (first < sch.n_items && col_thread) {
-        float bv, cv;
-        fetch_cols(gemm_item(args, sch, first), bv, cv);
-        bias_smem[(first & 1) * BN + et] = bv;
-        colsum_smem[(first & 1) * BN + et] = cv;
-      }
+    if (sch.n_items > 0 && col_thread) {
+      float bv, cv;
+      fetch_cols(gemm_item(args, sch, 0), bv, cv);
+      bias_smem[et] = bv;
+      colsum_smem[et] = cv;
     }
     // TMARES: residual ring of this warp (3 x 2 KiB) and its barriers; rg counts the chunks this warp has sent through it
     uint8_t* ring = smem + L::STAGE_OUT_OFF + (warp - 2) * (TMARES ? 3 : 1) * 2048;
@@ -288,7 +285,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const GemmItem w = gemm_item(args, sch, it);
       if (sch.has_end && !sk_reloaded && it + 2 >= sch.n_items && w.kind != GEMM_ITEM_START) sk_reload();
       if (w.kind == GEMM_ITEM_START) {
-        // ---- stream-K START item (always the first one): k-blocks [0, kb1) only; the raw fp32 accumulator goes to this unit's slot
+        // ---- stream-K START item (after the data-parallel tiles): k-blocks [0, kb1) only; the raw fp32 accumulator goes to this unit's slot
         // of the workspace ([chunk][4-column group][row][4]: every warp store covers 512 contiguous bytes) for the next unit
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
@@ -314,7 +311,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         if (et == 0) st_release_gpu(args.sk_flags + sk_slot, 1u);
         as ^= 1;
         if (as == 0) aphase ^= 1;
-        if (sch.has_end && !sk_reloaded && it + 2 >= sch.n_items) sk_reload();   // [START, END] only: own dump first (no chain of waits)
+        if (it + 1 < sch.n_items && col_thread) {   // bias / column sums of the next item (every warp has left item it - 1: barrier above)
+          float bv, cv;
+          fetch_cols(gemm_item(args, sch, it + 1), bv, cv);
+          bias_smem[as * BN + et] = bv;
+          colsum_smem[as * BN + et] = cv;
+        }
+        if (sch.has_end && !sk_reloaded && it + 2 >= sch.n_items) sk_reload();   // [.., START, END]: own dump first (no chain of waits)
         continue;
       }
       int m_blk, n_blk, seg, row_limit;
@@ -732,10 +735,12 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
     const int T = args.num_m_blk * args.num_n_blk;
     const int n_units = pair ? sms / 2 : sms, per_unit = pair ? 2 : 1;
     if (T > n_units && T % n_units != 0 && args.num_k_blk >= 8) {
-      const int waves = (T + n_units - 1) / n_units;
-      const double fill = (double)T / ((double)waves * n_units);
+      // measured on the B200 (profiles/r02i_*): worth it when the last wave is mostly empty (S = 4796 o / down: 4.11 waves, +6 ..
+      // +10 %; qkv 6.16: +1 %); with a half-full last wave (S = 2937: 2.59 waves) the staggered k ranges of the stream-K phase
+      // cost more L2 locality than the idle units did (-4 %), so those keep the plain schedule
+      const double frac = (double)T / n_units - (double)(T / n_units);
       const size_t need = SK_FLAG_BYTES + (size_t)n_units * per_unit * GEMM_BM * block_n * sizeof(float);
-      if (fill < 0.97 && need <= g_sk_bytes) {
+      if (frac <= 0.40 && need <= g_sk_bytes) {
         args.dp_tiles = (T / n_units - 1) * n_units;
         args.sk_tiles = T - args.dp_tiles;
         args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);

@@ -63,8 +63,8 @@ struct GemmArgs {
   // ---- stream-K tail (sk_tiles > 0; lp_gemm_set_streamk_workspace): the first dp_tiles tiles (a multiple of the unit count) are
   // scheduled one tile per unit per wave as usual; the K loops of the last sk_tiles tiles (n_units <= sk_tiles < 2 n_units) are
   // laid end to end and cut into n_units equal ranges, so every unit ends at the same time instead of a mostly idle last wave.
-  // A tile cut between units u and u + 1 is STARTED by u (its first work item: k-blocks [0, b), raw fp32 accumulator dumped to
-  // sk_ws) and FINISHED by u + 1 (its last item: the dump is loaded back into TMEM and the k loop continues at b) — the
+  // A tile cut between units u and u + 1 is STARTED by u (right after its data-parallel tiles: k-blocks [0, b), raw fp32 accumulator
+  // dumped to sk_ws) and FINISHED by u + 1 (its last item: the dump is loaded back into TMEM and the k loop continues at b) — the
   // accumulation order of every output element is exactly that of the unsplit kernel, so results are bit-identical to it.
   int sk_tiles, dp_tiles;
   float* sk_ws;                   // [n_units][CTAs per unit][BN / 32 chunks][8][128 rows][4] fp32
@@ -113,14 +113,18 @@ __device__ __forceinline__ GemmSchedule gemm_schedule(const GemmArgs& a, int uni
   return s;
 }
 
-// item order: [START piece] [data-parallel tiles] [whole stream-K tiles] [END piece].  The START piece comes first so that its dump
-// is in memory long before the neighbouring unit needs it for its (last) END item; unit 0 never has an END item, and units are
-// co-resident (persistent grid), so the waits cannot form a cycle.
+// item order: [data-parallel tiles] [START piece] [whole stream-K tiles] [END piece].  The data-parallel waves run exactly as in
+// the plain schedule (all units in step along K, which is what keeps the operand slices shared through L2).  The START piece comes
+// before the whole tiles so that its dump is in memory before the neighbouring unit reaches its END item (by construction that
+// happens (range - num_k_blk) k-blocks later); unit 0 never has an END item and all units are co-resident (persistent grid), so
+// the waits cannot form a cycle.
 __device__ __forceinline__ GemmItem gemm_item(const GemmArgs& a, const GemmSchedule& s, int i) {
   GemmItem w;
   w.kb0 = 0;
   w.kb1 = a.num_k_blk;
   w.kind = GEMM_ITEM_FULL;
+  if (i < s.dp_items) { w.tile = s.unit + i * s.n_units; return w; }
+  i -= s.dp_items;
   if (s.has_start) {
     if (i == 0) {
       w.tile = s.start_tile; w.kb1 = s.start_kb1; w.kind = GEMM_ITEM_START;
@@ -128,12 +132,11 @@ __device__ __forceinline__ GemmItem gemm_item(const GemmArgs& a, const GemmSched
     }
     --i;
   }
-  if (i < s.dp_items) { w.tile = s.unit + i * s.n_units; return w; }
-  i -= s.dp_items;
   if (i < s.n_whole) { w.tile = s.whole0 + i; return w; }
   w.tile = s.end_tile; w.kb0 = s.end_kb0; w.kind = GEMM_ITEM_END;
   return w;
 }
+
 
 struct GemmSegMaps {
   CUtensorMap m[8];

@@ -319,15 +319,15 @@ def test_stream_k_schedule_covers_every_k_block_exactly_once():
             t_first, b_off = divmod(b, KB)
             t_last, e_off = (e - 1) // KB, e - ((e - 1) // KB) * KB
             has_end, has_start = b_off > 0, e_off < KB
+            items[u] += [(u + i * P, 0, KB, "full") for i in range(dp // P)]
             if has_start:
                 items[u].append((dp + t_last, 0, e_off, "start"))
-            items[u] += [(u + i * P, 0, KB, "full") for i in range(dp // P)]
             items[u] += [(dp + t, 0, KB, "full") for t in range(t_first + has_end, t_last - has_start + 1)]
             if has_end:
                 items[u].append((dp + t_first, b_off, KB, "end"))
-        return items
+        return items, dp
     for T, KB, P in [(304, 64, 74), (304, 224, 74), (456, 64, 74), (192, 64, 74), (15, 6, 4), (9, 5, 2), (149, 18, 148)]:
-        items = schedule(T, KB, P)
+        items, dp = schedule(T, KB, P)
         seen = {}
         for u, its in items.items():
             for t, k0, k1, kind in its:
@@ -335,7 +335,12 @@ def test_stream_k_schedule_covers_every_k_block_exactly_once():
                     assert (t, k) not in seen
                     seen[(t, k)] = u
                 if kind == "end":
-                    assert seen[(t, 0)] == u - 1 and items[u - 1][0][0] == t and items[u - 1][0][2] == k0
+                    start = [i for i in items[u - 1] if i[3] == "start"]
+                    assert seen[(t, 0)] == u - 1 and start[0][0] == t and start[0][2] == k0
+                    # the neighbour's START is finished before this unit reaches its END item (k-block times after the data-parallel waves)
+                    t_start_done = start[0][2]
+                    t_reach_end = sum(k1_ - k0_ for tt, k0_, k1_, kd in its if kd != "end" and tt >= dp)
+                    assert t_reach_end >= t_start_done
         assert len(seen) == T * KB
         loads = [sum(k1 - k0 for _, k0, k1, _ in its) for its in items.values()]
         assert max(loads) - min(loads) <= 1
