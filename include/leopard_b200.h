@@ -337,6 +337,11 @@ int lp_vit_layers(const lp_vit_dims* dims, const lp_vit_weights* w, void* x, con
 size_t lp_project_workspace_bytes(int rows, int hidden);
 int lp_project(const lp_proj_weights* w, const void* shuffled, int rows, int in_dim, int hidden, void* out,
                long long ldo, void* workspace, size_t ws_bytes, void* stream);
+/* lp_project as ONE kernel (default, when the GEMM flag workspace of lp_gemm_set_streamk_workspace is present and rows > 128): the
+ * tiles of both layers share one persistent launch, a layer-2 tile waits (dataflow counters, no launch boundary) until the layer-1
+ * tiles of its row block have landed in the L2-resident intermediate; the pixel shuffle is ln_post's store, so shuffle + projector
+ * cost this single launch.  0 = two GEMM launches.  Same arithmetic: results are bit-identical.  Returns the previous setting. */
+int lp_model_set_chained_projector(int enable);
 
 /* Decoder prefill over n_seqs packed sequences (rows cu_seqlens_host[s] .. cu_seqlens_host[s+1]-1 of x).
  *   x: bf16 [R, hidden] merged embeddings; used as the residual stream and overwritten with the last layer's output.

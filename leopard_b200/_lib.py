@@ -86,6 +86,7 @@ _SIGS = {
     "lp_gemm_pick_block_n": (_i, [_i, _i, _i]),
     "lp_row_stats": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
     "lp_model_set_fused_norm": (_i, [_i]),
+    "lp_model_set_chained_projector": (_i, [_i]),
     "lp_gemm_set_pair_mode": (_i, [_i]),
     "lp_gemm_streamk_workspace_bytes": (_sz, []),
     "lp_gemm_set_streamk_workspace": (_i, [_vp, _sz]),

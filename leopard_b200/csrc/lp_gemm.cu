@@ -879,6 +879,11 @@ extern "C" int lp_gemm_set_streamk_workspace(void* ws, size_t bytes) {
   g_sk_bytes = ws ? bytes : 0;
   return 0;
 }
+namespace lp {
+// the workspace's flag page, shared with the chained projector launch (lp_gemm_chain.cu: words 511 ..)
+unsigned* gemm_flag_page() { return reinterpret_cast<unsigned*>(g_sk_ws); }
+}  // namespace lp
+
 extern "C" int lp_gemm_set_tma_residual(int enable) {
   const int old = g_gemm_tma_residual;
   g_gemm_tma_residual = enable ? 1 : 0;

@@ -228,6 +228,19 @@ extern "C" int lp_vit_layers(const lp_vit_dims* d, const lp_vit_weights* w, void
 }
 
 // ------------------------------------------------------------------------------------------------ projector
+namespace lp {
+int launch_gemm_chain(const void* X, long long ldx, const void* W1, const float* b1, int act1, void* mid, long long ld_mid,
+                      const void* W2, const float* b2, void* out, long long ldo, int M, int N1, int K1, int N2, cudaStream_t stream);
+unsigned* gemm_flag_page();
+}  // namespace lp
+// both projector layers in ONE kernel (lp_gemm_chain.cu) when the GEMM flag workspace is present; 0 = two GEMM launches
+static int g_chained_projector = 1;
+extern "C" int lp_model_set_chained_projector(int enable) {
+  const int old = g_chained_projector;
+  g_chained_projector = enable ? 1 : 0;
+  return old;
+}
+
 extern "C" size_t lp_project_workspace_bytes(int rows, int hidden) { return bf((size_t)rows * hidden) + 512; }
 
 extern "C" int lp_project(const lp_proj_weights* w, const void* shuffled, int rows, int in_dim, int hidden, void* out,
@@ -237,6 +250,10 @@ extern "C" int lp_project(const lp_proj_weights* w, const void* shuffled, int ro
   Carver cv(workspace, ws_bytes);
   void* mid = cv.take(bf((size_t)rows * hidden));
   int rc;
+  if (g_chained_projector && gemm_flag_page() != nullptr && rows > 128 && in_dim % 8 == 0 && hidden % 8 == 0 && ldo % 8 == 0 &&
+      rows <= 448 * 256)
+    return launch_gemm_chain(shuffled, in_dim, w->w1, w->b1, w->act, mid, hidden, w->w2, w->b2, out, ldo, rows, hidden, in_dim, hidden,
+                             reinterpret_cast<cudaStream_t>(stream));
   LP_TRY(lp_gemm_bf16(shuffled, in_dim, w->w1, in_dim, mid, hidden, rows, hidden, in_dim, w->b1, nullptr, 0, 0, w->act,
                       0, 0, stream));
   LP_TRY(lp_gemm_bf16(mid, hidden, w->w2, hidden, out, ldo, rows, hidden, hidden, w->b2, nullptr, 0, 0, LP_ACT_NONE, 0,

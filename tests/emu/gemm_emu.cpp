@@ -8,6 +8,7 @@ enum { LP_NORM_NONE = 0, LP_NORM_RMS = 1, LP_NORM_LAYER = 2 };
 #include "emu_helpers.inc"
 #include "gemm_kernel.inc"
 #include "gemm4_kernel.inc"
+#include "gemm_chain_kernel.inc"
 
 using namespace lp;
 
@@ -188,4 +189,33 @@ extern "C" void emu_gemm_tp(void* A, long long lda, const void* W, long long ldw
   CUtensorMap tmA = tmap2(A, K, M, lda, GEMM_BK, GEMM_BM, 2, 128);
   CUtensorMap tmB = tmap2(W, K, N, ldw, GEMM_BK, BN / 2, 2, 128);
   emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_bf16_tp_kernel<BN, 6, true>(tmA, tmB, segs, args); });
+}
+
+
+// Chained projector launch (lp_gemm_chain.cu): argument preparation as in launch_gemm_chain.  The emulator runs CTA pairs one after
+// another, so the cross-unit dataflow wait can only be exercised with ONE pair (ctas = 2); the work list, the two sets of tensor
+// maps, the per-layer epilogues and the counter protocol (publish / wait / re-zero) are what this checks.
+extern "C" void emu_gemm_chain(const void* X, long long ldx, const void* W1, const float* b1, int act1, void* mid, long long ld_mid,
+                               const void* W2, const float* b2, void* out, long long ldo, int M, int N1, int K1, int N2,
+                               unsigned* counters, int ctas) {
+  constexpr int BN = 256;
+  ChainArgs a = {};
+  a.M = M;
+  a.N[0] = N1; a.K[0] = K1; a.N[1] = N2; a.K[1] = N1;
+  a.num_m_blk = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  for (int l = 0; l < 2; ++l) {
+    a.num_n_blk[l] = (a.N[l] + BN - 1) / BN;
+    a.num_k_blk[l] = (a.K[l] + GEMM_BK - 1) / GEMM_BK;
+  }
+  a.bias[0] = b1; a.bias[1] = b2;
+  a.act[0] = act1; a.act[1] = LP_ACT_NONE;
+  a.row_done = counters + 1;
+  a.exit_count = counters;
+  CUtensorMap tmA1 = tmap2(X, K1, M, ldx, GEMM_BK, GEMM_BM, 2, 128);
+  CUtensorMap tmB1 = tmap2(W1, K1, N1, K1, GEMM_BK, BN / 2, 2, 128);
+  CUtensorMap tmC1 = tmap2(mid, N1, M, ld_mid, 32, 32, 2, 64);
+  CUtensorMap tmA2 = tmap2(mid, N1, M, ld_mid, GEMM_BK, GEMM_BM, 2, 128);
+  CUtensorMap tmB2 = tmap2(W2, N1, N2, N1, GEMM_BK, BN / 2, 2, 128);
+  CUtensorMap tmC2 = tmap2(out, N2, M, ldo, 32, 32, 2, 64);
+  emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_chain_kernel<BN, 6>(tmA1, tmB1, tmC1, tmA2, tmB2, tmC2, a); });
 }

@@ -41,7 +41,9 @@ def emu(tmp_path_factory):
     shared = shared.replace(named, "named_bar(1, 256, true);")
     k1 = kernel_part("leopard_b200/csrc/lp_gemm.cu", "template <int BN, int STAGES, bool CTA2>\nstatic int launch_gemm(")
     k4 = kernel_part("leopard_b200/csrc/lp_gemm4.cu", "#ifndef LP_EMULATE\ntemplate <int BN, int STAGES>\nstatic int launch4(")
-    assert "asm" not in shared + k1 + k4
+    kc = kernel_part("leopard_b200/csrc/lp_gemm_chain.cu", "#ifndef LP_EMULATE\n// counters live in")
+    assert "asm" not in shared + k1 + k4 + kc
+    (out / "gemm_chain_kernel.inc").write_text(kc + "\n}  // namespace lp\n")
     (out / "gemm_kernel.inc").write_text(shared + "\n" + k1 + "\n}  // namespace lp\n")
     (out / "gemm4_kernel.inc").write_text(k4 + "\n}  // namespace lp\n")
     lib = out / "libgemm.so"
@@ -382,3 +384,29 @@ def test_tma_residual_ring_matches_the_register_path(emu, M, N, K, bn, ctas, bia
     assert torch.equal(outs[0], outs[1])
     if stats:
         assert torch.equal(sts[0], sts[1])
+
+
+# ---- chained projector (lp_gemm_chain.cu): both layers in one persistent launch -------------------------------------------------
+@pytest.mark.parametrize("M,K1,N1,N2,act", [(300, 200, 512, 256, 2), (169, 136, 264, 520, 1)])
+def test_chained_projector_kernel_under_emulation(emu, M, K1, N1, N2, act):
+    g = torch.Generator().manual_seed(M + N1)
+    x = torch.randn((M, K1), generator=g).to(BF)
+    w1 = (torch.randn((N1, K1), generator=g) * K1 ** -0.5).to(BF)
+    w2 = (torch.randn((N2, N1), generator=g) * N1 ** -0.5).to(BF)
+    b1, b2 = torch.randn(N1, generator=g), torch.randn(N2, generator=g)
+    mid = torch.full((M, N1), float("nan"), dtype=BF)
+    out = torch.full((M, N2), float("nan"), dtype=BF)
+    counters = torch.zeros(64, dtype=torch.int32)
+    emu.emu_gemm_chain(P(x), LL(K1), P(w1), P(b1), act, P(mid), LL(N1), P(w2), P(b2), P(out), LL(N2), M, N1, K1, N2, P(counters), 2)
+    want_mid = ref.gemm(x, w1, bias=b1, act=act)
+    want = ref.gemm(want_mid, w2, bias=b2)
+    assert not bool(torch.isnan(out.float()).any())
+    assert float((mid.float() - want_mid.float()).abs().max() / want_mid.float().abs().max()) < 8e-3
+    assert float((out.float() - want.float()).abs().max() / want.float().abs().max()) < 1.2e-2
+    assert int(counters.abs().sum()) == 0          # the last CTA re-zeroed the dataflow counters
+    # the chained launch is the two plain launches fused: same bits
+    mid2 = torch.full((M, N1), float("nan"), dtype=BF)
+    out2 = torch.full((M, N2), float("nan"), dtype=BF)
+    emu.emu_gemm(P(x), LL(K1), P(w1), LL(K1), P(mid2), LL(N1), M, N1, K1, P(b1), None, LL(0), 0, act, 0, 256, 1, 1, 2)
+    emu.emu_gemm(P(mid2), LL(N1), P(w2), LL(N1), P(out2), LL(N2), M, N2, N1, P(b2), None, LL(0), 0, 0, 0, 256, 1, 1, 2)
+    assert torch.equal(mid, mid2) and torch.equal(out, out2)

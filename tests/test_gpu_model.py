@@ -58,6 +58,32 @@ def test_projector(small):
     assert e < 1.5e-2
 
 
+@pytest.mark.parametrize("crops", [1, 3, 28])
+def test_projector_single_kernel_equals_two_launches(small, crops):
+    """lp_project as ONE chained kernel (both GEMMs in a persistent launch with dataflow counters, lp_gemm_chain.cu) against the
+    two-launch sequence: same bits, repeated launches leave the counters clean, and it really is a single launch."""
+    cfg, ck, eng = small
+    from leopard_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(crops)
+    x = torch.randn(crops * 169, 4608, generator=g).to(torch.bfloat16).cuda()
+    try:
+        L.lp_model_set_chained_projector(0)
+        n0 = L.lp_launch_count()
+        two = eng.project(x).clone()
+        n_two = L.lp_launch_count() - n0
+        L.lp_model_set_chained_projector(1)
+        n0 = L.lp_launch_count()
+        one = eng.project(x).clone()
+        n_one = L.lp_launch_count() - n0
+        again = eng.project(x).clone()
+    finally:
+        L.lp_model_set_chained_projector(1)
+    torch.cuda.synchronize()
+    assert (n_two, n_one) == (2, 1)
+    assert torch.equal(one, two) and torch.equal(again, two)
+
+
 def test_decoder_all_logits_and_kv(small):
     cfg, ck, eng = small
     g = torch.Generator().manual_seed(6)

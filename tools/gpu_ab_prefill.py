@@ -33,6 +33,8 @@ def apply(setting):
         L.lp_norm_set_variant(v)
     elif k == "fused":
         L.lp_model_set_fused_norm(v)
+    elif k == "chain":
+        L.lp_model_set_chained_projector(v)
     elif k == "sk":
         L.lp_gemm_set_streamk(v)
     elif k == "tmares":
