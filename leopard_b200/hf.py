@@ -193,6 +193,46 @@ class _NativeParameters(nn.Module):
             self.register_parameter(attr, nn.Parameter(t, requires_grad=False))
 
 
+def plan_padded_batch(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], image_id: int, rows_per_image: int):
+    """Host plan of HF's `_merge_input_ids_with_image_features` for a padded batch (transformers 4.38-4.4x algorithm, SURVEY.md
+    App. A.1 steps 1-3; the reference's forward calls it at …anyres.py:285-287).  Padding is removed instead of masked: the rows the
+    attention mask keeps of batch row b form one packed sequence of S_b = kept ids + (rows_per_image - 1) per image placeholder,
+    with positions 0 .. S_b - 1 (= cumsum(mask) - 1 of step 4), and land in the merged [B, max_len] layout at offset off_b:
+    left padding -> right-aligned (new_pos += nb_image_pad), right padding -> left-aligned.
+    Returns (max_len, left_padding, [(t0, t1, n_images, S_b, off_b), ...])."""
+    B, L = input_ids.shape
+    ids = input_ids.cpu()
+    mask = torch.ones_like(ids, dtype=torch.bool) if attention_mask is None else attention_mask.cpu().bool()
+    if mask.shape != ids.shape:
+        raise ValueError(f"attention_mask {tuple(mask.shape)} does not match input_ids {tuple(ids.shape)}")
+    n_img = (ids == image_id).sum(-1)
+    max_len = int(n_img.max()) * (rows_per_image - 1) + L
+    left_padding = bool(mask[:, -1].all())          # HF: not any(input_ids[:, -1] == pad_token_id)
+    rows = []
+    for b in range(B):
+        keep = torch.nonzero(mask[b]).flatten()
+        if keep.numel() == 0:
+            raise ValueError(f"batch row {b} is all padding")
+        t0, t1 = int(keep[0]), int(keep[-1]) + 1
+        if t1 - t0 != keep.numel():
+            raise NotImplementedError(f"batch row {b}: padding inside the prompt is outside what HF's merge supports")
+        if bool(((ids[b] == image_id) & ~mask[b]).any()):
+            raise ValueError(f"batch row {b}: image placeholder under the padding mask")
+        if left_padding and t1 != L:
+            raise NotImplementedError("mixed left / right padding in one batch")
+        if not left_padding and t0 != 0:
+            raise NotImplementedError("mixed left / right padding in one batch")
+        nb = int(n_img[b])
+        if not left_padding and nb != int(n_img.max()):
+            # HF's step 3 drops the FIRST nb_image_pad empty positions of a row, which under right padding are real image rows:
+            # its own output is misplaced there ("breaks batch generation"); refuse instead of reproducing it
+            raise NotImplementedError("right-padded batches need the same number of images in every row (use left padding, as "
+                                      "HF's batched generation does)")
+        S_b = (t1 - t0) + nb * (rows_per_image - 1)
+        rows.append((t0, t1, nb, S_b, max_len - S_b if left_padding else 0))
+    return max_len, left_padding, rows
+
+
 class myLlavaForConditionalGeneration(nn.Module):
     """Native-backed stand-in for the reference class of the same name (…anyres.py:195-361).  An `nn.Module` like the
     `LlavaForConditionalGeneration` it replaces: `parameters()` / `named_parameters()` enumerate the kernel-layout weights,
@@ -395,10 +435,10 @@ class myLlavaForConditionalGeneration(nn.Module):
             out = self.language_model(inputs_embeds=inputs_embeds, position_ids=position_ids, use_cache=use_cache)
             logits, past = out.logits, out.past_key_values
         else:
-            if input_ids.dim() != 2 or input_ids.shape[0] != 1:
-                raise NotImplementedError("the reference eval path is B = 1, no padding (SURVEY.md App. A.1)")
-            if attention_mask is not None and not bool(attention_mask.all()):
-                raise NotImplementedError("padded prompts are outside the reference's usage (…anyres.py:443-446)")
+            if input_ids.dim() != 2:
+                raise ValueError("input_ids must be [B, L]")
+            if input_ids.shape[0] != 1 or (attention_mask is not None and not bool(attention_mask.all())):
+                return self._forward_padded_batch(input_ids, pixel_values, attention_mask, labels, use_cache, return_dict)
             pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
             ids = input_ids.to(eng.device, non_blocking=True)
             if self._precision == "fp32" and not use_cache:
@@ -424,6 +464,38 @@ class myLlavaForConditionalGeneration(nn.Module):
             return tuple(v for v in (loss, logits, past) if v is not None)
         return LlavaCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past)
 
+    def _forward_padded_batch(self, input_ids, pixel_values, attention_mask, labels, use_cache, return_dict):
+        """B > 1 and / or padded prompts: HF's batched merge (plan_padded_batch) on the packed engine — every batch row is one
+        packed decoder sequence without its padding, all crops go through the tower in one batch, and the logits are scattered
+        back into the merged [B, max_len, V] layout (zeros at padded rows, which HF fills with values nobody reads)."""
+        eng = self._eng()
+        if use_cache:
+            raise NotImplementedError("use_cache with a padded batch: generate() drives batched decoding row by row")
+        if labels is not None:
+            raise NotImplementedError("labels with a padded batch")
+        if self._precision == "fp32":
+            raise NotImplementedError("parity mode is B = 1")
+        cfg = self.config
+        max_len, _, rows = plan_padded_batch(input_ids, attention_mask, cfg.image_token_index, cfg.tokens_per_crop)
+        n_total = sum(r[2] for r in rows)
+        n_given = 0 if pixel_values is None else int(pixel_values.shape[0])
+        if n_total != n_given:
+            raise ValueError(
+                f"The input provided to the model are wrong. The number of image tokens is {n_total} while "
+                f"the number of image given to the model is {n_given}. This prevents correct indexing and breaks batch generation.")
+        pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
+        samples, c0 = [], 0
+        for b, (t0, t1, nb, _, _) in enumerate(rows):
+            samples.append((input_ids[b, t0:t1], pix[c0:c0 + nb] if nb else None))
+            c0 += nb
+        packed, _, cu = eng.prefill(samples, "all", torch.float32, slots=[r[2] for r in rows])
+        logits = torch.zeros((len(rows), max_len, packed.shape[-1]), dtype=packed.dtype, device=packed.device)
+        for b, (_, _, _, S_b, off) in enumerate(rows):
+            logits[b, off:off + S_b] = packed[cu[b]:cu[b + 1]]
+        if return_dict is False:
+            return (logits,)
+        return LlavaCausalLMOutputWithPast(logits=logits)
+
     # ------------------------------------------------------------------ generate (greedy, as the reference calls it)
     @torch.no_grad()
     def generate(self, input_ids, pixel_values=None, attention_mask=None, pad_token_id=None, eos_token_id=None,
@@ -431,11 +503,13 @@ class myLlavaForConditionalGeneration(nn.Module):
         """Greedy decoding; returns LongTensor [1, L_in + n_new] (prompt included, un-expanded — the caller slices
         `[:, L_in:]`, …anyres.py:453-454).  Prefill emits only the last row's logits (lp_decoder_prefill LAST mode)."""
         eng = self._eng()
-        if input_ids.dim() != 2 or input_ids.shape[0] != 1:
-            raise NotImplementedError("the reference eval path is B = 1")
+        if input_ids.dim() != 2:
+            raise ValueError("input_ids must be [B, L]")
         eos = set()
         if eos_token_id is not None:
             eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else {int(eos_token_id)}
+        if input_ids.shape[0] != 1 or (attention_mask is not None and not bool(attention_mask.all())):
+            return self._generate_padded_batch(input_ids, pixel_values, attention_mask, pad_token_id, eos, max_new_tokens)
         ids = input_ids.to(eng.device, non_blocking=True)
         pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
         from .decode import GreedyDecoder
@@ -443,3 +517,30 @@ class myLlavaForConditionalGeneration(nn.Module):
         # the ids the CALLER holds (normally host memory) plan the merge: counting placeholders there costs no device sync
         new_tokens = dec.run(input_ids[0], pix, max_new_tokens, eos)
         return torch.cat([ids, new_tokens[None]], dim=1)
+
+    def _generate_padded_batch(self, input_ids, pixel_values, attention_mask, pad_token_id, eos, max_new_tokens):
+        """Batched greedy generation the way GenerationMixin returns it: [B, L + longest continuation], rows that stopped early are
+        filled with pad_token_id.  Every row is prefilled without its padding and decoded over its own KV cache (the decode kernels
+        are single-sequence: rows run one after another)."""
+        eng = self._eng()
+        cfg = self.config
+        _, _, rows = plan_padded_batch(input_ids, attention_mask, cfg.image_token_index, cfg.tokens_per_crop)
+        if sum(r[2] for r in rows) != (0 if pixel_values is None else int(pixel_values.shape[0])):
+            raise ValueError("The input provided to the model are wrong: image placeholders and pixel_values disagree")
+        if pad_token_id is None:
+            if len(eos) == 0:
+                raise ValueError("batched generate needs pad_token_id (or an eos id to pad with)")
+            pad_token_id = min(eos)
+        pix = None if pixel_values is None else pixel_values.to(eng.device, non_blocking=True)
+        from .decode import GreedyDecoder
+        dec = GreedyDecoder(eng)
+        outs, c0 = [], 0
+        for b, (t0, t1, nb, _, _) in enumerate(rows):
+            outs.append(dec.run(input_ids[b, t0:t1], pix[c0:c0 + nb] if nb else None, max_new_tokens, eos))
+            c0 += nb
+        n_new = max(o.numel() for o in outs)
+        full = torch.full((len(rows), input_ids.shape[1] + n_new), int(pad_token_id), dtype=torch.long, device=eng.device)
+        full[:, : input_ids.shape[1]] = input_ids.to(eng.device)
+        for b, o in enumerate(outs):
+            full[b, input_ids.shape[1]: input_ids.shape[1] + o.numel()] = o
+        return full

@@ -125,6 +125,47 @@ def merge_hf_expand(ck, cfg, input_ids: torch.Tensor, image_features: torch.Tens
     return out, pos
 
 
+def merge_hf_batched(ck, cfg, input_ids: torch.Tensor, attention_mask: torch.Tensor, image_features: torch.Tensor,
+                     pad_token_id: int):
+    """HF `_merge_input_ids_with_image_features` for a padded batch, restated step by step from SURVEY.md App. A.1 (the
+    transformers 4.38-4.4x algorithm the reference's forward calls at EV/...anyres.py:285-287; "parity unpinned": the source
+    is in neither tree).  input_ids / attention_mask [B, L], image_features [N, P, D].  Returns (final_embedding [B, max_len, D],
+    final_attention_mask [B, max_len], position_ids [B, max_len])."""
+    table = ck.f32(LM + "embed_tokens.weight")
+    n, p, d = image_features.shape
+    B, L = input_ids.shape
+    inputs_embeds = table[input_ids.clamp(min=0)]
+    m = input_ids == cfg.image_token_index
+    # 1. target positions
+    max_len = int(m.sum(-1).max()) * (p - 1) + L
+    new_pos = torch.cumsum(m.long() * (p - 1) + 1, -1) - 1
+    nb_image_pad = max_len - 1 - new_pos[:, -1]
+    left_padding = not bool((input_ids[:, -1] == pad_token_id).any())
+    if left_padding:
+        new_pos = new_pos + nb_image_pad[:, None]
+    # 2. text tokens
+    final_embedding = torch.zeros(B, max_len, d)
+    final_mask = torch.zeros(B, max_len, dtype=torch.long)
+    bi, ti = torch.where(~m)
+    final_embedding[bi, new_pos[bi, ti]] = inputs_embeds[bi, ti]
+    final_mask[bi, new_pos[bi, ti]] = attention_mask[bi, ti].long()
+    # 3. image rows: the still-empty positions past the image padding, filled in row-major order
+    image_rows = torch.ones(B, max_len, dtype=torch.bool)
+    image_rows[bi, new_pos[bi, ti]] = False
+    image_rows &= (image_rows.long().cumsum(-1) - 1) >= nb_image_pad[:, None]
+    if int(image_rows.sum()) != n * p:
+        raise ValueError(
+            f"The input provided to the model are wrong. The number of image tokens is {int(m.sum())} while "
+            f"the number of image given to the model is {n}. This prevents correct indexing and breaks batch generation.")
+    final_embedding[image_rows] = image_features.reshape(-1, d)
+    final_mask |= image_rows.long()
+    # 4. positions; rows of pad tokens are zeroed again
+    position_ids = (final_mask.cumsum(-1) - 1).masked_fill(final_mask == 0, 1)
+    pb, pt = torch.where(input_ids == pad_token_id)
+    final_embedding[pb, new_pos[pb, pt]] = 0
+    return final_embedding, final_mask, position_ids
+
+
 def merge_megatron_scatter(ck, cfg, input_ids: torch.Tensor, image_features: torch.Tensor):
     """Megatron convention (MP/model/llava/vlm_model.py:516-533): ids hold one -200 per feature ROW; embeddings of
     clamp(ids, 0) are overwritten, in row-major order, by image_features.view(-1, D)."""
@@ -230,6 +271,25 @@ def decoder_forward(ck, cfg, embeds: torch.Tensor, position_ids: torch.Tensor, l
     if last_only:
         x = x[-1:]
     return F.linear(x, ck.f32("language_model.lm_head.weight"))
+
+
+@torch.no_grad()
+def prefill_logits_batched(ck, cfg, input_ids: torch.Tensor, attention_mask: torch.Tensor, pixel_values: torch.Tensor,
+                           pad_token_id: int):
+    """Padded batch through the HF forward (EV/...anyres.py:263-333): merge_hf_batched, then the decoder per batch row on the rows
+    the attention mask keeps, at the merge's position ids — masked keys get an exactly-zero softmax weight in the fp32 reference,
+    so the kept rows see the same arithmetic as in the padded [B, max_len] call.  Returns (logits [B, max_len, V] with zeros at
+    masked rows, final_attention_mask)."""
+    feats = projector(ck, cfg, vit_forward(ck, cfg, pixel_values))
+    emb, mask, pos = merge_hf_batched(ck, cfg, input_ids, attention_mask, feats, pad_token_id)
+    out = None
+    for b in range(emb.shape[0]):
+        keep = mask[b].bool()
+        lg = decoder_forward(ck, cfg, emb[b][keep], pos[b][keep])
+        if out is None:
+            out = torch.zeros(emb.shape[0], emb.shape[1], lg.shape[-1])
+        out[b][keep] = lg
+    return out, mask
 
 
 # ----------------------------------------------------------------------------------------------------------------

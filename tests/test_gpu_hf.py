@@ -185,3 +185,39 @@ def test_megatron_provider_matches_oracle(small):
     ref_loss = torch.nn.functional.cross_entropy(ref.float(), labels[0], ignore_index=-100, reduction="none")
     assert loss.shape == (1, s) and float((loss[0].cpu() - ref_loss).abs().max()) < 0.08
     assert bool((loss[0, 5:20] == 0).all())
+
+
+def test_padded_batch_forward_and_generate_follow_the_hf_merge(small):
+    """B = 3 left-padded batch with 1 / 2 / 0 images (HF's batched-generation layout): logits of the merged
+    [B, max_len, V] layout against the oracle's restatement of the HF merge + decoder; every kept row of a batch row equals the
+    same prompt run alone (packing / padding invariance, bit for bit); batched generate == per-row generate, padded with
+    pad_token_id."""
+    cfg, ck, model = small
+    PAD = 0
+    pixA, idsA = synth_inputs(cfg, n_crops=1, n_text=10, seed=21)
+    pixB, idsB = synth_inputs(cfg, n_crops=2, n_text=14, seed=22)
+    _, idsC = synth_inputs(cfg, n_crops=0, n_text=6, seed=23)
+    rows = [idsA[0].clamp(min=1), idsB[0].clamp(min=1), idsC[0].clamp(min=1)]       # no accidental pad ids inside the prompts
+    L = max(r.numel() for r in rows)
+    ids = torch.full((3, L), PAD, dtype=torch.long)
+    for b, r in enumerate(rows):
+        ids[b, L - r.numel():] = r
+    mask = (ids != PAD).long()
+    pix = torch.cat([pixA, pixB], 0)
+    out = model(input_ids=ids, pixel_values=pix, attention_mask=mask)
+    want, fmask = om.prefill_logits_batched(ck, cfg, ids, mask, pix.to(torch.bfloat16).float(), PAD)
+    assert out.logits.shape == want.shape
+    keep = fmask.bool()
+    assert rel_err(out.logits.cpu()[keep], want[keep]) < 3e-2
+    assert float(out.logits.cpu()[~keep].abs().max()) == 0.0
+    # each row alone (B = 1, no padding) gives the same bits on its kept rows
+    alone = model(input_ids=rows[1][None], pixel_values=pixB).logits[0]
+    assert torch.equal(out.logits[1, -alone.shape[0]:], alone)
+    # batched greedy generation
+    gen = model.generate(ids, pixel_values=pix, attention_mask=mask, pad_token_id=PAD, eos_token_id=[2047], max_new_tokens=3)
+    assert gen.shape == (3, L + 3) and torch.equal(gen[:, :L].cpu(), ids)
+    one = model.generate(rows[0][None], pixel_values=pixA, eos_token_id=[2047], max_new_tokens=3)
+    assert torch.equal(gen[0, L:], one[0, rows[0].numel():])
+    # mismatch between placeholders and crops is the reference's ValueError
+    with pytest.raises(ValueError):
+        model(input_ids=ids, pixel_values=pix[:2], attention_mask=mask)

@@ -410,3 +410,57 @@ def test_checkpoint_export_reads_the_live_trained_tensors():
     h4 = flat1["encoder.layers.0.mlp.dense_h_to_4h.weight"]           # [gate ; up]
     assert float(h4[cfg.dec.ffn].float().min()) == 0.5 and torch.equal(h4[: cfg.dec.ffn], flat0["encoder.layers.0.mlp.dense_h_to_4h.weight"][: cfg.dec.ffn])
     assert float(flat1["mm_projector.encoder.linear_fc2.bias"][7]) == 0.25
+
+
+def test_padded_batch_plan_reproduces_the_hf_merge_layout():
+    """plan_padded_batch (leopard_b200/hf.py) against the oracle's step-by-step restatement of HF's
+    `_merge_input_ids_with_image_features`: same max_len, the kept rows of every batch row land exactly where
+    HF's final_attention_mask is 1, positions 0 .. S_b - 1, image features consumed in batch-row order."""
+    import pytest
+    from types import SimpleNamespace as NS
+    from leopard_b200.hf import plan_padded_batch
+    from oracle import model as om
+    IMG, PAD, P, D = 7, 0, 5, 4
+    cfg = NS(image_token_index=IMG)
+    table = torch.arange(20 * D, dtype=torch.float32).view(20, D) + 1
+    ck = NS(f32=lambda name: table)
+
+    def check(ids, mask):
+        n = int((ids == IMG).sum())
+        feats = 1000 + torch.arange(n * P * D, dtype=torch.float32).view(n, P, D)
+        emb, fmask, pos = om.merge_hf_batched(ck, cfg, ids, mask, feats, PAD)
+        max_len, left, rows = plan_padded_batch(ids, mask, IMG, P)
+        assert max_len == emb.shape[1]
+        k = 0
+        for b, (t0, t1, nb, S_b, off) in enumerate(rows):
+            want = torch.zeros(max_len, dtype=torch.long)
+            want[off:off + S_b] = 1
+            assert torch.equal(fmask[b], want), (b, fmask[b], want)
+            assert torch.equal(pos[b, off:off + S_b], torch.arange(S_b))
+            # what the packed engine builds for this row: kept ids with every placeholder expanded to its crop's P rows
+            packed = []
+            for t in range(t0, t1):
+                if int(ids[b, t]) == IMG:
+                    packed.append(feats[k]); k += 1
+                else:
+                    packed.append(table[int(ids[b, t])][None])
+            assert torch.equal(torch.cat(packed, 0), emb[b, off:off + S_b])
+        return left
+
+    # left padding, unequal image counts (the batched-generation case)
+    ids = torch.tensor([[PAD, PAD, 3, IMG, 4, 5], [2, IMG, 3, IMG, 9, 6], [PAD, PAD, PAD, 8, 9, 11]])
+    assert check(ids, (ids != PAD).long()) is True
+    # right padding with the same number of images per row
+    ids = torch.tensor([[3, IMG, 4, PAD, PAD], [2, IMG, 3, 9, 6]])
+    assert check(ids, (ids != PAD).long()) is False
+    # B = 1 without a mask reduces to the expansion the reference uses
+    ids = torch.tensor([[3, IMG, 4, IMG]])
+    check(ids, torch.ones_like(ids))
+    # refused: right padding with unequal image counts (HF's own step 3 misplaces the rows), holes, placeholders under the mask
+    ids = torch.tensor([[3, IMG, 4, PAD, PAD], [2, IMG, 3, IMG, 6]])
+    with pytest.raises(NotImplementedError):
+        plan_padded_batch(ids, (ids != PAD).long(), IMG, P)
+    with pytest.raises(NotImplementedError):
+        plan_padded_batch(torch.tensor([[1, PAD, 2, 3]]), torch.tensor([[1, 0, 1, 1]]), IMG, P)
+    with pytest.raises(ValueError):
+        plan_padded_batch(torch.tensor([[IMG, 2, 3]]), torch.tensor([[0, 1, 1]]), IMG, P)
