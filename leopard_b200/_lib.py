@@ -207,6 +207,8 @@ def ensure_streamk_workspace(device=None):
     if os.environ.get("LEOPARD_STREAMK", "1") == "0" or not torch.cuda.is_available():
         return None
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.index is None:                   # "cuda" and "cuda:<current>" are the same device
+        dev = torch.device("cuda", torch.cuda.current_device())
     if _streamk_ws is not None:
         if _streamk_ws.device != dev:      # a second device in one process: the single workspace cannot serve both
             check(L.lp_gemm_set_streamk_workspace(None, 0), "lp_gemm_set_streamk_workspace")
