@@ -609,6 +609,39 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// same update, four parameters per thread with 16-byte accesses (30 B of HBM traffic per parameter: the scalar kernel above reached
+// 4.3 TB/s of the 6.5 TB/s the part copies at); element-wise arithmetic identical to adamw_kernel
+__global__ void __launch_bounds__(256)
+adamw_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                  uint2* __restrict__ p16, long long n4, float lr, float b1, float b2, float eps, float wd, float inv_bc1,
+                  float inv_bc2, const float* __restrict__ clip) {
+  if (clip != nullptr && !(clip[0] < INFINITY)) return;
+  const float cs = clip != nullptr ? clip[1] : 1.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 g4 = g[i];
+    float4 m4 = m[i], v4 = v[i], p4 = p[i];
+#define LP_ADAMW_ONE(C)                                                                   \
+    {                                                                                     \
+      const float gi = g4.C * cs;                                                         \
+      m4.C = b1 * m4.C + (1.f - b1) * gi;                                                 \
+      v4.C = b2 * v4.C + (1.f - b2) * gi * gi;                                            \
+      p4.C -= lr * (m4.C * inv_bc1 / (sqrtf(v4.C * inv_bc2) + eps) + wd * p4.C);          \
+    }
+    LP_ADAMW_ONE(x) LP_ADAMW_ONE(y) LP_ADAMW_ONE(z) LP_ADAMW_ONE(w)
+#undef LP_ADAMW_ONE
+    m[i] = m4;
+    v[i] = v4;
+    p[i] = p4;
+    if (p16 != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      p16[i] = u;
+    }
+  }
+}
+
 }  // namespace lp
 
 using namespace lp;
@@ -861,6 +894,14 @@ extern "C" int lp_adamw_step(float* p, const float* g, float* m, float* v, void*
   const float inv_bc1 = (float)(1.0 / (1.0 - pow((double)beta1, (double)step)));
   const float inv_bc2 = (float)(1.0 / (1.0 - pow((double)beta2, (double)step)));
   note_launch();
+  if (n % 4 == 0 && al16(p) && al16(g) && al16(m) && al16(v) && (p_bf16 == nullptr || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0)) {
+    adamw_vec4_kernel<<<grid_for(n / 4), 256, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                                            reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                                            reinterpret_cast<uint2*>(p_bf16), n / 4, lr, beta1, beta2, eps,
+                                                            weight_decay, inv_bc1, inv_bc2, norm_and_clip);
+    LP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, lr, beta1, beta2, eps,
                                                 weight_decay, inv_bc1, inv_bc2, norm_and_clip);
   LP_CHECK_CUDA(cudaGetLastError());

@@ -177,6 +177,17 @@ def test_grad_norm_adamw_accumulate(emu):
         emu.emu_adamw(P(pd), P(g), P(md), P(vd), P(p16), LL(1001), F(1e-3), F(0.9), F(0.999), F(1e-8), F(0.01), F(1.0), F(1.0),
                       P(bad_norm), I(2))
         assert all(torch.equal(x, y) for x, y in zip((pd, md, vd, p16), keep))
+    # the 16-byte variant (what lp_adamw_step launches for aligned tensors of 4 k elements) == the scalar kernel, bit for bit
+    n4 = 2052
+    p0, g0 = rnd(n4, seed=21, dtype=torch.float32), rnd(n4, seed=22, dtype=torch.float32)
+    res = []
+    for fn in (emu.emu_adamw, emu.emu_adamw_vec4):
+        pp, mm, vv, pb = p0.clone(), torch.full((n4,), 0.01), torch.full((n4,), 0.02), torch.empty(n4, dtype=BF)
+        for step in (1, 2):
+            fn(P(pp), P(g0), P(mm), P(vv), P(pb), LL(n4), F(1e-3), F(0.9), F(0.999), F(1e-8), F(0.01), F(1 / (1 - 0.9 ** step)),
+               F(1 / (1 - 0.999 ** step)), P(clip), I(2))
+        res.append((pp, mm, vv, pb))
+    assert all(torch.equal(x, y) for x, y in zip(*res))
     a, b = rnd(1003, seed=7, dtype=torch.float32), rnd(1003, seed=8, dtype=torch.float32)
     want = a + b
     emu.emu_accumulate(P(a), P(b), LL(1003), I(2))

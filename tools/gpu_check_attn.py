@@ -20,6 +20,7 @@ CASES = {
     "dec_2937_c": (1, 2937, 32, 8, 128, 128, True),
     "dec_4796_c": (1, 4796, 32, 8, 128, 128, True),
     "vit_28": (28, 676, 16, 16, 72, 80, False),
+    "vit_4900": (8, 4900, 16, 16, 72, 80, False),      # cfg4: Idefics2 NaViT tower, 8 images of 980 x 980
 }
 
 
