@@ -1,0 +1,176 @@
+#!/bin/bash
+# Every GPU call of round 2 as it was issued (`gpurun -- 'bash tools/gpu_runs_r02.sh <run>'`), one shell function per call; the files
+# under profiles/ carry the run's tag as prefix (r02a_* ... r02l_*).  The round's final evidence run is tools/gpu_evidence_r02.sh, the
+# N-GPU runs tools/gpu_multi_r02.sh.  Kept as the record of how each number in DESIGN.md / profiles/ was produced.
+mkdir -p gpurun_out
+run() { local name=$1; shift; echo "== $name"; timeout "${TMO:-600}" "$@" > gpurun_out/${T}_${name}.log 2>&1; echo "   exit $?"; tail -c ${TAIL:-1200} gpurun_out/${T}_${name}.log; echo; }
+
+round2_first() {
+  # First GPU call of the next round: everything that was written after round 1's GPU budget ran out, in the order that
+  # localises a failure fastest.  Usage:  gpurun --timeout 2400 -- 'bash tools/gpu_round2_first.sh'
+  # Each stage runs in its own process (a trapped kernel poisons only its stage) and writes one log under gpurun_out/.
+  T=${TAG:-r02a}
+  ZZ=tests/test_zz_gpu_train.py
+  # 1. per-kernel parity of lp_train.cu (element-wise / reduction kernels; emulation-green already)
+  run kernels   python -m pytest $ZZ --runxfail -q -x -k "transpose or rmsnorm or swiglu or colsum or masked_loss or softmax_backward or grad_norm or vision_tower_backward_kernels"
+  # 2. whole step, materialised attention backward, frozen and trainable tower, against autograd
+  run step_mat  python -m pytest $ZZ --runxfail -q -x -k "whole_sft_step_against_autograd or trainable_vision_tower"
+  # 3. flash backward kernels (tcgen05) — per case, so that one wedged configuration does not hide the others
+  for k in "1-128-4-1-True" "2-200-8-2-True" "1-384-4-4-False" "1-1024-8-2-True"; do
+    run flash_$k python -m pytest $ZZ --runxfail -q -k "closed_form and $k"
+  done
+  run flash_vit python -m pytest $ZZ --runxfail -q -k "vision_tower_layout"
+  run step_flash python -m pytest $ZZ --runxfail -q -k "flash_backward_matches_materialised"
+  # 4. first timings: 4 decoder layers, then the full model, both attention-backward routes
+  TMO=900 run speed_l4_mat   python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
+  LEOPARD_ATTN_BWD=flash TMO=900 run speed_l4_flash python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
+  LEOPARD_ATTN_BWD=flash TMO=1500 run speed_full_flash python tools/gpu_train_speed.py --steps 2
+  # recompute on / off at 16 layers (the full model + kept activations needs ~172 GB: too close to the 180 GB for a first run)
+  LEOPARD_ATTN_BWD=flash TMO=900 run speed_l16_flash_full python tools/gpu_train_speed.py --layers 16 --steps 2
+  LEOPARD_ATTN_BWD=flash TMO=900 run speed_l16_flash_none python tools/gpu_train_speed.py --layers 16 --steps 2 --recompute none
+  # 4b. the 4-CTA multicast GEMM (lp_gemm4.cu): correctness sweep + timing against the pair kernel, then the prefill A/B
+  TMO=600 run gemm_quad_eq python -m pytest $ZZ --runxfail -q -k four_cta_multicast
+  TMO=900 run gemm_quad python tools/gpu_check_gemm.py --quad --time
+  TMO=900 run gemm_pair python tools/gpu_check_gemm.py --pair --time
+  TMO=900 run ab_quad python tools/gpu_ab_prefill.py pair=1 pair=2
+  # 5. the example loop (Megatron-shim surface) and the regression suite
+  TMO=900 run example python examples/llava_sft_loop.py --layers 2 --iters 4
+  TMO=1500 run suite python -m pytest tests -m gpu -q -x
+  # 6. launch list of one 4-layer step (share of GEMM / transpose / attention-backward / optimizer)
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${T}_sft_launches.csv \
+      python tools/gpu_train_speed.py --layers 4 --vit-layers 2 --steps 0 > gpurun_out/${T}_sft_prof.log 2>&1
+  python tools/ncu_launch_agg.py gpurun_out/${T}_sft_launches.csv > gpurun_out/${T}_sft_launch_agg.txt 2>&1; head -30 gpurun_out/${T}_sft_launch_agg.txt
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02a() {
+  # Round 2, first GPU call: what round 1 wrote after its GPU budget ran out (SFT step, flash backward, 4-CTA GEMM).
+  # Usage: gpurun --timeout 1800 -- 'bash tools/gpu_r02a.sh'
+  T=${TAG:-r02a}
+  ZZ=tests/test_zz_gpu_train.py
+  nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.log 2>&1
+  run train_tests python -m pytest $ZZ --runxfail -q -rA --tb=long
+  TMO=600 run speed_l4_mat   python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
+  LEOPARD_ATTN_BWD=flash TMO=600 run speed_l4_flash python tools/gpu_train_speed.py --layers 4 --vit-layers 27 --steps 2
+  LEOPARD_ATTN_BWD=flash TMO=900 run speed_full_flash python tools/gpu_train_speed.py --steps 2
+  LEOPARD_ATTN_BWD=flash TMO=600 run speed_l16_flash_none python tools/gpu_train_speed.py --layers 16 --steps 2 --recompute none
+  TMO=600 run gemm_quad python tools/gpu_check_gemm.py --quad --time
+  TMO=600 run gemm_pair python tools/gpu_check_gemm.py --pair --time
+  TMO=600 run ab_quad python tools/gpu_ab_prefill.py pair=1 pair=2
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02b() {
+  # Round 2, second GPU call: SFT suite after the fixes + ncu --set full captures (with source) of the kernels VERDICT r1 names:
+  # the short-K ViT GEMMs with a residual epilogue and the ViT attention.
+  T=${TAG:-r02b}
+  run train_tests python -m pytest tests/test_zz_gpu_train.py -q -rA --tb=short
+  NCU="ncu --set full --clock-control none --import-source on"
+  for c in v_out v_fc2 v_patch v_qkv; do
+    TMO=300 run ncu_gemm_$c $NCU -k regex:gemm_bf16 -s 1 -c 1 -o gpurun_out/${T}_gemm_$c -f python tools/gpu_check_gemm.py --pair --case $c
+  done
+  TMO=300 run ncu_attn_vit $NCU -k regex:attn3 -s 1 -c 1 -o gpurun_out/${T}_attn_vit -f python tools/gpu_check_attn.py --case vit_28 --variant 80 --time
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02c() {
+  # Round 2, third GPU call: new bench legs (library GPU competitor, strong scaling at N=1, cfg2 / cfg4 / cfg5 workloads, bounded CPU
+  # arm), full-depth oracle fixtures for cfg2 / cfg3, ncu captures of the short-K ViT GEMMs.
+  T=${TAG:-r02c}
+  run bench_n1 python bench.py --steps 10 --warmup 3
+  run bench_ref python bench.py --impl reference --steps 3 --warmup 1
+  run bench_cfg2 python bench.py --workload cfg2 --steps 10 --no-cpu-baseline
+  run bench_cfg4 python bench.py --workload cfg4 --steps 5
+  run bench_cfg5 python bench.py --workload cfg5 --steps 3
+  run bench_cfg5_frozen python bench.py --workload cfg5 --steps 3 --sft-freeze-vit
+  TMO=1500 run fullsize python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_model.py -q -s -k "full_depth" 
+  NCU="ncu --set full --clock-control none --import-source on"
+  for c in v_out v_fc2 v_patch d_o; do
+    TMO=300 run ncu_gemm_$c $NCU -k regex:gemm_bf16 -s 2 -c 1 -o gpurun_out/${T}_gemm_$c -f python tools/gpu_check_gemm.py --pair --time --case $c
+  done
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02d() {
+  # Round 2, fourth GPU call: fused-norm / fused-RoPE GEMM epilogues — op parity, model parity, in-process A/B, whole GPU suite.
+  T=${TAG:-r02d}
+  run ops python -m pytest tests/test_gpu_ops.py -q -x -k "gemm_ex"
+  run model python -m pytest tests/test_gpu_model.py -q -x -s -k "fused_norm or end_to_end or decoder or vit"
+  run ab python tools/gpu_ab_prefill.py fused=0 fused=1
+  TMO=1500 run suite python -m pytest tests -m gpu -q -x
+  run bench_n1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02e() {
+  # Round 2, fifth GPU call: parity mode (fp32-equivalent forward) against the oracle, the whole GPU suite after the fused-norm
+  # invariance fix, N = 1 bench, then (separate call) N = 2.
+  T=${TAG:-r02e}
+  run parity_small python -m pytest tests/test_gpu_parity_mode.py -q -x -s -k "glue or split_gemm or reduced"
+  TMO=2400 run parity_full python -m pytest tests/test_gpu_parity_mode.py -q -s -k "full_depth"
+  TMO=1800 run suite python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_parity_mode.py
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02f() {
+  # Round 2, 2-GPU call: tensor-parallel fused kernels (all-gather -> GEMM, GEMM -> reduce-scatter over NVLink peer memory), the DP
+  # scatter / gather check, and the N = 2 bench line (NCCL scatter / gather inside the timed step, strong-scaling queue).
+  T=${TAG:-r02f}
+  N=${NGPU:-2}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  TMO=600 run tp_check $TR --master-port 29533 tests/gpu_tp_check.py
+  TMO=600 run dp_check $TR --master-port 29534 tests/gpu_dp_check.py
+  TMO=900 run bench_n$N $TR --master-port 29535 bench.py --gpus $N --steps 10 --warmup 3
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02h() {
+  # Round 2, GEMM scheduling call: stream-K tail (accumulator hand-over between CTA pairs), residual tile by TMA, pipelined bias / column
+  # sums, cached row statistics.  Parity first (bit-equality of every switch combination), then per-shape timing, then the whole step.
+  T=${TAG:-r02h}
+  TMO=900 run ops python -m pytest tests/test_gpu_ops.py -x -q -k "gemm"
+  SH="--case d_o --case d_down --case d_qkv --case d_gateup --case v_out --case v_fc2 --case v_patch --case v_qkv --case v_fc1 --case p_1 --case dec_o --case dec_down"
+  TAIL=4000 run gemm_new python tools/gpu_check_gemm.py --pair --time $SH
+  TAIL=4000 run gemm_old python tools/gpu_check_gemm.py --pair --time --streamk 0 --tma-res 0 $SH
+  TMO=900 run ab python tools/gpu_ab_prefill.py sk=0 sk=1 tmares=0 tmares=1
+  TMO=900 TAIL=6000 run bench_n1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras
+  TMO=900 run model python -m pytest tests/test_gpu_model.py tests/test_gpu_fullsize.py -x -q
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02i() {
+  # Round 2: stream-K with the data-parallel waves first (START / whole / END pieces at the end), every switch combination per shape,
+  # whole-step A/B, ncu source-level capture of the LayerNorm-consuming fc1 GEMM inside a real step.
+  T=${TAG:-r02i}
+  TMO=900 run ops python -m pytest tests/test_gpu_ops.py -x -q -k "gemm"
+  SH="--case d_o --case d_down --case d_qkv --case dec_o --case dec_down --case dec_qkv --case p_1 --case v_fc2 --case v_out"
+  for sk in 0 1; do for tm in 0 1; do
+    TAIL=3000 run gemm_sk${sk}_tma${tm} python tools/gpu_check_gemm.py --pair --time --streamk $sk --tma-res $tm $SH
+  done; done
+  TMO=900 run ab python tools/gpu_ab_prefill.py sk=0 sk=1
+  NCU="ncu --set full --clock-control none --import-source on"
+  TMO=400 run ncu_fc1 $NCU -k regex:gemm_bf16_kernel --launch-skip 122 --launch-count 1 -o gpurun_out/${T}_gemm_fc1_ln -f python bench.py --quick --steps 1 --warmup 1
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02j() {
+  # Round 2: chained single-kernel projector, padded-batch HF merge / batched generate, full GPU suite after the GEMM scheduling work.
+  T=${TAG:-r02j}
+  TMO=600 run new python -m pytest tests/test_gpu_model.py tests/test_gpu_hf.py -x -q -k "projector or padded"
+  TMO=600 run ab python tools/gpu_ab_prefill.py chain=0 chain=1
+  TMO=1500 run suite python -m pytest tests -m gpu -x -q
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+r02l() {
+  # Round 2: where the SFT step's time goes (ncu launch list of one cfg5 step, trainable tower) + the other workloads on the new GEMM code.
+  T=${TAG:-r02l}
+  TMO=900 run sft_speed python tools/gpu_train_speed.py --steps 3
+  TMO=1200 run sft_launches ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_sft_launches.csv python tools/gpu_train_speed.py --steps 0
+  TMO=600 run bench_cfg2 python bench.py --workload cfg2 --steps 10 --no-cpu-baseline --no-extras
+  TMO=600 run bench_cfg4 python bench.py --workload cfg4 --steps 5
+  TMO=900 run bench_cfg5 python bench.py --workload cfg5 --steps 3
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
+"$@"
