@@ -421,6 +421,18 @@ int lp_image_frontend(const void* rgb, int H, int W, int target_w, int target_h,
                       int out_fp32, double rescale, const float* mean, const float* std_, void* workspace,
                       size_t ws_bytes, void* stream);
 
+/* Idefics2ImageProcessor.preprocess for ONE image on the GPU (the processor evaluations/models/idefics2_multiimg.py:22-25 builds:
+ * size = {'longest_edge': R, 'shortest_edge': 0}, do_image_splitting = False; transformers' Idefics2ImageProcessor, PIL backend):
+ * `Image.resize((out_w, out_h), resample)` with Pillow's ImagingResample arithmetic (filter 0 = BICUBIC, 1 = BILINEAR — the
+ * processor's default), x * rescale in float64 rounded to float32, (x - mean) / std in float32, pasted at the top-left corner of a
+ * planar [3, canvas_h, canvas_w] canvas (fp32 or bf16) whose other pixels are `pad_value` (the processor pads with 0.0 AFTER
+ * normalising); mask (optional): int64 [canvas_h, canvas_w] = pixel_attention_mask.  (out_w, out_h) comes from the processor's own
+ * integer rule (leopard_b200.frontend.idefics2_resize_size).  Bit-identical to the PIL-backed processor. */
+size_t lp_image_resize_workspace_bytes(int H, int W, int out_w, int out_h, int filter);
+int lp_image_resize(const void* rgb, int H, int W, int out_w, int out_h, int filter, int canvas_w, int canvas_h, float pad_value,
+                    void* out, int out_fp32, long long* mask, double rescale, const float* mean, const float* std,
+                    void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * SFT step (FIRST IMPLEMENTATION, specification = oracle/train.py): the HBM-bound half of the backward
  * pass, the masked LM loss and the optimizer.  In the reference all of this is torch autograd + apex inside Megatron's

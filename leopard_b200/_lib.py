@@ -133,6 +133,8 @@ _SIGS = {
     "lp_decode_set_mode": (_i, [_i]),
     "lp_image_frontend_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lp_image_frontend": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
+    "lp_image_resize_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "lp_image_resize": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
     "lp_decode_debug_stamps": (_i, [_vp]),
     "lp_attention_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "lp_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp, _sz, _vp]),

@@ -93,3 +93,62 @@ class ImageFrontend:
             _lib.check(rc, "lp_image_frontend")
             n0 += n
         return out, per_image
+
+
+# ---- Idefics2 (evaluations/models/idefics2_multiimg.py:22-25: AutoProcessor(size={'longest_edge': R, 'shortest_edge': 0},
+# do_image_splitting=False)) -------------------------------------------------------------------------------------------------------
+def idefics2_resize_size(w: int, h: int, longest_edge: int, shortest_edge: int = 0) -> Tuple[int, int]:
+    """transformers' `get_resize_output_image_size` for Idefics2 (host integers, same float arithmetic): only an image whose
+    longer side exceeds `longest_edge` shrinks (aspect ratio kept, the other side truncated); both sides are then raised to
+    `shortest_edge`.  Returns (width, height)."""
+    aspect = w / h
+    if w >= h and w > longest_edge:
+        w = longest_edge
+        h = int(w / aspect)
+    elif h > w and h > longest_edge:
+        h = longest_edge
+        w = int(h * aspect)
+    return max(w, shortest_edge), max(h, shortest_edge)
+
+
+class Idefics2Frontend:
+    """`pixel_values, pixel_attention_mask = Idefics2Frontend('cuda:0', longest_edge=980)(images)` — the image half of the
+    reference's `processor(text=..., images=images, return_tensors='pt')` (idefics2_multiimg.py:88-90) for ONE sample: BILINEAR
+    resize by the longest-edge rule, rescale, normalise, zero-pad to the largest image, pixel mask.  uint8 pixels cross PCIe, the
+    arithmetic runs in `lp_image_resize` and is bit-identical to transformers' PIL-backed Idefics2ImageProcessor
+    (tests/golden/ref_idefics2_frontend.json).  Returns pixel_values [1, n, 3, Hmax, Wmax] and pixel_attention_mask [1, n, Hmax, Wmax]
+    on the device — the tensors `Idefics2ForConditionalGeneration.generate` takes."""
+
+    def __init__(self, device="cuda:0", longest_edge: int = 980, shortest_edge: int = 0, rescale: float = 1 / 255,
+                 mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+        if not torch.cuda.is_available():
+            raise _lib.NativeError("leopard_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        self.longest_edge, self.shortest_edge = int(longest_edge), int(shortest_edge)
+        self.rescale = float(rescale)
+        self._mean = (C.c_float * 3)(*mean)
+        self._std = (C.c_float * 3)(*std)
+        self._ws = None
+        _lib.lib()
+
+    @torch.no_grad()
+    def __call__(self, images, dtype=torch.float32):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("dtype must be float32 or bfloat16")
+        L = _lib.lib()
+        raws = [_as_uint8_hwc(im) for im in images]
+        sizes = [idefics2_resize_size(int(t.shape[1]), int(t.shape[0]), self.longest_edge, self.shortest_edge) for t in raws]
+        wm, hm = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        pv = torch.empty((1, len(raws), 3, hm, wm), dtype=dtype, device=self.device)
+        mask = torch.empty((1, len(raws), hm, wm), dtype=torch.long, device=self.device)
+        for i, (raw, (ow, oh)) in enumerate(zip(raws, sizes)):
+            h, w = int(raw.shape[0]), int(raw.shape[1])
+            dev = raw.to(self.device, non_blocking=True)
+            need = L.lp_image_resize_workspace_bytes(h, w, ow, oh, 1)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            rc = L.lp_image_resize(_lib.ptr(dev), h, w, ow, oh, 1, wm, hm, 0.0, _lib.ptr(pv[0, i]),
+                                   1 if dtype == torch.float32 else 0, _lib.ptr(mask[0, i]), self.rescale, self._mean, self._std,
+                                   _lib.ptr(self._ws), self._ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "lp_image_resize")
+        return pv, mask

@@ -38,10 +38,22 @@ def bicubic_filter(x: float) -> float:
     return 0.0
 
 
-def precompute_coeffs(in_size: int, out_size: int):
+def bilinear_filter(x: float) -> float:
+    """Triangle filter (Pillow Resample.c `bilinear_filter`, support 1.0) — Idefics2ImageProcessor's resample."""
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return 1.0 - x
+    return 0.0
+
+
+FILTERS = {"bicubic": (bicubic_filter, 2.0), "bilinear": (bilinear_filter, 1.0)}
+
+
+def precompute_coeffs(in_size: int, out_size: int, filt: str = "bicubic"):
     """Pillow `precompute_coeffs` + `normalize_coeffs_8bpc` for the whole-image box (in0 = 0, in1 = in_size).
     Returns (bounds int32 [out, 2] = (xmin, count), coeffs int32 [out, ksize], ksize)."""
-    support0 = 2.0
+    filter_fn, support0 = FILTERS[filt]
     scale = filterscale = float(in_size) / out_size
     if filterscale < 1.0:
         filterscale = 1.0
@@ -62,7 +74,7 @@ def precompute_coeffs(in_size: int, out_size: int):
         xmax -= xmin
         k = [0.0] * ksize
         for x in range(xmax):
-            w = bicubic_filter((x + xmin - center + 0.5) * ss)
+            w = filter_fn((x + xmin - center + 0.5) * ss)
             k[x] = w
             ww += w
         for x in range(xmax):
@@ -79,9 +91,9 @@ def _clip8(acc: np.ndarray) -> np.ndarray:
     return np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)
 
 
-def _resample_axis0(img: np.ndarray, out_size: int) -> np.ndarray:
+def _resample_axis0(img: np.ndarray, out_size: int, filt: str = "bicubic") -> np.ndarray:
     """1-D pass along axis 0 of a uint8 array [n, ...] -> [out_size, ...]."""
-    bounds, kk, _ = precompute_coeffs(img.shape[0], out_size)
+    bounds, kk, _ = precompute_coeffs(img.shape[0], out_size, filt)
     out = np.empty((out_size,) + img.shape[1:], np.uint8)
     src = img.astype(np.int64)
     for xx in range(out_size):
@@ -92,24 +104,65 @@ def _resample_axis0(img: np.ndarray, out_size: int) -> np.ndarray:
     return out
 
 
-def pil_resize_bicubic(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
-    """`PIL.Image.fromarray(img).resize((out_w, out_h))` for an RGB uint8 array [H, W, 3] (default BICUBIC, no box,
-    no reducing_gap): horizontal pass first, then vertical, each skipped when that size is unchanged — except for
+def pil_resize(img: np.ndarray, out_w: int, out_h: int, filt: str = "bicubic") -> np.ndarray:
+    """`PIL.Image.fromarray(img).resize((out_w, out_h), resample)` for an RGB uint8 array [H, W, 3] (no box, no
+    reducing_gap): horizontal pass first, then vertical, each skipped when that size is unchanged — except for
     images more than 100x taller than wide (see below)."""
     h, w = img.shape[:2]
     cur = img
     if h > w * 100 and out_h < h:
         # Pillow >= 11 (Image.resize, Python side): very tall images that shrink vertically are resampled vertically
         # FIRST at full width, then horizontally — observable in the result because of the uint8 intermediate
-        cur = _resample_axis0(cur, out_h)
+        cur = _resample_axis0(cur, out_h, filt)
         if out_w != w:
-            cur = _resample_axis0(cur.transpose(1, 0, 2), out_w).transpose(1, 0, 2)
+            cur = _resample_axis0(cur.transpose(1, 0, 2), out_w, filt).transpose(1, 0, 2)
         return np.ascontiguousarray(cur)
     if out_w != w:
-        cur = _resample_axis0(cur.transpose(1, 0, 2), out_w).transpose(1, 0, 2)
+        cur = _resample_axis0(cur.transpose(1, 0, 2), out_w, filt).transpose(1, 0, 2)
     if out_h != h:
-        cur = _resample_axis0(cur, out_h)
+        cur = _resample_axis0(cur, out_h, filt)
     return np.ascontiguousarray(cur)
+
+
+def pil_resize_bicubic(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
+    """Default resample of `Image.resize` = BICUBIC (what resize_and_pad_image and SiglipImageProcessor use)."""
+    return pil_resize(img, out_w, out_h, "bicubic")
+
+
+# ---- Idefics2 (evaluations/models/idefics2_multiimg.py:22-25: AutoProcessor(size={'longest_edge': R, 'shortest_edge': 0},
+# do_image_splitting=False) -> transformers' Idefics2ImageProcessor, un-vendored third-party code restated here and pinned against the
+# installed PIL-backed implementation, tests/golden/gen_idefics2_frontend_goldens.py) ------------------------------------------------
+def idefics2_resize_size(w: int, h: int, longest_edge: int, shortest_edge: int = 0) -> Tuple[int, int]:
+    """`get_resize_output_image_size`: only images whose longer side exceeds `longest_edge` shrink (aspect ratio kept, the
+    other side truncated), then both sides are raised to `shortest_edge`.  Returns (width, height)."""
+    aspect = w / h
+    if w >= h and w > longest_edge:
+        w = longest_edge
+        h = int(w / aspect)
+    elif h > w and h > longest_edge:
+        h = longest_edge
+        w = int(h * aspect)
+    return max(w, shortest_edge), max(h, shortest_edge)
+
+
+def idefics2_preprocess(images: List[np.ndarray], longest_edge: int = 980, shortest_edge: int = 0):
+    """One sample's images (RGB uint8 [H, W, 3]) -> (pixel_values fp32 [n, 3, Hmax, Wmax], pixel_attention_mask int64
+    [n, Hmax, Wmax]): BILINEAR `Image.resize`, x * (1/255) in float64 rounded to float32, (x - 0.5) / 0.5 in float32, then zero
+    padding (AFTER the normalisation: padded pixels are 0.0, not normalised black) at the bottom / right up to the largest image."""
+    lut = normalize_lut()
+    outs = []
+    for img in images:
+        h, w = img.shape[:2]
+        nw, nh = idefics2_resize_size(w, h, longest_edge, shortest_edge)
+        r = pil_resize(img, nw, nh, "bilinear")
+        outs.append(np.ascontiguousarray(lut[r].transpose(2, 0, 1)))
+    hm, wm = max(o.shape[1] for o in outs), max(o.shape[2] for o in outs)
+    pv = np.zeros((len(outs), 3, hm, wm), np.float32)
+    mask = np.zeros((len(outs), hm, wm), np.int64)
+    for i, o in enumerate(outs):
+        pv[i, :, :o.shape[1], :o.shape[2]] = o
+        mask[i, :o.shape[1], :o.shape[2]] = 1
+    return pv, mask
 
 
 def pad_geometry(w: int, h: int, target: Optional[Tuple[int, int]]):

@@ -62,3 +62,31 @@ def test_frontend_source_is_bit_exact_under_emulation(emu, h, w, target):
                                C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), None)
     assert rc == 0
     assert np.array_equal(out.numpy(), want)
+
+
+@pytest.mark.parametrize("sizes,longest", [
+    ([(420, 350), (100, 460), (200, 200)], 300),     # two images shrink (one by height, one by width), one is kept: zero padding to the largest
+    ([(64, 48)], 980),                               # smaller than the limit: identity resize, no padding
+    ([(2100, 16)], 400),                             # > 100x taller than wide and shrinking: Pillow's vertical-first order, bilinear
+])
+def test_idefics2_processor_source_is_bit_exact_under_emulation(emu, sizes, longest):
+    """lp_image_resize (BILINEAR Image.resize + rescale + normalise + zero padding + pixel mask) against the oracle's restatement of
+    transformers' PIL-backed Idefics2ImageProcessor, which tests/test_frontend_oracle.py pins to the installed processor itself."""
+    rng = np.random.default_rng(len(sizes) + longest)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    want_pv, want_mask = OF.idefics2_preprocess(imgs, longest, 0)
+    n, _, hm, wm = want_pv.shape
+    pv = torch.full((n, 3, hm, wm), float("nan"))
+    mask = torch.full((n, hm, wm), -1, dtype=torch.long)
+    mean, std = (C.c_float * 3)(0.5, 0.5, 0.5), (C.c_float * 3)(0.5, 0.5, 0.5)
+    emu.lp_image_resize_workspace_bytes.restype = C.c_size_t
+    for i, img in enumerate(imgs):
+        h, w = img.shape[:2]
+        ow, oh = OF.idefics2_resize_size(w, h, longest, 0)
+        buf = torch.from_numpy(img.copy())
+        ws = torch.empty(emu.lp_image_resize_workspace_bytes(h, w, ow, oh, 1), dtype=torch.uint8)
+        rc = emu.lp_image_resize(C.c_void_p(buf.data_ptr()), h, w, ow, oh, 1, wm, hm, C.c_float(0.0), C.c_void_p(pv[i].data_ptr()), 1,
+                                 C.c_void_p(mask[i].data_ptr()), C.c_double(1 / 255), mean, std, C.c_void_p(ws.data_ptr()),
+                                 C.c_size_t(ws.numel()), None)
+        assert rc == 0
+    assert np.array_equal(pv.numpy(), want_pv) and np.array_equal(mask.numpy(), want_mask)

@@ -67,3 +67,36 @@ def test_host_shim_to_pixel_values_follows_the_processor_rule():
     img = make_image(500, 420, 9)
     got = to_pixel_values([Image.fromarray(img, "RGB")]).numpy()[0]
     assert np.array_equal(got, fe.siglip_preprocess(img))
+
+
+# ---- Idefics2 processor (evaluations/models/idefics2_multiimg.py:22-25) ---------------------------------------------------------
+@pytest.mark.parametrize("w,h,ow,oh", [(500, 700, 250, 350), (100, 80, 364, 291), (1400, 1000, 980, 700), (37, 991, 14, 378),
+                                       (16, 2100, 3, 400), (300, 300, 300, 300), (1277, 958, 617, 329), (3, 2, 64, 43)])
+def test_bilinear_resize_is_bit_identical_to_pillow(w, h, ow, oh):
+    from PIL import Image
+    rng = np.random.default_rng(w * 5 + h)
+    a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    assert np.array_equal(fe.pil_resize(a, ow, oh, "bilinear"), np.asarray(Image.fromarray(a).resize((ow, oh), Image.BILINEAR)))
+
+
+def test_idefics2_oracle_matches_the_installed_pil_processor_and_its_goldens():
+    """oracle/frontend.py::idefics2_preprocess == transformers' PIL-backed Idefics2ImageProcessor, bit for bit: against committed
+    goldens made by executing the processor (tests/golden/gen_idefics2_frontend_goldens.py) and against the processor itself;
+    the product's host planning (leopard_b200.frontend.idefics2_resize_size) gives the processor's sizes."""
+    from leopard_b200.frontend import idefics2_resize_size
+    gold = json.loads((G / "ref_idefics2_frontend.json").read_text())
+    for case in gold:
+        imgs = [make_image(w, h, case["seed"] + i) for i, (w, h) in enumerate(case["sizes"])]
+        pv, mask = fe.idefics2_preprocess(imgs, case["longest_edge"], 0)
+        assert list(pv.shape) == case["shape"] and pv.dtype == np.float32 and mask.dtype == np.int64
+        assert hashlib.sha256(pv.tobytes()).hexdigest() == case["pixel_values_sha256"], case["name"]
+        assert hashlib.sha256(mask.tobytes()).hexdigest() == case["mask_sha256"], case["name"]
+        assert [list(idefics2_resize_size(w, h, case["longest_edge"], 0)) for w, h in case["sizes"]] == case["resized"]
+    from PIL import Image
+    from transformers.models.idefics2.image_processing_pil_idefics2 import Idefics2ImageProcessorPil
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(420, 350), (100, 460), (200, 200), (301, 299)]]
+    r = Idefics2ImageProcessorPil(size={"longest_edge": 300, "shortest_edge": 1}, do_image_splitting=False).preprocess(
+        [[Image.fromarray(i, "RGB") for i in imgs]], return_tensors="np")
+    pv, mask = fe.idefics2_preprocess(imgs, 300, 0)
+    assert np.array_equal(pv, r["pixel_values"][0]) and np.array_equal(mask, r["pixel_attention_mask"][0])

@@ -103,3 +103,31 @@ def test_argument_errors(fe):
     assert rc == -1 and b"workspace too small" in L.lp_last_error()
     with pytest.raises(ValueError):
         fe([np.zeros((4, 4), np.uint8)])
+
+
+def test_idefics2_processor_on_the_gpu_is_bit_exact():
+    """Idefics2Frontend (lp_image_resize: BILINEAR resize by the longest-edge rule + rescale + normalise + zero padding + pixel mask)
+    against goldens made by executing transformers' PIL-backed Idefics2ImageProcessor, and against the oracle on random images."""
+    import hashlib
+    import json
+    import sys
+    from pathlib import Path
+    G = Path(__file__).resolve().parent / "golden"
+    sys.path.insert(0, str(G))
+    from gen_frontend_goldens import make_image
+    from leopard_b200.frontend import Idefics2Frontend
+    from oracle import frontend as ofe
+    for case in json.loads((G / "ref_idefics2_frontend.json").read_text()):
+        imgs = [make_image(w, h, case["seed"] + i) for i, (w, h) in enumerate(case["sizes"])]
+        pv, mask = Idefics2Frontend("cuda:0", longest_edge=case["longest_edge"])(imgs)
+        assert list(pv.shape) == [1] + case["shape"] and list(mask.shape) == [1, case["shape"][0]] + case["shape"][2:]
+        assert hashlib.sha256(pv[0].cpu().numpy().tobytes()).hexdigest() == case["pixel_values_sha256"], case["name"]
+        assert hashlib.sha256(mask[0].cpu().numpy().tobytes()).hexdigest() == case["mask_sha256"], case["name"]
+    rng = np.random.default_rng(9)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(1300, 977), (640, 1500), (2100, 16)]]
+    fe2 = Idefics2Frontend("cuda:0", longest_edge=980)
+    pv, mask = fe2(imgs)
+    want_pv, want_mask = ofe.idefics2_preprocess(imgs, 980, 0)
+    assert np.array_equal(pv[0].cpu().numpy(), want_pv) and np.array_equal(mask[0].cpu().numpy(), want_mask)
+    pv16, _ = fe2(imgs, dtype=torch.bfloat16)                      # bf16 output == fp32 output rounded once
+    assert torch.equal(pv16, pv.to(torch.bfloat16))

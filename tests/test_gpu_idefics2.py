@@ -109,3 +109,26 @@ def test_megatron_style_provider_logits_and_loss(small):
     loss = model(ids, None, None, labels=labels, pixel_values=pv, pixel_attention_mask=pm)
     ref_loss = torch.nn.functional.cross_entropy(ref.float(), labels[0], ignore_index=-100, reduction="none")
     assert loss.shape == ids.shape and float((loss[0].cpu() - ref_loss).abs().max()) < 0.08
+
+
+def test_gpu_image_processor_feeds_the_model(small):
+    """raw RGB images -> Idefics2Frontend (the processor's image half on the GPU) -> forward: the logits equal those of the same
+    call fed with the oracle-processed tensors (the front-end is bit-exact), and match the oracle forward.  Sizes are multiples
+    of the 14-pixel patch after the longest-edge rule, as the reference's 980-pixel setting gives for its slide images."""
+    import numpy as np
+    from leopard_b200.frontend import Idefics2Frontend
+    from oracle import frontend as ofe
+    cfg, ck, model = small
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (280, 364, 3), dtype=np.uint8), rng.integers(0, 256, (98, 140, 3), dtype=np.uint8)]
+    pv, pm = Idefics2Frontend("cuda:0", longest_edge=182)(imgs)          # 364 x 280 -> 182 x 140; the small image is kept
+    assert pv.shape == (1, 2, 3, 140, 182) and pm.shape == (1, 2, 140, 182)
+    want_pv, want_pm = ofe.idefics2_preprocess(imgs, 182, 0)
+    assert np.array_equal(pv[0].cpu().numpy(), want_pv) and np.array_equal(pm[0].cpu().numpy(), want_pm)
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(0, cfg.image_token_id - 2, (10,), generator=g)
+    img = torch.full((cfg.perceiver.latents,), cfg.image_token_id)
+    ids = torch.cat([text[:4], img, text[4:7], img, text[7:]])[None]
+    out = model(input_ids=ids, pixel_values=pv, pixel_attention_mask=pm.bool(), attention_mask=torch.ones_like(ids))
+    ref = oi.prefill_logits(ck, cfg, ids, torch.from_numpy(want_pv)[None].to(torch.bfloat16).float(), torch.from_numpy(want_pm)[None].bool())
+    assert out.logits.shape == ref.shape and rel_err(out.logits, ref) < 3e-2
