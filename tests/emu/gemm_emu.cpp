@@ -53,7 +53,9 @@ extern "C" void emu_gemm_set_tma_residual(int on) { g_tma_res = on; }
 
 // stream-K tail (lp_gemm_set_streamk_workspace): set by emu_gemm_set_streamk before a launch, same split rule as lp_gemm_bf16_ex
 static void* g_sk_ws = nullptr;
+static int g_sk_pure = 0;     // pure stream-K over a column-block-fastest raster (lp_gemm_set_streamk mode 2, norm-consuming launches)
 extern "C" void emu_gemm_set_streamk(void* ws) { g_sk_ws = ws; }
+extern "C" void emu_gemm_set_streamk_pure(int on) { g_sk_pure = on; }
 
 extern "C" void emu_gemm_ex(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                             const float* bias, const void* residual, long long ldr, int res_row_mod, int act, int out_fp32,
@@ -80,7 +82,13 @@ extern "C" void emu_gemm_ex(const void* A, long long lda, const void* W, long lo
   args.prefetch_a = 0;
   if (g_sk_ws != nullptr) {
     const int T = args.num_m_blk * args.num_n_blk, n_units = pair ? ctas / 2 : ctas;
-    if (T > n_units && T % n_units != 0) {
+    if (g_sk_pure && T >= n_units) {
+      args.group_m = 1;
+      args.dp_tiles = 0;
+      args.sk_tiles = T;
+      args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);
+      args.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + 4096);
+    } else if (T > n_units && T % n_units != 0) {
       args.dp_tiles = (T / n_units - 1) * n_units;
       args.sk_tiles = T - args.dp_tiles;
       args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);

@@ -410,3 +410,35 @@ def test_chained_projector_kernel_under_emulation(emu, M, K1, N1, N2, act):
     emu.emu_gemm(P(x), LL(K1), P(w1), LL(K1), P(mid2), LL(N1), M, N1, K1, P(b1), None, LL(0), 0, act, 0, 256, 1, 1, 2)
     emu.emu_gemm(P(mid2), LL(N1), P(w2), LL(N1), P(out2), LL(N2), M, N2, N1, P(b2), None, LL(0), 0, 0, 0, 256, 1, 1, 2)
     assert torch.equal(mid, mid2) and torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("M,N,K,bn,pair,ctas,mode,act", [
+    (700, 1152, 264, 256, True, 4, 2, 1),      # LayerNorm + GELU consumer, 3 row blocks x 5 column blocks on 2 pairs: 7.5 tiles each
+    (600, 512, 200, 128, True, 6, 1, 0),       # RMSNorm consumer, 12 tiles on 3 pairs: whole tiles only (no cut)
+    (333, 640, 136, 128, False, 4, 2, 0),      # one CTA per tile, 15 tiles on 4 units
+])
+def test_pure_stream_k_for_norm_consumers_is_bit_identical(emu, M, N, K, bn, pair, ctas, mode, act):
+    """lp_gemm_set_streamk mode 2: the whole (row block, column block, k) space cut into one contiguous range per unit over a
+    column-block-fastest raster — same bits as the plain schedule, for the folded LayerNorm / RMSNorm epilogues."""
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn((M, K), generator=g) * 1.3 + 0.2).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    b = torch.randn(N, generator=g) * 0.1
+    colsum = w.float().sum(1).contiguous()
+    stats = _split_stats(x, 6)
+    ws = torch.zeros(4096 + ctas * 128 * bn * 4, dtype=torch.uint8)
+    outs = []
+    for pure in (0, 1):
+        out = torch.full((M, N), float("nan"), dtype=BF)
+        fx = _Fx(norm_mode=mode, stats_in=stats.data_ptr(), stats_in_parts=6, colsum=colsum.data_ptr(), norm_eps=1e-5)
+        emu.emu_gemm_set_streamk(P(ws) if pure else None)
+        emu.emu_gemm_set_streamk_pure(pure)
+        try:
+            _gemm_ex(emu, x, w, out, bias=b, act=act, bn=bn, pair=pair, ctas=ctas, fx=fx)
+        finally:
+            emu.emu_gemm_set_streamk(None)
+            emu.emu_gemm_set_streamk_pure(0)
+        outs.append(out)
+    assert not bool(torch.isnan(outs[1].float()).any())
+    assert torch.equal(outs[0], outs[1])
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0

@@ -1,6 +1,7 @@
 """A/B of whole-step prefill time on the cfg3 workload for different kernel switches, interleaved in ONE process so that
 box-to-box clock / power-cap differences cancel.  Usage: python tools/gpu_ab_prefill.py attn=2 attn=80 pair=0 ..."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -15,7 +16,7 @@ from leopard_b200.native_weights import random_native  # noqa: E402
 
 cfg = leopard_llava()
 eng = PrefillEngine(cfg, random_native(cfg, "cuda:0", seed=1234))
-pix, ids, n_crops, S, _ = bench.make_workload(cfg)
+pix, ids, n_crops, S, _ = bench.make_workload(cfg, os.environ.get("LEOPARD_AB_WORKLOAD", "cfg3"))   # cfg3 (default) or cfg2
 pix, ids = pix.cuda(), ids[0].cuda()
 L = _lib.lib()
 
