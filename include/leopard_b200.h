@@ -131,9 +131,10 @@ int lp_gemm_set_pair_mode(int enable);
  * that of the unsplit kernel, results are bit-identical with it on or off.  The library never allocates: the caller provides
  * `ws` = ZERO-FILLED device memory of lp_gemm_streamk_workspace_bytes() bytes, 256-byte aligned, used by one stream at a time and
  * valid until replaced (NULL = off, the default).  lp_gemm_set_streamk(mode) switches it without dropping the workspace and
- * returns the previous setting: 0 = off, 1 = the tail only, 2 (default) = additionally PURE stream-K (every CTA pair owns one
+ * returns the previous setting: 0 = off, 1 (default) = the tail only, 2 = additionally PURE stream-K (every CTA pair owns one
  * contiguous range of the (row block, column block, k) space) for norm-consuming launches whose operands are L2-resident — the
- * ViT's qkv / fc1 GEMMs: perfect balance at any crop count and the fused LayerNorm's row statistics are fetched once per pair. */
+ * ViT's qkv / fc1 GEMMs: balanced at any crop count, the fused LayerNorm's row statistics fetched once per pair; bit-identical,
+ * but measured slightly slower than mode 1 on the B200, hence opt-in. */
 size_t lp_gemm_streamk_workspace_bytes(void);
 int lp_gemm_set_streamk_workspace(void* ws, size_t bytes);
 int lp_gemm_set_streamk(int enable);

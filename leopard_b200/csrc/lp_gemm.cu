@@ -590,7 +590,7 @@ static int g_gemm_pair_mode = 1;  // 0 = one CTA per tile, 1 = CTA pairs where t
 // stream-K tail (GemmArgs::sk_*): caller-provided workspace (flags in the first 4 KiB, fp32 partial accumulators after them)
 static void* g_sk_ws = nullptr;
 static size_t g_sk_bytes = 0;
-static int g_sk_enable = 2;   // 0 = off, 1 = stream-K tail only, 2 = tail + pure stream-K for norm-consuming L2-resident launches
+static int g_sk_enable = 1;   // 0 = off, 1 = stream-K tail only (default), 2 = tail + pure stream-K for norm-consuming L2-resident launches (measured: no gain, opt-in)
 constexpr size_t SK_FLAG_BYTES = 4096;
 
 }  // namespace lp
@@ -751,7 +751,9 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
     // column-block-fastest raster — every unit owns one contiguous range of the (row block, column block, k) space, so it stays in
     // one or two row blocks (the row statistics of the fused LayerNorm are fetched once instead of per tile) and every unit ends
     // at the same time whatever M is (17 crops = 45 row blocks on 74 pairs would otherwise run 9.1 waves as 10).  With M a
-    // multiple of the unit count (28 crops = 74 row blocks) this is exactly the plain schedule.
+    // multiple of the unit count (28 crops = 74 row blocks) this is exactly the plain schedule.  Measured on the B200
+    // (profiles/r02o_ab_pure_streamk.jsonl): cfg3 80.3 -> 81.0 ms, cfg2 51.4 -> 51.7 ms per step — no gain (the column-block-fastest
+    // raster shares each W tile between fewer concurrent units), so it stays opt-in (lp_gemm_set_streamk(2)).
     const size_t need_pure = SK_FLAG_BYTES + (size_t)n_units * per_unit * GEMM_BM * block_n * sizeof(float);
     if (g_sk_enable == 2 && d->norm_mode != LP_NORM_NONE && T >= n_units && args.num_k_blk >= 8 && need_pure <= g_sk_bytes &&
         2.0 * M * K <= 56e6 && 2.0 * N * K <= 56e6) {
