@@ -403,6 +403,9 @@ void lp_decode_graph_destroy(lp_decode_graph* graph);
  *          instead of warp-per-row-pair;
  *   bit 4: lp_decode_greedy_step runs the whole step as ONE persistent cooperative kernel with grid barriers (21). */
 int lp_decode_set_mode(int mode);
+/* MiB of the NEXT projections' weights (o_proj, head of gate/up) that the decode attention kernel pulls into L2 while it runs —
+ * attention only reads the KV cache, so the HBM is nearly idle for its duration.  Results unchanged.  Defaults 32 / 48; 0 / 0 = off. */
+int lp_decode_set_prefetch(int o_proj_mb, int gateup_mb);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * GPU image front-end (SURVEY.md §8 a3 + a5, "next" row f-3): one RGB uint8 image -> the ViT inputs it contributes.

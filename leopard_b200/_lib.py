@@ -131,6 +131,7 @@ _SIGS = {
     "lp_decode_graph_launch": (_i, [_vp, _vp]),
     "lp_decode_graph_destroy": (None, [_vp]),
     "lp_decode_set_mode": (_i, [_i]),
+    "lp_decode_set_prefetch": (_i, [_i, _i]),
     "lp_image_frontend_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lp_image_frontend": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, C.c_double, _P(_f), _P(_f), _vp, _sz, _vp]),
     "lp_image_resize_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

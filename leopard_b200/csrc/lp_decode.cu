@@ -31,6 +31,9 @@
 
 namespace lp {
 
+// MiB of the o_proj / gate-up weights the decode attention kernel pulls into L2 while it runs (lp_decode_set_prefetch)
+static int g_dec_prefetch_mb[2] = {32, 48};
+
 int rope_table_base(int pos_base, const float* inv_freq, float* cs, float* sn, int S, int half, cudaStream_t stream);
 
 static int g_decode_mode = 7;  // bit 0: GEMV kernels, bit 1: programmatic dependent launch, bit 2: block-cooperative GEMV, bit 4: one persistent kernel per token
@@ -425,14 +428,24 @@ __device__ __forceinline__ void decode_attn_item(const bf16* q, const bf16* __re
   if (tid == 0) tickets[g] = 0u;  // ready for the next layer / step
 }
 
-// multi-kernel step: one CTA per (kv head, key range)
+// multi-kernel step: one CTA per (kv head, key range).
+// pf_a / pf_b: weights of the NEXT projections (o_proj, the head of gate/up) to pull into L2 while this kernel runs: attention reads
+// only the KV cache (20 MB per layer at S = 4796, latency-bound split-K), so the HBM is nearly idle for its ~19 us — time in which
+// ~100 MB of weights can cross it.  The lines are requested before griddepcontrol.wait (weights do not depend on earlier kernels).
 __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
 decode_attn_kernel(const bf16* q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
                    const int* __restrict__ pos_dev, int pos_host, int max_ctx, int kv_w, float scale_log2,
-                   float* part, unsigned* tickets, bf16* out) {
+                   float* part, unsigned* tickets, bf16* out, const uint8_t* pf_a, long long pf_a_bytes, const uint8_t* pf_b,
+                   long long pf_b_bytes) {
   extern __shared__ __align__(16) uint8_t da_smem[];
   __shared__ DecAttnSmem<DEC_SPLITS> sm;
   pdl_launch_dependents();
+  {
+    const long long nthr = (long long)gridDim.x * gridDim.y * blockDim.x;
+    const long long t = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    for (long long i = t * 128; i < pf_a_bytes; i += nthr * 128) prefetch_l2(pf_a + i);
+    for (long long i = t * 128; i < pf_b_bytes; i += nthr * 128) prefetch_l2(pf_b + i);
+  }
   pdl_wait();
   const int n_ctx = min(decode_position(pos_dev, pos_host) + 1, max_ctx);  // never read past the cache
   decode_attn_item<DEC_SPLITS>(q, kc, vc, n_ctx, kv_w, blockIdx.x, blockIdx.y, scale_log2, part, tickets, out, da_smem,
@@ -1075,6 +1088,12 @@ using namespace lp;
 
 static inline size_t bf(size_t n) { return n * 2; }
 
+extern "C" int lp_decode_set_prefetch(int o_proj_mb, int gateup_mb) {
+  g_dec_prefetch_mb[0] = o_proj_mb < 0 ? 0 : o_proj_mb;
+  g_dec_prefetch_mb[1] = gateup_mb < 0 ? 0 : gateup_mb;
+  return 0;
+}
+
 extern "C" int lp_decode_set_mode(int mode) {
   const int old = g_decode_mode;
   g_decode_mode = mode & 23;
@@ -1140,7 +1159,7 @@ static int decode_step_v1(const lp_dec_dims* d, const lp_dec_weights* w, const v
       note_launch();
       LP_TRY(decode_attn_configure());
       decode_attn_kernel<<<dim3(d->kv_heads, DEC_SPLITS), DEC_WARPS * 32, DA_SMEM_BYTES, stream>>>(
-          qkv, kc, vc, nullptr, position, (int)kv_capacity, kv_w, scale_log2, part, tickets, att);
+          qkv, kc, vc, nullptr, position, (int)kv_capacity, kv_w, scale_log2, part, tickets, att, nullptr, 0LL, nullptr, 0LL);
       LP_CHECK_CUDA(cudaGetLastError());
     }
     LP_TRY(lp_gemm_bf16(att, H, L->o_w, H, x, H, 1, H, H, nullptr, x, H, 0, LP_ACT_NONE, 0, 128, stream));
@@ -1191,7 +1210,9 @@ static int decode_step_v2(const lp_dec_dims* d, const lp_dec_weights* w, const v
       LP_TRY(decode_attn_configure());
       LP_TRY(launch_pdl(decode_attn_kernel, dim3(d->kv_heads, DEC_SPLITS), dim3(DEC_WARPS * 32), DA_SMEM_BYTES, stream,
                         (const bf16*)qb, (const bf16*)kc, (const bf16*)vc, pos_dev, pos_host, (int)kv_capacity, kv_w,
-                        scale_log2, part, tickets, att));
+                        scale_log2, part, tickets, att, (const uint8_t*)L->o_w,
+                        min((long long)g_dec_prefetch_mb[0] << 20, (long long)H * H * 2), (const uint8_t*)L->gateup_w,
+                        min((long long)g_dec_prefetch_mb[1] << 20, (long long)2 * d->ffn * H * 2)));
     }
     a = base;  // x += o_proj(att)
     a.W = (const bf16*)L->o_w; a.ldw = H; a.N = H; a.K = H; a.x = att; a.y = x; a.residual = 1;

@@ -221,3 +221,37 @@ def test_padded_batch_forward_and_generate_follow_the_hf_merge(small):
     # mismatch between placeholders and crops is the reference's ValueError
     with pytest.raises(ValueError):
         model(input_ids=ids, pixel_values=pix[:2], attention_mask=mask)
+
+
+def test_from_pretrained_directory_runs_on_the_gpu_path(small, tmp_path):
+    """The reference's load line (`myLlavaForConditionalGeneration.from_pretrained(ckpt, torch_dtype=torch.float32).eval().to('cuda:0')`,
+    …anyres.py:373-375) on a synthetic HF checkpoint DIRECTORY (config.json + sharded safetensors, the layout the reference's
+    converter writes): same logits, bit for bit, as the model built from the same tensors in memory; both key spellings
+    (towers at the top level / nested under `model.`)."""
+    import json
+    from safetensors.torch import save_file
+    from leopard_b200.weights import tensor_specs
+    cfg, ck, model = small
+    tensors = {n: ck[n].contiguous() for n, _, _ in tensor_specs(cfg)}
+    names = sorted(tensors)
+    for nested in (False, True):
+        d = tmp_path / ("nested" if nested else "flat")
+        d.mkdir()
+        ren = (lambda n: "model." + n.replace("language_model.model.", "language_model.") if nested and not n.startswith("language_model.lm_head") else n)
+        half = len(names) // 2
+        save_file({ren(n): tensors[n] for n in names[:half]}, str(d / "model-00001-of-00002.safetensors"))
+        save_file({ren(n): tensors[n] for n in names[half:]}, str(d / "model-00002-of-00002.safetensors"))
+        (d / "config.json").write_text(json.dumps({
+            "image_token_index": cfg.image_token_index, "projector_hidden_act": "gelu",
+            "text_config": {"hidden_size": 4096, "intermediate_size": 14336, "num_attention_heads": 32, "num_key_value_heads": 8,
+                            "num_hidden_layers": cfg.dec.layers, "vocab_size": cfg.dec.vocab, "rope_theta": 500000.0,
+                            "rope_scaling": {"factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                                             "original_max_position_embeddings": 8192, "rope_type": "llama3"},
+                            "rms_norm_eps": 1e-5},
+            "vision_config": {"hidden_size": 1152, "intermediate_size": 4304, "num_attention_heads": 16,
+                              "num_hidden_layers": cfg.vit.layers, "image_size": 364, "patch_size": 14, "layer_norm_eps": 1e-6}}))
+        m = hf.myLlavaForConditionalGeneration.from_pretrained(str(d), torch_dtype=torch.float32).eval().to("cuda:0")
+        assert m.device == torch.device("cuda:0")
+        pix, ids = synth_inputs(cfg, n_crops=1, n_text=9, seed=31)
+        assert torch.equal(m(input_ids=ids, pixel_values=pix).logits, model(input_ids=ids, pixel_values=pix).logits)
+        del m
