@@ -32,7 +32,7 @@
 namespace lp {
 
 // MiB of the o_proj / gate-up weights the decode attention kernel pulls into L2 while it runs (lp_decode_set_prefetch)
-static int g_dec_prefetch_mb[2] = {32, 48};
+static int g_dec_prefetch_mb[2] = {32, 24};   // profiles/r02p_decode_prefetch.jsonl: 3.14 ms/token vs 3.18-3.25 without (noise +-0.1)
 
 int rope_table_base(int pos_base, const float* inv_freq, float* cs, float* sn, int S, int half, cudaStream_t stream);
 

@@ -45,4 +45,4 @@ for rnd in range(2):
             ref = out
         print(json.dumps({"o_proj_mb": o_mb, "gateup_mb": gu_mb, "round": rnd, "ms_per_token": round((tn - t1) * 1e3 / (N_NEW - 1), 4),
                           "same_tokens": bool(torch.equal(out, ref))}), flush=True)
-L.lp_decode_set_prefetch(32, 48)
+L.lp_decode_set_prefetch(32, 24)
