@@ -63,7 +63,11 @@ int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, voi
  *   stats_out (producer): float2 [M, stats_out_parts], stats_out_parts == 2 * ceil(N / block_n) (lp_gemm_pick_block_n gives the
  *     block_n a block_n = 0 call will use): (sum, sum of squares) of the bf16-rounded outputs per (column block, epilogue half).
  *   rope_heads > 0: columns are 128-wide heads; heads [0, rope_heads) get rotate-half RoPE with cos / sin tables fp32 [M, 64]
- *     (lp_rope_table) applied to the fp32 accumulators before the single bf16 rounding.  bf16 output, no bias / act / residual. */
+ *     (lp_rope_table) applied to the fp32 accumulators before the single bf16 rounding.  bf16 output, no bias / act / residual.
+ *   a_t / b_t (transposed operands, the SFT step's dgrad and wgrad; autograd's `grad_output @ weight` and `grad_output.t() @ input`
+ *     of torch.nn.functional.linear): a_t: A is given as At [K, M] row-major (lda = its row stride); b_t: W is given as Wt [K, N]
+ *     row-major (ldw).  The tiles are fed to the tensor core as MN-major operands — no transposed copy is made.  Needs the CTA-pair
+ *     mode (M > 128 and at least one tile per SM pair), N % 256 == 0, M % 8 == 0 when a_t; plain epilogue (bias / out_fp32 only). */
 enum lp_norm_mode { LP_NORM_NONE = 0, LP_NORM_RMS = 1, LP_NORM_LAYER = 2 };
 typedef struct lp_gemm_desc {
   const void* A; long long lda;
@@ -76,6 +80,7 @@ typedef struct lp_gemm_desc {
   int norm_mode; const float* stats_in; int stats_in_parts; const float* colsum; float norm_eps;
   float* stats_out; int stats_out_parts;
   const float* rope_cos; const float* rope_sin; int rope_heads;
+  int a_t, b_t;
 } lp_gemm_desc;
 int lp_gemm_bf16_ex(const lp_gemm_desc* desc, void* stream);
 /* the tile width a block_n = 0 launch of this problem uses under the current scheduling mode */

@@ -58,7 +58,7 @@ class GemmDesc(C.Structure):
                 ("bias", _vp), ("residual", _vp), ("ldr", _ll), ("res_row_mod", _i), ("act", _i), ("out_fp32", _i),
                 ("block_n", _i), ("norm_mode", _i), ("stats_in", _vp), ("stats_in_parts", _i), ("colsum", _vp),
                 ("norm_eps", _f), ("stats_out", _vp), ("stats_out_parts", _i), ("rope_cos", _vp), ("rope_sin", _vp),
-                ("rope_heads", _i)]
+                ("rope_heads", _i), ("a_t", _i), ("b_t", _i)]
 
 
 NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2

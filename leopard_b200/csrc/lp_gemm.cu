@@ -36,7 +36,12 @@ namespace lp {
 // buffer — no residual registers, no global-load latency in the epilogue's dependency chain
 // RES: 0 = the kernel has no residual path at all (leaner epilogue for the qkv / fc1 / gate-up launches), 1 = residual through
 // registers (any layout: fp32 output, row-modulo residual = position embedding, one CTA per tile), 2 = TMARES
-template <int BN, int STAGES, bool CTA2, bool TP, int RES>
+// A_MN / B_MN: the operand is given TRANSPOSED in memory — A as At [K, M] row-major, W as Wt [K, N] row-major (the contraction index
+// is the ROW index) — and is fed to the tensor core as an MN-major operand: TMA brings 64 (k rows) x 64 (m or n columns) boxes into
+// 8 KiB slabs, the UMMA descriptor walks them with LBO = slab stride, a K = 16 step advances 16 rows = 2 KiB.  This is what the SFT
+// step's dgrad (dX = dY W: W is "Wt") and wgrad (dW = dY^T X: both operands) need; no transposed copies are materialised.
+// Tile width BN = 256 columns and N % 256 == 0 (the slabs of a ragged last column block would not line up).
+template <int BN, int STAGES, bool CTA2, bool TP, int RES, bool A_MN = false, bool B_MN = false>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                           const CUtensorMap* segC, const CUtensorMap& tmR, const GemmArgs& args) {
   constexpr bool TMARES = RES == 2;
@@ -125,8 +130,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             // both CTAs' bytes are counted on the LEADER's full barrier (it alone arrives, expecting 2 stages)
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_pair(sa, &tmA, bar, kb * GEMM_BK, a_row);
-            tma_load_2d_pair(sb, &tmB, bar, kb * GEMM_BK, b_row);
+            if (A_MN) {      // At [K, M]: two 64-column slabs of this CTA's 128 output rows
+              tma_load_2d_pair(sa, &tmA, bar, a_row, kb * GEMM_BK);
+              tma_load_2d_pair(sa + 8192, &tmA, bar, a_row + 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d_pair(sa, &tmA, bar, kb * GEMM_BK, a_row);
+            }
+            if (B_MN) {      // Wt [K, N]: this CTA's BN / 2 columns in 64-column slabs
+#pragma unroll
+              for (int sl = 0; sl < BN / 128; ++sl) tma_load_2d_pair(sb + sl * 8192, &tmB, bar, b_row + sl * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d_pair(sb, &tmB, bar, kb * GEMM_BK, b_row);
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, a_row);
@@ -148,7 +163,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         int m_blk_unused, n_blk;
         tile_coords(args, w.tile, m_blk_unused, n_blk);
         // the last column block of a ragged N issues narrower MMAs (N = valid columns rounded up to 32)
-        const uint32_t idesc = umma_idesc_bf16(BMT, min(BN, ((args.N - n_blk * BN) + 31) & ~31), 0, 0);
+        const uint32_t idesc = umma_idesc_bf16(BMT, min(BN, ((args.N - n_blk * BN) + 31) & ~31), A_MN ? 1 : 0, B_MN ? 1 : 0);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         const bool resume = w.kind == GEMM_ITEM_END;   // the accumulator continues another unit's partial sums
         if (resume) mbar_wait(tpre_bar, 0);
@@ -158,13 +173,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(a_addr, 0, 1024);
-          const uint64_t bdesc = umma_desc_sw128(a_addr + L::A_BYTES, 0, 1024);
+          const uint64_t adesc = umma_desc_sw128(a_addr, A_MN ? 8192 : 0, 1024);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + L::A_BYTES, B_MN ? 8192 : 0, 1024);
+          constexpr uint32_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;   // descriptor units of 16 B per K = 16 step
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {  // +32 B per K=16 step inside the 128 B swizzle row
             const uint32_t acc = (resume || kb > w.kb0 || k > 0) ? 1u : 0u;
-            if (CTA2) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            if (CTA2) umma_ss_pair(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, acc);
+            else umma_ss(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, acc);
           }
           // smem slot reusable once these MMAs retire (in both CTAs of a pair)
           if (CTA2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -519,6 +535,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   gemm_body<BN, STAGES, CTA2, false, 0>(tmA, tmB, tmC, nullptr, tmC, args);
 }
 
+// transposed-operand launches (SFT dgrad / wgrad): pair mode, no residual
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs args) {
+  static_assert(!A_MN || B_MN || true, "");
+  gemm_body<BN, STAGES, true, false, 0, A_MN, B_MN>(tmA, tmB, tmC, nullptr, tmC, args);
+}
+
 // residual through registers (see RES above)
 template <int BN, int STAGES, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -581,6 +606,26 @@ static int launch_gemm_res(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   const int pairs = sm_count() / 2;
   LP_CHECK_CUDA(launch_ex(kern, dim3(2 * (tiles < pairs ? tiles : pairs)), dim3(GEMM_THREADS), L::TOTAL, stream, 2, prefill_pdl(), tmA,
                           tmB, tmC, tmR, args));
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// transposed-operand launches (pair mode, 256-wide tiles): (A_MN, B_MN) = (0, 1) dgrad, (1, 1) wgrad, (1, 0) for completeness
+template <bool A_MN, bool B_MN_unused>
+static int launch_gemm_mn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& args,
+                          cudaStream_t stream, bool b_t) {
+  using L = GemmSmem<256, 6, true>;
+  auto kern = b_t ? gemm_bf16_mn_kernel<256, 6, A_MN, true> : gemm_bf16_mn_kernel<256, 6, A_MN, false>;
+  static bool configured = false;
+  if (!configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_mn_kernel<256, 6, A_MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    LP_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_mn_kernel<256, 6, A_MN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = args.num_m_blk * args.num_n_blk;
+  const int pairs = sm_count() / 2;
+  LP_CHECK_CUDA(launch_ex(kern, dim3(2 * (tiles < pairs ? tiles : pairs)), dim3(GEMM_THREADS), L::TOTAL, stream, 2, prefill_pdl(), tmA,
+                          tmB, tmC, args));
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -660,7 +705,7 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
   const int units = pair ? sms / 2 : sms;
   const int bm_unit = pair ? 2 * GEMM_BM : GEMM_BM;
   const long long mb = (M + bm_unit - 1) / bm_unit;
-  if (d->rope_heads > 0) block_n = 256;
+  if (d->rope_heads > 0 || d->a_t || d->b_t) block_n = 256;
   if (block_n == 0) block_n = pick_block_n(M, N, act, pair, sms);
   LP_REQUIRE(block_n == 128 || block_n == 160 || block_n == 192 || block_n == 224 || block_n == 256,
              "lp_gemm_bf16: block_n must be 0, 128, 160, 192, 224 or 256");
@@ -711,10 +756,20 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
   } else {
     tmC = CUtensorMap{};
   }
-  rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
+  const bool a_t = d->a_t != 0, b_t = d->b_t != 0;
+  if (a_t || b_t) {
+    LP_REQUIRE(pair && block_n == 256 && N % 256 == 0 && (!a_t || M % 8 == 0),
+               "lp_gemm_bf16_ex: transposed operands need the CTA-pair mode (M=%d N=%d: at least one 256-row tile per SM pair), block_n "
+               "256 and N %% 256 == 0", M, N);
+    LP_REQUIRE(residual == nullptr && act == LP_ACT_NONE && d->norm_mode == LP_NORM_NONE && d->stats_out == nullptr && d->rope_heads == 0,
+               "lp_gemm_bf16_ex: transposed operands take the plain epilogue (bias / fp32 output only)");
+  }
+  // K-major operand: [rows, K] with 64-wide k boxes; transposed (MN-major) operand: [K, rows] with 64 (rows) x 64 (k) boxes
+  rc = a_t ? make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK)
+           : make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK,
-                         (uint32_t)(pair ? block_n / 2 : block_n));
+  rc = b_t ? make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 64, GEMM_BK)
+           : make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, (uint32_t)(pair ? block_n / 2 : block_n));
   if (rc) return rc;
   ProfScope prof(1, M, N, K, stream);
   note_launch();
@@ -763,6 +818,10 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
       args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);
       args.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + SK_FLAG_BYTES);
     }
+  }
+  if (a_t || b_t) {
+    if (a_t) return launch_gemm_mn<true, true>(tmA, tmB, tmC, args, stream, b_t);
+    return launch_gemm_mn<false, true>(tmA, tmB, tmC, args, stream, b_t);
   }
   if (pair && g_gemm_tma_residual && residual != nullptr && res_row_mod == 0 && !out_fp32 && act != LP_ACT_SWIGLU &&
       d->rope_heads == 0) {

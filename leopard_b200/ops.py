@@ -58,15 +58,18 @@ def row_stats(x, out=None):
 
 
 def gemm_ex(a, w, bias=None, residual=None, act=ACT_NONE, out=None, out_fp32=False, res_row_mod=0, block_n=0, norm_mode=0,
-            stats_in=None, colsum=None, eps=0.0, want_stats=False, rope=None, rope_heads=0):
+            stats_in=None, colsum=None, eps=0.0, want_stats=False, rope=None, rope_heads=0, a_t=False, b_t=False):
     """lp_gemm_bf16_ex: lp_gemm_bf16 plus the epilogue fusions — `norm_mode` (NORM_RMS / NORM_LAYER) normalises the rows of
     `a` from `stats_in` fp32 [M, parts, 2] (w must be the gain-folded matrix; LAYER also needs `colsum` and the folded bias),
     `want_stats` returns (out, stats [M, parts, 2]) of the bf16 outputs, `rope` = (cos, sin) fp32 [M, 64] rotates the first
-    `rope_heads` 128-column heads."""
+    `rope_heads` 128-column heads.  `a_t` / `b_t`: the operand is given transposed — a as At [K, M], w as Wt [K, N] — and is
+    consumed as an MN-major tensor-core operand without a transposed copy (the SFT step's dgrad / wgrad)."""
     _chk_bf16(a, "a")
     _chk_bf16(w, "w")
-    M, K = a.shape
-    N = w.shape[0]
+    K, M = a.shape if a_t else a.shape[::-1]
+    N = w.shape[1] if b_t else w.shape[0]
+    if (w.shape[0] if b_t else w.shape[1]) != K:
+        raise ValueError(f"K mismatch: a {tuple(a.shape)} (a_t={a_t}) vs w {tuple(w.shape)} (b_t={b_t})")
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
@@ -89,6 +92,7 @@ def gemm_ex(a, w, bias=None, residual=None, act=ACT_NONE, out=None, out_fp32=Fal
         d.stats_out, d.stats_out_parts = _lib.ptr(stats), parts
     if rope is not None:
         d.rope_cos, d.rope_sin, d.rope_heads = _lib.ptr(rope[0]), _lib.ptr(rope[1]), rope_heads
+    d.a_t, d.b_t = int(bool(a_t)), int(bool(b_t))
     rc = _lib.lib().lp_gemm_bf16_ex(C.byref(d), _lib.stream_ptr())
     _lib.check(rc, "lp_gemm_bf16_ex")
     return (out, stats) if want_stats else out

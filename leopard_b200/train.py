@@ -172,6 +172,14 @@ class SFTTrainer:
         if not hasattr(engine, "_trainers"):
             engine._trainers = []
         engine._trainers.append(weakref.ref(self))
+        # dgrad / wgrad operands: "mn" = the GEMM consumes the row-major tensors as MN-major operands (lp_gemm_bf16_ex a_t / b_t), no
+        # transposed copies; "transpose" = explicit lp_transpose_bf16 copies (any shape).  Shapes the MN launch cannot take (N not a
+        # multiple of 256, fewer tiles than SM pairs: the vision tower's 1152-wide matrices) use the copies either way.
+        self.operands = os.environ.get("LEOPARD_SFT_OPERANDS", "mn")
+        try:
+            self._pairs = torch.cuda.get_device_properties(self.dev).multi_processor_count // 2
+        except Exception:  # noqa: BLE001  (CPU sequencing tests run this file against the op-contract restatement)
+            self._pairs = 74
         self.attn_bwd = attn_bwd or os.environ.get("LEOPARD_ATTN_BWD", "flash")   # flash: 73 vs 102 ms per 4-layer step on a B200
         if self.attn_bwd not in ("materialized", "flash"):
             raise ValueError(f"attn_bwd must be 'materialized' or 'flash', got {self.attn_bwd!r}")
@@ -220,10 +228,16 @@ class SFTTrainer:
                 named[n].copy_(sd["main"][n])
 
     # ------------------------------------------------------------------ GEMM forms
-    @staticmethod
-    def _dgrad(dy: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
-        """dX[M, K] = dY[M, N] W[N, K]: the GEMM contracts contiguous dims, so it is fed W^T [K, N]."""
+    def _dgrad(self, dy: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
+        """dX[M, K] = dY[M, N] W[N, K]: W is the contraction-major ("transposed") operand — consumed MN-major in place when the
+        shape allows, else through an explicit W^T [K, N] copy."""
+        if self._mn_ok(dy.shape[0], w.shape[1]):
+            return ops.gemm_ex(dy, w, out=out, b_t=True)
         return ops.gemm(dy, ops.transpose(w), out=out)
+
+    def _mn_ok(self, m: int, n: int) -> bool:
+        """Can lp_gemm_bf16_ex take this [m, n] output with transposed operands (CTA-pair mode, 256-wide tiles)?"""
+        return (self.operands == "mn" and n % 256 == 0 and m % 8 == 0 and m > 128 and -(-m // 256) * (n // 256) >= self._pairs)
 
     def _sink(self, name: str) -> Optional[torch.Tensor]:
         """Where a kernel that OVERWRITES its output should write the gradient of `name`: the tensor's slice of the flat
@@ -248,7 +262,10 @@ class SFTTrainer:
         """grad[name][N, K] (fp32) (+)= dY^T[N, M] X[M, K], fed dY^T and X^T [K, M]; skipped when frozen."""
         sink = self._sink(name)
         if sink is not None:
-            ops.gemm(ops.transpose(dy), ops.transpose(x), out=sink)
+            if self._mn_ok(dy.shape[1], x.shape[1]):      # dY [tokens, N] = At, X [tokens, K] = Wt: both consumed in place
+                ops.gemm_ex(dy, x, out=sink, a_t=True, b_t=True)
+            else:
+                ops.gemm(ops.transpose(dy), ops.transpose(x), out=sink)
             self._commit(name, sink)
 
     def _rms_bwd(self, name: str, x, gamma, dy, add=None) -> torch.Tensor:

@@ -45,6 +45,13 @@ def gemm(a, w, bias=None, residual=None, act=ACT_NONE, out=None, out_fp32=False,
     return _store(y, out, torch.float32 if out_fp32 else BF)
 
 
+def gemm_ex(a, w, bias=None, out=None, out_fp32=False, a_t=False, b_t=False, **unsupported):
+    """lp_gemm_bf16_ex's transposed-operand contract (what train.py uses it for): a_t -> `a` is At [K, M]; b_t -> `w` is Wt [K, N].
+    The epilogue fusions of the prefill path are restated next to their tests (tests/test_gemm_kernel_emulated.py), not here."""
+    assert not any(v for v in unsupported.values()), f"native_ops.gemm_ex: not restated here: {sorted(unsupported)}"
+    return gemm(a.t() if a_t else a, w.t() if b_t else w, bias=bias, out=out, out_fp32=out_fp32)
+
+
 def attention(qkv, B, T, n_heads, n_kv_heads, head_dim, head_stride, q_off, k_off, v_off, causal, scale=None, out=None,
               variant=0):
     scale = head_dim ** -0.5 if scale is None else scale

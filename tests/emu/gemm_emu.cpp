@@ -227,3 +227,33 @@ extern "C" void emu_gemm_chain(const void* X, long long ldx, const void* W1, con
   CUtensorMap tmC2 = tmap2(out, N2, M, ldo, 32, 32, 2, 64);
   emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { gemm_chain_kernel<BN, 6>(tmA1, tmB1, tmC1, tmA2, tmB2, tmC2, a); });
 }
+
+
+// Transposed operands (lp_gemm_desc a_t / b_t): A given as At [K, M], W as Wt [K, N]; pair mode, 256-wide tiles, plain epilogue.
+// Argument preparation as in lp_gemm_bf16_ex's a_t / b_t branch.
+extern "C" void emu_gemm_mn(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                            const float* bias, int out_fp32, int a_t, int b_t, int ctas) {
+  constexpr int BN = 256;
+  GemmArgs args = {};
+  args.M = M; args.N = N; args.K = K; args.C = C; args.ldc = ldc; args.out_fp32 = out_fp32; args.bias = bias; args.act = LP_ACT_NONE;
+  args.num_m_blk = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  args.num_n_blk = (N + BN - 1) / BN;
+  args.num_k_blk = (K + GEMM_BK - 1) / GEMM_BK;
+  args.group_m = args.num_m_blk;
+  if (g_sk_ws != nullptr) {
+    const int T = args.num_m_blk * args.num_n_blk, n_units = ctas / 2;
+    if (T > n_units && T % n_units != 0) {
+      args.dp_tiles = (T / n_units - 1) * n_units;
+      args.sk_tiles = T - args.dp_tiles;
+      args.sk_flags = reinterpret_cast<unsigned*>(g_sk_ws);
+      args.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_sk_ws) + 4096);
+    }
+  }
+  CUtensorMap tmC = tmap2(C, N, M, ldc, 32, 32, 2, 64);
+  CUtensorMap tmA = a_t ? tmap2(A, M, K, lda, 64, GEMM_BK, 2, 128) : tmap2(A, K, M, lda, GEMM_BK, GEMM_BM, 2, 128);
+  CUtensorMap tmB = b_t ? tmap2(W, N, K, ldw, 64, GEMM_BK, 2, 128) : tmap2(W, K, N, ldw, GEMM_BK, BN / 2, 2, 128);
+  auto go = [&](auto kern) { emu_tc::launch_pairs(dim3(ctas), dim3(GEMM_THREADS), [&] { kern(tmA, tmB, tmC, args); }); };
+  if (a_t && b_t) go(gemm_bf16_mn_kernel<BN, 6, true, true>);
+  else if (a_t) go(gemm_bf16_mn_kernel<BN, 6, true, false>);
+  else go(gemm_bf16_mn_kernel<BN, 6, false, true>);
+}

@@ -320,7 +320,7 @@ inline void umma_exec(uint32_t tmem_d, bool a_in_tmem, uint32_t tmem_a, uint64_t
                       uint32_t accumulate, bool pair) {
   const int M = (int)((idesc >> 24) & 0x1f) << 4, N = (int)((idesc >> 17) & 0x3f) << 3;
   const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
-  if (M != (pair ? 256 : 128) || a_mn || (pair && (a_in_tmem || b_mn))) {
+  if (M != (pair ? 256 : 128) || (a_mn && a_in_tmem) || (pair && a_in_tmem)) {
     std::fprintf(stderr, "emu: unsupported UMMA shape M=%d a_mn=%d pair=%d\n", M, (int)a_mn, (int)pair);
     std::abort();
   }
@@ -344,7 +344,10 @@ inline void umma_exec(uint32_t tmem_d, bool a_in_tmem, uint32_t tmem_a, uint64_t
         const uint32_t w = cm.tmem[ml][acol + (k >> 1)];
         a[k] = emu_tc::bf_bits((uint16_t)((k & 1) ? (w >> 16) : (w & 0xffff)));
       } else {
-        a[k] = ld(cm.smem, start(desc_a) + (ml >> 3) * sbo(desc_a) + (ml & 7) * 128 + k * 2);
+        // MN-major A (transposed operand): 64-row (m) slabs LBO apart, k rows of 128 B in 8-row groups SBO apart — the same
+        // reading of the descriptor as the MN-major B below, which the attention kernels validate on hardware
+        a[k] = a_mn ? ld(cm.smem, start(desc_a) + (ml >> 6) * lbo(desc_a) + (k >> 3) * sbo(desc_a) + (k & 7) * 128 + (ml & 63) * 2)
+                    : ld(cm.smem, start(desc_a) + (ml >> 3) * sbo(desc_a) + (ml & 7) * 128 + k * 2);
       }
     }
     for (int n = 0; n < N; ++n) {

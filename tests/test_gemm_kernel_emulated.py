@@ -442,3 +442,34 @@ def test_pure_stream_k_for_norm_consumers_is_bit_identical(emu, M, N, K, bn, pai
     assert not bool(torch.isnan(outs[1].float()).any())
     assert torch.equal(outs[0], outs[1])
     assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+
+
+# ---- transposed (MN-major) operands: the SFT step's dgrad and wgrad without transposed copies ------------------------------------
+@pytest.mark.parametrize("M,N,K,a_t,b_t,fp32,bias,sk", [
+    (520, 512, 200, False, True, False, False, False),     # dgrad: dX = dY W with W given as [K, N]; ragged M and K
+    (512, 256, 330, True, True, True, False, False),       # wgrad: dW = dY^T X, both operands transposed, fp32 output
+    (776, 768, 136, True, False, False, True, False),      # A transposed only, bias, M a multiple of 8 but not of the tile
+    (600, 1280, 320, False, True, False, False, True),     # with the stream-K tail (15 tiles on 2 pairs)
+])
+def test_transposed_operand_gemm_under_emulation(emu, M, N, K, a_t, b_t, fp32, bias, sk):
+    g = torch.Generator().manual_seed(M + N + K + 7)
+    a = torch.randn((M, K), generator=g).to(BF)
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).to(BF)
+    b = torch.randn(N, generator=g) if bias else None
+    A = a.t().contiguous() if a_t else a                         # what the caller holds: At [K, M] / Wt [K, N]
+    W = w.t().contiguous() if b_t else w
+    want = ref.gemm(a, w, bias=b, out_fp32=fp32)
+    out = torch.full((M, N), float("nan"), dtype=torch.float32 if fp32 else BF)
+    ws = torch.zeros(4096 + 4 * 128 * 256 * 4, dtype=torch.uint8)
+    emu.emu_gemm_set_streamk(P(ws) if sk else None)
+    try:
+        emu.emu_gemm_mn(P(A), LL(A.stride(0)), P(W), LL(W.stride(0)), P(out), LL(N), M, N, K, P(b), int(fp32), int(a_t), int(b_t), 4)
+    finally:
+        emu.emu_gemm_set_streamk(None)
+    assert not bool(torch.isnan(out.float()).any())
+    err = float((out.float() - want.float()).abs().max() / want.float().abs().max())
+    assert err < (1e-5 if fp32 else 8e-3), err
+    # same bits as the K-major kernel on explicitly transposed copies (same accumulation order)
+    out2 = torch.full((M, N), float("nan"), dtype=torch.float32 if fp32 else BF)
+    emu.emu_gemm(P(a), LL(K), P(w), LL(K), P(out2), LL(N), M, N, K, P(b), None, LL(0), 0, 0, int(fp32), 256, 1, 1, 4)
+    assert torch.equal(out, out2)

@@ -319,3 +319,29 @@ def test_gemm_stream_k_and_tma_residual_do_not_change_a_bit(native_lib, M, N, K,
         assert torch.equal(o, base), f"streamk={key[0]} tma_residual={key[1]} changed the output"
         if stats:
             assert torch.equal(st, base_st), f"streamk={key[0]} tma_residual={key[1]} changed the row statistics"
+
+
+@pytest.mark.parametrize("M,N,K,a_t,b_t,fp32", [
+    (4096, 4096, 14336, False, True, False),     # dgrad of the down projection: dX = dY W_down, W given as [K, N]
+    (4096, 14336, 4096, True, True, True),       # wgrad of gate / up (half of it): dW = dY^T X, fp32 output, both operands transposed
+    (6144, 4096, 4104, True, True, True),        # wgrad of qkv, ragged contraction length (4104 tokens)
+    (4796, 4096, 4096, False, True, False),      # ragged M
+    (2048, 4096, 1000, True, False, False),      # A transposed only
+])
+def test_gemm_transposed_operands_match_explicit_transposes_bit_for_bit(native_lib, M, N, K, a_t, b_t, fp32):
+    """lp_gemm_desc a_t / b_t (MN-major tensor-core operands straight from the row-major tensors, what the SFT step's dgrad and
+    wgrad use) against fp32 torch, and bit for bit against the same kernel fed explicit transposed copies."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    A = a.t().contiguous() if a_t else a
+    W = w.t().contiguous() if b_t else w
+    got = ops.gemm_ex(A, W, out_fp32=fp32, a_t=a_t, b_t=b_t)
+    plain = ops.gemm(a, w, out_fp32=fp32, block_n=256)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    if fp32:
+        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5
+    else:
+        _close(got, ref, BF, 1.0)
+    assert torch.equal(got, plain)
