@@ -67,7 +67,7 @@ int lp_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, voi
  *   a_t / b_t (transposed operands, the SFT step's dgrad and wgrad; autograd's `grad_output @ weight` and `grad_output.t() @ input`
  *     of torch.nn.functional.linear): a_t: A is given as At [K, M] row-major (lda = its row stride); b_t: W is given as Wt [K, N]
  *     row-major (ldw).  The tiles are fed to the tensor core as MN-major operands — no transposed copy is made.  Needs the CTA-pair
- *     mode (M > 128 and at least one tile per SM pair), N % 256 == 0, M % 8 == 0 when a_t; plain epilogue (bias / out_fp32 only). */
+ *     mode (M > 128 and at least one 256 x 256 tile per SM pair), M % 8 == 0 when a_t; plain epilogue (bias / out_fp32 only). */
 enum lp_norm_mode { LP_NORM_NONE = 0, LP_NORM_RMS = 1, LP_NORM_LAYER = 2 };
 typedef struct lp_gemm_desc {
   const void* A; long long lda;

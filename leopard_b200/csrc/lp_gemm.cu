@@ -40,7 +40,7 @@ namespace lp {
 // is the ROW index) — and is fed to the tensor core as an MN-major operand: TMA brings 64 (k rows) x 64 (m or n columns) boxes into
 // 8 KiB slabs, the UMMA descriptor walks them with LBO = slab stride, a K = 16 step advances 16 rows = 2 KiB.  This is what the SFT
 // step's dgrad (dX = dY W: W is "Wt") and wgrad (dW = dY^T X: both operands) need; no transposed copies are materialised.
-// Tile width BN = 256 columns and N % 256 == 0 (the slabs of a ragged last column block would not line up).
+// Tile width BN = 256 columns; a ragged last column block runs the full-width MMA on zero-filled columns.
 template <int BN, int STAGES, bool CTA2, bool TP, int RES, bool A_MN = false, bool B_MN = false>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                           const CUtensorMap* segC, const CUtensorMap& tmR, const GemmArgs& args) {
@@ -118,7 +118,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           gathered = true;
         }
         // ragged last column block: the MMA runs with N = n_rt (multiple of 32), so a pair splits n_rt, not BN
-        const int n_rt = min(BN, ((args.N - n_blk * BN) + 31) & ~31);
+        // (transposed operands always run full-width MMAs: their 64-column slabs would not line up with a narrower last block; the
+        //  columns beyond N are TMA zero fill and are clipped by the stores)
+        const int n_rt = (A_MN || B_MN) ? BN : min(BN, ((args.N - n_blk * BN) + 31) & ~31);
         const int b_row = n_blk * BN + (CTA2 ? (int)cta_rank * (n_rt / 2) : 0);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           // (an explicit cp.async.bulk.prefetch.tensor.L2 of the k-block 8 ahead was measured: every CTA of a
@@ -163,7 +165,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         int m_blk_unused, n_blk;
         tile_coords(args, w.tile, m_blk_unused, n_blk);
         // the last column block of a ragged N issues narrower MMAs (N = valid columns rounded up to 32)
-        const uint32_t idesc = umma_idesc_bf16(BMT, min(BN, ((args.N - n_blk * BN) + 31) & ~31), A_MN ? 1 : 0, B_MN ? 1 : 0);
+        const uint32_t idesc = umma_idesc_bf16(BMT, (A_MN || B_MN) ? BN : min(BN, ((args.N - n_blk * BN) + 31) & ~31), A_MN ? 1 : 0,
+                                               B_MN ? 1 : 0);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         const bool resume = w.kind == GEMM_ITEM_END;   // the accumulator continues another unit's partial sums
         if (resume) mbar_wait(tpre_bar, 0);
@@ -758,9 +761,9 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
   }
   const bool a_t = d->a_t != 0, b_t = d->b_t != 0;
   if (a_t || b_t) {
-    LP_REQUIRE(pair && block_n == 256 && N % 256 == 0 && (!a_t || M % 8 == 0),
-               "lp_gemm_bf16_ex: transposed operands need the CTA-pair mode (M=%d N=%d: at least one 256-row tile per SM pair), block_n "
-               "256 and N %% 256 == 0", M, N);
+    LP_REQUIRE(pair && block_n == 256 && (!a_t || M % 8 == 0),
+               "lp_gemm_bf16_ex: transposed operands need the CTA-pair mode (M=%d N=%d: at least one 256-row tile per SM pair) and "
+               "block_n 256", M, N);
     LP_REQUIRE(residual == nullptr && act == LP_ACT_NONE && d->norm_mode == LP_NORM_NONE && d->stats_out == nullptr && d->rope_heads == 0,
                "lp_gemm_bf16_ex: transposed operands take the plain epilogue (bias / fp32 output only)");
   }

@@ -173,8 +173,8 @@ class SFTTrainer:
             engine._trainers = []
         engine._trainers.append(weakref.ref(self))
         # dgrad / wgrad operands: "mn" = the GEMM consumes the row-major tensors as MN-major operands (lp_gemm_bf16_ex a_t / b_t), no
-        # transposed copies; "transpose" = explicit lp_transpose_bf16 copies (any shape).  Shapes the MN launch cannot take (N not a
-        # multiple of 256, fewer tiles than SM pairs: the vision tower's 1152-wide matrices) use the copies either way.
+        # transposed copies; "transpose" = explicit lp_transpose_bf16 copies (any shape).  Shapes the MN launch cannot take (fewer
+        # 256 x 256 tiles than SM pairs: the vision tower's 1152 x 1152 matrices) use the copies either way.
         self.operands = os.environ.get("LEOPARD_SFT_OPERANDS", "mn")
         try:
             self._pairs = torch.cuda.get_device_properties(self.dev).multi_processor_count // 2
@@ -237,7 +237,7 @@ class SFTTrainer:
 
     def _mn_ok(self, m: int, n: int) -> bool:
         """Can lp_gemm_bf16_ex take this [m, n] output with transposed operands (CTA-pair mode, 256-wide tiles)?"""
-        return (self.operands == "mn" and n % 256 == 0 and m % 8 == 0 and m > 128 and -(-m // 256) * (n // 256) >= self._pairs)
+        return (self.operands == "mn" and n % 8 == 0 and m % 8 == 0 and m > 128 and -(-m // 256) * -(-n // 256) >= self._pairs)
 
     def _sink(self, name: str) -> Optional[torch.Tensor]:
         """Where a kernel that OVERWRITES its output should write the gradient of `name`: the tensor's slice of the flat

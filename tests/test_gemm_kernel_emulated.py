@@ -450,6 +450,8 @@ def test_pure_stream_k_for_norm_consumers_is_bit_identical(emu, M, N, K, bn, pai
     (512, 256, 330, True, True, True, False, False),       # wgrad: dW = dY^T X, both operands transposed, fp32 output
     (776, 768, 136, True, False, False, True, False),      # A transposed only, bias, M a multiple of 8 but not of the tile
     (600, 1280, 320, False, True, False, False, True),     # with the stream-K tail (15 tiles on 2 pairs)
+    (520, 1152, 136, True, True, True, False, False),      # ragged last column block (1152 = 4.5 tiles): full-width MMA on zero fill
+    (300, 200, 72, False, True, False, True, False),       # N smaller than one tile, bias
 ])
 def test_transposed_operand_gemm_under_emulation(emu, M, N, K, a_t, b_t, fp32, bias, sk):
     g = torch.Generator().manual_seed(M + N + K + 7)

@@ -327,6 +327,8 @@ def test_gemm_stream_k_and_tma_residual_do_not_change_a_bit(native_lib, M, N, K,
     (6144, 4096, 4104, True, True, True),        # wgrad of qkv, ragged contraction length (4104 tokens)
     (4796, 4096, 4096, False, True, False),      # ragged M
     (2048, 4096, 1000, True, False, False),      # A transposed only
+    (4304, 1152, 14196, True, True, True),       # vision tower fc1 wgrad at 21 crops: ragged last column block, ragged contraction
+    (14196, 4304, 1152, False, True, False),     # vision tower fc2 dgrad: N = 4304 (16.8 tiles)
 ])
 def test_gemm_transposed_operands_match_explicit_transposes_bit_for_bit(native_lib, M, N, K, a_t, b_t, fp32):
     """lp_gemm_desc a_t / b_t (MN-major tensor-core operands straight from the row-major tensors, what the SFT step's dgrad and
