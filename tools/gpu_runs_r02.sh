@@ -173,4 +173,37 @@ r02l() {
   ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
 }
 
+r02o() {
+  # Idefics2 GPU image processor + pure stream-K A/B (cfg3 and cfg2)
+  T=${TAG:-r02o}
+  run tests python -m pytest tests/test_gpu_frontend.py tests/test_gpu_idefics2.py tests/test_gpu_ops.py -x -q
+  run ab_cfg3 python tools/gpu_ab_prefill.py sk=1 sk=2
+  LEOPARD_AB_WORKLOAD=cfg2 run ab_cfg2 python tools/gpu_ab_prefill.py sk=1 sk=2
+}
+
+r02p() {
+  # decode: L2 prefetch of the next projections' weights during the attention kernel
+  T=${TAG:-r02p}
+  TMO=900 run decode_prefetch python tools/gpu_decode_prefetch.py
+  run tests python -m pytest tests/test_gpu_hf.py tests/test_gpu_decode.py -x -q
+}
+
+r02r() {
+  # cfg5 bench line with explicit transposes vs MN-major operands (tower trainable), and frozen
+  T=${TAG:-r02r}
+  LEOPARD_SFT_OPERANDS=transpose run cfg5_transpose python bench.py --workload cfg5 --steps 3
+  LEOPARD_SFT_OPERANDS=mn run cfg5_mn python bench.py --workload cfg5 --steps 3
+  LEOPARD_SFT_OPERANDS=mn run cfg5_mn_frozen python bench.py --workload cfg5 --steps 3 --sft-freeze-vit
+}
+
+r02q() {
+  # Round 2: transposed (MN-major) GEMM operands for the SFT step's dgrad / wgrad — parity, then the step with and without them.
+  T=${TAG:-r02q}
+  run ops python -m pytest tests/test_gpu_ops.py -x -q -k "transposed or stream_k"
+  TMO=900 run train_tests python -m pytest tests/test_zz_gpu_train.py -x -q
+  LEOPARD_SFT_OPERANDS=transpose TMO=600 run sft_transpose python tools/gpu_train_speed.py --steps 3
+  LEOPARD_SFT_OPERANDS=mn TMO=600 run sft_mn python tools/gpu_train_speed.py --steps 3
+  ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
+}
+
 "$@"
