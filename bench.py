@@ -161,6 +161,11 @@ def run_reference(args):
     import torch
     from benchmarks.cpu_reference import CpuSample
     from leopard_b200.config import leopard_llava
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and takes every host thread it may use
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     cfg = leopard_llava()
     _, _, n_crops, S, per_image = make_workload(cfg, args.workload)
     sample = CpuSample(cfg, n_crops, S, sample_crops=args.cpu_sample_crops)
