@@ -149,11 +149,13 @@ resample_h_kernel(const uint8_t* __restrict__ in, long long in_pitch, long long 
 // tmp [h_in, w*3 bytes] (pitch multiple of 16) -> resized rows oy in [0, h_out); pixel (oy, x) lands at canvas position
 // (paste_y + oy, paste_x + x) of a canvas that is cut into 364 x 364 tiles, tiles_x per canvas row; tile t is written
 // at out + t * tile_stride elements, planar [3][364][364].
-template <typename OutT>
+// TILE = FE_CROP: the LLaVA crop grid with compile-time divisions; TILE = 0: tile_w_rt x tile_h_rt (Idefics2: one planar canvas)
+template <typename OutT, int TILE>
 __global__ void __launch_bounds__(256)
 resample_v_kernel(const uint8_t* __restrict__ tmp, long long pitch, int w, int h_out, const int2* __restrict__ bounds,
-                  const int* __restrict__ coeffs, int paste_x, int paste_y, int tiles_x, int tile_w, int tile_h,
+                  const int* __restrict__ coeffs, int paste_x, int paste_y, int tiles_x, int tile_w_rt, int tile_h_rt,
                   OutT* __restrict__ out, long long tile_stride, const FeLut lut) {
+  const int tile_w = TILE ? TILE : tile_w_rt, tile_h = TILE ? TILE : tile_h_rt;
   __shared__ float s_lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = lut.v[i >> 8][i & 255];
   __syncthreads();
@@ -217,10 +219,11 @@ resample_v_raw_kernel(const uint8_t* __restrict__ tmp, long long pitch, int w, i
 }
 
 // canvas pixels outside the pasted rectangle get the normalised value of black
-template <typename OutT>
+template <typename OutT, int TILE>
 __global__ void __launch_bounds__(256)
-pad_fill_kernel(int canvas_w, int canvas_h, int paste_x, int paste_y, int w, int h, int tiles_x, int tile_w, int tile_h,
+pad_fill_kernel(int canvas_w, int canvas_h, int paste_x, int paste_y, int w, int h, int tiles_x, int tile_w_rt, int tile_h_rt,
                 OutT* __restrict__ out, long long tile_stride, float pad0, float pad1, float pad2) {
+  const int tile_w = TILE ? TILE : tile_w_rt, tile_h = TILE ? TILE : tile_h_rt;
   const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
   if (cx >= canvas_w || cy >= canvas_h) return;
   if (cy >= paste_y && cy < paste_y + h && cx >= paste_x && cx < paste_x + w) return;
@@ -268,6 +271,7 @@ template <typename OutT>
 static int fe_resize_into(const uint8_t* rgb, int H, int W, int w_out, int h_out, const FeTarget& tg, OutT* out, const FeLut& lut,
                           uint8_t* ws, cudaStream_t stream) {
   const int canvas_w = tg.canvas_w, canvas_h = tg.canvas_h, paste_x = tg.paste_x, paste_y = tg.paste_y, filter = tg.filter;
+  const bool crop_tiles = tg.tile_w == FE_CROP && tg.tile_h == FE_CROP;
   const int kx = fe_ksize(W, w_out, filter), ky = fe_ksize(H, h_out, filter);
   LP_REQUIRE(kx <= FE_MAX_KSIZE && ky <= FE_MAX_KSIZE, "lp_image_frontend: downscale factor above 32 (%dx%d -> %dx%d)",
              W, H, w_out, h_out);
@@ -302,14 +306,25 @@ static int fe_resize_into(const uint8_t* rgb, int H, int W, int w_out, int h_out
     const int tiles_x1 = canvas_w / tg.tile_w;
     const long long tile_stride1 = 3LL * tg.tile_w * tg.tile_h;
     if (w_out != canvas_w || h_out != canvas_h) {
-      pad_fill_kernel<OutT><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
-          canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x1, tg.tile_w, tg.tile_h, out, tile_stride1, tg.pad[0],
-          tg.pad[1], tg.pad[2]);
+      if (crop_tiles) {
+        pad_fill_kernel<OutT, FE_CROP><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
+            canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x1, tg.tile_w, tg.tile_h, out, tile_stride1, tg.pad[0],
+            tg.pad[1], tg.pad[2]);
+      } else {
+        pad_fill_kernel<OutT, 0><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
+            canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x1, tg.tile_w, tg.tile_h, out, tile_stride1, tg.pad[0],
+            tg.pad[1], tg.pad[2]);
+      }
       note_launch();
     }
     const int g2 = (w_out * 3 + 3) / 4;
-    resample_v_kernel<OutT><<<dim3((g2 + 255) / 256, h_out), 256, 0, stream>>>(
-        t2, (long long)pitch, w_out, h_out, byi, cyi, paste_x, paste_y, tiles_x1, tg.tile_w, tg.tile_h, out, tile_stride1, lut);
+    if (crop_tiles) {
+      resample_v_kernel<OutT, FE_CROP><<<dim3((g2 + 255) / 256, h_out), 256, 0, stream>>>(
+          t2, (long long)pitch, w_out, h_out, byi, cyi, paste_x, paste_y, tiles_x1, tg.tile_w, tg.tile_h, out, tile_stride1, lut);
+    } else {
+      resample_v_kernel<OutT, 0><<<dim3((g2 + 255) / 256, h_out), 256, 0, stream>>>(
+          t2, (long long)pitch, w_out, h_out, byi, cyi, paste_x, paste_y, tiles_x1, tg.tile_w, tg.tile_h, out, tile_stride1, lut);
+    }
     note_launch(8);
     LP_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -333,14 +348,25 @@ static int fe_resize_into(const uint8_t* rgb, int H, int W, int w_out, int h_out
   const int tiles_x = canvas_w / tg.tile_w;
   const long long tile_stride = 3LL * tg.tile_w * tg.tile_h;
   if (w_out != canvas_w || h_out != canvas_h) {
-    pad_fill_kernel<OutT><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
-        canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x, tg.tile_w, tg.tile_h, out, tile_stride, tg.pad[0], tg.pad[1],
-        tg.pad[2]);
+    if (crop_tiles) {
+      pad_fill_kernel<OutT, FE_CROP><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
+          canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x, tg.tile_w, tg.tile_h, out, tile_stride, tg.pad[0], tg.pad[1],
+          tg.pad[2]);
+    } else {
+      pad_fill_kernel<OutT, 0><<<dim3((canvas_w + 255) / 256, canvas_h), 256, 0, stream>>>(
+          canvas_w, canvas_h, paste_x, paste_y, w_out, h_out, tiles_x, tg.tile_w, tg.tile_h, out, tile_stride, tg.pad[0], tg.pad[1],
+          tg.pad[2]);
+    }
     note_launch();
   }
   const int groups = (w_out * 3 + 3) / 4;
-  resample_v_kernel<OutT><<<dim3((groups + 255) / 256, h_out), 256, 0, stream>>>(
-      tmp, (long long)pitch, w_out, h_out, by, cys, paste_x, paste_y, tiles_x, tg.tile_w, tg.tile_h, out, tile_stride, lut);
+  if (crop_tiles) {
+    resample_v_kernel<OutT, FE_CROP><<<dim3((groups + 255) / 256, h_out), 256, 0, stream>>>(
+        tmp, (long long)pitch, w_out, h_out, by, cys, paste_x, paste_y, tiles_x, tg.tile_w, tg.tile_h, out, tile_stride, lut);
+  } else {
+    resample_v_kernel<OutT, 0><<<dim3((groups + 255) / 256, h_out), 256, 0, stream>>>(
+        tmp, (long long)pitch, w_out, h_out, by, cys, paste_x, paste_y, tiles_x, tg.tile_w, tg.tile_h, out, tile_stride, lut);
+  }
   note_launch(4);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
