@@ -169,7 +169,9 @@ int lp_set_prefill_pdl(int enable);
  *   2^x, rel. error 1.1e-4) instead of MUFU.EX2;
  * variant bit 6 (64): v3 kernel (lp_attn3.cu) — two query tiles, S in 64-key halves, one MMA issuer per tile; the
  *   softmax row sum is taken in fp32 before P is rounded to bf16 (as flash-attention does);
- * variant bits 4 / 5 (16 / 32): force the softmax turn protocol on / off (see lp_attention_set_pingpong). */
+ * variant bits 4 / 5 (16 / 32): force the softmax turn protocol on / off (see lp_attention_set_pingpong);
+ * variant bit 7 (128): v4 kernel (lp_attn4.cu) — v3's dataflow, but ONE softmax warpgroup whose thread r owns row r of both
+ *   query tiles and runs their exponentials as two independent instruction streams (no turn protocol). */
 int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, int n_kv_heads, int head_dim,
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);

@@ -76,6 +76,30 @@ __device__ __forceinline__ uint64_t a3_add2(uint64_t a, uint64_t b) {
       "r"(regs[14]), "r"(regs[15])                                                                                  \
       : "memory")
 
+// Phase trace (tools/micro/attn_trace.cu compiles this file with -DLP_ATTN_TRACE): lane 0 of the two issuer warps and of the first
+// warp of each softmax warpgroup of ONE chosen CTA stamp clock64() at the protocol points below; no code in normal builds.
+#ifdef LP_ATTN_TRACE
+__device__ unsigned long long* g_a3_trace = nullptr;   // [4 slots][4096]: slot 0 / 1 = issuer A / B, 2 / 3 = softmax A / B
+__device__ int g_a3_trace_blk = 0;
+#define A3_TRACE_INIT()                                                                                                   \
+  unsigned long long* tr_buf = nullptr;                                                                                   \
+  int tr_n = 0;                                                                                                           \
+  if ((int)blockIdx.y == g_a3_trace_blk && blockIdx.x == 0 && blockIdx.z == 0 && lane == 0 && g_a3_trace != nullptr &&    \
+      (warp == 1 || warp == 2 || warp == 4 || warp == 8))                                                                 \
+    tr_buf = g_a3_trace + (warp == 1 ? 0 : warp == 2 ? 1 : warp == 4 ? 2 : 3) * 4096
+#define A3_TRACE(id)                                                                                                      \
+  do {                                                                                                                    \
+    if (tr_buf != nullptr && tr_n < 4094) {                                                                               \
+      tr_buf[1 + tr_n] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xffffffffffffULL);          \
+      ++tr_n;                                                                                                             \
+      tr_buf[0] = (unsigned long long)tr_n;                                                                               \
+    }                                                                                                                     \
+  } while (0)
+#else
+#define A3_TRACE_INIT() do {} while (0)
+#define A3_TRACE(id) do {} while (0)
+#endif
+
 // EMU: how many of every 4 exponentials are evaluated with a3_ex2_fma instead of MUFU.EX2 (0, 1 or 2)
 template <int DH, bool CAUSAL, int EMU>
 __global__ void __launch_bounds__(A3_THREADS, 1)
@@ -98,15 +122,21 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
   uint64_t* v_empty = k_empty + 4;                                  // [4]
   uint64_t* s_full = v_empty + 4;                                   // [4]   q tile x half
   uint64_t* p_full = s_full + 4;                                    // [4]
-  uint64_t* pv_done = p_full + 4;                                   // [2]   one phase per P·V half
-  uint64_t* o_done = pv_done + 2;                                   // [2]
+  uint64_t* pv_done = p_full + 4;                                   // [4]   q tile x (half-step index & 1): one phase per P·V half
+  uint64_t* o_done = pv_done + 4;                                   // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  A3_TRACE_INIT();
 
-  const int qp = (int)gridDim.x - 1 - (int)blockIdx.x;  // heavy (late) causal pairs first
-  const int head = blockIdx.y, batch = blockIdx.z;
+  // Grid = (heads, query-tile pairs, batch) with the heads fastest and the pairs in descending order: the block scheduler hands out
+  // CTAs in linear order, so every head's heaviest causal pair (2 qp + 2 key tiles) starts first and the lightest pairs fill the
+  // tail — longest-processing-time-first over the WHOLE grid.  (With the pairs fastest only each head's own pairs were ordered; the
+  // last heads' 38-tile CTAs started at ~90 % of the kernel and ran alone: 440 k cycles instead of 353 k at S = 4796 by list-scheduling
+  // simulation, 0.208 -> ms measured.)
+  const int qp = (int)gridDim.y - 1 - (int)blockIdx.y;
+  const int head = blockIdx.x, batch = blockIdx.z;
   const int kv_head = head / args.group;
   const int T = args.T;  // self-attention only: Tk == T
   const int q0A = qp * 256, q0B = q0A + 128;
@@ -147,10 +177,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       mbar_init(&q_full[i], 1);
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&pv_done[i], 1);
       mbar_init(&o_done[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
+      mbar_init(&pv_done[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
@@ -193,6 +223,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       const uint32_t q_addr = smem_u32(smem + Q_OFF + q * HEAD_BYTES);
       const uint32_t s_tm = tmem_base + TM_S + (uint32_t)q * 128;
       const uint32_t d_o = tmem_base + TM_O + (uint32_t)q * 128;
+      int t_pv = 0;  // P·V halves issued so far
       auto issue_S = [&](int j, int h) {  // S_q(j).h = Q_q K_j[64h .. 64h+63]^T
         const uint32_t k_addr = smem_u32(smem + K_OFF + (j & 1) * HEAD_BYTES) + (uint32_t)h * 64 * 128;
 #pragma unroll
@@ -202,10 +233,13 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                   umma_desc_sw128(k_addr + off, 0, 1024), idesc_s, ks > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[q * 2 + h]);
+        A3_TRACE(14 + h);
       };
       auto issue_PV = [&](int j, int h) {  // O_q += P_q(j).h V_j[64h .. 64h+63]
         const uint32_t v_addr = smem_u32(smem + V_OFF + (j & 1) * HEAD_BYTES);
+        A3_TRACE(10 + h);
         mbar_wait(&p_full[q * 2 + h], j & 1);
+        A3_TRACE(12 + h);
         tc_fence_after();
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
@@ -213,7 +247,8 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           const uint64_t vdesc = umma_desc_sw128(v_addr + ks * 2048, A3_BOX, 1024);
           umma_ts(d_o, s_tm + (uint32_t)h * 64 + k4 * 8, vdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(&pv_done[q]);
+        umma_commit(&pv_done[q * 2 + (t_pv & 1)]);
+        ++t_pv;
       };
       mbar_wait(&q_full[q], 0);
       mbar_wait(&k_full[0], 0);
@@ -264,17 +299,25 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
       auto halves = [&](int n) { return 2 * n - ((n > 0 && (n - 1) * 128 + 64 >= T) ? 1 : 0); };
       const int hA = halves(nA);
       const bool turns = args.pingpong != 0 && actB;
-      for (int j = 0; j < n_q; ++j) {
+      // The S half of step t + 1 goes into the registers of step t's S as soon as its exponentials are done — before P(t) is
+      // handed to the issuer — so the barrier / tcgen05.ld round trips overlap the tcgen05.st drain and the hand-over instead of
+      // heading the next step (phase trace, tools/micro/attn_trace.cu: ~300 of ~2080 cycles per half step).  S(t + 1) never
+      // depends on P(t) (it follows P·V(t - 1) in the issuer's order), so waiting for it first cannot deadlock; it is only tried,
+      // not waited for, before the hand-over.
+      uint32_t v[64];
+      A3_TRACE(1);
+      mbar_wait(&s_full[q * 2 + 0], 0);
+      A3_TRACE(2);
+      tc_fence_after();
+      LP_TMEM_LD_32((v + 0), s_addr + 0);
+      LP_TMEM_LD_32((v + 32), s_addr + 32);
+      int j = 0, h = 0;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+      for (;;) {
+        {
           const int kv0 = j * 128 + h * 64;
-          if (h == 1 && kv0 >= T) break;  // trailing half tile beyond the sequence: skipped by the issuer too
-          mbar_wait(&s_full[q * 2 + h], j & 1);
-          tc_fence_after();
-          uint32_t v[64];
-          LP_TMEM_LD_32((v + 0), s_addr + h * 64 + 0);
-          LP_TMEM_LD_32((v + 32), s_addr + h * 64 + 32);
           tmem_wait_ld();
+          A3_TRACE(3);
           const bool need_mask = (kv0 + 64 > T) || (CAUSAL && j == diag);
           int lim = T - kv0;
           if (CAUSAL && j == diag) lim = min(lim, r + 1 - h * 64);
@@ -297,16 +340,14 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           }
           const float m_new = fmaxf(m_used, mx * args.scale_log2);
           const bool grow = (m_new - m_used) > 8.0f;
-          // pv_done_q completes one phase per P·V half; phase t-1 is consumed exactly once during half step t — early
-          // when O has to be rescaled, otherwise just before P(t) is published (by then it has normally retired).
-          // Consuming every phase in order keeps the parity wait unambiguous (phase t cannot start before P(t)).
-          bool pv_waited = (t == 0);
+          // pv_done[q][b] completes one phase per P·V half with (index & 1) == b; it is looked at only when O has to be rescaled.
+          // Half t - 1 is phase (t - 1) >> 1 of barrier (t - 1) & 1: the phase before it has completed by now (S(t - 1) followed
+          // P·V(t - 3) on the tensor pipe) and the one after it cannot start before P(t + 1), so the parity is unambiguous.
           if (t == 0) {
             m_used = m_new;
           } else if (__any_sync(0xffffffffu, grow)) {
             // every P·V issued so far (halves 0 .. t-1) must have retired before O_q is rescaled in place
-            mbar_wait(&pv_done[q], (t - 1) & 1);
-            pv_waited = true;
+            mbar_wait(&pv_done[q * 2 + ((t - 1) & 1)], ((t - 1) >> 1) & 1);
             tc_fence_after();
             float alpha = 1.0f;
             if (grow) {
@@ -328,10 +369,12 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
           const uint64_t sc2 = a3_pk2(args.scale_log2, args.scale_log2), nm2 = a3_pk2(neg_m, neg_m);
           uint64_t acc2 = a3_pk2(0.f, 0.f);
+          A3_TRACE(4);
           if (turns && t < hA) {
             if (q == 0) { if (t > 0) a3_bar_sync(2, 256); }
             else a3_bar_sync(3, 256);
           }
+          A3_TRACE(5);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t pk[16];
@@ -350,24 +393,49 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             }
             LP3_TMEM_ST_16(pk, s_addr + h * 64 + c * 16);  // P(j).h over the first 32 columns of its own S half
           }
+          A3_TRACE(6);
           if (turns && t < hA) {
             if (q == 0) a3_bar_arrive(3, 256);
             else if (t + 1 < hA) a3_bar_arrive(2, 256);
           }
+          // next half step (the trailing half tile beyond the sequence is skipped by the issuer too)
+          int jn = j, hn = 1;
+          if (h == 1 || j * 128 + 64 >= T) { jn = j + 1; hn = 0; }
+          const bool has_next = jn < n_q;
+          bool loaded = false;
+          if (has_next && mbar_test_wait(&s_full[q * 2 + hn], jn & 1)) {
+            tc_fence_after();
+            LP_TMEM_LD_32((v + 0), s_addr + hn * 64 + 0);
+            LP_TMEM_LD_32((v + 32), s_addr + hn * 64 + 32);
+            loaded = true;
+          }
           tmem_wait_st();
           tc_fence_before();
-          if (!pv_waited) mbar_wait(&pv_done[q], (t - 1) & 1);
+          A3_TRACE(7);
           mbar_arrive(&p_full[q * 2 + h]);
+          A3_TRACE(8);
           {
             float a0, a1;
             a3_upk2(acc2, a0, a1);
             l_sum += a0 + a1;
           }
           ++t;
+          if (!has_next) break;
+          if (!loaded) {
+            A3_TRACE(1);
+            mbar_wait(&s_full[q * 2 + hn], jn & 1);
+            A3_TRACE(2);
+            tc_fence_after();
+            LP_TMEM_LD_32((v + 0), s_addr + hn * 64 + 0);
+            LP_TMEM_LD_32((v + 32), s_addr + hn * 64 + 32);
+          }
+          j = jn;
+          h = hn;
         }
       }
       // ---- epilogue
       mbar_wait(&o_done[q], 0);
+      A3_TRACE(9);
       tc_fence_after();
       const float inv_l = 1.0f / l_sum;
       const bool row_ok = q_idx < T;
@@ -412,7 +480,7 @@ static int launch3(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream
     LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  dim3 grid((a.T + 255) / 256, a.n_heads, a.B);
+  dim3 grid(a.n_heads, (a.T + 255) / 256, a.B);
   LP_CHECK_CUDA(launch_ex(kern, grid, dim3(A3_THREADS), SMEM, stream, 1, prefill_pdl(), tm, a));
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -142,8 +142,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int q_tile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heavy causal tiles first
-  const int head = blockIdx.y, batch = blockIdx.z;
+  // grid = (heads, tiles, batch), heads fastest: the heaviest causal tiles of EVERY head are dispatched first (see lp_attn3.cu)
+  const int q_tile = (int)gridDim.y - 1 - (int)blockIdx.y;
+  const int head = blockIdx.x, batch = blockIdx.z;
   const int kv_head = head / args.group;
   const int q0 = q_tile * AB_T;
   const int T = args.T;
@@ -376,8 +377,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int kv_tile = blockIdx.x;     // tile 0 sees every q tile: heaviest first
-  const int kv_head = blockIdx.y, batch = blockIdx.z;
+  const int kv_tile = blockIdx.y;     // tile 0 sees every q tile: heaviest first, over all kv heads (grid = (kv heads, tiles, batch))
+  const int kv_head = blockIdx.x, batch = blockIdx.z;
   const int kv0 = kv_tile * AB_T;
   const int T = args.T;
   const int n_q = (T + AB_T - 1) / AB_T;
@@ -536,9 +537,9 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& td, const A
     configured = true;
   }
   const int tiles = (a.T + AB_T - 1) / AB_T;
-  attn_bwd_dq_kernel<DH, CAUSAL><<<dim3(tiles, a.n_heads, a.B), AB_THREADS, SMEM_DQ, stream>>>(tq, td, a);
+  attn_bwd_dq_kernel<DH, CAUSAL><<<dim3(a.n_heads, tiles, a.B), AB_THREADS, SMEM_DQ, stream>>>(tq, td, a);
   LP_CHECK_CUDA(cudaGetLastError());
-  attn_bwd_dkv_kernel<DH, CAUSAL><<<dim3(tiles, n_kv_heads, a.B), AB_THREADS, SMEM_DKV, stream>>>(tq, td, a);
+  attn_bwd_dkv_kernel<DH, CAUSAL><<<dim3(n_kv_heads, tiles, a.B), AB_THREADS, SMEM_DKV, stream>>>(tq, td, a);
   LP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,8 +17,8 @@ template <int DH, bool CAUSAL>
 static void run(const CUtensorMap& tq, const CUtensorMap& td, const AttnBwdArgs& a, int n_kv_heads, int which) {
   const int tiles = (a.T + AB_T - 1) / AB_T;
   emu::g_block_hook = [] { emu_tc::reset(); };
-  if (which & 1) emu::launch(dim3(tiles, a.n_heads, a.B), dim3(AB_THREADS), [&] { attn_bwd_dq_kernel<DH, CAUSAL>(tq, td, a); });
-  if (which & 2) emu::launch(dim3(tiles, n_kv_heads, a.B), dim3(AB_THREADS), [&] { attn_bwd_dkv_kernel<DH, CAUSAL>(tq, td, a); });
+  if (which & 1) emu::launch(dim3(a.n_heads, tiles, a.B), dim3(AB_THREADS), [&] { attn_bwd_dq_kernel<DH, CAUSAL>(tq, td, a); });
+  if (which & 2) emu::launch(dim3(n_kv_heads, tiles, a.B), dim3(AB_THREADS), [&] { attn_bwd_dkv_kernel<DH, CAUSAL>(tq, td, a); });
   emu::g_block_hook = nullptr;
 }
 

@@ -166,3 +166,47 @@ def test_default_prefill_attention_kernel_is_green_under_the_emulator(emu_v3, B,
     emu_v3.emu_attention3_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal),
                               C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), pingpong)
     assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2
+
+
+@pytest.fixture(scope="module")
+def emu_v4(tmp_path_factory):
+    """lp_attn4.cu: everything below its "kernel code" marker (the half-step function and the kernel template, no PTX) is cut out
+    verbatim; the inline-PTX helpers (a4_*) are restated in tests/emu/attn4_fwd_emu.cpp."""
+    out = tmp_path_factory.mktemp("emu_v4")
+    common = (ROOT / "leopard_b200/csrc/lp_common.cuh").read_text()
+    a = common.rindex("// ----", 0, common.index("// UMMA descriptors"))
+    (out / "emu_helpers.inc").write_text("namespace lp {\n" + common[a:common.rindex("}  // namespace lp")] + "\n}\n")
+    host = (ROOT / "leopard_b200/csrc/lp_host.h").read_text()
+    (out / "attn_args.inc").write_text(re.search(r"struct AttnArgs \{.*?\n\};", host, re.S).group(0) + "\n")
+    src = (ROOT / "leopard_b200/csrc/lp_attn4.cu").read_text()
+    body = src[src.index("// ---- kernel code"):src.index("template <int DH, bool CAUSAL, int EMU>\nstatic int launch4(")]
+    assert "asm" not in body
+    (out / "attn4_kernel.inc").write_text(body)
+    lib = out / "liba4.so"
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-shared", "-fPIC", "-I", str(out), "-I", str(ROOT / "tests/emu"),
+                        str(ROOT / "tests/emu/attn4_fwd_emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(str(lib))
+
+
+@pytest.mark.parametrize("B,T,heads,kv_heads,causal,hd,hs", [
+    (2, 200, 4, 2, True, 128, 128),      # one query-tile pair, the second tile ragged: dual steps + tile B's diagonal alone
+    (1, 520, 4, 1, True, 128, 128),      # three pairs, the last one without a tile B (single-stream body for tile A)
+    (2, 300, 2, 2, False, 72, 80),       # vision-tower layout, trailing half tile skipped
+    (1, 640, 2, 2, False, 128, 128),     # full attention, five kv tiles for both query tiles
+    (1, 100, 2, 1, True, 128, 128),      # a single query tile
+])
+def test_two_stream_attention_kernel_under_the_emulator(emu_v4, B, T, heads, kv_heads, causal, hd, hs):
+    """attn4_fwd_kernel (variant bit 7): same arithmetic per row as v3, so the same bound against the fp32 reference."""
+    g = torch.Generator().manual_seed(T + 1)
+    q_w, kv_w = heads * hs, kv_heads * hs
+    qkv = torch.randn((B * T, q_w + 2 * kv_w), generator=g).to(BF)
+    if hs != hd:
+        v = qkv.view(B * T, heads + 2 * kv_heads, hs)
+        v[:, :, hd:] = 0
+        qkv = v.reshape(B * T, -1).contiguous()
+    want = ref.attention(qkv, B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, causal)
+    got = torch.full((B * T, heads * hd), float("nan")).to(BF)
+    emu_v4.emu_attention4_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal),
+                              C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), 0)
+    assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2

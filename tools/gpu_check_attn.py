@@ -75,6 +75,9 @@ def run_case(name, variant, do_time):
     nbad = int(bad.sum())
     rec = {"case": name, "variant": variant, "max_err": float(err.max()), "ref_absmax": float(ref.abs().max()),
            "bad": nbad, "ok": nbad == 0 and bool(torch.isfinite(out.float()).all())}
+    if variant & 128:  # the two-stream kernel does v3's arithmetic row by row: results must be bit-identical
+        out3 = ops.attention(qkv, B, T, H, HK, dh, hs, offs[0], offs[1], offs[2], causal, variant=(variant & ~128) | 64 | 16)
+        rec["same_as_v3"] = bool(torch.equal(out, out3))
     if not rec["ok"]:
         eb = err.view(B, T, H, dh)
         rec["err_by_head"] = [round(float(x), 3) for x in eb.amax(dim=(0, 1, 3))[:16]]

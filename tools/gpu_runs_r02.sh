@@ -206,4 +206,34 @@ r02q() {
   ls -la gpurun_out/${T}_* | awk '{print $5, $9}'
 }
 
+r02v() {
+  # attention v4 (lp_attn4.cu: one softmax warpgroup, two rows per thread as independent exp streams) vs v3: parity, bit-equality, timing,
+  # then the whole cfg3 step with each
+  T=${TAG:-r02v}
+  TMO=240 run attn4_small python tools/gpu_check_attn.py --variant 128 --case dec_t128 --case dec_t128_c --case dec_t256 --case dec_t300_c --case vit_t128 --case vit_t676
+  TMO=300 TAIL=4000 run attn4_time python tools/gpu_check_attn.py --variant 80 --variant 128 --variant 132 --case dec_2937_c --case dec_4796_c --case vit_28 --case vit_4900 --time
+  TMO=300 run ab_attn python tools/gpu_ab_prefill.py attn=80 attn=128
+}
+
+r02x() {
+  # attention v3 with the next S half loaded before the hand-over + alternating pv_done barriers: parity (v4 = the unchanged arithmetic as
+  # cross-check), timing, phase trace, whole step
+  T=${TAG:-r02x}
+  TMO=240 run attn_small python tools/gpu_check_attn.py --variant 80 --variant 128 --case dec_t128 --case dec_t128_c --case dec_t256 --case dec_t300_c --case vit_t128 --case vit_t676
+  TMO=300 TAIL=4000 run attn_time python tools/gpu_check_attn.py --variant 80 --variant 96 --variant 128 --case dec_2937_c --case dec_4796_c --case vit_28 --case vit_4900 --time
+  timeout 60 tools/micro/attn_trace 4796 32 8 128 1 1 4 > gpurun_out/${T}_trace_dec_ping1.json 2>&1
+  timeout 60 tools/micro/attn_trace 676 16 16 72 0 1 2 28 > gpurun_out/${T}_trace_vit_ping1.json 2>&1
+  TMO=300 run ab_attn python tools/gpu_ab_prefill.py attn=80 attn=128
+}
+
+r02y() {
+  # attention grids with the heads fastest (global heaviest-first dispatch of the causal query-tile pairs): parity, timing, whole step,
+  # flash backward parity
+  T=${TAG:-r02y}
+  TMO=240 run attn_small python tools/gpu_check_attn.py --variant 80 --case dec_t128 --case dec_t128_c --case dec_t256 --case dec_t300_c --case vit_t128 --case vit_t676
+  TMO=300 TAIL=4000 run attn_time python tools/gpu_check_attn.py --variant 80 --variant 128 --case dec_2937_c --case dec_4796_c --case vit_28 --case vit_4900 --time
+  TMO=300 run ab_attn python tools/gpu_ab_prefill.py attn=80 attn=128
+  TMO=600 run bwd python -m pytest tests/test_zz_gpu_train.py -x -q -k "flash or closed_form or vision_tower_layout"
+}
+
 "$@"

@@ -14,9 +14,9 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; a
 
 template <int MODE>
 __global__ void k(float* out, long long* cyc, int iters) {
-  float v[64];
+  float v[64], w[64];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = -0.01f * (threadIdx.x + i);
+  for (int i = 0; i < 64; ++i) { v[i] = -0.01f * (threadIdx.x + i); w[i] = -0.02f * (threadIdx.x + i); }
   __syncthreads();
   const long long t0 = clock64();
   float acc = 0.f;
@@ -88,6 +88,24 @@ __global__ void k(float* out, long long* cyc, int iters) {
       float s0, s1, s3, s4; upk2(a2, s0, s1); upk2(b2, s3, s4); acc += s0 + s1 + s3 + s4 + __uint_as_float(pkd & 0x7fu);
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] = -v[i] * 0.5f - 0.01f;
+    } else if (MODE == 6) {   // TWO independent 64-value streams in one warp (rows of two query tiles per thread): 128 values
+      const uint64_t s2 = pk2(1.0001f, 1.0001f), c2 = pk2(-0.001f, -0.001f);
+      uint64_t a2 = pk2(0.f, 0.f), b2 = pk2(0.f, 0.f);
+      uint32_t pka = 0, pkb = 0;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        float x0, x1, y0, y1;
+        upk2(fma2(pk2(v[i], v[i + 1]), s2, c2), x0, x1);
+        upk2(fma2(pk2(w[i], w[i + 1]), s2, c2), y0, y1);
+        const float p0 = ex2(x0), p1 = ex2(x1), q0 = ex2(y0), q1 = ex2(y1);
+        a2 = add2(a2, pk2(p0, p1));
+        b2 = add2(b2, pk2(q0, q1));
+        __nv_bfloat162 ba = __floats2bfloat162_rn(p0, p1), bb = __floats2bfloat162_rn(q0, q1);
+        pka ^= *reinterpret_cast<uint32_t*>(&ba);
+        pkb ^= *reinterpret_cast<uint32_t*>(&bb);
+        v[i] = x0; v[i + 1] = x1; w[i] = y0; w[i + 1] = y1;
+      }
+      float s0, s1, s3, s4; upk2(a2, s0, s1); upk2(b2, s3, s4); acc += s0 + s1 + s3 + s4 + __uint_as_float((pka ^ pkb) & 0x7fu);
     } else if (MODE == 3) {   // bf16x2 exponentials: 32 MUFU-class ops for 64 values
       uint32_t pkd = 0;
 #pragma unroll
@@ -104,7 +122,7 @@ __global__ void k(float* out, long long* cyc, int iters) {
   const long long t1 = clock64();
   float s = acc;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) s += v[i];
+  for (int i = 0; i < 64; ++i) s += v[i] + (MODE == 6 ? w[i] : 0.f);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -133,6 +151,7 @@ int main() {
   run<3>("ex2 bf16x2 (32 per iter, 64 values)", 32);
   run<4>("three passes, pinned order (64 values)", 64);
   run<5>("software-pipelined 16-value groups (64 values)", 64);
+  run<6>("two 64-value streams in one warp (128 values, 128 MUFU)", 128);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
