@@ -148,6 +148,11 @@ int lp_gemm_set_streamk(int enable);
  * from the same buffer; 0 = the earlier register path (coalesced loads handed through the staging tile).  Same arithmetic:
  * results are bit-identical.  Returns the previous setting. */
 int lp_gemm_set_tma_residual(int enable);
+/* Tile raster of launches whose W fits L2 while A does not and whose last column block is ragged (the ViT fc2: N = 1152 = 4 x 256 +
+ * 128): 1 (default) = row-major tile order, so that every persistent unit gets each column block — and so the cheap ragged ones —
+ * equally often; 0 = the earlier groups of ~SMs / column-blocks row blocks (35 of 74 CTA pairs got all the half-width tiles).
+ * Scheduling only: results are bit-identical.  Returns the previous setting. */
+int lp_gemm_set_raster_balance(int enable);
 
 /* Launch the hot prefill kernels (GEMM, attention v3, norms, RoPE) with programmatic dependent launch: the next kernel's
  * CTAs are scheduled as SMs free up and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the

@@ -172,12 +172,14 @@ def main():
     ap.add_argument("--single", action="store_true", help="one CTA per tile")
     ap.add_argument("--quad", action="store_true", help="4-CTA clusters with A multicast (lp_gemm4.cu, mode 2)")
     ap.add_argument("--streamk", type=int, default=1, help="stream-K tail on / off (lp_gemm_set_streamk)")
+    ap.add_argument("--balance", type=int, default=1, help="row-major raster for ragged N (lp_gemm_set_raster_balance)")
     ap.add_argument("--tma-res", type=int, default=1, help="residual tile by TMA on / off (lp_gemm_set_tma_residual)")
     args = ap.parse_args()
     from leopard_b200 import _lib as _l
     _l.ensure_streamk_workspace("cuda:0")
     _l.lib().lp_gemm_set_streamk(args.streamk)
     _l.lib().lp_gemm_set_tma_residual(args.tma_res)
+    _l.lib().lp_gemm_set_raster_balance(args.balance)
     if args.quad:
         from leopard_b200 import _lib
         _lib.lib().lp_gemm_set_pair_mode(2)

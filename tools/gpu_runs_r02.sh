@@ -236,4 +236,13 @@ r02y() {
   TMO=600 run bwd python -m pytest tests/test_zz_gpu_train.py -x -q -k "flash or closed_form or vision_tower_layout"
 }
 
+r02z() {
+  # GEMM raster: row-major tile order for ragged N with W L2-resident (ViT fc2): per-shape timing off / on, bit-equality, whole step
+  T=${TAG:-r02z}
+  TMO=300 run gemm_bal0 python tools/gpu_check_gemm.py --pair --time --balance 0 --case v_fc2 --case v_out --case v_fc1 --case v_qkv
+  TMO=300 run gemm_bal1 python tools/gpu_check_gemm.py --pair --time --balance 1 --case v_fc2 --case v_out --case v_fc1 --case v_qkv
+  TMO=300 run ab_bal python tools/gpu_ab_prefill.py bal=0 bal=1
+  TMO=600 run ops python -m pytest tests/test_gpu_ops.py -x -q
+}
+
 "$@"
