@@ -176,7 +176,10 @@ int lp_set_prefill_pdl(int enable);
  *   softmax row sum is taken in fp32 before P is rounded to bf16 (as flash-attention does);
  * variant bits 4 / 5 (16 / 32): force the softmax turn protocol on / off (see lp_attention_set_pingpong);
  * variant bit 7 (128): v4 kernel (lp_attn4.cu) — v3's dataflow, but ONE softmax warpgroup whose thread r owns row r of both
- *   query tiles and runs their exponentials as two independent instruction streams (no turn protocol). */
+ *   query tiles and runs their exponentials as two independent instruction streams (no turn protocol);
+ * variant bit 8 (256): short non-causal (72, 80) problems whose query-tile pairs are all complete (the SigLIP tower: T = 676) run
+ *   the persistent form of v3 (lp_attn5.cu): one CTA per SM walks (batch, head, pair) items, barriers / TMEM set up once, the next
+ *   item's loads and first QK^T overlap the epilogue; other shapes ignore the bit.  Same arithmetic as v3: bit-identical. */
 int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, int n_kv_heads, int head_dim,
                      int head_stride, int q_off, int k_off, int v_off, int causal, float scale, void* out,
                      long long ldo, int variant, void* stream);
@@ -189,10 +192,11 @@ int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int n_heads, i
 int lp_attention_set_pingpong(int enable);
 
 /* Attention kernel the model-level entry points (lp_vit_forward, lp_vit_layers, lp_decoder_prefill) pass to
- * lp_attention_fwd as `variant`; returns the previous value.  Default 80 = variant bit 6 (64): the v3 kernel — two
+ * lp_attention_fwd as `variant`; returns the previous value.  Default 336 = variant bit 6 (64): the v3 kernel — two
  * query tiles per CTA, S delivered in 64-key halves with their own TMEM columns so QK^T of the next half never waits
  * for the softmax of the current one, one MMA-issuing thread per query tile — plus bit 4 (16): the turn protocol on
- * its exp sections.  2 selects the v2 two-tile kernel. */
+ * its exp sections, plus bit 8 (256): the persistent form for the vision tower's short sequences.  80 = v3 everywhere,
+ * 2 selects the v2 two-tile kernel. */
 int lp_model_set_attention_variant(int variant);
 
 /* Cross-attention with separate query and key/value buffers, non-causal (Idefics2 perceiver resampler: 64 latent

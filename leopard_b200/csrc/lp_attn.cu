@@ -380,6 +380,11 @@ extern "C" int lp_attention_fwd(const void* qkv, long long ld, int B, int T, int
   int rc = make_tmap_bf16_3d(&tm, qkv, (uint64_t)ld, (uint64_t)T, (uint64_t)B, (uint64_t)ld, (uint64_t)T * ld, 64,
                              128, 1);
   if (rc) return rc;
+  if ((variant & 256) && attn5_eligible(a, head_dim, causal)) {  // persistent v3 over (batch, head, query-tile pair) items (lp_attn5.cu)
+    ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
+    note_launch();
+    return launch_attn5(tm, a, stream);
+  }
   if (variant & 128) {  // v3's dataflow with one softmax warpgroup running both tiles' rows as two streams (lp_attn4.cu)
     ProfScope prof(2, B, T, n_heads * 1000 + head_dim, stream);
     note_launch();

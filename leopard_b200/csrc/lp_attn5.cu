@@ -1,0 +1,435 @@
+// leopard_b200 — flash attention v5: the v3 kernel (lp_attn3.cu) as a PERSISTENT kernel for short non-causal sequences — the SigLIP
+// tower's 28 x 16 x (T = 676) attention problems (TEDotProductAttention at MP/model/llava/clip_encoder.py:58-63).
+//
+// Why (phase trace of v3, tools/micro/attn_trace.cu, profiles/r02w_attn_trace_report.txt): a v3 CTA works on one pair of query tiles
+// of one head for 11 half steps (~21 k cycles) but lives ~27 k: ~1.8 k of launch / barrier init / TMEM allocation, 2.6 k waiting
+// for the first Q and K boxes to arrive, and the O epilogue with nothing else running on the SM.  With 1344 such CTAs per layer a
+// fifth of the kernel is fixed cost.  Here one CTA per SM walks a static list of (crop, head, query-tile pair) items:
+//   * barriers and TMEM are set up once; all mbarrier parities derive from running counters (every item has the same number of key
+//     tiles and half steps — the launcher takes this path only when every item has both query tiles);
+//   * the K/V ring simply keeps running across items, and the next item's Q tiles are requested as soon as the issuers have issued
+//     the item's last S MMAs (q_empty), i.e. ~1.5 key tiles before the item ends;
+//   * the issuers queue S(0) of the next item behind the last P·V of this one, so the first softmax step of the next item finds its
+//     scores ready; only its first P·V waits until the softmax warpgroup has pulled O of the previous item out of TMEM (o_free);
+//   * the epilogue reads O into registers first, releases the accumulator, and converts / stores afterwards.
+// Arithmetic per row is v3's: results are bit-identical.
+//   warp 0      TMA producer      warp 1 / 2  MMA issuer of tile A / B      warp 3  TMEM allocation
+//   warps 4-7   softmax of tile A      warps 8-11  softmax of tile B
+#include "lp_common.cuh"
+#include "lp_host.h"
+#include "../../include/leopard_b200.h"
+
+namespace lp {
+
+constexpr int A5_BOX = 128 * 128;  // one TMA box: 128 rows x 64 bf16
+constexpr int A5_THREADS = 384;
+
+__device__ __forceinline__ float a5_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void a5_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void a5_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ uint64_t a5_pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void a5_upk2(uint64_t r, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+__device__ __forceinline__ uint64_t a5_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t a5_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+#define LP5_TMEM_ST_16(regs, taddr)                                                                                 \
+  asm volatile(                                                                                                     \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
+      "%15, %16};" ::"r"(taddr),                                                                                    \
+      "r"(regs[0]), "r"(regs[1]), "r"(regs[2]), "r"(regs[3]), "r"(regs[4]), "r"(regs[5]), "r"(regs[6]),             \
+      "r"(regs[7]), "r"(regs[8]), "r"(regs[9]), "r"(regs[10]), "r"(regs[11]), "r"(regs[12]), "r"(regs[13]),         \
+      "r"(regs[14]), "r"(regs[15])                                                                                  \
+      : "memory")
+
+// ---- kernel code (no inline PTX below this line: tests/emu cuts it out verbatim)
+// n_pairs = query-tile pairs per (batch, head); items = B * heads * n_pairs, item -> CTA round-robin (neighbouring CTAs share a head)
+template <int DH>
+__global__ void __launch_bounds__(A5_THREADS, 1)
+attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args, const int n_pairs, const int n_items) {
+  constexpr int NB = (DH + 63) / 64;
+  constexpr int KS_QK = DH / 16;
+  constexpr int HEAD_BYTES = NB * A5_BOX;
+  constexpr int Q_OFF = 0;                       // 2 tiles
+  constexpr int K_OFF = Q_OFF + 2 * HEAD_BYTES;  // 2 stages
+  constexpr int V_OFF = K_OFF + 2 * HEAD_BYTES;  // 2 stages
+  constexpr int BAR_OFF = V_OFF + 2 * HEAD_BYTES;
+  constexpr uint32_t TM_S = 0, TM_O = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);  // [2]   per q tile, one phase per item
+  uint64_t* k_full = q_full + 2;                                    // [2]   per ring slot
+  uint64_t* v_full = k_full + 2;                                    // [2]
+  uint64_t* k_empty = v_full + 2;                                   // [4]   q tile x slot
+  uint64_t* v_empty = k_empty + 4;                                  // [4]
+  uint64_t* s_full = v_empty + 4;                                   // [4]   q tile x half
+  uint64_t* p_full = s_full + 4;                                    // [4]
+  uint64_t* pv_done = p_full + 4;                                   // [4]   q tile x (running half-step index & 1)
+  uint64_t* o_done = pv_done + 4;                                   // [2]   one phase per item
+  uint64_t* q_empty = o_done + 2;                                   // [2]   the item's last S MMAs have retired: Q tile may be replaced
+  uint64_t* o_free = q_empty + 2;                                   // [2]   the softmax warpgroup has read O of the item out of TMEM
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int T = args.T;  // self-attention only: Tk == T; every item has both query tiles (launcher)
+  const int n_total = (T + 127) / 128;                                   // key tiles per item
+  const int n_hi = n_total - (((n_total - 1) * 128 + 64 >= T) ? 1 : 0);  // key tiles whose second 64-key half holds real keys
+  const int halves = n_total + n_hi;                                     // half steps per item and tile
+  const int G = (int)gridDim.x;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&o_done[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&o_free[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 3) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // before any global load (TMA) or store (O rows)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it_n = 0;
+      for (int item = (int)blockIdx.x; item < n_items; item += G, ++it_n) {
+        const int pair = item % n_pairs, bh = item / n_pairs;
+        const int head = bh % args.n_heads, batch = bh / args.n_heads;
+        const int kv_head = head / args.group;
+        for (int q = 0; q < 2; ++q) {
+          if (it_n > 0) mbar_wait(&q_empty[q], (it_n - 1) & 1);
+          mbar_arrive_expect_tx(&q_full[q], HEAD_BYTES);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            tma_load_3d(smem + Q_OFF + q * HEAD_BYTES + b * A5_BOX, &tmQKV, &q_full[q],
+                        args.q_off + head * args.hs + b * 64, pair * 256 + q * 128, batch);
+        }
+        for (int j = 0; j < n_total; ++j) {
+          const int g = it_n * n_total + j;  // running key-tile count: ring slot g & 1
+          const int st = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          if (g >= 2) {
+            mbar_wait(&k_empty[0 * 2 + st], ph ^ 1);
+            mbar_wait(&k_empty[1 * 2 + st], ph ^ 1);
+          }
+          mbar_arrive_expect_tx(&k_full[st], HEAD_BYTES);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            tma_load_3d(smem + K_OFF + st * HEAD_BYTES + b * A5_BOX, &tmQKV, &k_full[st],
+                        args.k_off + kv_head * args.hs + b * 64, j * 128, batch);
+          if (g >= 2) {
+            mbar_wait(&v_empty[0 * 2 + st], ph ^ 1);
+            mbar_wait(&v_empty[1 * 2 + st], ph ^ 1);
+          }
+          mbar_arrive_expect_tx(&v_full[st], HEAD_BYTES);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            tma_load_3d(smem + V_OFF + st * HEAD_BYTES + b * A5_BOX, &tmQKV, &v_full[st],
+                        args.v_off + kv_head * args.hs + b * 64, j * 128, batch);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer of tile q
+    const int q = warp - 1;
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+      const uint32_t q_addr = smem_u32(smem + Q_OFF + q * HEAD_BYTES);
+      const uint32_t s_tm = tmem_base + TM_S + (uint32_t)q * 128;
+      const uint32_t d_o = tmem_base + TM_O + (uint32_t)q * 128;
+      int t_pv = 0;  // P·V halves issued so far (all items)
+      int it_n = 0;
+      for (int item = (int)blockIdx.x; item < n_items; item += G, ++it_n) {
+        const int g0 = it_n * n_total;            // running key-tile count of this item's tile 0
+        const int c_lo = it_n * n_total, c_hi = it_n * n_hi;   // completed phases of the lo / hi barriers before this item
+        auto issue_S = [&](int j, int h) {  // S_q(j).h = Q_q K_j[64h .. 64h+63]^T
+          const uint32_t k_addr = smem_u32(smem + K_OFF + ((g0 + j) & 1) * HEAD_BYTES) + (uint32_t)h * 64 * 128;
+#pragma unroll
+          for (int ks = 0; ks < KS_QK; ++ks) {
+            const uint32_t off = (ks >> 2) * A5_BOX + (ks & 3) * 32;
+            umma_ss(s_tm + (uint32_t)h * 64, umma_desc_sw128(q_addr + off, 0, 1024),
+                    umma_desc_sw128(k_addr + off, 0, 1024), idesc_s, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[q * 2 + h]);
+        };
+        auto issue_PV = [&](int j, int h) {  // O_q += P_q(j).h V_j[64h .. 64h+63]
+          const uint32_t v_addr = smem_u32(smem + V_OFF + ((g0 + j) & 1) * HEAD_BYTES);
+          mbar_wait(&p_full[q * 2 + h], ((h ? c_hi : c_lo) + j) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = h * 4 + k4;
+            const uint64_t vdesc = umma_desc_sw128(v_addr + ks * 2048, A5_BOX, 1024);
+            umma_ts(d_o, s_tm + (uint32_t)h * 64 + k4 * 8, vdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[q * 2 + (t_pv & 1)]);
+          ++t_pv;
+        };
+        mbar_wait(&q_full[q], it_n & 1);
+        mbar_wait(&k_full[g0 & 1], (g0 >> 1) & 1);
+        tc_fence_after();
+        issue_S(0, 0);
+        if (0 < n_hi) issue_S(0, 1);
+        umma_commit(&k_empty[q * 2 + (g0 & 1)]);
+        if (n_total == 1) umma_commit(&q_empty[q]);
+        for (int j = 0; j < n_total; ++j) {
+          const bool hi = j < n_hi;                  // second half of this tile holds real keys
+          const bool more = j + 1 < n_total;
+          const bool hi_next = more && (j + 1 < n_hi);
+          const int g = g0 + j;
+          mbar_wait(&v_full[g & 1], (g >> 1) & 1);
+          if (j == 0 && it_n > 0) {
+            // the first P·V of an item overwrites O: the softmax warpgroup must have read the previous item's result
+            mbar_wait(&o_free[q], (it_n - 1) & 1);
+            tc_fence_after();
+          }
+          issue_PV(j, 0);
+          if (more) {
+            mbar_wait(&k_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_S(j + 1, 0);
+          }
+          if (hi) issue_PV(j, 1);
+          umma_commit(&v_empty[q * 2 + (g & 1)]);
+          if (more) {
+            if (hi_next) issue_S(j + 1, 1);
+            umma_commit(&k_empty[q * 2 + ((g + 1) & 1)]);
+            if (j + 2 == n_total) umma_commit(&q_empty[q]);  // the item's last S MMAs are in flight: Q may be replaced once they retire
+          }
+          if (!more) umma_commit(&o_done[q]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int q = (warp - 4) >> 2;
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    const uint32_t s_addr = lane_addr + TM_S + (uint32_t)q * 128;
+    const uint32_t o_addr = lane_addr + TM_O + (uint32_t)q * 128;
+    // Turn protocol around the EXP sections (args.pingpong), as in v3: A(0) B(0) A(1) B(1) ... — here over the CTA's WHOLE sequence of
+    // half steps (both tiles have `halves` of them in every item), so the strict alternation also holds across item boundaries and
+    // neither named barrier (3 = "B may exp": A arrives, B syncs; 2 = "A may exp") can collect two arrivals of the same warpgroup.
+    const bool turns = args.pingpong != 0;
+    const int total_halves = ((n_items - (int)blockIdx.x + G - 1) / G) * halves;
+    int it_n = 0;
+    for (int item = (int)blockIdx.x; item < n_items; item += G, ++it_n) {
+      const int pair = item % n_pairs, bh = item / n_pairs;
+      const int head = bh % args.n_heads, batch = bh / args.n_heads;
+      const int q_idx = pair * 256 + q * 128 + r;
+      const int c_lo = it_n * n_total, c_hi = it_n * n_hi;
+      const int t_run0 = it_n * halves;  // running half-step index of this item's first half step
+      float m_used = -INFINITY, l_sum = 0.f;
+      int t = 0;  // half steps of this item published so far
+      uint32_t v[64];
+      mbar_wait(&s_full[q * 2 + 0], c_lo & 1);
+      tc_fence_after();
+      LP_TMEM_LD_32((v + 0), s_addr + 0);
+      LP_TMEM_LD_32((v + 32), s_addr + 32);
+      int j = 0, h = 0;
+#pragma unroll 1
+      for (;;) {
+        const int kv0 = j * 128 + h * 64;
+        tmem_wait_ld();
+        const bool need_mask = kv0 + 64 > T;
+        const int lim = T - kv0;
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= lim) v[i] = 0xff800000u;  // -inf
+        }
+        float mx;
+        {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; i += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
+        const float m_new = fmaxf(m_used, mx * args.scale_log2);
+        const bool grow = (m_new - m_used) > 8.0f;
+        if (t == 0) {
+          m_used = m_new;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          // every P·V of this item issued so far must have retired before O_q is rescaled in place: half t - 1 of the item is
+          // running half step tr = t_run0 + t - 1, phase tr >> 1 of barrier tr & 1 (see lp_attn3.cu for why the parity is unambiguous)
+          const int tr = t_run0 + t - 1;
+          mbar_wait(&pv_done[q * 2 + (tr & 1)], (tr >> 1) & 1);
+          tc_fence_after();
+          float alpha = 1.0f;
+          if (grow) {
+            alpha = a5_ex2(m_used - m_new);
+            m_used = m_new;
+            l_sum *= alpha;
+          }
+#pragma unroll 1
+          for (int c = 0; c < DH / 16; ++c) {
+            uint32_t o[16];
+            LP_TMEM_LD_16(o, o_addr + c * 16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            LP5_TMEM_ST_16(o, o_addr + c * 16);
+          }
+          tmem_wait_st();
+        }
+        const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+        const uint64_t sc2 = a5_pk2(args.scale_log2, args.scale_log2), nm2 = a5_pk2(neg_m, neg_m);
+        uint64_t acc2 = a5_pk2(0.f, 0.f);
+        if (turns) {
+          if (q == 0) { if (t_run0 + t > 0) a5_bar_sync(2, 256); }
+          else a5_bar_sync(3, 256);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0, x1;
+            a5_upk2(a5_fma2(a5_pk2(__uint_as_float(v[c * 32 + i]), __uint_as_float(v[c * 32 + i + 1])), sc2, nm2), x0, x1);
+            const float p0 = a5_ex2(x0), p1 = a5_ex2(x1);
+            acc2 = a5_add2(acc2, a5_pk2(p0, p1));   // fp32 row sum before the bf16 rounding of P, as in v3
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          LP5_TMEM_ST_16(pk, s_addr + h * 64 + c * 16);  // P(j).h over the first 32 columns of its own S half
+        }
+        if (turns) {
+          if (q == 0) a5_bar_arrive(3, 256);
+          else if (t_run0 + t + 1 < total_halves) a5_bar_arrive(2, 256);
+        }
+        // next half step of the item: its S half goes into v before P(t) is handed over (see lp_attn3.cu)
+        int jn = j, hn = 1;
+        if (h == 1 || j >= n_hi) { jn = j + 1; hn = 0; }
+        const bool has_next = jn < n_total;
+        const uint32_t next_par = ((hn ? c_hi : c_lo) + jn) & 1;
+        bool loaded = false;
+        if (has_next && mbar_test_wait(&s_full[q * 2 + hn], next_par)) {
+          tc_fence_after();
+          LP_TMEM_LD_32((v + 0), s_addr + hn * 64 + 0);
+          LP_TMEM_LD_32((v + 32), s_addr + hn * 64 + 32);
+          loaded = true;
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[q * 2 + h]);
+        {
+          float a0, a1;
+          a5_upk2(acc2, a0, a1);
+          l_sum += a0 + a1;
+        }
+        ++t;
+        if (!has_next) break;
+        if (!loaded) {
+          mbar_wait(&s_full[q * 2 + hn], next_par);
+          tc_fence_after();
+          LP_TMEM_LD_32((v + 0), s_addr + hn * 64 + 0);
+          LP_TMEM_LD_32((v + 32), s_addr + hn * 64 + 32);
+        }
+        j = jn;
+        h = hn;
+      }
+      // ---- epilogue: O into registers, accumulator released, then scaled / packed / stored
+      mbar_wait(&o_done[q], it_n & 1);
+      tc_fence_after();
+      uint32_t o[DH];
+#pragma unroll
+      for (int c = 0; c < DH / 16; ++c) LP_TMEM_LD_16((o + c * 16), o_addr + c * 16);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&o_free[q]);
+      const float inv_l = 1.0f / l_sum;
+      if (q_idx < T) {
+        bf16* op = args.O + ((long long)batch * T + q_idx) * args.ldo + (long long)head * args.dh_out;
+#pragma unroll
+        for (int g8 = 0; g8 < DH / 8; ++g8) {
+          if (g8 * 8 < args.dh_out) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[g8 * 8 + 0]) * inv_l, __uint_as_float(o[g8 * 8 + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(o[g8 * 8 + 2]) * inv_l, __uint_as_float(o[g8 * 8 + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(o[g8 * 8 + 4]) * inv_l, __uint_as_float(o[g8 * 8 + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(o[g8 * 8 + 6]) * inv_l, __uint_as_float(o[g8 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + g8 * 8) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side
+// eligible: non-causal, the (72, 80) head layout, every item with both query tiles (T % 256 == 0 or > 128) and short sequences —
+// with long ones (T = 4900, Idefics2's tower) a CTA's fixed cost is already negligible and the static item list only costs balance
+bool attn5_eligible(const AttnArgs& a, int head_dim, int causal) {
+  const int rem = a.T % 256;
+  return !causal && head_dim == 72 && a.T == a.Tk && a.T >= 256 && a.T <= 2048 && (rem == 0 || rem > 128);
+}
+
+int launch_attn5(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream) {
+  constexpr int DH = 80, NB = 2;
+  constexpr int SMEM = 6 * NB * A5_BOX + 512 + 1024;
+  auto kern = attn5_fwd_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    LP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int n_pairs = (a.T + 255) / 256;
+  const int n_items = a.B * a.n_heads * n_pairs;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  LP_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(A5_THREADS), SMEM, stream, 1, prefill_pdl(), tm, a, n_pairs, n_items));
+  LP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace lp

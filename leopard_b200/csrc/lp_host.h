@@ -89,6 +89,9 @@ struct AttnArgs {
 int launch_attn2(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, int emu, cudaStream_t stream);
 int launch_attn3(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, int emu, cudaStream_t stream);
 int launch_attn4(const CUtensorMap& tm, const AttnArgs& a, int head_dim, int causal, int emu, cudaStream_t stream);
+// persistent v3 for short non-causal sequences (lp_attn5.cu): the ViT tower's T = 676
+bool attn5_eligible(const AttnArgs& a, int head_dim, int causal);
+int launch_attn5(const CUtensorMap& tm, const AttnArgs& a, cudaStream_t stream);
 
 // 2-D / 3-D bf16 tensor maps with 128B swizzle (inner box = 64 elements = 128 B), zero OOB fill.
 // dims/strides are innermost-first; strides are in ELEMENTS for dims >= 1.

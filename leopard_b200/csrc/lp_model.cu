@@ -16,9 +16,10 @@
 
 using namespace lp;
 
-// attention kernel used by the layer loops: lp_attention_fwd `variant` (default 80 = v3 kernel with 64-key S halves,
-// one MMA issuer per query tile and the exp-section turn protocol; 2 = v2 two-tile kernel)
-static int g_attn_variant = 80;
+// attention kernel used by the layer loops: lp_attention_fwd `variant` (default 336 = v3 kernel with 64-key S halves,
+// one MMA issuer per query tile and the exp-section turn protocol, persistent form (lp_attn5.cu) for the tower's T = 676;
+// 80 = v3 everywhere, 2 = v2 two-tile kernel)
+static int g_attn_variant = 336;
 extern "C" int lp_model_set_attention_variant(int variant) {
   const int old = g_attn_variant;
   g_attn_variant = variant;

@@ -566,7 +566,7 @@ class SFTTrainer:
         """Forward, loss and backward of one micro-batch; gradients are written (first micro-batch) or added (later ones)
         into the flat buffer; on the last micro-batch every bucket's all-reduce is issued as soon as it is complete."""
         cfg, d, w = self.cfg, self.cfg.dec, self.w.named
-        self._attn_variant = 80
+        self._attn_variant = 336     # v3 attention (+ its persistent form for the vision tower's short sequences)
         b, s = tokens.shape
         if s % 8:
             raise ValueError(f"sequence length {s} must be a multiple of 8")

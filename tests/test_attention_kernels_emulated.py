@@ -210,3 +210,46 @@ def test_two_stream_attention_kernel_under_the_emulator(emu_v4, B, T, heads, kv_
     emu_v4.emu_attention4_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, int(causal),
                               C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), 0)
     assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2
+
+
+@pytest.fixture(scope="module")
+def emu_v5(tmp_path_factory):
+    """lp_attn5.cu (persistent v3 for the vision tower's short sequences): everything below its "kernel code" marker up to the host
+    side is cut out verbatim; the inline-PTX helpers (a5_*) are restated in tests/emu/attn5_fwd_emu.cpp."""
+    out = tmp_path_factory.mktemp("emu_v5")
+    common = (ROOT / "leopard_b200/csrc/lp_common.cuh").read_text()
+    a = common.rindex("// ----", 0, common.index("// UMMA descriptors"))
+    (out / "emu_helpers.inc").write_text("namespace lp {\n" + common[a:common.rindex("}  // namespace lp")] + "\n}\n")
+    host = (ROOT / "leopard_b200/csrc/lp_host.h").read_text()
+    (out / "attn_args.inc").write_text(re.search(r"struct AttnArgs \{.*?\n\};", host, re.S).group(0) + "\n")
+    src = (ROOT / "leopard_b200/csrc/lp_attn5.cu").read_text()
+    body = src[src.index("// ---- kernel code"):src.index("// ---- host side")]
+    assert "asm" not in body
+    (out / "attn5_kernel.inc").write_text(body)
+    lib = out / "liba5.so"
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-shared", "-fPIC", "-I", str(out), "-I", str(ROOT / "tests/emu"),
+                        str(ROOT / "tests/emu/attn5_fwd_emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(str(lib))
+
+
+@pytest.mark.parametrize("B,T,heads,kv_heads,grid,pingpong", [
+    (2, 300, 3, 3, 2, 1),     # 12 items on 2 CTAs: six items each, trailing half tile skipped, turn protocol across item boundaries
+    (1, 676, 2, 2, 4, 1),     # the tower's T: 6 items on 4 CTAs (two CTAs get two items, two get one)
+    (1, 512, 2, 2, 1, 0),     # T a multiple of 256, one CTA walks all four items; turn protocol off
+    (3, 420, 1, 1, 8, 1),     # more CTAs than items per head; grid > items is clamped
+])
+def test_persistent_attention_kernel_under_the_emulator(emu_v5, B, T, heads, kv_heads, grid, pingpong):
+    """attn5_fwd_kernel (variant bit 8): v3's arithmetic per row, barrier parities running across items."""
+    hd, hs = 72, 80
+    g = torch.Generator().manual_seed(T + grid)
+    q_w, kv_w = heads * hs, kv_heads * hs
+    qkv = torch.randn((B * T, q_w + 2 * kv_w), generator=g).to(BF)
+    v = qkv.view(B * T, heads + 2 * kv_heads, hs)
+    v[:, :, hd:] = 0
+    qkv = v.reshape(B * T, -1).contiguous()
+    want = ref.attention(qkv, B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, False)
+    got = torch.full((B * T, heads * hd), float("nan")).to(BF)
+    emu_v5.emu_attention5_fwd(P(qkv), C.c_longlong(qkv.stride(0)), B, T, heads, kv_heads, hd, hs, 0, q_w, q_w + kv_w, 0,
+                              C.c_float(hd ** -0.5), P(got), C.c_longlong(got.stride(0)), pingpong, grid)
+    assert not bool(torch.isnan(got.float()).any()) and _err(got, want) < 1.5e-2

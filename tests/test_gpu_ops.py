@@ -99,12 +99,29 @@ def _attn_ref(qkv, B, T, H, HK, dh, hs, wq, wk, causal):
     (3, 676, 16, 16, 72, 80, False),
     (2, 100, 16, 16, 72, 80, False),
 ])
-@pytest.mark.parametrize("variant", [0, 1, 2, 18, 64, 80, 84])
+@pytest.mark.parametrize("variant", [0, 1, 2, 18, 64, 80, 84, 128, 336])
 def test_attention(native_lib, B, T, H, HK, dh, hs, causal, variant):
     qkv, wq, wk = _qkv(B, T, H, HK, dh, hs, seed=T + H)
     ref = _attn_ref(qkv, B, T, H, HK, dh, hs, wq, wk, causal)
     out = ops.attention(qkv.cuda(), B, T, H, HK, dh, hs, 0, wq, wq + wk, causal, variant=variant)
     _close(out, ref, 2e-2, 0.5)
+
+
+@pytest.mark.parametrize("B,T,H,HK,dh,hs,causal", [
+    (5, 676, 16, 16, 72, 80, False),     # 240 items on 148 persistent CTAs: item loop, Q replacement, accumulator hand-back
+    (2, 1024, 16, 16, 72, 80, False),    # T a multiple of 256
+    (3, 420, 4, 4, 72, 80, False),       # fewer items than SMs
+    (2, 300, 8, 2, 128, 128, True),      # not eligible for the persistent form: falls through to v3
+])
+def test_attention_scheduling_variants_are_bit_identical(native_lib, B, T, H, HK, dh, hs, causal):
+    """Variant 128 (one softmax warpgroup, two rows per thread) and 336 (persistent CTAs for short non-causal sequences) reorganise
+    WHO does the work and WHEN; every row sees v3's arithmetic, so the outputs must match variant 80 bit for bit."""
+    qkv, wq, wk = _qkv(B, T, H, HK, dh, hs, seed=T + H + 1)
+    q = qkv.cuda()
+    base = ops.attention(q, B, T, H, HK, dh, hs, 0, wq, wq + wk, causal, variant=80)
+    for variant in (128, 336, 336 | 32):
+        out = ops.attention(q, B, T, H, HK, dh, hs, 0, wq, wq + wk, causal, variant=variant)
+        assert torch.equal(out, base), f"variant {variant}"
 
 
 @pytest.mark.parametrize("M,D", [(5, 1152), (676, 1152), (3, 4096), (8, 64)])

@@ -68,7 +68,7 @@ for rnd in range(3):
         res[s].append(round(timed(6), 3))
 for s in settings:
     print(json.dumps({"setting": s, "ms_per_step": res[s], "best": min(res[s]), "tokens_per_s": round(S / min(res[s]) * 1e3, 1)}))
-L.lp_model_set_attention_variant(80)
+L.lp_model_set_attention_variant(336)
 L.lp_gemm_set_pair_mode(1)
 L.lp_model_set_fused_norm(1)
 L.lp_gemm_set_streamk(1)

@@ -20,6 +20,9 @@ CASES = {
     "dec_2937_c": (1, 2937, 32, 8, 128, 128, True),
     "dec_4796_c": (1, 4796, 32, 8, 128, 128, True),
     "vit_28": (28, 676, 16, 16, 72, 80, False),
+    "vit_17": (17, 676, 16, 16, 72, 80, False),
+    "vit_5x420": (5, 420, 16, 16, 72, 80, False),
+    "vit_2x1024": (2, 1024, 16, 16, 72, 80, False),
     "vit_4900": (8, 4900, 16, 16, 72, 80, False),      # cfg4: Idefics2 NaViT tower, 8 images of 980 x 980
 }
 
@@ -75,8 +78,8 @@ def run_case(name, variant, do_time):
     nbad = int(bad.sum())
     rec = {"case": name, "variant": variant, "max_err": float(err.max()), "ref_absmax": float(ref.abs().max()),
            "bad": nbad, "ok": nbad == 0 and bool(torch.isfinite(out.float()).all())}
-    if variant & 128:  # the two-stream kernel does v3's arithmetic row by row: results must be bit-identical
-        out3 = ops.attention(qkv, B, T, H, HK, dh, hs, offs[0], offs[1], offs[2], causal, variant=(variant & ~128) | 64 | 16)
+    if variant & (128 | 256):  # the two-stream / persistent kernels do v3's arithmetic row by row: results must be bit-identical
+        out3 = ops.attention(qkv, B, T, H, HK, dh, hs, offs[0], offs[1], offs[2], causal, variant=(variant & ~(128 | 256)) | 64 | 16)
         rec["same_as_v3"] = bool(torch.equal(out, out3))
     if not rec["ok"]:
         eb = err.view(B, T, H, dh)

@@ -245,4 +245,12 @@ r02z() {
   TMO=600 run ops python -m pytest tests/test_gpu_ops.py -x -q
 }
 
+r03a() {
+  # persistent ViT attention (lp_attn5.cu, variant bit 8): parity + bit-equality with v3, timing, whole step
+  T=${TAG:-r03a}
+  TMO=240 run attn5_small python tools/gpu_check_attn.py --variant 336 --case vit_t676 --case vit_5x420 --case vit_2x1024 --case vit_17 --case vit_t128 --case dec_t300_c
+  TMO=300 TAIL=4000 run attn5_time python tools/gpu_check_attn.py --variant 80 --variant 336 --variant 368 --case vit_28 --case vit_17 --case vit_4900 --time
+  TMO=300 run ab_attn5 python tools/gpu_ab_prefill.py attn=80 attn=336
+}
+
 "$@"
