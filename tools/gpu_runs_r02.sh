@@ -253,4 +253,22 @@ r03a() {
   TMO=300 run ab_attn5 python tools/gpu_ab_prefill.py attn=80 attn=336
 }
 
+r03b() {
+  # mid-session validation of the scheduling changes (attention dispatch order, persistent ViT attention, GEMM raster): whole GPU suite,
+  # bench N=1 with the un-profiled stage timings, SFT step (flash backward grids)
+  T=${TAG:-r03b}
+  timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/${T}_pytest_gpu.log; cat gpurun_out/${T}_pytest_gpu.log
+  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err; tail -c 300 gpurun_out/${T}_bench_n1.err
+  python -c "
+import json
+d = json.load(open('gpurun_out/${T}_bench_n1.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
+print(d['stages']['roofline_by_stage'], d['stages'].get('stage_sum_ms'))
+print(d['stages']['roofline_by_stage_kernel_events'])
+print(d['roofline'])
+print(d['decode'])
+"
+  timeout 900 python bench.py --workload cfg5 --steps 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err; tail -c 400 gpurun_out/${T}_bench_cfg5.err; head -c 600 gpurun_out/${T}_bench_cfg5.json
+}
+
 "$@"
