@@ -375,6 +375,12 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             else a3_bar_sync(3, 256);
           }
           A3_TRACE(5);
+          // next half step (the trailing half tile beyond the sequence is skipped by the issuer too); its S barrier is probed here so
+          // that the probe's shared-memory round trip hides under the exponentials
+          int jn = j, hn = 1;
+          if (h == 1 || j * 128 + 64 >= T) { jn = j + 1; hn = 0; }
+          const bool has_next = jn < n_q;
+          const bool s_ready = has_next && mbar_test_wait(&s_full[q * 2 + hn], jn & 1);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t pk[16];
@@ -398,12 +404,8 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             if (q == 0) a3_bar_arrive(3, 256);
             else if (t + 1 < hA) a3_bar_arrive(2, 256);
           }
-          // next half step (the trailing half tile beyond the sequence is skipped by the issuer too)
-          int jn = j, hn = 1;
-          if (h == 1 || j * 128 + 64 >= T) { jn = j + 1; hn = 0; }
-          const bool has_next = jn < n_q;
           bool loaded = false;
-          if (has_next && mbar_test_wait(&s_full[q * 2 + hn], jn & 1)) {
+          if (s_ready || (has_next && mbar_test_wait(&s_full[q * 2 + hn], jn & 1))) {   // second probe: S often lands during the exponentials
             tc_fence_after();
             LP_TMEM_LD_32((v + 0), s_addr + hn * 64 + 0);
             LP_TMEM_LD_32((v + 32), s_addr + hn * 64 + 32);

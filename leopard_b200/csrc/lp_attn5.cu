@@ -324,6 +324,13 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args,
           if (q == 0) { if (t_run0 + t > 0) a5_bar_sync(2, 256); }
           else a5_bar_sync(3, 256);
         }
+        // next half step of the item: its S barrier is probed here (the round trip hides under the exponentials) and its S half goes
+        // into v before P(t) is handed over (see lp_attn3.cu)
+        int jn = j, hn = 1;
+        if (h == 1 || j >= n_hi) { jn = j + 1; hn = 0; }
+        const bool has_next = jn < n_total;
+        const uint32_t next_par = ((hn ? c_hi : c_lo) + jn) & 1;
+        const bool s_ready = has_next && mbar_test_wait(&s_full[q * 2 + hn], next_par);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
@@ -341,13 +348,8 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args,
           if (q == 0) a5_bar_arrive(3, 256);
           else if (t_run0 + t + 1 < total_halves) a5_bar_arrive(2, 256);
         }
-        // next half step of the item: its S half goes into v before P(t) is handed over (see lp_attn3.cu)
-        int jn = j, hn = 1;
-        if (h == 1 || j >= n_hi) { jn = j + 1; hn = 0; }
-        const bool has_next = jn < n_total;
-        const uint32_t next_par = ((hn ? c_hi : c_lo) + jn) & 1;
         bool loaded = false;
-        if (has_next && mbar_test_wait(&s_full[q * 2 + hn], next_par)) {
+        if (s_ready || (has_next && mbar_test_wait(&s_full[q * 2 + hn], next_par))) {   // second probe: S often lands during the exponentials
           tc_fence_after();
           LP_TMEM_LD_32((v + 0), s_addr + hn * 64 + 0);
           LP_TMEM_LD_32((v + 32), s_addr + hn * 64 + 32);

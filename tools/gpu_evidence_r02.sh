@@ -23,8 +23,13 @@ timeout 600 $NCU -k regex:gemm_bf16_res_kernel -s 2 -c 1 -f -o gpurun_out/${T}_g
 timeout 600 $NCU -k regex:gemm_chain_kernel -s 1 -c 1 -f -o gpurun_out/${T}_gemm_chain python tools/gpu_ab_prefill.py chain=1 >> gpurun_out/${T}_prof.log 2>&1
 timeout 600 $NCU -k regex:attn3_fwd -s 2 -c 1 -f -o gpurun_out/${T}_attn3_dec python tools/gpu_check_attn.py --case dec_4796_c --variant 80 --time >> gpurun_out/${T}_prof.log 2>&1
 timeout 600 $NCU -k regex:attn3_fwd -s 2 -c 1 -f -o gpurun_out/${T}_attn3_vit python tools/gpu_check_attn.py --case vit_28 --variant 80 --time >> gpurun_out/${T}_prof.log 2>&1
-for r in gemm_gateup gemm_d_down gemm_v_out gemm_chain attn3_dec attn3_vit; do
+timeout 600 $NCU -k regex:attn5_fwd -s 2 -c 1 -f -o gpurun_out/${T}_attn5_vit python tools/gpu_check_attn.py --case vit_28 --variant 336 --time >> gpurun_out/${T}_prof.log 2>&1
+timeout 600 $NCU -k regex:gemm_bf16_res_kernel -s 2 -c 1 -f -o gpurun_out/${T}_gemm_v_fc2 python tools/gpu_check_gemm.py --pair --time --case v_fc2 >> gpurun_out/${T}_prof.log 2>&1
+timeout 900 python bench.py --workload cfg2 --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${T}_bench_cfg2.json 2> gpurun_out/${T}_bench_cfg2.err
+timeout 900 python bench.py --workload cfg4 --steps 5 --warmup 3 > gpurun_out/${T}_bench_cfg4.json 2> gpurun_out/${T}_bench_cfg4.err
+timeout 900 python bench.py --workload cfg5 --steps 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err
+for r in gemm_gateup gemm_d_down gemm_v_out gemm_v_fc2 gemm_chain attn3_dec attn3_vit attn5_vit; do
   python tools/ncu_summary.py gpurun_out/${T}_$r.ncu-rep > gpurun_out/${T}_$r.txt 2>/dev/null
 done
-rm -f gpurun_out/${T}_gemm_gateup.ncu-rep gpurun_out/${T}_gemm_d_down.ncu-rep gpurun_out/${T}_gemm_chain.ncu-rep   # summaries travel; keep the reports with source pages
+rm -f gpurun_out/${T}_gemm_gateup.ncu-rep gpurun_out/${T}_gemm_d_down.ncu-rep gpurun_out/${T}_gemm_chain.ncu-rep gpurun_out/${T}_gemm_v_fc2.ncu-rep gpurun_out/${T}_attn3_vit.ncu-rep   # summaries travel; keep the reports with source pages
 ls -la gpurun_out/${T}_* | awk '{print $5, $9}'

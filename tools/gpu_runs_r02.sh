@@ -271,4 +271,12 @@ print(d['decode'])
   timeout 900 python bench.py --workload cfg5 --steps 3 > gpurun_out/${T}_bench_cfg5.json 2> gpurun_out/${T}_bench_cfg5.err; tail -c 400 gpurun_out/${T}_bench_cfg5.err; head -c 600 gpurun_out/${T}_bench_cfg5.json
 }
 
+r03c() {
+  # S-barrier probes (before and after the exponentials) in the attention kernels: timing, trace
+  T=${TAG:-r03c}
+  TMO=300 TAIL=3000 run attn_time python tools/gpu_check_attn.py --variant 336 --case dec_2937_c --case dec_4796_c --case vit_28 --case vit_4900 --case dec_t300_c --case vit_t676 --time
+  timeout 60 tools/micro/attn_trace 4796 32 8 128 1 1 4 > gpurun_out/${T}_trace_dec.json 2>&1
+  python tools/micro/attn_trace_report.py gpurun_out/${T}_trace_dec.json > gpurun_out/${T}_trace_report.txt; head -14 gpurun_out/${T}_trace_report.txt
+}
+
 "$@"
