@@ -289,6 +289,32 @@ def test_gemm_ex_rmsnorm_swiglu_and_rope(native_lib):
     assert float((got.float() - ref2.float()).abs().max() / want.abs().max()) < 2e-2
 
 
+def test_gemm_raster_balance_does_not_change_a_bit(native_lib):
+    """lp_gemm_set_raster_balance only changes which persistent unit runs which tile (ViT fc2: W L2-resident, A not, ragged last
+    column block): same bits either way, with and without the residual ring."""
+    from leopard_b200 import _lib
+    L = _lib.lib()
+    assert _lib.ensure_streamk_workspace("cuda:0") is not None
+    M, N, K = 18928, 1152, 4304
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.5
+    r = _bf(torch.randn(M, N, device="cuda", generator=g))
+    outs = []
+    try:
+        for bal in (0, 1):
+            L.lp_gemm_set_raster_balance(bal)
+            x = r.clone()
+            outs.append(ops.gemm_ex(a, w, bias=bias, residual=x, act=0, out=x))
+    finally:
+        L.lp_gemm_set_raster_balance(1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    rows = torch.arange(0, M, 97, device="cuda")
+    _close(outs[1][rows], a[rows].float() @ w.float().t() + bias + r[rows].float(), BF, 1.0)
+
+
 @pytest.mark.parametrize("M,N,K,res,act,stats", [
     (4796, 4096, 4096, True, 0, True),       # decoder o-proj at cfg3: 304 tiles on 74 CTA pairs -> stream-K tail, residual by TMA, row statistics
     (4796, 6144, 4096, False, 0, False),     # qkv: 456 tiles
