@@ -153,6 +153,10 @@ int lp_gemm_set_tma_residual(int enable);
  * equally often; 0 = the earlier groups of ~SMs / column-blocks row blocks (35 of 74 CTA pairs got all the half-width tiles).
  * Scheduling only: results are bit-identical.  Returns the previous setting. */
 int lp_gemm_set_raster_balance(int enable);
+/* Epilogue warps of lp_gemm_bf16(_ex) wait for a whole k loop before their tile is ready; `ns` > 0 makes them sleep that many
+ * nanoseconds between probes of the accumulator-full barrier instead of polling back to back (0 = poll).  Timing only: results
+ * are unaffected.  Returns the previous setting. */
+int lp_gemm_set_epilogue_sleep(int ns);
 
 /* Launch the hot prefill kernels (GEMM, attention v3, norms, RoPE) with programmatic dependent launch: the next kernel's
  * CTAs are scheduled as SMs free up and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the

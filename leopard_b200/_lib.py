@@ -93,6 +93,7 @@ _SIGS = {
     "lp_gemm_set_streamk": (_i, [_i]),
     "lp_gemm_set_tma_residual": (_i, [_i]),
     "lp_gemm_set_raster_balance": (_i, [_i]),
+    "lp_gemm_set_epilogue_sleep": (_i, [_i]),
     "lp_gemm_bf16_tp": (_i, [C.POINTER(GemmDesc), C.POINTER(TpDesc), _vp]),
     "lp_tp_reduce": (_i, [C.POINTER(TpDesc), _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp]),
     "lp_parity_split": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _vp]),

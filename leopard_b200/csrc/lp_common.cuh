@@ -114,6 +114,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait that is expected to be LONG (an epilogue warp waiting for a whole k loop): between probes the warp sleeps `ns` nanoseconds
+// instead of re-issuing the probe back to back, which keeps ~256 polling threads per SM off the issue ports (ns = 0: plain wait).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (ns == 0) { mbar_wait(bar, parity); return; }
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > LP_WATCHDOG_CYCLES) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // cross-CTA / cross-GPU flags in global memory (tensor-parallel fusions: peers are other GPUs over NVLink)
 // ----------------------------------------------------------------------------------------------

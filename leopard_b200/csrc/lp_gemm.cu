@@ -373,7 +373,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       float nbv = 0.f, ncv = 0.f;
       const bool prefetch_cols = it + 1 < sch.n_items;
       if (prefetch_cols) fetch_cols(gemm_item(args, sch, it + 1), nbv, ncv);
-      mbar_wait(&tfull_bar[as], aphase);
+      mbar_wait_relaxed(&tfull_bar[as], aphase, args.epi_sleep_ns);
       tc_fence_after();
       const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
@@ -634,6 +634,7 @@ static int launch_gemm_mn(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 static int g_gemm_tma_residual = 1;  // pair-mode residual launches fetch the residual tile by TMA (0 = register path, for A/B)
+static unsigned g_gemm_epi_sleep_ns = 0;   // lp_gemm_set_epilogue_sleep: nanosleep between probes of the accumulator-full barrier
 static int g_gemm_raster_balance = 1;  // row-major raster when W fits L2 and the last column block is ragged (lp_gemm_set_raster_balance)
 static int g_gemm_pair_mode = 1;  // 0 = one CTA per tile, 1 = CTA pairs where the problem is large enough (default)
 // stream-K tail (GemmArgs::sk_*): caller-provided workspace (flags in the first 4 KiB, fp32 partial accumulators after them)
@@ -722,6 +723,7 @@ extern "C" int lp_gemm_bf16_ex(const lp_gemm_desc* d, void* stream_) {
   args.residual = reinterpret_cast<const bf16*>(residual);
   args.ldr = ldr; args.res_row_mod = res_row_mod;
   args.act = act;
+  args.epi_sleep_ns = g_gemm_epi_sleep_ns;
   args.norm_mode = d->norm_mode;
   args.stats_in = reinterpret_cast<const float2*>(d->stats_in);
   args.stats_in_parts = d->stats_in_parts;
@@ -970,6 +972,11 @@ namespace lp {
 unsigned* gemm_flag_page() { return reinterpret_cast<unsigned*>(g_sk_ws); }
 }  // namespace lp
 
+extern "C" int lp_gemm_set_epilogue_sleep(int ns) {
+  const int old = (int)g_gemm_epi_sleep_ns;
+  g_gemm_epi_sleep_ns = ns < 0 ? 0u : (unsigned)ns;
+  return old;
+}
 extern "C" int lp_gemm_set_raster_balance(int enable) {
   const int old = g_gemm_raster_balance;
   g_gemm_raster_balance = enable ? 1 : 0;

@@ -26,6 +26,7 @@ struct GemmArgs {
   int num_m_blk, num_n_blk, num_k_blk;
   int group_m;
   int prefetch_a;
+  unsigned epi_sleep_ns;         // epilogue warps sleep this long between probes of the accumulator-full barrier (0 = spin)
   // ---- fused row normalisation of the A operand (consumer side; SURVEY.md K2/K5/K9: LayerNorm / RMSNorm folded into the GEMM).
   // The gain is folded into W offline (W' = W diag(gamma)), so norm(x) W^T = rs[row] * (x W'^T - mu[row] * colsum[col]) (+ beta W^T
   // + b, passed as `bias`).  mu / rs come from per-row partial (sum, sum of squares) pairs the PRODUCING GEMM's epilogue wrote.

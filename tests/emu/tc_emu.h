@@ -193,6 +193,8 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return (uint32_t)mbar_at(smem_u32(bar)).phase != parity;
 }
 inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity);
+inline void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   const auto t0 = std::chrono::steady_clock::now();
   while (!mbar_try_wait(bar, parity)) {

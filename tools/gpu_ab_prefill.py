@@ -38,6 +38,8 @@ def apply(setting):
         L.lp_model_set_chained_projector(v)
     elif k == "sk":
         L.lp_gemm_set_streamk(v)
+    elif k == "episleep":
+        L.lp_gemm_set_epilogue_sleep(v)
     elif k == "bal":
         L.lp_gemm_set_raster_balance(v)
     elif k == "tmares":

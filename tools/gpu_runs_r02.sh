@@ -279,4 +279,10 @@ r03c() {
   python tools/micro/attn_trace_report.py gpurun_out/${T}_trace_dec.json > gpurun_out/${T}_trace_report.txt; head -14 gpurun_out/${T}_trace_report.txt
 }
 
+r03f() {
+  # power wall: do the polling epilogue warps cost clock?  nanosleep between probes of the accumulator-full barrier, whole-step A/B
+  T=${TAG:-r03f}
+  TMO=400 run ab_episleep python tools/gpu_ab_prefill.py episleep=0 episleep=200 episleep=1000 episleep=4000
+}
+
 "$@"
