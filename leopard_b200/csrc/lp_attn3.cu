@@ -326,6 +326,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             for (int i = 0; i < 64; ++i)
               if (i >= lim) v[i] = 0xff800000u;  // -inf
           }
+          A3_TRACE(31);
           float mx;
           {
             float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -339,6 +340,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           }
           const float m_new = fmaxf(m_used, mx * args.scale_log2);
+          A3_TRACE(32);
           const bool grow = (m_new - m_used) > 8.0f;
           // pv_done[q][b] completes one phase per P·V half with (index & 1) == b; it is looked at only when O has to be rescaled.
           // Half t - 1 is phase (t - 1) >> 1 of barrier (t - 1) & 1: the phase before it has completed by now (S(t - 1) followed

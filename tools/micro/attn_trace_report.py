@@ -3,7 +3,7 @@ import json
 import sys
 from collections import defaultdict
 
-SM = {(1, 2): "wait S (s_full)", (2, 3): "tcgen05.ld S + wait", (3, 4): "mask / row max / rescale decision", (4, 5): "turn barrier (wait for the other tile's exp)",
+SM = {(1, 2): "wait S (s_full)", (2, 3): "tcgen05.ld S + wait", (3, 4): "mask / row max / rescale decision", (3, 31): "  mask", (31, 32): "  row max (33 x 3-input max) + scale", (32, 4): "  rescale decision (vote) / rescale", (4, 5): "turn barrier (wait for the other tile's exp)",
       (5, 6): "exp section (fma2 / ex2 / add2 / pack / tcgen05.st)", (6, 7): "wait::st + fence", (7, 8): "wait P.V(t-1) + arrive p_full", (8, 1): "loop overhead"}
 for path in sys.argv[1:]:
     d = json.load(open(path))
