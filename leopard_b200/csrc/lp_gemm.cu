@@ -41,6 +41,29 @@ namespace lp {
 // 8 KiB slabs, the UMMA descriptor walks them with LBO = slab stride, a K = 16 step advances 16 rows = 2 KiB.  This is what the SFT
 // step's dgrad (dX = dY W: W is "Wt") and wgrad (dW = dY^T X: both operands) need; no transposed copies are materialised.
 // Tile width BN = 256 columns; a ragged last column block runs the full-width MMA on zero-filled columns.
+// Phase trace (tools/micro/gemm_trace.cu compiles this file with -DLP_GEMM_TRACE): lane 0 of the MMA warp and of the first epilogue
+// warp of each warpgroup of ONE chosen CTA stamp clock64() at the points below; no code in normal builds.
+#ifdef LP_GEMM_TRACE
+__device__ unsigned long long* g_gemm_trace = nullptr;   // [3 slots][4096]: slot 0 = MMA issuer, 1 / 2 = epilogue warp 2 / 6
+__device__ int g_gemm_trace_blk = 0;
+#define G_TRACE_INIT()                                                                                                  \
+  unsigned long long* tr_buf = nullptr;                                                                                 \
+  int tr_n = 0;                                                                                                         \
+  if ((int)blockIdx.x == g_gemm_trace_blk && lane == 0 && g_gemm_trace != nullptr && (warp == 1 || warp == 2 || warp == 6)) \
+    tr_buf = g_gemm_trace + (warp == 1 ? 0 : warp == 2 ? 1 : 2) * 4096
+#define G_TRACE(id)                                                                                                     \
+  do {                                                                                                                  \
+    if (tr_buf != nullptr && tr_n < 4094) {                                                                             \
+      tr_buf[1 + tr_n] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xffffffffffffULL);        \
+      ++tr_n;                                                                                                           \
+      tr_buf[0] = (unsigned long long)tr_n;                                                                             \
+    }                                                                                                                   \
+  } while (0)
+#else
+#define G_TRACE_INIT() do {} while (0)
+#define G_TRACE(id) do {} while (0)
+#endif
+
 template <int BN, int STAGES, bool CTA2, bool TP, int RES, bool A_MN = false, bool B_MN = false>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                           const CUtensorMap* segC, const CUtensorMap& tmR, const GemmArgs& args) {
@@ -65,6 +88,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  G_TRACE_INIT();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -167,7 +191,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         // the last column block of a ragged N issues narrower MMAs (N = valid columns rounded up to 32)
         const uint32_t idesc = umma_idesc_bf16(BMT, (A_MN || B_MN) ? BN : min(BN, ((args.N - n_blk * BN) + 31) & ~31), A_MN ? 1 : 0,
                                                B_MN ? 1 : 0);
+        G_TRACE(20);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
+        G_TRACE(21);
         const bool resume = w.kind == GEMM_ITEM_END;   // the accumulator continues another unit's partial sums
         if (resume) mbar_wait(tpre_bar, 0);
         tc_fence_after();
@@ -191,6 +217,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
         // accumulator complete -> epilogue (of both CTAs)
         if (CTA2) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
+        G_TRACE(22);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -373,7 +400,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       float nbv = 0.f, ncv = 0.f;
       const bool prefetch_cols = it + 1 < sch.n_items;
       if (prefetch_cols) fetch_cols(gemm_item(args, sch, it + 1), nbv, ncv);
+      G_TRACE(30);
       mbar_wait_relaxed(&tfull_bar[as], aphase, args.epi_sleep_ns);
+      G_TRACE(31);
       tc_fence_after();
       const int rrow = args.res_row_mod > 0 ? row % args.res_row_mod : row;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
@@ -423,16 +452,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
               tma_store_wait_read<1>();
               if (c + 1 < c_end && col0 + 32 < args.N) res_issue(g + 1, col0 + 32);
             }
+            G_TRACE(35);
             uint32_t r[32];
             LP_TMEM_LD_32(r, taddr0 + c * 32);
             tmem_wait_ld();
+            G_TRACE(32);
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             apply_row_norm(args, v, cs + c * 32, rs, nmu);
             apply_bias_act(args, v, bs + c * 32);
+            G_TRACE(33);
             mbar_wait(&rbar[g % 3], (g / 3) & 1);
+            G_TRACE(36);
             ring_add_store_chunk(tmc, ring + (g % 3) * 2048, v, row_base, col0, lane, ostat_p);
+            G_TRACE(34);
             ++done;
           }
           rg += done;
@@ -447,6 +481,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           uint32_t r[32];
           LP_TMEM_LD_32(r, taddr0 + c * 32);
           tmem_wait_ld();
+          G_TRACE(32);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -458,7 +493,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             ResidualRegs cur = rr;
             if (has_res && c + 1 < c_end && col0 + 32 < args.N)  // prefetch the next chunk's residual
               residual_fetch(args, rr, row_base, col0 + 32, args.N, lane);
+            G_TRACE(33);
             staged_store_chunk(args, tmc, stage, v, has_res ? &cur : nullptr, row_base - st_shift, col0, lane, ostat_p);
+            G_TRACE(34);
           }
         }
         }
@@ -495,6 +532,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         bias_smem[(as ^ 1) * BN + et] = nbv;
         colsum_smem[(as ^ 1) * BN + et] = ncv;
       }
+      G_TRACE(37);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
