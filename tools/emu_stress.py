@@ -3,6 +3,9 @@
 shapes until the time budget is spent.  Scheduling noise of the OS threads varies from run to run, which is the point: a protocol
 race shows up as a mismatch or as the emulator's deadlock abort.
     python tools/emu_stress.py [--seconds 300] [--which attn,gemm4] [--seed 1]
+`--which fwd` adds the forward attention kernels whose scheduling changed last (lp_attn3.cu: next S half loaded before the hand-over,
+alternating pv_done barriers; lp_attn5.cu: persistent CTAs, barrier parities running across items) — 765 random cases in 600 s
+passed before the round closed.
 """
 import argparse
 import ctypes as C
@@ -118,6 +121,57 @@ def gemm4_case(L, n):
     return (e > 8e-3 or bool(torch.isnan(out.float()).any())), f"M{M} N{N} K{K} bn{bn} act{act} bias={bias} res={res} fp32={fp32} ctas={ctas}: {e:.2e}"
 
 
+def build_fwd(out):
+    """lp_attn3.cu / lp_attn5.cu kernel templates under the emulator (same cuts as tests/test_attention_kernels_emulated.py)."""
+    _helpers(out, "// UMMA descriptors")
+    host = (ROOT / "leopard_b200/csrc/lp_host.h").read_text()
+    (out / "attn_args.inc").write_text(re.search(r"struct AttnArgs \{.*?\n\};", host, re.S).group(0) + "\n")
+    src = (ROOT / "leopard_b200/csrc/lp_attn5.cu").read_text()
+    (out / "attn5_kernel.inc").write_text(src[src.index("// ---- kernel code"):src.index("// ---- host side")])
+    src = (ROOT / "leopard_b200/csrc/lp_attn3.cu").read_text()
+    (out / "attn3_kernel.inc").write_text(src[src.index("template <int DH, bool CAUSAL, int EMU>\n__global__"):
+                                              src.index("template <int DH, bool CAUSAL, int EMU>\nstatic int launch3(")])
+    return (_gxx(out, "attn5_fwd_emu.cpp", "liba5.so"), _gxx(out, "attn3_fwd_emu.cpp", "liba3.so"))
+
+
+def fwd_case(libs, n):
+    """60 % persistent-kernel cases (eligible T, 1..7 CTAs over B x heads x pairs items), 40 % v3 cases (causal GQA / full / tower layout)."""
+    l5, l3 = libs
+    if random.random() < 0.6:
+        while True:
+            T = random.randint(256, 1100)
+            if T % 256 == 0 or T % 256 > 128:
+                break
+        B, heads, grid, ping = random.randint(1, 3), random.randint(1, 3), random.randint(1, 7), random.randint(0, 1)
+        hd, hs, causal, kvh = 72, 80, False, heads
+    else:
+        T, B, causal, grid, ping = random.randint(1, 700), random.randint(1, 2), random.random() < 0.6, 0, random.randint(0, 1)
+        if random.random() < 0.4:
+            hd, hs, heads, causal = 72, 80, random.randint(1, 2), False
+            kvh = heads
+        else:
+            hd, hs, kvh = 128, 128, random.choice([1, 2])
+            heads = kvh * random.choice([1, 2, 4])
+    g = torch.Generator().manual_seed(random.randint(0, 1 << 30))
+    q_w, kv_w = heads * hs, kvh * hs
+    qkv = torch.randn((B * T, q_w + 2 * kv_w), generator=g).to(BF)
+    if hs != hd:
+        v = qkv.view(B * T, heads + 2 * kvh, hs)
+        v[:, :, hd:] = 0
+        qkv = v.reshape(B * T, -1).contiguous()
+    want = ref.attention(qkv, B, T, heads, kvh, hd, hs, 0, q_w, q_w + kv_w, causal)
+    got = torch.full((B * T, heads * hd), float("nan")).to(BF)
+    if grid:
+        l5.emu_attention5_fwd(P(qkv), LL(qkv.stride(0)), B, T, heads, kvh, hd, hs, 0, q_w, q_w + kv_w, 0, C.c_float(hd ** -0.5), P(got),
+                              LL(got.stride(0)), ping, grid)
+    else:
+        l3.emu_attention3_fwd(P(qkv), LL(qkv.stride(0)), B, T, heads, kvh, hd, hs, 0, q_w, q_w + kv_w, int(causal), C.c_float(hd ** -0.5),
+                              P(got), LL(got.stride(0)), ping)
+    d = (got.float() - want.float()).abs()
+    bad = bool(torch.isnan(got.float()).any()) or int((d > 2e-2 * want.float().abs().clamp(min=0.5)).sum()) > 0
+    return bad, f"{'v5' if grid else 'v3'} B={B} T={T} heads={heads}/{kvh} dh={hd} causal={causal} ping={ping} grid={grid} max_err={float(d.max()):.4f}"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=int, default=300)
@@ -135,6 +189,9 @@ def main():
         if "gemm4" in which:
             (out / "g").mkdir()
             jobs.append(("gemm4", build_gemm(out / "g"), gemm4_case))
+        if "fwd" in which:
+            (out / "f").mkdir()
+            jobs.append(("fwd", build_fwd(out / "f"), fwd_case))
         for name, lib, fn in jobs:
             t0, n, bad = time.time(), 0, 0
             while time.time() - t0 < a.seconds / len(jobs):
