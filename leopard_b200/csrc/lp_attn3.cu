@@ -18,7 +18,10 @@
 // TMEM map (512 columns): S_A.lo [0,64) S_A.hi [64,128) S_B.lo [128,192) S_B.hi [192,256) O_A [256,384) O_B [384,512).
 // Ordering facts relied upon: tcgen05.mma ops issued by ONE thread execute in issue order (P·V(j).h is issued before
 // S(j+1).h, so the new S cannot overwrite P early), and tcgen05.commit covers all MMAs previously issued by that
-// thread.  O_q is rescaled in place only after pv_done_q shows that every P·V issued so far has retired.
+// thread.  O_q is rescaled in place only after pv_done_q shows that every P·V issued so far has retired (a pair of alternating
+// barriers per tile, looked at only on that path).  The S half of step t + 1 is loaded into the registers of step t's S before
+// P(t) is handed over (its barrier is probed before and after the exponentials).  Grid = (heads, query-tile pairs, batch), pairs
+// descending: heaviest causal pairs first over the WHOLE grid (see the kernel body; found with the phase trace, A3_TRACE below).
 // A trailing half tile that lies entirely beyond T (T = 676: keys 704..767) is skipped by issuer and softmax alike.
 #include "lp_common.cuh"
 #include "lp_host.h"

@@ -1,7 +1,7 @@
 // leopard_b200 — flash attention v4: the v3 kernel (lp_attn3.cu: two 128-row query tiles per CTA, S delivered in 64-key halves with
 // their own TMEM columns, one MMA-issuing thread per query tile, lazy O rescale) with ONE softmax warpgroup for both tiles: thread
 // r owns row r of tile A and row r of tile B and runs their exponentials as two independent streams in the same instruction
-// window.  Same contract as attn4_fwd_kernel (SigLIP non-causal 16x72 with DH = 80 padded, decoder causal GQA 32/8x128; replaces
+// window.  Same contract as attn3_fwd_kernel (SigLIP non-causal 16x72 with DH = 80 padded, decoder causal GQA 32/8x128; replaces
 // flash_attn_varlen_func at MP/model/llava/transformer.py:476-515,869-877 and TEDotProductAttention at clip_encoder.py:58-63).
 //
 // Why (tools/micro/mufu_bench.cu, profiles/r02t_mufu_bench.jsonl): the softmax stream of one query tile (fma2 -> 2 x ex2 -> add2 ->
@@ -15,6 +15,10 @@
 //   warp 3      TMEM allocation
 //   warps 4-7   softmax of BOTH tiles: one thread per row pair
 // Causal pairs: tile A has one key tile fewer than tile B; the steps where only one tile is active run the single-stream body.
+// RESULT (profiles/r02v_attn4_time.log): bit-identical to v3 but 23-30 % SLOWER (decoder S = 4796: 693 vs 905 TFLOP/s) — with one warp
+// per sub-partition nothing hides the barrier / TMEM round trips between the exp sections (the phase trace of v3 later showed
+// that those, not the exponentials, are most of a half step).  Kept as variant bit 7 (128) for A/B and as the cross-check that
+// pinned v3's arithmetic while v3 itself was being restructured.
 #include "lp_common.cuh"
 #include "lp_host.h"
 #include "../../include/leopard_b200.h"
