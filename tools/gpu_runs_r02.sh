@@ -285,4 +285,59 @@ r03f() {
   TMO=400 run ab_episleep python tools/gpu_ab_prefill.py episleep=0 episleep=200 episleep=1000 episleep=4000
 }
 
+r03e() {
+  # N = 2 bench line on the last code (gpurun --gpus 2)
+  mkdir -p gpurun_out
+  T=r03e
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+  timeout 900 $TR --master-port 29541 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/${T}_bench_n2.log 2>&1
+  grep '"metric"' gpurun_out/${T}_bench_n2.log > gpurun_out/${T}_bench_n2.json
+  python -c "
+  import json
+  d=json.load(open('gpurun_out/r03e_bench_n2.json'))
+  print(d['value'], d['ms_per_step'], d['e2e']['value'], d['dp'], d['strong']['ms_per_step'] if d.get('strong') else None)
+  "
+}
+
+r03h() {
+  # last check of the round on the final tree: whole GPU suite + smoke (no bench: profiles/r03d_* holds the evidence run)
+  mkdir -p gpurun_out
+  T=${TAG:-r03h}
+  timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 > gpurun_out/${T}_pytest_gpu.log; cat gpurun_out/${T}_pytest_gpu.log
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -1 gpurun_out/${T}_smoke.log
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err
+  python -c "
+  import json
+  d = json.load(open('gpurun_out/${T}_bench_n1.json'))
+  print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'], d['stages']['roofline_by_stage'])
+  "
+}
+
+r03j() {
+  # compute-sanitizer memcheck over the kernels touched in the last session: persistent ViT attention (variant 336), v3 with the new grid
+  # order / early S load, v4, and the GEMM with the balanced raster (ops tests run the fc2 shape)
+  mkdir -p gpurun_out
+  T=${TAG:-r03j}
+  timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python tools/gpu_check_attn.py --variant 336 --variant 128 \
+      --case vit_t676 --case vit_5x420 --case dec_t300_c --case dec_t256 > gpurun_out/${T}_memcheck_attn.txt 2>&1
+  tail -6 gpurun_out/${T}_memcheck_attn.txt
+  timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_ops.py -q -x -k "raster_balance or scheduling_variants" > gpurun_out/${T}_memcheck_ops.txt 2>&1
+  tail -6 gpurun_out/${T}_memcheck_ops.txt
+}
+
+r03k() {
+  # N = 8 bench line on the last code (gpurun --gpus 8)
+  mkdir -p gpurun_out
+  T=r03k
+  N=${NGPU:-8}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  timeout 900 $TR --master-port 29541 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/${T}_bench_n$N.log 2>&1
+  grep '"metric"' gpurun_out/${T}_bench_n$N.log > gpurun_out/${T}_bench_n$N.json
+  python -c "
+  import json
+  d=json.load(open('gpurun_out/${T}_bench_n$N.json'))
+  print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['dp'], d['strong']['ms_per_step'] if d.get('strong') else None, d['clocks'])
+  "
+}
+
 "$@"
